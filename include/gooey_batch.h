@@ -1,0 +1,81 @@
+/* gooey_batch.h — additive batch entry points of libgooey_b200.so.
+ *
+ * libgooey renders one engine / one voice per call, sample by sample, on one
+ * CPU thread.  These entry points render THOUSANDS of independent voices or
+ * engines in one call on an NVIDIA B200.  They sit beside (not instead of) the
+ * reference's own C FFI (include/gooey.h): single-engine render/bounce keep
+ * working as a batch of one.
+ *
+ * Plain C ABI: pointers and sizes only.  Every function returns 0 on success
+ * and a negative GOOEY_E_* code on failure; gooey_b200_last_error() returns a
+ * thread-local description.  There is NO CPU fallback: without a CUDA device
+ * every compute entry fails with GOOEY_E_NO_DEVICE.
+ */
+#ifndef GOOEY_BATCH_H
+#define GOOEY_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOOEY_E_OK 0
+#define GOOEY_E_INVALID (-1)
+#define GOOEY_E_NO_DEVICE (-2)
+#define GOOEY_E_CUDA (-3)
+
+/* Instrument ids (reference: src/ffi.rs:1843-1853). */
+#define GOOEY_INSTRUMENT_KICK 0u
+#define GOOEY_INSTRUMENT_SNARE 1u
+#define GOOEY_INSTRUMENT_HIHAT 2u
+#define GOOEY_INSTRUMENT_TOM 3u
+#define GOOEY_INSTRUMENT_BASS 4u
+
+/* One voice patch = the argument list of the reference's `<Voice>::with_config`
+ * (Rust API, instrument level):
+ *   kick  : KickConfig::new_full order, 18 normalized values (src/instruments/kick.rs:118-160)
+ *   snare : SnareConfig::new_full order, 19 values, filter_type at [13] (src/instruments/snare.rs:135-180)
+ *   hihat : pitch, decay, attack, tone, volume; aux bit0 = pink noise, bit1 = 12 dB slope
+ *           (HiHat2Config, src/instruments/hihat2.rs:41-70; default white / 24 dB)
+ *   tom   : tune, bend, tone, color, decay, membrane, membrane_q, volume in 0-100 units
+ *           (Tom2Config, src/instruments/tom2.rs:105-115); aux bit0 = 1 to apply it, 0 = Tom2::new defaults
+ *   bass  : BassConfig order, 15 normalized values (src/instruments/bass.rs)
+ * `tuning` (0.5 neutral) is params[23] when aux bit8 is set.
+ */
+typedef struct GooeyVoicePatch {
+  uint32_t instrument;
+  uint32_t aux;
+  float params[24];
+} GooeyVoicePatch;
+
+typedef struct GooeyVoiceBatch GooeyVoiceBatch;
+
+const char* gooey_b200_last_error(void);
+/* Number of visible CUDA devices (0 = the library cannot compute). */
+int gooey_b200_device_count(void);
+/* Kernels launched by this process since load (bench.py reports it as gpu_launches). */
+uint64_t gooey_b200_launch_count(void);
+/* Device time (ms, CUDA events on the launching stream) of the most recent render call's kernels. */
+float gooey_b200_last_kernel_ms(void);
+
+/* Voice-level batch: n voices built `with_config`, then driven by per-voice events. */
+int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoicePatch* patches, int device,
+                          GooeyVoiceBatch** out_batch);
+void gooey_voice_batch_free(GooeyVoiceBatch* b);
+/* `voice.trigger_with_velocity(t_frame, velocity)` at frame `frame` (frames count from the batch's current position). */
+int gooey_voice_batch_trigger(GooeyVoiceBatch* b, uint32_t voice, uint32_t frame, float velocity);
+/* Same trigger for every voice; velocities may be NULL (=1.0). */
+int gooey_voice_batch_trigger_all(GooeyVoiceBatch* b, uint32_t frame, const float* velocities);
+/* FFI-style normalized parameter edit (`gooey_engine_set_*_param` ids) taking effect at `frame`; snap != 0 also snaps. */
+int gooey_voice_batch_set_param(GooeyVoiceBatch* b, uint32_t voice, uint32_t frame, uint32_t param, float value, int snap);
+/* Render `frames` samples of every voice: out_host[v * frames + i] (host memory; copies are part of the call). */
+int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_host);
+/* Same, leaving the result in device memory: out_dev[v * stride + i], stride >= frames. */
+int gooey_voice_batch_render_device(GooeyVoiceBatch* b, uint32_t frames, float* out_dev, size_t stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOOEY_BATCH_H */

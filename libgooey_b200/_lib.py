@@ -1,0 +1,54 @@
+"""ctypes binding of libgooey_b200.so (the C ABI in include/gooey_batch.h and include/gooey.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` into
+``libgooey_b200/lib/``.  There is no CPU fallback: if the library is missing the
+import of any compute entry raises, and on a box without a CUDA device every
+compute call returns GOOEY_E_NO_DEVICE which is raised as ``GooeyError``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgooey_b200.so")
+
+
+class GooeyError(RuntimeError):
+    pass
+
+
+class VoicePatch(ctypes.Structure):
+    """GooeyVoicePatch (include/gooey_batch.h)."""
+    _fields_ = [("instrument", ctypes.c_uint32), ("aux", ctypes.c_uint32), ("params", ctypes.c_float * 24)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GooeyError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). libgooey_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        c = ctypes
+        L.gooey_b200_last_error.restype = c.c_char_p
+        L.gooey_b200_device_count.restype = c.c_int
+        L.gooey_b200_launch_count.restype = c.c_uint64
+        L.gooey_b200_last_kernel_ms.restype = c.c_float
+        L.gooey_voice_batch_new.argtypes = [c.c_float, c.c_uint32, c.POINTER(VoicePatch), c.c_int, c.POINTER(c.c_void_p)]
+        L.gooey_voice_batch_free.argtypes = [c.c_void_p]
+        L.gooey_voice_batch_free.restype = None
+        L.gooey_voice_batch_trigger.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]
+        L.gooey_voice_batch_trigger_all.argtypes = [c.c_void_p, c.c_uint32, c.POINTER(c.c_float)]
+        L.gooey_voice_batch_set_param.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_uint32, c.c_float, c.c_int]
+        L.gooey_voice_batch_render.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p]
+        L.gooey_voice_batch_render_device.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_size_t]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GooeyError(f"libgooey_b200 error {rc}: {lib().gooey_b200_last_error().decode(errors='replace')}")
