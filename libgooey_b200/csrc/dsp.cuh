@@ -114,7 +114,7 @@ G_HD float max_curve_pos(float progress, float curve) {  // curve > 0 branch of 
   float hp = gm::g_powf((fabsf(curve) + 1e-20f) * 1.2f, 0.41f) * 0.91f;
   float fp = hp / (1.0f - hp);
   if (fabsf(fp) < 1e-6f) return progress;
-  return expm1f(fp * progress) / expm1f(fp);
+  return gm::g_expm1f(fp * progress) / gm::g_expm1f(fp);
 }
 G_HD float max_curve(float progress, float curve) {
   progress = clampf(progress, 0.0f, 1.0f);
@@ -250,7 +250,7 @@ struct Tpt { float cutoff, res, g, r, h, ic1, ic2; };
 G_HD void tpt_update(Tpt& f, float sr) {  // state_variable_tpt.rs:42-53
   float cutoff = clampf(f.cutoff, 20.0f, sr * 0.45f);
   float q = fmaxf(f.res, 0.5f);
-  float g = tanf(PI_F * cutoff / sr);
+  float g = gm::g_tanf(PI_F * cutoff / sr);
   float r = 1.0f / q;
   f.g = g; f.r = r; f.h = 1.0f / (1.0f + r * g + g * g);
 }
@@ -277,7 +277,7 @@ G_HD void rlp_update(Tpt& f, float sr) {
   float s = fmaxf(sr, 1.0f);
   float cutoff = clampf(f.cutoff, 20.0f, s * 0.45f);
   float q = clampf(f.res, 0.5f, 10.0f);
-  f.g = tanf(PI_F * cutoff / s);
+  f.g = gm::g_tanf(PI_F * cutoff / s);
   f.r = 1.0f / q;
   f.h = 1.0f / (1.0f + f.r * f.g + f.g * f.g);
 }
@@ -406,8 +406,8 @@ G_D float ws_process(WShaper& w, float in) {
   if (!isfinite(in)) { os_reset(w.os); return 0.0f; }
   if (w.mix <= 0.0001f || w.drive <= 1.0f) return in;
   float d = w.drive;
-  float comp = tanhf(0.5f) / tanhf(0.5f * d);
-  float sat = os_process(w.os, in, [&](float x) { return tanhf(x * d) * comp; });
+  float comp = gm::g_tanhf(0.5f) / gm::g_tanhf(0.5f * d);
+  float sat = os_process(w.os, in, [&](float x) { return gm::g_tanhf(x * d) * comp; });
   return in * (1.0f - w.mix) + sat * w.mix;
 }
 
@@ -434,8 +434,8 @@ G_HD void fbws_set_cutoff(FbShaper& w, float sr, float c) {
 }
 G_D float fbws_gain_comp(float env, float drive, float feedback) {  // :247-259
   float reference = fmaxf(env, 0.05f);
-  float driven = fmaxf(fabsf(tanhf(reference * drive)), 1e-6f);
-  float comp_no_fb = tanhf(reference) / driven;
+  float driven = fmaxf(fabsf(gm::g_tanhf(reference * drive)), 1e-6f);
+  float comp_no_fb = gm::g_tanhf(reference) / driven;
   float drive_norm = clampf((drive - 1.0f) / 99.0f, 0.0f, 1.0f);
   float fb_norm = clampf(feedback / 0.98f, 0.0f, 1.0f);
   float high_end = gm::g_powf(drive_norm, 1.35f) * gm::g_powf(fb_norm, 2.0f);
@@ -447,7 +447,7 @@ G_D float fbws_process(FbShaper& w, float in) {  // :109-169
   if (!isfinite(in)) { fbws_reset(w); return 0.0f; }
   if (w.mix <= 0.0001f || w.drive <= 1.0f) return in;
   float fb_in = w.drive * in + w.feedback * w.last_out;
-  float shaped = os_process(w.os, fb_in, [](float x) { return tanhf(x); });
+  float shaped = os_process(w.os, fb_in, [](float x) { return gm::g_tanhf(x); });
   float rect = fabsf(in);
   float coeff = rect > w.env ? w.env_att : w.env_rel;
   w.env += (1.0f - coeff) * (rect - w.env);

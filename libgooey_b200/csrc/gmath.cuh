@@ -315,4 +315,159 @@ GM_HD float g_cosf(float y) {
   return NAN;
 }
 
+
+// ------------------------------------------------- expm1f / tanhf / tanf ----
+// glibc 2.39 still uses the fdlibm single-precision routines for these
+// (sysdeps/ieee754/flt-32/{s_expm1f,s_tanhf,s_tanf,k_tanf,e_rem_pio2f}.c): plain f32
+// arithmetic, no FMA variant.  Restated operation-for-operation; every product/sum
+// below must stay unfused (-fmad=false on the device, -ffp-contract=off on the host).
+GM_HD float g_expm1f(float x) {
+  const float one = 1.0f, huge = 1.0e+30f, tiny = 1.0e-30f;
+  const float o_threshold = 8.8721679688e+01f, ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f, invln2 = 1.4426950216e+00f;
+  const float Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f, Q3 = -7.9365076090e-05f, Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
+  float y, hi, lo, c = 0.0f, t, e, hxs, hfx, r1;
+  int32_t k;
+  uint32_t hx = asuint(x);
+  uint32_t xsb = hx & 0x80000000u;
+  hx &= 0x7fffffffu;
+  if (hx >= 0x4195b844u) {            // |x| >= 27 ln2
+    if (hx >= 0x42b17218u) {          // |x| >= 88.72
+      if (hx > 0x7f800000u) return x + x;
+      if (hx == 0x7f800000u) return xsb == 0 ? x : -1.0f;
+      if (x > o_threshold) return huge * huge;
+    }
+    if (xsb != 0) return tiny - one;
+  }
+  if (hx > 0x3eb17218u) {             // |x| > 0.5 ln2
+    if (hx < 0x3F851592u) {           // |x| < 1.5 ln2
+      if (xsb == 0) { hi = x - ln2_hi; lo = ln2_lo; k = 1; }
+      else { hi = x + ln2_hi; lo = -ln2_lo; k = -1; }
+    } else {
+      k = (int32_t)(invln2 * x + (xsb == 0 ? 0.5f : -0.5f));
+      t = (float)k;
+      hi = x - t * ln2_hi;
+      lo = t * ln2_lo;
+    }
+    x = hi - lo;
+    c = (hi - x) - lo;
+  } else if (hx < 0x33000000u) {      // |x| < 2^-25
+    t = huge + x;
+    return x - (t - (huge + x));
+  } else k = 0;
+  hfx = 0.5f * x;
+  hxs = x * hfx;
+  r1 = one + hxs * (Q1 + hxs * (Q2 + hxs * (Q3 + hxs * (Q4 + hxs * Q5))));
+  t = 3.0f - r1 * hfx;
+  e = hxs * ((r1 - t) / (6.0f - x * t));
+  if (k == 0) return x - (x * e - hxs);
+  e = (x * (e - c) - c);
+  e -= hxs;
+  if (k == -1) return 0.5f * (x - e) - 0.5f;
+  if (k == 1) {
+    if (x < -0.25f) return -2.0f * (e - (x + 0.5f));
+    return one + 2.0f * (x - e);
+  }
+  if (k <= -2 || k > 56) {
+    y = one - (e - x);
+    y = asfloat(asuint(y) + ((uint32_t)k << 23));
+    return y - one;
+  }
+  if (k < 23) {
+    t = asfloat(0x3f800000u - (0x1000000u >> k));
+    y = t - (e - x);
+    y = asfloat(asuint(y) + ((uint32_t)k << 23));
+  } else {
+    t = asfloat((uint32_t)(0x7f - k) << 23);
+    y = x - (e + t);
+    y += one;
+    y = asfloat(asuint(y) + ((uint32_t)k << 23));
+  }
+  return y;
+}
+
+GM_HD float g_tanhf(float x) {
+  const float one = 1.0f, two = 2.0f, tiny = 1.0e-30f;
+  float t, z;
+  int32_t jx = (int32_t)asuint(x);
+  int32_t ix = jx & 0x7fffffff;
+  if (ix >= 0x7f800000) return jx >= 0 ? one / x + one : one / x - one;
+  if (ix < 0x41b00000) {              // |x| < 22
+    if (ix == 0) return x;
+    if (ix < 0x24000000) return x * (one + x);
+    if (ix >= 0x3f800000) { t = g_expm1f(two * fabsf(x)); z = one - two / (t + two); }
+    else { t = g_expm1f(-two * fabsf(x)); z = -t / (t + two); }
+  } else z = one - tiny;
+  return jx >= 0 ? z : -z;
+}
+
+GM_HD float g_kernel_tanf(float x, float y, int iy) {
+  const float one = 1.0f, pio4 = 7.8539812565e-01f, pio4lo = 3.7748947079e-08f;
+  const float T0 = 3.3333334327e-01f, T1 = 1.3333334029e-01f, T2 = 5.3968254477e-02f, T3 = 2.1869488060e-02f,
+              T4 = 8.8632395491e-03f, T5 = 3.5920790397e-03f, T6 = 1.4562094584e-03f, T7 = 5.8804126456e-04f,
+              T8 = 2.4646313977e-04f, T9 = 7.8179444245e-05f, T10 = 7.1407252108e-05f, T11 = -1.8558637748e-05f,
+              T12 = 2.5907305826e-05f;
+  float z, r, v, w, s;
+  int32_t hx = (int32_t)asuint(x);
+  int32_t ix = hx & 0x7fffffff;
+  if (ix < 0x39000000) {              // |x| < 2^-13
+    if ((int)x == 0) {
+      if ((ix | (iy + 1)) == 0) return one / fabsf(x);
+      else if (iy == 1) return x;
+      else return -one / x;
+    }
+  }
+  if (ix >= 0x3f2ca140) {             // |x| >= 0.6744
+    if (hx < 0) { x = -x; y = -y; }
+    z = pio4 - x;
+    w = pio4lo - y;
+    x = z + w; y = 0.0f;
+    if (fabsf(x) < 0x1p-13f) return (float)((1 - ((hx >> 30) & 2)) * iy) * (1.0f - (float)(2 * iy) * x);
+  }
+  z = x * x;
+  w = z * z;
+  r = T1 + w * (T3 + w * (T5 + w * (T7 + w * (T9 + w * T11))));
+  v = z * (T2 + w * (T4 + w * (T6 + w * (T8 + w * (T10 + w * T12)))));
+  s = z * x;
+  r = y + z * (s * (r + v) + y);
+  r += T0 * s;
+  w = x + r;
+  if (ix >= 0x3f2ca140) {
+    v = (float)iy;
+    return (float)(1 - ((hx >> 30) & 2)) * (v - 2.0f * (x - (w * w / (w + v) - r)));
+  }
+  if (iy == 1) return w;
+  float a, t;
+  z = asfloat(asuint(w) & 0xfffff000u);
+  v = r - (z - x);
+  t = a = -1.0f / w;
+  t = asfloat(asuint(t) & 0xfffff000u);
+  s = 1.0f + t * z;
+  return t + a * (s + t * v);
+}
+
+// tanf for |x| <= 3pi/4 through the fdlibm small-argument reduction (e_rem_pio2f.c first branch); larger
+// arguments never occur on this path (filter prewarp arguments are <= 0.45*pi) and fall back to NaN-safe tan.
+GM_HD float g_tanf(float x) {
+  const float pio2_1 = 1.5707855225e+00f, pio2_1t = 1.0804334124e-05f, pio2_2 = 1.0804273188e-05f, pio2_2t = 6.0770999344e-11f;
+  int32_t hx = (int32_t)asuint(x);
+  int32_t ix = hx & 0x7fffffff;
+  if (ix <= 0x3f490fda) return g_kernel_tanf(x, 0.0f, 1);
+  if (ix >= 0x7f800000) return x - x;
+  if (ix <= 0x4016cbe3) {             // |x| ~< 3pi/4
+    float z, y0, y1;
+    if (hx > 0) {
+      z = x - pio2_1;
+      if ((ix & 0xfffffff0) != 0x3fc90fd0) { y0 = z - pio2_1t; y1 = (z - y0) - pio2_1t; }
+      else { z -= pio2_2; y0 = z - pio2_2t; y1 = (z - y0) - pio2_2t; }
+      return g_kernel_tanf(y0, y1, -1);
+    } else {
+      z = x + pio2_1;
+      if ((ix & 0xfffffff0) != 0x3fc90fd0) { y0 = z + pio2_1t; y1 = (z - y0) + pio2_1t; }
+      else { z += pio2_2; y0 = z + pio2_2t; y1 = (z - y0) + pio2_2t; }
+      return g_kernel_tanf(y0, y1, -1);
+    }
+  }
+  return tanf(x);
+}
+
 }  // namespace gm

@@ -326,8 +326,9 @@ __global__ void math_selftest_kernel(int kind, const float* x, const float* y, f
     case 3: r = gm::g_expf(x[i]); break;
     case 4: r = gd::hash_noise((uint64_t)x[i]); break;
     case 5: r = gd::max_curve(x[i], y[i]); break;
-    case 6: r = tanhf(x[i]); break;
-    case 7: r = tanf(x[i]); break;
+    case 6: r = gm::g_tanhf(x[i]); break;
+    case 7: r = gm::g_tanf(x[i]); break;
+    case 8: r = gm::g_expm1f(x[i]); break;
     default: r = 0.0f;
   }
   out[i] = r;

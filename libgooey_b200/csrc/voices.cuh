@@ -614,7 +614,7 @@ G_D float tom_tick(TomState& s, const RateCtx& rc) {
     float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < 5; i++) acc += biquad_process(s.mem[i], mi);
-    float clipped = tanhf(acc);
+    float clipped = gm::g_tanhf(acc);
     s.ring_level = s.ring_level * 0.999f + fabsf(clipped) * 0.001f;
     mem_out = clipped;
   }

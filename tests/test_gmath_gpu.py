@@ -69,11 +69,23 @@ def test_hash_noise_matches_oracle():
     assert np.array_equal(bits(got), bits(want))
 
 
-def test_max_curve_close_to_oracle():
+def test_max_curve_matches_oracle():
     import oracle_lib as O
     rng = np.random.default_rng(4)
     p = rng.uniform(0, 1, 20000).astype(np.float32)
     c = rng.choice(np.array([-0.83, -0.8, -0.3, 0.8, 0.5], np.float32), 20000)
     got = dev(5, p, c)
     want = np.array([O.lib().orc_max_curve(float(a), float(b)) for a, b in zip(p, c)], np.float32)
-    assert np.abs(got - want).max() < 5e-7  # expm1f differs by <= 2 ulp between CUDA and glibc
+    assert np.array_equal(bits(got), bits(want))  # powf and expm1f are both bit-exact ports
+
+
+@pytest.mark.parametrize("kind,fn,lo,hi", [(6, "tanhf", -30.0, 30.0), (8, "expm1f", -30.0, 30.0), (7, "tanf", 0.0, 1.38)])
+def test_fdlibm_ports_bit_exact(kind, fn, lo, hi):
+    f = getattr(libm, fn)
+    f.restype = ctypes.c_float
+    f.argtypes = [ctypes.c_float]
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(lo, hi, N), rng.uniform(max(lo, -1.0), min(hi, 1.0), N)]).astype(np.float32)
+    got = dev(kind, x)
+    want = np.array([f(float(a)) for a in x], np.float32)
+    assert np.array_equal(bits(got), bits(want))
