@@ -139,25 +139,13 @@ static void voice_batch_render_impl(GooeyVoiceBatch* b, uint32_t frames, float* 
   cudaStream_t st = b->stream;
   b->kicks.ensure_uploaded(st); b->snares.ensure_uploaded(st); b->hats.ensure_uploaded(st); b->toms.ensure_uploaded(st);
   b->kicks.stage_events(st); b->snares.stage_events(st); b->hats.stage_events(st); b->toms.stage_events(st);
-  float* target = out_dev;
-  size_t tstride = stride;
-  if (!b->identity_rows) {
-    tstride = (frames + 3) & ~(size_t)3;
-    b->d_sorted.alloc((size_t)b->n * tstride);
-    target = b->d_sorted.p;
-  }
   GH_CUDA(cudaEventRecord(b->ev0, st));
+  const bool rows = !b->identity_rows;
   int row = 0;
-  b->kicks.launch(st, b->rc, 0, (int)frames, target, (long long)tstride, gd::OUT_VOICE_MAJOR, row); row += b->kicks.n;
-  b->snares.launch(st, b->rc, 0, (int)frames, target, (long long)tstride, gd::OUT_VOICE_MAJOR, row); row += b->snares.n;
-  b->hats.launch(st, b->rc, 0, (int)frames, target, (long long)tstride, gd::OUT_VOICE_MAJOR, row); row += b->hats.n;
-  b->toms.launch(st, b->rc, 0, (int)frames, target, (long long)tstride, gd::OUT_VOICE_MAJOR, row); row += b->toms.n;
-  if (!b->identity_rows) {
-    dim3 grid((frames + 1023) / 1024 < 64 ? (frames + 1023) / 1024 : 64, b->n);
-    unsort_rows_kernel<<<grid, 256, 0, st>>>(b->d_sorted.p, out_dev, b->d_row_map.p, b->n, frames, tstride, stride);
-    g_launches.fetch_add(1);
-    GH_CUDA(cudaGetLastError());
-  }
+  b->kicks.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->kicks.n;
+  b->snares.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->snares.n;
+  b->hats.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->hats.n;
+  b->toms.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->toms.n;
   GH_CUDA(cudaEventRecord(b->ev1, st));
 }
 
@@ -196,7 +184,7 @@ int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoice
         gd::KickState s; memset(&s, 0, sizeof s);
         gd::kick_init(s, p.params, sample_rate);
         if (p.aux & 0x100) s.cur[gd::K_TUNING] = s.tgt[gd::K_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->kicks.add(s, 0);
+        b->vindex[v] = b->kicks.add(s, (int)v);
       } break;
       case GOOEY_INSTRUMENT_SNARE: {
         gd::SnareState s; memset(&s, 0, sizeof s);
@@ -204,19 +192,19 @@ int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoice
         snare_cfg_from_patch(p.params, cfg, ft);
         gd::snare_init(s, cfg, ft, sample_rate);
         if (p.aux & 0x100) s.cur[gd::S_TUNING] = s.tgt[gd::S_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->snares.add(s, 0);
+        b->vindex[v] = b->snares.add(s, (int)v);
       } break;
       case GOOEY_INSTRUMENT_HIHAT: {
         gd::HatState s; memset(&s, 0, sizeof s);
         gd::hat_init(s, p.params, p.aux & 1, (p.aux & 2) ? 0 : 1, sample_rate);
         if (p.aux & 0x100) s.cur[gd::H_TUNING] = s.tgt[gd::H_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->hats.add(s, 0);
+        b->vindex[v] = b->hats.add(s, (int)v);
       } break;
       case GOOEY_INSTRUMENT_TOM: {
         gd::TomState s; memset(&s, 0, sizeof s);
         gd::tom_init(s, (p.aux & 1) ? p.params : nullptr, sample_rate);
         if (p.aux & 0x100) s.p[gd::T_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->toms.add(s, 0);
+        b->vindex[v] = b->toms.add(s, (int)v);
       } break;
       default: set_error("unsupported instrument id in voice patch"); return GOOEY_E_INVALID;
     }

@@ -30,6 +30,7 @@ struct VoiceLaunch {
   long long stride;
   int layout;
   int slot0;                 // first slot (time-major) / first row (voice-major)
+  const uint32_t* rows;      // optional voice -> output row map (voice-major); nullptr = slot0 + voice
   RateCtx rc;
 };
 
@@ -59,7 +60,7 @@ constexpr int TILE = 32;
 
 // Warp-cooperative store of a 32x32 tile (tile[lane][frame]) to voice-major output.
 __device__ __forceinline__ void store_tile_voice_major(const float* tile /*[32][33]*/, float* out, long long stride, int row0,
-                                                        int n_rows, int f0, int nf, int lane) {
+                                                        const uint32_t* rows, int n_rows, int f0, int nf, int lane) {
   const bool vec_ok = (nf == TILE) && ((stride & 3) == 0) && ((f0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (vec_ok) {
     const int c = (lane & 7) * 4;
@@ -69,12 +70,15 @@ __device__ __forceinline__ void store_tile_voice_major(const float* tile /*[32][
       if (r < n_rows) {
         const float* src = tile + r * 33 + c;
         float4 v = make_float4(src[0], src[1], src[2], src[3]);
-        *reinterpret_cast<float4*>(out + (long long)(row0 + r) * stride + f0 + c) = v;
+        const long long row = rows ? (long long)rows[r] : (long long)(row0 + r);
+        *reinterpret_cast<float4*>(out + row * stride + f0 + c) = v;
       }
     }
   } else {
-    for (int r = 0; r < n_rows; r++)
-      if (lane < nf) out[(long long)(row0 + r) * stride + f0 + lane] = tile[r * 33 + lane];
+    for (int r = 0; r < n_rows; r++) {
+      const long long row = rows ? (long long)rows[r] : (long long)(row0 + r);
+      if (lane < nf) out[row * stride + f0 + lane] = tile[r * 33 + lane];
+    }
   }
 }
 
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(BLOCK) voice_kernel(const VoiceLaunch L) {
     }
     if (L.layout == OUT_VOICE_MAJOR) {
       __syncwarp();
-      store_tile_voice_major(tile, L.out, L.stride, L.slot0 + warp_v0, n_rows, L.frame0 + f0, nf, lane);
+      store_tile_voice_major(tile, L.out, L.stride, L.slot0 + warp_v0, L.rows ? L.rows + warp_v0 : nullptr, n_rows, L.frame0 + f0, nf, lane);
       __syncwarp();
     }
   }

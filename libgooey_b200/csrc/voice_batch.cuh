@@ -33,7 +33,9 @@ template <class V> struct VoiceGroup {
   EventList events;
   DevBuf<uint32_t> d_state;
   DevBuf<gd::VoiceEvent> d_events;
-  DevBuf<uint32_t> d_ev_begin, d_ev_cursor;
+  DevBuf<uint32_t> d_ev_begin, d_ev_cursor, d_rows;
+  cudaStream_t stream = nullptr;   // each group renders on its own stream so type buckets overlap
+  cudaEvent_t done = nullptr;
   int n = 0, n_pad = 0;
   bool uploaded = false;
 
@@ -48,6 +50,11 @@ template <class V> struct VoiceGroup {
     if (uploaded || n == 0) return;
     n_pad = pad32(n);
     upload_states(d_state, init_states, n_pad, st);
+    std::vector<uint32_t> r(rows.begin(), rows.end());
+    d_rows.upload(r.data(), r.size(), st);
+    GH_CUDA(cudaStreamSynchronize(st));
+    GH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    GH_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     init_states.clear();
     init_states.shrink_to_fit();
     uploaded = true;
@@ -74,12 +81,16 @@ template <class V> struct VoiceGroup {
     GH_CUDA(cudaStreamSynchronize(st));        // host vectors are temporaries
   }
   // rows must be contiguous from rows[0] (voice-major) — groups are laid out that way by their owners
-  void launch(cudaStream_t st, const gd::RateCtx& rc, uint32_t frame0, int frames, float* out, long long stride, int layout, int slot0) {
+  ~VoiceGroup() { if (done) cudaEventDestroy(done); if (stream) cudaStreamDestroy(stream); }
+  // Forks from `parent` (waits on `start`), launches on the group's stream, and makes `parent` wait for completion.
+  void launch(cudaStream_t parent, cudaEvent_t start, const gd::RateCtx& rc, uint32_t frame0, int frames, float* out, long long stride, int layout, int slot0, bool use_rows) {
     if (n == 0 || frames <= 0) return;
+    cudaStream_t st = stream;
+    GH_CUDA(cudaStreamWaitEvent(st, start, 0));
     gd::VoiceLaunch L;
     L.state = d_state.p; L.n = n; L.n_pad = n_pad;
     L.events = d_events.p; L.ev_begin = d_ev_begin.p; L.ev_cursor = d_ev_cursor.p;
-    L.frame0 = frame0; L.frames = frames; L.out = out; L.stride = stride; L.layout = layout; L.slot0 = slot0; L.rc = rc;
+    L.frame0 = frame0; L.frames = frames; L.out = out; L.stride = stride; L.layout = layout; L.slot0 = slot0; L.rows = use_rows ? d_rows.p : nullptr; L.rc = rc;
     // Small batches: one warp per block so the warps spread over all 148 SMs; large: 128-thread blocks.
     if (n <= 148 * 32 * 4) {
       gd::voice_kernel<V, 32><<<(n + 31) / 32, 32, 0, st>>>(L);
@@ -88,6 +99,8 @@ template <class V> struct VoiceGroup {
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     GH_CUDA(cudaGetLastError());
+    GH_CUDA(cudaEventRecord(done, st));
+    GH_CUDA(cudaStreamWaitEvent(parent, done, 0));
   }
 };
 
