@@ -12,15 +12,17 @@
 //                    the store is coalesced without staging.
 #pragma once
 #include <cuda_runtime.h>
-#include "voices.cuh"
+#include "voices2.cuh"
 
 namespace gd {
 
 enum { OUT_VOICE_MAJOR = 0, OUT_TIME_MAJOR = 1 };
 
 struct VoiceLaunch {
-  uint32_t* state;        // [words][n_pad]
+  uint32_t* state;        // [words][n_pad]  (n_pad = pool capacity / row pitch in words)
   int n, n_pad;
+  const uint32_t* slots;     // optional launch index -> pool slot (nullptr = identity)
+  const uint32_t* out_slots; // optional launch index -> time-major output slot (nullptr = slot0 + index)
   const VoiceEvent* events;
   const uint32_t* ev_begin;  // [n+1] offsets into events
   uint32_t* ev_cursor;       // [n] running cursor (persists across chunked launches of one render)
@@ -93,8 +95,11 @@ __global__ void __launch_bounds__(BLOCK) voice_kernel(const VoiceLaunch L) {
   if (warp_v0 >= L.n) return;  // whole warp idle
   typename V::State st;
   uint32_t ev = 0, ev_end = 0;
+  int sv = v, ov = L.slot0 + v;
   if (valid) {
-    load_state(st, L.state, v, L.n_pad);
+    if (L.slots) sv = (int)L.slots[v];
+    if (L.out_slots) ov = (int)L.out_slots[v];
+    load_state(st, L.state, sv, L.n_pad);
     ev = L.ev_cursor[v];
     ev_end = L.ev_begin[v + 1];
   }
@@ -105,9 +110,13 @@ __global__ void __launch_bounds__(BLOCK) voice_kernel(const VoiceLaunch L) {
     if (valid) {
       for (int j = 0; j < nf; j++) {
         const uint32_t frame = L.frame0 + f0 + j;
-        while (ev < ev_end && L.events[ev].frame <= frame) { V::event(st, L.events[ev], L.rc); ev++; }
+        while (ev < ev_end && L.events[ev].frame <= frame) {
+          const VoiceEvent e = L.events[ev];
+          if (e.kind == EV_SET_TIME) st.t = (double)e.value; else V::event(st, e, L.rc);
+          ev++;
+        }
         const float y = V::tick(st, L.rc);
-        if (L.layout == OUT_TIME_MAJOR) L.out[(long long)(f0 + j) * L.stride + L.slot0 + v] = y;
+        if (L.layout == OUT_TIME_MAJOR) L.out[(long long)(f0 + j) * L.stride + ov] = y;
         else tile[lane * 33 + j] = y;
       }
     }
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(BLOCK) voice_kernel(const VoiceLaunch L) {
     }
   }
   if (valid) {
-    store_state(st, L.state, v, L.n_pad);
+    store_state(st, L.state, sv, L.n_pad);
     L.ev_cursor[v] = ev;
   }
 }

@@ -1,0 +1,478 @@
+// mix.cuh — the per-engine mix stage: voice strips (gain x mute, equal-power pan), MixerGraph
+// (scatter -> per-track strip + effect rack -> sum), master gain, global effect chain
+// (tilt / delay / spring reverb / plate reverb in the engine's effect order), optional soft limiter,
+// and the stereo or mono-downmix write-out.  One engine per thread.
+//
+// Delay-line memory lives in "ring arenas": one per effect slot, laid out [ring word][engine slot]
+// so that engines running in lock-step (same write index) touch adjacent addresses (coalesced).
+// Reference: src/ffi.rs:1264-1377, src/frame.rs:31-53, src/mixer/graph.rs:47-58,344-399,
+// src/effects/{tilt_filter,delay,reverb,plate_reverb,limiter}.rs.
+#pragma once
+#include "kernels.cuh"
+
+namespace gd {
+
+constexpr int MAX_TRACKS = 8;
+constexpr int MAX_FX = 8;        // slots 0..3 = global tilt/delay/spring/plate, 4..7 = track-rack effects
+constexpr int N_VOICE_CH = 5;
+enum { FXK_NONE = 0xff, FXK_DELAY = 1, FXK_TILT = 4, FXK_LIMITER = 5, FXK_SPRING = 6, FXK_PLATE = 9 };  // = FFI effect ids
+enum { FXS_TILT = 0, FXS_DELAY = 1, FXS_SPRING = 2, FXS_PLATE = 3, FXS_RACK0 = 4 };
+
+struct Sm { float c, t; };
+G_HD void sm_set(Sm& s, float v, float lo, float hi) { float c = clampf(v, lo, hi); if (fabsf(s.t - c) > 1e-8f) s.t = c; }
+G_HD float sm_tick(Sm& s, float coeff) { smooth_tick(s.c, s.t, coeff); return s.c; }
+
+struct TiltDyn { Sm cutoff[2], res[2]; Tpt svf[2]; float cutoff_target, res_target; };
+struct DelayCh { uint32_t write_index; float z1, z2; uint32_t prev_timing; Sm time, fb, mix, cutoff; };
+struct DelayDyn { DelayCh ch[2]; uint32_t timing_target; float bpm_target, fb_target, mix_target, cutoff_target; uint32_t pingpong; };
+struct SpringCh { uint32_t idx[6]; float fb, damp; Sm decay, mix, damping; };
+struct SpringDyn { SpringCh ch[2]; float decay_target, mix_target, damping_target; };
+struct PlateDyn {
+  uint32_t idx[13];   // 0 predelay, 1..4 input APs, 5 mod_ap_a, 6 delay1_a, 7 ap2_a, 8 delay2_a, 9 mod_ap_b, 10 delay1_b, 11 ap2_b, 12 delay2_b
+  float bandwidth, damp_a, damp_b, fb_a, fb_b, lfo_pa, lfo_pb;
+  Sm decay, mix, damping, predelay, width, size;
+  float t_decay, t_mix, t_damping, t_predelay, t_width, t_size;
+};
+union FxDyn { TiltDyn tilt; DelayDyn delay; SpringDyn spring; PlateDyn plate; uint32_t w[40]; };
+static_assert(sizeof(FxDyn) == 160, "FxDyn must stay 40 words");
+
+struct MixState {
+  Sm ch_gain[N_VOICE_CH], ch_mute[N_VOICE_CH], ch_pan[N_VOICE_CH];
+  Sm tr_gain[MAX_TRACKS], tr_pan[MAX_TRACKS], tr_mute[MAX_TRACKS];
+  Sm master;
+  FxDyn fx[MAX_FX];
+  double t;
+};
+// MixParam indices for MX_SET
+enum { MP_CH_GAIN = 0, MP_CH_MUTE = 5, MP_CH_PAN = 10, MP_TR_GAIN = 15, MP_TR_PAN = 23, MP_TR_MUTE = 31, MP_MASTER = 39 };
+
+// Host-authoritative structure of one engine's mixer (AoS; re-uploaded when edited).
+struct MixCfg {
+  uint32_t n_tracks;
+  int32_t route[7];                 // source -> track (-1 none): drumkit, bass, poly, granulator, loop mixer
+  uint32_t order[9];                // effect_order (ffi.rs:1583-1593)
+  uint32_t fx_kind[MAX_FX];         // FXK_* (FXK_NONE = slot unused)
+  uint32_t fx_enabled[MAX_FX];      // global slots: *_enabled flags; rack slots: 1
+  uint32_t rack_n[MAX_TRACKS];
+  uint8_t rack_slot[MAX_TRACKS][4];
+  uint32_t limiter_on;
+  float lim_th, lim_inv;
+  uint32_t src_poly, src_gran;      // 1 when the poly / granulator voice buffers carry this engine's output
+};
+
+// Geometry of the delay lines at the launch's sample rate (host-computed, reference formulas).
+struct FxGeom {
+  uint32_t delay_len;                 // (sr * 5) as usize + 1            (delay.rs:189)
+  uint32_t spring_off[12], spring_len[12];   // L0..5, R0..5             (reverb.rs:84-96)
+  uint32_t plate_off[13], plate_cap[13];     // DelayLine capacities       (plate_reverb.rs:236-262)
+  float plate_in_delay[4], plate_len[8], plate_excursion, plate_sr_scale, plate_lfo_ia, plate_lfo_ib;
+  uint32_t ring_words[4];             // words per engine for FXK_TILT(0)/DELAY/SPRING/PLATE arenas
+};
+
+struct MixLaunch {
+  uint32_t* state; int n, state_cap;  // MixState pool (SoA words, row pitch state_cap)
+  const uint32_t* slots;              // launch index -> engine slot in the pool / cfg array / ring arenas
+  int n_lpad;                         // channel stride of the voice buffer (launch count padded to 32)
+  const MixCfg* cfg;
+  const VoiceEvent* events; const uint32_t* ev_begin; uint32_t* ev_cursor;
+  const float* voice_buf;             // time-major [frame][voice_stride], slot = ch * n_lpad + launch index (ch 5 = poly, 6 = gran)
+  long long voice_stride;
+  float* ring[MAX_FX];                // per fx-slot arenas [word][ring_cap]
+  long long ring_cap;
+  uint32_t frame0; int frames;
+  float* out; long long out_stride; int out_mode;  // 0: mono downmix [engine][frame], 1: interleaved stereo [engine][2*frame]
+  const uint32_t* out_rows;
+  RateCtx rc; FxGeom geo;
+  float center_l, center_r;           // cos/sin(0.5 * pi/2) for the center-panned poly / granulator (ffi.rs:1287-1288)
+};
+
+// ---------------------------------------------------------------- effect constructors (device + host) ----
+G_HD void tilt_init(TiltDyn& d, float sr) {  // TiltFilterEffect::new
+  for (int c = 0; c < 2; c++) { d.cutoff[c] = {0.5f, 0.5f}; d.res[c] = {0.0f, 0.0f}; tpt_init(d.svf[c], sr, 1000.0f, 0.5f); }
+  d.cutoff_target = 0.5f; d.res_target = 0.0f;
+}
+G_HD float delay_beats(uint32_t t) {
+  switch (t) { case 0: return 4.0f; case 1: return 2.0f; case 2: return 1.0f; case 3: return 0.5f; case 4: return 0.25f;
+    case 5: return 4.0f / 3.0f; case 6: return 2.0f / 3.0f; case 7: return 1.0f / 3.0f; case 8: return 1.0f / 6.0f; default: return 1.0f; }
+}
+G_HD float delay_seconds(uint32_t timing, float bpm) { return fminf((60.0f / bpm) * delay_beats(timing), 5.0f); }
+G_HD void delay_init(DelayDyn& d, uint32_t timing, float bpm, float fb, float mix, float cutoff) {  // DelayEffect::new
+  float time = delay_seconds(timing, bpm);
+  float fbc = clampf(fb, 0.0f, 0.95f), mc = clampf(mix, 0.0f, 1.0f), cc = clampf(cutoff, 20.0f, 20000.0f);
+  for (int c = 0; c < 2; c++) {
+    DelayCh& s = d.ch[c];
+    s.write_index = 0; s.z1 = s.z2 = 0.0f; s.prev_timing = timing;
+    float tc = clampf(time, 0.0f, 5.0f);
+    s.time = {tc, tc}; s.fb = {fbc, fbc}; s.mix = {mc, mc}; s.cutoff = {cc, cc};
+  }
+  d.timing_target = timing; d.bpm_target = bpm; d.fb_target = fbc; d.mix_target = mc; d.cutoff_target = cc; d.pingpong = 0;
+}
+G_HD void spring_init(SpringDyn& d, float decay, float mix, float damping) {  // SpringReverbEffect::new
+  decay = clampf(decay, 0.0f, 1.0f); mix = clampf(mix, 0.0f, 1.0f); damping = clampf(damping, 0.0f, 1.0f);
+  for (int c = 0; c < 2; c++) {
+    SpringCh& s = d.ch[c];
+    for (int i = 0; i < 6; i++) s.idx[i] = 0;
+    s.fb = s.damp = 0.0f; s.decay = {decay, decay}; s.mix = {mix, mix}; s.damping = {damping, damping};
+  }
+  d.decay_target = decay; d.mix_target = mix; d.damping_target = damping;
+}
+G_HD void plate_init(PlateDyn& d, float decay, float mix, float damping) {  // PlateReverbEffect::new
+  decay = clampf(decay, 0.0f, 1.0f); mix = clampf(mix, 0.0f, 1.0f); damping = clampf(damping, 0.0f, 1.0f);
+  for (int i = 0; i < 13; i++) d.idx[i] = 0;
+  d.bandwidth = d.damp_a = d.damp_b = d.fb_a = d.fb_b = d.lfo_pa = d.lfo_pb = 0.0f;
+  d.decay = {decay, decay}; d.mix = {mix, mix}; d.damping = {damping, damping}; d.predelay = {0.0f, 0.0f}; d.width = {1.0f, 1.0f}; d.size = {0.5f, 0.5f};
+  d.t_decay = decay; d.t_mix = mix; d.t_damping = damping; d.t_predelay = 0.0f; d.t_width = 1.0f; d.t_size = 0.5f;
+}
+// effect_chain.rs:57-109 defaults for rack effects vs ffi.rs:869-884 defaults for the global instances
+G_HD void fx_construct(FxDyn& f, uint32_t kind, bool rack, float sr, float bpm) {
+  for (int i = 0; i < 40; i++) f.w[i] = 0;
+  switch (kind) {
+    case FXK_TILT: tilt_init(f.tilt, sr); break;
+    case FXK_DELAY: if (rack) delay_init(f.delay, 2, bpm, 0.3f, 0.3f, 8000.0f); else delay_init(f.delay, 2, bpm, 0.0f, 0.0f, 20000.0f); break;
+    case FXK_SPRING: spring_init(f.spring, 0.5f, rack ? 0.3f : 0.0f, 0.5f); break;
+    case FXK_PLATE: plate_init(f.plate, 0.5f, rack ? 0.3f : 0.0f, 0.5f); break;
+    default: break;
+  }
+}
+// `set_param` of each effect (ffi.rs:2988-3075 == effect_chain.rs:152-232): raw FFI value -> clamped atomic target
+G_HD void fx_set_param(FxDyn& f, uint32_t kind, uint32_t p, float v) {
+  switch (kind) {
+    case FXK_TILT: if (p == 0) f.tilt.cutoff_target = clampf(v, 0.0f, 1.0f); else if (p == 1) f.tilt.res_target = clampf(v, 0.0f, 1.0f); break;
+    case FXK_DELAY:
+      switch (p) {
+        case 0: { uint64_t t = f32_to_u64_sat(v); if (t <= 8) f.delay.timing_target = (uint32_t)t; } break;
+        case 1: f.delay.fb_target = clampf(v, 0.0f, 0.95f); break;
+        case 2: f.delay.mix_target = clampf(v, 0.0f, 1.0f); break;
+        case 3: f.delay.cutoff_target = clampf(v, 20.0f, 20000.0f); break;
+        case 4: f.delay.pingpong = v >= 0.5f; break;
+      }
+      break;
+    case FXK_SPRING: v = clampf(v, 0.0f, 1.0f); if (p == 0) f.spring.decay_target = v; else if (p == 1) f.spring.mix_target = v; else if (p == 2) f.spring.damping_target = v; break;
+    case FXK_PLATE:
+      v = clampf(v, 0.0f, 1.0f);
+      switch (p) { case 0: f.plate.t_decay = v; break; case 1: f.plate.t_mix = v; break; case 2: f.plate.t_damping = v; break;
+        case 3: f.plate.t_predelay = v; break; case 4: f.plate.t_width = v; break; case 5: f.plate.t_size = v; break; }
+      break;
+    default: break;
+  }
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- per-sample effect processing ----
+struct RingRef { float* base; long long cap; int es; __device__ __forceinline__ float& at(uint32_t j) const { return base[(long long)j * cap + es]; } };
+
+__device__ __forceinline__ float tilt_one(TiltDyn& d, int c, float in, const RateCtx& rc) {  // tilt_filter.rs:87-139
+  sm_set(d.cutoff[c], d.cutoff_target, 0.0f, 1.0f);
+  sm_set(d.res[c], d.res_target, 0.0f, 1.0f);
+  float knob = sm_tick(d.cutoff[c], rc.smooth30);
+  float resonance = sm_tick(d.res[c], rc.smooth30);
+  float mix, freq; bool lp;
+  if (knob < 0.5f) { mix = 1.0f - (knob * 2.0f); float t = knob * 2.0f; freq = 80.0f * gm::g_powf(20000.0f / 80.0f, t); lp = true; }
+  else { mix = (knob - 0.5f) * 2.0f; float t = (knob - 0.5f) * 2.0f; freq = 20.0f * gm::g_powf(8000.0f / 20.0f, t); lp = false; }
+  if (mix < 0.001f) return in;
+  float q = 0.5f + resonance * 8.0f;
+  tpt_set(d.svf[c], rc.sr, freq, q);
+  float lo, bd, hi;
+  tpt_process(d.svf[c], in, lo, bd, hi);
+  float wet = lp ? lo : hi;
+  float out = in * (1.0f - mix) + wet * mix;
+  if (!isfinite(out)) { d.svf[c].ic1 = d.svf[c].ic2 = 0.0f; return 0.0f; }
+  if (fabsf(out) < 1e-15f) return 0.0f;
+  return out;
+}
+
+struct DelayStep { float filtered, feedback, mix; };
+__device__ __forceinline__ DelayStep delay_read(DelayDyn& d, int c, const RingRef& r, uint32_t len, const RateCtx& rc) {  // delay.rs:321-399
+  DelayCh& s = d.ch[c];
+  const uint32_t base = c * len;
+  uint32_t tc = d.timing_target;
+  float time_target = delay_seconds(tc <= 8 ? tc : 2, d.bpm_target);
+  if (tc != s.prev_timing) {
+    s.prev_timing = tc;
+    for (uint32_t j = 0; j < len; j++) r.at(base + j) = 0.0f;
+    s.z1 = s.z2 = 0.0f;
+    float tcl = clampf(time_target, 0.0f, 5.0f);
+    s.time = {tcl, tcl};
+  }
+  sm_set(s.time, time_target, 0.0f, 5.0f); sm_set(s.fb, d.fb_target, 0.0f, 0.95f); sm_set(s.mix, d.mix_target, 0.0f, 1.0f); sm_set(s.cutoff, d.cutoff_target, 20.0f, 20000.0f);
+  float time = sm_tick(s.time, rc.smooth50), feedback = sm_tick(s.fb, rc.smooth30), mix = sm_tick(s.mix, rc.smooth30), cutoff = sm_tick(s.cutoff, rc.smooth30);
+  float ds = time * rc.sr;
+  uint32_t di = (uint32_t)f32_to_u64_sat(ds);
+  float df = ds - (float)di;
+  uint32_t r1 = (s.write_index + len - di) % len;
+  uint32_t r2 = (s.write_index + len - di - 1) % len;
+  float s1 = r.at(base + r1), s2 = r.at(base + r2);
+  float delayed = s1 * (1.0f - df) + s2 * df;
+  float g = 1.0f - gm::g_expf(-2.0f * PI_F * cutoff / rc.sr);
+  float rfb = 0.3f * (s.z1 - s.z2);
+  s.z1 = s.z1 + g * (delayed + rfb - s.z1);
+  s.z2 = s.z2 + g * (s.z1 - s.z2);
+  float filtered = s.z2;
+  if (fabsf(s.z1) < 1e-15f) s.z1 = 0.0f;
+  if (fabsf(s.z2) < 1e-15f) s.z2 = 0.0f;
+  return {filtered, feedback, mix};
+}
+__device__ __forceinline__ float delay_write(DelayDyn& d, int c, const RingRef& r, uint32_t len, float dry, float inject, const DelayStep& st, float tap) {  // :407-439
+  DelayCh& s = d.ch[c];
+  float w = inject + tap * st.feedback;
+  w = (isfinite(w) && fabsf(w) > 1e-15f) ? w : 0.0f;
+  r.at(c * len + s.write_index) = w;
+  s.write_index = (s.write_index + 1) % len;
+  float out = dry * (1.0f - st.mix) + st.filtered * st.mix;
+  return isfinite(out) ? out : dry;
+}
+__device__ __forceinline__ void delay_stereo(DelayDyn& d, const RingRef& r, uint32_t len, float& l, float& rr, const RateCtx& rc) {  // :460-491
+  if (!d.pingpong) {
+    float li = isfinite(l) ? l : 0.0f;
+    DelayStep a = delay_read(d, 0, r, len, rc);
+    l = delay_write(d, 0, r, len, li, li, a, a.filtered);
+    float ri = isfinite(rr) ? rr : 0.0f;
+    DelayStep b = delay_read(d, 1, r, len, rc);
+    rr = delay_write(d, 1, r, len, ri, ri, b, b.filtered);
+    return;
+  }
+  float li = isfinite(l) ? l : 0.0f, ri = isfinite(rr) ? rr : 0.0f;
+  DelayStep a = delay_read(d, 0, r, len, rc), b = delay_read(d, 1, r, len, rc);
+  l = delay_write(d, 0, r, len, li, li, a, b.filtered);
+  rr = delay_write(d, 1, r, len, ri, 0.0f, b, a.filtered);
+}
+
+__device__ __forceinline__ float spring_one(SpringDyn& d, int c, const RingRef& r, const FxGeom& g, float in, const RateCtx& rc) {  // reverb.rs:162-217
+  const float G[6] = {0.70f, 0.68f, 0.65f, 0.62f, 0.60f, 0.58f};
+  SpringCh& s = d.ch[c];
+  in = isfinite(in) ? in : 0.0f;
+  sm_set(s.decay, d.decay_target, 0.0f, 1.0f); sm_set(s.mix, d.mix_target, 0.0f, 1.0f); sm_set(s.damping, d.damping_target, 0.0f, 1.0f);
+  float decay = sm_tick(s.decay, rc.smooth15), mix = sm_tick(s.mix, rc.smooth15), damping = sm_tick(s.damping, rc.smooth15);
+  float feedback = gm::g_powf(decay, 0.4f) * 0.95f;
+  float d1 = damping, d2 = 1.0f - damping;
+  float sig = in + s.fb;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const uint32_t off = g.spring_off[c * 6 + i], len = g.spring_len[c * 6 + i];
+    float& cell = r.at(off + s.idx[i]);
+    float delayed = cell;
+    float v = sig - G[i] * delayed;
+    sig = G[i] * v + delayed;
+    cell = v;
+    s.idx[i] = (s.idx[i] + 1) % len;
+  }
+  s.damp = sig * d2 + s.damp * d1;
+  if (fabsf(s.damp) < 1e-15f) s.damp = 0.0f;
+  s.fb = s.damp * feedback;
+  if (fabsf(s.fb) < 1e-15f) s.fb = 0.0f;
+  float res = in * (1.0f - mix) + sig * mix;
+  return isfinite(res) ? res : in;
+}
+
+struct PlateLine {
+  const RingRef& r; uint32_t off, cap; uint32_t& idx;
+  __device__ __forceinline__ void write(float x) { r.at(off + idx) = x; idx = (idx + 1) % cap; }
+  __device__ __forceinline__ float read_frac(float o) const {
+    o = clampf(o, 1.0f, (float)(cap - 2));
+    uint32_t w = (uint32_t)o; float fr = o - (float)w;
+    float a = r.at(off + (idx + cap - w) % cap), b = r.at(off + (idx + cap - w - 1) % cap);
+    return a + fr * (b - a);
+  }
+  __device__ __forceinline__ float tap_frac(float o) const {
+    o = clampf(o, 0.0f, (float)(cap - 2));
+    uint32_t w = (uint32_t)o; float fr = o - (float)w;
+    float a = r.at(off + (idx + cap - 1 - w) % cap), b = r.at(off + (idx + cap - 2 - w) % cap);
+    return a + fr * (b - a);
+  }
+  __device__ __forceinline__ float allpass(float in, float g, float d) { float dl = read_frac(d); float v = in - g * dl; write(v); return g * v + dl; }
+};
+__device__ __forceinline__ void flush_dn(float& x) { if (fabsf(x) < 1e-15f) x = 0.0f; }
+__device__ __forceinline__ void plate_tank(PlateDyn& d, const RingRef& r, const FxGeom& g, float in, float& wl, float& wr, float& mix, const RateCtx& rc) {  // plate_reverb.rs:406-534
+  in = isfinite(in) ? in : 0.0f;
+  sm_set(d.decay, d.t_decay, 0, 1); sm_set(d.mix, d.t_mix, 0, 1); sm_set(d.damping, d.t_damping, 0, 1);
+  sm_set(d.predelay, d.t_predelay, 0, 1); sm_set(d.width, d.t_width, 0, 1); sm_set(d.size, d.t_size, 0, 1);
+  float decay_knob = sm_tick(d.decay, rc.smooth15); mix = sm_tick(d.mix, rc.smooth15); float damping = sm_tick(d.damping, rc.smooth15);
+  float predelay_knob = sm_tick(d.predelay, rc.smooth15); float width = sm_tick(d.width, rc.smooth15);
+  float sz = sm_tick(d.size, rc.smooth15);
+  float size = sz <= 0.5f ? gm::g_powf(4.0f, 2.0f * sz - 1.0f) : gm::g_powf(2.0f, 2.0f * sz - 1.0f);
+  float decay_gain = decay_knob * 0.95f;
+  float dd2 = clampf(decay_gain + 0.15f, 0.25f, 0.50f);
+  float damp = damping * 0.95f;
+#define PL(i) PlateLine{r, g.plate_off[i], g.plate_cap[i], d.idx[i]}
+  PlateLine predelay = PL(0);
+  predelay.write(in);
+  float pds = predelay_knob * 200.0f * 0.001f * rc.sr;
+  float delayed = predelay.tap_frac(pds);
+  d.bandwidth += 0.9995f * (delayed - d.bandwidth);
+  flush_dn(d.bandwidth);
+  float sig = d.bandwidth;
+  const float IAG[4] = {0.750f, 0.750f, 0.625f, 0.625f};
+#pragma unroll
+  for (int i = 0; i < 4; i++) { PlateLine ap = PL(1 + i); sig = ap.allpass(sig, IAG[i], g.plate_in_delay[i]); }
+  d.lfo_pa = fract(d.lfo_pa + g.plate_lfo_ia); d.lfo_pb = fract(d.lfo_pb + g.plate_lfo_ib);
+  const float TAU_F = 6.28318530717958647692f;
+  float lfo_a = gm::g_sinf(TAU_F * d.lfo_pa), lfo_b = gm::g_sinf(TAU_F * d.lfo_pb);
+  float in_a = sig + d.fb_b, in_b = sig + d.fb_a;
+  PlateLine mod_a = PL(5), d1a_l = PL(6), ap2a = PL(7), d2a_l = PL(8), mod_b = PL(9), d1b_l = PL(10), ap2b = PL(11), d2b_l = PL(12);
+  float a1 = mod_a.allpass(in_a, 0.70f, g.plate_len[0] * size + lfo_a * g.plate_excursion);
+  float d1a = d1a_l.read_frac(g.plate_len[1] * size);
+  d1a_l.write(a1);
+  d.damp_a = d1a * (1.0f - damp) + d.damp_a * damp; flush_dn(d.damp_a);
+  float a2 = ap2a.allpass(d.damp_a * decay_gain, dd2, g.plate_len[2] * size);
+  float d2a = d2a_l.read_frac(g.plate_len[3] * size);
+  d2a_l.write(a2);
+  float b1 = mod_b.allpass(in_b, 0.70f, g.plate_len[4] * size + lfo_b * g.plate_excursion);
+  float d1b = d1b_l.read_frac(g.plate_len[5] * size);
+  d1b_l.write(b1);
+  d.damp_b = d1b * (1.0f - damp) + d.damp_b * damp; flush_dn(d.damp_b);
+  float b2 = ap2b.allpass(d.damp_b * decay_gain, dd2, g.plate_len[6] * size);
+  float d2b = d2b_l.read_frac(g.plate_len[7] * size);
+  d2b_l.write(b2);
+  d.fb_a = d2a * decay_gain; flush_dn(d.fb_a);
+  d.fb_b = d2b * decay_gain; flush_dn(d.fb_b);
+  float ts = g.plate_sr_scale * size;
+  float yl = 0.6f * (d1b_l.tap_frac(266.0f * ts) + d1b_l.tap_frac(2974.0f * ts) - ap2b.tap_frac(1913.0f * ts) + d2b_l.tap_frac(1996.0f * ts)
+                     - d1a_l.tap_frac(1990.0f * ts) - ap2a.tap_frac(187.0f * ts) - d2a_l.tap_frac(1066.0f * ts));
+  float yr = 0.6f * (d1a_l.tap_frac(353.0f * ts) + d1a_l.tap_frac(3627.0f * ts) - ap2a.tap_frac(1228.0f * ts) + d2a_l.tap_frac(2673.0f * ts)
+                     - d1b_l.tap_frac(2111.0f * ts) - ap2b.tap_frac(335.0f * ts) - d2b_l.tap_frac(121.0f * ts));
+#undef PL
+  float mid = 0.5f * (yl + yr);
+  float side = 0.5f * (yl - yr) * width;
+  wl = mid + side; wr = mid - side;
+}
+__device__ __forceinline__ void plate_stereo(PlateDyn& d, const RingRef& r, const FxGeom& g, float& l, float& rr, const RateCtx& rc) {  // :552-565
+  float li = isfinite(l) ? l : 0.0f, ri = isfinite(rr) ? rr : 0.0f;
+  float wl, wr, mix;
+  plate_tank(d, r, g, 0.5f * (li + ri), wl, wr, mix, rc);
+  float ol = li * (1.0f - mix) + wl * mix, orr = ri * (1.0f - mix) + wr * mix;
+  l = isfinite(ol) ? ol : li; rr = isfinite(orr) ? orr : ri;
+}
+
+__device__ __forceinline__ void fx_process(FxDyn& f, uint32_t kind, const RingRef& r, const FxGeom& g, float& l, float& rr, const RateCtx& rc) {
+  switch (kind) {
+    case FXK_TILT: l = tilt_one(f.tilt, 0, l, rc); rr = tilt_one(f.tilt, 1, rr, rc); break;
+    case FXK_DELAY: delay_stereo(f.delay, r, g.delay_len, l, rr, rc); break;
+    case FXK_SPRING: l = spring_one(f.spring, 0, r, g, l, rc); rr = spring_one(f.spring, 1, r, g, rr, rc); break;
+    case FXK_PLATE: plate_stereo(f.plate, r, g, l, rr, rc); break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ void mix_event(MixState& s, const MixCfg& cfg, const VoiceEvent& e, const RateCtx& rc) {
+  switch (e.kind) {
+    case EV_SET_TIME: s.t = (double)e.value; break;
+    case MX_SET: {
+      const uint32_t p = e.param;
+      if (p < MP_CH_MUTE) sm_set(s.ch_gain[p - MP_CH_GAIN], e.value, 0.0f, 1.0f);
+      else if (p < MP_CH_PAN) sm_set(s.ch_mute[p - MP_CH_MUTE], e.value, 0.0f, 1.0f);
+      else if (p < MP_TR_GAIN) sm_set(s.ch_pan[p - MP_CH_PAN], e.value, 0.0f, 1.0f);
+      else if (p < MP_TR_PAN) sm_set(s.tr_gain[p - MP_TR_GAIN], e.value, 0.0f, 2.0f);
+      else if (p < MP_TR_MUTE) sm_set(s.tr_pan[p - MP_TR_PAN], e.value, 0.0f, 1.0f);
+      else if (p < MP_MASTER) sm_set(s.tr_mute[p - MP_TR_MUTE], e.value, 0.0f, 1.0f);
+      else if (p == MP_MASTER) sm_set(s.master, e.value, 0.0f, 2.0f);
+    } break;
+    case MX_SNAP:
+      if (e.param == 0) { for (int i = 0; i < N_VOICE_CH; i++) { s.ch_mute[i].c = s.ch_mute[i].t; s.ch_gain[i].c = s.ch_gain[i].t; s.ch_pan[i].c = s.ch_pan[i].t; } }
+      else if (e.param == 1) { for (int i = 0; i < MAX_TRACKS; i++) { s.tr_gain[i].c = s.tr_gain[i].t; s.tr_pan[i].c = s.tr_pan[i].t; s.tr_mute[i].c = s.tr_mute[i].t; } }
+      else s.master.c = s.master.t;
+      break;
+    case MX_FX_SET: { uint32_t slot = e.param >> 8; if (slot < MAX_FX) fx_set_param(s.fx[slot], cfg.fx_kind[slot], e.param & 0xff, e.value); } break;
+    case MX_FX_INIT: if (e.param < MAX_FX) fx_construct(s.fx[e.param], e.aux & 0xff, e.param >= FXS_RACK0, rc.sr, e.value); break;
+    case MX_FX_BPM: if (e.param < MAX_FX && cfg.fx_kind[e.param] == FXK_DELAY) s.fx[e.param].delay.bpm_target = e.value; break;
+    case MX_TRACK_INIT: if (e.param < MAX_TRACKS) { s.tr_gain[e.param] = {1.0f, 1.0f}; s.tr_pan[e.param] = {0.5f, 0.5f}; s.tr_mute[e.param] = {1.0f, 1.0f}; } break;
+    default: break;
+  }
+}
+
+// One engine per thread; 32 engines x 32 frames staged per warp for the coalesced write-out.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) mix_kernel(const MixLaunch L) {
+  __shared__ float tiles[BLOCK / 32][2][TILE * 33];
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warp_i0 = i - lane;
+  if (warp_i0 >= L.n) return;
+  const bool valid = i < L.n;
+  MixState st;
+  MixCfg cfg;
+  uint32_t ev = 0, ev_end = 0;
+  int es = 0;
+  if (valid) {
+    es = (int)L.slots[i];
+    load_state(st, L.state, es, L.state_cap);
+    cfg = L.cfg[es];
+    ev = L.ev_cursor[i]; ev_end = L.ev_begin[i + 1];
+  }
+  float* tl = tiles[warp][0];
+  float* tr = tiles[warp][1];
+  const int n_rows = min(32, L.n - warp_i0);
+  const RateCtx& rc = L.rc;
+  // pan trig cache (pan is constant during a bounce; recomputed when the smoothed value moves)
+  float pan_v[N_VOICE_CH], pan_cos[N_VOICE_CH], pan_sin[N_VOICE_CH];
+#pragma unroll
+  for (int c = 0; c < N_VOICE_CH; c++) { pan_v[c] = -1.0f; pan_cos[c] = pan_sin[c] = 0.0f; }
+  for (int f0 = 0; f0 < L.frames; f0 += TILE) {
+    const int nf = min(TILE, L.frames - f0);
+    if (valid) {
+      for (int j = 0; j < nf; j++) {
+        const uint32_t frame = L.frame0 + f0 + j;
+        while (ev < ev_end && L.events[ev].frame <= frame) { mix_event(st, cfg, L.events[ev], rc); ev++; }
+        const float* vb = L.voice_buf + (long long)(f0 + j) * L.voice_stride + i;
+        float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
+#pragma unroll
+        for (int c = 0; c < N_VOICE_CH; c++) {  // ffi.rs:1268-1283
+          float x = vb[(long long)c * L.n_lpad] * sm_tick(st.ch_gain[c], rc.smooth10) * sm_tick(st.ch_mute[c], rc.smooth10);
+          float pan = sm_tick(st.ch_pan[c], rc.smooth10);
+          if (pan != pan_v[c]) { float ang = clampf(pan, 0.0f, 1.0f) * 1.57079632679489661923f; pan_v[c] = pan; pan_cos[c] = gm::g_cosf(ang); pan_sin[c] = gm::g_sinf(ang); }
+          float pl = x * pan_cos[c], pr = x * pan_sin[c];
+          if (c < 4) { kit_l += pl; kit_r += pr; } else { bass_l += pl; bass_r += pr; }
+        }
+        float src_l[5] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f}, src_r[5] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f};
+        if (cfg.src_poly) { float x = vb[5LL * L.n_lpad]; src_l[2] = x * L.center_l; src_r[2] = x * L.center_r; }
+        if (cfg.src_gran) { float x = vb[6LL * L.n_lpad]; src_l[3] = x * L.center_l; src_r[3] = x * L.center_r; }
+        float ml = 0.0f, mr = 0.0f;
+        for (uint32_t t = 0; t < cfg.n_tracks; t++) {  // graph.rs:344-350, 385-399
+          float fl = 0.0f, fr = 0.0f;
+#pragma unroll
+          for (int s = 0; s < 5; s++) if (cfg.route[s] == (int32_t)t) { fl += src_l[s]; fr += src_r[s]; }
+          float gain = sm_tick(st.tr_gain[t], rc.smooth10) * sm_tick(st.tr_mute[t], rc.smooth10);
+          fl *= gain; fr *= gain;
+          float pan = clampf(sm_tick(st.tr_pan[t], rc.smooth10), 0.0f, 1.0f);
+          fl *= fminf(2.0f * (1.0f - pan), 1.0f);
+          fr *= fminf(2.0f * pan, 1.0f);
+          for (uint32_t k = 0; k < cfg.rack_n[t]; k++) {
+            const uint32_t slot = cfg.rack_slot[t][k];
+            fx_process(st.fx[slot], cfg.fx_kind[slot], RingRef{L.ring[slot], L.ring_cap, es}, L.geo, fl, fr, rc);
+          }
+          ml += fl; mr += fr;
+        }
+        const float mg = sm_tick(st.master, rc.smooth30);
+        ml *= mg; mr *= mg;
+#pragma unroll 1
+        for (int o = 0; o < 9; o++) {  // ffi.rs:1317-1364
+          const uint32_t id = cfg.order[o];
+          int slot = id == FXK_TILT ? FXS_TILT : id == FXK_DELAY ? FXS_DELAY : id == FXK_SPRING ? FXS_SPRING : id == FXK_PLATE ? FXS_PLATE : -1;
+          if (slot >= 0 && cfg.fx_enabled[slot]) fx_process(st.fx[slot], id, RingRef{L.ring[slot], L.ring_cap, es}, L.geo, ml, mr, rc);
+        }
+        if (cfg.limiter_on) { ml = gm::g_tanhf(ml * cfg.lim_inv) * cfg.lim_th; mr = gm::g_tanhf(mr * cfg.lim_inv) * cfg.lim_th; }
+        st.t += rc.dt;
+        if (L.out_mode == 0) tl[lane * 33 + j] = 0.5f * (ml + mr);
+        else { tl[lane * 33 + j] = ml; tr[lane * 33 + j] = mr; }
+      }
+    }
+    __syncwarp();
+    if (L.out_mode == 0) {
+      store_tile_voice_major(tl, L.out, L.out_stride, warp_i0, L.out_rows ? L.out_rows + warp_i0 : nullptr, n_rows, L.frame0 + f0, nf, lane);
+    } else {
+      // interleave L/R: row r, frame f -> out[row*stride + 2*(frame0+f0+f) + ch]; 64 consecutive floats per row
+      for (int r = 0; r < n_rows; r++) {
+        const long long row = L.out_rows ? (long long)L.out_rows[warp_i0 + r] : (long long)(warp_i0 + r);
+        float* dst = L.out + row * L.out_stride + 2LL * (L.frame0 + f0);
+        for (int k = lane; k < 2 * nf; k += 32) dst[k] = (k & 1) ? tr[r * 33 + (k >> 1)] : tl[r * 33 + (k >> 1)];
+      }
+    }
+    __syncwarp();
+  }
+  if (valid) {
+    store_state(st, L.state, es, L.state_cap);
+    L.ev_cursor[i] = ev;
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace gd

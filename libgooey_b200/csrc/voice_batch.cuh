@@ -88,7 +88,7 @@ template <class V> struct VoiceGroup {
     cudaStream_t st = stream;
     GH_CUDA(cudaStreamWaitEvent(st, start, 0));
     gd::VoiceLaunch L;
-    L.state = d_state.p; L.n = n; L.n_pad = n_pad;
+    L.state = d_state.p; L.n = n; L.n_pad = n_pad; L.slots = nullptr; L.out_slots = nullptr;
     L.events = d_events.p; L.ev_begin = d_ev_begin.p; L.ev_cursor = d_ev_cursor.p;
     L.frame0 = frame0; L.frames = frames; L.out = out; L.stride = stride; L.layout = layout; L.slot0 = slot0; L.rows = use_rows ? d_rows.p : nullptr; L.rc = rc;
     // Small batches: one warp per block so the warps spread over all 148 SMs; large: 128-thread blocks.

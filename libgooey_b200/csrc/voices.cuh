@@ -16,6 +16,7 @@ struct RateCtx {
   float sr;
   double dt;          // 1.0 / (sr as f64)  (bounce.rs:46, ffi.rs:1096)
   float smooth15;     // SmoothedParam coeff, 15 ms (DEFAULT_SMOOTH_TIME_MS)
+  float smooth10, smooth30, smooth50;
   float click_alpha;  // kick click HP: 1 - exp(-2pi*8000/sr) (resonant_highpass.rs:44-45)
   float asym_down;    // hihat AsymmetricSmoother(100 samples) (hihat2.rs:295-305)
   PinkCoef pink;
@@ -25,6 +26,9 @@ G_HD RateCtx make_rate_ctx(float sr) {
   c.sr = sr;
   c.dt = 1.0 / (double)sr;
   c.smooth15 = smooth_coeff(sr, 15.0f);
+  c.smooth10 = smooth_coeff(sr, 10.0f);
+  c.smooth30 = smooth_coeff(sr, 30.0f);
+  c.smooth50 = smooth_coeff(sr, 50.0f);
   c.click_alpha = 1.0f - gm::g_expf(-2.0f * PI_F * 8000.0f / sr);
   c.asym_down = 1.0f - gm::g_expf(-1.0f / 100.0f);
   c.pink = pink_coefs(sr);
@@ -47,6 +51,7 @@ struct KickState {
   FbShaper ws;
   float velocity;
   uint32_t active;
+  float saved_freq; uint32_t has_saved;   // VoiceStrip.saved_global_freq (ffi.rs:596, 1176-1194)
   double t;
 };
 
@@ -71,7 +76,7 @@ G_HD void kick_init(KickState& s, const float* cfg, float sr) {
   pink_reset(s.pink);
   rlp_init(s.noise_lp, sr, denorm(s.cur[K_NOISE_CUTOFF], 20.0f, 10000.0f), denorm(s.cur[K_NOISE_RES], 0.0f, 5.0f));
   fbws_init(s.ws, sr, overdrive_to_drive(s.cur[K_OVERDRIVE]), s.cur[K_FEEDBACK] * 0.98f, 200.0f + s.cur[K_FB_CUTOFF] * 3800.0f, 1.0f);
-  s.velocity = 1.0f; s.active = 0; s.t = 0.0;
+  s.velocity = 1.0f; s.active = 0; s.saved_freq = 0.0f; s.has_saved = 0; s.t = 0.0;
 }
 
 // KickDrum::trigger_with_velocity (kick.rs:971-1086)
@@ -111,6 +116,20 @@ G_HD void kick_event(KickState& s, const VoiceEvent& e) {
     case EV_SET_TARGET: if (e.param < K_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;
     case EV_SNAP: for (int i = 0; i < K_NP; i++) s.cur[i] = s.tgt[i]; break;
     case EV_SET_AUX: if (e.param == AUX_OVERSAMPLING) { uint32_t m = (uint32_t)e.value; if (s.ws.os.mode != m) { s.ws.os.mode = m; os_reset(s.ws.os); } } break;
+    case EV_NOTE_FREQ: {
+      if (!s.has_saved) { s.saved_freq = s.cur[K_FREQ]; s.has_saved = 1; }
+      float c = clampf(e.value, 0.0f, 1.0f);
+      if (fabsf(s.tgt[K_FREQ] - c) > 1e-8f) s.tgt[K_FREQ] = c;
+      for (int i = 0; i < K_NP; i++) s.cur[i] = s.tgt[i];
+    } break;
+    case EV_RESTORE_FREQ:
+      if (s.has_saved) {
+        s.has_saved = 0;
+        float c = clampf(s.saved_freq, 0.0f, 1.0f);
+        if (fabsf(s.tgt[K_FREQ] - c) > 1e-8f) s.tgt[K_FREQ] = c;
+        for (int i = 0; i < K_NP; i++) s.cur[i] = s.tgt[i];
+      }
+      break;
     default: break;
   }
 }
@@ -468,6 +487,7 @@ struct TomState {
   uint32_t past_attack, main_done, active, tri_enabled;
   Biquad mem[5];
   float mem_q_scale, mem_gain_scale, ring_level;
+  float saved_freq; uint32_t has_saved;
   double t;
 };
 #ifdef __CUDACC__
@@ -511,7 +531,7 @@ G_HD void tom_init(TomState& s, const float* cfg, float sr) {
   s.mem_q_scale = 0.01f; s.mem_gain_scale = 0.0031f; s.ring_level = 0.0f;
   tom_membrane_update(s, sr);           // MembraneResonator::with_params
   tom_update_membrane_params(s, sr);    // Tom2::new tail
-  s.t = 0.0;
+  s.saved_freq = 0.0f; s.has_saved = 0; s.t = 0.0;
   if (cfg) {
     for (int i = 0; i < 8; i++) s.p[i] = cfg[i];
     tom_update_membrane_params(s, sr);
@@ -539,6 +559,13 @@ G_HD void tom_event(TomState& s, const VoiceEvent& e, float sr) {
         s.p[e.param] = e.param == T_TUNING ? clampf(e.value, 0.0f, 1.0f) : clampf(e.value, 0.0f, 100.0f);
         if (e.param == T_MEMBRANE_Q) tom_update_membrane_params(s, sr);
       }
+      break;
+    case EV_NOTE_FREQ:   // get_freq_param() = tune (0-100); set_param(0, v) = clamp01(v)*100 (ffi.rs:131-137, 213-217)
+      if (!s.has_saved) { s.saved_freq = s.p[T_TUNE]; s.has_saved = 1; }
+      s.p[T_TUNE] = clampf(clampf(e.value, 0.0f, 1.0f) * 100.0f, 0.0f, 100.0f);
+      break;
+    case EV_RESTORE_FREQ:
+      if (s.has_saved) { s.has_saved = 0; s.p[T_TUNE] = clampf(clampf(s.saved_freq, 0.0f, 1.0f) * 100.0f, 0.0f, 100.0f); }
       break;
     case EV_SET_AUX:
       if (e.param >= AUX_TOM_RAW_PARAM0 && e.param < AUX_TOM_RAW_PARAM0 + 8) s.p[e.param - AUX_TOM_RAW_PARAM0] = e.value;  // set_config: unclamped

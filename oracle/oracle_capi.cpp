@@ -5,7 +5,7 @@
 #include <thread>
 #include <atomic>
 #include <memory>
-#include "drums.hpp"
+#include "synths.hpp"
 #include "../include/gooey_batch.h"
 
 using namespace orc;
@@ -41,6 +41,13 @@ static std::unique_ptr<Instrument> make_voice(const GooeyVoicePatch& p, float sr
       if (p.aux & 1) t->set_config({p.params[0], p.params[1], p.params[2], p.params[3], p.params[4], p.params[5], p.params[6], p.params[7]});
       if (p.aux & 0x100) t->tuning = clampf(p.params[23], 0.0f, 1.0f);
       return t;
+    }
+    case GOOEY_INSTRUMENT_BASS: {
+      BassConfig c;
+      for (int i = 0; i < 15; i++) c.v[i] = clampf(p.params[i], 0.0f, 1.0f);
+      auto b = std::make_unique<BassSynth>(sr, c);
+      if (p.aux & 0x100) b->p[B_TUNING].set_immediate(p.params[23]);
+      return b;
     }
     default: return nullptr;
   }
@@ -102,5 +109,158 @@ void orc_oversample(int mode, float drive, const float* in, float* out, uint32_t
   for (uint32_t i = 0; i < n; i++) out[i] = os.process(in[i], [&](float x) { return drive > 0.0f ? tanhf(x * drive) : x; });
 }
 void orc_pink(float sr, float* out, uint32_t n) { PinkNoise p(sr); for (uint32_t i = 0; i < n; i++) out[i] = p.tick(); }
+
+}  // extern "C"
+
+// =====================================================================================================
+// Engine-level mirror of the reference C FFI subset (include/gooey.h) with an orc_ prefix, so a test can
+// run one call script against both the oracle and the product.
+// =====================================================================================================
+#include "engine.hpp"
+
+extern "C" {
+
+void* orc_engine_new(float sr) { return new FfiEngine(sr); }
+void orc_engine_free(void* e) { delete (FfiEngine*)e; }
+#define E ((FfiEngine*)e)
+static void set_typed(void* e, uint32_t type, uint32_t param, float v) { if (!e) return; if (VoiceStrip* s = E->by_type(type)) s->inst->set_param(param, v); }
+void orc_engine_set_kick_param(void* e, uint32_t p, float v) { set_typed(e, 0, p, v); }
+void orc_engine_set_snare_param(void* e, uint32_t p, float v) { set_typed(e, 1, p, v); }
+void orc_engine_set_hihat_param(void* e, uint32_t p, float v) { set_typed(e, 2, p, v); }
+void orc_engine_set_tom_param(void* e, uint32_t p, float v) { set_typed(e, 3, p, v); }
+void orc_engine_set_bass_param(void* e, uint32_t p, float v) { set_typed(e, 4, p, v); }
+void orc_engine_set_channel_param(void* e, uint32_t ch, uint32_t p, float v) { if (e && ch < 5) E->voices[ch].inst->set_param(p, v); }
+void orc_engine_set_channel_instrument_type(void* e, uint32_t ch, uint32_t type) {
+  if (!e || ch >= 5 || type > 4 || E->voices[ch].type == type) return;
+  E->voices[ch].inst = make_instrument(type, E->sample_rate);
+  E->voices[ch].type = type;
+}
+void orc_engine_load_bass_preset(void* e, uint32_t id) {
+  if (!e || id > 3) return;
+  VoiceStrip* s = E->by_type(4);
+  if (!s) return;
+  BassConfig c = id == 0 ? BassConfig::acid() : id == 1 ? BassConfig::sub() : id == 2 ? BassConfig::reese() : BassConfig::stab();
+  static_cast<BassSynth*>(s->inst.get())->set_config(c);
+}
+void orc_engine_set_bpm(void* e, float b) { if (e) E->set_bpm(b); }
+void orc_engine_set_swing(void* e, float s) { if (e) E->set_swing(s); }
+void orc_engine_set_master_gain(void* e, float g) { if (e && std::isfinite(g)) E->master_gain.set_target(g); }
+void orc_engine_sequencer_set_instrument_step_settings(void* e, uint32_t inst, uint32_t step, bool enabled, bool set_vel, float vel, bool set_blend,
+                                                       float bx, float by, bool set_note, uint8_t note) {
+  if (!e || inst >= 5) return;
+  VoiceStrip* s = &E->voices[inst];  // sequencer_for_instrument = channel index (ffi.rs:3767-3770)
+  if (step >= s->seq.pattern.size()) return;
+  SeqStep& st = s->seq.pattern[step];
+  st.enabled = enabled;
+  if (set_vel) st.velocity = clampf(vel, 0.0f, 1.0f);
+  if (set_blend) { st.has_blend = true; st.bx = clampf(bx, 0, 1); st.by = clampf(by, 0, 1); }
+  if (set_note) { if (note == 255) st.has_note = false; else { st.has_note = true; st.note = note; } }
+}
+void orc_engine_sequencer_set_instrument_step(void* e, uint32_t inst, uint32_t step, bool enabled) {
+  if (!e || inst >= 5) return;
+  VoiceStrip* s = &E->voices[inst];
+  if (step < s->seq.pattern.size()) s->seq.pattern[step].enabled = enabled;
+}
+void orc_engine_sequencer_start(void* e) { if (e) for (auto& v : E->voices) v.seq.start(); }
+void orc_engine_sequencer_stop(void* e) { if (e) for (auto& v : E->voices) v.seq.stop(); }
+void orc_engine_sequencer_reset(void* e) { if (e) for (auto& v : E->voices) v.seq.reset(); }
+void orc_engine_set_global_effect_param(void* e, uint32_t fx, uint32_t p, float v) {
+  if (!e) return;
+  switch (fx) { case 1: E->delay.set_param(p, v); break; case 4: E->tilt.set_param(p, v); break; case 6: E->reverb.set_param(p, v); break;
+    case 9: E->plate.set_param(p, v); break; case 5: if (p == 0) E->limiter.set_threshold(v); break; }
+}
+void orc_engine_set_global_effect_enabled(void* e, uint32_t fx, bool on) {
+  if (!e) return;
+  switch (fx) { case 1: E->delay_enabled = on; break; case 4: E->tilt_enabled = on; break; case 6: E->reverb_enabled = on; break;
+    case 9: E->plate_enabled = on; break; case 5: E->limiter_enabled = on; break; }
+}
+bool orc_engine_set_effect_order(void* e, const uint32_t* ids, uint32_t len) {
+  if (!e || !ids || len != 9) return false;
+  for (uint32_t i = 0; i < 9; i++) { if (ids[i] > 9 || ids[i] == 5) return false; for (uint32_t j = 0; j < i; j++) if (ids[j] == ids[i]) return false; }
+  for (uint32_t i = 0; i < 9; i++) E->effect_order[i] = ids[i];
+  return true;  // reset_effect_states: tests only reorder before any audio has run
+}
+void orc_engine_set_instrument_gain(void* e, uint32_t i, float g) { if (e && i < 5) E->voices[i].channel_gain.set_target(clampf(g, 0, 1)); }
+void orc_engine_set_instrument_pan(void* e, uint32_t i, float p) { if (e && i < 5) E->voices[i].pan.set_target(clampf(p, 0, 1)); }
+void orc_engine_set_instrument_mute(void* e, uint32_t i, bool m) { if (e && i < 5) E->voices[i].muted = m; }
+void orc_engine_set_instrument_solo(void* e, uint32_t i, bool s) { if (e && i < 5) E->voices[i].soloed = s; }
+void orc_engine_trigger_instrument_with_velocity(void* e, uint32_t i, float v) { if (e && i < 5) { E->voices[i].trigger_velocity = clampf(v, 0, 1); E->voices[i].trigger_pending = true; } }
+int32_t orc_engine_mixer_add_track(void* e, const char*) { return e ? (int32_t)E->graph.add_track() : -1; }
+bool orc_engine_mixer_route_source(void* e, uint32_t src, uint32_t track) { return e ? E->graph.route(src, track) : false; }
+void orc_engine_mixer_set_track_gain(void* e, uint32_t t, float g) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].gain.set_target(clampf(g, 0.0f, 2.0f)); }
+void orc_engine_mixer_set_track_pan(void* e, uint32_t t, float p) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].pan.set_target(clampf(p, 0.0f, 1.0f)); }
+void orc_engine_mixer_set_track_mute(void* e, uint32_t t, bool m) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].muted = m; }
+void orc_engine_mixer_set_track_solo(void* e, uint32_t t, bool s) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].soloed = s; }
+int32_t orc_engine_track_effect_add(void* e, uint32_t t, uint32_t fx) {
+  if (!e || t >= E->graph.tracks.size()) return -1;
+  auto eff = make_channel_effect(fx, E->sample_rate, E->graph.bpm);
+  if (!eff) return -1;
+  E->graph.tracks[t].rack.push_back(std::move(eff));
+  return (int32_t)E->graph.tracks[t].rack.size() - 1;
+}
+void orc_engine_track_effect_set_param(void* e, uint32_t t, uint32_t slot, uint32_t p, float v) {
+  if (e && t < E->graph.tracks.size() && slot < E->graph.tracks[t].rack.size()) E->graph.tracks[t].rack[slot]->set_param(p, v);
+}
+bool orc_engine_granulator_set_buffer(void* e, const float* s, uint32_t len, float sr) {
+  if (!e || !s || len == 0 || !std::isfinite(sr) || sr <= 0.0f) return false;
+  for (uint32_t i = 0; i < len; i++) if (!std::isfinite(s[i])) return false;
+  E->granulator.set_buffer(std::make_shared<std::vector<float>>(s, s + len), sr);
+  return true;
+}
+void orc_engine_granulator_trigger(void* e, float v) { if (e) E->granulator.trigger_with_velocity(E->current_time, clampf(v, 0, 1)); }
+void orc_engine_granulator_set_param(void* e, uint32_t p, float v) { if (e) E->granulator.set_param(p, v); }
+void orc_engine_granulator_set_seed(void* e, uint32_t s) { if (e) E->granulator.set_seed(s); }
+void orc_engine_granulator_snap_params(void* e) { if (e) E->granulator.snap_params(); }
+void orc_engine_poly_trigger_notes(void* e, const uint8_t* notes, uint32_t n, uint32_t preset, float vel) {
+  if (!e) return;
+  vel = clampf(vel, 0, 1);
+  E->poly.set_config(PolyConfig::preset(preset));
+  E->poly.release_all();
+  for (uint32_t i = 0; i < n; i++) E->poly.trigger_note(notes[i], vel);
+}
+void orc_engine_poly_release(void* e) { if (e) E->poly.release_all(); }
+void orc_engine_poly_set_preset(void* e, uint32_t p) { if (e) E->poly.set_config(PolyConfig::preset(p)); }
+void orc_engine_poly_set_param(void* e, uint32_t p, float v) { if (e) E->poly.set_param(p, v); }
+void orc_engine_render(void* e, float* buf, uint32_t frames) { if (e && buf) E->render(buf, frames); }
+float* orc_engine_bounce_to_buffer(void* e, uint32_t bars, uint32_t* out_len) {
+  if (!e || !out_len) return nullptr;
+  std::vector<float> v = E->bounce_to_buffer(bars);
+  float* p = (float*)malloc(v.size() * sizeof(float) + 4);
+  memcpy(p, v.data(), v.size() * sizeof(float));
+  *out_len = (uint32_t)v.size();
+  return p;
+}
+void orc_engine_free_buffer(float* p, uint32_t) { free(p); }
+// sequencer trigger table of channel `ch` over `frames` samples after reset+start (bit-exact gate)
+uint32_t orc_engine_trigger_table(void* e, uint32_t ch, uint32_t frames, uint32_t* out_frames, float* out_vel, uint32_t cap) {
+  if (!e || ch >= 5) return 0;
+  Sequencer s = E->voices[ch].seq;
+  s.reset(); s.start();
+  uint32_t n = 0;
+  for (uint32_t f = 0; f < frames; f++) { SeqTrigger t; if (s.tick(t)) { if (n < cap) { out_frames[n] = f; out_vel[n] = t.velocity; } n++; } }
+  return n;
+}
+#undef E
+
+// ---- Rust-API engine (engine/mod.rs + bounce.rs): instruments by type with optional config, one sequencer each ----
+void* orc_rust_engine_new(float sr) { return new RustEngine(sr); }
+void orc_rust_engine_free(void* e) { delete (RustEngine*)e; }
+#define R ((RustEngine*)e)
+int orc_rust_engine_add_instrument(void* e, const char* name, const GooeyVoicePatch* patch) {
+  auto inst = make_voice(*patch, R->sample_rate);
+  if (!inst) return -1;
+  R->instruments.emplace_back(std::string(name), std::move(inst));
+  return 0;
+}
+void orc_rust_engine_add_sequencer(void* e, const char* name, const uint8_t* enabled, const float* velocity, uint32_t steps) {
+  Sequencer s(R->bpm, R->sample_rate, steps, false);
+  for (uint32_t i = 0; i < steps; i++) { s.pattern[i].enabled = enabled[i] != 0; s.pattern[i].velocity = velocity ? clampf(velocity[i], 0, 1) : 1.0f; }
+  R->sequencers.emplace_back(std::move(s), std::string(name));
+}
+void orc_rust_engine_set_bpm(void* e, float b) { R->bpm = b; }
+void orc_rust_engine_set_master_gain(void* e, float g) { R->master_gain.set_target(g); }
+void orc_rust_engine_clear_global_effects(void* e) { R->limiter_on = false; }
+void orc_rust_engine_bounce_samples(void* e, uint32_t n, float* out) { auto v = R->bounce_samples(n); memcpy(out, v.data(), n * sizeof(float)); }
+#undef R
 
 }  // extern "C"
