@@ -91,7 +91,9 @@ G_HD float env_shape(const Env& e, float elapsed) {
   }
   return e.sustain;
 }
-G_HD float env_amp(Env& e, double now) {  // envelope.rs:154-211
+// Envelope::get_amplitude (envelope.rs:154-211) split into its pure value and its latch side effects so that
+// the time-parallel front-end can evaluate the value from a span-start snapshot (see DESIGN.md "A/B/C").
+G_HD float env_value(const Env& e, double now) {
   if (!(e.flags & 1)) return 0.0f;
   float elapsed = (float)(now - e.trig);
   if (e.flags & 2) {
@@ -101,12 +103,53 @@ G_HD float env_amp(Env& e, double now) {  // envelope.rs:154-211
       float rp = rel_el / e.release;
       return ra * (1.0f - rp);
     }
-    e.flags &= ~1u;
     return 0.0f;
   }
   if (elapsed < e.attack + e.decay || elapsed < e.attack) return env_shape(e, elapsed);
-  if (e.sustain == 0.0f) { e.flags |= 2; e.rel_start = now; }
   return e.sustain;
+}
+G_HD void env_latch(Env& e, double now) {
+  if (!(e.flags & 1)) return;
+  if (e.flags & 2) {
+    float rel_el = (float)(now - e.rel_start);
+    if (!(rel_el < e.release)) e.flags &= ~1u;
+    return;
+  }
+  float elapsed = (float)(now - e.trig);
+  if (elapsed < e.attack + e.decay || elapsed < e.attack) return;
+  if (e.sustain == 0.0f) { e.flags |= 2; e.rel_start = now; }
+}
+G_HD float env_amp(Env& e, double now) { float v = env_value(e, now); env_latch(e, now); return v; }
+
+// ---- analytic advance of the latches over a frame range (planner, kernel A) -----------------------------------------
+// tt[k] is the engine clock after k additions of 1/sr (bounce.rs:48-53); frame j of the call has k = kbase + j.
+constexpr int J_NONE = 0x7fffffff;
+// smallest j in [ja, jb) with pred(tt[kbase + j]) (pred monotone false->true); jb if none
+template <class P> G_HD int first_true(const double* tt, uint32_t kbase, int ja, int jb, const P& pred) {
+  int lo = ja, hi = jb;
+  while (lo < hi) { int mid = lo + ((hi - lo) >> 1); if (pred(tt[kbase + mid])) hi = mid; else lo = mid + 1; }
+  return lo;
+}
+struct EnvPastDecay { const Env* e; float ad; G_HD bool operator()(double now) const { float el = (float)(now - e->trig); return !(el < ad || el < e->attack); } };
+struct EnvPastRelease { const Env* e; G_HD bool operator()(double now) const { float r = (float)(now - e->rel_start); return !(r < e->release); } };
+// Applies to `e` exactly the latch transitions that ticking frames [ja, jb) would; returns the frame at whose tick
+// the envelope became inactive (J_NONE if it does not within the range).
+G_HD int env_advance(Env& e, const double* tt, uint32_t kbase, int ja, int jb) {
+  if (!(e.flags & 1) || ja >= jb) return J_NONE;
+  int j = ja;
+  if (!(e.flags & 2)) {
+    if (e.sustain != 0.0f) return J_NONE;
+    EnvPastDecay p{&e, e.attack + e.decay};
+    int j1 = first_true(tt, kbase, ja, jb, p);
+    if (j1 >= jb) return J_NONE;
+    e.flags |= 2; e.rel_start = tt[kbase + j1];
+    j = j1 + 1;
+  }
+  EnvPastRelease q{&e};
+  int j2 = first_true(tt, kbase, j, jb, q);
+  if (j2 >= jb) return J_NONE;
+  e.flags &= ~1u;
+  return j2;
 }
 
 // ---- max_curve.rs ----------------------------------------------------------------------
@@ -415,6 +458,7 @@ G_D float ws_process(WShaper& w, float in) {
 struct FbShaper {
   float drive, mix, feedback, cutoff, filter_coeff, env_att, env_rel;
   float last_out, filter_state, dc_x1, dc_y1, env;
+  float memo_drive, memo_fb, memo_makeup;   // makeup gain is a pure function of (drive, feedback): cached, bit-identical
   Oversamp os;
 };
 G_HD float fbws_filter_coeff(float c, float sr) { float g = 1.0f - gm::g_expf(-2.0f * PI_F * c / sr); return clampf(g, 0.0f, 0.9f); }
@@ -425,6 +469,7 @@ G_HD void fbws_init(FbShaper& w, float sr, float drive, float fb, float cutoff, 
   w.env_att = gm::g_expf(-1.0f / (1.0f / 1000.0f * sr));
   w.env_rel = gm::g_expf(-1.0f / (120.0f / 1000.0f * sr));
   w.last_out = w.filter_state = w.dc_x1 = w.dc_y1 = w.env = 0.0f;
+  w.memo_drive = -1.0f; w.memo_fb = -1.0f; w.memo_makeup = 1.0f;
   os_init(w.os);
 }
 G_HD void fbws_reset(FbShaper& w) { w.last_out = w.filter_state = w.dc_x1 = w.dc_y1 = w.env = 0.0f; os_reset(w.os); }
@@ -432,15 +477,22 @@ G_HD void fbws_set_cutoff(FbShaper& w, float sr, float c) {
   c = clampf(c, 200.0f, 20000.0f);
   if (c != w.cutoff) { w.cutoff = c; w.filter_coeff = fbws_filter_coeff(c, sr); }  // pure function of (c, sr)
 }
-G_D float fbws_gain_comp(float env, float drive, float feedback) {  // :247-259
+G_D float fbws_makeup(FbShaper& w) {  // the level-independent factor of gain_compensation (:252-256)
+  if (w.drive != w.memo_drive || w.feedback != w.memo_fb) {
+    float drive_norm = clampf((w.drive - 1.0f) / 99.0f, 0.0f, 1.0f);
+    float fb_norm = clampf(w.feedback / 0.98f, 0.0f, 1.0f);
+    float high_end = gm::g_powf(drive_norm, 1.35f) * gm::g_powf(fb_norm, 2.0f);
+    w.memo_makeup = gm::g_powf(10.0f, 5.1f * high_end / 20.0f);
+    w.memo_drive = w.drive; w.memo_fb = w.feedback;
+  }
+  return w.memo_makeup;
+}
+G_D float fbws_gain_comp(FbShaper& w, float env) {  // :247-259
   float reference = fmaxf(env, 0.05f);
-  float driven = fmaxf(fabsf(gm::g_tanhf(reference * drive)), 1e-6f);
+  float driven = fmaxf(fabsf(gm::g_tanhf(reference * w.drive)), 1e-6f);
   float comp_no_fb = gm::g_tanhf(reference) / driven;
-  float drive_norm = clampf((drive - 1.0f) / 99.0f, 0.0f, 1.0f);
-  float fb_norm = clampf(feedback / 0.98f, 0.0f, 1.0f);
-  float high_end = gm::g_powf(drive_norm, 1.35f) * gm::g_powf(fb_norm, 2.0f);
-  float makeup = gm::g_powf(10.0f, 5.1f * high_end / 20.0f);
-  float taming = 1.0f / (1.0f + comp_no_fb * feedback * 0.25f);
+  float makeup = fbws_makeup(w);
+  float taming = 1.0f / (1.0f + comp_no_fb * w.feedback * 0.25f);
   return fminf(comp_no_fb * taming * makeup, 3.0f);
 }
 G_D float fbws_process(FbShaper& w, float in) {  // :109-169
@@ -452,7 +504,7 @@ G_D float fbws_process(FbShaper& w, float in) {  // :109-169
   float coeff = rect > w.env ? w.env_att : w.env_rel;
   w.env += (1.0f - coeff) * (rect - w.env);
   if (fabsf(w.env) < 1e-15f) w.env = 0.0f;
-  float comp = fbws_gain_comp(w.env, w.drive, w.feedback);
+  float comp = fbws_gain_comp(w, w.env);
   float compensated = shaped * comp;
   float out = compensated - w.dc_x1 + 0.995f * w.dc_y1;
   w.dc_x1 = compensated;
@@ -466,15 +518,41 @@ G_D float fbws_process(FbShaper& w, float in) {  // :109-169
 
 // ---- instruments/fm_snap.rs:102-169 -----------------------------------------------------------------------------
 struct PhaseMod { double trig; uint32_t active; };
-G_HD float phasemod_tick(PhaseMod& m, double now) {
+G_HD float phasemod_value(const PhaseMod& m, double now) {
   if (!m.active) return 0.0f;
   float el = (float)(now - m.trig);
   const float attack = 0.001f, decay = 0.005f;
   float total = attack + decay;
-  if (el > total) { m.active = 0; return 0.0f; }
+  if (el > total) return 0.0f;
   if (el < attack) return gm::g_powf(el / attack, 0.3f);
   float de = el - attack;
   return 1.0f - gm::g_powf(de / decay, 0.4f);
+}
+G_HD void phasemod_latch(PhaseMod& m, double now) {
+  if (!m.active) return;
+  float el = (float)(now - m.trig);
+  if (el > 0.001f + 0.005f) m.active = 0;
+}
+G_HD float phasemod_tick(PhaseMod& m, double now) { float v = phasemod_value(m, now); phasemod_latch(m, now); return v; }
+struct PmPast { const PhaseMod* m; G_HD bool operator()(double now) const { float el = (float)(now - m->trig); return el > 0.001f + 0.005f; } };
+G_HD int phasemod_advance(PhaseMod& m, const double* tt, uint32_t kbase, int ja, int jb) {
+  if (!m.active || ja >= jb) return J_NONE;
+  PmPast p{&m};
+  int j = first_true(tt, kbase, ja, jb, p);
+  if (j >= jb) return J_NONE;
+  m.active = 0;
+  return j;
+}
+
+// MaxCurveEnvelope transitions are path independent (each depends only on `now`), so the value at any frame can be
+// computed from a span-start snapshot, and the state after a range is the state after its last frame.
+G_HD float maxenv_value_pure(const MaxEnv2& e, double now) { MaxEnv2 t = e; return maxenv_value(t, now); }
+struct MaxEnvDone { const MaxEnv2* e; G_HD bool operator()(double now) const { MaxEnv2 t = *e; maxenv_value(t, now); return t.seg >= 2; } };
+// first frame in [ja, jb) whose tick leaves the envelope complete (seg >= 2); jb if none
+G_HD int maxenv_complete_frame(const MaxEnv2& e, const double* tt, uint32_t kbase, int ja, int jb) {
+  if (!e.active) return e.seg >= 2 ? ja : jb;
+  MaxEnvDone p{&e};
+  return first_true(tt, kbase, ja, jb, p);
 }
 
 }  // namespace gd

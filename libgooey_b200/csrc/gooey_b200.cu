@@ -3,7 +3,8 @@
 // templates (kernels.cuh), this file instantiates them and owns the host side.
 #include <mutex>
 #include <memory>
-#include "voice_batch.cuh"
+#include "pool.cuh"
+#include "patch.h"
 #include "halfband_design.h"
 
 namespace gh {
@@ -11,6 +12,20 @@ namespace gh {
 std::string& last_error() { static thread_local std::string e; return e; }
 std::atomic<uint64_t> g_launches{0};
 static float g_last_kernel_ms = 0.0f;
+
+ClockTable& clock_table(float sr) {
+  static std::mutex mu;
+  static std::map<uint32_t, ClockTable*> tables;
+  std::lock_guard<std::mutex> lk(mu);
+  uint32_t key; memcpy(&key, &sr, 4);
+  auto it = tables.find(key);
+  if (it == tables.end()) {
+    ClockTable* t = new ClockTable();
+    t->dt = 1.0 / (double)sr;
+    it = tables.emplace(key, t).first;
+  }
+  return *it->second;
+}
 
 // ---- device bring-up --------------------------------------------------------------------------
 static std::mutex g_dev_mutex;
@@ -38,42 +53,42 @@ static void use_device(int device) {
   }
 }
 
-// FFI parameter id -> smoother index (ffi.rs:168-250 with ids ffi.rs:1737-1836)
-static const int kKickFfi[8] = {gd::K_FREQ, gd::K_PUNCH, gd::K_SUB, gd::K_CLICK, gd::K_OSC_DECAY, gd::K_PITCH_ENV_AMT, gd::K_VOLUME, gd::K_TUNING};
-static const int kSnareFfi[20] = {gd::S_FREQ, gd::S_DECAY, gd::S_BRIGHTNESS, gd::S_VOLUME, gd::S_TONAL, gd::S_NOISE, gd::S_PITCH_DROP,
-                                  gd::S_TONAL_DECAY, gd::S_NOISE_DECAY, gd::S_NOISE_TAIL_DECAY, gd::S_FILTER_CUTOFF, gd::S_FILTER_RES, -1,
-                                  gd::S_XFADE, gd::S_PHASE_MOD, gd::S_OVERDRIVE, gd::S_AMP_DECAY, gd::S_AMP_DECAY_CURVE,
-                                  gd::S_TONAL_DECAY_CURVE, gd::S_TUNING};
-static const int kHatFfi[6] = {gd::H_PITCH, gd::H_DECAY, gd::H_ATTACK, gd::H_TONE, gd::H_VOLUME, gd::H_TUNING};
-
-static inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
-
-// Translate `ChannelInstrument::set_param(param, value)` into voice events.  Returns false for unknown ids
-// (the reference ignores them silently).
-template <class AddFn> static bool ffi_param_to_events(uint32_t instrument, uint32_t param, float value, AddFn add) {
-  switch (instrument) {
-    case GOOEY_INSTRUMENT_KICK:
-      if (param >= 8) return false;
-      add(gd::EV_SET_TARGET, kKickFfi[param], clamp01(value));
-      return true;
-    case GOOEY_INSTRUMENT_SNARE:
-      if (param >= 20) return false;
-      if (param == 12) {  // `value as u8` (saturating) then .min(3)
-        int t = !(value == value) ? 0 : (value <= 0.0f ? 0 : (value >= 255.0f ? 255 : (int)value));
-        add(gd::EV_SET_AUX, gd::AUX_SNARE_FILTER_TYPE, (float)(t > 3 ? 3 : t));
-      } else add(gd::EV_SET_TARGET, kSnareFfi[param], clamp01(value));
-      return true;
-    case GOOEY_INSTRUMENT_HIHAT:
-      if (param >= 6) return false;
-      add(gd::EV_SET_TARGET, kHatFfi[param], clamp01(value));
-      return true;
-    case GOOEY_INSTRUMENT_TOM:
-      if (param >= 9) return false;
-      add(gd::EV_SET_TARGET, param, param == 8 ? clamp01(value) : clamp01(value) * 100.0f);
-      return true;
-    default: return false;
+// Every voice-type bucket of one device-resident set of voices.
+struct VoiceBank {
+  TypeRunner<gd::KickV> kicks;
+  TypeRunner<gd::SnareV> snares;
+  TypeRunner<gd::HatV> hats;
+  TypeRunner<gd::TomV> toms;
+  TypeRunner<gd::BassV> basses;
+  void reset() { kicks.reset(); snares.reset(); hats.reset(); toms.reset(); basses.reset(); }
+  // returns the pool slot of a new voice built from `p` (the reference's `<Voice>::with_config`); -1 = bad instrument
+  int create(const GooeyVoicePatch& p, float sr) {
+    switch (p.instrument) {
+      case GOOEY_INSTRUMENT_KICK: { gd::KickState s; init_from_patch(s, p, sr); return kicks.pool.alloc(s); }
+      case GOOEY_INSTRUMENT_SNARE: { gd::SnareState s; init_from_patch(s, p, sr); return snares.pool.alloc(s); }
+      case GOOEY_INSTRUMENT_HIHAT: { gd::HatState s; init_from_patch(s, p, sr); return hats.pool.alloc(s); }
+      case GOOEY_INSTRUMENT_TOM: { gd::TomState s; init_from_patch(s, p, sr); return toms.pool.alloc(s); }
+      case GOOEY_INSTRUMENT_BASS: { gd::BassState s; init_from_patch(s, p, sr); return basses.pool.alloc(s); }
+      default: return -1;
+    }
   }
-}
+  void add(uint32_t type, uint32_t slot, uint32_t row, const std::vector<gd::VoiceEvent>& ev) {
+    switch (type) {
+      case GOOEY_INSTRUMENT_KICK: kicks.add(slot, row, ev); break;
+      case GOOEY_INSTRUMENT_SNARE: snares.add(slot, row, ev); break;
+      case GOOEY_INSTRUMENT_HIHAT: hats.add(slot, row, ev); break;
+      case GOOEY_INSTRUMENT_TOM: toms.add(slot, row, ev); break;
+      case GOOEY_INSTRUMENT_BASS: basses.add(slot, row, ev); break;
+    }
+  }
+  void launch(cudaStream_t parent, cudaEvent_t start, const gd::RateCtx& rc, const double* tt, int frames, float* out, long long stride) {
+    kicks.launch(parent, start, rc, tt, frames, out, stride);
+    snares.launch(parent, start, rc, tt, frames, out, stride);
+    hats.launch(parent, start, rc, tt, frames, out, stride);
+    toms.launch(parent, start, rc, tt, frames, out, stride);
+    basses.launch(parent, start, rc, tt, frames, out, stride);
+  }
+};
 
 }  // namespace gh
 
@@ -89,21 +104,13 @@ struct GooeyVoiceBatch {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n = 0;
-  // voice v -> (type, index in its group); rows are regrouped so each group is contiguous: kick rows first, ...
+  uint32_t k = 0;                        // engine clock index of the next frame (shared by every voice of the batch)
   std::vector<uint8_t> vtype;
-  std::vector<uint32_t> vindex;
-  std::vector<uint32_t> row_of_voice;   // position in the type-sorted row space
-  VoiceGroup<gd::KickV> kicks;
-  VoiceGroup<gd::SnareV> snares;
-  VoiceGroup<gd::HatV> hats;
-  VoiceGroup<gd::TomV> toms;
-  DevBuf<float> d_sorted;               // [n][stride] type-sorted rows when the caller's order is mixed
-  DevBuf<uint32_t> d_row_map;
-  bool identity_rows = true;
-  float* pinned = nullptr;
-  size_t pinned_floats = 0;
+  std::vector<uint32_t> vslot;
+  std::vector<std::vector<gd::VoiceEvent>> pending;   // per voice, frames relative to the next render
+  VoiceBank bank;
+  DevBuf<float> d_out;
   ~GooeyVoiceBatch() {
-    if (pinned) cudaFreeHost(pinned);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -112,41 +119,25 @@ struct GooeyVoiceBatch {
 
 namespace gh {
 
-// out[v][f] = sorted[row_of_voice[v]][f]  — only needed when patches of different types interleave.
-__global__ void unsort_rows_kernel(const float* __restrict__ sorted, float* __restrict__ out, const uint32_t* __restrict__ row_of_voice,
-                                   uint32_t n, uint32_t frames, size_t sstride, size_t ostride) {
-  const uint32_t v = blockIdx.y;
-  const size_t src = (size_t)row_of_voice[v] * sstride;
-  const size_t dst = (size_t)v * ostride;
-  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += gridDim.x * blockDim.x) out[dst + f] = sorted[src + f];
-}
-
-static void snare_cfg_from_patch(const float* p, float* cfg, uint32_t& filter_type) {
-  // new_full order -> S_* order (snare.rs:135-180 / SnareParams::from_config :420-545)
-  // p: 0 freq,1 tonal,2 noise,3 crack,4 decay,5 pitch_drop,6 volume,7 tonal_decay,8 tonal_decay_curve,9 noise_decay,
-  //    10 noise_tail_decay,11 filter_cutoff,12 filter_res,13 filter_type,14 xfade,15 phase_mod,16 overdrive,17 amp_decay,18 amp_decay_curve
-  cfg[gd::S_FREQ] = p[0]; cfg[gd::S_TONAL] = p[1]; cfg[gd::S_NOISE] = p[2]; cfg[gd::S_BRIGHTNESS] = p[3]; cfg[gd::S_DECAY] = p[4];
-  cfg[gd::S_PITCH_DROP] = p[5]; cfg[gd::S_VOLUME] = p[6]; cfg[gd::S_TONAL_DECAY] = p[7]; cfg[gd::S_TONAL_DECAY_CURVE] = p[8];
-  cfg[gd::S_NOISE_DECAY] = p[9]; cfg[gd::S_NOISE_TAIL_DECAY] = p[10]; cfg[gd::S_FILTER_CUTOFF] = p[11]; cfg[gd::S_FILTER_RES] = p[12];
-  float ft = p[13];
-  int t = !(ft == ft) ? 0 : (ft <= 0.0f ? 0 : (ft >= 255.0f ? 255 : (int)ft));
-  filter_type = (uint32_t)(t > 3 ? 3 : t);
-  cfg[gd::S_XFADE] = p[14]; cfg[gd::S_PHASE_MOD] = p[15]; cfg[gd::S_OVERDRIVE] = p[16]; cfg[gd::S_AMP_DECAY] = p[17]; cfg[gd::S_AMP_DECAY_CURVE] = p[18];
-}
-
 static void voice_batch_render_impl(GooeyVoiceBatch* b, uint32_t frames, float* out_dev, size_t stride) {
   use_device(b->device);
   cudaStream_t st = b->stream;
-  b->kicks.ensure_uploaded(st); b->snares.ensure_uploaded(st); b->hats.ensure_uploaded(st); b->toms.ensure_uploaded(st);
-  b->kicks.stage_events(st); b->snares.stage_events(st); b->hats.stage_events(st); b->toms.stage_events(st);
+  if ((uint64_t)b->k + frames >= 0xffffffffull) throw std::runtime_error("engine clock index overflow");
+  const double* tt = clock_table(b->sr).ensure(b->device, (size_t)b->k + frames + 1, st);
+  b->bank.reset();
+  std::vector<gd::VoiceEvent> now, later;
+  for (uint32_t v = 0; v < b->n; v++) {
+    auto& ev = b->pending[v];
+    std::stable_sort(ev.begin(), ev.end(), [](const gd::VoiceEvent& a, const gd::VoiceEvent& c) { return a.frame < c.frame; });
+    now.clear(); later.clear();
+    for (auto& e : ev) { if (e.frame < frames) now.push_back(e); else { e.frame -= frames; later.push_back(e); } }
+    b->bank.add(b->vtype[v], b->vslot[v], v, now);
+    ev = later;
+  }
   GH_CUDA(cudaEventRecord(b->ev0, st));
-  const bool rows = !b->identity_rows;
-  int row = 0;
-  b->kicks.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->kicks.n;
-  b->snares.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->snares.n;
-  b->hats.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->hats.n;
-  b->toms.launch(st, b->ev0, b->rc, 0, (int)frames, out_dev, (long long)stride, gd::OUT_VOICE_MAJOR, row, rows); row += b->toms.n;
+  b->bank.launch(st, b->ev0, b->rc, tt, (int)frames, out_dev, (long long)stride);
   GH_CUDA(cudaEventRecord(b->ev1, st));
+  b->k += frames;
 }
 
 }  // namespace gh
@@ -176,50 +167,12 @@ int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoice
   GH_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   GH_CUDA(cudaEventCreate(&b->ev0));
   GH_CUDA(cudaEventCreate(&b->ev1));
-  b->vtype.resize(n_voices); b->vindex.resize(n_voices); b->row_of_voice.resize(n_voices);
+  b->vtype.resize(n_voices); b->vslot.resize(n_voices); b->pending.resize(n_voices);
   for (uint32_t v = 0; v < n_voices; v++) {
-    const GooeyVoicePatch& p = patches[v];
-    switch (p.instrument) {
-      case GOOEY_INSTRUMENT_KICK: {
-        gd::KickState s; memset(&s, 0, sizeof s);
-        gd::kick_init(s, p.params, sample_rate);
-        if (p.aux & 0x100) s.cur[gd::K_TUNING] = s.tgt[gd::K_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->kicks.add(s, (int)v);
-      } break;
-      case GOOEY_INSTRUMENT_SNARE: {
-        gd::SnareState s; memset(&s, 0, sizeof s);
-        float cfg[18]; uint32_t ft;
-        snare_cfg_from_patch(p.params, cfg, ft);
-        gd::snare_init(s, cfg, ft, sample_rate);
-        if (p.aux & 0x100) s.cur[gd::S_TUNING] = s.tgt[gd::S_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->snares.add(s, (int)v);
-      } break;
-      case GOOEY_INSTRUMENT_HIHAT: {
-        gd::HatState s; memset(&s, 0, sizeof s);
-        gd::hat_init(s, p.params, p.aux & 1, (p.aux & 2) ? 0 : 1, sample_rate);
-        if (p.aux & 0x100) s.cur[gd::H_TUNING] = s.tgt[gd::H_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->hats.add(s, (int)v);
-      } break;
-      case GOOEY_INSTRUMENT_TOM: {
-        gd::TomState s; memset(&s, 0, sizeof s);
-        gd::tom_init(s, (p.aux & 1) ? p.params : nullptr, sample_rate);
-        if (p.aux & 0x100) s.p[gd::T_TUNING] = clamp01(p.params[23]);
-        b->vindex[v] = b->toms.add(s, (int)v);
-      } break;
-      default: set_error("unsupported instrument id in voice patch"); return GOOEY_E_INVALID;
-    }
-    b->vtype[v] = (uint8_t)p.instrument;
-  }
-  // type-sorted row space: kicks, snares, hats, toms
-  uint32_t base[4] = {0, (uint32_t)b->kicks.n, (uint32_t)(b->kicks.n + b->snares.n), (uint32_t)(b->kicks.n + b->snares.n + b->hats.n)};
-  b->identity_rows = true;
-  for (uint32_t v = 0; v < n_voices; v++) {
-    b->row_of_voice[v] = base[b->vtype[v]] + b->vindex[v];
-    if (b->row_of_voice[v] != v) b->identity_rows = false;
-  }
-  if (!b->identity_rows) {
-    b->d_row_map.upload(b->row_of_voice.data(), n_voices, b->stream);
-    GH_CUDA(cudaStreamSynchronize(b->stream));
+    int slot = b->bank.create(patches[v], sample_rate);
+    if (slot < 0) { set_error("unsupported instrument id in voice patch"); return GOOEY_E_INVALID; }
+    b->vtype[v] = (uint8_t)patches[v].instrument;
+    b->vslot[v] = (uint32_t)slot;
   }
   *out_batch = b.release();
   return GOOEY_E_OK;
@@ -229,23 +182,14 @@ int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoice
 void gooey_voice_batch_free(GooeyVoiceBatch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  cudaDeviceSynchronize();
   delete b;
-}
-
-static void vb_add_event(GooeyVoiceBatch* b, uint32_t v, uint32_t frame, uint32_t kind, uint32_t param, float value) {
-  const uint32_t i = b->vindex[v];
-  switch (b->vtype[v]) {
-    case GOOEY_INSTRUMENT_KICK: b->kicks.events.add(i, frame, kind, param, value); break;
-    case GOOEY_INSTRUMENT_SNARE: b->snares.events.add(i, frame, kind, param, value); break;
-    case GOOEY_INSTRUMENT_HIHAT: b->hats.events.add(i, frame, kind, param, value); break;
-    case GOOEY_INSTRUMENT_TOM: b->toms.events.add(i, frame, kind, param, value); break;
-  }
 }
 
 int gooey_voice_batch_trigger(GooeyVoiceBatch* b, uint32_t voice, uint32_t frame, float velocity) {
   GOOEY_TRY
   if (!b || voice >= b->n) { set_error("bad batch/voice"); return GOOEY_E_INVALID; }
-  vb_add_event(b, voice, frame, gd::EV_TRIGGER, 0, velocity);
+  b->pending[voice].push_back(make_event(frame, gd::EV_TRIGGER, 0, velocity));
   return GOOEY_E_OK;
   GOOEY_CATCH
 }
@@ -253,7 +197,7 @@ int gooey_voice_batch_trigger(GooeyVoiceBatch* b, uint32_t voice, uint32_t frame
 int gooey_voice_batch_trigger_all(GooeyVoiceBatch* b, uint32_t frame, const float* velocities) {
   GOOEY_TRY
   if (!b) { set_error("null batch"); return GOOEY_E_INVALID; }
-  for (uint32_t v = 0; v < b->n; v++) vb_add_event(b, v, frame, gd::EV_TRIGGER, 0, velocities ? velocities[v] : 1.0f);
+  for (uint32_t v = 0; v < b->n; v++) b->pending[v].push_back(make_event(frame, gd::EV_TRIGGER, 0, velocities ? velocities[v] : 1.0f));
   return GOOEY_E_OK;
   GOOEY_CATCH
 }
@@ -262,8 +206,8 @@ int gooey_voice_batch_set_param(GooeyVoiceBatch* b, uint32_t voice, uint32_t fra
   GOOEY_TRY
   if (!b || voice >= b->n) { set_error("bad batch/voice"); return GOOEY_E_INVALID; }
   bool known = ffi_param_to_events(b->vtype[voice], param, value,
-                                   [&](uint32_t kind, uint32_t p, float v) { vb_add_event(b, voice, frame, kind, p, v); });
-  if (known && snap) vb_add_event(b, voice, frame, gd::EV_SNAP, 0, 0.0f);
+                                   [&](uint32_t kind, uint32_t p, float v) { b->pending[voice].push_back(make_event(frame, kind, p, v)); });
+  if (known && snap) b->pending[voice].push_back(make_event(frame, gd::EV_SNAP, 0, 0.0f));
   return GOOEY_E_OK;
   GOOEY_CATCH
 }
@@ -283,13 +227,9 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
   if (!b || !out_host) { set_error("bad arguments"); return GOOEY_E_INVALID; }
   use_device(b->device);
   const size_t stride = (frames + 3) & ~(size_t)3;
-  const size_t total = (size_t)b->n * stride;
-  static thread_local DevBuf<float>* scratch = nullptr;
-  DevBuf<float> local;
-  (void)scratch;
-  local.alloc(total);
-  voice_batch_render_impl(b, frames, local.p, stride);
-  GH_CUDA(cudaMemcpy2DAsync(out_host, (size_t)frames * 4, local.p, stride * 4, (size_t)frames * 4, b->n, cudaMemcpyDeviceToHost, b->stream));
+  b->d_out.alloc((size_t)b->n * stride);
+  voice_batch_render_impl(b, frames, b->d_out.p, stride);
+  GH_CUDA(cudaMemcpy2DAsync(out_host, (size_t)frames * 4, b->d_out.p, stride * 4, (size_t)frames * 4, b->n, cudaMemcpyDeviceToHost, b->stream));
   GH_CUDA(cudaStreamSynchronize(b->stream));
   GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, b->ev0, b->ev1));
   return GOOEY_E_OK;

@@ -1,14 +1,17 @@
-// pool.cuh — host-side state pools and launch staging.
+// pool.cuh — host-side state pools, the engine clock table and the per-type launch sequence.
 //
 // Pool<S>: every instance of one voice type (or every engine's mix state) on one device, stored
 // word-interleaved (SoA) with a fixed row pitch (capacity).  Slots are allocated on the host, their
 // constructor-built initial states (voices.cuh init functions run on the host through the bit-exact
-// gm:: math) are uploaded lazily in bulk.  LaunchSet<V>: the per-render list of (slot, output slot,
-// events) for one type bucket and the launch of voice_kernel<V>.  Type bucketing keeps warps
-// type-homogeneous (no cross-instrument divergence).
+// gm:: math) are uploaded lazily in bulk.
+// TypeRunner<V>: the per-render list of (slot, output row, events) for one type bucket and the
+// A -> (B | C pipelined over time chunks) + S launch sequence of kernels.cuh.  Type bucketing keeps
+// warps type-homogeneous (no cross-instrument divergence).
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include "device_rt.h"
 #include "kernels.cuh"
 #include "../../include/gooey_batch.h"
@@ -80,73 +83,142 @@ inline gd::VoiceEvent make_event(uint32_t frame, uint32_t kind, uint32_t param, 
   return e;
 }
 
-// Flattened per-render event lists of n launch items.
-struct EventStage {
-  std::vector<uint32_t> begin;
-  std::vector<gd::VoiceEvent> flat;
-  DevBuf<gd::VoiceEvent> d_events;
-  DevBuf<uint32_t> d_begin, d_cursor;
-  void reset() { begin.clear(); flat.clear(); begin.push_back(0); }
-  // append one item's events (already ordered by frame)
-  void push_item(const std::vector<gd::VoiceEvent>& ev) {
-    flat.insert(flat.end(), ev.begin(), ev.end());
-    begin.push_back((uint32_t)flat.size());
-  }
-  void upload(cudaStream_t st) {
-    if (begin.size() <= 1) return;
-    if (flat.empty()) flat.push_back(make_event(0xffffffffu, 0xffff, 0, 0.0f));
-    d_events.upload(flat.data(), flat.size(), st);
-    d_begin.upload(begin.data(), begin.size(), st);
-    d_cursor.upload(begin.data(), begin.size() - 1, st);
+// The engine clock: tt[k] = value of a f64 accumulator after k additions of 1/sr, exactly as the reference's
+// `current_time += 1.0 / sample_rate` (bounce.rs:48-53, ffi.rs:1379).  Built once on the host, mirrored per device.
+struct ClockTable {
+  double dt = 0.0;
+  std::vector<double> host;
+  std::map<int, std::pair<DevBuf<double>*, size_t>> dev;   // device -> (buffer, valid entries)
+  std::mutex mu;
+  const double* ensure(int device, size_t n, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (host.size() < n) {
+      size_t target = std::max(n, host.size() * 2);
+      target = std::max<size_t>(target, 1u << 16);
+      host.reserve(target);
+      if (host.empty()) host.push_back(0.0);
+      while (host.size() < target) host.push_back(host.back() + dt);
+    }
+    auto& d = dev[device];
+    if (!d.first) d.first = new DevBuf<double>();
+    if (d.second < n) {
+      // reallocation invalidates pointers held by in-flight launches of other batches: drain the device first
+      GH_CUDA(cudaDeviceSynchronize());
+      d.first->upload(host.data(), host.size(), st);
+      GH_CUDA(cudaStreamSynchronize(st));
+      d.second = host.size();
+    }
+    return d.first->p;
   }
 };
+ClockTable& clock_table(float sr);
 
 // One type bucket of one render call.
-template <class V> struct LaunchSet {
+template <class V> struct TypeRunner {
   using State = typename V::State;
-  std::vector<uint32_t> slots, out_slots;
-  EventStage ev;
-  DevBuf<uint32_t> d_slots, d_out_slots;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  Pool<State> pool;
+  std::vector<uint32_t> slots, rows, ev_begin, span_off;
+  std::vector<gd::VoiceEvent> ev_flat;
+  DevBuf<uint32_t> d_slots, d_rows, d_ev_begin, d_span_off, d_n_spans, d_span_cursor;
+  DevBuf<gd::VoiceEvent> d_events;
+  DevBuf<uint8_t> d_mode, d_spans;
+  DevBuf<float> d_planes[2];
+  cudaStream_t sB = nullptr, sC = nullptr, sS = nullptr;
+  cudaEvent_t evA = nullptr, evB[2] = {nullptr, nullptr}, evC[2] = {nullptr, nullptr}, evDoneC = nullptr, evDoneS = nullptr;
+  int chunk_frames = 8192;
+
   int n() const { return (int)slots.size(); }
-  void reset() { slots.clear(); out_slots.clear(); ev.reset(); }
-  void add(uint32_t slot, uint32_t out_slot, const std::vector<gd::VoiceEvent>& events) {
-    slots.push_back(slot); out_slots.push_back(out_slot); ev.push_item(events);
+  void reset() { slots.clear(); rows.clear(); ev_flat.clear(); ev_begin.clear(); ev_begin.push_back(0); span_off.clear(); span_off.push_back(0); }
+  // events must be ordered by frame and lie inside the call
+  void add(uint32_t slot, uint32_t out_row, const std::vector<gd::VoiceEvent>& events) {
+    slots.push_back(slot); rows.push_back(out_row);
+    uint32_t distinct = 0, last = 0xffffffffu;
+    for (const auto& e : events) { if (e.frame != last) { distinct++; last = e.frame; } }
+    ev_flat.insert(ev_flat.end(), events.begin(), events.end());
+    ev_begin.push_back((uint32_t)ev_flat.size());
+    span_off.push_back(span_off.back() + distinct + 1);
   }
-  void upload(cudaStream_t st) {
-    if (slots.empty()) return;
-    if (!stream) {
-      GH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-      GH_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-    }
-    d_slots.upload(slots.data(), slots.size(), st);
-    d_out_slots.upload(out_slots.data(), out_slots.size(), st);
-    ev.upload(st);
+  void ensure_streams() {
+    if (sC) return;
+    GH_CUDA(cudaStreamCreateWithFlags(&sB, cudaStreamNonBlocking));
+    GH_CUDA(cudaStreamCreateWithFlags(&sC, cudaStreamNonBlocking));
+    GH_CUDA(cudaStreamCreateWithFlags(&sS, cudaStreamNonBlocking));
+    cudaEvent_t* evs[] = {&evA, &evB[0], &evB[1], &evC[0], &evC[1], &evDoneC, &evDoneS};
+    for (auto e : evs) GH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
-  ~LaunchSet() { if (done) cudaEventDestroy(done); if (stream) cudaStreamDestroy(stream); }
-  // Forks from `parent` (after `start`), launches on this bucket's stream, joins back into `parent`.
-  void launch(Pool<State>& pool, cudaStream_t parent, cudaEvent_t start, const gd::RateCtx& rc, uint32_t frame0, int frames, float* out,
-              long long stride, int layout) {
+  ~TypeRunner() {
+    cudaEvent_t evs[] = {evA, evB[0], evB[1], evC[0], evC[1], evDoneC, evDoneS};
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+    if (sB) cudaStreamDestroy(sB);
+    if (sC) cudaStreamDestroy(sC);
+    if (sS) cudaStreamDestroy(sS);
+  }
+  // Forks from `parent` (after `start`), runs the bucket on its own streams, joins back into `parent`.
+  void launch(cudaStream_t parent, cudaEvent_t start, const gd::RateCtx& rc, const double* tt, int frames, float* out, long long stride) {
     const int cnt = n();
     if (cnt == 0 || frames <= 0) return;
-    cudaStream_t st = stream;
-    GH_CUDA(cudaStreamWaitEvent(st, start, 0));
+    ensure_streams();
+    GH_CUDA(cudaStreamWaitEvent(sC, start, 0));
+    pool.flush(sC);
+    d_slots.upload(slots.data(), slots.size(), sC);
+    d_rows.upload(rows.data(), rows.size(), sC);
+    if (ev_flat.empty()) ev_flat.push_back(make_event(0xffffffffu, 0xffff, 0, 0.0f));
+    d_events.upload(ev_flat.data(), ev_flat.size(), sC);
+    d_ev_begin.upload(ev_begin.data(), ev_begin.size(), sC);
     gd::VoiceLaunch L;
+    memset(&L, 0, sizeof L);
     L.state = pool.d.p; L.n = cnt; L.n_pad = pool.cap;
-    L.slots = d_slots.p;
-    L.out_slots = layout == gd::OUT_TIME_MAJOR ? d_out_slots.p : nullptr;
-    L.events = ev.d_events.p; L.ev_begin = ev.d_begin.p; L.ev_cursor = ev.d_cursor.p;
-    L.frame0 = frame0; L.frames = frames; L.out = out; L.stride = stride; L.layout = layout; L.slot0 = 0;
-    L.rows = layout == gd::OUT_VOICE_MAJOR ? d_out_slots.p : nullptr;
-    L.rc = rc;
-    // Small buckets: one warp per block so the warps spread over all 148 SMs; large: 128-thread blocks.
-    if (cnt <= 148 * 32 * 4) gd::voice_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, st>>>(L);
-    else gd::voice_kernel<V, 128><<<(cnt + 127) / 128, 128, 0, st>>>(L);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    GH_CUDA(cudaGetLastError());
-    GH_CUDA(cudaEventRecord(done, st));
-    GH_CUDA(cudaStreamWaitEvent(parent, done, 0));
+    L.slots = d_slots.p; L.rows = d_rows.p; L.row0 = 0;
+    L.events = d_events.p; L.ev_begin = d_ev_begin.p; L.tt = tt; L.frames = frames; L.out = out; L.stride = stride; L.rc = rc;
+    if constexpr (V::FAST) {
+      using Span = typename V::Span;
+      d_span_off.upload(span_off.data(), span_off.size(), sC);
+      d_n_spans.alloc(cnt); d_span_cursor.alloc(cnt); d_mode.alloc(cnt);
+      d_spans.alloc((size_t)span_off.back() * sizeof(Span));
+      const int chunk = std::min(chunk_frames, (frames + 31) & ~31);
+      const int rows_pad = pad32(cnt);
+      const size_t plane_floats = (size_t)rows_pad * chunk;
+      d_planes[0].alloc(plane_floats * V::NPL); d_planes[1].alloc(plane_floats * V::NPL);
+      L.mode = d_mode.p; L.spans = d_spans.p; L.span_off = d_span_off.p; L.n_spans = d_n_spans.p; L.span_cursor = d_span_cursor.p;
+      L.plane_stride = (long long)plane_floats; L.pitch = chunk;
+      gd::plan_kernel<V><<<(cnt + 63) / 64, 64, 0, sC>>>(L);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      GH_CUDA(cudaGetLastError());
+      GH_CUDA(cudaEventRecord(evA, sC));
+      GH_CUDA(cudaStreamWaitEvent(sB, evA, 0));
+      GH_CUDA(cudaStreamWaitEvent(sS, evA, 0));
+      // general path for the voices A could not plan (whole call, one launch)
+      gd::slow_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sS>>>(L);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      GH_CUDA(cudaGetLastError());
+      GH_CUDA(cudaEventRecord(evDoneS, sS));
+      int i = 0;
+      for (int c0 = 0; c0 < frames; c0 += chunk, i++) {
+        const int b = i & 1;
+        L.chunk0 = c0; L.chunk_frames = std::min(chunk, frames - c0);
+        L.planes = d_planes[b].p;
+        if (i >= 2) GH_CUDA(cudaStreamWaitEvent(sB, evC[b], 0));   // plane buffer b is free once C of chunk i-2 is done
+        const int bpv = (L.chunk_frames + 255) / 256;
+        gd::front_kernel<V, 256><<<(unsigned)((size_t)cnt * bpv), 256, 0, sB>>>(L, bpv);
+        GH_CUDA(cudaGetLastError());
+        GH_CUDA(cudaEventRecord(evB[b], sB));
+        GH_CUDA(cudaStreamWaitEvent(sC, evB[b], 0));
+        gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one warp per CTA: the warps spread over all SMs
+        GH_CUDA(cudaGetLastError());
+        GH_CUDA(cudaEventRecord(evC[b], sC));
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+      }
+      GH_CUDA(cudaEventRecord(evDoneC, sC));
+      GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
+      GH_CUDA(cudaStreamWaitEvent(parent, evDoneS, 0));
+    } else {
+      if (cnt <= 148 * 32 * 4) gd::slow_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
+      else gd::slow_kernel<V, 128><<<(cnt + 127) / 128, 128, 0, sC>>>(L);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      GH_CUDA(cudaGetLastError());
+      GH_CUDA(cudaEventRecord(evDoneC, sC));
+      GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
+    }
   }
 };
 

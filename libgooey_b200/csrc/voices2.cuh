@@ -6,6 +6,12 @@
 
 namespace gd {
 
+#ifdef __CUDA_ARCH__
+#define G_LDG(p) __ldg(p)
+#else
+#define G_LDG(p) (*(p))
+#endif
+
 // polyBLEP on f64 phases (gen/polyblep.rs:8-40)
 G_HD double poly_blep(double t, double dt) {
   if (t < dt) { t = t / dt; return 2.0 * t - t * t - 1.0; }
@@ -33,7 +39,7 @@ struct BassState {
   float velocity, trig_freq;
   uint32_t active;
   float saved_freq; uint32_t has_saved;
-  double t;
+  uint32_t k, pad_k;
 };
 G_HD float exp_denorm(float n, float mn, float mx) { return mn * gm::g_powf(mx / mn, clampf(n, 0.0f, 1.0f)); }
 // BassSynth::with_config (bass.rs:613-634); cfg = BassConfig::new order (15)
@@ -45,10 +51,9 @@ G_HD void bass_init(BassState& s, const float* cfg, float sr) {
   env_init(s.amp_env); env_init(s.flt_env);
   ws_init(s.ws, s.cur[B_OVERDRIVE], 1.0f);
   s.velocity = 1.0f; s.trig_freq = denorm(s.cur[B_FREQ], 30.0f, 200.0f); s.active = 0;
-  s.saved_freq = 0.0f; s.has_saved = 0; s.t = 0.0;
+  s.saved_freq = 0.0f; s.has_saved = 0; s.k = 0; s.pad_k = 0;
 }
-G_HD void bass_trigger(BassState& s, float velocity) {  // bass.rs:747-791
-  double time = s.t;
+G_HD void bass_trigger(BassState& s, float velocity, double time) {  // bass.rs:747-791
   s.velocity = clampf(velocity, 0.0f, 1.0f);
   s.active = 1;
   s.sub_phase = s.osc_phase = s.detune_phase = 0.0;
@@ -64,9 +69,10 @@ G_HD void bass_trigger(BassState& s, float velocity) {  // bass.rs:747-791
   s.filter.ic1 = s.filter.ic2 = 0.0f;
   s.ws.drive = clampf(1.0f + s.cur[B_OVERDRIVE] * 9.0f, 1.0f, 10.0f);
 }
-G_HD void bass_event(BassState& s, const VoiceEvent& e) {
+G_HD void bass_event(BassState& s, const VoiceEvent& e, const double* tt) {
   switch (e.kind) {
-    case EV_TRIGGER: bass_trigger(s, e.value); break;
+    case EV_TRIGGER: bass_trigger(s, e.value, tt[s.k]); break;
+    case EV_SET_TIME: s.k = e.aux; break;
     case EV_SET_TARGET: if (e.param < B_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;
     case EV_SNAP: for (int i = 0; i < B_NP; i++) s.cur[i] = s.tgt[i]; break;
     case EV_NOTE_FREQ: {
@@ -87,9 +93,9 @@ G_HD void bass_event(BassState& s, const VoiceEvent& e) {
     default: break;
   }
 }
-G_D float bass_tick(BassState& s, const RateCtx& rc) {  // bass.rs:793-877
-  const double now = s.t;
-  s.t = now + rc.dt;
+G_D float bass_tick(BassState& s, const double* tt, const RateCtx& rc) {  // bass.rs:793-877
+  const double now = tt[s.k];
+  s.k += 1;
 #pragma unroll
   for (int i = 0; i < B_NP; i++) smooth_tick(s.cur[i], s.tgt[i], rc.smooth15);
   if (!s.active) return 0.0f;
@@ -142,7 +148,7 @@ struct PolyState {
   PolyVoice v[6];
   uint32_t counter_lo, counter_hi;
   double last_tick_time;          // PolySynth.current_time: time of the most recent tick (poly_synth.rs:513)
-  double t;
+  uint32_t k, pad_k;
 };
 #ifdef __CUDACC__
 __constant__ double c_midi_freq[128];   // 440 * 2^((n-69)/12) in f64, filled by the host with the platform libm (music/note.rs:81-83)
@@ -160,7 +166,7 @@ G_HD void poly_init(PolyState& s, const float* cfg, float sr) {  // PolySynth::w
     tpt_init(v.filter, sr, 1000.0f, 1.0f);
     v.velocity = 1.0f; v.midi_note = 0; v.active = 0; v.order_lo = v.order_hi = 0;
   }
-  s.counter_lo = s.counter_hi = 0; s.last_tick_time = 0.0; s.t = 0.0;
+  s.counter_lo = s.counter_hi = 0; s.last_tick_time = 0.0; s.k = 0; s.pad_k = 0;
 }
 G_HD float poly_env_time(float n) { return 0.001f * gm::g_powf(5000.0f, n); }
 G_D void poly_trigger_note(PolyState& s, uint32_t note, float velocity) {  // :309-342
@@ -189,6 +195,7 @@ G_D void poly_trigger_note(PolyState& s, uint32_t note, float velocity) {  // :3
 }
 G_D void poly_event(PolyState& s, const VoiceEvent& e) {
   switch (e.kind) {
+    case EV_SET_TIME: s.k = e.aux; break;
     case EV_POLY_NOTE: poly_trigger_note(s, e.param, e.value); break;
     case EV_POLY_RELEASE: { double t = s.last_tick_time; for (int k = 0; k < 6; k++) if (s.v[k].active) { env_release(s.v[k].amp_env, t); env_release(s.v[k].flt_env, t); } } break;
     case EV_SET_TARGET: if (e.param < P_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;
@@ -196,9 +203,9 @@ G_D void poly_event(PolyState& s, const VoiceEvent& e) {
     default: break;
   }
 }
-G_D float poly_tick(PolyState& s, const RateCtx& rc) {  // :437-525
-  const double now = s.t;
-  s.t = now + rc.dt;
+G_D float poly_tick(PolyState& s, const double* tt, const RateCtx& rc) {  // :437-525
+  const double now = tt[s.k];
+  s.k += 1;
   s.last_tick_time = now;
 #pragma unroll
   for (int i = 0; i < P_NP; i++) smooth_tick(s.cur[i], s.tgt[i], rc.smooth15);
@@ -252,7 +259,7 @@ struct GranState {
   WShaper drive;
   uint32_t buf_lo, buf_hi, buf_len;   // device pointer to the (shared, read-only) source buffer
   float buf_sr;
-  double t;
+  uint32_t k, pad_k;
 };
 G_HD void gran_init(GranState& s, float sr) {  // Granulator::with_config :332-352 with GranulatorConfig::default :188-205
   const float D[12] = {0.5f, 0.16f, 0.12f, 0.5f, 0.35f, 0.25f, 0.0f, 0.35f, 0.8f, 0.0f, 0.0f, 0.0f};
@@ -261,10 +268,12 @@ G_HD void gran_init(GranState& s, float sr) {  // Granulator::with_config :332-3
   s.gc_cur = s.gc_tgt = 1.0f;
   s.cloud_active = 0; s.cloud_end = 0.0; s.next_grain = 0.0; s.velocity = 1.0f; s.rng = 0x1234abcdu;
   ws_init(s.drive, 4.0f, 0.0f);
-  s.buf_lo = s.buf_hi = 0; s.buf_len = 0; s.buf_sr = 44100.0f; s.t = 0.0;
+  s.buf_lo = s.buf_hi = 0; s.buf_len = 0; s.buf_sr = 44100.0f; s.k = 0; s.pad_k = 0;
   (void)sr;
 }
 G_HD float gran_next_f32(GranState& s) { uint32_t x = s.rng; x ^= x << 13; x ^= x >> 17; x ^= x << 5; s.rng = x; return (float)x / 4294967296.0f; }
+G_HD int imax(int a, int b) { return a > b ? a : b; }
+G_HD int imin(int a, int b) { return a < b ? a : b; }
 G_D float gran_sample(const float* buf, uint32_t len, float pos) {  // SampleBuffer::sample_interpolated :161-177
   if (len == 1) return buf[0];
   float last = (float)len - 1.0f;
@@ -272,8 +281,8 @@ G_D float gran_sample(const float* buf, uint32_t len, float pos) {  // SampleBuf
   int idx = (int)floorf(pos);
   float frac = pos - (float)idx;
   int lasti = (int)len - 1;
-  float p0 = __ldg(buf + max(0, min(lasti, idx - 1))), p1 = __ldg(buf + max(0, min(lasti, idx)));
-  float p2 = __ldg(buf + max(0, min(lasti, idx + 1))), p3 = __ldg(buf + max(0, min(lasti, idx + 2)));
+  float p0 = G_LDG(buf + imax(0, imin(lasti, idx - 1))), p1 = G_LDG(buf + imax(0, imin(lasti, idx)));
+  float p2 = G_LDG(buf + imax(0, imin(lasti, idx + 1))), p3 = G_LDG(buf + imax(0, imin(lasti, idx + 2)));
   float a0 = -0.5f * p0 + 1.5f * p1 - 1.5f * p2 + 0.5f * p3;
   float a1 = p0 - 2.5f * p1 + 2.0f * p2 - 0.5f * p3;
   float a2 = -0.5f * p0 + 0.5f * p2;
@@ -325,20 +334,21 @@ G_D void gran_spawn(GranState& s, float sr) {  // :546-620
   g.active = 1; g.source_pos = source_pos; g.age = 0.0f; g.duration = duration; g.speed = speed; g.direction = direction;
   g.window_shape = wshape; g.velocity = s.velocity * amp_factor; g.release_samples = 0.0f; g.release_total = 0.0f;
 }
-G_D void gran_event(GranState& s, const VoiceEvent& e) {
+G_D void gran_event(GranState& s, const VoiceEvent& e, const double* tt) {
   switch (e.kind) {
+    case EV_SET_TIME: s.k = e.aux; break;
     case EV_TRIGGER: {  // :722-728 (cloud length from the TARGET of cloud_duration)
       s.velocity = clampf(e.value, 0.0f, 1.0f);
       s.cloud_active = 1;
       float c = clampf(s.tgt[G_CLOUD], 0.0f, 1.0f);
-      s.cloud_end = s.t + (double)(50.0f + c * c * (8000.0f - 50.0f)) * 0.001;
-      s.next_grain = s.t;
+      s.cloud_end = tt[s.k] + (double)(50.0f + c * c * (8000.0f - 50.0f)) * 0.001;
+      s.next_grain = tt[s.k];
     } break;
     case EV_SET_TARGET: if (e.param < G_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;
     case EV_SNAP: for (int i = 0; i < G_NP; i++) s.cur[i] = s.tgt[i]; s.gc_cur = s.gc_tgt; break;
     case EV_GRAN_SEED: s.rng = e.aux == 0 ? 0x6d2b79f5u : e.aux; break;
     case EV_GRAN_BUFFER:
-      s.buf_lo = __float_as_uint(e.value); s.buf_hi = e.aux;
+      s.buf_lo = gm::asuint(e.value); s.buf_hi = e.aux;
       for (int i = 0; i < 80; i++) s.grains[i].active = 0;
       s.cloud_active = 0;
       break;
@@ -346,9 +356,9 @@ G_D void gran_event(GranState& s, const VoiceEvent& e) {
     default: break;
   }
 }
-G_D float gran_tick(GranState& s, const RateCtx& rc) {  // :730-742
-  const double now = s.t;
-  s.t = now + rc.dt;
+G_D float gran_tick(GranState& s, const double* tt, const RateCtx& rc) {  // :730-742
+  const double now = tt[s.k];
+  s.k += 1;
 #pragma unroll
   for (int i = 0; i < G_NP; i++) smooth_tick(s.cur[i], s.tgt[i], rc.smooth15);
   const float sr = rc.sr;
@@ -405,12 +415,5 @@ G_D float gran_tick(GranState& s, const RateCtx& rc) {  // :730-742
   float driven = ws_process(s.drive, raw);
   return driven * s.cur[G_VOLUME];
 }
-
-struct BassV { using State = BassState; static __device__ __forceinline__ float tick(State& s, const RateCtx& rc) { return bass_tick(s, rc); }
-               static __device__ __forceinline__ void event(State& s, const VoiceEvent& e, const RateCtx&) { bass_event(s, e); } };
-struct PolyV { using State = PolyState; static __device__ __forceinline__ float tick(State& s, const RateCtx& rc) { return poly_tick(s, rc); }
-               static __device__ __forceinline__ void event(State& s, const VoiceEvent& e, const RateCtx&) { poly_event(s, e); } };
-struct GranV { using State = GranState; static __device__ __forceinline__ float tick(State& s, const RateCtx& rc) { return gran_tick(s, rc); }
-               static __device__ __forceinline__ void event(State& s, const VoiceEvent& e, const RateCtx&) { gran_event(s, e); } };
 
 }  // namespace gd

@@ -1,0 +1,178 @@
+// tests/emu/emu.cpp — TEST INFRASTRUCTURE ONLY (never loaded by the product).
+// Host execution of the SAME device functions the kernels call (libgooey_b200/csrc/*.cuh compiled by g++), driven by
+// plain loops that mirror kernels.cuh: mode 0 = general path (slow_kernel: tick per sample), mode 1 = split path
+// (plan_kernel -> front_kernel -> back_kernel).  Lets the CPU test-suite check the kernel logic — span planning,
+// envelope latch search, pure front evaluation — against the oracle without a GPU.
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+#include "../../libgooey_b200/csrc/patch.h"
+#include "../../libgooey_b200/csrc/halfband_design.h"
+
+namespace gd {
+float g_hb_host[8];
+double g_midi_freq_host[128];
+}
+using namespace gd;
+
+static std::vector<double> make_clock(float sr, size_t n) {
+  std::vector<double> t(n);
+  double dt = 1.0 / (double)sr, x = 0.0;
+  for (size_t i = 0; i < n; i++) { t[i] = x; x += dt; }
+  return t;
+}
+
+struct KickE { using State = KickState; using Span = KickSpan; enum { NPL = KICK_PLANES };
+  static bool settled(const KickCtl& c) { return params_settled<K_NP>(c.cur, c.tgt); }
+  static void event(KickCtl& c, const VoiceEvent& e, const double* tt, uint32_t& r) { kick_event(c, e, tt, r); }
+  static void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx&) { uint32_t r = 0; kick_event(s.c, e, tt, r); kick_span_begin(s.a, s.c, r); }
+  static float tick(State& s, const double* tt, const RateCtx& rc) { return kick_tick(s, tt, rc); }
+  static void plan(KickCtl& c, uint32_t r, const double* tt, int ja, int jb, Span& sp) { kick_plan(c, r, tt, ja, jb, sp); }
+  static int front_end(const Span& sp) { return sp.j_act; }
+  static void front(const Span& sp, double now, uint32_t, float sr, float* o) { KickFront f = kick_front(sp.c, sp.d, now, sr); o[0] = f.p1; o[1] = f.raw_click; o[2] = f.ne; o[3] = f.amp; }
+  static void span_begin(KickAud& a, const Span& sp, float) { kick_span_begin(a, sp.c, sp.resets); }
+  static float back(KickAud& a, const Span& sp, int j, const float* p, const RateCtx& rc) {
+    if (j >= sp.j_act) return 0.0f;
+    KickFront f; f.p1 = p[0]; f.raw_click = p[1]; f.ne = p[2]; f.amp = p[3];
+    return kick_back(a, sp.d, f, rc); } };
+struct SnareE { using State = SnareState; using Span = SnareSpan; enum { NPL = SNARE_PLANES };
+  static bool settled(const SnareCtl& c) { return params_settled<S_NP>(c.cur, c.tgt); }
+  static void event(SnareCtl& c, const VoiceEvent& e, const double* tt, uint32_t& r) { snare_event(c, e, tt, r); }
+  static void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx&) { uint32_t r = 0; snare_event(s.c, e, tt, r); snare_span_begin(s.a, s.c, r); }
+  static float tick(State& s, const double* tt, const RateCtx& rc) { return snare_tick(s, tt, rc); }
+  static void plan(SnareCtl& c, uint32_t r, const double* tt, int ja, int jb, Span& sp) { snare_plan(c, r, tt, ja, jb, sp); }
+  static int front_end(const Span& sp) { return sp.j_act; }
+  static void front(const Span& sp, double now, uint32_t, float sr, float* o) { SnareFront f = snare_front(sp.c, sp.d, now, sr); o[0] = f.tonal_out; o[1] = f.raw_noise; o[2] = f.cne; o[3] = f.crack_out; o[4] = f.amp; }
+  static void span_begin(SnareAud& a, const Span& sp, float) { snare_span_begin(a, sp.c, sp.resets); }
+  static float back(SnareAud& a, const Span& sp, int j, const float* p, const RateCtx& rc) {
+    if (j >= sp.j_act) return 0.0f;
+    SnareFront f; f.tonal_out = p[0]; f.raw_noise = p[1]; f.cne = p[2]; f.crack_out = p[3]; f.amp = p[4];
+    return snare_back(a, sp.d, f, rc); } };
+struct HatE { using State = HatState; using Span = HatSpan; enum { NPL = HAT_PLANES };
+  static bool settled(const HatCtl& c) { return params_settled<H_NP>(c.cur, c.tgt); }
+  static void event(HatCtl& c, const VoiceEvent& e, const double* tt, uint32_t& r) { hat_event(c, e, tt, r); }
+  static void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx&) { uint32_t r = 0; hat_event(s.c, e, tt, r); hat_span_begin(s.a, s.c, r); }
+  static float tick(State& s, const double* tt, const RateCtx& rc) { return hat_tick(s, tt, rc); }
+  static void plan(HatCtl& c, uint32_t r, const double* tt, int ja, int jb, Span& sp) { hat_plan(c, r, tt, ja, jb, sp); }
+  static int front_end(const Span& sp) { return sp.j_env < sp.j1 ? sp.j_env : sp.j1; }
+  static void front(const Span& sp, double now, uint32_t, float sr, float* o) { o[0] = hat_front(sp.c, sp.d, now, sr).env; }
+  static void span_begin(HatAud& a, const Span& sp, float) { hat_span_begin(a, sp.c, sp.resets); }
+  static float back(HatAud& a, const Span& sp, int j, const float* p, const RateCtx& rc) {
+    if (!a.active) return 0.0f;
+    HatFront f; f.env = j < sp.j_env ? p[0] : sp.env_final;
+    return hat_back(a, sp.d, f, j >= sp.j_env, rc); } };
+struct TomE { using State = TomState; using Span = TomSpan; enum { NPL = TOM_PLANES };
+  static bool settled(const TomCtl&) { return true; }
+  static void event(TomCtl& c, const VoiceEvent& e, const double* tt, uint32_t& r) { tom_event(c, e, tt, r); }
+  static void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx& rc) {
+    uint32_t r = 0; tom_event(s.c, e, tt, r); tom_span_begin(s.a, s.c.mem_q_scale, s.c.mem_gain_scale, s.c.mem_dirty, r, rc.sr); s.c.mem_dirty = 0; }
+  static float tick(State& s, const double* tt, const RateCtx& rc) { return tom_tick(s, tt, rc); }
+  static void plan(TomCtl& c, uint32_t r, const double* tt, int ja, int jb, Span& sp) { tom_plan(c, r, tt, ja, jb, sp); }
+  static int front_end(const Span& sp) { return sp.d.membrane > 0.0f ? sp.j1 : (sp.j_env < sp.j1 ? sp.j_env + 1 : sp.j1); }
+  static void front(const Span& sp, double now, uint32_t k, float, float* o) { TomFront f = tom_front(sp.c, sp.d, now, k); o[0] = f.env; o[1] = f.noise; o[2] = f.rnd; }
+  static void span_begin(TomAud& a, const Span& sp, float sr) { tom_span_begin(a, sp.mem_q_scale, sp.mem_gain_scale, sp.mem_dirty, sp.resets, sr); }
+  static float back(TomAud& a, const Span& sp, int j, const float* p, const RateCtx& rc) {
+    if (!a.active) return 0.0f;
+    TomFront f; f.env = j < sp.j_env ? p[0] : sp.env_final; f.noise = p[1]; f.rnd = p[2];
+    return tom_back(a, sp.d, f, j >= sp.j_env, rc); } };
+
+// returns 1 if the split path was taken, 0 if the voice had to use the general path
+template <class V> static int run_voice(typename V::State& st, const std::vector<VoiceEvent>& ev, const double* tt, const RateCtx& rc, int frames, int mode, float* out) {
+  using Span = typename V::Span;
+  if (mode == 1) {
+    // A
+    auto c = st.c;
+    std::vector<Span> spans;
+    size_t e = 0;
+    bool fast = true;
+    int j = 0;
+    while (fast && j < frames) {
+      uint32_t resets = 0;
+      while (e < ev.size() && ev[e].frame <= (uint32_t)j) { V::event(c, ev[e], tt, resets); e++; }
+      if (!V::settled(c)) { fast = false; break; }
+      int jn = frames;
+      if (e < ev.size() && ev[e].frame < (uint32_t)jn) jn = (int)ev[e].frame;
+      Span sp; memset(&sp, 0, sizeof sp);
+      V::plan(c, resets, tt, j, jn, sp);
+      spans.push_back(sp);
+      j = jn;
+    }
+    if (fast) {
+      st.c = c;
+      // B: planes; entries that B does not write are poisoned with NaN so that C reading them shows up
+      std::vector<float> planes((size_t)V::NPL * frames, NAN);
+      for (const Span& sp : spans)
+        for (int jj = sp.j0; jj < std::min(V::front_end(sp), sp.j1); jj++) {
+          float o[V::NPL];
+          uint32_t k = sp.kbase + (uint32_t)jj;
+          V::front(sp, tt[k], k, rc.sr, o);
+          for (int p = 0; p < V::NPL; p++) planes[(size_t)p * frames + jj] = o[p];
+        }
+      // C
+      for (const Span& sp : spans) {
+        V::span_begin(st.a, sp, rc.sr);
+        for (int jj = sp.j0; jj < sp.j1; jj++) {
+          float p[V::NPL];
+          for (int q = 0; q < V::NPL; q++) p[q] = planes[(size_t)q * frames + jj];
+          out[jj] = V::back(st.a, sp, jj, p, rc);
+        }
+      }
+      return 1;
+    }
+  }
+  size_t e = 0;
+  for (int j = 0; j < frames; j++) {
+    while (e < ev.size() && ev[e].frame <= (uint32_t)j) { V::slow_event(st, ev[e], tt, rc); e++; }
+    out[j] = V::tick(st, tt, rc);
+  }
+  return 0;
+}
+
+extern "C" {
+
+// Same event vocabulary as orc_render_voices (kind 0 trigger, 1 set_param, 2 set_param + snap).  The render is done in
+// `n_calls` consecutive calls of frames/n_calls frames (state carried) to exercise call boundaries.  took_fast[v] is
+// the number of calls of voice v that went through the split path.
+int emu_render_voices(const GooeyVoicePatch* patches, uint32_t n, float sr, uint32_t frames, uint32_t n_events,
+                      const uint32_t* ev_voice, const uint32_t* ev_frame, const uint32_t* ev_kind, const uint32_t* ev_param,
+                      const float* ev_value, float* out, int mode, int n_calls, int* took_fast) {
+  design_halfband8(g_hb_host);
+  const RateCtx rc = make_rate_ctx(sr);
+  std::vector<double> clock = make_clock(sr, (size_t)frames + 2);
+  const double* tt = clock.data();
+  if (n_calls < 1) n_calls = 1;
+  for (uint32_t v = 0; v < n; v++) {
+    std::vector<VoiceEvent> all;
+    for (uint32_t e = 0; e < n_events; e++) {
+      if (ev_voice[e] != v) continue;
+      auto add = [&](uint32_t kind, uint32_t p, float val) { VoiceEvent x; x.frame = ev_frame[e]; x.kind = (uint16_t)kind; x.param = (uint16_t)p; x.value = val; x.aux = 0; all.push_back(x); };
+      if (ev_kind[e] == 0) add(EV_TRIGGER, 0, ev_value[e]);
+      else { bool known = gh::ffi_param_to_events(patches[v].instrument, ev_param[e], ev_value[e], add); if (known && ev_kind[e] == 2) add(EV_SNAP, 0, 0.0f); }
+    }
+    std::stable_sort(all.begin(), all.end(), [](const VoiceEvent& a, const VoiceEvent& b) { return a.frame < b.frame; });
+    float* o = out + (size_t)v * frames;
+    int fast_calls = 0;
+    auto run_calls = [&](auto tag, auto& st) {
+      using V = decltype(tag);
+      uint32_t f0 = 0;
+      for (int c = 0; c < n_calls; c++) {
+        uint32_t f1 = c == n_calls - 1 ? frames : (uint32_t)((uint64_t)frames * (c + 1) / n_calls);
+        std::vector<VoiceEvent> ev;
+        for (auto x : all) if (x.frame >= f0 && x.frame < f1) { x.frame -= f0; ev.push_back(x); }
+        fast_calls += run_voice<V>(st, ev, tt, rc, (int)(f1 - f0), mode, o + f0);
+        f0 = f1;
+      }
+    };
+    switch (patches[v].instrument) {
+      case GOOEY_INSTRUMENT_KICK: { KickState s; gh::init_from_patch(s, patches[v], sr); run_calls(KickE{}, s); } break;
+      case GOOEY_INSTRUMENT_SNARE: { SnareState s; gh::init_from_patch(s, patches[v], sr); run_calls(SnareE{}, s); } break;
+      case GOOEY_INSTRUMENT_HIHAT: { HatState s; gh::init_from_patch(s, patches[v], sr); run_calls(HatE{}, s); } break;
+      case GOOEY_INSTRUMENT_TOM: { TomState s; gh::init_from_patch(s, patches[v], sr); run_calls(TomE{}, s); } break;
+      default: return -1;
+    }
+    if (took_fast) took_fast[v] = fast_calls;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+"""ctypes access to tests/emu/libemu.so — host execution of the device functions (TEST INFRASTRUCTURE ONLY).
+
+The kernels in libgooey_b200/csrc/kernels.cuh are thin index wrappers around __host__ __device__ functions; this
+library compiles those same functions with g++ and drives them with loops that mirror the kernels, so that the CPU
+suite can check planner/front/back logic against the oracle.  It is never loaded by the product package.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SRC = os.path.join(ROOT, "tests", "emu", "emu.cpp")
+_SO = os.path.join(ROOT, "tests", "emu", "libemu.so")
+_lib = None
+
+
+def build():
+    csrc = os.path.join(ROOT, "libgooey_b200", "csrc")
+    deps = [_SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if os.path.exists(_SO) and all(os.path.getmtime(d) <= os.path.getmtime(_SO) for d in deps):
+        return
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-shared", "-o", _SO, _SRC], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def render_voices(patches, frames, triggers=(), params=(), sample_rate=44100.0, mode=1, n_calls=1):
+    """Same arguments as oracle_lib.render_voices.  mode 0 = general per-sample path, 1 = plan/front/back split.
+    Returns (audio[n, frames], fast_calls[n])."""
+    from libgooey_b200._lib import VoicePatch
+    n = len(patches)
+    arr = patches if isinstance(patches, ctypes.Array) else (VoicePatch * n)(*patches)
+    ev = [(v, f, 0, 0, vel) for (v, f, vel) in triggers] + [(v, f, 2 if s else 1, p, x) for (v, f, p, x, s) in params]
+    ev.sort(key=lambda e: (e[0], e[1]))
+    m = len(ev)
+    ev_v = np.array([e[0] for e in ev], np.uint32)
+    ev_f = np.array([e[1] for e in ev], np.uint32)
+    ev_k = np.array([e[2] for e in ev], np.uint32)
+    ev_p = np.array([e[3] for e in ev], np.uint32)
+    ev_x = np.array([e[4] for e in ev], np.float32)
+    out = np.zeros((n, frames), np.float32)
+    fast = np.zeros(n, np.int32)
+    u32, f32 = ctypes.c_uint32, ctypes.c_float
+    rc = lib().emu_render_voices(arr, n, f32(sample_rate), frames, m, _p(ev_v, u32), _p(ev_f, u32), _p(ev_k, u32), _p(ev_p, u32),
+                                 _p(ev_x, f32), _p(out, f32), int(mode), int(n_calls), _p(fast, ctypes.c_int))
+    assert rc == 0
+    return out, fast

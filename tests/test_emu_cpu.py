@@ -1,0 +1,56 @@
+"""CPU checks of the kernel LOGIC: the device functions of libgooey_b200/csrc compiled for the host (tests/emu) and
+driven exactly as the kernels drive them, against the oracle.  On the host both sides go through the same libm, so
+the comparison is bit-exact; the GPU parity tests (test_voices_gpu.py) allow the 1e-5 of BASELINE.json."""
+import numpy as np
+import pytest
+
+from libgooey_b200 import voices as V
+import emu_lib as E
+import oracle_lib as O
+from workloads import drum_sweep_patches
+
+
+@pytest.mark.parametrize("exact_tier", [True, False])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_drum_sweep_bit_exact(exact_tier, mode):
+    patches, vel, kinds = drum_sweep_patches(48, seed=0x600E7, exact_tier=exact_tier)
+    trig = [(i, 0, float(vel[i])) for i in range(len(patches))]
+    want = O.render_voices(patches, 16384, triggers=trig, threads=8)
+    got, fast = E.render_voices(patches, 16384, triggers=trig, mode=mode)
+    assert fast.sum() == (len(patches) if mode else 0)
+    assert np.array_equal(got, want)
+
+
+def _kit():
+    return [V.patch(V.KICK, V.KICK_PRESETS["punch"]), V.patch(V.SNARE, V.SNARE_PRESETS["loose"]),
+            V.patch(V.HIHAT, V.HIHAT_PRESETS["loose"]), V.patch(V.TOM, V.TOM_PRESETS["ring"], aux=1),
+            V.patch(V.KICK, V.KICK_PRESETS["dirt"]), V.patch(V.SNARE, V.SNARE_PRESETS["hiss"]),
+            V.patch(V.HIHAT, V.HIHAT_PRESETS["soft"]), V.patch(V.TOM, V.TOM_PRESETS["void"], aux=1)]
+
+
+@pytest.mark.parametrize("n_calls", [1, 3, 7])
+def test_retrigger_snapped_edits_split_path(n_calls):
+    patches = _kit()
+    n = len(patches)
+    trig = [(i, 0, 0.5 + 0.05 * i) for i in range(n)]
+    for i in range(n):
+        for f in (5513, 11026, 30000, 30001, 52000):
+            trig.append((i, f, 0.6))
+    params = [(i, 9000, 4 if i % 4 == 0 else 1, 0.5, True) for i in range(n)] + [(3, 9000, 6, 0.9, True), (7, 12000, 5, 0.0, True)]
+    want = O.render_voices(patches, 60000, triggers=trig, params=params)
+    got, fast = E.render_voices(patches, 60000, triggers=trig, params=params, mode=1, n_calls=n_calls)
+    assert (fast == n_calls).all()          # every call planned: parameters were snapped
+    assert np.array_equal(got, want)
+
+
+def test_gliding_parameters_fall_back_to_general_path_and_recover():
+    patches = _kit()
+    n = len(patches)
+    trig = [(i, 0, 1.0) for i in range(n)] + [(i, 40000, 0.7) for i in range(n)]
+    params = [(i, 3000, 0, 0.8, False) for i in range(n)]   # unsnapped edit: the smoother glides for ~150 ms
+    want = O.render_voices(patches, 60000, triggers=trig, params=params)
+    got, fast = E.render_voices(patches, 60000, triggers=trig, params=params, mode=1, n_calls=4)
+    smoothed = np.array([p.instrument != V.TOM for p in patches])
+    assert (fast[smoothed] == 3).all()      # the call containing the edit runs the general path, the others split
+    assert (fast[~smoothed] == 4).all()     # Tom2 parameters are not smoothed
+    assert np.array_equal(got, want)
