@@ -369,9 +369,7 @@ G_HD float biquad_process(Biquad& b, float in) {
   b.x2 = b.x1; b.x1 = in; b.y2 = b.y1; b.y1 = out;
   return fabsf(out) < 1e-15f ? 0.0f : out;
 }
-G_HD void bp_set(Biquad& b, float sr, float freq, float q, float gain) {  // biquad_bandpass.rs:73-119
-  if (fabsf(freq - b.last_freq) < 0.01f && fabsf(q - b.last_q) < 0.001f && fabsf(gain - b.last_gain) < 0.001f) return;
-  b.last_freq = freq; b.last_q = q; b.last_gain = gain;
+G_HD void bp_compute(Biquad& b, float sr, float freq, float q, float gain) {  // coefficient formulas of biquad_bandpass.rs:88-119
   float nyq = sr * 0.5f;
   freq = clampf(freq, 20.0f, nyq * 0.95f);
   q = clampf(q, 0.1f, 100.0f);
@@ -381,6 +379,14 @@ G_HD void bp_set(Biquad& b, float sr, float freq, float q, float gain) {  // biq
   float B0 = q * alpha * gain, B1 = 0.0f, B2 = -q * alpha * gain;
   float A0 = 1.0f + alpha, A1 = -2.0f * cs, A2 = 1.0f - alpha;
   b.b0 = B0 / A0; b.b1 = B1 / A0; b.b2 = B2 / A0; b.a1 = A1 / A0; b.a2 = A2 / A0;
+}
+G_HD bool bp_unchanged(const Biquad& b, float freq, float q, float gain) {  // :73-87
+  return fabsf(freq - b.last_freq) < 0.01f && fabsf(q - b.last_q) < 0.001f && fabsf(gain - b.last_gain) < 0.001f;
+}
+G_HD void bp_set(Biquad& b, float sr, float freq, float q, float gain) {  // biquad_bandpass.rs:73-119
+  if (bp_unchanged(b, freq, q, gain)) return;
+  b.last_freq = freq; b.last_q = q; b.last_gain = gain;
+  bp_compute(b, sr, freq, q, gain);
 }
 G_HD void bp_init(Biquad& b, float sr) { b.last_freq = b.last_q = b.last_gain = -1.0f; biquad_reset(b); bp_set(b, sr, 1000.0f, 1.0f, 1.0f); }
 G_HD void hp_set(Biquad& b, float sr, float freq, float q) {  // biquad_highpass.rs:68-96

@@ -25,13 +25,13 @@ constexpr int TILE = 32;
 template <class S> __device__ __forceinline__ void load_words(S& s, const uint32_t* base, int slot, int n_pad, int w0) {
   constexpr int W = sizeof(S) / 4;
   uint32_t* w = reinterpret_cast<uint32_t*>(&s);
-#pragma unroll 8
+#pragma unroll
   for (int i = 0; i < W; i++) w[i] = base[(size_t)(w0 + i) * n_pad + slot];
 }
 template <class S> __device__ __forceinline__ void store_words(const S& s, uint32_t* base, int slot, int n_pad, int w0) {
   constexpr int W = sizeof(S) / 4;
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
-#pragma unroll 8
+#pragma unroll
   for (int i = 0; i < W; i++) base[(size_t)(w0 + i) * n_pad + slot] = w[i];
 }
 
@@ -54,6 +54,7 @@ struct KickV {
   static __device__ __forceinline__ void span_begin(Aud& a, const Span& sp, Run& r, float) { kick_span_begin(a, sp.c, sp.resets); r.d = sp.d; r.j_act = sp.j_act; }
   static __device__ __forceinline__ void span_resume(const Span& sp, Run& r) { r.d = sp.d; r.j_act = sp.j_act; }
   static __device__ __forceinline__ bool wants_planes(const Aud&, const Run& r, int j) { return j < r.j_act; }
+  static __device__ __forceinline__ bool is_active(const Aud&, const Run& r, int j) { return j < r.j_act; }
   static __device__ __forceinline__ float back(Aud& a, const Run& r, int j, const float* p, const RateCtx& rc) {
     if (j >= r.j_act) return 0.0f;
     KickFront f; f.p1 = p[0]; f.raw_click = p[1]; f.ne = p[2]; f.amp = p[3];
@@ -78,6 +79,7 @@ struct SnareV {
   static __device__ __forceinline__ void span_begin(Aud& a, const Span& sp, Run& r, float) { snare_span_begin(a, sp.c, sp.resets); r.d = sp.d; r.j_act = sp.j_act; }
   static __device__ __forceinline__ void span_resume(const Span& sp, Run& r) { r.d = sp.d; r.j_act = sp.j_act; }
   static __device__ __forceinline__ bool wants_planes(const Aud&, const Run& r, int j) { return j < r.j_act; }
+  static __device__ __forceinline__ bool is_active(const Aud&, const Run& r, int j) { return j < r.j_act; }
   static __device__ __forceinline__ float back(Aud& a, const Run& r, int j, const float* p, const RateCtx& rc) {
     if (j >= r.j_act) return 0.0f;
     SnareFront f; f.tonal_out = p[0]; f.raw_noise = p[1]; f.cne = p[2]; f.crack_out = p[3]; f.amp = p[4];
@@ -100,6 +102,7 @@ struct HatV {
   static __device__ __forceinline__ void span_begin(Aud& a, const Span& sp, Run& r, float) { hat_span_begin(a, sp.c, sp.resets); span_resume(sp, r); }
   static __device__ __forceinline__ void span_resume(const Span& sp, Run& r) { r.d = sp.d; r.j_env = sp.j_env; r.env_final = sp.env_final; }
   static __device__ __forceinline__ bool wants_planes(const Aud& a, const Run& r, int j) { return a.active && j < r.j_env; }
+  static __device__ __forceinline__ bool is_active(const Aud& a, const Run&, int) { return a.active != 0; }
   static __device__ __forceinline__ float back(Aud& a, const Run& r, int j, const float* p, const RateCtx& rc) {
     if (!a.active) return 0.0f;
     HatFront f; f.env = j < r.j_env ? p[0] : r.env_final;
@@ -127,6 +130,7 @@ struct TomV {
   }
   static __device__ __forceinline__ void span_resume(const Span& sp, Run& r) { r.d = sp.d; r.j_env = sp.j_env; r.env_final = sp.env_final; }
   static __device__ __forceinline__ bool wants_planes(const Aud& a, const Run&, int) { return a.active != 0; }
+  static __device__ __forceinline__ bool is_active(const Aud& a, const Run&, int) { return a.active != 0; }
   static __device__ __forceinline__ float back(Aud& a, const Run& r, int j, const float* p, const RateCtx& rc) {
     if (!a.active) return 0.0f;
     TomFront f; f.env = j < r.j_env ? p[0] : r.env_final; f.noise = p[1]; f.rnd = p[2];

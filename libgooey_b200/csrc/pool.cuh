@@ -13,7 +13,7 @@
 #include <map>
 #include <mutex>
 #include "device_rt.h"
-#include "kernels.cuh"
+#include "wave.cuh"
 #include "../../include/gooey_batch.h"
 
 namespace gh {
@@ -113,6 +113,16 @@ struct ClockTable {
 };
 ClockTable& clock_table(float sr);
 
+// Which voice types have a warp-per-voice scan back-end (wave.cuh); the others use back_kernel (one voice per lane).
+template <class V> struct WaveOf { static constexpr bool has = false; using type = void; };
+template <> struct WaveOf<gd::KickV> { static constexpr bool has = true; using type = gd::KickW; };
+template <> struct WaveOf<gd::SnareV> { static constexpr bool has = true; using type = gd::SnareW; };
+template <> struct WaveOf<gd::HatV> { static constexpr bool has = true; using type = gd::HatW; };
+template <> struct WaveOf<gd::TomV> { static constexpr bool has = true; using type = gd::TomW; };
+// GOOEY_B200_BACKEND=serial forces the per-sample-order back-end (kernel C) everywhere: the A/B switch used by the
+// parity tests to compare the two back-ends.
+inline bool serial_backend() { const char* e = getenv("GOOEY_B200_BACKEND"); return e && strcmp(e, "serial") == 0; }
+
 // One type bucket of one render call.
 template <class V> struct TypeRunner {
   using State = typename V::State;
@@ -203,7 +213,10 @@ template <class V> struct TypeRunner {
         GH_CUDA(cudaGetLastError());
         GH_CUDA(cudaEventRecord(evB[b], sB));
         GH_CUDA(cudaStreamWaitEvent(sC, evB[b], 0));
-        gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one warp per CTA: the warps spread over all SMs
+        if constexpr (WaveOf<V>::has) {
+          if (!serial_backend()) gd::wave_kernel<typename WaveOf<V>::type, 4><<<(cnt + 3) / 4, 128, 0, sC>>>(L);   // one warp per voice
+          else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
+        } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());
         GH_CUDA(cudaEventRecord(evC[b], sC));
         g_launches.fetch_add(2, std::memory_order_relaxed);
