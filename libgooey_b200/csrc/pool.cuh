@@ -214,7 +214,7 @@ template <class V> struct TypeRunner {
         GH_CUDA(cudaEventRecord(evB[b], sB));
         GH_CUDA(cudaStreamWaitEvent(sC, evB[b], 0));
         if constexpr (WaveOf<V>::has) {
-          if (!serial_backend()) gd::wave_kernel<typename WaveOf<V>::type, 4><<<(cnt + 3) / 4, 128, 0, sC>>>(L);   // one warp per voice
+          if (!serial_backend()) gd::wave_kernel<typename WaveOf<V>::type, 1><<<cnt, 32, 0, sC>>>(L);   // one warp per voice
           else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
         } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());

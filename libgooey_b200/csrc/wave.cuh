@@ -190,7 +190,7 @@ __device__ __forceinline__ void lin2_scan(const Lin2& S, float& f0, float& f1, f
 }
 
 // Per-warp read-only tables in shared memory (written by span_setup, then only read).
-struct WaveScratch { Lin2 lin[3]; };
+struct WaveScratch { Lin2 lin[3]; float stash[6][32]; };
 
 // The Aud state is held in REGISTERS, replicated in every lane (all lanes compute the same state updates from
 // shuffled values), so there are no shared-memory hazards; the exact-order serial sections below are executed by all
@@ -252,6 +252,7 @@ struct KickW {
     const float p1 = p[0], raw_click = p[1], ne = p[2], amp = p[3];
     // click high-pass and the pink-noise layer: cheap recurrences, replayed in the reference's order (kick.rs:1171-1193)
     float hp_l = 0.0f, fn_l = 0.0f;
+#pragma unroll 4
     for (int n = 0; n < nl; n++) {
       const float raw = LANE_VAL(raw_click, n);
       const float hp = raw - a.click_hp;
@@ -266,6 +267,7 @@ struct KickW {
     float od = total;
     const bool finite = __all_sync(FULLMASK, isfinite(total));
     if (w.serial || (w.shaper && !finite)) {       // feedback > 0 (or a non-finite input): the reference's per-sample order
+#pragma unroll 4
       for (int n = 0; n < nl; n++) {
         const float y = fbws_process(a.ws, LANE_VAL(total, n));
         if (n == lane) od = y;
@@ -277,6 +279,7 @@ struct KickW {
       // envelope follower: the coefficient depends on a comparison with the running state -> replay
       const float rect_l = fabsf(total);
       float env_l = 0.0f;
+#pragma unroll 4
       for (int n = 0; n < nl; n++) {
         const float rect = LANE_VAL(rect_l, n);
         const float coeff = rect > ws.env ? ws.env_att : ws.env_rel;
@@ -288,6 +291,7 @@ struct KickW {
       const float compensated = shaped * comp;
       // DC blocker and the one-pole that feeds last_out (feedback_waveshaper.rs:262-271, 151-159): replay
       float out_l = 0.0f;
+#pragma unroll 4
       for (int n = 0; n < nl; n++) {
         const float c = LANE_VAL(compensated, n);
         const float out = c - ws.dc_x1 + 0.995f * ws.dc_y1;
@@ -321,16 +325,27 @@ struct SnareW {
     const float tonal_out = p[0], raw_noise = p[1], cne = p[2], crack_out = p[3], amp = p[4];
     // Chamberlin SVF: replayed exactly (it is unstable for high cutoff x low resonance, and the reference's
     // blow-up -> NaN -> Waveshaper guard -> 0 sequence has to be reproduced sample for sample)
-    float filtered = 0.0f;
-    for (int n = 0; n < nl; n++) {
-      const float y = chamb_process(a.filt, LANE_VAL(raw_noise, n), r.d.filter_type);
-      if (n == lane) filtered = y;
+    float low_l = 0.0f, band_l = 0.0f, high_l = 0.0f;
+    {
+      const float f = a.filt.f, q = a.filt.q;
+      float low = a.filt.low, band = a.filt.band;
+#pragma unroll 4
+      for (int n = 0; n < nl; n++) {
+        const float in = LANE_VAL(raw_noise, n);
+        float high = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 2; i++) { low = low + f * band; high = in - low - q * band; band = f * high + band; }
+        if (n == lane) { low_l = low; band_l = band; high_l = high; }
+      }
+      a.filt.low = low; a.filt.band = band;
     }
+    const float filtered = svf_pick(low_l, band_l, high_l, r.d.filter_type);
     const float noise_out = filtered * cne * r.d.noise_mix;
     const float total = tonal_out + noise_out + crack_out;
     float od = total;
     const bool finite = __all_sync(FULLMASK, isfinite(total));
     if (!finite) {          // waveshaper.rs:49-53 resets its oversampler on a non-finite input: per-sample order
+#pragma unroll 4
       for (int n = 0; n < nl; n++) {
         const float y = ws_process(a.ws, LANE_VAL(total, n));
         if (n == lane) od = y;
@@ -347,21 +362,24 @@ struct SnareW {
 // ---- hi-hat ----------------------------------------------------------------------------------------------
 struct HatW {
   using V = HatV;
-  struct Span2 { int dummy; };
+  struct Span2 { TptLin svf; };
   static __device__ __forceinline__ int active_end(const HatV::Run&) { return 0x7fffffff; }
-  static __device__ __forceinline__ void span_setup(HatAud& a, const HatV::Run& r, Span2&, WaveScratch&, const RateCtx& rc, int) {
+  static __device__ __forceinline__ void span_setup(HatAud& a, const HatV::Run& r, Span2& w, WaveScratch& sc, const RateCtx& rc, int lane) {
     hp_set(a.hp1, rc.sr, r.d.pitch_hz, 1.0f);
-    if (r.d.db24) hp_set(a.hp2, rc.sr, r.d.pitch_hz, 1.0f);
+    biquad_lin_init(sc.lin[0], a.hp1, lane);
+    if (r.d.db24) { hp_set(a.hp2, rc.sr, r.d.pitch_hz, 1.0f); biquad_lin_init(sc.lin[1], a.hp2, lane); }
     tpt_set(a.svf, rc.sr, r.d.tone_hz, 0.5f);
+    w.svf = tpt_lin_init(sc.lin[2], a.svf, lane);
   }
   // j = frame of lane 0.  May shorten nl when the voice deactivates inside the block (frames after it are silent).
-  static __device__ __forceinline__ float block(HatAud& a, const HatV::Run& r, const Span2&, WaveScratch&, const GeoTables&,
+  static __device__ __forceinline__ float block(HatAud& a, const HatV::Run& r, const Span2& w, WaveScratch& sc, const GeoTables&,
                                                 const float* p, int j, int& nl, const RateCtx& rc, int lane) {
     const float sr = rc.sr;
     // envelope through the asymmetric smoother and the deactivation test (hihat2.rs:489-506): replay
     const float env_l = (j + lane) < r.j_env ? p[0] : r.env_final;
     float es_l = 0.0f;
     int nv = nl;
+#pragma unroll 4
     for (int n = 0; n < nl; n++) {
       const float e = LANE_VAL(env_l, n);
       if (e >= a.env_smooth) a.env_smooth = e; else a.env_smooth += rc.asym_down * (e - a.env_smooth);
@@ -372,6 +390,7 @@ struct HatW {
     // noise and the two phase accumulators: replay
     float noise = 0.0f, mph = 0.0f, nph = 0.0f;
     const float inc_mod = fmaxf(r.d.pitch_hz * 0.1f, 0.0f) / sr, inc_main = fmaxf(r.d.pitch_hz, 0.0f) / sr;
+#pragma unroll 4
     for (int n = 0; n < nv; n++) {
       float x;
       if (r.d.pink_on) x = pink_tick(a.pink, rc.pink);
@@ -385,18 +404,17 @@ struct HatW {
     const float mod_out = gm::g_sinf(2.0f * PI_F * ph);
     ph = nph + mod_out * 0.75f; ph -= floorf(ph);
     const float main_out = gm::g_sinf(2.0f * PI_F * ph);
-    // two RBJ high-passes, envelope, TPT high-pass: replay (about 30 flops per frame)
-    float o_l = 0.0f;
-    const float g = r.d.vel035;
-    for (int n = 0; n < nv; n++) {
-      float filtered = biquad_process(a.hp1, LANE_VAL(main_out, n));
-      if (r.d.db24) filtered = biquad_process(a.hp2, filtered) * 0.8f;
-      const float out = filtered * LANE_VAL(es_l, n) * g * 0.35f;
-      float lo, bd, hi;
-      tpt_process(a.svf, out, lo, bd, hi);
-      if (n == lane) o_l = hi * r.d.volume;
-    }
-    return o_l;
+    // two RBJ high-passes (Q = 1), envelope, TPT high-pass (Q = 0.5): well damped LTI sections -> 2x2 scans
+    const int last = nv - 1;
+    float filtered = biquad_scan(sc.lin[0], a.hp1, main_out, lane, last);
+    if (r.d.db24) filtered = biquad_scan(sc.lin[1], a.hp2, filtered, lane, last) * 0.8f;
+    const float out = filtered * es_l * r.d.vel035 * 0.35f;
+    float ic1p, ic2p;
+    tpt_scan(sc.lin[2], w.svf, a.svf, out, ic1p, ic2p, lane, last);
+    const float v1 = (a.svf.g * (out - ic2p) + ic1p) * a.svf.h;
+    const float v2 = ic2p + a.svf.g * v1;
+    const float hi = out - (a.svf.r * v1 + v2);
+    return hi * r.d.volume;
   }
 };
 
@@ -406,7 +424,7 @@ struct TomW {
   struct Span2 { int dummy; };
   static __device__ __forceinline__ int active_end(const TomV::Run&) { return 0x7fffffff; }
   static __device__ __forceinline__ void span_setup(TomAud&, const TomV::Run&, Span2&, WaveScratch&, const RateCtx&, int) {}
-  static __device__ __forceinline__ float block(TomAud& a, const TomV::Run& r, const Span2&, WaveScratch&, const GeoTables&,
+  static __device__ __forceinline__ float block(TomAud& a, const TomV::Run& r, const Span2&, WaveScratch& sc, const GeoTables&,
                                                 const float* p, int j, int& nl, const RateCtx& rc, int lane) {
     const TomDer& d = r.d;
     const float sr = rc.sr;
@@ -426,6 +444,7 @@ struct TomW {
       // the ringing tail (membrane) is gated by its own level: the reference's per-sample order, replayed
       float y_l = 0.0f;
       int nv = nl;
+#pragma unroll 4
       for (int n = 0; n < nl; n++) {
         TomFront f; f.env = LANE_VAL(env_l, n); f.noise = LANE_VAL(noise_l, n); f.rnd = LANE_VAL(rnd_l, n);
         const float y = tom_back(a, d, f, (j + n) >= r.j_env, rc);
@@ -450,19 +469,22 @@ struct TomW {
       a.click_pos = min(64u, a.click_pos + (uint32_t)nv);
       if (a.click_pos >= 64u) a.click_playing = 0;
     }
-    // phase accumulators and the rand~ sample-and-hold: replay (morph_osc.rs:137-202)
+    // phase accumulators and the rand~ sample-and-hold: replay (morph_osc.rs:137-202).  The per-frame increments f / sr
+    // are formed once per lane (same f32 division as phase_advance) instead of six times per replayed frame.
     float tp = 0.0f, msp = 0.0f, mtp = 0.0f, fsp = 0.0f, gsp = 0.0f, rp = 0.0f, rcur = 0.0f, rtgt = 0.0f;
+    const float inc_l = mf_l / sr, inc_fixed = 190.0f / sr, inc_rand = d.rand_freq / sr;
+#pragma unroll 4
     for (int n = 0; n < nv; n++) {
-      const float mf = LANE_VAL(mf_l, n), rnd = LANE_VAL(rnd_l, n);
+      const float inc = LANE_VAL(inc_l, n), rnd = LANE_VAL(rnd_l, n);
       if (n == lane) { tp = a.tri_phase; msp = a.main_sine_phase; mtp = a.mtri_phase; fsp = a.fixed_sine_phase; gsp = a.gated_sine_phase; }
-      phase_advance(a.tri_phase, mf, sr);
-      phase_advance(a.main_sine_phase, mf, sr);
-      phase_advance(a.mtri_phase, mf, sr);
-      phase_advance(a.fixed_sine_phase, 190.0f, sr);
+      a.tri_phase += inc; if (a.tri_phase >= 1.0f) a.tri_phase -= 1.0f;
+      a.main_sine_phase += inc; if (a.main_sine_phase >= 1.0f) a.main_sine_phase -= 1.0f;
+      a.mtri_phase += inc; if (a.mtri_phase >= 1.0f) a.mtri_phase -= 1.0f;
+      a.fixed_sine_phase += inc_fixed; if (a.fixed_sine_phase >= 1.0f) a.fixed_sine_phase -= 1.0f;
       const float prev = a.rand_phase;
-      phase_advance(a.rand_phase, d.rand_freq, sr);
+      a.rand_phase += inc_rand; if (a.rand_phase >= 1.0f) a.rand_phase -= 1.0f;
       if (a.rand_phase < prev) { a.rand_current = a.rand_target; a.rand_target = rnd; }
-      phase_advance(a.gated_sine_phase, mf, sr);
+      a.gated_sine_phase += inc; if (a.gated_sine_phase >= 1.0f) a.gated_sine_phase -= 1.0f;
       if (n == lane) { rp = a.rand_phase; rcur = a.rand_current; rtgt = a.rand_target; }
     }
     const float click_out = click * 1.1f;
@@ -483,6 +505,7 @@ struct TomW {
     Biquad spec;
     bp_compute(spec, sr, ff_l, d.fq, 1.1f);
     float filtered = 0.0f;
+#pragma unroll 4
     for (int n = 0; n < nv; n++) {
       const float ffn = LANE_VAL(ff_l, n);
       if (!bp_unchanged(a.bp, ffn, d.fq, 1.1f)) {
@@ -495,17 +518,31 @@ struct TomW {
     }
     float mem_out = 0.0f;
     if (d.membrane > 0.0f) {  // MembraneResonator::process (membrane_resonator.rs:189-200); main_done is false here
+      // Five fixed band-passes on the same input.  At 165-326 Hz a direct-form-I section amplifies its own f32
+      // rounding noise ~40x, so any re-association (scan) drifts 1e-4 from the reference: they are replayed in the
+      // reference's operation order — but the five independent filters run on five LANES at once (lane i owns
+      // filter i), and frame n then sums the five outputs in the reference's order.
       const float mi_l = filtered * env_l;
-      float acc_l = 0.0f;
+      Biquad mine = a.mem[4];
+      if (lane == 0) mine = a.mem[0]; else if (lane == 1) mine = a.mem[1]; else if (lane == 2) mine = a.mem[2]; else if (lane == 3) mine = a.mem[3];
+#pragma unroll 4
       for (int n = 0; n < nv; n++) {
-        const float mi = LANE_VAL(mi_l, n);
-        float acc = 0.0f;
+        const float y = biquad_process(mine, LANE_VAL(mi_l, n));
+        if (lane < 5) sc.stash[lane][n] = y;
+      }
+      __syncwarp();
+      float acc_l = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 5; i++) acc += biquad_process(a.mem[i], mi);
-        if (n == lane) acc_l = acc;
+      for (int i = 0; i < 5; i++) acc_l += sc.stash[i][lane];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        a.mem[i].x1 = LANE_VAL(mine.x1, i); a.mem[i].x2 = LANE_VAL(mine.x2, i);
+        a.mem[i].y1 = LANE_VAL(mine.y1, i); a.mem[i].y2 = LANE_VAL(mine.y2, i);
       }
       const float clipped = gm::g_tanhf(acc_l);
       const float ac = fabsf(clipped);
+#pragma unroll 4
       for (int n = 0; n < nv; n++) a.ring_level = a.ring_level * 0.999f + LANE_VAL(ac, n) * 0.001f;
       mem_out = clipped;
     }

@@ -91,7 +91,7 @@ def test_two_renders_continue_state():
     whole = b2.render(12003)
     b2.close()
     two = np.concatenate([a1, a2], axis=1)
-    assert np.array_equal(two[1], whole[1])               # hi-hat: no scans, block boundaries do not matter
+    assert np.abs(two[1] - whole[1]).max() <= 2e-6          # hi-hat: 2x2 scans of its high-passes
     assert np.abs(two[0] - whole[0]).max() <= 2e-6          # kick: half-band scans re-associate per 32-frame block
 
 
@@ -117,5 +117,3 @@ def test_wave_backend_matches_serial_backend(monkeypatch):
         print(f"instrument {k}: max |wave - serial| = {err[np.array(kinds) == k].max():.3e}")
     assert np.isfinite(wav).all()
     assert err.max() <= 5e-6
-    assert err[np.array(kinds) == 2].max() == 0.0   # the hi-hat and tom back-ends have no scans: bit-identical
-    assert err[np.array(kinds) == 3].max() == 0.0
