@@ -1,0 +1,148 @@
+/* gooey.h — the subset of libgooey's C FFI that drives the offline bounce path, as exported by libgooey_b200.so.
+ *
+ * The reference generates its header with cbindgen at build time (build.rs:1-28) and does not check it in; this file
+ * restates, by hand, the entry points of src/ffi.rs that the bounce path needs, with the same
+ * names, argument meaning and error behaviour: setters ignore a null engine / bad index / unknown id, getters return
+ * sentinels, nothing unwinds.  Every function cites the reference definition it replaces (src/ffi.rs:LINE).
+ * Rendering happens on an NVIDIA B200; there is no CPU fallback: without a CUDA device gooey_engine_new returns NULL
+ * and gooey_b200_last_error() says why.
+ *
+ * Out of scope in this build (calls are accepted where noted): UI getters, LFO pool, preset blend,
+ * samplers, loop mixer, clip grid, MIDI/Link, saturation / compressor / lowpass / waveshaper global effects.
+ */
+#ifndef GOOEY_H
+#define GOOEY_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "gooey_batch.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct GooeyEngine GooeyEngine;
+
+/* ---- ABI constants (src/ffi.rs:1547-2007) ---- */
+#define GOOEY_OUTPUT_CHANNELS 2u              /* :2047 interleaved [L, R] */
+#define GOOEY_INSTRUMENT_COUNT 5u             /* :1853 */
+#define GOOEY_EFFECT_LOWPASS_FILTER 0u        /* :1548-1593 */
+#define GOOEY_EFFECT_DELAY 1u
+#define GOOEY_EFFECT_SATURATION 2u
+#define GOOEY_EFFECT_COMPRESSOR 3u
+#define GOOEY_EFFECT_TILT_FILTER 4u
+#define GOOEY_EFFECT_LIMITER 5u
+#define GOOEY_EFFECT_REVERB 6u
+#define GOOEY_EFFECT_WAVESHAPER 7u
+#define GOOEY_EFFECT_FEEDBACK_WAVESHAPER 8u
+#define GOOEY_EFFECT_PLATE_REVERB 9u
+#define GOOEY_DELAY_PARAM_TIMING 0u           /* :1600-1730 */
+#define GOOEY_DELAY_PARAM_FEEDBACK 1u
+#define GOOEY_DELAY_PARAM_MIX 2u
+#define GOOEY_DELAY_PARAM_FILTER_CUTOFF 3u
+#define GOOEY_DELAY_PARAM_PINGPONG 4u
+#define GOOEY_TILT_PARAM_CUTOFF 0u
+#define GOOEY_TILT_PARAM_RESONANCE 1u
+#define GOOEY_REVERB_PARAM_DECAY 0u
+#define GOOEY_REVERB_PARAM_MIX 1u
+#define GOOEY_REVERB_PARAM_DAMPING 2u
+#define GOOEY_PLATE_PARAM_DECAY 0u
+#define GOOEY_PLATE_PARAM_MIX 1u
+#define GOOEY_PLATE_PARAM_DAMPING 2u
+#define GOOEY_PLATE_PARAM_PREDELAY 3u
+#define GOOEY_PLATE_PARAM_WIDTH 4u
+#define GOOEY_PLATE_PARAM_SIZE 5u
+#define GOOEY_LIMITER_PARAM_THRESHOLD 0u
+#define GOOEY_SOURCE_DRUMKIT 0u               /* src/mixer/graph.rs:27-42 */
+#define GOOEY_SOURCE_BASS 1u
+#define GOOEY_SOURCE_POLYSYNTH 2u
+#define GOOEY_SOURCE_GRANULATOR 3u
+#define GOOEY_SOURCE_LOOPMIXER 4u
+#define GOOEY_STEP_NOTE_NONE 255u             /* :1980 */
+#define GOOEY_BASS_PRESET_ACID 0u             /* :1882-1998 */
+#define GOOEY_BASS_PRESET_SUB 1u
+#define GOOEY_BASS_PRESET_REESE 2u
+#define GOOEY_BASS_PRESET_STAB 3u
+
+/* ---- lifetime (:2024-2039) ---- */
+GooeyEngine* gooey_engine_new(float sample_rate);
+void gooey_engine_free(GooeyEngine* engine);
+/* libgooey_b200 addition: CUDA device used by engines created afterwards on this thread (default 0). */
+int gooey_b200_set_device(int device);
+
+/* ---- render / bounce (:2067-2122, :7897-7930) ---- */
+void gooey_engine_render(GooeyEngine* engine, float* buffer, uint32_t frames);
+float* gooey_engine_bounce_to_buffer(GooeyEngine* engine, uint32_t bars, uint32_t* out_length);
+void gooey_engine_free_buffer(float* buffer, uint32_t length);
+/* Batch of the two calls above over n engines (libgooey_b200 addition; SURVEY.md section 8b "what calls it"):
+ * every engine is bounced `bars` bars in ONE device pass.  out_buffers[i] receives a callee-allocated mono buffer
+ * (free with gooey_engine_free_buffer), out_lengths[i] its length.  Returns 0 or a GOOEY_E_* code. */
+int gooey_batch_bounce(GooeyEngine* const* engines, uint32_t n, uint32_t bars, float** out_buffers, uint32_t* out_lengths);
+/* Same, result left in device memory: out_dev[i * stride + frame]; all engines must share bpm (equal length).
+ * *out_frames receives the length. */
+int gooey_batch_bounce_device(GooeyEngine* const* engines, uint32_t n, uint32_t bars, float* out_dev, size_t stride, uint32_t* out_frames);
+/* Batch of gooey_engine_render: interleaved stereo, out_host[i * 2 * frames + 2 * f + ch]. */
+int gooey_batch_render(GooeyEngine* const* engines, uint32_t n, uint32_t frames, float* out_host);
+
+/* ---- errors (:2236-2284) ---- */
+bool gooey_engine_has_error(const GooeyEngine* engine);
+const char* gooey_engine_get_error_message(const GooeyEngine* engine);
+void gooey_engine_set_error_callback(GooeyEngine* engine, void* context, void (*callback)(void*, const char*));
+
+/* ---- instrument parameters, normalized 0-1 (:2623, :2767, :2689, :2835, :2907, channel :166-250) ---- */
+void gooey_engine_set_kick_param(GooeyEngine* engine, uint32_t param, float value);
+void gooey_engine_set_snare_param(GooeyEngine* engine, uint32_t param, float value);
+void gooey_engine_set_hihat_param(GooeyEngine* engine, uint32_t param, float value);
+void gooey_engine_set_tom_param(GooeyEngine* engine, uint32_t param, float value);
+void gooey_engine_set_bass_param(GooeyEngine* engine, uint32_t param, float value);
+void gooey_engine_set_channel_param(GooeyEngine* engine, uint32_t channel, uint32_t param, float value);
+void gooey_engine_load_bass_preset(GooeyEngine* engine, uint32_t preset);                        /* :2933 */
+
+/* ---- transport (:3337-3364, :3469, :3300) ---- */
+void gooey_engine_set_bpm(GooeyEngine* engine, float bpm);
+float gooey_engine_get_bpm(const GooeyEngine* engine);
+void gooey_engine_set_swing(GooeyEngine* engine, float swing);
+void gooey_engine_set_master_gain(GooeyEngine* engine, float gain);
+
+/* ---- sequencer (:3695-3708, :3864-3995, :4089, :4191, start/stop/reset) ---- */
+void gooey_engine_sequencer_set_step(GooeyEngine* engine, uint32_t step, bool enabled);        /* kick only */
+void gooey_engine_sequencer_set_instrument_step(GooeyEngine* engine, uint32_t instrument, uint32_t step, bool enabled);
+void gooey_engine_sequencer_set_instrument_step_with_velocity(GooeyEngine* engine, uint32_t instrument, uint32_t step, bool enabled, float velocity);
+void gooey_engine_sequencer_set_instrument_step_settings(GooeyEngine* engine, uint32_t instrument, uint32_t step, bool enabled,
+                                                         bool set_velocity, float velocity, bool set_blend, float blend_x, float blend_y,
+                                                         bool set_note, uint8_t midi_note);
+void gooey_engine_sequencer_set_instrument_step_note(GooeyEngine* engine, uint32_t instrument, uint32_t step, uint8_t midi_note);
+void gooey_engine_sequencer_set_instrument_pattern(GooeyEngine* engine, uint32_t instrument, const bool* pattern16);
+void gooey_engine_sequencer_start(GooeyEngine* engine);
+void gooey_engine_sequencer_stop(GooeyEngine* engine);
+void gooey_engine_sequencer_reset(GooeyEngine* engine);
+
+/* ---- voice strips (:5036-5210) and manual triggers (:2518-2552; latched, fire at frame 0 of the next render) ---- */
+void gooey_engine_set_instrument_gain(GooeyEngine* engine, uint32_t instrument, float gain);
+void gooey_engine_set_instrument_pan(GooeyEngine* engine, uint32_t instrument, float pan);
+void gooey_engine_set_instrument_mute(GooeyEngine* engine, uint32_t instrument, bool muted);
+void gooey_engine_set_instrument_solo(GooeyEngine* engine, uint32_t instrument, bool soloed);
+void gooey_engine_trigger_instrument(GooeyEngine* engine, uint32_t instrument);
+void gooey_engine_trigger_instrument_with_velocity(GooeyEngine* engine, uint32_t instrument, float velocity);
+
+/* ---- global effect chain (:2988-3072, :3176-3200, :4498-4595): delay, tilt, spring reverb, plate reverb, limiter ---- */
+void gooey_engine_set_global_effect_param(GooeyEngine* engine, uint32_t effect, uint32_t param, float value);
+void gooey_engine_set_global_effect_enabled(GooeyEngine* engine, uint32_t effect, bool enabled);
+bool gooey_engine_set_effect_order(GooeyEngine* engine, const uint32_t* ids, uint32_t len);
+
+/* ---- mixer graph (:6324-6674) ---- */
+int32_t gooey_engine_mixer_add_track(GooeyEngine* engine, const char* name);
+uint32_t gooey_engine_mixer_get_track_count(const GooeyEngine* engine);
+bool gooey_engine_mixer_route_source(GooeyEngine* engine, uint32_t source, uint32_t track);
+void gooey_engine_mixer_set_track_gain(GooeyEngine* engine, uint32_t track, float gain);
+void gooey_engine_mixer_set_track_pan(GooeyEngine* engine, uint32_t track, float pan);
+void gooey_engine_mixer_set_track_mute(GooeyEngine* engine, uint32_t track, bool muted);
+void gooey_engine_mixer_set_track_solo(GooeyEngine* engine, uint32_t track, bool soloed);
+int32_t gooey_engine_track_effect_add(GooeyEngine* engine, uint32_t track, uint32_t effect_id);
+void gooey_engine_track_effect_set_param(GooeyEngine* engine, uint32_t track, uint32_t slot, uint32_t param, float value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOOEY_H */

@@ -75,6 +75,12 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
 /* Same, leaving the result in device memory: out_dev[v * stride + i], stride >= frames. */
 int gooey_voice_batch_render_device(GooeyVoiceBatch* b, uint32_t frames, float* out_dev, size_t stride);
 
+/* Host-only (no device needed): frames and velocities at which a bounce of an engine with this tempo, swing and step
+ * pattern fires its triggers — the schedule the host resolves into kernel event tables (reference:
+ * Sequencer::tick_with_settings, src/engine/sequencer.rs:883-952).  Returns the number of triggers (may exceed capacity). */
+uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing, const uint8_t* enabled, const float* velocity, uint32_t steps,
+                                       uint32_t frames, uint32_t* out_frames, float* out_velocity, uint32_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

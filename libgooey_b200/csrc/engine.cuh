@@ -1,0 +1,394 @@
+// engine.cuh — host side of the engine-level path: the reference's GooeyEngine (src/ffi.rs:670-1541) restated as a
+// thin host object whose audio state lives in device pools, plus the batch renderer that drives thousands of them in
+// one pass: host-resolved sequencer schedule -> per-voice event tables -> voice kernels (kernels.cuh / wave.cuh) ->
+// mix kernel (mix.cuh: strips, pan, MixerGraph, master gain, global effect chain, limiter, stereo / mono write-out).
+#pragma once
+#include <cmath>
+#include <map>
+#include <memory>
+#include "pool.cuh"
+#include "patch.h"
+#include "mix.cuh"
+
+namespace gh {
+
+// ---- engine/sequencer.rs: the 16th-note step sequencer, host side, event driven ------------------------------------
+// Identical arithmetic to Sequencer::tick_with_settings (:883-952): u64 counters, f32 step math, f32::round, the swing
+// SmoothedParam ticking once per sample while running.  Instead of ticking every sample it jumps from firing to firing;
+// the swing smoother is stepped sample by sample only while it is unsettled.
+struct SeqStep { bool enabled = false; float velocity = 1.0f; bool has_note = false; uint8_t note = 0; bool has_blend = false; float bx = 0, by = 0; };
+struct SeqFire { uint32_t frame; float velocity; bool has_note; uint8_t note; };
+struct HostSeq {
+  float bpm = 120.0f, sr = 44100.0f, sps = 0.0f;
+  uint64_t sample_count = 0, next_trigger = 0;
+  std::vector<SeqStep> pattern;
+  size_t current_step = 0;
+  bool running = false;
+  float sw_cur = 0.5f, sw_tgt = 0.5f, sw_coeff = 1.0f;
+  static float calc_sps(float bpm, float sr) { float s16 = (60.0f / bpm) / 4.0f; return s16 * sr; }   // :583-588
+  void init(float bpm_, float sr_) { bpm = bpm_; sr = sr_; sps = calc_sps(bpm, sr); pattern.assign(16, SeqStep()); sw_coeff = gd::smooth_coeff(sr, 15.0f); }
+  void set_bpm(float b) { bpm = b; sps = calc_sps(b, sr); }
+  void set_swing(float s) { float c = gd::clampf(s, 0.0f, 1.0f); if (fabsf(sw_tgt - c) > 1e-8f) sw_tgt = c; }
+  void start() { running = true; next_trigger = sample_count; }
+  void stop() { running = false; }
+  void reset() { sample_count = 0; next_trigger = 0; current_step = 0; }
+  void swing_ticks(uint64_t n) { while (n > 0 && sw_cur != sw_tgt) { gd::smooth_tick(sw_cur, sw_tgt, sw_coeff); n--; } }
+  void run(uint32_t frames, std::vector<SeqFire>& out) {
+    uint32_t f = 0;
+    while (f < frames) {
+      if (!running || pattern.empty()) { sample_count += frames - f; return; }
+      const uint64_t wait = next_trigger > sample_count ? next_trigger - sample_count : 0;
+      if (wait >= (uint64_t)(frames - f)) { swing_ticks(frames - f); sample_count += frames - f; return; }
+      swing_ticks(wait);
+      sample_count += wait; f += (uint32_t)wait;
+      swing_ticks(1);
+      const SeqStep& st = pattern[current_step];
+      if (st.enabled) out.push_back({f, st.velocity, st.has_note, st.note});
+      current_step = (current_step + 1) % pattern.size();
+      const float swing_offset = (sw_cur - 0.5f) * 2.0f * sps;
+      const float signed_off = (current_step % 2 == 1) ? swing_offset : -swing_offset;
+      const float nx = roundf((float)next_trigger + sps + signed_off);
+      next_trigger = gd::f32_to_u64_sat(nx);
+      sample_count += 1; f += 1;
+    }
+  }
+};
+
+// ---- geometry of the delay lines at a sample rate (delay.rs:189, reverb.rs:84-96, plate_reverb.rs:236-262) ----------
+inline gd::FxGeom make_fx_geom(float sr) {
+  gd::FxGeom g;
+  memset(&g, 0, sizeof g);
+  g.delay_len = (uint32_t)gd::f32_to_u64_sat(sr * 5.0f) + 1u;
+  const float DL[6] = {131, 251, 389, 521, 617, 787}, DR[6] = {127, 263, 397, 541, 631, 797};
+  const float scale = sr / 44100.0f;
+  uint32_t off = 0;
+  for (int i = 0; i < 12; i++) {
+    const float base = i < 6 ? DL[i] : DR[i - 6];
+    g.spring_len[i] = (uint32_t)gd::f32_to_u64_sat(fmaxf(base * scale, 1.0f));
+    g.spring_off[i] = off; off += g.spring_len[i];
+  }
+  const uint32_t spring_words = off;
+  const float sr_scale = sr / 29761.0f;
+  g.plate_sr_scale = sr_scale;
+  g.plate_excursion = 16.0f * sr_scale;
+  auto fixed = [&](float base) { return (uint32_t)gd::f32_to_u64_sat(ceilf(base * sr_scale)) + 4u; };
+  auto sized = [&](float base, float head) { return (uint32_t)gd::f32_to_u64_sat(ceilf(base * 2.0f * sr_scale + head)) + 4u; };
+  auto cap4 = [](uint32_t c) { return c < 4u ? 4u : c; };
+  const float IAD[4] = {142.0f, 107.0f, 379.0f, 277.0f};
+  uint32_t caps[13];
+  caps[0] = cap4((uint32_t)gd::f32_to_u64_sat(ceilf(200.0f * 0.001f * sr)) + 8u);
+  for (int i = 0; i < 4; i++) { caps[1 + i] = cap4(fixed(IAD[i])); g.plate_in_delay[i] = fmaxf(IAD[i] * sr_scale, 1.0f); }
+  const float TL[8] = {672.0f, 4453.0f, 1800.0f, 3720.0f, 908.0f, 4217.0f, 2656.0f, 3163.0f};
+  for (int i = 0; i < 8; i++) { caps[5 + i] = cap4(sized(TL[i], (i == 0 || i == 4) ? g.plate_excursion : 0.0f)); g.plate_len[i] = TL[i] * sr_scale; }
+  off = 0;
+  for (int i = 0; i < 13; i++) { g.plate_cap[i] = caps[i]; g.plate_off[i] = off; off += caps[i]; }
+  g.plate_lfo_ia = 0.50f / sr; g.plate_lfo_ib = 0.71f / sr;
+  g.ring_words[0] = 0; g.ring_words[1] = 2u * g.delay_len; g.ring_words[2] = spring_words; g.ring_words[3] = off;
+  return g;
+}
+inline uint32_t ring_words_of(const gd::FxGeom& g, uint32_t kind) {
+  switch (kind) { case gd::FXK_DELAY: return g.ring_words[1]; case gd::FXK_SPRING: return g.ring_words[2]; case gd::FXK_PLATE: return g.ring_words[3]; default: return 0; }
+}
+
+// ---- everything resident on one device for one sample rate ---------------------------------------------------------
+struct EngineBank {
+  int device; float sr;
+  gd::RateCtx rc; gd::FxGeom geo;
+  VoiceBank voices;
+  Pool<gd::MixState> mix_pool;
+  std::vector<gd::MixCfg> cfgs;           // by mix slot (host authoritative)
+  DevBuf<gd::MixCfg> d_cfg;
+  DevBuf<float> ring[gd::MAX_FX]; uint32_t ring_words[gd::MAX_FX] = {0}; long long ring_cap = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece = nullptr;
+  DevBuf<float> d_voice_buf, d_out;
+  DevBuf<uint32_t> d_mix_slots, d_mix_ev_begin;
+  DevBuf<gd::VoiceEvent> d_mix_events;
+  std::mutex mu;
+  float last_ms = 0.0f;
+  EngineBank(int dev, float sr_) : device(dev), sr(sr_) {
+    rc = gd::make_rate_ctx(sr); geo = make_fx_geom(sr);
+    GH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    GH_CUDA(cudaEventCreate(&ev0)); GH_CUDA(cudaEventCreate(&ev1)); GH_CUDA(cudaEventCreateWithFlags(&ev_piece, cudaEventDisableTiming));
+  }
+  // makes sure arena `slot` holds `words` ring words for `cap` engine slots (content preserving)
+  void ensure_ring(int slot, uint32_t words, long long cap) {
+    if (words == 0) return;
+    if (ring[slot].p && ring_words[slot] >= words && ring_cap_of[slot] >= cap) return;
+    const uint32_t nw = std::max(words, ring_words[slot]);
+    const long long nc = std::max(cap, ring_cap_of[slot]);
+    DevBuf<float> nb;
+    nb.alloc((size_t)nw * (size_t)nc);
+    GH_CUDA(cudaMemsetAsync(nb.p, 0, (size_t)nw * (size_t)nc * 4, stream));
+    if (ring[slot].p && ring_words[slot] > 0)
+      GH_CUDA(cudaMemcpy2DAsync(nb.p, (size_t)nc * 4, ring[slot].p, (size_t)ring_cap_of[slot] * 4, (size_t)ring_cap_of[slot] * 4, ring_words[slot], cudaMemcpyDeviceToDevice, stream));
+    GH_CUDA(cudaStreamSynchronize(stream));
+    std::swap(ring[slot].p, nb.p); std::swap(ring[slot].n, nb.n);
+    ring_words[slot] = nw; ring_cap_of[slot] = nc;
+  }
+  long long ring_cap_of[gd::MAX_FX] = {0};
+};
+EngineBank& engine_bank(int device, float sr);
+
+}  // namespace gh
+
+// ---- the engine handle (opaque to C callers) --------------------------------------------------------------------------
+struct GooeyEngine {
+  gh::EngineBank* bank = nullptr;
+  float sr = 44100.0f, bpm = 120.0f, swing = 0.5f;
+  uint32_t k = 0;                       // engine clock index (current_time = tt[k])
+  struct Strip {
+    uint32_t type = 0; int slot = -1;
+    gh::HostSeq seq;
+    bool muted = false, soloed = false, trig_pending = false;
+    float trig_vel = 1.0f;
+    std::vector<gd::VoiceEvent> pending;
+  } strip[5];
+  int mix_slot = -1;
+  gd::MixCfg cfg;
+  std::vector<gd::VoiceEvent> mix_pending;
+  bool track_muted[gd::MAX_TRACKS] = {false}, track_soloed[gd::MAX_TRACKS] = {false};
+  bool seq_triggers_enabled = true;
+  bool has_error = false;
+  std::string error;
+  void (*error_cb)(void*, const char*) = nullptr; void* error_ctx = nullptr;
+  bool error_cb_fired = false;
+};
+
+namespace gh {
+
+inline void engine_fail(GooeyEngine* e, const std::string& msg) {   // sticky error + one-shot callback (ffi.rs:2236-2284)
+  if (!e) return;
+  if (!e->has_error) { e->has_error = true; e->error = msg; }
+  if (e->error_cb && !e->error_cb_fired) { e->error_cb_fired = true; e->error_cb(e->error_ctx, e->error.c_str()); }
+}
+
+inline GooeyEngine* engine_create(int device, float sr) {
+  EngineBank& B = engine_bank(device, sr);
+  std::lock_guard<std::mutex> lk(B.mu);
+  std::unique_ptr<GooeyEngine> e(new GooeyEngine);
+  e->bank = &B; e->sr = sr;
+  // default voices: kick(tight) / snare(tight) / hihat(short) / tom(Tom2::new) / bass(acid) (ffi.rs:809-954)
+  static const float KICK_TIGHT[18] = {0.22f, 0.00f, 1.00f, 0.00f, 0.12f, 0.70f, 0.01f, 0.85f, 0.64f, 1.00f, 0.07f, 0.01f, 0.02f, 0.20f, 0.00f, 0.47f, 0.12f, 0.02f};
+  static const float BASS_ACID[15] = {0.24f, 0.40f, 0.80f, 0.00f, 0.00f, 0.10f, 0.15f, 0.70f, 0.85f, 0.15f, 0.08f, 0.35f, 0.10f, 0.30f, 0.80f};
+  GooeyVoicePatch p[5];
+  memset(p, 0, sizeof p);
+  p[0].instrument = GOOEY_INSTRUMENT_KICK; memcpy(p[0].params, KICK_TIGHT, sizeof KICK_TIGHT);
+  {  // SnareConfig::tight() = SnareConfig::new(0.2, 0.4, 0.7, 0.5, 0.029, 0.3, 0.8) (snare.rs:99-132, 270-280)
+    const float d = 0.029f;
+    const float s[19] = {0.2f, 0.4f, 0.7f, 0.5f, d, 0.3f, 0.8f, d * 0.8f, 0.091f, d * 0.6f, d, 0.495f, 0.053f, 1.0f, 0.5f, 0.0f, 0.0f, 0.125f, 0.02f};
+    p[1].instrument = GOOEY_INSTRUMENT_SNARE; memcpy(p[1].params, s, sizeof s);
+  }
+  { const float h[5] = {0.76f, 0.05f, 0.00f, 1.00f, 1.0f}; p[2].instrument = GOOEY_INSTRUMENT_HIHAT; memcpy(p[2].params, h, sizeof h); }
+  p[3].instrument = GOOEY_INSTRUMENT_TOM;
+  p[4].instrument = GOOEY_INSTRUMENT_BASS; memcpy(p[4].params, BASS_ACID, sizeof BASS_ACID);
+  for (int ch = 0; ch < 5; ch++) {
+    e->strip[ch].type = p[ch].instrument;
+    e->strip[ch].slot = B.voices.create(p[ch], sr);
+    e->strip[ch].seq.init(120.0f, sr);
+  }
+  gd::MixState ms;
+  memset(&ms, 0, sizeof ms);
+  for (int c = 0; c < gd::N_VOICE_CH; c++) { ms.ch_gain[c] = {1.0f, 1.0f}; ms.ch_mute[c] = {1.0f, 1.0f}; ms.ch_pan[c] = {0.5f, 0.5f}; }
+  for (int t = 0; t < gd::MAX_TRACKS; t++) { ms.tr_gain[t] = {1.0f, 1.0f}; ms.tr_pan[t] = {0.5f, 0.5f}; ms.tr_mute[t] = {1.0f, 1.0f}; }
+  ms.master = {0.25f, 0.25f};
+  const uint32_t kinds[4] = {gd::FXK_TILT, gd::FXK_DELAY, gd::FXK_SPRING, gd::FXK_PLATE};
+  for (int s = 0; s < 4; s++) gd::fx_construct(ms.fx[s], kinds[s], false, sr, 120.0f);
+  e->mix_slot = B.mix_pool.alloc(ms);
+  gd::MixCfg& c = e->cfg;
+  memset(&c, 0, sizeof c);
+  c.n_tracks = 4;
+  const int32_t routes[7] = {0, 1, 2, 3, 3, -1, -1};
+  for (int i = 0; i < 7; i++) c.route[i] = routes[i];
+  const uint32_t order[9] = {7, 2, 0, 4, 1, 3, 8, 6, 9};   // DEFAULT_EFFECT_ORDER (ffi.rs:1583-1593)
+  for (int i = 0; i < 9; i++) c.order[i] = order[i];
+  for (int s = 0; s < gd::MAX_FX; s++) { c.fx_kind[s] = s < 4 ? kinds[s] : (uint32_t)gd::FXK_NONE; c.fx_enabled[s] = 0; }
+  c.limiter_on = 0; c.lim_th = 1.0f; c.lim_inv = 1.0f;
+  if ((int)B.cfgs.size() <= e->mix_slot) B.cfgs.resize(e->mix_slot + 1);
+  B.cfgs[e->mix_slot] = c;
+  return e.release();
+}
+
+inline void engine_destroy(GooeyEngine* e) {
+  if (!e) return;
+  EngineBank& B = *e->bank;
+  std::lock_guard<std::mutex> lk(B.mu);
+  for (int ch = 0; ch < 5; ch++) {
+    switch (e->strip[ch].type) {
+      case GOOEY_INSTRUMENT_KICK: B.voices.kicks.pool.release(e->strip[ch].slot); break;
+      case GOOEY_INSTRUMENT_SNARE: B.voices.snares.pool.release(e->strip[ch].slot); break;
+      case GOOEY_INSTRUMENT_HIHAT: B.voices.hats.pool.release(e->strip[ch].slot); break;
+      case GOOEY_INSTRUMENT_TOM: B.voices.toms.pool.release(e->strip[ch].slot); break;
+      case GOOEY_INSTRUMENT_BASS: B.voices.basses.pool.release(e->strip[ch].slot); break;
+    }
+  }
+  B.mix_pool.release(e->mix_slot);
+  delete e;
+}
+
+// note -> normalized frequency parameter of the voice (ffi.rs:1505-1518)
+inline bool note_freq_range(uint32_t type, float& mn, float& mx) {
+  if (type == GOOEY_INSTRUMENT_BASS) { mn = 30.0f; mx = 200.0f; return true; }
+  if (type == GOOEY_INSTRUMENT_KICK) { mn = 30.0f; mx = 120.0f; return true; }
+  if (type == GOOEY_INSTRUMENT_TOM) { mn = 40.0f; mx = 600.0f; return true; }
+  return false;
+}
+inline float midi_to_norm(uint8_t note, float mn, float mx) {
+  float hz = 440.0f * gm::g_powf(2.0f, ((float)note - 69.0f) / 12.0f);
+  return gd::clampf((hz - mn) / (mx - mn), 0.0f, 1.0f);
+}
+
+enum { OUT_MONO = 0, OUT_STEREO = 1 };
+
+// Renders `frames` frames of every engine of `E` (all on one bank) into out_dev: mono rows [n][stride] (the bounce
+// downmix 0.5 (l + r)) or interleaved stereo rows [n][stride >= 2 frames].  `bounce`: apply the reference's bounce
+// preamble first (ffi.rs:7840-7854): clock to 0, sequencers reset + start, strips / graph / master snapped.
+inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, int out_mode, bool bounce, float* out_dev, size_t stride) {
+  if (E.empty() || frames == 0) return;
+  EngineBank& B = *E[0]->bank;
+  std::lock_guard<std::mutex> lk(B.mu);
+  GH_CUDA(cudaSetDevice(B.device));
+  cudaStream_t st = B.stream;
+  const int n = (int)E.size();
+  const int n_lpad = pad32(n);
+  // ---- schedule resolution (host): per voice and per engine event lists over the whole call ----
+  std::vector<std::vector<gd::VoiceEvent>> vev((size_t)n * 5), mev(n);
+  uint32_t kmax = 0;
+  std::vector<SeqFire> fires;
+  for (int i = 0; i < n; i++) {
+    GooeyEngine* e = E[i];
+    if (e->bank != &B) throw std::runtime_error("engines of one batch must share device and sample rate");
+    if (bounce) {
+      e->k = 0;
+      for (auto& s : e->strip) { s.seq.reset(); s.seq.start(); }
+    }
+    if ((uint64_t)e->k + frames >= 0xffffffffull) throw std::runtime_error("engine clock index overflow");
+    kmax = std::max(kmax, e->k + frames);
+    auto& mx = mev[i];
+    mx = e->mix_pending; e->mix_pending.clear();
+    if (bounce) {
+      mx.push_back(make_event(0, gd::MX_SNAP, 0, 0.0f));       // voice strips snap to their current targets
+    }
+    // per-buffer mute / solo targets (ffi.rs:1099-1109, graph.rs update_mute_solo_targets)
+    bool any_solo = false;
+    for (auto& s : e->strip) any_solo |= s.soloed;
+    bool any_tsolo = false;
+    for (uint32_t t = 0; t < e->cfg.n_tracks; t++) any_tsolo |= e->track_soloed[t];
+    std::vector<gd::VoiceEvent> mute_ev;
+    for (int ch = 0; ch < 5; ch++) {
+      const auto& s = e->strip[ch];
+      mute_ev.push_back(make_event(0, gd::MX_SET, gd::MP_CH_MUTE + ch, s.soloed ? 1.0f : (any_solo ? 0.0f : (s.muted ? 0.0f : 1.0f))));
+    }
+    std::vector<gd::VoiceEvent> tmute_ev;
+    for (uint32_t t = 0; t < e->cfg.n_tracks; t++)
+      tmute_ev.push_back(make_event(0, gd::MX_SET, gd::MP_TR_MUTE + t, e->track_soloed[t] ? 1.0f : ((any_tsolo || e->track_muted[t]) ? 0.0f : 1.0f)));
+    if (bounce) {
+      // graph.snap_strip_params() refreshes the track mute targets and snaps; master_gain.snap(); the voice-strip
+      // mute targets are only written by render() afterwards, so they glide (ffi.rs:7846-7854, 1099-1109)
+      mx.insert(mx.end(), tmute_ev.begin(), tmute_ev.end());
+      mx.push_back(make_event(0, gd::MX_SNAP, 1, 0.0f));
+      mx.push_back(make_event(0, gd::MX_SNAP, 2, 0.0f));
+      mx.insert(mx.end(), mute_ev.begin(), mute_ev.end());
+    } else {
+      mx.insert(mx.end(), mute_ev.begin(), mute_ev.end());
+      mx.insert(mx.end(), tmute_ev.begin(), tmute_ev.end());
+    }
+    for (int ch = 0; ch < 5; ch++) {
+      auto& s = e->strip[ch];
+      auto& ev = vev[(size_t)i * 5 + ch];
+      if (bounce) ev.push_back(make_event(0, gd::EV_SET_TIME, 0, 0.0f, 0));
+      ev.insert(ev.end(), s.pending.begin(), s.pending.end());
+      s.pending.clear();
+      if (s.trig_pending) { s.trig_pending = false; ev.push_back(make_event(0, gd::EV_TRIGGER, 0, s.trig_vel)); }
+      fires.clear();
+      s.seq.run(frames, fires);
+      if (e->seq_triggers_enabled) {
+        for (const SeqFire& f : fires) {   // ffi.rs:1162-1198
+          float mn, mxf;
+          if (f.has_note) { if (note_freq_range(s.type, mn, mxf)) ev.push_back(make_event(f.frame, gd::EV_NOTE_FREQ, 0, midi_to_norm(f.note, mn, mxf))); }
+          else ev.push_back(make_event(f.frame, gd::EV_RESTORE_FREQ, 0, 0.0f));
+          ev.push_back(make_event(f.frame, gd::EV_TRIGGER, 0, f.velocity));
+        }
+      }
+    }
+  }
+  const double* tt = clock_table(B.sr).ensure(B.device, (size_t)kmax + 1, st);
+  // ---- device state: pools, configs, rings ----
+  B.mix_pool.flush(st);
+  B.d_cfg.upload(B.cfgs.data(), B.cfgs.size(), st);
+  uint32_t need_words[gd::MAX_FX] = {0};
+  for (int i = 0; i < n; i++) {
+    const gd::MixCfg& c = E[i]->cfg;
+    for (int s = 0; s < gd::MAX_FX; s++) {
+      bool used = s < 4 ? c.fx_enabled[s] != 0 : false;
+      for (uint32_t t = 0; t < c.n_tracks && !used; t++) for (uint32_t r = 0; r < c.rack_n[t]; r++) if (c.rack_slot[t][r] == s) used = true;
+      if (used) need_words[s] = std::max(need_words[s], ring_words_of(B.geo, c.fx_kind[s]));
+    }
+  }
+  // every arena shares one row pitch (the mix pool's capacity); arenas that already exist are re-laid when it grows
+  const long long ring_cap = B.mix_pool.cap;
+  for (int s = 0; s < gd::MAX_FX; s++) {
+    const uint32_t words = std::max(need_words[s], B.ring_words[s]);
+    if (words) B.ensure_ring(s, words, ring_cap);
+  }
+  std::vector<uint32_t> mix_slots(n);
+  for (int i = 0; i < n; i++) mix_slots[i] = (uint32_t)E[i]->mix_slot;
+  B.d_mix_slots.upload(mix_slots.data(), n, st);
+  // ---- pieces: bound the voice buffer (5 rows per engine) to ~2 GiB ----
+  const size_t rows = (size_t)5 * n_lpad;
+  size_t piece = ((size_t)2 << 30) / (rows * 4);
+  piece = std::min<size_t>(std::max<size_t>(piece & ~(size_t)31, 2048), 65536);
+  piece = std::min<size_t>(piece, (frames + 31) & ~31u);
+  B.d_voice_buf.alloc(rows * piece);
+  GH_CUDA(cudaEventRecord(B.ev0, st));
+  std::vector<gd::VoiceEvent> cur, mflat;
+  std::vector<uint32_t> mbegin;
+  std::vector<size_t> vpos((size_t)n * 5, 0), mpos(n, 0);
+  for (uint32_t f0 = 0; f0 < frames; f0 += (uint32_t)piece) {
+    const uint32_t nf = std::min<uint32_t>((uint32_t)piece, frames - f0);
+    B.voices.reset();
+    for (int i = 0; i < n; i++)
+      for (int ch = 0; ch < 5; ch++) {
+        auto& ev = vev[(size_t)i * 5 + ch];
+        size_t& p = vpos[(size_t)i * 5 + ch];
+        cur.clear();
+        while (p < ev.size() && ev[p].frame < f0 + nf) { gd::VoiceEvent x = ev[p++]; x.frame -= f0; cur.push_back(x); }
+        B.voices.add(E[i]->strip[ch].type, (uint32_t)E[i]->strip[ch].slot, (uint32_t)(ch * n_lpad + i), cur);
+      }
+    cudaEvent_t start = B.ev_piece;
+    GH_CUDA(cudaEventRecord(start, st));
+    // the clock index differs per engine only through e->k; voices carry their own k, the launch passes the table
+    B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_buf.p, (long long)piece);
+    mflat.clear(); mbegin.assign(1, 0);
+    for (int i = 0; i < n; i++) {
+      auto& ev = mev[i];
+      size_t& p = mpos[i];
+      while (p < ev.size() && ev[p].frame < f0 + nf) { gd::VoiceEvent x = ev[p++]; x.frame -= f0; mflat.push_back(x); }
+      mbegin.push_back((uint32_t)mflat.size());
+    }
+    if (mflat.empty()) mflat.push_back(make_event(0xffffffffu, 0xffff, 0, 0.0f));
+    B.d_mix_events.upload(mflat.data(), mflat.size(), st);
+    B.d_mix_ev_begin.upload(mbegin.data(), mbegin.size(), st);
+    gd::MixLaunch M;
+    memset(&M, 0, sizeof M);
+    M.state = B.mix_pool.d.p; M.n = n; M.state_cap = B.mix_pool.cap; M.slots = B.d_mix_slots.p; M.n_lpad = n_lpad;
+    M.cfg = B.d_cfg.p; M.events = B.d_mix_events.p; M.ev_begin = B.d_mix_ev_begin.p;
+    M.voice_buf = B.d_voice_buf.p; M.voice_stride = (long long)piece; M.chan_mask = 0x1fu;
+    for (int s = 0; s < gd::MAX_FX; s++) M.ring[s] = B.ring[s].p;
+    M.ring_cap = ring_cap;
+    M.frames = (int)nf;
+    M.out = out_dev + (out_mode == OUT_MONO ? (size_t)f0 : (size_t)2 * f0); M.out_stride = (long long)stride; M.out_mode = out_mode; M.out_rows = nullptr;
+    M.rc = B.rc; M.geo = B.geo;
+    M.center_l = gm::g_cosf(0.5f * 1.57079632679489661923f); M.center_r = gm::g_sinf(0.5f * 1.57079632679489661923f);
+    gd::mix_kernel<<<(n + 31) / 32, 32, 0, st>>>(M);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GH_CUDA(cudaGetLastError());
+  }
+  GH_CUDA(cudaEventRecord(B.ev1, st));
+  for (int i = 0; i < n; i++) {
+    E[i]->k += frames;
+    if (bounce) for (auto& s : E[i]->strip) s.seq.stop();
+  }
+}
+
+}  // namespace gh

@@ -1,0 +1,310 @@
+// engine_api.cuh — extern "C" surface of include/gooey.h over engine.cuh (reference: src/ffi.rs, cited per function in
+// the header).  Conventions follow the reference: null / out-of-range arguments are ignored, nothing throws across the
+// boundary; a device failure latches the engine's sticky error and zero-fills the output (ffi.rs:2079-2121).
+#pragma once
+#include "engine.cuh"
+#include "../../include/gooey.h"
+
+namespace gh {
+static thread_local int g_cur_device = 0;
+EngineBank& engine_bank(int device, float sr) {
+  static std::mutex mu;
+  static std::map<std::pair<int, uint32_t>, EngineBank*> banks;
+  std::lock_guard<std::mutex> lk(mu);
+  uint32_t key; memcpy(&key, &sr, 4);
+  auto it = banks.find({device, key});
+  if (it == banks.end()) it = banks.emplace(std::make_pair(device, key), new EngineBank(device, sr)).first;
+  return *it->second;
+}
+static GooeyEngine::Strip* strip_by_type(GooeyEngine* e, uint32_t type) {
+  for (auto& s : e->strip) if (s.type == type) return &s;
+  return nullptr;
+}
+static void strip_set_param(GooeyEngine::Strip* s, uint32_t param, float value) {
+  if (!s) return;
+  ffi_param_to_events(s->type, param, value, [&](uint32_t kind, uint32_t p, float v) { s->pending.push_back(make_event(0, kind, p, v)); });
+}
+static int fx_slot_of(uint32_t effect) {
+  switch (effect) { case gd::FXK_TILT: return gd::FXS_TILT; case gd::FXK_DELAY: return gd::FXS_DELAY; case gd::FXK_SPRING: return gd::FXS_SPRING; case gd::FXK_PLATE: return gd::FXS_PLATE; default: return -1; }
+}
+static void sync_cfg(GooeyEngine* e) {
+  EngineBank& B = *e->bank;
+  std::lock_guard<std::mutex> lk(B.mu);
+  B.cfgs[e->mix_slot] = e->cfg;
+}
+static uint32_t bounce_frames(const GooeyEngine* e, uint32_t bars) {   // ffi.rs:7836-7838 / bounce.rs:20-32
+  double spb = 4.0 * (60.0 / (double)e->bpm) * (double)e->sr;
+  double tot = round((double)bars * spb);
+  if (!(tot > 0.0)) return 0;
+  return tot >= 4294967295.0 ? 0xffffffffu : (uint32_t)tot;
+}
+}  // namespace gh
+
+extern "C" {
+
+int gooey_b200_set_device(int device) {
+  if (device < 0 || device >= gh::device_count()) { gh::set_error("device index out of range"); return GOOEY_E_INVALID; }
+  gh::g_cur_device = device;
+  return GOOEY_E_OK;
+}
+
+GooeyEngine* gooey_engine_new(float sample_rate) {
+  try {
+    if (!(sample_rate > 0.0f)) { gh::set_error("sample_rate must be > 0"); return nullptr; }
+    gh::use_device(gh::g_cur_device);
+    return gh::engine_create(gh::g_cur_device, sample_rate);
+  } catch (const std::exception& ex) { gh::set_error(ex.what()); return nullptr; }
+}
+void gooey_engine_free(GooeyEngine* e) { try { gh::engine_destroy(e); } catch (...) {} }
+
+bool gooey_engine_has_error(const GooeyEngine* e) { return e ? e->has_error : false; }
+const char* gooey_engine_get_error_message(const GooeyEngine* e) { return (e && e->has_error) ? e->error.c_str() : nullptr; }
+void gooey_engine_set_error_callback(GooeyEngine* e, void* ctx, void (*cb)(void*, const char*)) { if (e) { e->error_cb = cb; e->error_ctx = ctx; } }
+
+void gooey_engine_set_kick_param(GooeyEngine* e, uint32_t p, float v) { if (e) gh::strip_set_param(gh::strip_by_type(e, GOOEY_INSTRUMENT_KICK), p, v); }
+void gooey_engine_set_snare_param(GooeyEngine* e, uint32_t p, float v) { if (e) gh::strip_set_param(gh::strip_by_type(e, GOOEY_INSTRUMENT_SNARE), p, v); }
+void gooey_engine_set_hihat_param(GooeyEngine* e, uint32_t p, float v) { if (e) gh::strip_set_param(gh::strip_by_type(e, GOOEY_INSTRUMENT_HIHAT), p, v); }
+void gooey_engine_set_tom_param(GooeyEngine* e, uint32_t p, float v) { if (e) gh::strip_set_param(gh::strip_by_type(e, GOOEY_INSTRUMENT_TOM), p, v); }
+void gooey_engine_set_bass_param(GooeyEngine* e, uint32_t p, float v) { if (e) gh::strip_set_param(gh::strip_by_type(e, GOOEY_INSTRUMENT_BASS), p, v); }
+void gooey_engine_set_channel_param(GooeyEngine* e, uint32_t ch, uint32_t p, float v) { if (e && ch < 5) gh::strip_set_param(&e->strip[ch], p, v); }
+void gooey_engine_load_bass_preset(GooeyEngine* e, uint32_t id) {
+  if (!e || id > 3) return;
+  static const float P[4][15] = {   // BassConfig::{acid,sub,reese,stab} (bass.rs:188-269); set_config = 15 set_targets
+      {0.24f, 0.40f, 0.80f, 0.00f, 0.00f, 0.10f, 0.15f, 0.70f, 0.85f, 0.15f, 0.08f, 0.35f, 0.10f, 0.30f, 0.80f},
+      {0.18f, 1.00f, 0.15f, 0.00f, 0.00f, 0.00f, 0.70f, 0.05f, 0.10f, 0.30f, 0.20f, 0.60f, 0.15f, 0.00f, 0.85f},
+      {0.18f, 0.30f, 0.80f, 0.80f, 0.50f, 0.05f, 0.35f, 0.30f, 0.50f, 0.40f, 0.15f, 0.55f, 0.12f, 0.60f, 0.80f},
+      {0.30f, 0.20f, 0.90f, 0.00f, 0.00f, 0.90f, 0.20f, 0.40f, 0.90f, 0.08f, 0.05f, 0.20f, 0.08f, 0.20f, 0.80f}};
+  GooeyEngine::Strip* s = gh::strip_by_type(e, GOOEY_INSTRUMENT_BASS);
+  if (!s) return;
+  for (uint32_t i = 0; i < 15; i++) s->pending.push_back(gh::make_event(0, gd::EV_SET_TARGET, i, gh::clamp01(P[id][i])));
+}
+
+void gooey_engine_set_bpm(GooeyEngine* e, float bpm) {
+  if (!e) return;
+  e->bpm = bpm;
+  for (auto& s : e->strip) s.seq.set_bpm(bpm);
+  for (int slot = 0; slot < gd::MAX_FX; slot++)
+    if (e->cfg.fx_kind[slot] == gd::FXK_DELAY) e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_BPM, slot, bpm));
+}
+float gooey_engine_get_bpm(const GooeyEngine* e) { return e ? e->bpm : 120.0f; }
+void gooey_engine_set_swing(GooeyEngine* e, float swing) {
+  if (!e) return;
+  float c = gd::clampf(swing, 0.0f, 1.0f);
+  e->swing = c;
+  for (auto& s : e->strip) s.seq.set_swing(c);
+}
+void gooey_engine_set_master_gain(GooeyEngine* e, float g) { if (e && std::isfinite(g)) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_MASTER, g)); }
+
+void gooey_engine_sequencer_set_instrument_step_settings(GooeyEngine* e, uint32_t inst, uint32_t step, bool enabled, bool set_vel, float vel,
+                                                         bool set_blend, float bx, float by, bool set_note, uint8_t note) {
+  if (!e || inst >= 5) return;
+  auto& pat = e->strip[inst].seq.pattern;
+  if (step >= pat.size()) return;
+  gh::SeqStep& st = pat[step];
+  st.enabled = enabled;
+  if (set_vel) st.velocity = gd::clampf(vel, 0.0f, 1.0f);
+  if (set_blend) { st.has_blend = true; st.bx = gd::clampf(bx, 0.0f, 1.0f); st.by = gd::clampf(by, 0.0f, 1.0f); }
+  if (set_note) { if (note == 255) st.has_note = false; else { st.has_note = true; st.note = note; } }
+}
+void gooey_engine_sequencer_set_instrument_step(GooeyEngine* e, uint32_t inst, uint32_t step, bool enabled) {
+  if (!e || inst >= 5) return;
+  auto& pat = e->strip[inst].seq.pattern;
+  if (step < pat.size()) pat[step].enabled = enabled;
+}
+void gooey_engine_sequencer_set_step(GooeyEngine* e, uint32_t step, bool enabled) { gooey_engine_sequencer_set_instrument_step(e, 0, step, enabled); }
+void gooey_engine_sequencer_set_instrument_step_with_velocity(GooeyEngine* e, uint32_t inst, uint32_t step, bool enabled, float vel) {
+  if (!e || inst >= 5) return;
+  auto& pat = e->strip[inst].seq.pattern;
+  if (step < pat.size()) { pat[step].enabled = enabled; pat[step].velocity = gd::clampf(vel, 0.0f, 1.0f); }
+}
+void gooey_engine_sequencer_set_instrument_step_note(GooeyEngine* e, uint32_t inst, uint32_t step, uint8_t note) {
+  if (!e || inst >= 5) return;
+  auto& pat = e->strip[inst].seq.pattern;
+  if (step < pat.size()) { if (note == 255) pat[step].has_note = false; else { pat[step].has_note = true; pat[step].note = note; } }
+}
+void gooey_engine_sequencer_set_instrument_pattern(GooeyEngine* e, uint32_t inst, const bool* pattern) {
+  if (!e || !pattern || inst >= 5) return;
+  gh::HostSeq& q = e->strip[inst].seq;
+  q.pattern.assign(16, gh::SeqStep());            // SequencerStep::from(bool): velocity 1, no blend, no note
+  for (int i = 0; i < 16; i++) q.pattern[i].enabled = pattern[i];
+  if (q.current_step >= q.pattern.size()) q.current_step = 0;
+}
+void gooey_engine_sequencer_start(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.start(); }
+void gooey_engine_sequencer_stop(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.stop(); }
+void gooey_engine_sequencer_reset(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.reset(); }
+
+void gooey_engine_set_instrument_gain(GooeyEngine* e, uint32_t i, float g) { if (e && i < 5) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_CH_GAIN + i, gd::clampf(g, 0.0f, 1.0f))); }
+void gooey_engine_set_instrument_pan(GooeyEngine* e, uint32_t i, float p) { if (e && i < 5) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_CH_PAN + i, gd::clampf(p, 0.0f, 1.0f))); }
+void gooey_engine_set_instrument_mute(GooeyEngine* e, uint32_t i, bool m) { if (e && i < 5) e->strip[i].muted = m; }
+void gooey_engine_set_instrument_solo(GooeyEngine* e, uint32_t i, bool s) { if (e && i < 5) e->strip[i].soloed = s; }
+void gooey_engine_trigger_instrument_with_velocity(GooeyEngine* e, uint32_t i, float v) {
+  if (e && i < 5) { e->strip[i].trig_vel = gd::clampf(v, 0.0f, 1.0f); e->strip[i].trig_pending = true; }
+}
+void gooey_engine_trigger_instrument(GooeyEngine* e, uint32_t i) { gooey_engine_trigger_instrument_with_velocity(e, i, 1.0f); }
+
+void gooey_engine_set_global_effect_param(GooeyEngine* e, uint32_t fx, uint32_t p, float v) {
+  if (!e) return;
+  if (fx == gd::FXK_LIMITER) {
+    if (p == 0 && std::isfinite(v)) { float t = gd::clampf(v, 0.001f, 1.0f); e->cfg.lim_th = t; e->cfg.lim_inv = 1.0f / t; gh::sync_cfg(e); }
+    return;
+  }
+  int slot = gh::fx_slot_of(fx);
+  if (slot >= 0 && p < 256) e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_SET, ((uint32_t)slot << 8) | p, v));
+}
+void gooey_engine_set_global_effect_enabled(GooeyEngine* e, uint32_t fx, bool on) {
+  if (!e) return;
+  if (fx == gd::FXK_LIMITER) e->cfg.limiter_on = on;
+  else { int slot = gh::fx_slot_of(fx); if (slot < 0) return; e->cfg.fx_enabled[slot] = on; }
+  gh::sync_cfg(e);
+}
+bool gooey_engine_set_effect_order(GooeyEngine* e, const uint32_t* ids, uint32_t len) {   // a permutation of the 9 reorderable ids
+  if (!e || !ids || len != 9) return false;
+  for (uint32_t i = 0; i < 9; i++) { if (ids[i] > 9 || ids[i] == gd::FXK_LIMITER) return false; for (uint32_t j = 0; j < i; j++) if (ids[j] == ids[i]) return false; }
+  for (uint32_t i = 0; i < 9; i++) e->cfg.order[i] = ids[i];
+  gh::sync_cfg(e);
+  return true;
+}
+
+int32_t gooey_engine_mixer_add_track(GooeyEngine* e, const char*) {
+  if (!e || e->cfg.n_tracks >= gd::MAX_TRACKS) return -1;
+  const uint32_t t = e->cfg.n_tracks++;
+  e->cfg.rack_n[t] = 0;
+  e->track_muted[t] = e->track_soloed[t] = false;
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_TRACK_INIT, t, 0.0f));
+  gh::sync_cfg(e);
+  return (int32_t)t;
+}
+uint32_t gooey_engine_mixer_get_track_count(const GooeyEngine* e) { return e ? e->cfg.n_tracks : 0; }
+bool gooey_engine_mixer_route_source(GooeyEngine* e, uint32_t src, uint32_t track) {
+  if (!e || src >= 5 || track >= e->cfg.n_tracks) return false;
+  e->cfg.route[src] = (int32_t)track;
+  gh::sync_cfg(e);
+  return true;
+}
+void gooey_engine_mixer_set_track_gain(GooeyEngine* e, uint32_t t, float g) { if (e && t < e->cfg.n_tracks) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_TR_GAIN + t, gd::clampf(g, 0.0f, 2.0f))); }
+void gooey_engine_mixer_set_track_pan(GooeyEngine* e, uint32_t t, float p) { if (e && t < e->cfg.n_tracks) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_TR_PAN + t, gd::clampf(p, 0.0f, 1.0f))); }
+void gooey_engine_mixer_set_track_mute(GooeyEngine* e, uint32_t t, bool m) { if (e && t < e->cfg.n_tracks) e->track_muted[t] = m; }
+void gooey_engine_mixer_set_track_solo(GooeyEngine* e, uint32_t t, bool s) { if (e && t < e->cfg.n_tracks) e->track_soloed[t] = s; }
+int32_t gooey_engine_track_effect_add(GooeyEngine* e, uint32_t t, uint32_t fx) {   // effect_chain.rs:57-109; this build: delay / tilt / spring / plate
+  if (!e || t >= e->cfg.n_tracks) return -1;
+  if (gh::fx_slot_of(fx) < 0) return -1;
+  if (e->cfg.rack_n[t] >= 4) return -1;
+  int slot = -1;
+  for (int s = gd::FXS_RACK0; s < gd::MAX_FX; s++) if (e->cfg.fx_kind[s] == gd::FXK_NONE) { slot = s; break; }
+  if (slot < 0) return -1;
+  e->cfg.fx_kind[slot] = fx; e->cfg.fx_enabled[slot] = 1;
+  const uint32_t pos = e->cfg.rack_n[t]++;
+  e->cfg.rack_slot[t][pos] = (uint8_t)slot;
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_INIT, slot, e->bpm, fx));
+  gh::sync_cfg(e);
+  return (int32_t)pos;
+}
+void gooey_engine_track_effect_set_param(GooeyEngine* e, uint32_t t, uint32_t pos, uint32_t p, float v) {
+  if (!e || t >= e->cfg.n_tracks || pos >= e->cfg.rack_n[t] || p >= 256) return;
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_SET, ((uint32_t)e->cfg.rack_slot[t][pos] << 8) | p, v));
+}
+
+// Host-only: the trigger schedule the bounce of an engine with this tempo / swing / pattern resolves to (the frames at
+// which kernel events are placed).  Needs no device; used by the CPU tests for the bit-exact trigger-index gate.
+uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing, const uint8_t* enabled, const float* velocity, uint32_t steps,
+                                       uint32_t frames, uint32_t* out_frames, float* out_velocity, uint32_t capacity) {
+  if (!enabled || steps == 0) return 0;
+  gh::HostSeq q;
+  q.init(120.0f, sample_rate);
+  q.set_bpm(bpm);
+  q.pattern.assign(steps, gh::SeqStep());
+  for (uint32_t i = 0; i < steps; i++) { q.pattern[i].enabled = enabled[i] != 0; q.pattern[i].velocity = velocity ? gd::clampf(velocity[i], 0.0f, 1.0f) : 1.0f; }
+  q.set_swing(swing);
+  q.reset(); q.start();
+  std::vector<gh::SeqFire> fires;
+  q.run(frames, fires);
+  uint32_t n = 0;
+  for (const auto& f : fires) { if (n < capacity) { if (out_frames) out_frames[n] = f.frame; if (out_velocity) out_velocity[n] = f.velocity; } n++; }
+  return n;
+}
+
+// ---- render / bounce ----
+static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t frames, int mode, bool bounce, float* out_dev, size_t stride,
+                             float* out_host, size_t host_pitch) {
+  std::vector<GooeyEngine*> E(engines, engines + n);
+  try {
+    gh::EngineBank& B = *E[0]->bank;
+    gh::use_device(B.device);
+    float* dst = out_dev;
+    const size_t row = mode == gh::OUT_MONO ? (size_t)frames : (size_t)2 * frames;
+    if (!dst) {
+      stride = (row + 3) & ~(size_t)3;
+      std::lock_guard<std::mutex> lk(B.mu);
+      B.d_out.alloc((size_t)n * stride);
+      dst = B.d_out.p;
+    }
+    gh::engines_render(E, frames, mode, bounce, dst, stride);
+    if (out_host) GH_CUDA(cudaMemcpy2DAsync(out_host, host_pitch * 4, dst, stride * 4, row * 4, n, cudaMemcpyDeviceToHost, B.stream));
+    GH_CUDA(cudaStreamSynchronize(B.stream));
+    GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, B.ev0, B.ev1));
+    return GOOEY_E_OK;
+  } catch (const std::exception& ex) {
+    gh::set_error(ex.what());
+    for (auto* e : E) gh::engine_fail(e, ex.what());
+    return GOOEY_E_CUDA;
+  }
+}
+
+void gooey_engine_render(GooeyEngine* e, float* buffer, uint32_t frames) {
+  if (!e || !buffer) return;
+  if (frames == 0) return;
+  if (e->has_error || batch_render_impl(&e, 1, frames, gh::OUT_STEREO, false, nullptr, 0, buffer, (size_t)2 * frames) != GOOEY_E_OK)
+    memset(buffer, 0, (size_t)frames * 2 * sizeof(float));
+}
+int gooey_batch_render(GooeyEngine* const* engines, uint32_t n, uint32_t frames, float* out_host) {
+  if (!engines || !out_host) { gh::set_error("null argument"); return GOOEY_E_INVALID; }
+  if (n == 0 || frames == 0) return GOOEY_E_OK;
+  for (uint32_t i = 0; i < n; i++) if (!engines[i]) { gh::set_error("null engine in batch"); return GOOEY_E_INVALID; }
+  return batch_render_impl(engines, n, frames, gh::OUT_STEREO, false, nullptr, 0, out_host, (size_t)2 * frames);
+}
+float* gooey_engine_bounce_to_buffer(GooeyEngine* e, uint32_t bars, uint32_t* out_length) {
+  if (!e || !out_length) return nullptr;
+  float* buf = nullptr;
+  if (gooey_batch_bounce(&e, 1, bars, &buf, out_length) != GOOEY_E_OK) return nullptr;
+  return buf;
+}
+void gooey_engine_free_buffer(float* buffer, uint32_t) { free(buffer); }
+
+int gooey_batch_bounce(GooeyEngine* const* engines, uint32_t n, uint32_t bars, float** out_buffers, uint32_t* out_lengths) {
+  if (!engines || !out_buffers || !out_lengths) { gh::set_error("null argument"); return GOOEY_E_INVALID; }
+  for (uint32_t i = 0; i < n; i++) { if (!engines[i]) { gh::set_error("null engine in batch"); return GOOEY_E_INVALID; } out_buffers[i] = nullptr; out_lengths[i] = 0; }
+  // engines whose tempo gives a different length are bounced as separate groups
+  std::map<uint32_t, std::vector<uint32_t>> groups;
+  for (uint32_t i = 0; i < n; i++) groups[gh::bounce_frames(engines[i], bars)].push_back(i);
+  for (auto& g : groups) {
+    const uint32_t frames = g.first;
+    std::vector<GooeyEngine*> E;
+    for (uint32_t i : g.second) E.push_back(engines[i]);
+    const size_t cnt = E.size();
+    std::vector<float> host((size_t)cnt * std::max<uint32_t>(frames, 1));
+    if (frames > 0) {
+      int rc = batch_render_impl(E.data(), (uint32_t)cnt, frames, gh::OUT_MONO, true, nullptr, 0, host.data(), frames);
+      if (rc != GOOEY_E_OK) return rc;
+    }
+    for (size_t j = 0; j < cnt; j++) {
+      float* p = (float*)malloc(std::max<size_t>((size_t)frames, 1) * sizeof(float));
+      if (!p) { gh::set_error("out of host memory"); return GOOEY_E_INVALID; }
+      if (frames) memcpy(p, host.data() + j * frames, (size_t)frames * sizeof(float));
+      out_buffers[g.second[j]] = p;
+      out_lengths[g.second[j]] = frames;
+    }
+  }
+  return GOOEY_E_OK;
+}
+int gooey_batch_bounce_device(GooeyEngine* const* engines, uint32_t n, uint32_t bars, float* out_dev, size_t stride, uint32_t* out_frames) {
+  if (!engines || !out_dev || n == 0) { gh::set_error("bad arguments"); return GOOEY_E_INVALID; }
+  for (uint32_t i = 0; i < n; i++) if (!engines[i]) { gh::set_error("null engine in batch"); return GOOEY_E_INVALID; }
+  const uint32_t frames = gh::bounce_frames(engines[0], bars);
+  for (uint32_t i = 1; i < n; i++) if (gh::bounce_frames(engines[i], bars) != frames) { gh::set_error("engines of a device-resident batch must have equal length"); return GOOEY_E_INVALID; }
+  if (stride < frames) { gh::set_error("stride < frames"); return GOOEY_E_INVALID; }
+  if (out_frames) *out_frames = frames;
+  if (frames == 0) return GOOEY_E_OK;
+  return batch_render_impl(engines, n, frames, gh::OUT_MONO, true, out_dev, stride, nullptr, 0);
+}
+
+}  // extern "C"

@@ -210,6 +210,12 @@ __device__ __forceinline__ void load_tile_rows(float* tile /*[32][33]*/, const f
   }
 }
 
+// Same for any pitch / alignment / partial width (scalar loads, still one 128-byte segment per row).
+__device__ __forceinline__ void load_tile_rows_any(float* tile /*[32][33]*/, const float* plane, long long pitch, int row0, int n_rows, int c0, int nf, int lane) {
+  for (int r = 0; r < n_rows; r++)
+    if (lane < nf) tile[r * 33 + lane] = plane[(long long)(row0 + r) * pitch + c0 + lane];
+}
+
 // ------------------------------------------------------------------------------------------- S: general path ----
 template <class V, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) slow_kernel(const VoiceLaunch L) {

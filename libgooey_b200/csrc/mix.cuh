@@ -41,7 +41,6 @@ struct MixState {
   Sm tr_gain[MAX_TRACKS], tr_pan[MAX_TRACKS], tr_mute[MAX_TRACKS];
   Sm master;
   FxDyn fx[MAX_FX];
-  double t;
 };
 // MixParam indices for MX_SET
 enum { MP_CH_GAIN = 0, MP_CH_MUTE = 5, MP_CH_PAN = 10, MP_TR_GAIN = 15, MP_TR_PAN = 23, MP_TR_MUTE = 31, MP_MASTER = 39 };
@@ -72,14 +71,15 @@ struct FxGeom {
 struct MixLaunch {
   uint32_t* state; int n, state_cap;  // MixState pool (SoA words, row pitch state_cap)
   const uint32_t* slots;              // launch index -> engine slot in the pool / cfg array / ring arenas
-  int n_lpad;                         // channel stride of the voice buffer (launch count padded to 32)
+  int n_lpad;                         // launch count padded to 32: voice row of channel ch, engine i = ch * n_lpad + i
   const MixCfg* cfg;
-  const VoiceEvent* events; const uint32_t* ev_begin; uint32_t* ev_cursor;
-  const float* voice_buf;             // time-major [frame][voice_stride], slot = ch * n_lpad + launch index (ch 5 = poly, 6 = gran)
+  const VoiceEvent* events; const uint32_t* ev_begin;
+  const float* voice_buf;             // voice-major [row][voice_stride]; ch 0-4 = voice strips, 5 = poly, 6 = granulator
   long long voice_stride;
+  uint32_t chan_mask;                 // bit ch set: some engine of the launch has a source on that channel
   float* ring[MAX_FX];                // per fx-slot arenas [word][ring_cap]
   long long ring_cap;
-  uint32_t frame0; int frames;
+  int frames;
   float* out; long long out_stride; int out_mode;  // 0: mono downmix [engine][frame], 1: interleaved stereo [engine][2*frame]
   const uint32_t* out_rows;
   RateCtx rc; FxGeom geo;
@@ -355,7 +355,6 @@ __device__ __forceinline__ void fx_process(FxDyn& f, uint32_t kind, const RingRe
 
 __device__ __forceinline__ void mix_event(MixState& s, const MixCfg& cfg, const VoiceEvent& e, const RateCtx& rc) {
   switch (e.kind) {
-    case EV_SET_TIME: s.t = (double)e.value; break;
     case MX_SET: {
       const uint32_t p = e.param;
       if (p < MP_CH_MUTE) sm_set(s.ch_gain[p - MP_CH_GAIN], e.value, 0.0f, 1.0f);
@@ -379,28 +378,29 @@ __device__ __forceinline__ void mix_event(MixState& s, const MixCfg& cfg, const 
   }
 }
 
-// One engine per thread; 32 engines x 32 frames staged per warp for the coalesced write-out.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) mix_kernel(const MixLaunch L) {
-  __shared__ float tiles[BLOCK / 32][2][TILE * 33];
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// One engine per thread.  Voice rows come in and the mix goes out through 32 engines x 32 frames shared-memory tiles,
+// so every global access is a 128-byte row segment.
+constexpr int MIX_CH = 7;
+__global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
+  __shared__ float tin[MIX_CH][TILE * 33];
+  __shared__ float tout[2][TILE * 33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int lane = threadIdx.x;
   const int warp_i0 = i - lane;
   if (warp_i0 >= L.n) return;
   const bool valid = i < L.n;
+  const uint32_t row_mask = __ballot_sync(0xffffffffu, valid);
+  const int n_rows = min(32, L.n - warp_i0);
   MixState st;
   MixCfg cfg;
   uint32_t ev = 0, ev_end = 0;
   int es = 0;
   if (valid) {
     es = (int)L.slots[i];
-    load_state(st, L.state, es, L.state_cap);
+    load_words(st, L.state, es, L.state_cap, 0);
     cfg = L.cfg[es];
-    ev = L.ev_cursor[i]; ev_end = L.ev_begin[i + 1];
+    ev = L.ev_begin[i]; ev_end = L.ev_begin[i + 1];
   }
-  float* tl = tiles[warp][0];
-  float* tr = tiles[warp][1];
-  const int n_rows = min(32, L.n - warp_i0);
   const RateCtx& rc = L.rc;
   // pan trig cache (pan is constant during a bounce; recomputed when the smoothed value moves)
   float pan_v[N_VOICE_CH], pan_cos[N_VOICE_CH], pan_sin[N_VOICE_CH];
@@ -408,23 +408,25 @@ __global__ void __launch_bounds__(BLOCK) mix_kernel(const MixLaunch L) {
   for (int c = 0; c < N_VOICE_CH; c++) { pan_v[c] = -1.0f; pan_cos[c] = pan_sin[c] = 0.0f; }
   for (int f0 = 0; f0 < L.frames; f0 += TILE) {
     const int nf = min(TILE, L.frames - f0);
+    for (int c = 0; c < MIX_CH; c++)
+      if ((L.chan_mask >> c) & 1u) load_tile_rows_any(tin[c], L.voice_buf, L.voice_stride, c * L.n_lpad + warp_i0, n_rows, f0, nf, lane);
+    __syncwarp();
     if (valid) {
       for (int j = 0; j < nf; j++) {
-        const uint32_t frame = L.frame0 + f0 + j;
+        const uint32_t frame = f0 + j;
         while (ev < ev_end && L.events[ev].frame <= frame) { mix_event(st, cfg, L.events[ev], rc); ev++; }
-        const float* vb = L.voice_buf + (long long)(f0 + j) * L.voice_stride + i;
         float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
 #pragma unroll
         for (int c = 0; c < N_VOICE_CH; c++) {  // ffi.rs:1268-1283
-          float x = vb[(long long)c * L.n_lpad] * sm_tick(st.ch_gain[c], rc.smooth10) * sm_tick(st.ch_mute[c], rc.smooth10);
+          float x = tin[c][lane * 33 + j] * sm_tick(st.ch_gain[c], rc.smooth10) * sm_tick(st.ch_mute[c], rc.smooth10);
           float pan = sm_tick(st.ch_pan[c], rc.smooth10);
           if (pan != pan_v[c]) { float ang = clampf(pan, 0.0f, 1.0f) * 1.57079632679489661923f; pan_v[c] = pan; pan_cos[c] = gm::g_cosf(ang); pan_sin[c] = gm::g_sinf(ang); }
           float pl = x * pan_cos[c], pr = x * pan_sin[c];
           if (c < 4) { kit_l += pl; kit_r += pr; } else { bass_l += pl; bass_r += pr; }
         }
         float src_l[5] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f}, src_r[5] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f};
-        if (cfg.src_poly) { float x = vb[5LL * L.n_lpad]; src_l[2] = x * L.center_l; src_r[2] = x * L.center_r; }
-        if (cfg.src_gran) { float x = vb[6LL * L.n_lpad]; src_l[3] = x * L.center_l; src_r[3] = x * L.center_r; }
+        if (cfg.src_poly) { float x = tin[5][lane * 33 + j]; src_l[2] = x * L.center_l; src_r[2] = x * L.center_r; }
+        if (cfg.src_gran) { float x = tin[6][lane * 33 + j]; src_l[3] = x * L.center_l; src_r[3] = x * L.center_r; }
         float ml = 0.0f, mr = 0.0f;
         for (uint32_t t = 0; t < cfg.n_tracks; t++) {  // graph.rs:344-350, 385-399
           float fl = 0.0f, fr = 0.0f;
@@ -450,28 +452,24 @@ __global__ void __launch_bounds__(BLOCK) mix_kernel(const MixLaunch L) {
           if (slot >= 0 && cfg.fx_enabled[slot]) fx_process(st.fx[slot], id, RingRef{L.ring[slot], L.ring_cap, es}, L.geo, ml, mr, rc);
         }
         if (cfg.limiter_on) { ml = gm::g_tanhf(ml * cfg.lim_inv) * cfg.lim_th; mr = gm::g_tanhf(mr * cfg.lim_inv) * cfg.lim_th; }
-        st.t += rc.dt;
-        if (L.out_mode == 0) tl[lane * 33 + j] = 0.5f * (ml + mr);
-        else { tl[lane * 33 + j] = ml; tr[lane * 33 + j] = mr; }
+        if (L.out_mode == 0) tout[0][lane * 33 + j] = 0.5f * (ml + mr);
+        else { tout[0][lane * 33 + j] = ml; tout[1][lane * 33 + j] = mr; }
       }
     }
     __syncwarp();
     if (L.out_mode == 0) {
-      store_tile_voice_major(tl, L.out, L.out_stride, warp_i0, L.out_rows ? L.out_rows + warp_i0 : nullptr, n_rows, L.frame0 + f0, nf, lane);
+      store_tile_voice_major(tout[0], L.out, L.out_stride, warp_i0, L.out_rows ? L.out_rows + warp_i0 : nullptr, row_mask, f0, nf, lane);
     } else {
-      // interleave L/R: row r, frame f -> out[row*stride + 2*(frame0+f0+f) + ch]; 64 consecutive floats per row
+      // interleave L/R: row r, frame f -> out[row*stride + 2*(f0+f) + ch]; 64 consecutive floats per row
       for (int r = 0; r < n_rows; r++) {
         const long long row = L.out_rows ? (long long)L.out_rows[warp_i0 + r] : (long long)(warp_i0 + r);
-        float* dst = L.out + row * L.out_stride + 2LL * (L.frame0 + f0);
-        for (int k = lane; k < 2 * nf; k += 32) dst[k] = (k & 1) ? tr[r * 33 + (k >> 1)] : tl[r * 33 + (k >> 1)];
+        float* dst = L.out + row * L.out_stride + 2LL * f0;
+        for (int k = lane; k < 2 * nf; k += 32) dst[k] = (k & 1) ? tout[1][r * 33 + (k >> 1)] : tout[0][r * 33 + (k >> 1)];
       }
     }
     __syncwarp();
   }
-  if (valid) {
-    store_state(st, L.state, es, L.state_cap);
-    L.ev_cursor[i] = ev;
-  }
+  if (valid) store_words(st, L.state, es, L.state_cap, 0);
 }
 #endif  // __CUDACC__
 

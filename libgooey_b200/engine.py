@@ -1,0 +1,138 @@
+"""Engine-level API: the reference's C FFI (``gooey_engine_*``, include/gooey.h) bound with ctypes, plus the batch
+bounce that renders thousands of engines in one device pass.
+
+``Engine`` mirrors the FFI one method per function (``e.set_kick_param(p, v)`` = ``gooey_engine_set_kick_param``).
+The same class drives the CPU oracle in the tests (``prefix="orc_engine_"``), so one call script runs on both sides.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import GooeyError, check, lib
+
+c = ctypes
+_SIGS = {
+    "set_kick_param": [c.c_uint32, c.c_float], "set_snare_param": [c.c_uint32, c.c_float], "set_hihat_param": [c.c_uint32, c.c_float],
+    "set_tom_param": [c.c_uint32, c.c_float], "set_bass_param": [c.c_uint32, c.c_float],
+    "set_channel_param": [c.c_uint32, c.c_uint32, c.c_float], "load_bass_preset": [c.c_uint32],
+    "set_bpm": [c.c_float], "set_swing": [c.c_float], "set_master_gain": [c.c_float],
+    "sequencer_set_instrument_step": [c.c_uint32, c.c_uint32, c.c_bool],
+    "sequencer_set_instrument_step_settings": [c.c_uint32, c.c_uint32, c.c_bool, c.c_bool, c.c_float, c.c_bool, c.c_float, c.c_float, c.c_bool, c.c_uint8],
+    "sequencer_start": [], "sequencer_stop": [], "sequencer_reset": [],
+    "set_instrument_gain": [c.c_uint32, c.c_float], "set_instrument_pan": [c.c_uint32, c.c_float],
+    "set_instrument_mute": [c.c_uint32, c.c_bool], "set_instrument_solo": [c.c_uint32, c.c_bool],
+    "trigger_instrument_with_velocity": [c.c_uint32, c.c_float],
+    "set_global_effect_param": [c.c_uint32, c.c_uint32, c.c_float], "set_global_effect_enabled": [c.c_uint32, c.c_bool],
+    "mixer_set_track_gain": [c.c_uint32, c.c_float], "mixer_set_track_pan": [c.c_uint32, c.c_float],
+    "mixer_set_track_mute": [c.c_uint32, c.c_bool], "mixer_set_track_solo": [c.c_uint32, c.c_bool],
+    "track_effect_set_param": [c.c_uint32, c.c_uint32, c.c_uint32, c.c_float],
+}
+_bound = set()
+
+
+def _bind(L, prefix):
+    key = (id(L), prefix)
+    if key in _bound:
+        return
+    for name, args in _SIGS.items():
+        f = getattr(L, prefix + name)
+        f.argtypes = [c.c_void_p] + args
+        f.restype = None
+    getattr(L, prefix + "new").restype = c.c_void_p
+    getattr(L, prefix + "new").argtypes = [c.c_float]
+    getattr(L, prefix + "free").argtypes = [c.c_void_p]
+    getattr(L, prefix + "free").restype = None
+    f = getattr(L, prefix + "set_effect_order"); f.argtypes = [c.c_void_p, c.POINTER(c.c_uint32), c.c_uint32]; f.restype = c.c_bool
+    f = getattr(L, prefix + "mixer_add_track"); f.argtypes = [c.c_void_p, c.c_char_p]; f.restype = c.c_int32
+    f = getattr(L, prefix + "mixer_route_source"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_bool
+    f = getattr(L, prefix + "track_effect_add"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_int32
+    f = getattr(L, prefix + "render"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32]; f.restype = None
+    f = getattr(L, prefix + "bounce_to_buffer"); f.argtypes = [c.c_void_p, c.c_uint32, c.POINTER(c.c_uint32)]; f.restype = c.POINTER(c.c_float)
+    f = getattr(L, prefix + "free_buffer"); f.argtypes = [c.POINTER(c.c_float), c.c_uint32]; f.restype = None
+    _bound.add(key)
+
+
+class Engine:
+    """One GooeyEngine handle.  Methods are the FFI function names without the ``gooey_engine_`` prefix."""
+
+    def __init__(self, sample_rate=44100.0, library=None, prefix="gooey_engine_"):
+        self._L = library if library is not None else lib()
+        self._prefix = prefix
+        _bind(self._L, prefix)
+        self._h = getattr(self._L, prefix + "new")(c.c_float(sample_rate))
+        if not self._h:
+            raise GooeyError("gooey_engine_new failed: " + (lib().gooey_b200_last_error().decode() if library is None else "oracle"))
+        self.sample_rate = sample_rate
+
+    def close(self):
+        if self._h:
+            getattr(self._L, self._prefix + "free")(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __getattr__(self, name):
+        if name in _SIGS:
+            f = getattr(self._L, self._prefix + name)
+            return lambda *a: f(self._h, *a)
+        raise AttributeError(name)
+
+    def set_effect_order(self, ids):
+        arr = (c.c_uint32 * len(ids))(*ids)
+        return bool(getattr(self._L, self._prefix + "set_effect_order")(self._h, arr, len(ids)))
+
+    def mixer_add_track(self, name="track"):
+        return int(getattr(self._L, self._prefix + "mixer_add_track")(self._h, name.encode()))
+
+    def mixer_route_source(self, source, track):
+        return bool(getattr(self._L, self._prefix + "mixer_route_source")(self._h, source, track))
+
+    def track_effect_add(self, track, effect_id):
+        return int(getattr(self._L, self._prefix + "track_effect_add")(self._h, track, effect_id))
+
+    def render(self, frames):
+        """gooey_engine_render: (frames, 2) interleaved stereo."""
+        out = np.zeros((frames, 2), np.float32)
+        getattr(self._L, self._prefix + "render")(self._h, out.ctypes.data, frames)
+        return out
+
+    def bounce_to_buffer(self, bars):
+        n = c.c_uint32(0)
+        p = getattr(self._L, self._prefix + "bounce_to_buffer")(self._h, bars, c.byref(n))
+        if not p:
+            raise GooeyError("bounce_to_buffer returned NULL")
+        out = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        getattr(self._L, self._prefix + "free_buffer")(p, n)
+        return out
+
+
+def batch_bounce(engines, bars):
+    """gooey_batch_bounce: every engine bounced `bars` bars in one device pass; returns a list of mono arrays."""
+    L = lib()
+    n = len(engines)
+    hs = (c.c_void_p * n)(*[e._h for e in engines])
+    bufs = (c.POINTER(c.c_float) * n)()
+    lens = (c.c_uint32 * n)()
+    L.gooey_batch_bounce.argtypes = [c.POINTER(c.c_void_p), c.c_uint32, c.c_uint32, c.POINTER(c.POINTER(c.c_float)), c.POINTER(c.c_uint32)]
+    check(L.gooey_batch_bounce(hs, n, bars, bufs, lens))
+    _bind(L, "gooey_engine_")
+    out = []
+    for i in range(n):
+        out.append(np.ctypeslib.as_array(bufs[i], shape=(lens[i],)).copy())
+        L.gooey_engine_free_buffer(bufs[i], lens[i])
+    return out
+
+
+def batch_bounce_device(engines, bars, dev_ptr, stride):
+    """gooey_batch_bounce_device: result stays in device memory (rows of `stride` floats); returns frames."""
+    L = lib()
+    n = len(engines)
+    hs = (c.c_void_p * n)(*[e._h for e in engines])
+    frames = c.c_uint32(0)
+    L.gooey_batch_bounce_device.argtypes = [c.POINTER(c.c_void_p), c.c_uint32, c.c_uint32, c.c_void_p, c.c_size_t, c.POINTER(c.c_uint32)]
+    check(L.gooey_batch_bounce_device(hs, n, bars, c.c_void_p(dev_ptr), stride, c.byref(frames)))
+    return frames.value
+
+
+def set_device(device):
+    check(lib().gooey_b200_set_device(int(device)))

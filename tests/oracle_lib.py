@@ -56,3 +56,20 @@ def render_voices(patches, frames, triggers=(), params=(), sample_rate=44100.0, 
                                  _p(ev_x, f32), _p(out, f32), int(threads))
     assert rc == 0
     return out
+
+
+def oracle_engine(sample_rate=44100.0):
+    """The oracle's FfiEngine behind the same Python class the product uses (FFI-named methods)."""
+    from libgooey_b200.engine import Engine
+    return Engine(sample_rate, library=lib(), prefix="orc_engine_")
+
+
+def trigger_table(engine, channel, frames, cap=4096):
+    """Sequencer trigger frames / velocities of one channel after reset + start (bit-exact gate)."""
+    L = lib()
+    fr = np.zeros(cap, np.uint32)
+    ve = np.zeros(cap, np.float32)
+    L.orc_engine_trigger_table.restype = ctypes.c_uint32
+    L.orc_engine_trigger_table.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    n = L.orc_engine_trigger_table(engine._h, channel, frames, fr.ctypes.data, ve.ctypes.data, cap)
+    return fr[:n].copy(), ve[:n].copy()
