@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgooey_b200.so")
+# GOOEY_B200_LIB selects another build of the same library (kernel tuning experiments); never a different backend.
+LIB_PATH = os.environ.get("GOOEY_B200_LIB") or os.path.join(_HERE, "lib", "libgooey_b200.so")
 
 
 class GooeyError(RuntimeError):

@@ -195,6 +195,11 @@ inline GooeyEngine* engine_create(int device, float sr) {
   const uint32_t kinds[4] = {gd::FXK_TILT, gd::FXK_DELAY, gd::FXK_SPRING, gd::FXK_PLATE};
   for (int s = 0; s < 4; s++) gd::fx_construct(ms.fx[s], kinds[s], false, sr, 120.0f);
   e->mix_slot = B.mix_pool.alloc(ms);
+  // a recycled slot inherits its predecessor's delay-line columns: a fresh engine starts from silence
+  GH_CUDA(cudaSetDevice(B.device));
+  for (int s = 0; s < gd::MAX_FX; s++)
+    if (B.ring[s].p && e->mix_slot < B.ring_cap_of[s])
+      GH_CUDA(cudaMemset2DAsync(B.ring[s].p + e->mix_slot, (size_t)B.ring_cap_of[s] * 4, 0, 4, B.ring_words[s], B.stream));
   gd::MixCfg& c = e->cfg;
   memset(&c, 0, sizeof c);
   c.n_tracks = 4;

@@ -88,6 +88,9 @@ struct VoiceBank {
     toms.launch(parent, start, rc, tt, frames, out, stride);
     basses.launch(parent, start, rc, tt, frames, out, stride);
   }
+  // frames per output chunk of the last launch (identical for every bucket) and the per-chunk completion fence
+  int chunk_frames(int frames) const { return TypeRunner<gd::KickV>::chunk_of(frames, kicks.chunk_frames); }
+  void wait_chunk(cudaStream_t s, int i) { kicks.wait_chunk(s, i); snares.wait_chunk(s, i); hats.wait_chunk(s, i); toms.wait_chunk(s, i); basses.wait_chunk(s, i); }
 };
 
 }  // namespace gh
@@ -101,7 +104,7 @@ struct GooeyVoiceBatch {
   int device = 0;
   float sr = 44100.0f;
   gd::RateCtx rc;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n = 0;
   uint32_t k = 0;                        // engine clock index of the next frame (shared by every voice of the batch)
@@ -114,6 +117,7 @@ struct GooeyVoiceBatch {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };
 
@@ -165,6 +169,7 @@ int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoice
   b->device = device; b->sr = sample_rate; b->n = n_voices;
   b->rc = gd::make_rate_ctx(sample_rate);
   GH_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  GH_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
   GH_CUDA(cudaEventCreate(&b->ev0));
   GH_CUDA(cudaEventCreate(&b->ev1));
   b->vtype.resize(n_voices); b->vslot.resize(n_voices); b->pending.resize(n_voices);
@@ -229,7 +234,15 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
   const size_t stride = (frames + 3) & ~(size_t)3;
   b->d_out.alloc((size_t)b->n * stride);
   voice_batch_render_impl(b, frames, b->d_out.p, stride);
-  GH_CUDA(cudaMemcpy2DAsync(out_host, (size_t)frames * 4, b->d_out.p, stride * 4, (size_t)frames * 4, b->n, cudaMemcpyDeviceToHost, b->stream));
+  // drain chunk by chunk while later chunks are still being rendered (overlaps with compute when out_host is pinned)
+  const uint32_t chunk = (uint32_t)b->bank.chunk_frames((int)frames);
+  int ci = 0;
+  for (uint32_t c0 = 0; c0 < frames; c0 += chunk, ci++) {
+    const uint32_t nf = std::min(chunk, frames - c0);
+    b->bank.wait_chunk(b->copy_stream, ci);
+    GH_CUDA(cudaMemcpy2DAsync(out_host + c0, (size_t)frames * 4, b->d_out.p + c0, stride * 4, (size_t)nf * 4, b->n, cudaMemcpyDeviceToHost, b->copy_stream));
+  }
+  GH_CUDA(cudaStreamSynchronize(b->copy_stream));
   GH_CUDA(cudaStreamSynchronize(b->stream));
   GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, b->ev0, b->ev1));
   return GOOEY_E_OK;

@@ -135,7 +135,17 @@ template <class V> struct TypeRunner {
   DevBuf<float> d_planes[2];
   cudaStream_t sB = nullptr, sC = nullptr, sS = nullptr;
   cudaEvent_t evA = nullptr, evB[2] = {nullptr, nullptr}, evC[2] = {nullptr, nullptr}, evDoneC = nullptr, evDoneS = nullptr;
+  std::vector<cudaEvent_t> evChunk;      // evChunk[i]: frames of chunk i are final in the output (fast-path voices)
   int chunk_frames = 8192;
+  int launched_chunks = 0;               // chunks of the most recent launch (0 = one undivided launch)
+  static int chunk_of(int frames, int chunk_frames) { return std::min(chunk_frames, (frames + 31) & ~31); }
+  // Makes `s` wait until every voice of this bucket has written frames [i * chunk, (i + 1) * chunk) of the last launch.
+  void wait_chunk(cudaStream_t s, int i) {
+    if (n() == 0) return;
+    if (launched_chunks == 0) { GH_CUDA(cudaStreamWaitEvent(s, evDoneC, 0)); return; }
+    GH_CUDA(cudaStreamWaitEvent(s, evDoneS, 0));
+    GH_CUDA(cudaStreamWaitEvent(s, evChunk[std::min(i, launched_chunks - 1)], 0));
+  }
 
   int n() const { return (int)slots.size(); }
   void reset() { slots.clear(); rows.clear(); ev_flat.clear(); ev_begin.clear(); ev_begin.push_back(0); span_off.clear(); span_off.push_back(0); }
@@ -159,6 +169,7 @@ template <class V> struct TypeRunner {
   ~TypeRunner() {
     cudaEvent_t evs[] = {evA, evB[0], evB[1], evC[0], evC[1], evDoneC, evDoneS};
     for (auto e : evs) if (e) cudaEventDestroy(e);
+    for (auto e : evChunk) cudaEventDestroy(e);
     if (sB) cudaStreamDestroy(sB);
     if (sC) cudaStreamDestroy(sC);
     if (sS) cudaStreamDestroy(sS);
@@ -166,6 +177,7 @@ template <class V> struct TypeRunner {
   // Forks from `parent` (after `start`), runs the bucket on its own streams, joins back into `parent`.
   void launch(cudaStream_t parent, cudaEvent_t start, const gd::RateCtx& rc, const double* tt, int frames, float* out, long long stride) {
     const int cnt = n();
+    launched_chunks = 0;
     if (cnt == 0 || frames <= 0) return;
     ensure_streams();
     GH_CUDA(cudaStreamWaitEvent(sC, start, 0));
@@ -185,7 +197,7 @@ template <class V> struct TypeRunner {
       d_span_off.upload(span_off.data(), span_off.size(), sC);
       d_n_spans.alloc(cnt); d_span_cursor.alloc(cnt); d_mode.alloc(cnt);
       d_spans.alloc((size_t)span_off.back() * sizeof(Span));
-      const int chunk = std::min(chunk_frames, (frames + 31) & ~31);
+      const int chunk = chunk_of(frames, chunk_frames);
       const int rows_pad = pad32(cnt);
       const size_t plane_floats = (size_t)rows_pad * chunk;
       d_planes[0].alloc(plane_floats * V::NPL); d_planes[1].alloc(plane_floats * V::NPL);
@@ -214,13 +226,16 @@ template <class V> struct TypeRunner {
         GH_CUDA(cudaEventRecord(evB[b], sB));
         GH_CUDA(cudaStreamWaitEvent(sC, evB[b], 0));
         if constexpr (WaveOf<V>::has) {
-          if (!serial_backend()) gd::wave_kernel<typename WaveOf<V>::type, 1><<<cnt, 32, 0, sC>>>(L);   // one warp per voice
+          if (!serial_backend()) gd::wave_kernel<typename WaveOf<V>::type, GOOEY_WAVE_WARPS><<<(cnt + GOOEY_WAVE_WARPS - 1) / GOOEY_WAVE_WARPS, GOOEY_WAVE_WARPS * 32, 0, sC>>>(L);   // one warp per voice
           else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
         } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());
         GH_CUDA(cudaEventRecord(evC[b], sC));
+        if ((int)evChunk.size() <= i) { cudaEvent_t e; GH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evChunk.push_back(e); }
+        GH_CUDA(cudaEventRecord(evChunk[i], sC));
         g_launches.fetch_add(2, std::memory_order_relaxed);
       }
+      launched_chunks = i;
       GH_CUDA(cudaEventRecord(evDoneC, sC));
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneS, 0));

@@ -555,8 +555,14 @@ struct TomW {
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
 // One warp per voice; WARPS voices per CTA.
+#ifndef GOOEY_WAVE_MIN_CTAS
+#define GOOEY_WAVE_MIN_CTAS 1
+#endif
+#ifndef GOOEY_WAVE_WARPS
+#define GOOEY_WAVE_WARPS 1
+#endif
 template <class W, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) wave_kernel(const VoiceLaunch L) {
+__global__ void __launch_bounds__(WARPS * 32, GOOEY_WAVE_MIN_CTAS) wave_kernel(const VoiceLaunch L) {
   using V = typename W::V; using Span = typename V::Span; using Aud = typename V::Aud;
   constexpr int WC = sizeof(typename V::Ctl) / 4;
   __shared__ GeoTables T;
