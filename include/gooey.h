@@ -75,6 +75,8 @@ int gooey_b200_set_device(int device);
 void gooey_engine_render(GooeyEngine* engine, float* buffer, uint32_t frames);
 float* gooey_engine_bounce_to_buffer(GooeyEngine* engine, uint32_t bars, uint32_t* out_length);
 void gooey_engine_free_buffer(float* buffer, uint32_t length);
+/* :7942-7980 — mono 16-bit PCM WAV of the bounce; false on null arguments or I/O failure. */
+bool gooey_engine_bounce_to_wav(GooeyEngine* engine, uint32_t bars, const char* utf8_path);
 /* Batch of the two calls above over n engines (libgooey_b200 addition; SURVEY.md section 8b "what calls it"):
  * every engine is bounced `bars` bars in ONE device pass.  out_buffers[i] receives a callee-allocated mono buffer
  * (free with gooey_engine_free_buffer), out_lengths[i] its length.  Returns 0 or a GOOEY_E_* code. */

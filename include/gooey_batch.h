@@ -75,6 +75,29 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
 /* Same, leaving the result in device memory: out_dev[v * stride + i], stride >= frames. */
 int gooey_voice_batch_render_device(GooeyVoiceBatch* b, uint32_t frames, float* out_dev, size_t stride);
 
+/* ---- batches of Rust-API engines (reference: src/engine/mod.rs:109-253 Engine, src/bounce.rs:41-59 bounce_to_buffer) ----
+ * One GooeyRsBatch holds n independent `Engine`s.  Per engine: named instruments (`Engine::add_instrument(name,
+ * Box::new(<Voice>::with_config(sr, cfg)))`), sequencers that name their instrument (`Sequencer::with_pattern /
+ * with_velocity_pattern(bpm, sr, pattern, name)`), `set_bpm`, `set_master_gain` (default 0.25) and the global effect chain,
+ * which starts as [SoftLimiter(1.0)] (`clear_global_effects`, `add_global_effect(SoftLimiter::new(th))`).
+ * gooey_rs_batch_bounce = `bounce_to_buffer(&mut engine, BounceLength::Samples(samples))` of every engine in one device
+ * pass: out_host[engine * samples + i], mono.  Bars / Beats lengths are converted by the host mirror (bounce.rs:20-32). */
+typedef struct GooeyRsBatch GooeyRsBatch;
+int gooey_rs_batch_new(float sample_rate, uint32_t n_engines, int device, GooeyRsBatch** out_batch);
+void gooey_rs_batch_free(GooeyRsBatch* b);
+int gooey_rs_batch_add_instrument(GooeyRsBatch* b, uint32_t engine, const char* name, const GooeyVoicePatch* patch);
+int gooey_rs_batch_add_sequencer(GooeyRsBatch* b, uint32_t engine, const char* instrument_name, float bpm, const uint8_t* enabled,
+                                 const float* velocity, uint32_t steps);
+int gooey_rs_batch_set_bpm(GooeyRsBatch* b, uint32_t engine, float bpm);
+float gooey_rs_batch_get_bpm(const GooeyRsBatch* b, uint32_t engine);
+int gooey_rs_batch_set_master_gain(GooeyRsBatch* b, uint32_t engine, float gain);
+int gooey_rs_batch_clear_global_effects(GooeyRsBatch* b, uint32_t engine);
+int gooey_rs_batch_add_limiter(GooeyRsBatch* b, uint32_t engine, float threshold);
+int gooey_rs_batch_bounce(GooeyRsBatch* b, uint32_t samples, float* out_host);
+int gooey_rs_batch_bounce_device(GooeyRsBatch* b, uint32_t samples, float* out_dev, size_t stride);
+/* Mono PCM WAV writer of bounce_to_wav (bounce.rs:80-133; ffi.rs:7942-7980): bit_depth 16 or 24, sample = round(s * (2^(bits-1) - 1)). */
+int gooey_b200_write_wav(const char* utf8_path, const float* samples, uint32_t n, uint32_t sample_rate, uint32_t bit_depth);
+
 /* Host-only (no device needed): frames and velocities at which a bounce of an engine with this tempo, swing and step
  * pattern fires its triggers — the schedule the host resolves into kernel event tables (reference:
  * Sequencer::tick_with_settings, src/engine/sequencer.rs:883-952).  Returns the number of triggers (may exceed capacity). */

@@ -2,3 +2,4 @@
 from ._lib import GooeyError, LIB_PATH, VoicePatch, lib  # noqa: F401
 from . import voices  # noqa: F401
 from . import engine  # noqa: F401
+from . import bounce  # noqa: F401

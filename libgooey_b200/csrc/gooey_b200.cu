@@ -252,6 +252,7 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
 }  // extern "C"
 
 #include "engine_api.cuh"
+#include "rs_api.cuh"
 
 // =================================================================================================
 // Self-test hooks (tests/test_gmath_gpu.py): evaluate the gm:: routines on the device so the test can

@@ -45,6 +45,12 @@ TOM_PRESETS = {  # tune, bend, tone, color, decay, membrane, membrane_q, volume 
     "brush": [40.0, 20.0, 10.0, 90.0, 30.0, 0.0, 50.0, 100.0],
     "void": [60.0, 30.0, 100.0, 50.0, 90.0, 40.0, 80.0, 100.0],
 }
+BASS_PRESETS = {  # BassConfig::{acid,sub,reese,stab} in field order (src/instruments/bass.rs:188-269)
+    "acid": [0.24, 0.40, 0.80, 0.00, 0.00, 0.10, 0.15, 0.70, 0.85, 0.15, 0.08, 0.35, 0.10, 0.30, 0.80],
+    "sub": [0.18, 1.00, 0.15, 0.00, 0.00, 0.00, 0.70, 0.05, 0.10, 0.30, 0.20, 0.60, 0.15, 0.00, 0.85],
+    "reese": [0.18, 0.30, 0.80, 0.80, 0.50, 0.05, 0.35, 0.30, 0.50, 0.40, 0.15, 0.55, 0.12, 0.60, 0.80],
+    "stab": [0.30, 0.20, 0.90, 0.00, 0.00, 0.90, 0.20, 0.40, 0.90, 0.08, 0.05, 0.20, 0.08, 0.20, 0.80],
+}
 
 
 def patch(instrument, params=(), aux=0, tuning=None):

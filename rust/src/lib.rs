@@ -1,0 +1,77 @@
+//! Rust host side of libgooey_b200: raw bindings of `include/gooey_batch.h` and safe wrappers that mirror
+//! `gooey::bounce` (reference `src/bounce.rs`) for whole batches of engines.
+//!
+//! The reference resolves nothing ahead of time: `Engine::tick` walks sequencers and instruments sample by sample.
+//! Here the host describes each engine (instruments as `with_config` argument lists, sequencer patterns, master gain,
+//! limiter chain) once; the library resolves the sequencer schedule into per-voice trigger tables (bit-exact with
+//! `Sequencer::tick_with_settings`) and renders every engine of the batch in one pass on a B200.
+//!
+//! This crate cannot be compiled in the repository's own image (no Rust toolchain there); it is the binding a libgooey
+//! maintainer adds, kept next to the header it binds so the two stay in step.
+
+pub mod bounce;
+
+use std::ffi::{c_char, c_float, c_int, CStr, CString};
+
+/// `GooeyVoicePatch` (include/gooey_batch.h): instrument id, aux bits, `with_config` arguments.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct GooeyVoicePatch {
+    pub instrument: u32,
+    pub aux: u32,
+    pub params: [f32; 24],
+}
+
+pub const GOOEY_INSTRUMENT_KICK: u32 = 0;
+pub const GOOEY_INSTRUMENT_SNARE: u32 = 1;
+pub const GOOEY_INSTRUMENT_HIHAT: u32 = 2;
+pub const GOOEY_INSTRUMENT_TOM: u32 = 3;
+pub const GOOEY_INSTRUMENT_BASS: u32 = 4;
+
+#[repr(C)]
+pub struct GooeyRsBatch {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct GooeyVoiceBatch {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn gooey_b200_last_error() -> *const c_char;
+    pub fn gooey_b200_device_count() -> c_int;
+
+    pub fn gooey_rs_batch_new(sample_rate: c_float, n_engines: u32, device: c_int, out: *mut *mut GooeyRsBatch) -> c_int;
+    pub fn gooey_rs_batch_free(b: *mut GooeyRsBatch);
+    pub fn gooey_rs_batch_add_instrument(b: *mut GooeyRsBatch, engine: u32, name: *const c_char, patch: *const GooeyVoicePatch) -> c_int;
+    pub fn gooey_rs_batch_add_sequencer(
+        b: *mut GooeyRsBatch, engine: u32, instrument_name: *const c_char, bpm: c_float, enabled: *const u8, velocity: *const c_float, steps: u32,
+    ) -> c_int;
+    pub fn gooey_rs_batch_set_bpm(b: *mut GooeyRsBatch, engine: u32, bpm: c_float) -> c_int;
+    pub fn gooey_rs_batch_set_master_gain(b: *mut GooeyRsBatch, engine: u32, gain: c_float) -> c_int;
+    pub fn gooey_rs_batch_clear_global_effects(b: *mut GooeyRsBatch, engine: u32) -> c_int;
+    pub fn gooey_rs_batch_add_limiter(b: *mut GooeyRsBatch, engine: u32, threshold: c_float) -> c_int;
+    pub fn gooey_rs_batch_bounce(b: *mut GooeyRsBatch, samples: u32, out_host: *mut c_float) -> c_int;
+
+    pub fn gooey_voice_batch_new(sample_rate: c_float, n: u32, patches: *const GooeyVoicePatch, device: c_int, out: *mut *mut GooeyVoiceBatch) -> c_int;
+    pub fn gooey_voice_batch_free(b: *mut GooeyVoiceBatch);
+    pub fn gooey_voice_batch_trigger(b: *mut GooeyVoiceBatch, voice: u32, frame: u32, velocity: c_float) -> c_int;
+    pub fn gooey_voice_batch_set_param(b: *mut GooeyVoiceBatch, voice: u32, frame: u32, param: u32, value: c_float, snap: c_int) -> c_int;
+    pub fn gooey_voice_batch_render(b: *mut GooeyVoiceBatch, frames: u32, out_host: *mut c_float) -> c_int;
+
+    pub fn gooey_b200_write_wav(path: *const c_char, samples: *const c_float, n: u32, sample_rate: u32, bit_depth: u32) -> c_int;
+}
+
+/// The library's thread-local error text, as the `Err(String)` the reference's Rust API uses.
+pub(crate) fn last_error() -> String {
+    unsafe {
+        let p = gooey_b200_last_error();
+        if p.is_null() { String::from("libgooey_b200: unknown error") } else { CStr::from_ptr(p).to_string_lossy().into_owned() }
+    }
+}
+pub(crate) fn check(rc: c_int) -> Result<(), String> {
+    if rc == 0 { Ok(()) } else { Err(format!("libgooey_b200 error {rc}: {}", last_error())) }
+}
+pub(crate) fn cstr(s: &str) -> Result<CString, String> {
+    CString::new(s).map_err(|_| String::from("name contains a NUL byte"))
+}

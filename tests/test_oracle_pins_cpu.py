@@ -1,0 +1,136 @@
+"""What pins the CPU oracle.  The reference cannot be built here and stores no audio vectors, so
+the oracle is pinned by (a) the known answers the reference's own unit tests assert, (b) published vectors of the
+third-party algorithms it restates, (c) the reference's metamorphic properties, (d) committed regression fixtures.
+Parity stays "unpinned" for the halfband crate's coefficients and for DefaultHasher output values (no vectors exist)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import engine_scripts as S
+from golden_cases import kit_patches, KIT_FRAMES, ENGINE_CASES, ENGINE_KEEP
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+c = ctypes
+
+
+def test_siphash_2_4_published_vector_pins_round_function_and_finalisation():
+    # SipHash reference vectors (Aumasson & Bernstein), key 00..0f, message 00..07 -> 62 24 93 9a 79 f5 f5 93
+    k0, k1, m = 0x0706050403020100, 0x0F0E0D0C0B0A0908, 0x0706050403020100
+    assert O.lib().orc_siphash(m, k0, k1, 2, 4) == 0x93F5F5799A932462
+    # the reference's noise is the same function with (c, d) = (1, 3) and zero keys (std DefaultHasher)
+    a = O.lib().orc_siphash(12345, 0, 0, 1, 3)
+    assert a != O.lib().orc_siphash(12345, 0, 0, 2, 4) and a != O.lib().orc_siphash(12346, 0, 0, 1, 3)
+
+
+def test_hash_noise_range_and_mean():
+    # oscillator.rs:187-196: (h as f32) / (u64::MAX as f32) * 2 - 1; the reference tests only range / energy
+    x = np.array([O.lib().orc_hash_noise(i) for i in range(20000)], np.float32)
+    assert x.min() >= -1.0 and x.max() <= 1.0
+    assert abs(float(x.mean())) < 0.02 and 0.5 < float(x.std()) < 0.65
+
+
+def test_click_osc_table_known_answers():
+    # click_osc.rs:7-14, 97-125: 64 taps, first tap 0.884058
+    t = np.zeros(64, np.float32)
+    O.lib().orc_click_table(t.ctypes.data_as(c.POINTER(c.c_float)))
+    assert t[0] == np.float32(0.884058)
+    assert np.isfinite(t).all() and np.abs(t).max() <= 1.0
+
+
+def test_pink_noise_reset_reproducible_and_bounded():
+    # pink_noise.rs:7-12 (seed 0x123456789abcdef0), :145-157 (a fresh generator reproduces the sequence)
+    a, b = np.zeros(4096, np.float32), np.zeros(4096, np.float32)
+    O.lib().orc_pink(c.c_float(44100.0), a.ctypes.data_as(c.POINTER(c.c_float)), 4096)
+    O.lib().orc_pink(c.c_float(44100.0), b.ctypes.data_as(c.POINTER(c.c_float)), 4096)
+    assert np.array_equal(a, b)
+    assert np.abs(a).max() < 1.0 and a.std() > 0.01
+
+
+def test_smoother_coefficient_formula():
+    # smoother.rs:69-77: 1 - exp(-1 / (ms / 1000 * sr)) in f32
+    for sr, ms in [(44100.0, 15.0), (44100.0, 30.0), (48000.0, 10.0), (44100.0, 50.0)]:
+        n = np.float32(np.float32(ms) / np.float32(1000.0)) * np.float32(sr)
+        want = np.float32(1.0) - np.float32(np.exp(np.float32(-1.0) / n, dtype=np.float32))
+        got = np.float32(O.lib().orc_smoother_coeff(sr, ms))
+        assert abs(float(got) - float(want)) <= 1.2e-7          # 1 - exp(): one ulp of 1.0 between numpy's and glibc's expf
+    assert O.lib().orc_smoother_coeff(44100.0, 0.0) == 1.0
+
+
+def test_max_curve_endpoints_and_monotonic():
+    # max_curve.rs:21-48: g(0) = 0, g(1) = 1, monotonic for every curvature; curvature 0 is linear
+    for cv in (-0.9, -0.83, -0.3, 0.0, 0.3, 0.8):
+        xs = np.linspace(0.0, 1.0, 101, dtype=np.float32)
+        ys = np.array([O.lib().orc_max_curve(float(x), cv) for x in xs])
+        assert abs(ys[0]) < 1e-6 and abs(ys[-1] - 1.0) < 1e-6
+        assert (np.diff(ys) >= -1e-6).all()
+    assert abs(O.lib().orc_max_curve(0.5, 0.0) - 0.5) < 1e-3
+
+
+@pytest.mark.parametrize("mode", [2, 4])
+def test_reconstructed_halfband_meets_the_reference_oversampler_properties(mode):
+    # oversampler.rs:277-321 DC passthrough within 0.01 after 200 samples; :323-339 a fresh instance is reproducible
+    L = O.lib()
+    L.orc_oversample.argtypes = [c.c_int, c.c_float, c.c_void_p, c.c_void_p, c.c_uint32]
+    x = np.full(400, 0.5, np.float32)
+    y, y2 = np.zeros(400, np.float32), np.zeros(400, np.float32)
+    L.orc_oversample(mode, c.c_float(0.0), x.ctypes.data, y.ctypes.data, 400)      # drive 0: identity nonlinearity
+    L.orc_oversample(mode, c.c_float(0.0), x.ctypes.data, y2.ctypes.data, 400)
+    assert np.array_equal(y, y2)
+    assert abs(float(y[-1]) - 0.5) < 0.01
+    # :372-394 a 10 kHz fundamental at 48 kHz passes within 1 dB
+    n = np.arange(4800)
+    s = (0.25 * np.sin(2 * np.pi * 10000.0 * n / 48000.0)).astype(np.float32)
+    o = np.zeros_like(s)
+    L.orc_oversample(mode, c.c_float(0.0), s.ctypes.data, o.ctypes.data, len(s))
+    gain_db = 20 * np.log10(np.sqrt(np.mean(o[2000:] ** 2)) / np.sqrt(np.mean(s[2000:] ** 2)))
+    assert abs(gain_db) < 1.0
+
+
+def test_halfband_coefficients_are_a_valid_allpass_pair():
+    h = np.zeros(8, np.float32)
+    O.lib().orc_halfband_coefs(h.ctypes.data_as(c.POINTER(c.c_float)))
+    assert (h > 0).all() and (h < 1).all() and (np.diff(h) > 0).all()
+
+
+def test_master_gain_doubling_and_silence_properties():
+    # tests/ffi_gain_staging.rs: doubling the master gain doubles a bounce (<1e-6); engine_basics: empty pattern = silence
+    def script(e):
+        for s in (0, 4, 8, 12):
+            e.sequencer_set_instrument_step(S.KICK, s, True)
+    a = O.oracle_engine(); script(a); a.set_master_gain(0.25); x = a.bounce_to_buffer(1); a.close()
+    b = O.oracle_engine(); script(b); b.set_master_gain(0.5); y = b.bounce_to_buffer(1); b.close()
+    assert np.abs(x).max() > 0.01
+    assert np.abs(y - 2.0 * x).max() < 1e-6
+    z = O.oracle_engine(); q = z.bounce_to_buffer(1); z.close()
+    assert np.abs(q).max() < 1e-3 and len(q) == 88200          # tests/bounce.rs:31-35: one bar = 88 200 samples
+
+
+def test_two_fresh_engines_identical_and_center_pan_l_equals_r():
+    def script(e):
+        S.pattern_engine(e, 2, graph=False)
+    a = O.oracle_engine(); script(a); x = a.render(20000); a.close()
+    b = O.oracle_engine(); script(b); y = b.render(20000); b.close()
+    assert np.array_equal(x, y)
+    assert np.array_equal(x[:, 0], x[:, 1])                     # tests/ffi_stereo.rs: centre pan => L == R
+
+
+def test_oracle_reproduces_committed_kit_fixture_bit_exact():
+    g = np.load(os.path.join(GOLD, "preset_kit.npz"))
+    patches, vel, names = kit_patches()
+    assert list(g["names"]) == names
+    audio = O.render_voices(patches, KIT_FRAMES, triggers=[(i, 0, float(vel[i])) for i in range(len(patches))])
+    assert np.array_equal(audio, g["audio"])
+
+
+@pytest.mark.parametrize("name", sorted(ENGINE_CASES))
+def test_oracle_reproduces_committed_engine_fixture_bit_exact(name):
+    g = np.load(os.path.join(GOLD, f"engine_{name}.npz"))
+    o = O.oracle_engine()
+    ENGINE_CASES[name](o)
+    buf = o.bounce_to_buffer(1)
+    o.close()
+    assert len(buf) == int(g["length"])
+    assert np.array_equal(buf[:ENGINE_KEEP], g["audio"])
