@@ -144,6 +144,33 @@ void gooey_engine_mixer_set_track_solo(GooeyEngine* engine, uint32_t track, bool
 int32_t gooey_engine_track_effect_add(GooeyEngine* engine, uint32_t track, uint32_t effect_id);
 void gooey_engine_track_effect_set_param(GooeyEngine* engine, uint32_t track, uint32_t slot, uint32_t param, float value);
 
+/* ---- poly synth ("chord oscillators"; :5571-5648, :5899-5935).  Calls act at the engine's current time, like the reference.
+ * gooey_engine_poly_trigger_chord's chord -> MIDI-note step (src/music, host-side tables) is not part of this library:
+ * pass the notes `music::apply_voicing` produced to gooey_engine_poly_trigger_notes, which is the rest of that function. ---- */
+#define GOOEY_POLY_PRESET_DEFAULT 0u
+#define GOOEY_POLY_PRESET_PAD 1u
+#define GOOEY_POLY_PRESET_PLUCK 2u
+#define GOOEY_POLY_PRESET_KEYS 3u
+#define GOOEY_POLY_PRESET_STRINGS 4u
+void gooey_engine_poly_trigger_notes(GooeyEngine* engine, const uint8_t* midi_notes, uint32_t n, uint32_t preset, float velocity);
+void gooey_engine_poly_release(GooeyEngine* engine);
+void gooey_engine_poly_set_preset(GooeyEngine* engine, uint32_t preset);
+void gooey_engine_poly_set_param(GooeyEngine* engine, uint32_t param, float value);
+
+/* ---- granulator (:5969-5990 set_buffer copies and validates; :7656-7827).  Parameter ids (:1944-1968): 0 scan position,
+ * 1 grain length, 2 spray, 3 pitch, 4 density, 5 texture, 6 direction, 7 cloud duration, 8 volume, 9 random timing,
+ * 10 random amp, 11 drive. ---- */
+#define GOOEY_GRANULATOR_PARAM_COUNT 12u
+bool gooey_engine_granulator_set_buffer(GooeyEngine* engine, const float* samples, uint32_t len, float sample_rate);
+uint32_t gooey_engine_granulator_buffer_len(const GooeyEngine* engine);
+float gooey_engine_granulator_buffer_sample_rate(const GooeyEngine* engine);
+void gooey_engine_granulator_trigger(GooeyEngine* engine, float velocity);
+void gooey_engine_granulator_set_param(GooeyEngine* engine, uint32_t param, float value);
+void gooey_engine_granulator_set_seed(GooeyEngine* engine, uint32_t seed);
+void gooey_engine_granulator_snap_params(GooeyEngine* engine);
+/* libgooey_b200 addition: dst plays the buffer already loaded into src, without another device copy. */
+bool gooey_b200_granulator_share_buffer(GooeyEngine* dst, const GooeyEngine* src);
+
 #ifdef __cplusplus
 }
 #endif

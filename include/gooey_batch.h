@@ -32,6 +32,11 @@ extern "C" {
 #define GOOEY_INSTRUMENT_HIHAT 2u
 #define GOOEY_INSTRUMENT_TOM 3u
 #define GOOEY_INSTRUMENT_BASS 4u
+/* libgooey_b200 voice kinds beyond the five sequenced instruments (GooeyVoicePatch.instrument):
+ * the poly synth (params = PolyConfig, 14 normalized values, src/instruments/poly_synth.rs:20-47) and the granulator
+ * (GranulatorConfig::default; buffer and parameters arrive as events). */
+#define GOOEY_B200_VOICE_POLY 5u
+#define GOOEY_B200_VOICE_GRANULATOR 6u
 
 /* One voice patch = the argument list of the reference's `<Voice>::with_config`
  * (Rust API, instrument level):

@@ -102,6 +102,7 @@ struct EngineBank {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece = nullptr;
   DevBuf<float> d_voice_buf, d_out;
+  DevBuf<float> d_silent;                 // the granulator's 1-sample silent placeholder buffer (ffi.rs:929-933)
   DevBuf<uint32_t> d_mix_slots, d_mix_ev_begin;
   DevBuf<gd::VoiceEvent> d_mix_events;
   std::mutex mu;
@@ -110,6 +111,7 @@ struct EngineBank {
     rc = gd::make_rate_ctx(sr); geo = make_fx_geom(sr);
     GH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     GH_CUDA(cudaEventCreate(&ev0)); GH_CUDA(cudaEventCreate(&ev1)); GH_CUDA(cudaEventCreateWithFlags(&ev_piece, cudaEventDisableTiming));
+    d_silent.alloc(4); d_silent.zero(stream);
   }
   // makes sure arena `slot` holds `words` ring words for `cap` engine slots (content preserving)
   void ensure_ring(int slot, uint32_t words, long long cap) {
@@ -144,6 +146,15 @@ struct GooeyEngine {
     float trig_vel = 1.0f;
     std::vector<gd::VoiceEvent> pending;
   } strip[5];
+  // poly synth and granulator: their FFI calls act immediately in the reference (ffi.rs:5571-5648, 7702-7827); here they
+  // queue events that are applied before frame 0 of the next render — the same instant, since nothing ticks in between.
+  // The voices are only launched once the host has touched them (until then they contribute exactly +0.0).
+  struct Aux {
+    int slot = -1; bool used = false;
+    std::vector<gd::VoiceEvent> pending;
+  } poly, gran;
+  std::shared_ptr<gh::DevBuf<float>> gran_buf;    // may be shared by many engines (gooey_b200_granulator_share_buffer)
+  uint32_t gran_len = 1; float gran_sr = 44100.0f;
   int mix_slot = -1;
   gd::MixCfg cfg;
   std::vector<gd::VoiceEvent> mix_pending;
@@ -187,6 +198,15 @@ inline GooeyEngine* engine_create(int device, float sr) {
     e->strip[ch].slot = B.voices.create(p[ch], sr);
     e->strip[ch].seq.init(120.0f, sr);
   }
+  {
+    GooeyVoicePatch q;
+    memset(&q, 0, sizeof q);
+    static const float POLY_DEFAULT[14] = {0.0f, 0.2f, 0.6f, 0.15f, 0.3f, 0.55f, 0.7f, 0.7f, 0.8f, 0.5f, 0.65f, 0.4f, 0.75f, 0.7f};   // PolySynthConfig::default (poly_synth.rs:49-66)
+    q.instrument = GOOEY_B200_VOICE_POLY; memcpy(q.params, POLY_DEFAULT, sizeof POLY_DEFAULT);
+    e->poly.slot = B.voices.create(q, sr);
+    q.instrument = GOOEY_B200_VOICE_GRANULATOR;
+    e->gran.slot = B.voices.create(q, sr);
+  }
   gd::MixState ms;
   memset(&ms, 0, sizeof ms);
   for (int c = 0; c < gd::N_VOICE_CH; c++) { ms.ch_gain[c] = {1.0f, 1.0f}; ms.ch_mute[c] = {1.0f, 1.0f}; ms.ch_pan[c] = {0.5f, 0.5f}; }
@@ -218,15 +238,10 @@ inline void engine_destroy(GooeyEngine* e) {
   if (!e) return;
   EngineBank& B = *e->bank;
   std::lock_guard<std::mutex> lk(B.mu);
-  for (int ch = 0; ch < 5; ch++) {
-    switch (e->strip[ch].type) {
-      case GOOEY_INSTRUMENT_KICK: B.voices.kicks.pool.release(e->strip[ch].slot); break;
-      case GOOEY_INSTRUMENT_SNARE: B.voices.snares.pool.release(e->strip[ch].slot); break;
-      case GOOEY_INSTRUMENT_HIHAT: B.voices.hats.pool.release(e->strip[ch].slot); break;
-      case GOOEY_INSTRUMENT_TOM: B.voices.toms.pool.release(e->strip[ch].slot); break;
-      case GOOEY_INSTRUMENT_BASS: B.voices.basses.pool.release(e->strip[ch].slot); break;
-    }
-  }
+  for (int ch = 0; ch < 5; ch++) B.voices.release(e->strip[ch].type, e->strip[ch].slot);
+  B.voices.release(GOOEY_B200_VOICE_POLY, e->poly.slot);
+  B.voices.release(GOOEY_B200_VOICE_GRANULATOR, e->gran.slot);
+  if (e->gran_buf) { cudaSetDevice(B.device); cudaStreamSynchronize(B.stream); }   // no launch may still read the buffer
   B.mix_pool.release(e->mix_slot);
   delete e;
 }
@@ -245,6 +260,25 @@ inline float midi_to_norm(uint8_t note, float mn, float mx) {
 
 enum { OUT_MONO = 0, OUT_STEREO = 1 };
 
+// First FFI touch of the poly synth / granulator of an engine: from now on the voice is launched with the engine.  It was
+// not ticked so far (an untouched poly synth / granulator is bit-exactly silent and its state does not move), so its
+// clock is set to the engine's and, for the granulator, the placeholder buffer is attached.
+inline void aux_touch(GooeyEngine* e, bool is_gran) {
+  GooeyEngine::Aux& a = is_gran ? e->gran : e->poly;
+  if (a.used) return;
+  a.used = true;
+  a.pending.push_back(make_event(0, gd::EV_SET_TIME, 1, 0.0f, e->k));
+  if (is_gran) {
+    const uint64_t ptr = (uint64_t)(uintptr_t)e->bank->d_silent.p;
+    float lo; uint32_t lo_bits = (uint32_t)ptr; memcpy(&lo, &lo_bits, 4);
+    a.pending.push_back(make_event(0, gd::EV_GRAN_BUFFER, 0, lo, (uint32_t)(ptr >> 32)));
+    a.pending.push_back(make_event(0, gd::EV_SET_AUX, gd::AUX_GRAN_BUFINFO, 44100.0f, 1));
+    e->cfg.src_gran = 1;
+  } else e->cfg.src_poly = 1;
+  std::lock_guard<std::mutex> lk(e->bank->mu);
+  e->bank->cfgs[e->mix_slot] = e->cfg;
+}
+
 // Renders `frames` frames of every engine of `E` (all on one bank) into out_dev: mono rows [n][stride] (the bounce
 // downmix 0.5 (l + r)) or interleaved stereo rows [n][stride >= 2 frames].  `bounce`: apply the reference's bounce
 // preamble first (ffi.rs:7840-7854): clock to 0, sequencers reset + start, strips / graph / master snapped.
@@ -257,7 +291,8 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   const int n = (int)E.size();
   const int n_lpad = pad32(n);
   // ---- schedule resolution (host): per voice and per engine event lists over the whole call ----
-  std::vector<std::vector<gd::VoiceEvent>> vev((size_t)n * 5), mev(n);
+  std::vector<std::vector<gd::VoiceEvent>> vev((size_t)n * 7), mev(n);   // per engine: 5 strips, poly, granulator
+  bool any_poly = false, any_gran = false;
   uint32_t kmax = 0;
   std::vector<SeqFire> fires;
   for (int i = 0; i < n; i++) {
@@ -298,9 +333,17 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       mx.insert(mx.end(), mute_ev.begin(), mute_ev.end());
       mx.insert(mx.end(), tmute_ev.begin(), tmute_ev.end());
     }
+    for (int ax = 0; ax < 2; ax++) {   // immediate-mode events first, then the bounce's clock reset
+      GooeyEngine::Aux& a = ax ? e->gran : e->poly;
+      if (!a.used) continue;
+      (ax ? any_gran : any_poly) = true;
+      auto& ev = vev[(size_t)i * 7 + 5 + ax];
+      ev = a.pending; a.pending.clear();
+      if (bounce) ev.push_back(make_event(0, gd::EV_SET_TIME, 0, 0.0f, 0));
+    }
     for (int ch = 0; ch < 5; ch++) {
       auto& s = e->strip[ch];
-      auto& ev = vev[(size_t)i * 5 + ch];
+      auto& ev = vev[(size_t)i * 7 + ch];
       if (bounce) ev.push_back(make_event(0, gd::EV_SET_TIME, 0, 0.0f, 0));
       ev.insert(ev.end(), s.pending.begin(), s.pending.end());
       s.pending.clear();
@@ -340,7 +383,8 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   for (int i = 0; i < n; i++) mix_slots[i] = (uint32_t)E[i]->mix_slot;
   B.d_mix_slots.upload(mix_slots.data(), n, st);
   // ---- pieces: bound the voice buffer (5 rows per engine) to ~2 GiB ----
-  const size_t rows = (size_t)5 * n_lpad;
+  const int n_ch = any_gran ? 7 : (any_poly ? 6 : 5);
+  const size_t rows = (size_t)n_ch * n_lpad;
   size_t piece = ((size_t)2 << 30) / (rows * 4);
   piece = std::min<size_t>(std::max<size_t>(piece & ~(size_t)31, 2048), 65536);
   piece = std::min<size_t>(piece, (frames + 31) & ~31u);
@@ -348,17 +392,21 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   GH_CUDA(cudaEventRecord(B.ev0, st));
   std::vector<gd::VoiceEvent> cur, mflat;
   std::vector<uint32_t> mbegin;
-  std::vector<size_t> vpos((size_t)n * 5, 0), mpos(n, 0);
+  std::vector<size_t> vpos((size_t)n * 7, 0), mpos(n, 0);
   for (uint32_t f0 = 0; f0 < frames; f0 += (uint32_t)piece) {
     const uint32_t nf = std::min<uint32_t>((uint32_t)piece, frames - f0);
     B.voices.reset();
     for (int i = 0; i < n; i++)
-      for (int ch = 0; ch < 5; ch++) {
-        auto& ev = vev[(size_t)i * 5 + ch];
-        size_t& p = vpos[(size_t)i * 5 + ch];
+      for (int ch = 0; ch < 7; ch++) {
+        if (ch == 5 && !E[i]->poly.used) continue;
+        if (ch == 6 && !E[i]->gran.used) continue;
+        auto& ev = vev[(size_t)i * 7 + ch];
+        size_t& p = vpos[(size_t)i * 7 + ch];
         cur.clear();
         while (p < ev.size() && ev[p].frame < f0 + nf) { gd::VoiceEvent x = ev[p++]; x.frame -= f0; cur.push_back(x); }
-        B.voices.add(E[i]->strip[ch].type, (uint32_t)E[i]->strip[ch].slot, (uint32_t)(ch * n_lpad + i), cur);
+        const uint32_t type = ch < 5 ? E[i]->strip[ch].type : (ch == 5 ? GOOEY_B200_VOICE_POLY : GOOEY_B200_VOICE_GRANULATOR);
+        const int slot = ch < 5 ? E[i]->strip[ch].slot : (ch == 5 ? E[i]->poly.slot : E[i]->gran.slot);
+        B.voices.add(type, (uint32_t)slot, (uint32_t)(ch * n_lpad + i), cur);
       }
     cudaEvent_t start = B.ev_piece;
     GH_CUDA(cudaEventRecord(start, st));
@@ -378,7 +426,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     memset(&M, 0, sizeof M);
     M.state = B.mix_pool.d.p; M.n = n; M.state_cap = B.mix_pool.cap; M.slots = B.d_mix_slots.p; M.n_lpad = n_lpad;
     M.cfg = B.d_cfg.p; M.events = B.d_mix_events.p; M.ev_begin = B.d_mix_ev_begin.p;
-    M.voice_buf = B.d_voice_buf.p; M.voice_stride = (long long)piece; M.chan_mask = 0x1fu;
+    M.voice_buf = B.d_voice_buf.p; M.voice_stride = (long long)piece; M.chan_mask = 0x1fu | (any_poly ? 0x20u : 0u) | (any_gran ? 0x40u : 0u);
     for (int s = 0; s < gd::MAX_FX; s++) M.ring[s] = B.ring[s].p;
     M.ring_cap = ring_cap;
     M.frames = (int)nf;

@@ -204,6 +204,95 @@ void gooey_engine_track_effect_set_param(GooeyEngine* e, uint32_t t, uint32_t po
   e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_SET, ((uint32_t)e->cfg.rack_slot[t][pos] << 8) | p, v));
 }
 
+// ---- poly synth (ffi.rs:5571-5648, 5899-5935; poly_synth.rs) ----
+static const float GOOEY_POLY_PRESETS[5][14] = {   // PolySynthConfig::{default,pad,pluck,keys,strings} (poly_synth.rs:49-142), ffi preset ids 0-4
+    {0.0f, 0.2f, 0.6f, 0.15f, 0.3f, 0.55f, 0.7f, 0.7f, 0.8f, 0.5f, 0.65f, 0.4f, 0.75f, 0.7f},
+    {0.0f, 0.4f, 0.45f, 0.2f, 0.2f, 0.8f, 0.75f, 0.8f, 0.85f, 0.75f, 0.7f, 0.5f, 0.8f, 0.6f},
+    {0.3f, 0.1f, 0.7f, 0.25f, 0.6f, 0.0f, 0.75f, 0.0f, 0.65f, 0.0f, 0.7f, 0.1f, 0.65f, 0.7f},
+    {0.5f, 0.15f, 0.55f, 0.1f, 0.4f, 0.35f, 0.7f, 0.5f, 0.75f, 0.3f, 0.65f, 0.3f, 0.7f, 0.7f},
+    {0.0f, 0.5f, 0.5f, 0.1f, 0.15f, 0.85f, 0.7f, 0.9f, 0.85f, 0.8f, 0.7f, 0.6f, 0.8f, 0.5f}};
+void gooey_engine_poly_set_preset(GooeyEngine* e, uint32_t preset) {   // set_config: 14 smoothed targets, no snap
+  if (!e) return;
+  gh::aux_touch(e, false);
+  const float* t = GOOEY_POLY_PRESETS[preset < 5 ? preset : 0];
+  for (uint32_t i = 0; i < 14; i++) e->poly.pending.push_back(gh::make_event(0, gd::EV_SET_TARGET, i, t[i]));
+}
+void gooey_engine_poly_set_param(GooeyEngine* e, uint32_t param, float value) {
+  if (!e || param >= 14) return;
+  gh::aux_touch(e, false);
+  e->poly.pending.push_back(gh::make_event(0, gd::EV_SET_TARGET, param, gd::clampf(value, 0.0f, 1.0f)));
+}
+void gooey_engine_poly_release(GooeyEngine* e) {
+  if (!e) return;
+  gh::aux_touch(e, false);
+  e->poly.pending.push_back(gh::make_event(0, gd::EV_POLY_RELEASE, 0, 0.0f));
+}
+// The tail of gooey_engine_poly_trigger_chord (ffi.rs:5594-5611) once `music::apply_voicing` has produced the MIDI notes:
+// preset as smoothed targets, release_all, trigger every note.  (The chord -> notes tables of src/music are host-side
+// integer logic outside this library's scope)
+void gooey_engine_poly_trigger_notes(GooeyEngine* e, const uint8_t* notes, uint32_t n, uint32_t preset, float velocity) {
+  if (!e || (!notes && n)) return;
+  gooey_engine_poly_set_preset(e, preset);
+  const float v = gd::clampf(velocity, 0.0f, 1.0f);
+  e->poly.pending.push_back(gh::make_event(0, gd::EV_POLY_RELEASE, 0, 0.0f));
+  for (uint32_t i = 0; i < n; i++) e->poly.pending.push_back(gh::make_event(0, gd::EV_POLY_NOTE, notes[i], v));
+}
+
+// ---- granulator (ffi.rs:5969-5990, 7702-7827; granulator.rs) ----
+static void gran_attach(GooeyEngine* e) {
+  gh::aux_touch(e, true);
+  const uint64_t ptr = (uint64_t)(uintptr_t)e->gran_buf->p;
+  float lo; uint32_t lo_bits = (uint32_t)ptr; memcpy(&lo, &lo_bits, 4);
+  e->gran.pending.push_back(gh::make_event(0, gd::EV_GRAN_BUFFER, 0, lo, (uint32_t)(ptr >> 32)));   // kills all grains, like set_buffer
+  e->gran.pending.push_back(gh::make_event(0, gd::EV_SET_AUX, gd::AUX_GRAN_BUFINFO, e->gran_sr, e->gran_len));
+}
+bool gooey_engine_granulator_set_buffer(GooeyEngine* e, const float* samples, uint32_t len, float sample_rate) {
+  if (!e || !samples || len == 0) return false;
+  if (!std::isfinite(sample_rate) || !(sample_rate > 0.0f)) return false;            // SampleBuffer::from_mono (granulator.rs:60-90)
+  for (uint32_t i = 0; i < len; i++) if (!std::isfinite(samples[i])) return false;
+  try {
+    gh::use_device(e->bank->device);
+    auto buf = std::make_shared<gh::DevBuf<float>>();
+    buf->alloc(len);
+    GH_CUDA(cudaMemcpy(buf->p, samples, (size_t)len * 4, cudaMemcpyHostToDevice));
+    GH_CUDA(cudaStreamSynchronize(e->bank->stream));   // the previous buffer may still be read by an in-flight render
+    e->gran_buf = buf; e->gran_len = len; e->gran_sr = sample_rate;
+  } catch (const std::exception& ex) { gh::set_error(ex.what()); return false; }
+  gran_attach(e);
+  return true;
+}
+// libgooey_b200 addition: `dst` plays the buffer already loaded into `src` (same device) without another copy —
+// thousands of granulators over one 60 s source keep one 10.6 MB buffer resident instead of one each.
+bool gooey_b200_granulator_share_buffer(GooeyEngine* dst, const GooeyEngine* src) {
+  if (!dst || !src || !src->gran_buf || dst->bank->device != src->bank->device) return false;
+  try { gh::use_device(dst->bank->device); GH_CUDA(cudaStreamSynchronize(dst->bank->stream)); } catch (const std::exception& ex) { gh::set_error(ex.what()); return false; }
+  dst->gran_buf = src->gran_buf; dst->gran_len = src->gran_len; dst->gran_sr = src->gran_sr;
+  gran_attach(dst);
+  return true;
+}
+void gooey_engine_granulator_trigger(GooeyEngine* e, float velocity) {
+  if (!e) return;
+  gh::aux_touch(e, true);
+  e->gran.pending.push_back(gh::make_event(0, gd::EV_TRIGGER, 0, gd::clampf(velocity, 0.0f, 1.0f)));
+}
+void gooey_engine_granulator_set_param(GooeyEngine* e, uint32_t param, float value) {
+  if (!e || param >= 12) return;
+  gh::aux_touch(e, true);
+  e->gran.pending.push_back(gh::make_event(0, gd::EV_SET_TARGET, param, gd::clampf(value, 0.0f, 1.0f)));
+}
+void gooey_engine_granulator_set_seed(GooeyEngine* e, uint32_t seed) {
+  if (!e) return;
+  gh::aux_touch(e, true);
+  e->gran.pending.push_back(gh::make_event(0, gd::EV_GRAN_SEED, 0, 0.0f, seed));
+}
+void gooey_engine_granulator_snap_params(GooeyEngine* e) {
+  if (!e) return;
+  gh::aux_touch(e, true);
+  e->gran.pending.push_back(gh::make_event(0, gd::EV_SNAP, 0, 0.0f));
+}
+uint32_t gooey_engine_granulator_buffer_len(const GooeyEngine* e) { return e ? e->gran_len : 0; }                        /* :7665 */
+float gooey_engine_granulator_buffer_sample_rate(const GooeyEngine* e) { return e ? e->gran_sr : 0.0f; }               /* :7680 */
+
 // Host-only: the trigger schedule the bounce of an engine with this tempo / swing / pattern resolves to (the frames at
 // which kernel events are placed).  Needs no device; used by the CPU tests for the bit-exact trigger-index gate.
 uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing, const uint8_t* enabled, const float* velocity, uint32_t steps,

@@ -49,6 +49,9 @@ static void use_device(int device) {
     float hb[8];
     gd::design_halfband8(hb);
     GH_CUDA(cudaMemcpyToSymbol(gd::c_hb, hb, sizeof hb));
+    double mf[128];   // music/note.rs:81-83 midi_to_freq in f64, with the platform libm
+    for (int n = 0; n < 128; n++) mf[n] = 440.0 * pow(2.0, ((double)n - 69.0) / 12.0);
+    GH_CUDA(cudaMemcpyToSymbol(gd::c_midi_freq, mf, sizeof mf));
     g_dev_ready[device] = 1;
   }
 }
@@ -60,7 +63,9 @@ struct VoiceBank {
   TypeRunner<gd::HatV> hats;
   TypeRunner<gd::TomV> toms;
   TypeRunner<gd::BassV> basses;
-  void reset() { kicks.reset(); snares.reset(); hats.reset(); toms.reset(); basses.reset(); }
+  TypeRunner<gd::PolyV> polys;
+  TypeRunner<gd::GranV> grans;
+  void reset() { kicks.reset(); snares.reset(); hats.reset(); toms.reset(); basses.reset(); polys.reset(); grans.reset(); }
   // returns the pool slot of a new voice built from `p` (the reference's `<Voice>::with_config`); -1 = bad instrument
   int create(const GooeyVoicePatch& p, float sr) {
     switch (p.instrument) {
@@ -69,6 +74,8 @@ struct VoiceBank {
       case GOOEY_INSTRUMENT_HIHAT: { gd::HatState s; init_from_patch(s, p, sr); return hats.pool.alloc(s); }
       case GOOEY_INSTRUMENT_TOM: { gd::TomState s; init_from_patch(s, p, sr); return toms.pool.alloc(s); }
       case GOOEY_INSTRUMENT_BASS: { gd::BassState s; init_from_patch(s, p, sr); return basses.pool.alloc(s); }
+      case GOOEY_B200_VOICE_POLY: { gd::PolyState s; memset(&s, 0, sizeof s); gd::poly_init(s, p.params, sr); return polys.pool.alloc(s); }   // params = PolyConfig (14 values)
+      case GOOEY_B200_VOICE_GRANULATOR: { gd::GranState s; memset(&s, 0, sizeof s); gd::gran_init(s, sr); return grans.pool.alloc(s); }
       default: return -1;
     }
   }
@@ -79,6 +86,19 @@ struct VoiceBank {
       case GOOEY_INSTRUMENT_HIHAT: hats.add(slot, row, ev); break;
       case GOOEY_INSTRUMENT_TOM: toms.add(slot, row, ev); break;
       case GOOEY_INSTRUMENT_BASS: basses.add(slot, row, ev); break;
+      case GOOEY_B200_VOICE_POLY: polys.add(slot, row, ev); break;
+      case GOOEY_B200_VOICE_GRANULATOR: grans.add(slot, row, ev); break;
+    }
+  }
+  void release(uint32_t type, int slot) {
+    switch (type) {
+      case GOOEY_INSTRUMENT_KICK: kicks.pool.release(slot); break;
+      case GOOEY_INSTRUMENT_SNARE: snares.pool.release(slot); break;
+      case GOOEY_INSTRUMENT_HIHAT: hats.pool.release(slot); break;
+      case GOOEY_INSTRUMENT_TOM: toms.pool.release(slot); break;
+      case GOOEY_INSTRUMENT_BASS: basses.pool.release(slot); break;
+      case GOOEY_B200_VOICE_POLY: polys.pool.release(slot); break;
+      case GOOEY_B200_VOICE_GRANULATOR: grans.pool.release(slot); break;
     }
   }
   void launch(cudaStream_t parent, cudaEvent_t start, const gd::RateCtx& rc, const double* tt, int frames, float* out, long long stride) {
@@ -87,10 +107,12 @@ struct VoiceBank {
     hats.launch(parent, start, rc, tt, frames, out, stride);
     toms.launch(parent, start, rc, tt, frames, out, stride);
     basses.launch(parent, start, rc, tt, frames, out, stride);
+    polys.launch(parent, start, rc, tt, frames, out, stride);
+    grans.launch(parent, start, rc, tt, frames, out, stride);
   }
   // frames per output chunk of the last launch (identical for every bucket) and the per-chunk completion fence
   int chunk_frames(int frames) const { return TypeRunner<gd::KickV>::chunk_of(frames, kicks.chunk_frames); }
-  void wait_chunk(cudaStream_t s, int i) { kicks.wait_chunk(s, i); snares.wait_chunk(s, i); hats.wait_chunk(s, i); toms.wait_chunk(s, i); basses.wait_chunk(s, i); }
+  void wait_chunk(cudaStream_t s, int i) { kicks.wait_chunk(s, i); snares.wait_chunk(s, i); hats.wait_chunk(s, i); toms.wait_chunk(s, i); basses.wait_chunk(s, i); polys.wait_chunk(s, i); grans.wait_chunk(s, i); }
 };
 
 }  // namespace gh

@@ -142,7 +142,7 @@ struct BassV { using State = BassState; static constexpr bool FAST = false;
   static __device__ __forceinline__ void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx&) { bass_event(s, e, tt); } };
 struct PolyV { using State = PolyState; static constexpr bool FAST = false;
   static __device__ __forceinline__ float tick(State& s, const double* tt, const RateCtx& rc) { return poly_tick(s, tt, rc); }
-  static __device__ __forceinline__ void slow_event(State& s, const VoiceEvent& e, const double*, const RateCtx&) { poly_event(s, e); } };
+  static __device__ __forceinline__ void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx&) { poly_event(s, e, tt); } };
 struct GranV { using State = GranState; static constexpr bool FAST = false;
   static __device__ __forceinline__ float tick(State& s, const double* tt, const RateCtx& rc) { return gran_tick(s, tt, rc); }
   static __device__ __forceinline__ void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx&) { gran_event(s, e, tt); } };

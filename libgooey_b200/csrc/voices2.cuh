@@ -193,9 +193,10 @@ G_D void poly_trigger_note(PolyState& s, uint32_t note, float velocity) {  // :3
   env_trigger(v.flt_env, time);
   v.filter.ic1 = v.filter.ic2 = 0.0f;
 }
-G_D void poly_event(PolyState& s, const VoiceEvent& e) {
+G_D void poly_event(PolyState& s, const VoiceEvent& e, const double* tt) {
   switch (e.kind) {
-    case EV_SET_TIME: s.k = e.aux; break;
+    // param 1: the voice was not ticked while untouched; catch up `current_time` = time of the engine's previous tick
+    case EV_SET_TIME: s.k = e.aux; if (e.param == 1) s.last_tick_time = e.aux ? tt[e.aux - 1] : 0.0; break;
     case EV_POLY_NOTE: poly_trigger_note(s, e.param, e.value); break;
     case EV_POLY_RELEASE: { double t = s.last_tick_time; for (int k = 0; k < 6; k++) if (s.v[k].active) { env_release(s.v[k].amp_env, t); env_release(s.v[k].flt_env, t); } } break;
     case EV_SET_TARGET: if (e.param < P_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;

@@ -26,6 +26,9 @@ _SIGS = {
     "mixer_set_track_gain": [c.c_uint32, c.c_float], "mixer_set_track_pan": [c.c_uint32, c.c_float],
     "mixer_set_track_mute": [c.c_uint32, c.c_bool], "mixer_set_track_solo": [c.c_uint32, c.c_bool],
     "track_effect_set_param": [c.c_uint32, c.c_uint32, c.c_uint32, c.c_float],
+    "poly_release": [], "poly_set_preset": [c.c_uint32], "poly_set_param": [c.c_uint32, c.c_float],
+    "granulator_trigger": [c.c_float], "granulator_set_param": [c.c_uint32, c.c_float], "granulator_set_seed": [c.c_uint32],
+    "granulator_snap_params": [],
 }
 _bound = set()
 
@@ -46,6 +49,8 @@ def _bind(L, prefix):
     f = getattr(L, prefix + "mixer_add_track"); f.argtypes = [c.c_void_p, c.c_char_p]; f.restype = c.c_int32
     f = getattr(L, prefix + "mixer_route_source"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_bool
     f = getattr(L, prefix + "track_effect_add"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_int32
+    f = getattr(L, prefix + "poly_trigger_notes"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]; f.restype = None
+    f = getattr(L, prefix + "granulator_set_buffer"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32, c.c_float]; f.restype = c.c_bool
     f = getattr(L, prefix + "render"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32]; f.restype = None
     f = getattr(L, prefix + "bounce_to_buffer"); f.argtypes = [c.c_void_p, c.c_uint32, c.POINTER(c.c_uint32)]; f.restype = c.POINTER(c.c_float)
     f = getattr(L, prefix + "free_buffer"); f.argtypes = [c.POINTER(c.c_float), c.c_uint32]; f.restype = None
@@ -89,6 +94,22 @@ class Engine:
 
     def track_effect_add(self, track, effect_id):
         return int(getattr(self._L, self._prefix + "track_effect_add")(self._h, track, effect_id))
+
+    def poly_trigger_notes(self, notes, preset=0, velocity=1.0):
+        """The tail of gooey_engine_poly_trigger_chord once the voicing has produced MIDI notes (ffi.rs:5594-5611)."""
+        arr = np.asarray(notes, np.uint8)
+        getattr(self._L, self._prefix + "poly_trigger_notes")(self._h, arr.ctypes.data, len(arr), preset, c.c_float(velocity))
+
+    def granulator_set_buffer(self, samples, sample_rate):
+        """gooey_engine_granulator_set_buffer (copies; False on empty / non-finite input)."""
+        arr = np.ascontiguousarray(samples, np.float32)
+        return bool(getattr(self._L, self._prefix + "granulator_set_buffer")(self._h, arr.ctypes.data, len(arr), c.c_float(sample_rate)))
+
+    def granulator_share_buffer(self, other):
+        """libgooey_b200 addition: play the buffer already resident for `other` (no second device copy)."""
+        f = self._L.gooey_b200_granulator_share_buffer
+        f.argtypes = [c.c_void_p, c.c_void_p]; f.restype = c.c_bool
+        return bool(f(self._h, other._h))
 
     def render(self, frames):
         """gooey_engine_render: (frames, 2) interleaved stereo."""
