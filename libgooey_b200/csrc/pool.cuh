@@ -14,6 +14,12 @@
 #include <mutex>
 #include "device_rt.h"
 #include "wave.cuh"
+#ifndef GOOEY_WAVE_G_KICK
+#define GOOEY_WAVE_G_KICK 32
+#define GOOEY_WAVE_G_SNARE 32
+#define GOOEY_WAVE_G_HAT 32
+#define GOOEY_WAVE_G_TOM 32
+#endif
 #include "../../include/gooey_batch.h"
 
 namespace gh {
@@ -113,12 +119,48 @@ struct ClockTable {
 };
 ClockTable& clock_table(float sr);
 
-// Which voice types have a warp-per-voice scan back-end (wave.cuh); the others use back_kernel (one voice per lane).
-template <class V> struct WaveOf { static constexpr bool has = false; using type = void; };
-template <> struct WaveOf<gd::KickV> { static constexpr bool has = true; using type = gd::KickW; };
-template <> struct WaveOf<gd::SnareV> { static constexpr bool has = true; using type = gd::SnareW; };
-template <> struct WaveOf<gd::HatV> { static constexpr bool has = true; using type = gd::HatW; };
-template <> struct WaveOf<gd::TomV> { static constexpr bool has = true; using type = gd::TomW; };
+// Which voice types have a scan back-end (wave.cuh); the others use back_kernel (one voice per lane).  ID indexes the
+// per-type group width table below.
+template <class V> struct WaveOf { static constexpr bool has = false; static constexpr int ID = -1; };
+template <> struct WaveOf<gd::KickV> { static constexpr bool has = true; static constexpr int ID = 0; using w32 = gd::w32::KickW;
+#ifdef GOOEY_WAVE_ALL_WIDTHS
+  using w16 = gd::w16::KickW; using w8 = gd::w8::KickW;
+#endif
+};
+template <> struct WaveOf<gd::SnareV> { static constexpr bool has = true; static constexpr int ID = 1; using w32 = gd::w32::SnareW;
+#ifdef GOOEY_WAVE_ALL_WIDTHS
+  using w16 = gd::w16::SnareW; using w8 = gd::w8::SnareW;
+#endif
+};
+template <> struct WaveOf<gd::HatV> { static constexpr bool has = true; static constexpr int ID = 2; using w32 = gd::w32::HatW;
+#ifdef GOOEY_WAVE_ALL_WIDTHS
+  using w16 = gd::w16::HatW; using w8 = gd::w8::HatW;
+#endif
+};
+template <> struct WaveOf<gd::TomV> { static constexpr bool has = true; static constexpr int ID = 3; using w32 = gd::w32::TomW;
+#ifdef GOOEY_WAVE_ALL_WIDTHS
+  using w16 = gd::w16::TomW; using w8 = gd::w8::TomW;
+#endif
+};
+// Lanes per voice for kick / snare / hat / tom (see wave.cuh "Group width").  GOOEY_B200_WAVE_G="32,32,8,8" overrides
+// (tuning only; every width renders the same audio up to the scans' re-association noise).
+inline int wave_group_width(int id) {
+  static int table[4] = {0, 0, 0, 0};
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const int def[4] = {GOOEY_WAVE_G_KICK, GOOEY_WAVE_G_SNARE, GOOEY_WAVE_G_HAT, GOOEY_WAVE_G_TOM};
+    for (int i = 0; i < 4; i++) table[i] = def[i];
+    if (const char* e = getenv("GOOEY_B200_WAVE_G")) {
+      int v[4];
+      if (sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+        for (int i = 0; i < 4; i++) if (v[i] == 8 || v[i] == 16 || v[i] == 32) table[i] = v[i];
+    }
+#ifndef GOOEY_WAVE_ALL_WIDTHS
+    for (int i = 0; i < 4; i++) table[i] = 32;
+#endif
+  });
+  return table[id];
+}
 // GOOEY_B200_BACKEND=serial forces the per-sample-order back-end (kernel C) everywhere: the A/B switch used by the
 // parity tests to compare the two back-ends.
 inline bool serial_backend() { const char* e = getenv("GOOEY_B200_BACKEND"); return e && strcmp(e, "serial") == 0; }
@@ -226,8 +268,16 @@ template <class V> struct TypeRunner {
         GH_CUDA(cudaEventRecord(evB[b], sB));
         GH_CUDA(cudaStreamWaitEvent(sC, evB[b], 0));
         if constexpr (WaveOf<V>::has) {
-          if (!serial_backend()) gd::wave_kernel<typename WaveOf<V>::type, GOOEY_WAVE_WARPS><<<(cnt + GOOEY_WAVE_WARPS - 1) / GOOEY_WAVE_WARPS, GOOEY_WAVE_WARPS * 32, 0, sC>>>(L);   // one warp per voice
-          else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
+          if (!serial_backend()) {
+            const int g = wave_group_width(WaveOf<V>::ID);          // voices per warp = 32 / g, one warp per CTA
+            const int warps = (cnt * g + 31) / 32;
+#ifdef GOOEY_WAVE_ALL_WIDTHS
+            if (g == 16) gd::w16::wave_kernel<typename WaveOf<V>::w16, 1><<<warps, 32, 0, sC>>>(L);
+            else if (g == 8) gd::w8::wave_kernel<typename WaveOf<V>::w8, 1><<<warps, 32, 0, sC>>>(L);
+            else
+#endif
+            gd::w32::wave_kernel<typename WaveOf<V>::w32, 1><<<warps, 32, 0, sC>>>(L);
+          } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
         } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());
         GH_CUDA(cudaEventRecord(evC[b], sC));

@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests_3.log 2>&1; tail -3 gpurun_out/gpu_tests_3.log
-python bench.py --steps 3 --warmup 2 > gpurun_out/bench_r1_g.json 2> gpurun_out/bench_r1_g.err; cat gpurun_out/bench_r1_g.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('main', d['ms_per_step'], d['e2e']['ms_per_step'])"
-for v in m12 m16 w2_m8 w4_m3 w4_m4; do GOOEY_B200_LIB=$PWD/libgooey_b200/lib/exp/lib_$v.so python bench.py --steps 3 --warmup 2 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['ms_per_step'], d['e2e']['ms_per_step'], d['checksum'])"; done
+for g in 32 8; do
+GOOEY_B200_WAVE_G=$g,$g,$g,$g ncu --metrics smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.per_cycle_active --clock-control none -k regex:wave_kernel -s 8 -c 8 --csv --log-file gpurun_out/ncu_g$g.csv python bench.py --steps 1 --warmup 1 > /dev/null 2>&1
+done
