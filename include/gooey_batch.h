@@ -64,6 +64,10 @@ int gooey_b200_device_count(void);
 uint64_t gooey_b200_launch_count(void);
 /* Device time (ms, CUDA events on the launching stream) of the most recent render call's kernels. */
 float gooey_b200_last_kernel_ms(void);
+/* Accumulated device time of one back-end kernel ("wave_kernel<KickW>" / "<SnareW>" / "<HatW>" / "<TomW>") since load or
+ * the last reset: launches, summed launch durations (ms, CUDA events on the launching stream) and voice-frames written. */
+int gooey_b200_kernel_stat(const char* kernel, uint64_t* launches, double* total_ms, double* voice_frames);
+void gooey_b200_kernel_stats_reset(void);
 
 /* Voice-level batch: n voices built `with_config`, then driven by per-voice events. */
 int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoicePatch* patches, int device,

@@ -12,6 +12,8 @@ namespace gh {
 std::string& last_error() { static thread_local std::string e; return e; }
 std::atomic<uint64_t> g_launches{0};
 static float g_last_kernel_ms = 0.0f;
+std::map<std::string, KernelStat>& kernel_stats() { static std::map<std::string, KernelStat> m; return m; }
+std::mutex& kernel_stats_mutex() { static std::mutex m; return m; }
 
 ClockTable& clock_table(float sr) {
   static std::mutex mu;
@@ -110,6 +112,8 @@ struct VoiceBank {
     polys.launch(parent, start, rc, tt, frames, out, stride);
     grans.launch(parent, start, rc, tt, frames, out, stride);
   }
+  // call after the launching stream has been synchronised
+  void collect_stats() { kicks.collect_stats("wave_kernel<KickW>"); snares.collect_stats("wave_kernel<SnareW>"); hats.collect_stats("wave_kernel<HatW>"); toms.collect_stats("wave_kernel<TomW>"); }
   // frames per output chunk of the last launch (identical for every bucket) and the per-chunk completion fence
   int chunk_frames(int frames) const { return TypeRunner<gd::KickV>::chunk_of(frames, kicks.chunk_frames); }
   void wait_chunk(cudaStream_t s, int i) { kicks.wait_chunk(s, i); snares.wait_chunk(s, i); hats.wait_chunk(s, i); toms.wait_chunk(s, i); basses.wait_chunk(s, i); polys.wait_chunk(s, i); grans.wait_chunk(s, i); }
@@ -180,6 +184,17 @@ const char* gooey_b200_last_error(void) { return gh::last_error().c_str(); }
 int gooey_b200_device_count(void) { return gh::device_count(); }
 uint64_t gooey_b200_launch_count(void) { return gh::g_launches.load(); }
 float gooey_b200_last_kernel_ms(void) { return gh::g_last_kernel_ms; }
+int gooey_b200_kernel_stat(const char* kernel, uint64_t* launches, double* total_ms, double* voice_frames) {
+  if (!kernel) return GOOEY_E_INVALID;
+  std::lock_guard<std::mutex> lk(gh::kernel_stats_mutex());
+  auto it = gh::kernel_stats().find(kernel);
+  gh::KernelStat k = it == gh::kernel_stats().end() ? gh::KernelStat() : it->second;
+  if (launches) *launches = k.launches;
+  if (total_ms) *total_ms = k.ms;
+  if (voice_frames) *voice_frames = k.voice_frames;
+  return GOOEY_E_OK;
+}
+void gooey_b200_kernel_stats_reset(void) { std::lock_guard<std::mutex> lk(gh::kernel_stats_mutex()); gh::kernel_stats().clear(); }
 
 int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoicePatch* patches, int device, GooeyVoiceBatch** out_batch) {
   GOOEY_TRY
@@ -245,6 +260,7 @@ int gooey_voice_batch_render_device(GooeyVoiceBatch* b, uint32_t frames, float* 
   voice_batch_render_impl(b, frames, out_dev, stride);
   GH_CUDA(cudaStreamSynchronize(b->stream));
   GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, b->ev0, b->ev1));
+  b->bank.collect_stats();
   return GOOEY_E_OK;
   GOOEY_CATCH
 }
@@ -267,6 +283,7 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
   GH_CUDA(cudaStreamSynchronize(b->copy_stream));
   GH_CUDA(cudaStreamSynchronize(b->stream));
   GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, b->ev0, b->ev1));
+  b->bank.collect_stats();
   return GOOEY_E_OK;
   GOOEY_CATCH
 }

@@ -26,6 +26,11 @@ namespace gh {
 
 extern std::atomic<uint64_t> g_launches;
 
+// Per-kernel device time, measured with CUDA events on the stream the kernel is launched on (bench.py's roofline line).
+struct KernelStat { uint64_t launches = 0; double ms = 0.0; double voice_frames = 0.0; };
+std::map<std::string, KernelStat>& kernel_stats();
+std::mutex& kernel_stats_mutex();
+
 __global__ void scatter_words_kernel(uint32_t* __restrict__ dst, long long cap, const uint32_t* __restrict__ src, const uint32_t* __restrict__ slots,
                                      int n, int words) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +182,8 @@ template <class V> struct TypeRunner {
   DevBuf<float> d_planes[2];
   cudaStream_t sB = nullptr, sC = nullptr, sS = nullptr;
   cudaEvent_t evA = nullptr, evB[2] = {nullptr, nullptr}, evC[2] = {nullptr, nullptr}, evDoneC = nullptr, evDoneS = nullptr;
+  std::vector<cudaEvent_t> evT0, evT1;   // timing brackets of the back-end launch of chunk i (on sC)
+  std::vector<double> timed_units;       // voice-frames of that launch
   std::vector<cudaEvent_t> evChunk;      // evChunk[i]: frames of chunk i are final in the output (fast-path voices)
   int chunk_frames = 8192;
   int launched_chunks = 0;               // chunks of the most recent launch (0 = one undivided launch)
@@ -186,7 +193,7 @@ template <class V> struct TypeRunner {
     if (n() == 0) return;
     if (launched_chunks == 0) { GH_CUDA(cudaStreamWaitEvent(s, evDoneC, 0)); return; }
     GH_CUDA(cudaStreamWaitEvent(s, evDoneS, 0));
-    GH_CUDA(cudaStreamWaitEvent(s, evChunk[std::min(i, launched_chunks - 1)], 0));
+    GH_CUDA(cudaStreamWaitEvent(s, evChunk[std::min(i, std::abs(launched_chunks) - 1)], 0));
   }
 
   int n() const { return (int)slots.size(); }
@@ -212,9 +219,23 @@ template <class V> struct TypeRunner {
     cudaEvent_t evs[] = {evA, evB[0], evB[1], evC[0], evC[1], evDoneC, evDoneS};
     for (auto e : evs) if (e) cudaEventDestroy(e);
     for (auto e : evChunk) cudaEventDestroy(e);
+    for (auto e : evT0) cudaEventDestroy(e);
+    for (auto e : evT1) cudaEventDestroy(e);
     if (sB) cudaStreamDestroy(sB);
     if (sC) cudaStreamDestroy(sC);
     if (sS) cudaStreamDestroy(sS);
+  }
+  // After the launch's streams have been synchronised: add the back-end launches of the last call to the global table.
+  void collect_stats(const char* name) {
+    if (launched_chunks <= 0) return;
+    std::lock_guard<std::mutex> lk(kernel_stats_mutex());
+    KernelStat& k = kernel_stats()[name];
+    for (int i = 0; i < launched_chunks; i++) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, evT0[i], evT1[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+      k.launches++; k.ms += ms; k.voice_frames += timed_units[i];
+    }
+    launched_chunks = -launched_chunks;   // collected once
   }
   // Forks from `parent` (after `start`), runs the bucket on its own streams, joins back into `parent`.
   void launch(cudaStream_t parent, cudaEvent_t start, const gd::RateCtx& rc, const double* tt, int frames, float* out, long long stride) {
@@ -267,6 +288,9 @@ template <class V> struct TypeRunner {
         GH_CUDA(cudaGetLastError());
         GH_CUDA(cudaEventRecord(evB[b], sB));
         GH_CUDA(cudaStreamWaitEvent(sC, evB[b], 0));
+        if ((int)evT0.size() <= i) { cudaEvent_t e0, e1; GH_CUDA(cudaEventCreate(&e0)); GH_CUDA(cudaEventCreate(&e1)); evT0.push_back(e0); evT1.push_back(e1); timed_units.push_back(0.0); }
+        timed_units[i] = (double)cnt * L.chunk_frames;
+        GH_CUDA(cudaEventRecord(evT0[i], sC));
         if constexpr (WaveOf<V>::has) {
           if (!serial_backend()) {
             const int g = wave_group_width(WaveOf<V>::ID);          // voices per warp = 32 / g, one warp per CTA
@@ -280,6 +304,7 @@ template <class V> struct TypeRunner {
           } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
         } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());
+        GH_CUDA(cudaEventRecord(evT1[i], sC));
         GH_CUDA(cudaEventRecord(evC[b], sC));
         if ((int)evChunk.size() <= i) { cudaEvent_t e; GH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); evChunk.push_back(e); }
         GH_CUDA(cudaEventRecord(evChunk[i], sC));

@@ -1,3 +1,4 @@
-for g in 32 8; do
-GOOEY_B200_WAVE_G=$g,$g,$g,$g ncu --metrics smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.per_cycle_active --clock-control none -k regex:wave_kernel -s 8 -c 8 --csv --log-file gpurun_out/ncu_g$g.csv python bench.py --steps 1 --warmup 1 > /dev/null 2>&1
+export GOOEY_B200_LIB=$PWD/libgooey_b200/lib/exp/lib_allw.so
+for cfg in 32,32,32,32 32,32,16,16 32,32,8,8 32,32,32,16 32,32,16,32 32,32,8,16 32,32,32,8 16,32,32,32 32,16,32,32; do
+  GOOEY_B200_WAVE_G=$cfg python bench.py --steps 3 --warmup 2 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('G=$cfg', 'dev ms', round(d['ms_per_step'],2), 'e2e ms', round(d['e2e']['ms_per_step'],2), {k[12:-1]: round(v['avg_ms'],2) for k,v in d['kernels'].items()})"
 done
