@@ -104,6 +104,8 @@ struct EngineBank {
   DevBuf<float> d_voice_buf, d_out;
   DevBuf<float> d_silent;                 // the granulator's 1-sample silent placeholder buffer (ffi.rs:929-933)
   DevBuf<uint32_t> d_mix_slots, d_mix_ev_begin;
+  DevBuf<uint8_t> d_mix_fast;
+  DevBuf<gd::MixConst> d_mix_consts;
   DevBuf<gd::VoiceEvent> d_mix_events;
   std::mutex mu;
   float last_ms = 0.0f;
@@ -393,8 +395,20 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   std::vector<gd::VoiceEvent> cur, mflat;
   std::vector<uint32_t> mbegin;
   std::vector<size_t> vpos((size_t)n * 7, 0), mpos(n, 0);
-  for (uint32_t f0 = 0; f0 < frames; f0 += (uint32_t)piece) {
-    const uint32_t nf = std::min<uint32_t>((uint32_t)piece, frames - f0);
+  // Piece schedule.  Parameters edited through the FFI glide for ~10 smoother time constants (kick.rs: 15 ms -> ~6000
+  // samples) and the planner keeps a voice on the per-sample general path for a whole piece while anything glides, so the
+  // first pieces are short: a gliding voice re-enters the time-parallel path within a few thousand frames.
+  std::vector<uint32_t> cuts;
+  {
+    const uint32_t lead[4] = {4096, 4096, 8192, 16384};
+    uint32_t f = 0;
+    for (int k = 0; k < 4 && f + lead[k] < frames && lead[k] < piece; k++) { f += lead[k]; cuts.push_back(f); }
+    while (f + piece < frames) { f += (uint32_t)piece; cuts.push_back(f); }
+    cuts.push_back(frames);
+  }
+  uint32_t f0 = 0;
+  for (size_t pc = 0; pc < cuts.size(); f0 = cuts[pc], pc++) {
+    const uint32_t nf = cuts[pc] - f0;
     B.voices.reset();
     for (int i = 0; i < n; i++)
       for (int ch = 0; ch < 7; ch++) {
@@ -433,8 +447,12 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     M.out = out_dev + (out_mode == OUT_MONO ? (size_t)f0 : (size_t)2 * f0); M.out_stride = (long long)stride; M.out_mode = out_mode; M.out_rows = nullptr;
     M.rc = B.rc; M.geo = B.geo;
     M.center_l = gm::g_cosf(0.5f * 1.57079632679489661923f); M.center_r = gm::g_sinf(0.5f * 1.57079632679489661923f);
+    B.d_mix_fast.alloc(n); B.d_mix_consts.alloc(n);
+    M.fast = B.d_mix_fast.p; M.consts = B.d_mix_consts.p;
+    gd::mix_prepare_kernel<<<(n + 127) / 128, 128, 0, st>>>(M);
+    gd::mix_fast_kernel<<<dim3((nf + 1023) / 1024, n), 256, 0, st>>>(M);
     gd::mix_kernel<<<(n + 31) / 32, 32, 0, st>>>(M);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_launches.fetch_add(3, std::memory_order_relaxed);
     GH_CUDA(cudaGetLastError());
   }
   GH_CUDA(cudaEventRecord(B.ev1, st));

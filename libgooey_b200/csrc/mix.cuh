@@ -84,6 +84,17 @@ struct MixLaunch {
   const uint32_t* out_rows;
   RateCtx rc; FxGeom geo;
   float center_l, center_r;           // cos/sin(0.5 * pi/2) for the center-panned poly / granulator (ffi.rs:1287-1288)
+  // time-parallel path for engines whose mixer is memoryless over this launch (see mix_prepare_kernel)
+  uint8_t* fast;                      // [n] 1 = handled by mix_fast_kernel, the general kernel skips it
+  struct MixConst* consts;            // [n]
+};
+// Everything mix_fast_kernel needs for one engine: the settled smoother values and the trig of the constant pans.
+struct MixConst {
+  float g[N_VOICE_CH], m[N_VOICE_CH], pc[N_VOICE_CH], ps[N_VOICE_CH];
+  float tgain[MAX_TRACKS], tbl[MAX_TRACKS], tbr[MAX_TRACKS];
+  float master, lim_th, lim_inv;
+  uint32_t n_tracks, limiter_on, src_poly, src_gran;
+  int32_t route[5];
 };
 
 // ---------------------------------------------------------------- effect constructors (device + host) ----
@@ -388,8 +399,9 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
   const int lane = threadIdx.x;
   const int warp_i0 = i - lane;
   if (warp_i0 >= L.n) return;
-  const bool valid = i < L.n;
+  const bool valid = i < L.n && !(L.fast && L.fast[i]);
   const uint32_t row_mask = __ballot_sync(0xffffffffu, valid);
+  if (row_mask == 0) return;
   const int n_rows = min(32, L.n - warp_i0);
   MixState st;
   MixCfg cfg;
@@ -470,6 +482,115 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
     __syncwarp();
   }
   if (valid) store_words(st, L.state, es, L.state_cap, 0);
+}
+
+// ---- time-parallel mixer ------------------------------------------------------------------------------------------
+// With no effect in the chain or in any rack, the mixer's only memory is its smoothed parameters.  Once they have
+// settled (cur == tgt, so SmoothedParam::tick returns the same value every sample) every output frame is the same
+// pure function of that frame's voice samples, evaluated here in the reference's operation order — one thread per
+// (engine, 4 frames) instead of one thread per engine.  mix_prepare_kernel (thread per engine) applies the launch's
+// frame-0 events, decides eligibility and freezes the constants; events later in the launch disqualify the engine.
+__global__ void __launch_bounds__(128) mix_prepare_kernel(const MixLaunch L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.n) return;
+  const int es = (int)L.slots[i];
+  const MixCfg cfg = L.cfg[es];
+  const uint32_t ev0 = L.ev_begin[i], ev1 = L.ev_begin[i + 1];
+  bool ok = true;
+  for (int s = 0; s < 4; s++) ok = ok && !cfg.fx_enabled[s];
+  for (uint32_t t = 0; t < cfg.n_tracks; t++) ok = ok && cfg.rack_n[t] == 0;
+  for (uint32_t e = ev0; e < ev1; e++) ok = ok && L.events[e].frame == 0 && L.events[e].kind != MX_FX_INIT;
+  if (!ok) { L.fast[i] = 0; return; }
+  MixState st;
+  load_words(st, L.state, es, L.state_cap, 0);
+  for (uint32_t e = ev0; e < ev1; e++) mix_event(st, cfg, L.events[e], L.rc);
+  for (int c = 0; c < N_VOICE_CH; c++) ok = ok && st.ch_gain[c].c == st.ch_gain[c].t && st.ch_mute[c].c == st.ch_mute[c].t && st.ch_pan[c].c == st.ch_pan[c].t;
+  for (uint32_t t = 0; t < cfg.n_tracks; t++) ok = ok && st.tr_gain[t].c == st.tr_gain[t].t && st.tr_mute[t].c == st.tr_mute[t].t && st.tr_pan[t].c == st.tr_pan[t].t;
+  ok = ok && st.master.c == st.master.t;
+  L.fast[i] = ok ? 1 : 0;
+  if (!ok) return;                                   // state untouched: the general kernel re-applies the events itself
+  store_words(st, L.state, es, L.state_cap, 0);      // events consumed
+  MixConst k;
+  for (int c = 0; c < N_VOICE_CH; c++) {
+    k.g[c] = st.ch_gain[c].c; k.m[c] = st.ch_mute[c].c;
+    const float ang = clampf(st.ch_pan[c].c, 0.0f, 1.0f) * 1.57079632679489661923f;
+    k.pc[c] = gm::g_cosf(ang); k.ps[c] = gm::g_sinf(ang);
+  }
+  for (int t = 0; t < MAX_TRACKS; t++) {
+    k.tgain[t] = st.tr_gain[t].c * st.tr_mute[t].c;
+    const float pan = clampf(st.tr_pan[t].c, 0.0f, 1.0f);
+    k.tbl[t] = fminf(2.0f * (1.0f - pan), 1.0f); k.tbr[t] = fminf(2.0f * pan, 1.0f);
+  }
+  k.master = st.master.c; k.lim_th = cfg.lim_th; k.lim_inv = cfg.lim_inv;
+  k.n_tracks = cfg.n_tracks; k.limiter_on = cfg.limiter_on; k.src_poly = cfg.src_poly; k.src_gran = cfg.src_gran;
+  for (int s = 0; s < 5; s++) k.route[s] = cfg.route[s];
+  L.consts[i] = k;
+}
+
+__device__ __forceinline__ void mix_fast_frame(const MixConst& k, const float* x, float center_l, float center_r, float& ml, float& mr) {
+  float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
+#pragma unroll
+  for (int c = 0; c < N_VOICE_CH; c++) {
+    const float v = x[c] * k.g[c] * k.m[c];
+    const float pl = v * k.pc[c], pr = v * k.ps[c];
+    if (c < 4) { kit_l += pl; kit_r += pr; } else { bass_l += pl; bass_r += pr; }
+  }
+  float src_l[5] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f}, src_r[5] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f};
+  if (k.src_poly) { src_l[2] = x[5] * center_l; src_r[2] = x[5] * center_r; }
+  if (k.src_gran) { src_l[3] = x[6] * center_l; src_r[3] = x[6] * center_r; }
+  ml = 0.0f; mr = 0.0f;
+  for (uint32_t t = 0; t < k.n_tracks; t++) {
+    float fl = 0.0f, fr = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 5; s++) if (k.route[s] == (int32_t)t) { fl += src_l[s]; fr += src_r[s]; }
+    fl *= k.tgain[t]; fr *= k.tgain[t];
+    fl *= k.tbl[t]; fr *= k.tbr[t];
+    ml += fl; mr += fr;
+  }
+  ml *= k.master; mr *= k.master;
+  if (k.limiter_on) { ml = gm::g_tanhf(ml * k.lim_inv) * k.lim_th; mr = gm::g_tanhf(mr * k.lim_inv) * k.lim_th; }
+}
+
+// grid = (ceil(frames / 1024), n engines), 256 threads, 4 frames per thread
+__global__ void __launch_bounds__(256) mix_fast_kernel(const MixLaunch L) {
+  const int i = blockIdx.y;
+  if (!L.fast[i]) return;
+  const int f = (blockIdx.x * 256 + threadIdx.x) * 4;
+  __shared__ MixConst ks;
+  if (threadIdx.x == 0) ks = L.consts[i];
+  __syncthreads();
+  if (f >= L.frames) return;
+  const int nf = min(4, L.frames - f);
+  const bool vec_in = nf == 4 && (L.voice_stride & 3) == 0;
+  float x[MIX_CH][4];
+#pragma unroll
+  for (int c = 0; c < MIX_CH; c++) {
+    x[c][0] = x[c][1] = x[c][2] = x[c][3] = 0.0f;
+    if (!((L.chan_mask >> c) & 1u)) continue;
+    if (c == 5 && !ks.src_poly) continue;
+    if (c == 6 && !ks.src_gran) continue;
+    const float* row = L.voice_buf + (long long)(c * L.n_lpad + i) * L.voice_stride + f;
+    if (vec_in) { const float4 v = *reinterpret_cast<const float4*>(row); x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w; }
+    else for (int q = 0; q < nf; q++) x[c][q] = row[q];
+  }
+  float ol[4], orr[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    float xs[MIX_CH];
+#pragma unroll
+    for (int c = 0; c < MIX_CH; c++) xs[c] = x[c][q];
+    mix_fast_frame(ks, xs, L.center_l, L.center_r, ol[q], orr[q]);
+  }
+  const long long row = L.out_rows ? (long long)L.out_rows[i] : (long long)i;
+  if (L.out_mode == 0) {
+    float* dst = L.out + row * L.out_stride + f;
+    if (nf == 4 && (L.out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(L.out) & 15) == 0)
+      *reinterpret_cast<float4*>(dst) = make_float4(0.5f * (ol[0] + orr[0]), 0.5f * (ol[1] + orr[1]), 0.5f * (ol[2] + orr[2]), 0.5f * (ol[3] + orr[3]));
+    else for (int q = 0; q < nf; q++) dst[q] = 0.5f * (ol[q] + orr[q]);
+  } else {
+    float* dst = L.out + row * L.out_stride + 2LL * f;
+    for (int q = 0; q < nf; q++) { dst[2 * q] = ol[q]; dst[2 * q + 1] = orr[q]; }
+  }
 }
 #endif  // __CUDACC__
 
