@@ -29,6 +29,11 @@ ClockTable& clock_table(float sr) {
   return *it->second;
 }
 
+// One hardware work queue per stream: the render uses up to 3 streams per voice type plus a copy stream, and with the
+// default of 8 connections independent launches alias onto the same queue and serialise.  Read by the driver when the
+// context is created, so it is set when the library is loaded (never overriding the host's own choice).
+static const int g_conn_env = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+
 // ---- device bring-up --------------------------------------------------------------------------
 static std::mutex g_dev_mutex;
 static std::vector<char> g_dev_ready;

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <set>
 #include <mutex>
 #include "device_rt.h"
 #include "wave.cuh"
@@ -170,6 +171,25 @@ inline int wave_group_width(int id) {
 // parity tests to compare the two back-ends.
 inline bool serial_backend() { const char* e = getenv("GOOEY_B200_BACKEND"); return e && strcmp(e, "serial") == 0; }
 
+// Kernels whose shared-memory carve-out differs cannot share an SM: the L1 / shared split is an SM-wide setting, so a
+// back end with 19 KB of scan tables per CTA and one with 3.5 KB would be given disjoint SMs instead of interleaving
+// their warps.  Every kernel of the render is therefore pinned to the same (maximum shared) carve-out, once per device.
+template <class K> inline void same_carveout(K kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.insert({dev, (const void*)kernel}).second)
+    GH_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+}
+#define GH_LAUNCH(kernel, grid, block, stream, ...) do { same_carveout(kernel); kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); } while (0)
+
+// Frames per front/back pipeline stage.  GOOEY_B200_CHUNK overrides (tuning).
+inline int default_chunk_frames() {
+  if (const char* e = getenv("GOOEY_B200_CHUNK")) { int v = atoi(e); if (v >= 1024 && v <= (1 << 20)) return (v + 31) & ~31; }
+  return 8192;
+}
 // One type bucket of one render call.
 template <class V> struct TypeRunner {
   using State = typename V::State;
@@ -185,7 +205,7 @@ template <class V> struct TypeRunner {
   std::vector<cudaEvent_t> evT0, evT1;   // timing brackets of the back-end launch of chunk i (on sC)
   std::vector<double> timed_units;       // voice-frames of that launch
   std::vector<cudaEvent_t> evChunk;      // evChunk[i]: frames of chunk i are final in the output (fast-path voices)
-  int chunk_frames = 8192;
+  int chunk_frames = default_chunk_frames();
   int launched_chunks = 0;               // chunks of the most recent launch (0 = one undivided launch)
   static int chunk_of(int frames, int chunk_frames) { return std::min(chunk_frames, (frames + 31) & ~31); }
   // Makes `s` wait until every voice of this bucket has written frames [i * chunk, (i + 1) * chunk) of the last launch.
@@ -266,14 +286,14 @@ template <class V> struct TypeRunner {
       d_planes[0].alloc(plane_floats * V::NPL); d_planes[1].alloc(plane_floats * V::NPL);
       L.mode = d_mode.p; L.spans = d_spans.p; L.span_off = d_span_off.p; L.n_spans = d_n_spans.p; L.span_cursor = d_span_cursor.p;
       L.plane_stride = (long long)plane_floats; L.pitch = chunk;
-      gd::plan_kernel<V><<<(cnt + 63) / 64, 64, 0, sC>>>(L);
+      GH_LAUNCH((gd::plan_kernel<V>), (cnt + 63) / 64, 64, sC, L);
       g_launches.fetch_add(1, std::memory_order_relaxed);
       GH_CUDA(cudaGetLastError());
       GH_CUDA(cudaEventRecord(evA, sC));
       GH_CUDA(cudaStreamWaitEvent(sB, evA, 0));
       GH_CUDA(cudaStreamWaitEvent(sS, evA, 0));
       // general path for the voices A could not plan (whole call, one launch)
-      gd::slow_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sS>>>(L);
+      GH_LAUNCH((gd::slow_kernel<V, 32>), (cnt + 31) / 32, 32, sS, L);
       g_launches.fetch_add(1, std::memory_order_relaxed);
       GH_CUDA(cudaGetLastError());
       GH_CUDA(cudaEventRecord(evDoneS, sS));
@@ -284,7 +304,7 @@ template <class V> struct TypeRunner {
         L.planes = d_planes[b].p;
         if (i >= 2) GH_CUDA(cudaStreamWaitEvent(sB, evC[b], 0));   // plane buffer b is free once C of chunk i-2 is done
         const int bpv = (L.chunk_frames + 255) / 256;
-        gd::front_kernel<V, 256><<<(unsigned)((size_t)cnt * bpv), 256, 0, sB>>>(L, bpv);
+        GH_LAUNCH((gd::front_kernel<V, 256>), (unsigned)((size_t)cnt * bpv), 256, sB, L, bpv);
         GH_CUDA(cudaGetLastError());
         GH_CUDA(cudaEventRecord(evB[b], sB));
         GH_CUDA(cudaStreamWaitEvent(sC, evB[b], 0));
@@ -296,13 +316,13 @@ template <class V> struct TypeRunner {
             const int g = wave_group_width(WaveOf<V>::ID);          // voices per warp = 32 / g, one warp per CTA
             const int warps = (cnt * g + 31) / 32;
 #ifdef GOOEY_WAVE_ALL_WIDTHS
-            if (g == 16) gd::w16::wave_kernel<typename WaveOf<V>::w16, 1><<<warps, 32, 0, sC>>>(L);
-            else if (g == 8) gd::w8::wave_kernel<typename WaveOf<V>::w8, 1><<<warps, 32, 0, sC>>>(L);
+            if (g == 16) GH_LAUNCH((gd::w16::wave_kernel<typename WaveOf<V>::w16, 1>), warps, 32, sC, L);
+            else if (g == 8) GH_LAUNCH((gd::w8::wave_kernel<typename WaveOf<V>::w8, 1>), warps, 32, sC, L);
             else
 #endif
-            gd::w32::wave_kernel<typename WaveOf<V>::w32, 1><<<warps, 32, 0, sC>>>(L);
-          } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
-        } else gd::back_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);   // one voice per lane, one warp per CTA
+            GH_LAUNCH((gd::w32::wave_kernel<typename WaveOf<V>::w32, 1>), warps, 32, sC, L);
+          } else GH_LAUNCH((gd::back_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);
+        } else GH_LAUNCH((gd::back_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());
         GH_CUDA(cudaEventRecord(evT1[i], sC));
         GH_CUDA(cudaEventRecord(evC[b], sC));
@@ -315,8 +335,8 @@ template <class V> struct TypeRunner {
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneS, 0));
     } else {
-      if (cnt <= 148 * 32 * 4) gd::slow_kernel<V, 32><<<(cnt + 31) / 32, 32, 0, sC>>>(L);
-      else gd::slow_kernel<V, 128><<<(cnt + 127) / 128, 128, 0, sC>>>(L);
+      if (cnt <= 148 * 32 * 4) GH_LAUNCH((gd::slow_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);
+      else GH_LAUNCH((gd::slow_kernel<V, 128>), (cnt + 127) / 128, 128, sC, L);
       g_launches.fetch_add(1, std::memory_order_relaxed);
       GH_CUDA(cudaGetLastError());
       GH_CUDA(cudaEventRecord(evDoneC, sC));

@@ -20,6 +20,20 @@
 #pragma once
 #include "kernels.cuh"
 
+// Register budget per back end: __launch_bounds__(32, MIN_CTAS).  1 = let ptxas take what it wants.
+#ifndef GOOEY_MIN_CTAS_KICK
+#define GOOEY_MIN_CTAS_KICK 1
+#endif
+#ifndef GOOEY_MIN_CTAS_SNARE
+#define GOOEY_MIN_CTAS_SNARE 1
+#endif
+#ifndef GOOEY_MIN_CTAS_HAT
+#define GOOEY_MIN_CTAS_HAT 1
+#endif
+#ifndef GOOEY_MIN_CTAS_TOM
+#define GOOEY_MIN_CTAS_TOM 1
+#endif
+
 #define WG 32
 #define WNS w32
 #include "wave_impl.inc"
