@@ -229,8 +229,14 @@ template <class V> struct TypeRunner {
   }
   void ensure_streams() {
     if (sC) return;
-    GH_CUDA(cudaStreamCreateWithFlags(&sB, cudaStreamNonBlocking));
-    GH_CUDA(cudaStreamCreateWithFlags(&sC, cudaStreamNonBlocking));
+    // GOOEY_B200_FRONT_PRIO=1 gives the front-end stream the highest priority (tuning knob; measured slightly slower on
+    // C2: 72.2 vs 69.5 ms, so the default is equal priorities).
+    int prio_lo = 0, prio_hi = 0;
+    GH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char* pe = getenv("GOOEY_B200_FRONT_PRIO");
+    const bool front_prio = pe && pe[0] == '1';
+    GH_CUDA(cudaStreamCreateWithPriority(&sB, cudaStreamNonBlocking, front_prio ? prio_hi : prio_lo));
+    GH_CUDA(cudaStreamCreateWithPriority(&sC, cudaStreamNonBlocking, prio_lo));
     GH_CUDA(cudaStreamCreateWithFlags(&sS, cudaStreamNonBlocking));
     cudaEvent_t* evs[] = {&evA, &evB[0], &evB[1], &evC[0], &evC[1], &evDoneC, &evDoneS};
     for (auto e : evs) GH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
