@@ -1,5 +1,3 @@
-run() { python bench.py --steps 4 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', 'dev ms', round(d['ms_per_step'],2), 'e2e ms', round(d['e2e']['ms_per_step'],2), {k[12:-1]: round(v['avg_ms'],2) for k,v in d['kernels'].items()})"; }
-GOOEY_B200_FRONT_PRIO=0 run noprio
-run prio
-GOOEY_B200_CHUNK=16384 run prio_chunk16k
-GOOEY_B200_CHUNK=4096 run prio_chunk4k
+python -m pytest tests/test_voices_gpu.py tests/test_golden_gpu.py -m gpu -q -s 2>&1 | grep -E "instrument|passed|failed|max \|wave|Error|assert" | tail -30
+python bench.py --steps 4 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('main', 'dev ms', round(d['ms_per_step'],2), 'e2e ms', round(d['e2e']['ms_per_step'],2), {k[12:-1]: round(v['avg_ms'],2) for k,v in d['kernels'].items()})"
+python tools/type_scaling.py snare,kick,tom 2>&1 | grep " 1024 "

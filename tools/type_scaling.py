@@ -10,7 +10,8 @@ from libgooey_b200 import voices as V, lib
 from workloads import drum_sweep_patches
 
 FRAMES = 88200
-patches, vel, kinds = drum_sweep_patches(16384, seed=0x600E7)
+EXACT = os.environ.get("EXACT_TIER") == "1"
+patches, vel, kinds = drum_sweep_patches(16384, seed=0x600E7, exact_tier=EXACT)
 L = lib()
 only = sys.argv[1].split(",") if len(sys.argv) > 1 else ["tom", "hat", "snare", "kick"]
 for kind, name in [(3, "tom"), (2, "hat"), (1, "snare"), (0, "kick")]:
