@@ -11,10 +11,12 @@
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <type_traits>
 #include <set>
 #include <mutex>
 #include "device_rt.h"
 #include "wave.cuh"
+#include "gran_wave.cuh"
 #ifndef GOOEY_WAVE_G_KICK
 #define GOOEY_WAVE_G_KICK 32
 #define GOOEY_WAVE_G_SNARE 32
@@ -341,6 +343,17 @@ template <class V> struct TypeRunner {
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneS, 0));
     } else {
+      if constexpr (std::is_same<V, gd::GranV>::value) {
+        const char* ge = getenv("GOOEY_B200_GRAN");
+        if (!(ge && strcmp(ge, "serial") == 0)) {       // one warp per granulator, grains on lanes (gran_wave.cuh)
+          GH_LAUNCH((gd::gran_wave_kernel<4>), (cnt + 3) / 4, 128, sC, L);
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          GH_CUDA(cudaGetLastError());
+          GH_CUDA(cudaEventRecord(evDoneC, sC));
+          GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
+          return;
+        }
+      }
       if (cnt <= 148 * 32 * 4) GH_LAUNCH((gd::slow_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);
       else GH_LAUNCH((gd::slow_kernel<V, 128>), (cnt + 127) / 128, 128, sC, L);
       g_launches.fetch_add(1, std::memory_order_relaxed);
