@@ -56,7 +56,10 @@ template <int NP> G_HD bool params_settled(const float* cur, const float* tgt) {
   return ok;
 }
 template <int NP> G_HD void params_set_target(float* tgt, uint32_t p, float v) {
-  if (p < (uint32_t)NP) { float c = clampf(v, 0.0f, 1.0f); if (fabsf(tgt[p] - c) > 1e-8f) tgt[p] = c; }
+  // compare-select over every slot instead of tgt[p]: a dynamic index would force the whole state into local memory
+  const float c = clampf(v, 0.0f, 1.0f);
+#pragma unroll
+  for (int i = 0; i < NP; i++) if ((uint32_t)i == p && fabsf(tgt[i] - c) > 1e-8f) tgt[i] = c;
 }
 template <int NP> G_HD void params_snap(float* cur, const float* tgt) {
 #pragma unroll
@@ -781,7 +784,11 @@ G_HD void tom_event(TomCtl& c, const VoiceEvent& e, const double* tt, uint32_t& 
     case EV_TRIGGER: tom_trigger(c, tt[c.k]); resets |= RST_TRIGGER; break;
     case EV_SET_TARGET:  // value already in the voice's internal units (0-100; tuning 0-1)
       if (e.param < T_NP) {
-        c.p[e.param] = e.param == T_TUNING ? clampf(e.value, 0.0f, 1.0f) : clampf(e.value, 0.0f, 100.0f);
+        {
+          const float nv = e.param == T_TUNING ? clampf(e.value, 0.0f, 1.0f) : clampf(e.value, 0.0f, 100.0f);
+#pragma unroll
+          for (int i = 0; i < T_NP; i++) if ((uint32_t)i == e.param) c.p[i] = nv;
+        }
         if (e.param == T_MEMBRANE_Q) tom_update_membrane_params(c);
       }
       break;
@@ -794,7 +801,10 @@ G_HD void tom_event(TomCtl& c, const VoiceEvent& e, const double* tt, uint32_t& 
       if (c.has_saved) { c.has_saved = 0; c.p[T_TUNE] = clampf(clampf(c.saved_freq, 0.0f, 1.0f) * 100.0f, 0.0f, 100.0f); }
       break;
     case EV_SET_AUX:
-      if (e.param >= AUX_TOM_RAW_PARAM0 && e.param < AUX_TOM_RAW_PARAM0 + 8) c.p[e.param - AUX_TOM_RAW_PARAM0] = e.value;  // set_config: unclamped
+      if (e.param >= AUX_TOM_RAW_PARAM0 && e.param < AUX_TOM_RAW_PARAM0 + 8) {  // set_config: unclamped
+#pragma unroll
+        for (int i = 0; i < 8; i++) if ((uint32_t)i == e.param - AUX_TOM_RAW_PARAM0) c.p[i] = e.value;
+      }
       else if (e.param == AUX_TOM_CONFIG_DONE) tom_update_membrane_params(c);
       break;
     default: break;

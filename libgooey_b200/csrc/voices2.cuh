@@ -73,7 +73,8 @@ G_HD void bass_event(BassState& s, const VoiceEvent& e, const double* tt) {
   switch (e.kind) {
     case EV_TRIGGER: bass_trigger(s, e.value, tt[s.k]); break;
     case EV_SET_TIME: s.k = e.aux; break;
-    case EV_SET_TARGET: if (e.param < B_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;
+    case EV_SET_TARGET: { const float c = clampf(e.value, 0.0f, 1.0f);
+      for (int i = 0; i < B_NP; i++) if ((uint32_t)i == e.param && fabsf(s.tgt[i] - c) > 1e-8f) s.tgt[i] = c; } break;   // select, not tgt[param]: keeps the state in registers
     case EV_SNAP: for (int i = 0; i < B_NP; i++) s.cur[i] = s.tgt[i]; break;
     case EV_NOTE_FREQ: {
       if (!s.has_saved) { s.saved_freq = s.cur[B_FREQ]; s.has_saved = 1; }
@@ -199,7 +200,8 @@ G_D void poly_event(PolyState& s, const VoiceEvent& e, const double* tt) {
     case EV_SET_TIME: s.k = e.aux; if (e.param == 1) s.last_tick_time = e.aux ? tt[e.aux - 1] : 0.0; break;
     case EV_POLY_NOTE: poly_trigger_note(s, e.param, e.value); break;
     case EV_POLY_RELEASE: { double t = s.last_tick_time; for (int k = 0; k < 6; k++) if (s.v[k].active) { env_release(s.v[k].amp_env, t); env_release(s.v[k].flt_env, t); } } break;
-    case EV_SET_TARGET: if (e.param < P_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;
+    case EV_SET_TARGET: { const float c = clampf(e.value, 0.0f, 1.0f);
+      for (int i = 0; i < P_NP; i++) if ((uint32_t)i == e.param && fabsf(s.tgt[i] - c) > 1e-8f) s.tgt[i] = c; } break;   // select, not tgt[param]: keeps the state in registers
     case EV_SNAP: for (int i = 0; i < P_NP; i++) s.cur[i] = s.tgt[i]; break;
     default: break;
   }
@@ -345,7 +347,8 @@ G_D void gran_event(GranState& s, const VoiceEvent& e, const double* tt) {
       s.cloud_end = tt[s.k] + (double)(50.0f + c * c * (8000.0f - 50.0f)) * 0.001;
       s.next_grain = tt[s.k];
     } break;
-    case EV_SET_TARGET: if (e.param < G_NP) { float c = clampf(e.value, 0.0f, 1.0f); if (fabsf(s.tgt[e.param] - c) > 1e-8f) s.tgt[e.param] = c; } break;
+    case EV_SET_TARGET: { const float c = clampf(e.value, 0.0f, 1.0f);
+      for (int i = 0; i < G_NP; i++) if ((uint32_t)i == e.param && fabsf(s.tgt[i] - c) > 1e-8f) s.tgt[i] = c; } break;   // select, not tgt[param]: keeps the state in registers
     case EV_SNAP: for (int i = 0; i < G_NP; i++) s.cur[i] = s.tgt[i]; s.gc_cur = s.gc_tgt; break;
     case EV_GRAN_SEED: s.rng = e.aux == 0 ? 0x6d2b79f5u : e.aux; break;
     case EV_GRAN_BUFFER:
