@@ -400,9 +400,9 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   // first pieces are short: a gliding voice re-enters the time-parallel path within a few thousand frames.
   std::vector<uint32_t> cuts;
   {
-    const uint32_t lead[4] = {4096, 4096, 8192, 16384};
+    const uint32_t lead[10] = {2048, 2048, 2048, 2048, 2048, 2048, 4096, 4096, 8192, 16384};
     uint32_t f = 0;
-    for (int k = 0; k < 4 && f + lead[k] < frames && lead[k] < piece; k++) { f += lead[k]; cuts.push_back(f); }
+    for (int k = 0; k < 10 && f + lead[k] < frames && lead[k] < piece; k++) { f += lead[k]; cuts.push_back(f); }
     while (f + piece < frames) { f += (uint32_t)piece; cuts.push_back(f); }
     cuts.push_back(frames);
   }

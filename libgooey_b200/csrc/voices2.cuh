@@ -40,6 +40,8 @@ struct BassState {
   uint32_t active;
   float saved_freq; uint32_t has_saved;
   uint32_t k, pad_k;
+  // pure functions of one smoothed parameter, re-evaluated only when it moves (three powf per tick otherwise)
+  float memo_tuning_in, memo_tuning_out, memo_cents_in, memo_cents_out, memo_cutoff_in, memo_cutoff_out;
 };
 G_HD float exp_denorm(float n, float mn, float mx) { return mn * gm::g_powf(mx / mn, clampf(n, 0.0f, 1.0f)); }
 // BassSynth::with_config (bass.rs:613-634); cfg = BassConfig::new order (15)
@@ -52,6 +54,8 @@ G_HD void bass_init(BassState& s, const float* cfg, float sr) {
   ws_init(s.ws, s.cur[B_OVERDRIVE], 1.0f);
   s.velocity = 1.0f; s.trig_freq = denorm(s.cur[B_FREQ], 30.0f, 200.0f); s.active = 0;
   s.saved_freq = 0.0f; s.has_saved = 0; s.k = 0; s.pad_k = 0;
+  s.memo_tuning_in = s.memo_cents_in = s.memo_cutoff_in = -1.0f;   // no valid input is negative
+  s.memo_tuning_out = s.memo_cents_out = s.memo_cutoff_out = 0.0f;
 }
 G_HD void bass_trigger(BassState& s, float velocity, double time) {  // bass.rs:747-791
   s.velocity = clampf(velocity, 0.0f, 1.0f);
@@ -101,11 +105,13 @@ G_D float bass_tick(BassState& s, const double* tt, const RateCtx& rc) {  // bas
   for (int i = 0; i < B_NP; i++) smooth_tick(s.cur[i], s.tgt[i], rc.smooth15);
   if (!s.active) return 0.0f;
   const float sr = rc.sr;
-  float freq = s.trig_freq * tuning_to_multiplier(s.cur[B_TUNING]);
+  if (s.cur[B_TUNING] != s.memo_tuning_in) { s.memo_tuning_in = s.cur[B_TUNING]; s.memo_tuning_out = tuning_to_multiplier(s.cur[B_TUNING]); }
+  float freq = s.trig_freq * s.memo_tuning_out;
   float sub_level = s.cur[B_SUB], osc_level = s.cur[B_OSC], detune_level = s.cur[B_DETUNE_LEVEL];
   float detune_cents = denorm(s.cur[B_DETUNE_AMT], 0.0f, 30.0f);
   float osc_shape = s.cur[B_SHAPE];
-  float detune_ratio = gm::g_powf(2.0f, detune_cents / 1200.0f);
+  if (detune_cents != s.memo_cents_in) { s.memo_cents_in = detune_cents; s.memo_cents_out = gm::g_powf(2.0f, detune_cents / 1200.0f); }
+  float detune_ratio = s.memo_cents_out;
   float detune_freq = freq * detune_ratio;
   double dt = 1.0 / (double)sr;
   double sub_inc = (double)freq * dt, osc_inc = (double)freq * dt, det_inc = (double)detune_freq * dt;
@@ -122,7 +128,8 @@ G_D float bass_tick(BassState& s, const double* tt, const RateCtx& rc) {  // bas
   s.ws.drive = clampf(1.0f + od * 9.0f, 1.0f, 10.0f);
   float sat = od > 0.001f ? ws_process(s.ws, mix) : mix;
   float fenv = env_amp(s.flt_env, now);
-  float base_cutoff = exp_denorm(s.cur[B_CUTOFF], 20.0f, 18000.0f);
+  if (s.cur[B_CUTOFF] != s.memo_cutoff_in) { s.memo_cutoff_in = s.cur[B_CUTOFF]; s.memo_cutoff_out = exp_denorm(s.cur[B_CUTOFF], 20.0f, 18000.0f); }
+  float base_cutoff = s.memo_cutoff_out;
   float env_offset = (18000.0f - base_cutoff) * s.cur[B_FENV_AMT] * fenv;
   float cutoff = clampf(base_cutoff + env_offset, 20.0f, 18000.0f);
   tpt_set(s.filter, sr, cutoff, denorm(s.cur[B_RES], 0.5f, 15.0f));
