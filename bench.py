@@ -9,7 +9,11 @@ voice, per-voice envelopes + filters, per-voice f32 output kept.  One "step" = o
 
 * ours: `value` = voice-samples/s with patches and output resident in HBM (device time, CUDA events on the
   library's launching streams, max over ranks); `e2e` = the same through the C ABI with HOST buffers
-  (event tables H2D + kernels + D2H of every voice's audio into pinned host memory inside the timed region).
+  (event tables H2D + kernels + D2H of every voice's audio into pinned host memory inside the timed region; the
+  library drains finished 8192-frame chunks on a copy stream while later chunks render).
+  `roofline` is the contract's store-bandwidth figure for the dominant back-end kernel (algorithmic bytes per launch /
+  its mean launch duration, CUDA events inside the library; `traffic` from the committed ncu capture); `kernels` lists
+  all four back ends.  The kernels are latency-bound, not byte-bound: DESIGN.md section 4 and profiles/README.md.
 * reference: the reference's CPU implementation of the same path.  The Rust reference cannot be built here
   (no toolchain in the image), so this arm times the C++ restatement in oracle/ ("port") on all host cores,
   on a bounded sample of the same patches.

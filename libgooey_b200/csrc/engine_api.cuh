@@ -313,8 +313,9 @@ uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing
 }
 
 // ---- render / bounce ----
+// out_rows (optional): one host pointer per engine instead of a pitched block (the per-engine buffers of batch bounce)
 static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t frames, int mode, bool bounce, float* out_dev, size_t stride,
-                             float* out_host, size_t host_pitch) {
+                             float* out_host, size_t host_pitch, float* const* out_rows = nullptr) {
   std::vector<GooeyEngine*> E(engines, engines + n);
   try {
     gh::EngineBank& B = *E[0]->bank;
@@ -329,6 +330,7 @@ static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t f
     }
     gh::engines_render(E, frames, mode, bounce, dst, stride);
     if (out_host) GH_CUDA(cudaMemcpy2DAsync(out_host, host_pitch * 4, dst, stride * 4, row * 4, n, cudaMemcpyDeviceToHost, B.stream));
+    if (out_rows) for (uint32_t i = 0; i < n; i++) GH_CUDA(cudaMemcpyAsync(out_rows[i], dst + (size_t)i * stride, row * 4, cudaMemcpyDeviceToHost, B.stream));
     GH_CUDA(cudaStreamSynchronize(B.stream));
     GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, B.ev0, B.ev1));
     return GOOEY_E_OK;
@@ -370,18 +372,17 @@ int gooey_batch_bounce(GooeyEngine* const* engines, uint32_t n, uint32_t bars, f
     std::vector<GooeyEngine*> E;
     for (uint32_t i : g.second) E.push_back(engines[i]);
     const size_t cnt = E.size();
-    std::vector<float> host((size_t)cnt * std::max<uint32_t>(frames, 1));
-    if (frames > 0) {
-      int rc = batch_render_impl(E.data(), (uint32_t)cnt, frames, gh::OUT_MONO, true, nullptr, 0, host.data(), frames);
-      if (rc != GOOEY_E_OK) return rc;
-    }
+    // each engine's result goes straight from the device into the buffer the caller will own (no staging copy)
+    std::vector<float*> bufs(cnt, nullptr);
     for (size_t j = 0; j < cnt; j++) {
-      float* p = (float*)malloc(std::max<size_t>((size_t)frames, 1) * sizeof(float));
-      if (!p) { gh::set_error("out of host memory"); return GOOEY_E_INVALID; }
-      if (frames) memcpy(p, host.data() + j * frames, (size_t)frames * sizeof(float));
-      out_buffers[g.second[j]] = p;
-      out_lengths[g.second[j]] = frames;
+      bufs[j] = (float*)malloc(std::max<size_t>((size_t)frames, 1) * sizeof(float));
+      if (!bufs[j]) { for (float* q : bufs) free(q); gh::set_error("out of host memory"); return GOOEY_E_INVALID; }
     }
+    if (frames > 0) {
+      int rc = batch_render_impl(E.data(), (uint32_t)cnt, frames, gh::OUT_MONO, true, nullptr, 0, nullptr, 0, bufs.data());
+      if (rc != GOOEY_E_OK) { for (float* q : bufs) free(q); return rc; }
+    }
+    for (size_t j = 0; j < cnt; j++) { out_buffers[g.second[j]] = bufs[j]; out_lengths[g.second[j]] = frames; }
   }
   return GOOEY_E_OK;
 }
