@@ -187,6 +187,14 @@ template <class K> inline void same_carveout(K kernel) {
 }
 #define GH_LAUNCH(kernel, grid, block, stream, ...) do { same_carveout(kernel); kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); } while (0)
 
+// Rank of a voice type by the length of its per-chunk dependency chain (tools/type_scaling.py: tom 31 ms, snare 22 ms,
+// kick 11 ms, hi-hat 10 ms per 1024 voices x 2 s); used for stream priorities.
+template <class V> struct PrioOf { static constexpr int rank = 4; };
+template <> struct PrioOf<gd::TomV> { static constexpr int rank = 0; };
+template <> struct PrioOf<gd::SnareV> { static constexpr int rank = 1; };
+template <> struct PrioOf<gd::KickV> { static constexpr int rank = 2; };
+template <> struct PrioOf<gd::HatV> { static constexpr int rank = 3; };
+
 // Frames per front/back pipeline stage.  GOOEY_B200_CHUNK overrides (tuning).
 inline int default_chunk_frames() {
   if (const char* e = getenv("GOOEY_B200_CHUNK")) { int v = atoi(e); if (v >= 1024 && v <= (1 << 20)) return (v + 31) & ~31; }
@@ -231,14 +239,18 @@ template <class V> struct TypeRunner {
   }
   void ensure_streams() {
     if (sC) return;
-    // GOOEY_B200_FRONT_PRIO=1 gives the front-end stream the highest priority (tuning knob; measured slightly slower on
-    // C2: 72.2 vs 69.5 ms, so the default is equal priorities).
+    // Stream priorities.  The buckets overlap on the device and the step ends when the slowest bucket's chunk chain
+    // does (tom on C2), so the bucket with the longest chain should win the block scheduler's slots whenever one frees up
+    // and the cheaper buckets fill the gaps: PrioOf<V> ranks the types by per-voice cost, 0 = longest chain.
+    // Measured on C2: 54.4 ms ranked vs 55.1 ms equal (noise) — the tom chain is slowed by sharing issue slots, not by
+    // waiting for slots — so equal priorities stay the default; GOOEY_B200_PRIO=1 enables the ranking (tuning knob).
     int prio_lo = 0, prio_hi = 0;
-    GH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    const char* pe = getenv("GOOEY_B200_FRONT_PRIO");
-    const bool front_prio = pe && pe[0] == '1';
-    GH_CUDA(cudaStreamCreateWithPriority(&sB, cudaStreamNonBlocking, front_prio ? prio_hi : prio_lo));
-    GH_CUDA(cudaStreamCreateWithPriority(&sC, cudaStreamNonBlocking, prio_lo));
+    GH_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
+    const char* pe = getenv("GOOEY_B200_PRIO");
+    int prio = prio_lo;
+    if (pe && pe[0] == '1') prio = std::min(prio_lo, prio_hi + PrioOf<V>::rank);
+    GH_CUDA(cudaStreamCreateWithPriority(&sB, cudaStreamNonBlocking, prio));
+    GH_CUDA(cudaStreamCreateWithPriority(&sC, cudaStreamNonBlocking, prio));
     GH_CUDA(cudaStreamCreateWithFlags(&sS, cudaStreamNonBlocking));
     cudaEvent_t* evs[] = {&evA, &evB[0], &evB[1], &evC[0], &evC[1], &evDoneC, &evDoneS};
     for (auto e : evs) GH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
