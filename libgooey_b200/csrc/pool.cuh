@@ -17,6 +17,7 @@
 #include "device_rt.h"
 #include "wave.cuh"
 #include "gran_wave.cuh"
+#include "bass_wave.cuh"
 #ifndef GOOEY_WAVE_G_KICK
 #define GOOEY_WAVE_G_KICK 32
 #define GOOEY_WAVE_G_SNARE 32
@@ -359,6 +360,17 @@ template <class V> struct TypeRunner {
         const char* ge = getenv("GOOEY_B200_GRAN");
         if (!(ge && strcmp(ge, "serial") == 0)) {       // one warp per granulator, grains on lanes (gran_wave.cuh)
           GH_LAUNCH((gd::gran_wave_kernel<4>), (cnt + 3) / 4, 128, sC, L);
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          GH_CUDA(cudaGetLastError());
+          GH_CUDA(cudaEventRecord(evDoneC, sC));
+          GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
+          return;
+        }
+      }
+      if constexpr (std::is_same<V, gd::BassV>::value) {
+        const char* be = getenv("GOOEY_B200_BASS");
+        if (!(be && strcmp(be, "serial") == 0)) {       // one warp per bass voice, lane = frame (bass_wave.cuh)
+          GH_LAUNCH((gd::bass_wave_kernel<2>), (cnt + 1) / 2, 64, sC, L);
           g_launches.fetch_add(1, std::memory_order_relaxed);
           GH_CUDA(cudaGetLastError());
           GH_CUDA(cudaEventRecord(evDoneC, sC));
