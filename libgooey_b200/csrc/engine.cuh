@@ -101,18 +101,23 @@ struct EngineBank {
   DevBuf<float> ring[gd::MAX_FX]; uint32_t ring_words[gd::MAX_FX] = {0}; long long ring_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_piece = nullptr;
-  DevBuf<float> d_voice_buf, d_out;
+  // The mix of piece p runs on its own stream while the voices of piece p + 1 render into the other voice buffer.
+  cudaStream_t mix_stream = nullptr;
+  cudaEvent_t ev_voices[2] = {nullptr, nullptr}, ev_mixed[2] = {nullptr, nullptr};
+  DevBuf<float> d_voice_bufs[2], d_out;
   DevBuf<float> d_silent;                 // the granulator's 1-sample silent placeholder buffer (ffi.rs:929-933)
-  DevBuf<uint32_t> d_mix_slots, d_mix_ev_begin;
+  DevBuf<uint32_t> d_mix_slots, d_mix_ev_begins[2];
   DevBuf<uint8_t> d_mix_fast;
   DevBuf<gd::MixConst> d_mix_consts;
-  DevBuf<gd::VoiceEvent> d_mix_events;
+  DevBuf<gd::VoiceEvent> d_mix_eventss[2];
   std::mutex mu;
   float last_ms = 0.0f;
   EngineBank(int dev, float sr_) : device(dev), sr(sr_) {
     rc = gd::make_rate_ctx(sr); geo = make_fx_geom(sr);
     GH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     GH_CUDA(cudaEventCreate(&ev0)); GH_CUDA(cudaEventCreate(&ev1)); GH_CUDA(cudaEventCreateWithFlags(&ev_piece, cudaEventDisableTiming));
+    GH_CUDA(cudaStreamCreateWithFlags(&mix_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) { GH_CUDA(cudaEventCreateWithFlags(&ev_voices[b], cudaEventDisableTiming)); GH_CUDA(cudaEventCreateWithFlags(&ev_mixed[b], cudaEventDisableTiming)); }
     d_silent.alloc(4); d_silent.zero(stream);
   }
   // makes sure arena `slot` holds `words` ring words for `cap` engine slots (content preserving)
@@ -390,7 +395,12 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   size_t piece = ((size_t)2 << 30) / (rows * 4);
   piece = std::min<size_t>(std::max<size_t>(piece & ~(size_t)31, 2048), 65536);
   piece = std::min<size_t>(piece, (frames + 31) & ~31u);
-  B.d_voice_buf.alloc(rows * piece);
+  const bool two_bufs = frames > piece || frames > 4096;      // more than one piece: overlap mix(p) with voices(p + 1)
+  B.d_voice_bufs[0].alloc(rows * piece);
+  if (two_bufs) B.d_voice_bufs[1].alloc(rows * piece);
+  cudaStream_t ms = B.mix_stream;
+  GH_CUDA(cudaEventRecord(B.ev_piece, st));
+  GH_CUDA(cudaStreamWaitEvent(ms, B.ev_piece, 0));             // the mix stream starts after everything queued so far (uploads, ring set-up)
   GH_CUDA(cudaEventRecord(B.ev0, st));
   std::vector<gd::VoiceEvent> cur, mflat;
   std::vector<uint32_t> mbegin;
@@ -406,9 +416,15 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     while (f + piece < frames) { f += (uint32_t)piece; cuts.push_back(f); }
     cuts.push_back(frames);
   }
+  // GOOEY_B200_TRACE=1: per-piece device times of the voice stage and of the mix stage on stderr (diagnostic)
+  const bool trace = getenv("GOOEY_B200_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tv0, tv1, tm0, tm1;
+  auto tev = [&](std::vector<cudaEvent_t>& v, cudaStream_t s2) { if (!trace) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s2); v.push_back(e); };
   uint32_t f0 = 0;
   for (size_t pc = 0; pc < cuts.size(); f0 = cuts[pc], pc++) {
     const uint32_t nf = cuts[pc] - f0;
+    const int vb = two_bufs ? (int)(pc & 1) : 0;
+    if (pc >= (two_bufs ? 2u : 1u)) GH_CUDA(cudaStreamWaitEvent(st, B.ev_mixed[vb], 0));   // voice buffer vb is free again
     B.voices.reset();
     for (int i = 0; i < n; i++)
       for (int ch = 0; ch < 7; ch++) {
@@ -425,7 +441,11 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     cudaEvent_t start = B.ev_piece;
     GH_CUDA(cudaEventRecord(start, st));
     // the clock index differs per engine only through e->k; voices carry their own k, the launch passes the table
-    B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_buf.p, (long long)piece);
+    tev(tv0, st);
+    B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_bufs[vb].p, (long long)piece);
+    tev(tv1, st);
+    GH_CUDA(cudaEventRecord(B.ev_voices[vb], st));
+    GH_CUDA(cudaStreamWaitEvent(ms, B.ev_voices[vb], 0));
     mflat.clear(); mbegin.assign(1, 0);
     for (int i = 0; i < n; i++) {
       auto& ev = mev[i];
@@ -434,13 +454,13 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       mbegin.push_back((uint32_t)mflat.size());
     }
     if (mflat.empty()) mflat.push_back(make_event(0xffffffffu, 0xffff, 0, 0.0f));
-    B.d_mix_events.upload(mflat.data(), mflat.size(), st);
-    B.d_mix_ev_begin.upload(mbegin.data(), mbegin.size(), st);
+    B.d_mix_eventss[vb].upload(mflat.data(), mflat.size(), ms);      // pageable source: staged before the call returns
+    B.d_mix_ev_begins[vb].upload(mbegin.data(), mbegin.size(), ms);
     gd::MixLaunch M;
     memset(&M, 0, sizeof M);
     M.state = B.mix_pool.d.p; M.n = n; M.state_cap = B.mix_pool.cap; M.slots = B.d_mix_slots.p; M.n_lpad = n_lpad;
-    M.cfg = B.d_cfg.p; M.events = B.d_mix_events.p; M.ev_begin = B.d_mix_ev_begin.p;
-    M.voice_buf = B.d_voice_buf.p; M.voice_stride = (long long)piece; M.chan_mask = 0x1fu | (any_poly ? 0x20u : 0u) | (any_gran ? 0x40u : 0u);
+    M.cfg = B.d_cfg.p; M.events = B.d_mix_eventss[vb].p; M.ev_begin = B.d_mix_ev_begins[vb].p;
+    M.voice_buf = B.d_voice_bufs[vb].p; M.voice_stride = (long long)piece; M.chan_mask = 0x1fu | (any_poly ? 0x20u : 0u) | (any_gran ? 0x40u : 0u);
     for (int s = 0; s < gd::MAX_FX; s++) M.ring[s] = B.ring[s].p;
     M.ring_cap = ring_cap;
     M.frames = (int)nf;
@@ -449,13 +469,31 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     M.center_l = gm::g_cosf(0.5f * 1.57079632679489661923f); M.center_r = gm::g_sinf(0.5f * 1.57079632679489661923f);
     B.d_mix_fast.alloc(n); B.d_mix_consts.alloc(n);
     M.fast = B.d_mix_fast.p; M.consts = B.d_mix_consts.p;
-    gd::mix_prepare_kernel<<<(n + 127) / 128, 128, 0, st>>>(M);
-    gd::mix_fast_kernel<<<dim3((nf + 1023) / 1024, n), 256, 0, st>>>(M);
-    gd::mix_kernel<<<(n + 31) / 32, 32, 0, st>>>(M);
+    tev(tm0, ms);
+    gd::mix_prepare_kernel<<<(n + 127) / 128, 128, 0, ms>>>(M);
+    gd::mix_fast_kernel<<<dim3((nf + 1023) / 1024, n), 256, 0, ms>>>(M);
+    {
+      static std::set<int> opted;      // per device: allow the mix kernel its dynamic shared memory (> 48 KB with the static tiles)
+      if (opted.insert(B.device).second) GH_CUDA(cudaFuncSetAttribute(gd::mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gd::MIX_DYN_SMEM));
+    }
+    gd::mix_kernel<<<(n + 31) / 32, 32, gd::MIX_DYN_SMEM, ms>>>(M);
     g_launches.fetch_add(3, std::memory_order_relaxed);
     GH_CUDA(cudaGetLastError());
+    GH_CUDA(cudaEventRecord(B.ev_mixed[vb], ms));
+    tev(tm1, ms);
   }
+  GH_CUDA(cudaStreamWaitEvent(st, B.ev_mixed[0], 0));
+  if (two_bufs && cuts.size() > 1) GH_CUDA(cudaStreamWaitEvent(st, B.ev_mixed[1], 0));
   GH_CUDA(cudaEventRecord(B.ev1, st));
+  if (trace) {
+    GH_CUDA(cudaStreamSynchronize(st));
+    for (size_t pc = 0; pc < tv0.size(); pc++) {
+      float a = 0, b = 0, c = 0, d = 0;
+      cudaEventElapsedTime(&a, tv0[0], tv0[pc]); cudaEventElapsedTime(&b, tv0[pc], tv1[pc]); cudaEventElapsedTime(&c, tv0[0], tm0[pc]); cudaEventElapsedTime(&d, tm0[pc], tm1[pc]);
+      fprintf(stderr, "[gooey trace] piece %zu frames %u: voices start %.1f ms, take %.1f ms; mix start %.1f ms, takes %.1f ms\n", pc, cuts[pc] - (pc ? cuts[pc - 1] : 0), a, b, c, d);
+    }
+    for (auto* v : {&tv0, &tv1, &tm0, &tm1}) for (auto e : *v) cudaEventDestroy(e);
+  }
   for (int i = 0; i < n; i++) {
     E[i]->k += frames;
     if (bounce) for (auto& s : E[i]->strip) s.seq.stop();

@@ -193,7 +193,12 @@ __device__ __forceinline__ float tilt_one(TiltDyn& d, int c, float in, const Rat
 }
 
 struct DelayStep { float filtered, feedback, mix; };
-__device__ __forceinline__ DelayStep delay_read(DelayDyn& d, int c, const RingRef& r, uint32_t len, const RateCtx& rc) {  // delay.rs:321-399
+// The ring reads of a frame have addresses that depend on state only, never on this frame's audio, so every effect
+// first computes its addresses (`*_prep`), then issues ALL its loads back to back, and only then runs the dependent
+// arithmetic: the L2 / HBM latency is paid once per effect and frame instead of once per tap (the reference order of
+// the arithmetic is untouched; the taps read cells written >= 1 frame earlier, the writes of this frame come after).
+struct DelayPrep { uint32_t r1, r2; float df, feedback, mix, cutoff; };
+__device__ __forceinline__ DelayPrep delay_prep(DelayDyn& d, int c, const RingRef& r, uint32_t len, const RateCtx& rc) {  // delay.rs:321-360
   DelayCh& s = d.ch[c];
   const uint32_t base = c * len;
   uint32_t tc = d.timing_target;
@@ -206,22 +211,27 @@ __device__ __forceinline__ DelayStep delay_read(DelayDyn& d, int c, const RingRe
     s.time = {tcl, tcl};
   }
   sm_set(s.time, time_target, 0.0f, 5.0f); sm_set(s.fb, d.fb_target, 0.0f, 0.95f); sm_set(s.mix, d.mix_target, 0.0f, 1.0f); sm_set(s.cutoff, d.cutoff_target, 20.0f, 20000.0f);
-  float time = sm_tick(s.time, rc.smooth50), feedback = sm_tick(s.fb, rc.smooth30), mix = sm_tick(s.mix, rc.smooth30), cutoff = sm_tick(s.cutoff, rc.smooth30);
+  DelayPrep p;
+  float time = sm_tick(s.time, rc.smooth50);
+  p.feedback = sm_tick(s.fb, rc.smooth30); p.mix = sm_tick(s.mix, rc.smooth30); p.cutoff = sm_tick(s.cutoff, rc.smooth30);
   float ds = time * rc.sr;
   uint32_t di = (uint32_t)f32_to_u64_sat(ds);
-  float df = ds - (float)di;
-  uint32_t r1 = (s.write_index + len - di) % len;
-  uint32_t r2 = (s.write_index + len - di - 1) % len;
-  float s1 = r.at(base + r1), s2 = r.at(base + r2);
-  float delayed = s1 * (1.0f - df) + s2 * df;
-  float g = 1.0f - gm::g_expf(-2.0f * PI_F * cutoff / rc.sr);
+  p.df = ds - (float)di;
+  p.r1 = base + (s.write_index + len - di) % len;
+  p.r2 = base + (s.write_index + len - di - 1) % len;
+  return p;
+}
+__device__ __forceinline__ DelayStep delay_filter(DelayDyn& d, int c, const DelayPrep& p, float s1, float s2, const RateCtx& rc) {  // :361-399
+  DelayCh& s = d.ch[c];
+  float delayed = s1 * (1.0f - p.df) + s2 * p.df;
+  float g = 1.0f - gm::g_expf(-2.0f * PI_F * p.cutoff / rc.sr);
   float rfb = 0.3f * (s.z1 - s.z2);
   s.z1 = s.z1 + g * (delayed + rfb - s.z1);
   s.z2 = s.z2 + g * (s.z1 - s.z2);
   float filtered = s.z2;
   if (fabsf(s.z1) < 1e-15f) s.z1 = 0.0f;
   if (fabsf(s.z2) < 1e-15f) s.z2 = 0.0f;
-  return {filtered, feedback, mix};
+  return {filtered, p.feedback, p.mix};
 }
 __device__ __forceinline__ float delay_write(DelayDyn& d, int c, const RingRef& r, uint32_t len, float dry, float inject, const DelayStep& st, float tap) {  // :407-439
   DelayCh& s = d.ch[c];
@@ -233,22 +243,20 @@ __device__ __forceinline__ float delay_write(DelayDyn& d, int c, const RingRef& 
   return isfinite(out) ? out : dry;
 }
 __device__ __forceinline__ void delay_stereo(DelayDyn& d, const RingRef& r, uint32_t len, float& l, float& rr, const RateCtx& rc) {  // :460-491
+  const float li = isfinite(l) ? l : 0.0f, ri = isfinite(rr) ? rr : 0.0f;
+  const DelayPrep pa = delay_prep(d, 0, r, len, rc), pb = delay_prep(d, 1, r, len, rc);
+  const float a1 = r.at(pa.r1), a2 = r.at(pa.r2), b1 = r.at(pb.r1), b2 = r.at(pb.r2);   // the two channels own disjoint halves
+  const DelayStep a = delay_filter(d, 0, pa, a1, a2, rc), b = delay_filter(d, 1, pb, b1, b2, rc);
   if (!d.pingpong) {
-    float li = isfinite(l) ? l : 0.0f;
-    DelayStep a = delay_read(d, 0, r, len, rc);
     l = delay_write(d, 0, r, len, li, li, a, a.filtered);
-    float ri = isfinite(rr) ? rr : 0.0f;
-    DelayStep b = delay_read(d, 1, r, len, rc);
     rr = delay_write(d, 1, r, len, ri, ri, b, b.filtered);
     return;
   }
-  float li = isfinite(l) ? l : 0.0f, ri = isfinite(rr) ? rr : 0.0f;
-  DelayStep a = delay_read(d, 0, r, len, rc), b = delay_read(d, 1, r, len, rc);
   l = delay_write(d, 0, r, len, li, li, a, b.filtered);
   rr = delay_write(d, 1, r, len, ri, 0.0f, b, a.filtered);
 }
 
-__device__ __forceinline__ float spring_one(SpringDyn& d, int c, const RingRef& r, const FxGeom& g, float in, const RateCtx& rc) {  // reverb.rs:162-217
+__device__ __forceinline__ float spring_one(SpringDyn& d, int c, const RingRef& r, const FxGeom& g, float in, const RateCtx& rc, const float* dl) {  // reverb.rs:162-217
   const float G[6] = {0.70f, 0.68f, 0.65f, 0.62f, 0.60f, 0.58f};
   SpringCh& s = d.ch[c];
   in = isfinite(in) ? in : 0.0f;
@@ -260,11 +268,10 @@ __device__ __forceinline__ float spring_one(SpringDyn& d, int c, const RingRef& 
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     const uint32_t off = g.spring_off[c * 6 + i], len = g.spring_len[c * 6 + i];
-    float& cell = r.at(off + s.idx[i]);
-    float delayed = cell;
+    const float delayed = dl[i];          // loaded by the caller for both channels before either chain starts
     float v = sig - G[i] * delayed;
     sig = G[i] * v + delayed;
-    cell = v;
+    r.at(off + s.idx[i]) = v;
     s.idx[i] = (s.idx[i] + 1) % len;
   }
   s.damp = sig * d2 + s.damp * d1;
@@ -358,7 +365,14 @@ __device__ __forceinline__ void fx_process(FxDyn& f, uint32_t kind, const RingRe
   switch (kind) {
     case FXK_TILT: l = tilt_one(f.tilt, 0, l, rc); rr = tilt_one(f.tilt, 1, rr, rc); break;
     case FXK_DELAY: delay_stereo(f.delay, r, g.delay_len, l, rr, rc); break;
-    case FXK_SPRING: l = spring_one(f.spring, 0, r, g, l, rc); rr = spring_one(f.spring, 1, r, g, rr, rc); break;
+    case FXK_SPRING: {
+      float dl[2][6];
+#pragma unroll
+      for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int i = 0; i < 6; i++) dl[c][i] = r.at(g.spring_off[c * 6 + i] + f.spring.ch[c].idx[i]);
+      l = spring_one(f.spring, 0, r, g, l, rc, dl[0]); rr = spring_one(f.spring, 1, r, g, rr, rc, dl[1]);
+    } break;
     case FXK_PLATE: plate_stereo(f.plate, r, g, l, rr, rc); break;
     default: break;
   }
@@ -392,6 +406,7 @@ __device__ __forceinline__ void mix_event(MixState& s, const MixCfg& cfg, const 
 // One engine per thread.  Voice rows come in and the mix goes out through 32 engines x 32 frames shared-memory tiles,
 // so every global access is a 128-byte row segment.
 constexpr int MIX_CH = 7;
+constexpr size_t MIX_DYN_SMEM = 32 * (sizeof(MixState) + sizeof(MixCfg));
 __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
   __shared__ float tin[MIX_CH][TILE * 33];
   __shared__ float tout[2][TILE * 33];
@@ -403,8 +418,12 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
   const uint32_t row_mask = __ballot_sync(0xffffffffu, valid);
   if (row_mask == 0) return;
   const int n_rows = min(32, L.n - warp_i0);
-  MixState st;
-  MixCfg cfg;
+  // The per-engine mixer state (414 words) and configuration are indexed with run-time slots (effect order, racks,
+  // routes), which would put them in local memory — 3.7 MB for 2048 engines, thrashing L1 on every access.  They live in
+  // dynamic shared memory instead (one struct per lane, 58 KB per CTA; MIX_DYN_SMEM).
+  extern __shared__ __align__(16) unsigned char mix_dyn_smem[];
+  MixState& st = reinterpret_cast<MixState*>(mix_dyn_smem)[lane];
+  MixCfg& cfg = reinterpret_cast<MixCfg*>(mix_dyn_smem + 32 * sizeof(MixState))[lane];
   uint32_t ev = 0, ev_end = 0;
   int es = 0;
   if (valid) {
