@@ -22,16 +22,17 @@ struct Sm { float c, t; };
 G_HD void sm_set(Sm& s, float v, float lo, float hi) { float c = clampf(v, lo, hi); if (fabsf(s.t - c) > 1e-8f) s.t = c; }
 G_HD float sm_tick(Sm& s, float coeff) { smooth_tick(s.c, s.t, coeff); return s.c; }
 
-struct TiltDyn { Sm cutoff[2], res[2]; Tpt svf[2]; float cutoff_target, res_target; };
+struct TiltDyn { Sm cutoff[2], res[2]; Tpt svf[2]; float cutoff_target, res_target; float memo_t[2], memo_pow[2]; };   // memo: powf of the settled knob
 struct DelayCh { uint32_t write_index; float z1, z2; uint32_t prev_timing; Sm time, fb, mix, cutoff; };
-struct DelayDyn { DelayCh ch[2]; uint32_t timing_target; float bpm_target, fb_target, mix_target, cutoff_target; uint32_t pingpong; };
+struct DelayDyn { DelayCh ch[2]; uint32_t timing_target; float bpm_target, fb_target, mix_target, cutoff_target; uint32_t pingpong; float memo_cut[2], memo_g[2]; };
 struct SpringCh { uint32_t idx[6]; float fb, damp; Sm decay, mix, damping; };
-struct SpringDyn { SpringCh ch[2]; float decay_target, mix_target, damping_target; };
+struct SpringDyn { SpringCh ch[2]; float decay_target, mix_target, damping_target; float memo_decay[2], memo_fb[2]; };
 struct PlateDyn {
   uint32_t idx[13];   // 0 predelay, 1..4 input APs, 5 mod_ap_a, 6 delay1_a, 7 ap2_a, 8 delay2_a, 9 mod_ap_b, 10 delay1_b, 11 ap2_b, 12 delay2_b
   float bandwidth, damp_a, damp_b, fb_a, fb_b, lfo_pa, lfo_pb;
   Sm decay, mix, damping, predelay, width, size;
   float t_decay, t_mix, t_damping, t_predelay, t_width, t_size;
+  float memo_sz, memo_size;
 };
 union FxDyn { TiltDyn tilt; DelayDyn delay; SpringDyn spring; PlateDyn plate; uint32_t w[40]; };
 static_assert(sizeof(FxDyn) == 160, "FxDyn must stay 40 words");
@@ -101,6 +102,7 @@ struct MixConst {
 G_HD void tilt_init(TiltDyn& d, float sr) {  // TiltFilterEffect::new
   for (int c = 0; c < 2; c++) { d.cutoff[c] = {0.5f, 0.5f}; d.res[c] = {0.0f, 0.0f}; tpt_init(d.svf[c], sr, 1000.0f, 0.5f); }
   d.cutoff_target = 0.5f; d.res_target = 0.0f;
+  d.memo_t[0] = d.memo_t[1] = -1.0f; d.memo_pow[0] = d.memo_pow[1] = 0.0f;   // no valid input is negative
 }
 G_HD float delay_beats(uint32_t t) {
   switch (t) { case 0: return 4.0f; case 1: return 2.0f; case 2: return 1.0f; case 3: return 0.5f; case 4: return 0.25f;
@@ -117,6 +119,7 @@ G_HD void delay_init(DelayDyn& d, uint32_t timing, float bpm, float fb, float mi
     s.time = {tc, tc}; s.fb = {fbc, fbc}; s.mix = {mc, mc}; s.cutoff = {cc, cc};
   }
   d.timing_target = timing; d.bpm_target = bpm; d.fb_target = fbc; d.mix_target = mc; d.cutoff_target = cc; d.pingpong = 0;
+  d.memo_cut[0] = d.memo_cut[1] = -1.0f; d.memo_g[0] = d.memo_g[1] = 0.0f;
 }
 G_HD void spring_init(SpringDyn& d, float decay, float mix, float damping) {  // SpringReverbEffect::new
   decay = clampf(decay, 0.0f, 1.0f); mix = clampf(mix, 0.0f, 1.0f); damping = clampf(damping, 0.0f, 1.0f);
@@ -126,6 +129,7 @@ G_HD void spring_init(SpringDyn& d, float decay, float mix, float damping) {  //
     s.fb = s.damp = 0.0f; s.decay = {decay, decay}; s.mix = {mix, mix}; s.damping = {damping, damping};
   }
   d.decay_target = decay; d.mix_target = mix; d.damping_target = damping;
+  d.memo_decay[0] = d.memo_decay[1] = -1.0f; d.memo_fb[0] = d.memo_fb[1] = 0.0f;
 }
 G_HD void plate_init(PlateDyn& d, float decay, float mix, float damping) {  // PlateReverbEffect::new
   decay = clampf(decay, 0.0f, 1.0f); mix = clampf(mix, 0.0f, 1.0f); damping = clampf(damping, 0.0f, 1.0f);
@@ -133,6 +137,7 @@ G_HD void plate_init(PlateDyn& d, float decay, float mix, float damping) {  // P
   d.bandwidth = d.damp_a = d.damp_b = d.fb_a = d.fb_b = d.lfo_pa = d.lfo_pb = 0.0f;
   d.decay = {decay, decay}; d.mix = {mix, mix}; d.damping = {damping, damping}; d.predelay = {0.0f, 0.0f}; d.width = {1.0f, 1.0f}; d.size = {0.5f, 0.5f};
   d.t_decay = decay; d.t_mix = mix; d.t_damping = damping; d.t_predelay = 0.0f; d.t_width = 1.0f; d.t_size = 0.5f;
+  d.memo_sz = -1.0f; d.memo_size = 0.0f;
 }
 // effect_chain.rs:57-109 defaults for rack effects vs ffi.rs:869-884 defaults for the global instances
 G_HD void fx_construct(FxDyn& f, uint32_t kind, bool rack, float sr, float bpm) {
@@ -178,8 +183,10 @@ __device__ __forceinline__ float tilt_one(TiltDyn& d, int c, float in, const Rat
   float knob = sm_tick(d.cutoff[c], rc.smooth30);
   float resonance = sm_tick(d.res[c], rc.smooth30);
   float mix, freq; bool lp;
-  if (knob < 0.5f) { mix = 1.0f - (knob * 2.0f); float t = knob * 2.0f; freq = 80.0f * gm::g_powf(20000.0f / 80.0f, t); lp = true; }
-  else { mix = (knob - 0.5f) * 2.0f; float t = (knob - 0.5f) * 2.0f; freq = 20.0f * gm::g_powf(8000.0f / 20.0f, t); lp = false; }
+  // the powf is a pure function of the knob: re-evaluated only when the smoothed knob moves (bit-identical)
+  if (knob != d.memo_t[c]) { d.memo_t[c] = knob; d.memo_pow[c] = knob < 0.5f ? gm::g_powf(20000.0f / 80.0f, knob * 2.0f) : gm::g_powf(8000.0f / 20.0f, (knob - 0.5f) * 2.0f); }
+  if (knob < 0.5f) { mix = 1.0f - (knob * 2.0f); freq = 80.0f * d.memo_pow[c]; lp = true; }
+  else { mix = (knob - 0.5f) * 2.0f; freq = 20.0f * d.memo_pow[c]; lp = false; }
   if (mix < 0.001f) return in;
   float q = 0.5f + resonance * 8.0f;
   tpt_set(d.svf[c], rc.sr, freq, q);
@@ -224,7 +231,8 @@ __device__ __forceinline__ DelayPrep delay_prep(DelayDyn& d, int c, const RingRe
 __device__ __forceinline__ DelayStep delay_filter(DelayDyn& d, int c, const DelayPrep& p, float s1, float s2, const RateCtx& rc) {  // :361-399
   DelayCh& s = d.ch[c];
   float delayed = s1 * (1.0f - p.df) + s2 * p.df;
-  float g = 1.0f - gm::g_expf(-2.0f * PI_F * p.cutoff / rc.sr);
+  if (p.cutoff != d.memo_cut[c]) { d.memo_cut[c] = p.cutoff; d.memo_g[c] = 1.0f - gm::g_expf(-2.0f * PI_F * p.cutoff / rc.sr); }
+  float g = d.memo_g[c];
   float rfb = 0.3f * (s.z1 - s.z2);
   s.z1 = s.z1 + g * (delayed + rfb - s.z1);
   s.z2 = s.z2 + g * (s.z1 - s.z2);
@@ -262,7 +270,8 @@ __device__ __forceinline__ float spring_one(SpringDyn& d, int c, const RingRef& 
   in = isfinite(in) ? in : 0.0f;
   sm_set(s.decay, d.decay_target, 0.0f, 1.0f); sm_set(s.mix, d.mix_target, 0.0f, 1.0f); sm_set(s.damping, d.damping_target, 0.0f, 1.0f);
   float decay = sm_tick(s.decay, rc.smooth15), mix = sm_tick(s.mix, rc.smooth15), damping = sm_tick(s.damping, rc.smooth15);
-  float feedback = gm::g_powf(decay, 0.4f) * 0.95f;
+  if (decay != d.memo_decay[c]) { d.memo_decay[c] = decay; d.memo_fb[c] = gm::g_powf(decay, 0.4f) * 0.95f; }
+  float feedback = d.memo_fb[c];
   float d1 = damping, d2 = 1.0f - damping;
   float sig = in + s.fb;
 #pragma unroll
@@ -307,7 +316,8 @@ __device__ __forceinline__ void plate_tank(PlateDyn& d, const RingRef& r, const 
   float decay_knob = sm_tick(d.decay, rc.smooth15); mix = sm_tick(d.mix, rc.smooth15); float damping = sm_tick(d.damping, rc.smooth15);
   float predelay_knob = sm_tick(d.predelay, rc.smooth15); float width = sm_tick(d.width, rc.smooth15);
   float sz = sm_tick(d.size, rc.smooth15);
-  float size = sz <= 0.5f ? gm::g_powf(4.0f, 2.0f * sz - 1.0f) : gm::g_powf(2.0f, 2.0f * sz - 1.0f);
+  if (sz != d.memo_sz) { d.memo_sz = sz; d.memo_size = sz <= 0.5f ? gm::g_powf(4.0f, 2.0f * sz - 1.0f) : gm::g_powf(2.0f, 2.0f * sz - 1.0f); }
+  float size = d.memo_size;
   float decay_gain = decay_knob * 0.95f;
   float dd2 = clampf(decay_gain + 0.15f, 0.25f, 0.50f);
   float damp = damping * 0.95f;
