@@ -177,7 +177,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION/INFO would print to stdout next to the one JSON line
+        # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
