@@ -173,6 +173,14 @@ inline int wave_group_width(int id) {
 // GOOEY_B200_BACKEND=serial forces the per-sample-order back-end (kernel C) everywhere: the A/B switch used by the
 // parity tests to compare the two back-ends.
 inline bool serial_backend() { const char* e = getenv("GOOEY_B200_BACKEND"); return e && strcmp(e, "serial") == 0; }
+// Above this many voices of one type the per-sample-order back end with one voice per THREAD wins: the warp-per-voice
+// back end spends 32 lanes on the replayed recurrences of one voice, which pays only while voices are too few to fill the
+// device with threads (measured, 32768 voices x 2 s: tom 234 vs 526 ms, hi-hat 117 vs 193 ms; at 16384: 176 vs 263 and
+// 104 vs 97 ms).  GOOEY_B200_SERIAL_ABOVE overrides.
+inline int serial_above() {
+  if (const char* e = getenv("GOOEY_B200_SERIAL_ABOVE")) { int v = atoi(e); if (v > 0) return v; }
+  return 12288;
+}
 
 // Kernels whose shared-memory carve-out differs cannot share an SM: the L1 / shared split is an SM-wide setting, so a
 // back end with 19 KB of scan tables per CTA and one with 3.5 KB would be given disjoint SMs instead of interleaving
@@ -333,7 +341,7 @@ template <class V> struct TypeRunner {
         timed_units[i] = (double)cnt * L.chunk_frames;
         GH_CUDA(cudaEventRecord(evT0[i], sC));
         if constexpr (WaveOf<V>::has) {
-          if (!serial_backend()) {
+          if (!serial_backend() && cnt < serial_above()) {
             const int g = wave_group_width(WaveOf<V>::ID);          // voices per warp = 32 / g, one warp per CTA
             const int warps = (cnt * g + 31) / 32;
 #ifdef GOOEY_WAVE_ALL_WIDTHS

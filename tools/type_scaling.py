@@ -11,14 +11,15 @@ from workloads import drum_sweep_patches
 
 FRAMES = 88200
 EXACT = os.environ.get("EXACT_TIER") == "1"
-patches, vel, kinds = drum_sweep_patches(16384, seed=0x600E7, exact_tier=EXACT)
+COUNTS = [int(x) for x in os.environ.get("COUNTS", "").split(",") if x]
+patches, vel, kinds = drum_sweep_patches(max([16384] + [4 * c for c in COUNTS]), seed=0x600E7, exact_tier=EXACT)
 L = lib()
 only = sys.argv[1].split(",") if len(sys.argv) > 1 else ["tom", "hat", "snare", "kick"]
 for kind, name in [(3, "tom"), (2, "hat"), (1, "snare"), (0, "kick")]:
     if name not in only:
         continue
     idx = [i for i, k in enumerate(kinds) if k == kind]
-    for n in ([1024, 2048, 4096] if len(sys.argv) > 1 else [256, 512, 1024, 2048, 4096]):
+    for n in (COUNTS or ([1024, 2048, 4096] if len(sys.argv) > 1 else [256, 512, 1024, 2048, 4096])):
         sel = idx[:n]
         b = V.VoiceBatch([patches[i] for i in sel], 44100.0)
         v = np.ascontiguousarray(vel[sel])
