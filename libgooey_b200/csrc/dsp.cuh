@@ -229,12 +229,21 @@ G_HD float hash_noise(uint64_t idx) {
 
 // ---- gen/oscillator.rs: time-based waveforms ----------------------------------------------
 // idx = f32(elapsed) * sr ; sine = sin(idx * freq * 2pi / sr), left-to-right in f32 (:42-46)
-G_HD float osc_sine(float idx, float freq, float sr) {
+// 1 / (i * i) for odd i = 2 k + 1 < 2 INV_SQ_N, evaluated on the host with the expression of oscillator.rs:118 (an IEEE
+// division costs ~10 instructions per harmonic otherwise); filled next to c_hb.
+constexpr int INV_SQ_N = 1024;
+#ifdef __CUDACC__
+__constant__ float c_inv_sq[INV_SQ_N];
+#endif
+// FAST = the ~1-ulp sine (gm::g_sinf_fast) instead of the bit-exact glibc port: the time-parallel front end only
+template <bool FAST = false> G_HD float osc_sine(float idx, float freq, float sr) {
   const float two_pi = 2.0f * PI_F;
-  return gm::g_sinf(idx * freq * two_pi / sr);
+  const float x = idx * freq * two_pi / sr;
+  if (FAST) return gm::g_sinf_fast(x);
+  return gm::g_sinf(x);
 }
 // additive "triangle": odd harmonics, gain 1/i^2 (powf(i,2) is exact so 1/(i*i) matches), Gibbs taper (:106-131)
-G_HD float osc_triangle(float idx, float freq, float sr) {
+template <bool FAST = false> G_HD float osc_triangle(float idx, float freq, float sr) {
   float output = 0.0f;
   float nyquist = sr / 2.0f;
   float q = nyquist / freq;
@@ -242,12 +251,16 @@ G_HD float osc_triangle(float idx, float freq, float sr) {
   for (int i = 1; i <= max_h; i += 2) {
     float fi = (float)i;
     if (freq * fi > nyquist) break;
+#ifdef __CUDA_ARCH__
+    float gain = i < 2 * INV_SQ_N ? c_inv_sq[i >> 1] : 1.0f / (fi * fi);   // same f32 quotient, tabulated (i is uniform across the warp)
+#else
     float gain = 1.0f / (fi * fi);
+#endif
     float hf = freq * fi;
     float ratio = hf / nyquist;
     float taper = 1.0f;
     if (ratio > 0.75f) { float t = (ratio - 0.75f) / 0.25f; taper = 1.0f - t * t; }
-    output += gain * taper * osc_sine(idx, hf, sr);
+    output += gain * taper * osc_sine<FAST>(idx, hf, sr);
   }
   return output;
 }

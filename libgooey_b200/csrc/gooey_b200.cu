@@ -56,6 +56,11 @@ static void use_device(int device) {
     float hb[8];
     gd::design_halfband8(hb);
     GH_CUDA(cudaMemcpyToSymbol(gd::c_hb, hb, sizeof hb));
+    {
+      static float inv_sq[gd::INV_SQ_N];
+      for (int k = 0; k < gd::INV_SQ_N; k++) { volatile float fi = (float)(2 * k + 1); volatile float sq = fi * fi; inv_sq[k] = 1.0f / sq; }
+      GH_CUDA(cudaMemcpyToSymbol(gd::c_inv_sq, inv_sq, sizeof inv_sq));
+    }
     double mf[128];   // music/note.rs:81-83 midi_to_freq in f64, with the platform libm
     for (int n = 0; n < 128; n++) mf[n] = 440.0 * pow(2.0, ((double)n - 69.0) / 12.0);
     GH_CUDA(cudaMemcpyToSymbol(gd::c_midi_freq, mf, sizeof mf));

@@ -204,7 +204,7 @@ G_HD KickDer kick_derive(const KickCtl& c) {
 }
 // Oscillator::tick x3 (oscillator.rs:242-286) + envelope values.  An oscillator whose envelope amplitude or volume
 // is exactly 0 contributes raw*0 = +-0, so its waveform is skipped (raw is always finite).
-G_HD KickFront kick_front(const KickCtl& c, const KickDer& d, double now, float sr) {
+template <bool FAST = false> G_HD KickFront kick_front(const KickCtl& c, const KickDer& d, double now, float sr) {
   KickFront f;
   float pev = env_value(c.pitch_env, now);
   float fm = 1.0f + (c.tpm - 1.0f) * pev;
@@ -219,12 +219,12 @@ G_HD KickFront kick_front(const KickCtl& c, const KickDer& d, double now, float 
   {
     float idx = env_active(c.sub_env) ? (float)(now - c.sub_env.trig) * sr : 0.0f;
     float amp = env_value(c.sub_env, now);
-    if (amp != 0.0f && d.sub_vol != 0.0f) sub_out = osc_sine(idx, sub_f, sr) * amp * d.sub_vol;
+    if (amp != 0.0f && d.sub_vol != 0.0f) sub_out = osc_sine<FAST>(idx, sub_f, sr) * amp * d.sub_vol;
   }
   {
     float idx = env_active(c.punch_env) ? (float)(now - c.punch_env.trig) * sr : 0.0f;
     float amp = env_value(c.punch_env, now);
-    if (amp != 0.0f && d.punch_vol != 0.0f) punch_out = osc_triangle(idx, punch_f, sr) * amp * d.punch_vol;
+    if (amp != 0.0f && d.punch_vol != 0.0f) punch_out = osc_triangle<FAST>(idx, punch_f, sr) * amp * d.punch_vol;
   }
   {
     float idx = env_active(c.click_env) ? (float)(now - c.click_env.trig) * sr : 0.0f;
@@ -435,7 +435,7 @@ G_HD SnareDer snare_derive(const SnareCtl& c) {
   d.filter_type = c.filter_type;
   return d;
 }
-G_HD SnareFront snare_front(const SnareCtl& c, const SnareDer& d, double now, float sr) {
+template <bool FAST = false> G_HD SnareFront snare_front(const SnareCtl& c, const SnareDer& d, double now, float sr) {
   SnareFront f;
   float pev = env_value(c.pitch_env, now);
   float fm = 1.0f + (c.psm - 1.0f) * pev;
@@ -451,7 +451,7 @@ G_HD SnareFront snare_front(const SnareCtl& c, const SnareDer& d, double now, fl
   float tonal_env = env_value(c.tonal_env, now);
   f.tonal_out = 0.0f;
   if (osc_amp != 0.0f && c.tonal_vol != 0.0f && tonal_env != 0.0f && d.tonal_mix != 0.0f)
-    f.tonal_out = osc_triangle(idx_t, tonal_f, sr) * osc_amp * c.tonal_vol * tonal_env * d.tonal_mix;
+    f.tonal_out = osc_triangle<FAST>(idx_t, tonal_f, sr) * osc_amp * c.tonal_vol * tonal_env * d.tonal_mix;
   float idx_n = env_active(c.noise_osc_env) ? (float)(now - c.noise_osc_env.trig) * sr : 0.0f;
   float namp = env_value(c.noise_osc_env, now);
   f.raw_noise = 0.0f;
