@@ -257,9 +257,11 @@ template <bool FAST = false> G_HD float osc_triangle(float idx, float freq, floa
     float gain = 1.0f / (fi * fi);
 #endif
     float hf = freq * fi;
-    float ratio = hf / nyquist;
     float taper = 1.0f;
-    if (ratio > 0.75f) { float t = (ratio - 0.75f) / 0.25f; taper = 1.0f - t * t; }
+    if (hf > 0.7f * nyquist) {          // below that hf / nyquist cannot round above 0.75: skip the division (same result)
+      float ratio = hf / nyquist;
+      if (ratio > 0.75f) { float t = (ratio - 0.75f) / 0.25f; taper = 1.0f - t * t; }
+    }
     output += gain * taper * osc_sine<FAST>(idx, hf, sr);
   }
   return output;
