@@ -18,6 +18,9 @@
 #include "wave.cuh"
 #include "gran_wave.cuh"
 #include "bass_wave.cuh"
+#ifndef GOOEY_WAVE_CTA_WARPS_DEFAULT
+#define GOOEY_WAVE_CTA_WARPS_DEFAULT 1
+#endif
 #ifndef GOOEY_WAVE_G_KICK
 #define GOOEY_WAVE_G_KICK 32
 #define GOOEY_WAVE_G_SNARE 32
@@ -177,6 +180,15 @@ inline bool serial_backend() { const char* e = getenv("GOOEY_B200_BACKEND"); ret
 // back end spends 32 lanes on the replayed recurrences of one voice, which pays only while voices are too few to fill the
 // device with threads (measured, 32768 voices x 2 s: tom 234 vs 526 ms, hi-hat 117 vs 193 ms; at 16384: 176 vs 263 and
 // 104 vs 97 ms).  GOOEY_B200_SERIAL_ABOVE overrides.
+// Warps (= voices) per CTA of the scan back end: 8 keeps an SM's warps in step (one CTA barrier per block) so they share
+// instruction fetches, 1 lets every voice run free.  Measured on C2: no gain from the lock-step (isolated buckets equal,
+// the mix 54.7 vs 50.1 ms), so 1 is the default; GOOEY_B200_WAVE_WARPS=1|8 (tuning knob).
+inline int wave_cta_warps() {
+  const char* e = getenv("GOOEY_B200_WAVE_WARPS");
+  if (e && atoi(e) == 1) return 1;
+  if (e && atoi(e) == 8) return 8;
+  return GOOEY_WAVE_CTA_WARPS_DEFAULT;
+}
 inline int serial_above() {
   if (const char* e = getenv("GOOEY_B200_SERIAL_ABOVE")) { int v = atoi(e); if (v > 0) return v; }
   return 12288;
@@ -349,7 +361,8 @@ template <class V> struct TypeRunner {
             else if (g == 8) GH_LAUNCH((gd::w8::wave_kernel<typename WaveOf<V>::w8, 1>), warps, 32, sC, L);
             else
 #endif
-            GH_LAUNCH((gd::w32::wave_kernel<typename WaveOf<V>::w32, 1>), warps, 32, sC, L);
+            if (wave_cta_warps() == 8) GH_LAUNCH((gd::w32::wave_kernel<typename WaveOf<V>::w32, 8>), (warps + 7) / 8, 256, sC, L);
+            else GH_LAUNCH((gd::w32::wave_kernel<typename WaveOf<V>::w32, 1>), warps, 32, sC, L);
           } else GH_LAUNCH((gd::back_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);
         } else GH_LAUNCH((gd::back_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());
