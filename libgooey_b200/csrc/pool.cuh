@@ -182,7 +182,7 @@ inline bool serial_backend() { const char* e = getenv("GOOEY_B200_BACKEND"); ret
 // 104 vs 97 ms).  GOOEY_B200_SERIAL_ABOVE overrides.
 // Warps (= voices) per CTA of the scan back end: 8 keeps an SM's warps in step (one CTA barrier per block) so they share
 // instruction fetches, 1 lets every voice run free.  Measured on C2: no gain from the lock-step (isolated buckets equal,
-// the mix 54.7 vs 50.1 ms), so 1 is the default; GOOEY_B200_WAVE_WARPS=1|8 (tuning knob).
+// the mix 54.7 vs 50.1 ms), so 1 is the default; build with -DGOOEY_WAVE_LOCKSTEP and set GOOEY_B200_WAVE_WARPS=8 to try it.
 inline int wave_cta_warps() {
   const char* e = getenv("GOOEY_B200_WAVE_WARPS");
   if (e && atoi(e) == 1) return 1;
@@ -361,8 +361,11 @@ template <class V> struct TypeRunner {
             else if (g == 8) GH_LAUNCH((gd::w8::wave_kernel<typename WaveOf<V>::w8, 1>), warps, 32, sC, L);
             else
 #endif
+#ifdef GOOEY_WAVE_LOCKSTEP          // compiled on request only (it doubles the build time of the back ends)
             if (wave_cta_warps() == 8) GH_LAUNCH((gd::w32::wave_kernel<typename WaveOf<V>::w32, 8>), (warps + 7) / 8, 256, sC, L);
-            else GH_LAUNCH((gd::w32::wave_kernel<typename WaveOf<V>::w32, 1>), warps, 32, sC, L);
+            else
+#endif
+            GH_LAUNCH((gd::w32::wave_kernel<typename WaveOf<V>::w32, 1>), warps, 32, sC, L);
           } else GH_LAUNCH((gd::back_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);
         } else GH_LAUNCH((gd::back_kernel<V, 32>), (cnt + 31) / 32, 32, sC, L);   // one voice per lane, one warp per CTA
         GH_CUDA(cudaGetLastError());
