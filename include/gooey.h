@@ -7,8 +7,9 @@
  * Rendering happens on an NVIDIA B200; there is no CPU fallback: without a CUDA device gooey_engine_new returns NULL
  * and gooey_b200_last_error() says why.
  *
- * Out of scope in this build (calls are accepted where noted): UI getters, LFO pool, preset blend,
- * samplers, loop mixer, clip grid, MIDI/Link, saturation / compressor / lowpass / waveshaper global effects.
+ * Out of scope in this build: UI getters, samplers, loop mixer, clip grid, MIDI / Link.  A call that asks for
+ * something this build cannot render (more effect instances than it has slots) latches the sticky error and fires the error
+ * callback instead of rendering different audio silently.
  */
 #ifndef GOOEY_H
 #define GOOEY_H
@@ -54,6 +55,35 @@ typedef struct GooeyEngine GooeyEngine;
 #define GOOEY_PLATE_PARAM_WIDTH 4u
 #define GOOEY_PLATE_PARAM_SIZE 5u
 #define GOOEY_LIMITER_PARAM_THRESHOLD 0u
+#define GOOEY_FILTER_PARAM_CUTOFF 0u          /* low-pass: Hz 20-20000, resonance 0-0.95 */
+#define GOOEY_FILTER_PARAM_RESONANCE 1u
+#define GOOEY_SATURATION_PARAM_DRIVE 0u
+#define GOOEY_SATURATION_PARAM_WARMTH 1u
+#define GOOEY_SATURATION_PARAM_MIX 2u
+#define GOOEY_COMPRESSOR_PARAM_THRESHOLD 0u   /* dB -60..0, ratio 1..20, attack ms 0.1..100, release ms 5..1000, mix 0..1 */
+#define GOOEY_COMPRESSOR_PARAM_RATIO 1u
+#define GOOEY_COMPRESSOR_PARAM_ATTACK 2u
+#define GOOEY_COMPRESSOR_PARAM_RELEASE 3u
+#define GOOEY_COMPRESSOR_PARAM_MIX 4u
+#define GOOEY_COMPRESSOR_SIDECHAIN_NONE 0xFFFFFFFFu
+#define GOOEY_WAVESHAPER_PARAM_DRIVE 0u       /* 1-10 */
+#define GOOEY_WAVESHAPER_PARAM_MIX 1u
+#define GOOEY_FEEDBACK_WAVESHAPER_PARAM_DRIVE 0u          /* 1-100 */
+#define GOOEY_FEEDBACK_WAVESHAPER_PARAM_FEEDBACK 1u       /* 0-0.98 */
+#define GOOEY_FEEDBACK_WAVESHAPER_PARAM_FILTER_CUTOFF 2u  /* Hz 200-20000 */
+#define GOOEY_FEEDBACK_WAVESHAPER_PARAM_MIX 3u
+#define GOOEY_SCALE_MAJOR 0u                  /* :5502-5515 */
+#define GOOEY_SCALE_MINOR 1u
+#define GOOEY_VOICING_ROOT_POSITION 0u
+#define GOOEY_VOICING_FIRST_INVERSION 1u
+#define GOOEY_VOICING_SECOND_INVERSION 2u
+#define GOOEY_VOICING_THIRD_INVERSION 3u
+#define GOOEY_VOICING_OPEN 4u
+#define GOOEY_VOICING_DROP2 5u
+#define GOOEY_VOICING_DROP3 6u
+#define GOOEY_VOICING_SPREAD 7u
+#define GOOEY_VOICING_SHELL 8u
+#define GOOEY_VOICING_ROOTLESS 9u
 #define GOOEY_SOURCE_DRUMKIT 0u               /* src/mixer/graph.rs:27-42 */
 #define GOOEY_SOURCE_BASS 1u
 #define GOOEY_SOURCE_POLYSYNTH 2u
@@ -100,6 +130,9 @@ void gooey_engine_set_tom_param(GooeyEngine* engine, uint32_t param, float value
 void gooey_engine_set_bass_param(GooeyEngine* engine, uint32_t param, float value);
 void gooey_engine_set_channel_param(GooeyEngine* engine, uint32_t channel, uint32_t param, float value);
 void gooey_engine_load_bass_preset(GooeyEngine* engine, uint32_t preset);                        /* :2933 */
+/* :2304-2343 — another synthesizer type on a channel (0-3 kit, 4 bass); the new instrument is `<Voice>::new(sample_rate)`. */
+void gooey_engine_set_channel_instrument_type(GooeyEngine* engine, uint32_t channel, uint32_t instrument_type);
+uint32_t gooey_engine_get_channel_instrument_type(const GooeyEngine* engine, uint32_t channel);  /* :2360-2372 */
 
 /* ---- transport (:3337-3364, :3469, :3300) ---- */
 void gooey_engine_set_bpm(GooeyEngine* engine, float bpm);
@@ -128,10 +161,16 @@ void gooey_engine_set_instrument_solo(GooeyEngine* engine, uint32_t instrument, 
 void gooey_engine_trigger_instrument(GooeyEngine* engine, uint32_t instrument);
 void gooey_engine_trigger_instrument_with_velocity(GooeyEngine* engine, uint32_t instrument, float velocity);
 
-/* ---- global effect chain (:2988-3072, :3176-3200, :4498-4595): delay, tilt, spring reverb, plate reverb, limiter ---- */
+/* ---- global effect chain (:2988-3072, :3176-3237, :3252-3281, :4498-4620): all ten effects; the nine before the limiter
+ * can be reordered, which resets their state (:1417-1425) ---- */
 void gooey_engine_set_global_effect_param(GooeyEngine* engine, uint32_t effect, uint32_t param, float value);
 void gooey_engine_set_global_effect_enabled(GooeyEngine* engine, uint32_t effect, bool enabled);
+bool gooey_engine_get_global_effect_enabled(const GooeyEngine* engine, uint32_t effect);
+void gooey_engine_set_compressor_sidechain(GooeyEngine* engine, uint32_t instrument);
+uint32_t gooey_engine_get_compressor_sidechain(const GooeyEngine* engine);
 bool gooey_engine_set_effect_order(GooeyEngine* engine, const uint32_t* ids, uint32_t len);
+bool gooey_engine_move_effect(GooeyEngine* engine, uint32_t effect_id, uint32_t new_position);
+uint32_t gooey_engine_get_effect_order(const GooeyEngine* engine, uint32_t* out_ids, uint32_t max_len);
 
 /* ---- mixer graph (:6324-6674) ---- */
 int32_t gooey_engine_mixer_add_track(GooeyEngine* engine, const char* name);
@@ -143,16 +182,25 @@ void gooey_engine_mixer_set_track_mute(GooeyEngine* engine, uint32_t track, bool
 void gooey_engine_mixer_set_track_solo(GooeyEngine* engine, uint32_t track, bool soloed);
 int32_t gooey_engine_track_effect_add(GooeyEngine* engine, uint32_t track, uint32_t effect_id);
 void gooey_engine_track_effect_set_param(GooeyEngine* engine, uint32_t track, uint32_t slot, uint32_t param, float value);
+bool gooey_engine_track_effect_remove(GooeyEngine* engine, uint32_t track, uint32_t slot);
+bool gooey_engine_track_effect_move(GooeyEngine* engine, uint32_t track, uint32_t slot, uint32_t new_position);
+uint32_t gooey_engine_track_effect_count(const GooeyEngine* engine, uint32_t track);
+/* This build: at most 4 effects per track rack and 8 rack + {low-pass, saturation, compressor, waveshaper, feedback waveshaper}
+ * instances per engine; one more latches the sticky error. */
 
 /* ---- poly synth ("chord oscillators"; :5571-5648, :5899-5935).  Calls act at the engine's current time, like the reference.
- * gooey_engine_poly_trigger_chord's chord -> MIDI-note step (src/music, host-side tables) is not part of this library:
- * pass the notes `music::apply_voicing` produced to gooey_engine_poly_trigger_notes, which is the rest of that function. ---- */
+ * gooey_engine_poly_trigger_chord = diatonic seventh chord of (root, scale) at `degree` (src/music/key.rs:55-84), voiced
+ * (src/music/voicing.rs:76-172), then gooey_engine_poly_trigger_notes (libgooey_b200 addition: the same with explicit notes). ---- */
 #define GOOEY_POLY_PRESET_DEFAULT 0u
 #define GOOEY_POLY_PRESET_PAD 1u
 #define GOOEY_POLY_PRESET_PLUCK 2u
 #define GOOEY_POLY_PRESET_KEYS 3u
 #define GOOEY_POLY_PRESET_STRINGS 4u
+void gooey_engine_poly_trigger_chord(GooeyEngine* engine, uint32_t root, uint32_t scale_type, uint32_t degree, uint32_t voicing, uint32_t preset,
+                                     int32_t octave, float velocity);
 void gooey_engine_poly_trigger_notes(GooeyEngine* engine, const uint8_t* midi_notes, uint32_t n, uint32_t preset, float velocity);
+/* host-only: the notes the call above would trigger; returns their count */
+uint32_t gooey_b200_chord_notes(uint32_t root, uint32_t scale_type, uint32_t degree, uint32_t voicing, int32_t octave, uint8_t* out_notes, uint32_t capacity);
 void gooey_engine_poly_release(GooeyEngine* engine);
 void gooey_engine_poly_set_preset(GooeyEngine* engine, uint32_t preset);
 void gooey_engine_poly_set_param(GooeyEngine* engine, uint32_t param, float value);

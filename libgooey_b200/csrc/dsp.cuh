@@ -466,14 +466,15 @@ template <class F> G_D float os_process(Oversamp& o, float in, F f) {
 // ---- effects/waveshaper.rs:48-72 -----------------------------------------------------------------------------
 struct WShaper { float drive, mix; Oversamp os; };
 G_HD void ws_init(WShaper& w, float drive, float mix) { w.drive = clampf(drive, 1.0f, 10.0f); w.mix = clampf(mix, 0.0f, 1.0f); os_init(w.os); }
-G_D float ws_process(WShaper& w, float in) {
-  if (!isfinite(in)) { os_reset(w.os); return 0.0f; }
-  if (w.mix <= 0.0001f || w.drive <= 1.0f) return in;
-  float d = w.drive;
+G_D float ws_core(float drive, float mix, Oversamp& os, float in) {
+  if (!isfinite(in)) { os_reset(os); return 0.0f; }
+  if (mix <= 0.0001f || drive <= 1.0f) return in;
+  float d = drive;
   float comp = gm::g_tanhf(0.5f) / gm::g_tanhf(0.5f * d);
-  float sat = os_process(w.os, in, [&](float x) { return gm::g_tanhf(x * d) * comp; });
-  return in * (1.0f - w.mix) + sat * w.mix;
+  float sat = os_process(os, in, [&](float x) { return gm::g_tanhf(x * d) * comp; });
+  return in * (1.0f - mix) + sat * mix;
 }
+G_D float ws_process(WShaper& w, float in) { return ws_core(w.drive, w.mix, w.os, in); }
 
 // ---- effects/feedback_waveshaper.rs ---------------------------------------------------------------------------
 struct FbShaper {
@@ -498,7 +499,9 @@ G_HD void fbws_set_cutoff(FbShaper& w, float sr, float c) {
   c = clampf(c, 200.0f, 20000.0f);
   if (c != w.cutoff) { w.cutoff = c; w.filter_coeff = fbws_filter_coeff(c, sr); }  // pure function of (c, sr)
 }
-G_D float fbws_makeup(FbShaper& w) {  // the level-independent factor of gain_compensation (:252-256)
+// The functions below are templates over the state struct: FbShaper (a voice's own shaper, oversampler inside) and mix.cuh's
+// FbSmall (an effect slot, whose oversampler history lives in the slot's ring arena) share field names.
+template <class S> G_D float fbws_makeup(S& w) {  // the level-independent factor of gain_compensation (:252-256)
   if (w.drive != w.memo_drive || w.feedback != w.memo_fb) {
     float drive_norm = clampf((w.drive - 1.0f) / 99.0f, 0.0f, 1.0f);
     float fb_norm = clampf(w.feedback / 0.98f, 0.0f, 1.0f);
@@ -508,7 +511,7 @@ G_D float fbws_makeup(FbShaper& w) {  // the level-independent factor of gain_co
   }
   return w.memo_makeup;
 }
-G_D float fbws_gain_comp(FbShaper& w, float env) {  // :247-259
+template <class S> G_D float fbws_gain_comp(S& w, float env) {  // :247-259
   float reference = fmaxf(env, 0.05f);
   float driven = fmaxf(fabsf(gm::g_tanhf(reference * w.drive)), 1e-6f);
   float comp_no_fb = gm::g_tanhf(reference) / driven;
@@ -516,11 +519,11 @@ G_D float fbws_gain_comp(FbShaper& w, float env) {  // :247-259
   float taming = 1.0f / (1.0f + comp_no_fb * w.feedback * 0.25f);
   return fminf(comp_no_fb * taming * makeup, 3.0f);
 }
-G_D float fbws_process(FbShaper& w, float in) {  // :109-169
-  if (!isfinite(in)) { fbws_reset(w); return 0.0f; }
+template <class S> G_D float fbws_core(S& w, Oversamp& os, float in) {  // :109-169
+  if (!isfinite(in)) { w.last_out = w.filter_state = w.dc_x1 = w.dc_y1 = w.env = 0.0f; os_reset(os); return 0.0f; }
   if (w.mix <= 0.0001f || w.drive <= 1.0f) return in;
   float fb_in = w.drive * in + w.feedback * w.last_out;
-  float shaped = os_process(w.os, fb_in, [](float x) { return gm::g_tanhf(x); });
+  float shaped = os_process(os, fb_in, [](float x) { return gm::g_tanhf(x); });
   float rect = fabsf(in);
   float coeff = rect > w.env ? w.env_att : w.env_rel;
   w.env += (1.0f - coeff) * (rect - w.env);
@@ -533,9 +536,10 @@ G_D float fbws_process(FbShaper& w, float in) {  // :109-169
   w.filter_state += w.filter_coeff * (out - w.filter_state);
   if (fabsf(w.filter_state) < 1e-15f) w.filter_state = 0.0f;
   w.last_out = w.filter_state;
-  if (!isfinite(w.last_out) || fabsf(w.last_out) > 50.0f) { fbws_reset(w); return in; }
+  if (!isfinite(w.last_out) || fabsf(w.last_out) > 50.0f) { w.last_out = w.filter_state = w.dc_x1 = w.dc_y1 = w.env = 0.0f; os_reset(os); return in; }
   return in * (1.0f - w.mix) + out * w.mix;
 }
+G_D float fbws_process(FbShaper& w, float in) { return fbws_core(w, w.os, in); }
 
 // ---- instruments/fm_snap.rs:102-169 -----------------------------------------------------------------------------
 struct PhaseMod { double trig; uint32_t active; };

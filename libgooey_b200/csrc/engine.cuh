@@ -87,7 +87,9 @@ inline gd::FxGeom make_fx_geom(float sr) {
   return g;
 }
 inline uint32_t ring_words_of(const gd::FxGeom& g, uint32_t kind) {
-  switch (kind) { case gd::FXK_DELAY: return g.ring_words[1]; case gd::FXK_SPRING: return g.ring_words[2]; case gd::FXK_PLATE: return g.ring_words[3]; default: return 0; }
+  switch (kind) { case gd::FXK_DELAY: return g.ring_words[1]; case gd::FXK_SPRING: return g.ring_words[2]; case gd::FXK_PLATE: return g.ring_words[3];
+    case gd::FXK_SATURATION: case gd::FXK_COMPRESSOR: case gd::FXK_WAVESHAPER: case gd::FXK_FBWS: return 2u * gd::OS_WORDS;   // oversampler history, one per channel
+    default: return 0; }
 }
 
 // ---- everything resident on one device for one sample rate ---------------------------------------------------------
@@ -95,6 +97,7 @@ struct EngineBank {
   int device; float sr;
   gd::RateCtx rc; gd::FxGeom geo;
   VoiceBank voices;
+  ClockWindow clock;
   Pool<gd::MixState> mix_pool;
   std::vector<gd::MixCfg> cfgs;           // by mix slot (host authoritative)
   DevBuf<gd::MixCfg> d_cfg;
@@ -110,7 +113,7 @@ struct EngineBank {
   DevBuf<uint8_t> d_mix_fast;
   DevBuf<gd::MixConst> d_mix_consts;
   DevBuf<gd::VoiceEvent> d_mix_eventss[2];
-  std::mutex mu;
+  std::recursive_mutex mu;   // every use of the bank's shared buffers / streams, held for a whole render call
   float last_ms = 0.0f;
   EngineBank(int dev, float sr_) : device(dev), sr(sr_) {
     rc = gd::make_rate_ctx(sr); geo = make_fx_geom(sr);
@@ -175,31 +178,43 @@ struct GooeyEngine {
 
 namespace gh {
 
+struct BadBatch : std::runtime_error { using std::runtime_error::runtime_error; };   // caller error, not a device failure
+
 inline void engine_fail(GooeyEngine* e, const std::string& msg) {   // sticky error + one-shot callback (ffi.rs:2236-2284)
   if (!e) return;
   if (!e->has_error) { e->has_error = true; e->error = msg; }
   if (e->error_cb && !e->error_cb_fired) { e->error_cb_fired = true; e->error_cb(e->error_ctx, e->error.c_str()); }
 }
 
-inline GooeyEngine* engine_create(int device, float sr) {
-  EngineBank& B = engine_bank(device, sr);
-  std::lock_guard<std::mutex> lk(B.mu);
-  std::unique_ptr<GooeyEngine> e(new GooeyEngine);
-  e->bank = &B; e->sr = sr;
-  // default voices: kick(tight) / snare(tight) / hihat(short) / tom(Tom2::new) / bass(acid) (ffi.rs:809-954)
+// `<Voice>::new(sample_rate)` of each channel instrument: kick(tight) / snare(tight) / hihat(short) / Tom2::new / bass(acid)
+// (ffi.rs:809-850 and :2320-2326; kick.rs:772, snare.rs:764, hihat2.rs:350, tom2.rs:199, bass.rs:608)
+inline GooeyVoicePatch default_patch(uint32_t type) {
   static const float KICK_TIGHT[18] = {0.22f, 0.00f, 1.00f, 0.00f, 0.12f, 0.70f, 0.01f, 0.85f, 0.64f, 1.00f, 0.07f, 0.01f, 0.02f, 0.20f, 0.00f, 0.47f, 0.12f, 0.02f};
   static const float BASS_ACID[15] = {0.24f, 0.40f, 0.80f, 0.00f, 0.00f, 0.10f, 0.15f, 0.70f, 0.85f, 0.15f, 0.08f, 0.35f, 0.10f, 0.30f, 0.80f};
-  GooeyVoicePatch p[5];
-  memset(p, 0, sizeof p);
-  p[0].instrument = GOOEY_INSTRUMENT_KICK; memcpy(p[0].params, KICK_TIGHT, sizeof KICK_TIGHT);
-  {  // SnareConfig::tight() = SnareConfig::new(0.2, 0.4, 0.7, 0.5, 0.029, 0.3, 0.8) (snare.rs:99-132, 270-280)
-    const float d = 0.029f;
-    const float s[19] = {0.2f, 0.4f, 0.7f, 0.5f, d, 0.3f, 0.8f, d * 0.8f, 0.091f, d * 0.6f, d, 0.495f, 0.053f, 1.0f, 0.5f, 0.0f, 0.0f, 0.125f, 0.02f};
-    p[1].instrument = GOOEY_INSTRUMENT_SNARE; memcpy(p[1].params, s, sizeof s);
+  GooeyVoicePatch p;
+  memset(&p, 0, sizeof p);
+  p.instrument = type;
+  switch (type) {
+    case GOOEY_INSTRUMENT_KICK: memcpy(p.params, KICK_TIGHT, sizeof KICK_TIGHT); break;
+    case GOOEY_INSTRUMENT_SNARE: {  // SnareConfig::tight() = SnareConfig::new(0.2, 0.4, 0.7, 0.5, 0.029, 0.3, 0.8) (snare.rs:99-132, 270-280)
+      const float d = 0.029f;
+      const float s[19] = {0.2f, 0.4f, 0.7f, 0.5f, d, 0.3f, 0.8f, d * 0.8f, 0.091f, d * 0.6f, d, 0.495f, 0.053f, 1.0f, 0.5f, 0.0f, 0.0f, 0.125f, 0.02f};
+      memcpy(p.params, s, sizeof s);
+    } break;
+    case GOOEY_INSTRUMENT_HIHAT: { const float h[5] = {0.76f, 0.05f, 0.00f, 1.00f, 1.0f}; memcpy(p.params, h, sizeof h); } break;
+    case GOOEY_INSTRUMENT_BASS: memcpy(p.params, BASS_ACID, sizeof BASS_ACID); break;
+    default: break;   // tom: Tom2::new
   }
-  { const float h[5] = {0.76f, 0.05f, 0.00f, 1.00f, 1.0f}; p[2].instrument = GOOEY_INSTRUMENT_HIHAT; memcpy(p[2].params, h, sizeof h); }
-  p[3].instrument = GOOEY_INSTRUMENT_TOM;
-  p[4].instrument = GOOEY_INSTRUMENT_BASS; memcpy(p[4].params, BASS_ACID, sizeof BASS_ACID);
+  return p;
+}
+
+inline GooeyEngine* engine_create(int device, float sr) {
+  EngineBank& B = engine_bank(device, sr);
+  std::lock_guard<std::recursive_mutex> lk(B.mu);
+  std::unique_ptr<GooeyEngine> e(new GooeyEngine);
+  e->bank = &B; e->sr = sr;
+  GooeyVoicePatch p[5];
+  for (uint32_t t = 0; t < 5; t++) p[t] = default_patch(t);
   for (int ch = 0; ch < 5; ch++) {
     e->strip[ch].type = p[ch].instrument;
     e->strip[ch].slot = B.voices.create(p[ch], sr);
@@ -235,6 +250,9 @@ inline GooeyEngine* engine_create(int device, float sr) {
   const uint32_t order[9] = {7, 2, 0, 4, 1, 3, 8, 6, 9};   // DEFAULT_EFFECT_ORDER (ffi.rs:1583-1593)
   for (int i = 0; i < 9; i++) c.order[i] = order[i];
   for (int s = 0; s < gd::MAX_FX; s++) { c.fx_kind[s] = s < 4 ? kinds[s] : (uint32_t)gd::FXK_NONE; c.fx_enabled[s] = 0; }
+  for (int i = 0; i < 12; i++) c.gslot[i] = 0xff;
+  for (int s = 0; s < 4; s++) c.gslot[kinds[s]] = (uint8_t)s;
+  c.comp_sidechain = 0xFFFFFFFFu; c.fx_rack = 0;
   c.limiter_on = 0; c.lim_th = 1.0f; c.lim_inv = 1.0f;
   if ((int)B.cfgs.size() <= e->mix_slot) B.cfgs.resize(e->mix_slot + 1);
   B.cfgs[e->mix_slot] = c;
@@ -244,7 +262,7 @@ inline GooeyEngine* engine_create(int device, float sr) {
 inline void engine_destroy(GooeyEngine* e) {
   if (!e) return;
   EngineBank& B = *e->bank;
-  std::lock_guard<std::mutex> lk(B.mu);
+  std::lock_guard<std::recursive_mutex> lk(B.mu);
   for (int ch = 0; ch < 5; ch++) B.voices.release(e->strip[ch].type, e->strip[ch].slot);
   B.voices.release(GOOEY_B200_VOICE_POLY, e->poly.slot);
   B.voices.release(GOOEY_B200_VOICE_GRANULATOR, e->gran.slot);
@@ -282,7 +300,7 @@ inline void aux_touch(GooeyEngine* e, bool is_gran) {
     a.pending.push_back(make_event(0, gd::EV_SET_AUX, gd::AUX_GRAN_BUFINFO, 44100.0f, 1));
     e->cfg.src_gran = 1;
   } else e->cfg.src_poly = 1;
-  std::lock_guard<std::mutex> lk(e->bank->mu);
+  std::lock_guard<std::recursive_mutex> lk(e->bank->mu);
   e->bank->cfgs[e->mix_slot] = e->cfg;
 }
 
@@ -292,7 +310,7 @@ inline void aux_touch(GooeyEngine* e, bool is_gran) {
 inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, int out_mode, bool bounce, float* out_dev, size_t stride) {
   if (E.empty() || frames == 0) return;
   EngineBank& B = *E[0]->bank;
-  std::lock_guard<std::mutex> lk(B.mu);
+  std::lock_guard<std::recursive_mutex> lk(B.mu);
   GH_CUDA(cudaSetDevice(B.device));
   cudaStream_t st = B.stream;
   const int n = (int)E.size();
@@ -300,17 +318,26 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   // ---- schedule resolution (host): per voice and per engine event lists over the whole call ----
   std::vector<std::vector<gd::VoiceEvent>> vev((size_t)n * 7), mev(n);   // per engine: 5 strips, poly, granulator
   bool any_poly = false, any_gran = false;
-  uint32_t kmax = 0;
+  // argument errors are found before any engine is touched (BadBatch -> GOOEY_E_INVALID, no sticky error)
+  {
+    std::set<const GooeyEngine*> seen;
+    for (int i = 0; i < n; i++) {
+      const GooeyEngine* e = E[i];
+      if (e->bank != &B) throw BadBatch("engines of one batch must share device and sample rate");
+      if (!seen.insert(e).second) throw BadBatch("the same engine appears twice in one batch");
+      if (!bounce && (uint64_t)e->k + frames >= 0xffffffffull) throw BadBatch("engine clock index would pass 2^32 frames (27 h at 44.1 kHz); bounce or recreate the engine");
+    }
+  }
+  uint64_t kmin = ~0ull, kmax = 0;
   std::vector<SeqFire> fires;
   for (int i = 0; i < n; i++) {
     GooeyEngine* e = E[i];
-    if (e->bank != &B) throw std::runtime_error("engines of one batch must share device and sample rate");
     if (bounce) {
       e->k = 0;
       for (auto& s : e->strip) { s.seq.reset(); s.seq.start(); }
     }
-    if ((uint64_t)e->k + frames >= 0xffffffffull) throw std::runtime_error("engine clock index overflow");
-    kmax = std::max(kmax, e->k + frames);
+    kmin = std::min<uint64_t>(kmin, e->k);
+    kmax = std::max<uint64_t>(kmax, (uint64_t)e->k + frames);
     auto& mx = mev[i];
     mx = e->mix_pending; e->mix_pending.clear();
     if (bounce) {
@@ -367,7 +394,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       }
     }
   }
-  const double* tt = clock_table(B.sr).ensure(B.device, (size_t)kmax + 1, st);
+  const double* tt = B.clock.view(clock_table(B.sr), kmin, kmax, st);
   // ---- device state: pools, configs, rings ----
   B.mix_pool.flush(st);
   B.d_cfg.upload(B.cfgs.data(), B.cfgs.size(), st);
@@ -375,8 +402,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   for (int i = 0; i < n; i++) {
     const gd::MixCfg& c = E[i]->cfg;
     for (int s = 0; s < gd::MAX_FX; s++) {
-      bool used = s < 4 ? c.fx_enabled[s] != 0 : false;
-      for (uint32_t t = 0; t < c.n_tracks && !used; t++) for (uint32_t r = 0; r < c.rack_n[t]; r++) if (c.rack_slot[t][r] == s) used = true;
+      const bool used = c.fx_kind[s] != gd::FXK_NONE && (s >= 4 || c.fx_enabled[s] != 0);
       if (used) need_words[s] = std::max(need_words[s], ring_words_of(B.geo, c.fx_kind[s]));
     }
   }

@@ -3,6 +3,7 @@
 // boundary; a device failure latches the engine's sticky error and zero-fills the output (ffi.rs:2079-2121).
 #pragma once
 #include "engine.cuh"
+#include "music.h"
 #include "../../include/gooey.h"
 
 namespace gh {
@@ -24,12 +25,24 @@ static void strip_set_param(GooeyEngine::Strip* s, uint32_t param, float value) 
   if (!s) return;
   ffi_param_to_events(s->type, param, value, [&](uint32_t kind, uint32_t p, float v) { s->pending.push_back(make_event(0, kind, p, v)); });
 }
-static int fx_slot_of(uint32_t effect) {
-  switch (effect) { case gd::FXK_TILT: return gd::FXS_TILT; case gd::FXK_DELAY: return gd::FXS_DELAY; case gd::FXK_SPRING: return gd::FXS_SPRING; case gd::FXK_PLATE: return gd::FXS_PLATE; default: return -1; }
+// Slot of a global effect.  Tilt / delay / spring / plate own slots 0-3 from construction; the other five reorderable
+// effects are built in a free slot the first time the host touches them (until then they sit, disabled, in their constructor
+// state, which nothing can observe).  -1: not a slot effect (limiter, unknown id) or no slot left (sticky error).
+static int gslot_ensure(GooeyEngine* e, uint32_t effect) {
+  if (effect > 9 || effect == gd::FXK_LIMITER) return -1;
+  if (e->cfg.gslot[effect] != 0xff) return e->cfg.gslot[effect];
+  for (int s = gd::FXS_RACK0; s < gd::MAX_FX; s++)
+    if (e->cfg.fx_kind[s] == gd::FXK_NONE) {
+      e->cfg.fx_kind[s] = effect; e->cfg.fx_enabled[s] = 0; e->cfg.gslot[effect] = (uint8_t)s;
+      e->mix_pending.push_back(make_event(0, gd::MX_FX_INIT, s, e->bpm, effect));
+      return s;
+    }
+  engine_fail(e, "libgooey_b200: more than 8 track-rack + saturation/compressor/lowpass/waveshaper effect instances on one engine");
+  return -1;
 }
 static void sync_cfg(GooeyEngine* e) {
   EngineBank& B = *e->bank;
-  std::lock_guard<std::mutex> lk(B.mu);
+  std::lock_guard<std::recursive_mutex> lk(B.mu);
   B.cfgs[e->mix_slot] = e->cfg;
 }
 static uint32_t bounce_frames(const GooeyEngine* e, uint32_t bars) {   // ffi.rs:7836-7838 / bounce.rs:20-32
@@ -67,6 +80,27 @@ void gooey_engine_set_hihat_param(GooeyEngine* e, uint32_t p, float v) { if (e) 
 void gooey_engine_set_tom_param(GooeyEngine* e, uint32_t p, float v) { if (e) gh::strip_set_param(gh::strip_by_type(e, GOOEY_INSTRUMENT_TOM), p, v); }
 void gooey_engine_set_bass_param(GooeyEngine* e, uint32_t p, float v) { if (e) gh::strip_set_param(gh::strip_by_type(e, GOOEY_INSTRUMENT_BASS), p, v); }
 void gooey_engine_set_channel_param(GooeyEngine* e, uint32_t ch, uint32_t p, float v) { if (e && ch < 5) gh::strip_set_param(&e->strip[ch], p, v); }
+// ffi.rs:2304-2343: a different synthesizer type on `channel`; the new instrument is `<Voice>::new(sample_rate)` and
+// starts fresh, the strip (gain, pan, mute / solo, sequencer pattern) is kept.  Parameter edits still queued for the old
+// instrument were applied to it (and die with it).
+void gooey_engine_set_channel_instrument_type(GooeyEngine* e, uint32_t ch, uint32_t type) {
+  if (!e || ch >= 5 || type > GOOEY_INSTRUMENT_BASS) return;
+  GooeyEngine::Strip& s = e->strip[ch];
+  if (s.type == type) return;
+  try {
+    gh::EngineBank& B = *e->bank;
+    std::lock_guard<std::recursive_mutex> lk(B.mu);
+    const GooeyVoicePatch p = gh::default_patch(type);
+    const int slot = B.voices.create(p, e->sr);
+    if (slot < 0) return;
+    B.voices.release(s.type, s.slot);
+    s.type = type; s.slot = slot;
+    s.pending.clear();
+    s.pending.push_back(gh::make_event(0, gd::EV_SET_TIME, 0, 0.0f, e->k));   // the fresh voice joins the engine's clock
+  } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); }
+}
+uint32_t gooey_engine_get_channel_instrument_type(const GooeyEngine* e, uint32_t ch) { return (e && ch < 5) ? e->strip[ch].type : 0xFFFFFFFFu; }   /* :2354-2371 */
+
 void gooey_engine_load_bass_preset(GooeyEngine* e, uint32_t id) {
   if (!e || id > 3) return;
   static const float P[4][15] = {   // BassConfig::{acid,sub,reese,stab} (bass.rs:188-269); set_config = 15 set_targets
@@ -148,21 +182,52 @@ void gooey_engine_set_global_effect_param(GooeyEngine* e, uint32_t fx, uint32_t 
     if (p == 0 && std::isfinite(v)) { float t = gd::clampf(v, 0.001f, 1.0f); e->cfg.lim_th = t; e->cfg.lim_inv = 1.0f / t; gh::sync_cfg(e); }
     return;
   }
-  int slot = gh::fx_slot_of(fx);
+  const int slot = gh::gslot_ensure(e, fx);
   if (slot >= 0 && p < 256) e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_SET, ((uint32_t)slot << 8) | p, v));
+  if (slot >= 0) gh::sync_cfg(e);
 }
 void gooey_engine_set_global_effect_enabled(GooeyEngine* e, uint32_t fx, bool on) {
   if (!e) return;
   if (fx == gd::FXK_LIMITER) e->cfg.limiter_on = on;
-  else { int slot = gh::fx_slot_of(fx); if (slot < 0) return; e->cfg.fx_enabled[slot] = on; }
+  else { const int slot = gh::gslot_ensure(e, fx); if (slot < 0) return; e->cfg.fx_enabled[slot] = on; }
   gh::sync_cfg(e);
 }
-bool gooey_engine_set_effect_order(GooeyEngine* e, const uint32_t* ids, uint32_t len) {   // a permutation of the 9 reorderable ids
+bool gooey_engine_get_global_effect_enabled(const GooeyEngine* e, uint32_t fx) {   /* :3214-3237 */
+  if (!e || fx > 9) return false;
+  if (fx == gd::FXK_LIMITER) return e->cfg.limiter_on != 0;
+  const uint32_t slot = e->cfg.gslot[fx];
+  return slot < (uint32_t)gd::MAX_FX && e->cfg.fx_enabled[slot] != 0;
+}
+void gooey_engine_set_compressor_sidechain(GooeyEngine* e, uint32_t instrument) { if (e) { e->cfg.comp_sidechain = instrument; gh::sync_cfg(e); } }   /* :3252-3265 */
+uint32_t gooey_engine_get_compressor_sidechain(const GooeyEngine* e) { return e ? e->cfg.comp_sidechain : 0xFFFFFFFFu; }
+static bool gooey_reorderable(uint32_t id) { return id <= 9 && id != gd::FXK_LIMITER; }
+bool gooey_engine_set_effect_order(GooeyEngine* e, const uint32_t* ids, uint32_t len) {   // a permutation of the 9 reorderable ids (:4498-4528)
   if (!e || !ids || len != 9) return false;
-  for (uint32_t i = 0; i < 9; i++) { if (ids[i] > 9 || ids[i] == gd::FXK_LIMITER) return false; for (uint32_t j = 0; j < i; j++) if (ids[j] == ids[i]) return false; }
+  for (uint32_t i = 0; i < 9; i++) { if (!gooey_reorderable(ids[i])) return false; for (uint32_t j = 0; j < i; j++) if (ids[j] == ids[i]) return false; }
   for (uint32_t i = 0; i < 9; i++) e->cfg.order[i] = ids[i];
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_RESET, 0, 0.0f));   // reset_effect_states
   gh::sync_cfg(e);
   return true;
+}
+bool gooey_engine_move_effect(GooeyEngine* e, uint32_t effect_id, uint32_t new_position) {   /* :4544-4581 */
+  if (!e || !gooey_reorderable(effect_id) || new_position >= 9) return false;
+  int cur = -1;
+  for (int i = 0; i < 9; i++) if (e->cfg.order[i] == effect_id) cur = i;
+  if (cur < 0) return false;
+  const int np = (int)new_position;
+  if (cur == np) return true;
+  if (np > cur) for (int i = cur; i < np; i++) e->cfg.order[i] = e->cfg.order[i + 1];
+  else for (int i = cur - 1; i >= np; i--) e->cfg.order[i + 1] = e->cfg.order[i];
+  e->cfg.order[np] = effect_id;
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_RESET, 0, 0.0f));
+  gh::sync_cfg(e);
+  return true;
+}
+uint32_t gooey_engine_get_effect_order(const GooeyEngine* e, uint32_t* out_ids, uint32_t max_len) {   /* :4596-4615 */
+  if (!e || !out_ids || max_len == 0) return 0;
+  const uint32_t n = max_len < 9 ? max_len : 9;
+  for (uint32_t i = 0; i < n; i++) out_ids[i] = e->cfg.order[i];
+  return n;
 }
 
 int32_t gooey_engine_mixer_add_track(GooeyEngine* e, const char*) {
@@ -185,20 +250,46 @@ void gooey_engine_mixer_set_track_gain(GooeyEngine* e, uint32_t t, float g) { if
 void gooey_engine_mixer_set_track_pan(GooeyEngine* e, uint32_t t, float p) { if (e && t < e->cfg.n_tracks) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_TR_PAN + t, gd::clampf(p, 0.0f, 1.0f))); }
 void gooey_engine_mixer_set_track_mute(GooeyEngine* e, uint32_t t, bool m) { if (e && t < e->cfg.n_tracks) e->track_muted[t] = m; }
 void gooey_engine_mixer_set_track_solo(GooeyEngine* e, uint32_t t, bool s) { if (e && t < e->cfg.n_tracks) e->track_soloed[t] = s; }
-int32_t gooey_engine_track_effect_add(GooeyEngine* e, uint32_t t, uint32_t fx) {   // effect_chain.rs:57-109; this build: delay / tilt / spring / plate
+int32_t gooey_engine_track_effect_add(GooeyEngine* e, uint32_t t, uint32_t fx) {   // ChannelEffect::from_id (effect_chain.rs:57-109): every effect but the limiter
   if (!e || t >= e->cfg.n_tracks) return -1;
-  if (gh::fx_slot_of(fx) < 0) return -1;
-  if (e->cfg.rack_n[t] >= 4) return -1;
+  if (!gooey_reorderable(fx)) return -1;
+  if (e->cfg.rack_n[t] >= 4) { gh::engine_fail(e, "libgooey_b200: a track rack holds at most 4 effects"); return -1; }
   int slot = -1;
   for (int s = gd::FXS_RACK0; s < gd::MAX_FX; s++) if (e->cfg.fx_kind[s] == gd::FXK_NONE) { slot = s; break; }
-  if (slot < 0) return -1;
-  e->cfg.fx_kind[slot] = fx; e->cfg.fx_enabled[slot] = 1;
+  if (slot < 0) { gh::engine_fail(e, "libgooey_b200: more than 8 track-rack + saturation/compressor/lowpass/waveshaper effect instances on one engine"); return -1; }
+  e->cfg.fx_kind[slot] = fx; e->cfg.fx_enabled[slot] = 1; e->cfg.fx_rack |= 1u << slot;
   const uint32_t pos = e->cfg.rack_n[t]++;
   e->cfg.rack_slot[t][pos] = (uint8_t)slot;
-  e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_INIT, slot, e->bpm, fx));
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_INIT, slot, e->bpm, fx | 0x100u));
   gh::sync_cfg(e);
   return (int32_t)pos;
 }
+// A removed effect frees its slot; queued edits that were addressed to it are dropped with it (they were applied to an effect
+// that no longer exists).  Ring memory of the slot is cleared when the slot is constructed again (MX_FX_INIT).
+bool gooey_engine_track_effect_remove(GooeyEngine* e, uint32_t t, uint32_t pos) {   /* :6607-6616, effect_chain.rs:310-317 */
+  if (!e || t >= e->cfg.n_tracks || pos >= e->cfg.rack_n[t]) return false;
+  const uint32_t slot = e->cfg.rack_slot[t][pos];
+  for (uint32_t k = pos; k + 1 < e->cfg.rack_n[t]; k++) e->cfg.rack_slot[t][k] = e->cfg.rack_slot[t][k + 1];
+  e->cfg.rack_n[t]--;
+  e->cfg.fx_kind[slot] = gd::FXK_NONE; e->cfg.fx_enabled[slot] = 0; e->cfg.fx_rack &= ~(1u << slot);
+  auto& mp = e->mix_pending;
+  mp.erase(std::remove_if(mp.begin(), mp.end(), [&](const gd::VoiceEvent& v) {
+    return ((v.kind == gd::MX_FX_SET && (uint32_t)(v.param >> 8) == slot) || ((v.kind == gd::MX_FX_INIT || v.kind == gd::MX_FX_BPM) && v.param == slot)); }), mp.end());
+  gh::sync_cfg(e);
+  return true;
+}
+bool gooey_engine_track_effect_move(GooeyEngine* e, uint32_t t, uint32_t pos, uint32_t new_position) {   /* :6623-6640, effect_chain.rs:322-330 */
+  if (!e || t >= e->cfg.n_tracks || pos >= e->cfg.rack_n[t]) return false;
+  const uint32_t n = e->cfg.rack_n[t];
+  uint8_t tmp[4]; uint32_t m = 0;
+  const uint8_t moved = e->cfg.rack_slot[t][pos];
+  for (uint32_t k = 0; k < n; k++) if (k != pos) tmp[m++] = e->cfg.rack_slot[t][k];
+  const uint32_t dest = new_position < m ? new_position : m;
+  for (uint32_t k = 0, j = 0; k < n; k++) e->cfg.rack_slot[t][k] = (k == dest) ? moved : tmp[j++];
+  gh::sync_cfg(e);
+  return true;
+}
+uint32_t gooey_engine_track_effect_count(const GooeyEngine* e, uint32_t t) { return (e && t < e->cfg.n_tracks) ? e->cfg.rack_n[t] : 0; }
 void gooey_engine_track_effect_set_param(GooeyEngine* e, uint32_t t, uint32_t pos, uint32_t p, float v) {
   if (!e || t >= e->cfg.n_tracks || pos >= e->cfg.rack_n[t] || p >= 256) return;
   e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_SET, ((uint32_t)e->cfg.rack_slot[t][pos] << 8) | p, v));
@@ -236,6 +327,20 @@ void gooey_engine_poly_trigger_notes(GooeyEngine* e, const uint8_t* notes, uint3
   const float v = gd::clampf(velocity, 0.0f, 1.0f);
   e->poly.pending.push_back(gh::make_event(0, gd::EV_POLY_RELEASE, 0, 0.0f));
   for (uint32_t i = 0; i < n; i++) e->poly.pending.push_back(gh::make_event(0, gd::EV_POLY_NOTE, notes[i], v));
+}
+
+// ffi.rs:5571-5611: diatonic seventh chord of (root, scale) at `degree`, voiced, on the poly synth
+void gooey_engine_poly_trigger_chord(GooeyEngine* e, uint32_t root, uint32_t scale_type, uint32_t degree, uint32_t voicing, uint32_t preset,
+                                     int32_t octave, float velocity) {
+  if (!e) return;
+  const std::vector<uint8_t> notes = gh::chord_notes(root, scale_type, degree, voicing, octave);
+  gooey_engine_poly_trigger_notes(e, notes.data(), (uint32_t)notes.size(), preset, velocity);
+}
+// host-only view of the table above (tests, hosts that want to display the notes)
+uint32_t gooey_b200_chord_notes(uint32_t root, uint32_t scale_type, uint32_t degree, uint32_t voicing, int32_t octave, uint8_t* out_notes, uint32_t capacity) {
+  const std::vector<uint8_t> notes = gh::chord_notes(root, scale_type, degree, voicing, octave);
+  for (uint32_t i = 0; i < notes.size() && i < capacity; i++) if (out_notes) out_notes[i] = notes[i];
+  return (uint32_t)notes.size();
 }
 
 // ---- granulator (ffi.rs:5969-5990, 7702-7827; granulator.rs) ----
@@ -320,11 +425,13 @@ static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t f
   try {
     gh::EngineBank& B = *E[0]->bank;
     gh::use_device(B.device);
+    // The bank's output / voice buffers, streams and events are shared by every engine of (device, sample rate): the lock
+    // is held from the allocation to the end of the drain, so concurrent renders of different engines serialise here.
+    std::lock_guard<std::recursive_mutex> lk(B.mu);
     float* dst = out_dev;
     const size_t row = mode == gh::OUT_MONO ? (size_t)frames : (size_t)2 * frames;
     if (!dst) {
       stride = (row + 3) & ~(size_t)3;
-      std::lock_guard<std::mutex> lk(B.mu);
       B.d_out.alloc((size_t)n * stride);
       dst = B.d_out.p;
     }
@@ -334,6 +441,9 @@ static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t f
     GH_CUDA(cudaStreamSynchronize(B.stream));
     GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, B.ev0, B.ev1));
     return GOOEY_E_OK;
+  } catch (const gh::BadBatch& ex) {
+    gh::set_error(ex.what());
+    return GOOEY_E_INVALID;
   } catch (const std::exception& ex) {
     gh::set_error(ex.what());
     for (auto* e : E) gh::engine_fail(e, ex.what());
@@ -376,11 +486,19 @@ int gooey_batch_bounce(GooeyEngine* const* engines, uint32_t n, uint32_t bars, f
     std::vector<float*> bufs(cnt, nullptr);
     for (size_t j = 0; j < cnt; j++) {
       bufs[j] = (float*)malloc(std::max<size_t>((size_t)frames, 1) * sizeof(float));
-      if (!bufs[j]) { for (float* q : bufs) free(q); gh::set_error("out of host memory"); return GOOEY_E_INVALID; }
+      if (!bufs[j]) {
+        for (float* q : bufs) free(q);
+        for (uint32_t i = 0; i < n; i++) { free(out_buffers[i]); out_buffers[i] = nullptr; out_lengths[i] = 0; }
+        gh::set_error("out of host memory"); return GOOEY_E_INVALID;
+      }
     }
     if (frames > 0) {
       int rc = batch_render_impl(E.data(), (uint32_t)cnt, frames, gh::OUT_MONO, true, nullptr, 0, nullptr, 0, bufs.data());
-      if (rc != GOOEY_E_OK) { for (float* q : bufs) free(q); return rc; }
+      if (rc != GOOEY_E_OK) {
+        for (float* q : bufs) free(q);
+        for (uint32_t i = 0; i < n; i++) { free(out_buffers[i]); out_buffers[i] = nullptr; out_lengths[i] = 0; }   // earlier groups
+        return rc;
+      }
     }
     for (size_t j = 0; j < cnt; j++) { out_buffers[g.second[j]] = bufs[j]; out_lengths[g.second[j]] = frames; }
   }

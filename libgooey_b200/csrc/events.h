@@ -23,9 +23,10 @@ enum : uint32_t {
   MX_SET = 32,        // param = MixParam index, value = target (SmoothedParam::set_target on a strip/track/master)
   MX_SNAP = 33,       // param = 0 voice strips, 1 graph strips, 2 master gain
   MX_FX_SET = 34,     // param = (fx slot << 8) | effect param id, value = raw FFI value
-  MX_FX_INIT = 35,    // param = fx slot, aux = kind : construct the effect's dynamic state
+  MX_FX_INIT = 35,    // param = fx slot, aux = kind | rack << 8, value = bpm : construct the effect's dynamic state
   MX_TRACK_INIT = 36, // param = track index
   MX_FX_BPM = 37,     // param = fx slot, value = bpm
+  MX_FX_RESET = 38,   // reset_effect_states (ffi.rs:1417-1425): every global reorderable effect except the waveshapers
 };
 enum : uint32_t {
   AUX_OVERSAMPLING = 1,        // 0 / 2 / 4

@@ -144,6 +144,7 @@ struct GooeyVoiceBatch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint32_t n = 0;
   uint32_t k = 0;                        // engine clock index of the next frame (shared by every voice of the batch)
+  gh::ClockWindow clock;
   std::vector<uint8_t> vtype;
   std::vector<uint32_t> vslot;
   std::vector<std::vector<gd::VoiceEvent>> pending;   // per voice, frames relative to the next render
@@ -163,7 +164,7 @@ static void voice_batch_render_impl(GooeyVoiceBatch* b, uint32_t frames, float* 
   use_device(b->device);
   cudaStream_t st = b->stream;
   if ((uint64_t)b->k + frames >= 0xffffffffull) throw std::runtime_error("engine clock index overflow");
-  const double* tt = clock_table(b->sr).ensure(b->device, (size_t)b->k + frames + 1, st);
+  const double* tt = b->clock.view(clock_table(b->sr), b->k, (uint64_t)b->k + frames, st);
   b->bank.reset();
   std::vector<gd::VoiceEvent> now, later;
   for (uint32_t v = 0; v < b->n; v++) {

@@ -13,10 +13,12 @@
 namespace gd {
 
 constexpr int MAX_TRACKS = 8;
-constexpr int MAX_FX = 8;        // slots 0..3 = global tilt/delay/spring/plate, 4..7 = track-rack effects
+constexpr int MAX_FX = 12;       // slots 0..3 = global tilt/delay/spring/plate, 4..11 = track-rack effects and the other global effects (on first use)
 constexpr int N_VOICE_CH = 5;
-enum { FXK_NONE = 0xff, FXK_DELAY = 1, FXK_TILT = 4, FXK_LIMITER = 5, FXK_SPRING = 6, FXK_PLATE = 9 };  // = FFI effect ids
+enum { FXK_NONE = 0xff, FXK_LOWPASS = 0, FXK_DELAY = 1, FXK_SATURATION = 2, FXK_COMPRESSOR = 3, FXK_TILT = 4, FXK_LIMITER = 5, FXK_SPRING = 6,
+       FXK_WAVESHAPER = 7, FXK_FBWS = 8, FXK_PLATE = 9 };  // = FFI effect ids (ffi.rs:1548-1575)
 enum { FXS_TILT = 0, FXS_DELAY = 1, FXS_SPRING = 2, FXS_PLATE = 3, FXS_RACK0 = 4 };
+constexpr uint32_t OS_WORDS = 64;   // half-band history of one Oversampler (4 stages x 8 sections x {x, y}), kept in the slot's ring arena
 
 struct Sm { float c, t; };
 G_HD void sm_set(Sm& s, float v, float lo, float hi) { float c = clampf(v, lo, hi); if (fabsf(s.t - c) > 1e-8f) s.t = c; }
@@ -34,7 +36,15 @@ struct PlateDyn {
   float t_decay, t_mix, t_damping, t_predelay, t_width, t_size;
   float memo_sz, memo_size;
 };
-union FxDyn { TiltDyn tilt; DelayDyn delay; SpringDyn spring; PlateDyn plate; uint32_t w[40]; };
+// effects/lowpass_filter.rs, saturation.rs, compressor.rs; waveshaper.rs / feedback_waveshaper.rs as effect slots.  Index 0 = left / mono,
+// 1 = right.  The global waveshapers are ONE instance fed L then R (ffi.rs:1344-1355): `shared` = 1 and only index 0 is used.
+struct LpDyn { Sm cutoff[2], res[2]; float stage1[2], stage2[2]; float cutoff_target, res_target; float memo_c[2], memo_g[2]; };
+struct SatDyn { Sm drive[2], warmth[2], mix[2]; float dc_x1[2], dc_y1[2]; float t_drive, t_warmth, t_mix; };
+struct CompDyn { Sm th[2], ratio[2], att[2], rel[2], mix[2]; float env[2], gain[2], dc_x1[2], dc_y1[2]; float t_th, t_ratio, t_att, t_rel, t_mix; };
+struct WsDyn { float drive[2], mix[2]; uint32_t shared; };
+struct FbSmall { float drive, mix, feedback, cutoff, filter_coeff, env_att, env_rel, last_out, filter_state, dc_x1, dc_y1, env, memo_drive, memo_fb, memo_makeup; };
+struct FbwsDyn { FbSmall s[2]; uint32_t shared; };
+union FxDyn { TiltDyn tilt; DelayDyn delay; SpringDyn spring; PlateDyn plate; LpDyn lp; SatDyn sat; CompDyn comp; WsDyn ws; FbwsDyn fbws; uint32_t w[40]; };
 static_assert(sizeof(FxDyn) == 160, "FxDyn must stay 40 words");
 
 struct MixState {
@@ -51,8 +61,11 @@ struct MixCfg {
   uint32_t n_tracks;
   int32_t route[7];                 // source -> track (-1 none): drumkit, bass, poly, granulator, loop mixer
   uint32_t order[9];                // effect_order (ffi.rs:1583-1593)
+  uint8_t gslot[12];                // global effect id -> slot (0xff = never touched: the effect is still in its constructor state and disabled)
+  uint32_t comp_sidechain;          // compressor_sidechain (ffi.rs:3252-3265): instrument 0-4 or 0xFFFFFFFF
   uint32_t fx_kind[MAX_FX];         // FXK_* (FXK_NONE = slot unused)
   uint32_t fx_enabled[MAX_FX];      // global slots: *_enabled flags; rack slots: 1
+  uint32_t fx_rack;                 // bit s: slot s belongs to a track rack (not touched by reset_effect_states)
   uint32_t rack_n[MAX_TRACKS];
   uint8_t rack_slot[MAX_TRACKS][4];
   uint32_t limiter_on;
@@ -139,10 +152,42 @@ G_HD void plate_init(PlateDyn& d, float decay, float mix, float damping) {  // P
   d.t_decay = decay; d.t_mix = mix; d.t_damping = damping; d.t_predelay = 0.0f; d.t_width = 1.0f; d.t_size = 0.5f;
   d.memo_sz = -1.0f; d.memo_size = 0.0f;
 }
-// effect_chain.rs:57-109 defaults for rack effects vs ffi.rs:869-884 defaults for the global instances
+G_HD void lp_init(LpDyn& d, float cutoff, float res) {  // LowpassFilterEffect::new (lowpass_filter.rs:55-81)
+  cutoff = clampf(cutoff, 20.0f, 20000.0f); res = clampf(res, 0.0f, 0.95f);
+  for (int c = 0; c < 2; c++) { d.cutoff[c] = {cutoff, cutoff}; d.res[c] = {res, res}; d.stage1[c] = d.stage2[c] = 0.0f; d.memo_c[c] = -1.0f; d.memo_g[c] = 0.0f; }
+  d.cutoff_target = cutoff; d.res_target = res;
+}
+G_HD void sat_init(SatDyn& d, float drive, float warmth, float mix) {  // TubeSaturation::new (saturation.rs:68-91)
+  drive = clampf(drive, 0.0f, 1.0f); warmth = clampf(warmth, 0.0f, 1.0f); mix = clampf(mix, 0.0f, 1.0f);
+  for (int c = 0; c < 2; c++) { d.drive[c] = {drive, drive}; d.warmth[c] = {warmth, warmth}; d.mix[c] = {mix, mix}; d.dc_x1[c] = d.dc_y1[c] = 0.0f; }
+  d.t_drive = drive; d.t_warmth = warmth; d.t_mix = mix;
+}
+G_HD void comp_init(CompDyn& d, float th, float ratio, float att, float rel, float mix) {  // TubeCompressor::new (compressor.rs:55-96)
+  th = clampf(th, -60.0f, 0.0f); ratio = clampf(ratio, 1.0f, 20.0f); att = clampf(att, 0.1f, 100.0f); rel = clampf(rel, 5.0f, 1000.0f); mix = clampf(mix, 0.0f, 1.0f);
+  for (int c = 0; c < 2; c++) {
+    d.th[c] = {th, th}; d.ratio[c] = {ratio, ratio}; d.att[c] = {att, att}; d.rel[c] = {rel, rel}; d.mix[c] = {mix, mix};
+    d.env[c] = 0.0f; d.gain[c] = 1.0f; d.dc_x1[c] = d.dc_y1[c] = 0.0f;
+  }
+  d.t_th = th; d.t_ratio = ratio; d.t_att = att; d.t_rel = rel; d.t_mix = mix;
+}
+G_HD void fbsmall_init(FbSmall& w, float sr, float drive, float fb, float cutoff, float mix) {  // FeedbackWaveshaper::new; same arithmetic as fbws_init
+  w.drive = clampf(drive, 1.0f, 100.0f); w.mix = clampf(mix, 0.0f, 1.0f); w.feedback = clampf(fb, 0.0f, 0.98f);
+  w.cutoff = clampf(cutoff, 200.0f, 20000.0f);
+  w.filter_coeff = fbws_filter_coeff(w.cutoff, sr);
+  w.env_att = gm::g_expf(-1.0f / (1.0f / 1000.0f * sr));
+  w.env_rel = gm::g_expf(-1.0f / (120.0f / 1000.0f * sr));
+  w.last_out = w.filter_state = w.dc_x1 = w.dc_y1 = w.env = 0.0f;
+  w.memo_drive = -1.0f; w.memo_fb = -1.0f; w.memo_makeup = 1.0f;
+}
+// effect_chain.rs:57-109 defaults for rack effects vs ffi.rs:852-884 defaults for the global instances
 G_HD void fx_construct(FxDyn& f, uint32_t kind, bool rack, float sr, float bpm) {
   for (int i = 0; i < 40; i++) f.w[i] = 0;
   switch (kind) {
+    case FXK_LOWPASS: lp_init(f.lp, 20000.0f, 0.0f); break;
+    case FXK_SATURATION: sat_init(f.sat, 0.3f, 0.4f, 0.5f); break;
+    case FXK_COMPRESSOR: comp_init(f.comp, -12.0f, 4.0f, 5.0f, 100.0f, 0.5f); break;
+    case FXK_WAVESHAPER: for (int c = 0; c < 2; c++) { f.ws.drive[c] = 1.0f; f.ws.mix[c] = 0.0f; } f.ws.shared = rack ? 0u : 1u; break;
+    case FXK_FBWS: for (int c = 0; c < 2; c++) fbsmall_init(f.fbws.s[c], sr, 1.0f, 0.0f, 2000.0f, 0.0f); f.fbws.shared = rack ? 0u : 1u; break;
     case FXK_TILT: tilt_init(f.tilt, sr); break;
     case FXK_DELAY: if (rack) delay_init(f.delay, 2, bpm, 0.3f, 0.3f, 8000.0f); else delay_init(f.delay, 2, bpm, 0.0f, 0.0f, 20000.0f); break;
     case FXK_SPRING: spring_init(f.spring, 0.5f, rack ? 0.3f : 0.0f, 0.5f); break;
@@ -151,8 +196,25 @@ G_HD void fx_construct(FxDyn& f, uint32_t kind, bool rack, float sr, float bpm) 
   }
 }
 // `set_param` of each effect (ffi.rs:2988-3075 == effect_chain.rs:152-232): raw FFI value -> clamped atomic target
-G_HD void fx_set_param(FxDyn& f, uint32_t kind, uint32_t p, float v) {
+G_HD void fx_set_param(FxDyn& f, uint32_t kind, uint32_t p, float v, float sr) {
   switch (kind) {
+    case FXK_LOWPASS: if (p == 0) f.lp.cutoff_target = clampf(v, 20.0f, 20000.0f); else if (p == 1) f.lp.res_target = clampf(v, 0.0f, 0.95f); break;
+    case FXK_SATURATION: v = clampf(v, 0.0f, 1.0f); if (p == 0) f.sat.t_drive = v; else if (p == 1) f.sat.t_warmth = v; else if (p == 2) f.sat.t_mix = v; break;
+    case FXK_COMPRESSOR:
+      switch (p) { case 0: f.comp.t_th = clampf(v, -60.0f, 0.0f); break; case 1: f.comp.t_ratio = clampf(v, 1.0f, 20.0f); break; case 2: f.comp.t_att = clampf(v, 0.1f, 100.0f); break;
+        case 3: f.comp.t_rel = clampf(v, 5.0f, 1000.0f); break; case 4: f.comp.t_mix = clampf(v, 0.0f, 1.0f); break; }
+      break;
+    case FXK_WAVESHAPER:   // Waveshaper::set_drive / set_mix act immediately (waveshaper.rs:29-46); rack: both channel instances
+      for (int c = 0; c < 2; c++) { if (p == 0) f.ws.drive[c] = clampf(v, 1.0f, 10.0f); else if (p == 1) f.ws.mix[c] = clampf(v, 0.0f, 1.0f); }
+      break;
+    case FXK_FBWS:         // feedback_waveshaper.rs:171-200
+      for (int c = 0; c < 2; c++) {
+        FbSmall& w = f.fbws.s[c];
+        if (p == 0) w.drive = clampf(v, 1.0f, 100.0f); else if (p == 1) w.feedback = clampf(v, 0.0f, 0.98f);
+        else if (p == 2) { w.cutoff = clampf(v, 200.0f, 20000.0f); w.filter_coeff = fbws_filter_coeff(w.cutoff, sr); }
+        else if (p == 3) w.mix = clampf(v, 0.0f, 1.0f);
+      }
+      break;
     case FXK_TILT: if (p == 0) f.tilt.cutoff_target = clampf(v, 0.0f, 1.0f); else if (p == 1) f.tilt.res_target = clampf(v, 0.0f, 1.0f); break;
     case FXK_DELAY:
       switch (p) {
@@ -374,8 +436,168 @@ __device__ __forceinline__ void plate_stereo(PlateDyn& d, const RingRef& r, cons
   l = isfinite(ol) ? ol : li; rr = isfinite(orr) ? orr : ri;
 }
 
-__device__ __forceinline__ void fx_process(FxDyn& f, uint32_t kind, const RingRef& r, const FxGeom& g, float& l, float& rr, const RateCtx& rc) {
+// ---- effects whose oversampler history lives in the slot's ring arena (OS_WORDS floats per instance at `base`) ----
+__device__ __forceinline__ void os_ring_load(Oversamp& o, const RingRef& r, uint32_t base) {
+  float* w = reinterpret_cast<float*>(&o);
+#pragma unroll 8
+  for (uint32_t i = 0; i < OS_WORDS; i++) w[i] = r.at(base + i);
+  o.mode = 4;                             // no FFI call changes the mode of an effect-slot oversampler: always X4
+}
+__device__ __forceinline__ void os_ring_store(const Oversamp& o, const RingRef& r, uint32_t base) {
+  const float* w = reinterpret_cast<const float*>(&o);
+#pragma unroll 8
+  for (uint32_t i = 0; i < OS_WORDS; i++) r.at(base + i) = w[i];
+}
+__device__ __forceinline__ void os_ring_clear(const RingRef& r, uint32_t base) { for (uint32_t i = 0; i < OS_WORDS; i++) r.at(base + i) = 0.0f; }
+static_assert(sizeof(Hb8) * 4 == OS_WORDS * 4 && offsetof(Oversamp, mode) == OS_WORDS * 4, "Oversamp = 64 history words + mode");
+
+__device__ __forceinline__ float lowpass_one(LpDyn& d, int c, float in, const RateCtx& rc) {  // lowpass_filter.rs:129-194
+  sm_set(d.cutoff[c], d.cutoff_target, 20.0f, 20000.0f);
+  sm_set(d.res[c], d.res_target, 0.0f, 0.95f);
+  const float cutoff = sm_tick(d.cutoff[c], rc.smooth30), resonance = sm_tick(d.res[c], rc.smooth30);
+  const float max_cutoff = rc.sr * 0.40f;
+  const float safe_cutoff = fminf(cutoff, max_cutoff);
+  if (safe_cutoff != d.memo_c[c]) {           // g is a pure function of the smoothed cutoff: one expf per change, not per sample
+    d.memo_c[c] = safe_cutoff;
+    const float nf = safe_cutoff / rc.sr;
+    d.memo_g[c] = clampf(1.0f - gm::g_expf(-2.0f * PI_F * nf), 0.0f, 0.90f);
+  }
+  const float g = d.memo_g[c];
+  const float freq_ratio = fminf(safe_cutoff / 5000.0f, 1.0f);
+  const float resonance_scale = 1.0f - (freq_ratio * freq_ratio * 0.7f);
+  const float feedback = (resonance * resonance_scale) * 3.5f;
+  const float fbs = d.stage2[c] * feedback;
+  const float iwf = in - gm::g_tanhf(fbs) * fminf(feedback, 1.0f);
+  d.stage1[c] += g * (iwf - d.stage1[c]);
+  d.stage2[c] += g * (d.stage1[c] - d.stage2[c]);
+  const float out = gm::g_tanhf(d.stage2[c]);
+  if (fabsf(d.stage1[c]) < 1e-15f) d.stage1[c] = 0.0f;
+  if (fabsf(d.stage2[c]) < 1e-15f) d.stage2[c] = 0.0f;
+  if (!isfinite(out)) { d.stage1[c] = d.stage2[c] = 0.0f; return 0.0f; }
+  return out;
+}
+__device__ __forceinline__ float dc_block(float in, float& x1, float& y1) {  // saturation.rs:135-146 == compressor.rs:120-130
+  const float out = in - x1 + 0.995f * y1;
+  x1 = in;
+  y1 = fabsf(out) < 1e-15f ? 0.0f : out;
+  return out;
+}
+constexpr float FRAC_2_PI_F = 0.63661977236758134308f;
+// atanf: CUDA's (1 ulp) instead of a glibc port — it feeds half-band decimators, a DC blocker and a dry/wet mix only
+// (bounded gain, no recurrence), like the tanh of the scan back ends (DESIGN.md "where approximation is allowed").
+__device__ __forceinline__ float sat_shape(float in, float drive, float bias) {  // saturation.rs:104-123
+  const float driven = in * drive;
+  const float biased = driven + bias * fabsf(driven);
+  const float soft = atanf(biased) * FRAC_2_PI_F;
+  const float second = (soft * soft) * copysignf(1.0f, soft) * 0.15f;
+  return soft + second * bias;
+}
+__device__ __forceinline__ float sat_one(SatDyn& d, int c, const RingRef& r, float in, const RateCtx& rc) {  // saturation.rs:202-255
+  const uint32_t base = (uint32_t)c * OS_WORDS;
+  if (!isfinite(in)) { d.dc_x1[c] = d.dc_y1[c] = 0.0f; os_ring_clear(r, base); return 0.0f; }
+  sm_set(d.drive[c], d.t_drive, 0.0f, 1.0f); sm_set(d.warmth[c], d.t_warmth, 0.0f, 1.0f); sm_set(d.mix[c], d.t_mix, 0.0f, 1.0f);
+  const float drive = 1.0f + sm_tick(d.drive[c], rc.smooth30) * 7.0f;
+  const float warmth = sm_tick(d.warmth[c], rc.smooth30) * 0.4f;
+  const float mix = sm_tick(d.mix[c], rc.smooth30);
+  if (mix < 0.0001f) return in;
+  Oversamp os;
+  os_ring_load(os, r, base);
+  const float sat = os_process(os, in, [&](float x) { return sat_shape(x, drive, warmth); });
+  const float dcb = dc_block(sat, d.dc_x1[c], d.dc_y1[c]);
+  const float out = in * (1.0f - mix) + dcb * mix;
+  if (!isfinite(out)) { d.dc_x1[c] = d.dc_y1[c] = 0.0f; os_ring_clear(r, base); return 0.0f; }
+  os_ring_store(os, r, base);
+  return out;
+}
+__device__ __forceinline__ float comp_gr_db(float over_db, float ratio) {  // compressor.rs:103-117, 6 dB soft knee
+  const float slope = 1.0f - 1.0f / ratio;
+  if (over_db <= -3.0f) return 0.0f;
+  if (over_db >= 3.0f) return over_db * slope;
+  const float x = over_db + 3.0f;
+  return x * x / (2.0f * 6.0f) * slope;
+}
+__device__ __forceinline__ float comp_one(CompDyn& d, int c, const RingRef& r, float in, float sidechain, const RateCtx& rc) {  // compressor.rs:133-250
+  if (!isfinite(in) || !isfinite(sidechain)) return 0.0f;
+  sm_set(d.th[c], d.t_th, -60.0f, 0.0f); sm_set(d.ratio[c], d.t_ratio, 1.0f, 20.0f); sm_set(d.att[c], d.t_att, 0.1f, 100.0f);
+  sm_set(d.rel[c], d.t_rel, 5.0f, 1000.0f); sm_set(d.mix[c], d.t_mix, 0.0f, 1.0f);
+  const float threshold_db = sm_tick(d.th[c], rc.smooth30), ratio = sm_tick(d.ratio[c], rc.smooth30), attack_ms = sm_tick(d.att[c], rc.smooth30);
+  const float release_ms = sm_tick(d.rel[c], rc.smooth30), mix = sm_tick(d.mix[c], rc.smooth30);
+  if (mix < 0.0001f) return in;
+  const float sc = fabsf(sidechain);
+  const float tms = sc > d.env[c] ? attack_ms : release_ms;
+  const float coeff = gm::g_expf(-1.0f / (tms * 0.001f * rc.sr));
+  d.env[c] = coeff * d.env[c] + (1.0f - coeff) * sc;
+  if (d.env[c] < 1e-15f) d.env[c] = 0.0f;
+  const float env_db = 20.0f * log10f(d.env[c] + 1e-20f);          // CUDA log10f (2 ulp): a level in dB that becomes a smoothed gain
+  const float gr = comp_gr_db(env_db - threshold_db, ratio);
+  const float gain_linear = gm::g_powf(10.0f, -gr * 0.05f);
+  d.gain[c] += 0.05f * (gain_linear - d.gain[c]);
+  const float compressed = in * d.gain[c];
+  const uint32_t base = (uint32_t)c * OS_WORDS;
+  Oversamp os;
+  os_ring_load(os, r, base);
+  const float colored_os = os_process(os, compressed, [](float x) { return atanf(x) * FRAC_2_PI_F * 1.1f; });
+  os_ring_store(os, r, base);
+  const float colored = d.gain[c] < 0.99f ? colored_os : compressed;
+  const float dcb = dc_block(colored, d.dc_x1[c], d.dc_y1[c]);
+  const float out = in * (1.0f - mix) + dcb * mix;
+  if (!isfinite(out)) { d.dc_x1[c] = d.dc_y1[c] = 0.0f; d.env[c] = 0.0f; d.gain[c] = 1.0f; return 0.0f; }
+  return out;
+}
+__device__ __forceinline__ float wsfx_one(WsDyn& d, int c, const RingRef& r, float in) {  // waveshaper.rs:48-72 on instance c
+  if (isfinite(in) && (d.mix[c] <= 0.0001f || d.drive[c] <= 1.0f)) return in;   // bypass leaves the half-band history untouched
+  const uint32_t base = (uint32_t)c * OS_WORDS;
+  Oversamp os;
+  os_ring_load(os, r, base);
+  const float y = ws_core(d.drive[c], d.mix[c], os, in);
+  os_ring_store(os, r, base);
+  return y;
+}
+__device__ __forceinline__ float fbwsfx_one(FbwsDyn& d, int c, const RingRef& r, float in) {  // feedback_waveshaper.rs:109-169 on instance c
+  FbSmall& w = d.s[c];
+  if (isfinite(in) && (w.mix <= 0.0001f || w.drive <= 1.0f)) return in;
+  const uint32_t base = (uint32_t)c * OS_WORDS;
+  Oversamp os;
+  os_ring_load(os, r, base);
+  const float y = fbws_core(w, os, in);
+  os_ring_store(os, r, base);
+  return y;
+}
+// `reset()` of each reorderable effect, as gooey_engine_set_effect_order / move_effect call it (ffi.rs:1417-1425): saturation,
+// low-pass, tilt, delay, compressor, spring, plate.  The two waveshapers are not in that list.
+__device__ __forceinline__ void fx_reset(FxDyn& f, uint32_t kind, const RingRef& r, const FxGeom& g) {
   switch (kind) {
+    case FXK_SATURATION: for (int c = 0; c < 2; c++) { f.sat.dc_x1[c] = f.sat.dc_y1[c] = 0.0f; os_ring_clear(r, c * OS_WORDS); } break;
+    case FXK_LOWPASS: for (int c = 0; c < 2; c++) f.lp.stage1[c] = f.lp.stage2[c] = 0.0f; break;
+    case FXK_TILT: for (int c = 0; c < 2; c++) f.tilt.svf[c].ic1 = f.tilt.svf[c].ic2 = 0.0f; break;
+    case FXK_DELAY:
+      for (uint32_t j = 0; j < 2u * g.delay_len; j++) r.at(j) = 0.0f;
+      for (int c = 0; c < 2; c++) { f.delay.ch[c].write_index = 0; f.delay.ch[c].z1 = f.delay.ch[c].z2 = 0.0f; }
+      break;
+    case FXK_COMPRESSOR: for (int c = 0; c < 2; c++) { f.comp.env[c] = 0.0f; f.comp.gain[c] = 1.0f; f.comp.dc_x1[c] = f.comp.dc_y1[c] = 0.0f; os_ring_clear(r, c * OS_WORDS); } break;
+    case FXK_SPRING:
+      for (uint32_t j = 0; j < g.ring_words[2]; j++) r.at(j) = 0.0f;
+      for (int c = 0; c < 2; c++) { for (int i = 0; i < 6; i++) f.spring.ch[c].idx[i] = 0; f.spring.ch[c].fb = f.spring.ch[c].damp = 0.0f; }
+      break;
+    case FXK_PLATE:
+      for (uint32_t j = 0; j < g.ring_words[3]; j++) r.at(j) = 0.0f;
+      for (int i = 0; i < 13; i++) f.plate.idx[i] = 0;
+      f.plate.bandwidth = f.plate.damp_a = f.plate.damp_b = f.plate.fb_a = f.plate.fb_b = f.plate.lfo_pa = f.plate.lfo_pb = 0.0f;
+      break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ void fx_process(FxDyn& f, uint32_t kind, const RingRef& r, const FxGeom& g, float& l, float& rr, const RateCtx& rc, float sidechain = 0.0f, bool has_sidechain = false) {
+  switch (kind) {
+    case FXK_LOWPASS: l = lowpass_one(f.lp, 0, l, rc); rr = lowpass_one(f.lp, 1, rr, rc); break;
+    case FXK_SATURATION: l = sat_one(f.sat, 0, r, l, rc); rr = sat_one(f.sat, 1, r, rr, rc); break;
+    case FXK_COMPRESSOR: {
+      const float sl = has_sidechain ? sidechain : l, sr_ = has_sidechain ? sidechain : rr;
+      l = comp_one(f.comp, 0, r, l, sl, rc); rr = comp_one(f.comp, 1, r, rr, sr_, rc);
+    } break;
+    case FXK_WAVESHAPER: l = wsfx_one(f.ws, 0, r, l); rr = wsfx_one(f.ws, f.ws.shared ? 0 : 1, r, rr); break;
+    case FXK_FBWS: l = fbwsfx_one(f.fbws, 0, r, l); rr = fbwsfx_one(f.fbws, f.fbws.shared ? 0 : 1, r, rr); break;
     case FXK_TILT: l = tilt_one(f.tilt, 0, l, rc); rr = tilt_one(f.tilt, 1, rr, rc); break;
     case FXK_DELAY: delay_stereo(f.delay, r, g.delay_len, l, rr, rc); break;
     case FXK_SPRING: {
@@ -408,8 +630,8 @@ __device__ __forceinline__ void mix_event(MixState& s, const MixCfg& cfg, const 
       else if (e.param == 1) { for (int i = 0; i < MAX_TRACKS; i++) { s.tr_gain[i].c = s.tr_gain[i].t; s.tr_pan[i].c = s.tr_pan[i].t; s.tr_mute[i].c = s.tr_mute[i].t; } }
       else s.master.c = s.master.t;
       break;
-    case MX_FX_SET: { uint32_t slot = e.param >> 8; if (slot < MAX_FX) fx_set_param(s.fx[slot], cfg.fx_kind[slot], e.param & 0xff, e.value); } break;
-    case MX_FX_INIT: if (e.param < MAX_FX) fx_construct(s.fx[e.param], e.aux & 0xff, e.param >= FXS_RACK0, rc.sr, e.value); break;
+    case MX_FX_SET: { uint32_t slot = e.param >> 8; if (slot < MAX_FX) fx_set_param(s.fx[slot], cfg.fx_kind[slot], e.param & 0xff, e.value, rc.sr); } break;
+    case MX_FX_INIT: if (e.param < MAX_FX) fx_construct(s.fx[e.param], e.aux & 0xff, (e.aux >> 8) & 1u, rc.sr, e.value); break;   // aux bit 8: rack variant
     case MX_FX_BPM: if (e.param < MAX_FX && cfg.fx_kind[e.param] == FXK_DELAY) s.fx[e.param].delay.bpm_target = e.value; break;
     case MX_TRACK_INIT: if (e.param < MAX_TRACKS) { s.tr_gain[e.param] = {1.0f, 1.0f}; s.tr_pan[e.param] = {0.5f, 0.5f}; s.tr_mute[e.param] = {1.0f, 1.0f}; } break;
     default: break;
@@ -458,11 +680,28 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
     if (valid) {
       for (int j = 0; j < nf; j++) {
         const uint32_t frame = f0 + j;
-        while (ev < ev_end && L.events[ev].frame <= frame) { mix_event(st, cfg, L.events[ev], rc); ev++; }
+        while (ev < ev_end && L.events[ev].frame <= frame) {
+          const VoiceEvent& e = L.events[ev];
+          if (e.kind == MX_FX_RESET) {   // reset_effect_states (ffi.rs:1417-1425): needs the ring arenas
+            for (int s = 0; s < MAX_FX; s++) if (cfg.fx_kind[s] != FXK_NONE && !((cfg.fx_rack >> s) & 1u)) fx_reset(st.fx[s], cfg.fx_kind[s], RingRef{L.ring[s], L.ring_cap, es}, L.geo);
+          } else {
+            mix_event(st, cfg, e, rc);
+            if (e.kind == MX_FX_INIT && e.param < MAX_FX && L.ring[e.param]) {   // a (re)built effect starts from silent delay lines
+              const RingRef r{L.ring[e.param], L.ring_cap, es};
+              const uint32_t k = e.aux & 0xff;
+              const uint32_t words = k == FXK_DELAY ? L.geo.ring_words[1] : k == FXK_SPRING ? L.geo.ring_words[2] : k == FXK_PLATE ? L.geo.ring_words[3]
+                                   : (k == FXK_SATURATION || k == FXK_COMPRESSOR || k == FXK_WAVESHAPER || k == FXK_FBWS) ? 2u * OS_WORDS : 0u;
+              for (uint32_t j = 0; j < words; j++) r.at(j) = 0.0f;
+            }
+          }
+          ev++;
+        }
         float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
+        float channel_outs[N_VOICE_CH];
 #pragma unroll
         for (int c = 0; c < N_VOICE_CH; c++) {  // ffi.rs:1268-1283
           float x = tin[c][lane * 33 + j] * sm_tick(st.ch_gain[c], rc.smooth10) * sm_tick(st.ch_mute[c], rc.smooth10);
+          channel_outs[c] = x;
           float pan = sm_tick(st.ch_pan[c], rc.smooth10);
           if (pan != pan_v[c]) { float ang = clampf(pan, 0.0f, 1.0f) * 1.57079632679489661923f; pan_v[c] = pan; pan_cos[c] = gm::g_cosf(ang); pan_sin[c] = gm::g_sinf(ang); }
           float pl = x * pan_cos[c], pr = x * pan_sin[c];
@@ -492,8 +731,15 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
 #pragma unroll 1
         for (int o = 0; o < 9; o++) {  // ffi.rs:1317-1364
           const uint32_t id = cfg.order[o];
-          int slot = id == FXK_TILT ? FXS_TILT : id == FXK_DELAY ? FXS_DELAY : id == FXK_SPRING ? FXS_SPRING : id == FXK_PLATE ? FXS_PLATE : -1;
-          if (slot >= 0 && cfg.fx_enabled[slot]) fx_process(st.fx[slot], id, RingRef{L.ring[slot], L.ring_cap, es}, L.geo, ml, mr, rc);
+          const uint32_t slot = id < 12u ? cfg.gslot[id] : 0xffu;
+          if (slot >= (uint32_t)MAX_FX || !cfg.fx_enabled[slot]) continue;
+          float sc = 0.0f; bool has_sc = false;
+          if (id == FXK_COMPRESSOR && cfg.comp_sidechain < (uint32_t)N_VOICE_CH) {   // ffi.rs:1331-1343
+            has_sc = true;
+#pragma unroll
+            for (int c = 0; c < N_VOICE_CH; c++) if ((uint32_t)c == cfg.comp_sidechain) sc = channel_outs[c];
+          }
+          fx_process(st.fx[slot], id, RingRef{L.ring[slot], L.ring_cap, es}, L.geo, ml, mr, rc, sc, has_sc);
         }
         if (cfg.limiter_on) { ml = gm::g_tanhf(ml * cfg.lim_inv) * cfg.lim_th; mr = gm::g_tanhf(mr * cfg.lim_inv) * cfg.lim_th; }
         if (L.out_mode == 0) tout[0][lane * 33 + j] = 0.5f * (ml + mr);
@@ -529,9 +775,9 @@ __global__ void __launch_bounds__(128) mix_prepare_kernel(const MixLaunch L) {
   const MixCfg cfg = L.cfg[es];
   const uint32_t ev0 = L.ev_begin[i], ev1 = L.ev_begin[i + 1];
   bool ok = true;
-  for (int s = 0; s < 4; s++) ok = ok && !cfg.fx_enabled[s];
+  for (int s = 0; s < MAX_FX; s++) ok = ok && !(cfg.fx_kind[s] != FXK_NONE && cfg.fx_enabled[s]);
   for (uint32_t t = 0; t < cfg.n_tracks; t++) ok = ok && cfg.rack_n[t] == 0;
-  for (uint32_t e = ev0; e < ev1; e++) ok = ok && L.events[e].frame == 0 && L.events[e].kind != MX_FX_INIT;
+  for (uint32_t e = ev0; e < ev1; e++) ok = ok && L.events[e].frame == 0 && L.events[e].kind != MX_FX_INIT && L.events[e].kind != MX_FX_RESET;
   if (!ok) { L.fast[i] = 0; return; }
   MixState st;
   load_words(st, L.state, es, L.state_cap, 0);

@@ -102,31 +102,44 @@ inline gd::VoiceEvent make_event(uint32_t frame, uint32_t kind, uint32_t param, 
 }
 
 // The engine clock: tt[k] = value of a f64 accumulator after k additions of 1/sr, exactly as the reference's
-// `current_time += 1.0 / sample_rate` (bounce.rs:48-53, ffi.rs:1379).  Built once on the host, mirrored per device.
+// `current_time += 1.0 / sample_rate` (bounce.rs:48-53, ffi.rs:1379).  The host keeps one checkpoint every CK additions
+// (8 bytes per 1.5 s of audio) and rebuilds any window [k0, k0 + n) from the nearest checkpoint by the same repeated
+// addition, so memory does not grow with how long an engine has been streaming.
 struct ClockTable {
+  static constexpr uint64_t CK = 65536;
   double dt = 0.0;
-  std::vector<double> host;
-  std::map<int, std::pair<DevBuf<double>*, size_t>> dev;   // device -> (buffer, valid entries)
+  std::vector<double> ckpt;   // ckpt[i] = value after i * CK additions
   std::mutex mu;
-  const double* ensure(int device, size_t n, cudaStream_t st) {
+  void fill(uint64_t k0, size_t n, double* out) {
     std::lock_guard<std::mutex> lk(mu);
-    if (host.size() < n) {
-      size_t target = std::max(n, host.size() * 2);
-      target = std::max<size_t>(target, 1u << 16);
-      host.reserve(target);
-      if (host.empty()) host.push_back(0.0);
-      while (host.size() < target) host.push_back(host.back() + dt);
+    if (ckpt.empty()) ckpt.push_back(0.0);
+    const uint64_t need = k0 / CK;
+    while (ckpt.size() <= need) { double t = ckpt.back(); for (uint64_t i = 0; i < CK; i++) t += dt; ckpt.push_back(t); }
+    double t = ckpt[need];
+    for (uint64_t k = need * CK; k < k0; k++) t += dt;
+    for (size_t i = 0; i < n; i++) { out[i] = t; t += dt; }
+  }
+};
+// A caller-owned device copy of tt[k0 .. k0 + n): view() returns a pointer `p` such that p[k] is valid for every k of the
+// requested range (kernels index the clock with absolute k).  Uploads are ordered on the caller's stream; a window that
+// already covers the range is reused (a bounce always asks for [0, frames]).
+struct ClockWindow {
+  DevBuf<double> d;
+  std::vector<double> h;
+  uint64_t k0 = 0; size_t n = 0;
+  const double* view(ClockTable& T, uint64_t kmin, uint64_t kmax, cudaStream_t st) {
+    if (kmin > 0) kmin -= 1;                                   // the poly synth's catch-up reads tt[k - 1]
+    if (!(n && kmin >= k0 && kmax < k0 + n)) {
+      const size_t want = (size_t)(kmax - kmin + 1);
+      const size_t cap = std::max<size_t>((want + 8191) & ~(size_t)8191, 1u << 16);
+      if (d.n < cap) { GH_CUDA(cudaStreamSynchronize(st)); d.alloc(cap); }
+      h.resize(want);
+      T.fill(kmin, want, h.data());
+      GH_CUDA(cudaMemcpyAsync(d.p, h.data(), want * sizeof(double), cudaMemcpyHostToDevice, st));
+      GH_CUDA(cudaStreamSynchronize(st));                      // h is reused by the next call
+      k0 = kmin; n = want;
     }
-    auto& d = dev[device];
-    if (!d.first) d.first = new DevBuf<double>();
-    if (d.second < n) {
-      // reallocation invalidates pointers held by in-flight launches of other batches: drain the device first
-      GH_CUDA(cudaDeviceSynchronize());
-      d.first->upload(host.data(), host.size(), st);
-      GH_CUDA(cudaStreamSynchronize(st));
-      d.second = host.size();
-    }
-    return d.first->p;
+    return d.p - k0;
   }
 };
 ClockTable& clock_table(float sr);

@@ -68,6 +68,7 @@ struct GooeyRsBatch {
   };
   std::vector<Eng> engines;
   gh::VoiceBank bank;
+  gh::ClockWindow clock;
   gh::DevBuf<float> d_voices, d_out, d_master, d_lim_th, d_lim_inv;
   gh::DevBuf<uint32_t> d_first, d_nlim;
   ~GooeyRsBatch() {
@@ -83,7 +84,7 @@ static void rs_bounce_impl(GooeyRsBatch* b, uint32_t frames, float* out_dev, siz
   use_device(b->device);
   cudaStream_t st = b->stream;
   const uint32_t ne = (uint32_t)b->engines.size();
-  const double* tt = clock_table(b->sr).ensure(b->device, (size_t)frames + 1, st);
+  const double* tt = b->clock.view(clock_table(b->sr), 0, frames, st);
   b->bank.reset();
   std::vector<uint32_t> first(ne + 1, 0), nlim(ne);
   std::vector<float> master(ne), lth((size_t)ne * gd::RS_MAX_LIM, 1.0f), linv((size_t)ne * gd::RS_MAX_LIM, 1.0f);
@@ -171,7 +172,7 @@ int gooey_rs_batch_add_instrument(GooeyRsBatch* b, uint32_t engine, const char* 
   const int slot = b->bank.create(*patch, b->sr);
   if (slot < 0) { set_error("unsupported instrument id in voice patch"); return GOOEY_E_INVALID; }
   // HashMap::insert semantics: a second instrument under the same name replaces the first (engine/mod.rs:190-192)
-  for (auto& i : E.insts) if (i.name == name) { i.type = patch->instrument; i.slot = (uint32_t)slot; return GOOEY_E_OK; }
+  for (auto& i : E.insts) if (i.name == name) { b->bank.release(i.type, (int)i.slot); i.type = patch->instrument; i.slot = (uint32_t)slot; return GOOEY_E_OK; }
   E.insts.push_back({name, patch->instrument, (uint32_t)slot});
   return GOOEY_E_OK;
   GOOEY_CATCH

@@ -18,7 +18,12 @@ _SIGS = {
     "set_bpm": [c.c_float], "set_swing": [c.c_float], "set_master_gain": [c.c_float],
     "sequencer_set_instrument_step": [c.c_uint32, c.c_uint32, c.c_bool],
     "sequencer_set_instrument_step_settings": [c.c_uint32, c.c_uint32, c.c_bool, c.c_bool, c.c_float, c.c_bool, c.c_float, c.c_float, c.c_bool, c.c_uint8],
+    "sequencer_set_step": [c.c_uint32, c.c_bool],
+    "sequencer_set_instrument_step_with_velocity": [c.c_uint32, c.c_uint32, c.c_bool, c.c_float],
+    "sequencer_set_instrument_step_note": [c.c_uint32, c.c_uint32, c.c_uint8],
     "sequencer_start": [], "sequencer_stop": [], "sequencer_reset": [],
+    "set_channel_instrument_type": [c.c_uint32, c.c_uint32], "set_compressor_sidechain": [c.c_uint32],
+    "trigger_instrument": [c.c_uint32],
     "set_instrument_gain": [c.c_uint32, c.c_float], "set_instrument_pan": [c.c_uint32, c.c_float],
     "set_instrument_mute": [c.c_uint32, c.c_bool], "set_instrument_solo": [c.c_uint32, c.c_bool],
     "trigger_instrument_with_velocity": [c.c_uint32, c.c_float],
@@ -49,6 +54,10 @@ def _bind(L, prefix):
     f = getattr(L, prefix + "mixer_add_track"); f.argtypes = [c.c_void_p, c.c_char_p]; f.restype = c.c_int32
     f = getattr(L, prefix + "mixer_route_source"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_bool
     f = getattr(L, prefix + "track_effect_add"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_int32
+    f = getattr(L, prefix + "track_effect_remove"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_bool
+    f = getattr(L, prefix + "track_effect_move"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_uint32]; f.restype = c.c_bool
+    f = getattr(L, prefix + "move_effect"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_bool
+    f = getattr(L, prefix + "sequencer_set_instrument_pattern"); f.argtypes = [c.c_void_p, c.c_uint32, c.POINTER(c.c_bool)]; f.restype = None
     f = getattr(L, prefix + "poly_trigger_notes"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]; f.restype = None
     f = getattr(L, prefix + "granulator_set_buffer"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32, c.c_float]; f.restype = c.c_bool
     f = getattr(L, prefix + "render"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32]; f.restype = None
@@ -70,7 +79,7 @@ class Engine:
         self.sample_rate = sample_rate
 
     def close(self):
-        if self._h:
+        if getattr(self, "_h", None):
             getattr(self._L, self._prefix + "free")(self._h)
             self._h = None
 
@@ -95,6 +104,25 @@ class Engine:
     def track_effect_add(self, track, effect_id):
         return int(getattr(self._L, self._prefix + "track_effect_add")(self._h, track, effect_id))
 
+    def track_effect_remove(self, track, slot):
+        return bool(getattr(self._L, self._prefix + "track_effect_remove")(self._h, track, slot))
+
+    def track_effect_move(self, track, slot, new_position):
+        return bool(getattr(self._L, self._prefix + "track_effect_move")(self._h, track, slot, new_position))
+
+    def move_effect(self, effect_id, new_position):
+        return bool(getattr(self._L, self._prefix + "move_effect")(self._h, effect_id, new_position))
+
+    def sequencer_set_instrument_pattern(self, instrument, pattern16):
+        arr = (c.c_bool * 16)(*[bool(x) for x in pattern16])
+        getattr(self._L, self._prefix + "sequencer_set_instrument_pattern")(self._h, instrument, arr)
+
+    def poly_trigger_chord(self, root, scale, degree, voicing, preset=0, octave=4, velocity=1.0):
+        """gooey_engine_poly_trigger_chord (product only; the oracle takes the notes: poly_trigger_notes)."""
+        f = self._L.gooey_engine_poly_trigger_chord
+        f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_uint32, c.c_uint32, c.c_uint32, c.c_int32, c.c_float]; f.restype = None
+        f(self._h, root, scale, degree, voicing, preset, octave, c.c_float(velocity))
+
     def poly_trigger_notes(self, notes, preset=0, velocity=1.0):
         """The tail of gooey_engine_poly_trigger_chord once the voicing has produced MIDI notes (ffi.rs:5594-5611)."""
         arr = np.asarray(notes, np.uint8)
@@ -110,6 +138,39 @@ class Engine:
         f = self._L.gooey_b200_granulator_share_buffer
         f.argtypes = [c.c_void_p, c.c_void_p]; f.restype = c.c_bool
         return bool(f(self._h, other._h))
+
+    # ---- product-only entry points (no oracle counterpart) ----
+    def bounce_to_wav(self, bars, path):
+        """gooey_engine_bounce_to_wav: mono 16-bit PCM of the bounce."""
+        f = self._L.gooey_engine_bounce_to_wav
+        f.argtypes = [c.c_void_p, c.c_uint32, c.c_char_p]; f.restype = c.c_bool
+        return bool(f(self._h, bars, str(path).encode()))
+
+    def has_error(self):
+        f = self._L.gooey_engine_has_error
+        f.argtypes = [c.c_void_p]; f.restype = c.c_bool
+        return bool(f(self._h))
+
+    def get_error_message(self):
+        f = self._L.gooey_engine_get_error_message
+        f.argtypes = [c.c_void_p]; f.restype = c.c_char_p
+        m = f(self._h)
+        return m.decode() if m else None
+
+    def set_error_callback(self, fn):
+        """gooey_engine_set_error_callback(engine, context, callback); `fn(message: str)`."""
+        CB = c.CFUNCTYPE(None, c.c_void_p, c.c_char_p)
+        self._cb = CB(lambda ctx, msg: fn(msg.decode() if msg else ""))      # keep the thunk alive
+        f = self._L.gooey_engine_set_error_callback
+        f.argtypes = [c.c_void_p, c.c_void_p, CB]; f.restype = None
+        f(self._h, None, self._cb)
+
+    def get_effect_order(self):
+        out = (c.c_uint32 * 9)()
+        f = self._L.gooey_engine_get_effect_order
+        f.argtypes = [c.c_void_p, c.POINTER(c.c_uint32), c.c_uint32]; f.restype = c.c_uint32
+        n = f(self._h, out, 9)
+        return list(out[:n])
 
     def render(self, frames):
         """gooey_engine_render: (frames, 2) interleaved stereo."""
@@ -141,6 +202,17 @@ def batch_bounce(engines, bars):
     for i in range(n):
         out.append(np.ctypeslib.as_array(bufs[i], shape=(lens[i],)).copy())
         L.gooey_engine_free_buffer(bufs[i], lens[i])
+    return out
+
+
+def batch_render(engines, frames):
+    """gooey_batch_render: every engine rendered `frames` frames in one device pass; (n, frames, 2) interleaved stereo."""
+    L = lib()
+    n = len(engines)
+    hs = (c.c_void_p * n)(*[e._h for e in engines])
+    out = np.zeros((n, frames, 2), np.float32)
+    L.gooey_batch_render.argtypes = [c.POINTER(c.c_void_p), c.c_uint32, c.c_uint32, c.c_void_p]
+    check(L.gooey_batch_render(hs, n, frames, out.ctypes.data))
     return out
 
 

@@ -80,7 +80,7 @@ class VoiceBatch:
         self._h = h
 
     def close(self):
-        if self._h:
+        if getattr(self, "_h", None):       # the constructor may have raised before the handle existed
             lib().gooey_voice_batch_free(self._h)
             self._h = None
 

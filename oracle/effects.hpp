@@ -1,6 +1,7 @@
 // oracle/effects.hpp — TEST INFRASTRUCTURE ONLY.
-// CPU restatement of the effects on the hot path: TiltFilterEffect, DelayEffect,
-// SpringReverbEffect, PlateReverbEffect (effects/{tilt_filter,delay,reverb,plate_reverb}.rs).
+// CPU restatement of the effects on the hot path: TiltFilterEffect, LowpassFilterEffect, TubeSaturation, TubeCompressor,
+// DelayEffect, SpringReverbEffect, PlateReverbEffect (effects/{tilt_filter,lowpass_filter,saturation,compressor,delay,
+// reverb,plate_reverb}.rs) and the per-channel waveshaper pairs of the track racks (mixer/effect_chain.rs).
 #pragma once
 #include "prims.hpp"
 
@@ -41,8 +42,167 @@ struct TiltFilterEffect : StereoEffect {
     if (fabsf(out) < 1e-15f) return 0.0f;
     return out;
   }
+  void reset() { for (auto& s : st) s.svf.reset(); }   // tilt_filter.rs:79-84
   float process(float in) override { return one(st[0], in); }
   StereoFrame process_stereo(StereoFrame in) override { StereoFrame o; o.l = one(st[0], in.l); o.r = one(st[1], in.r); return o; }
+};
+
+// ---- effects/lowpass_filter.rs:129-194 (two-pole "Moog-style" low-pass with tanh feedback) -----------------------------
+struct LowpassFilterEffect : StereoEffect {
+  struct St { SmoothedParam cutoff, res; float stage1 = 0, stage2 = 0; };
+  float sample_rate;
+  St st[2];
+  float cutoff_target, res_target;
+  LowpassFilterEffect(float sr, float cutoff, float res) : sample_rate(sr) {
+    cutoff = clampf(cutoff, 20.0f, 20000.0f); res = clampf(res, 0.0f, 0.95f);
+    for (auto& s : st) { s.cutoff = SmoothedParam(cutoff, 20.0f, 20000.0f, sr, 30.0f); s.res = SmoothedParam(res, 0.0f, 0.95f, sr, 30.0f); }
+    cutoff_target = cutoff; res_target = res;
+  }
+  void set_param(uint32_t p, float v) override { if (p == 0) cutoff_target = clampf(v, 20.0f, 20000.0f); else if (p == 1) res_target = clampf(v, 0.0f, 0.95f); }
+  void reset() { for (auto& s : st) s.stage1 = s.stage2 = 0.0f; }
+  float one(St& s, float in) {
+    s.cutoff.set_target(cutoff_target); s.res.set_target(res_target);
+    float cutoff = s.cutoff.tick(), resonance = s.res.tick();
+    float max_cutoff = sample_rate * 0.40f;
+    float safe_cutoff = rust_min(cutoff, max_cutoff);
+    float nf = safe_cutoff / sample_rate;
+    float g = 1.0f - expf(-2.0f * PI_F * nf);
+    g = clampf(g, 0.0f, 0.90f);
+    float freq_ratio = rust_min(safe_cutoff / 5000.0f, 1.0f);
+    float resonance_scale = 1.0f - (freq_ratio * freq_ratio * 0.7f);
+    float effective = resonance * resonance_scale;
+    float feedback = effective * 3.5f;
+    float fbs = s.stage2 * feedback;
+    float iwf = in - tanhf(fbs) * rust_min(feedback, 1.0f);
+    s.stage1 += g * (iwf - s.stage1);
+    s.stage2 += g * (s.stage1 - s.stage2);
+    float out = tanhf(s.stage2);
+    if (fabsf(s.stage1) < 1e-15f) s.stage1 = 0.0f;
+    if (fabsf(s.stage2) < 1e-15f) s.stage2 = 0.0f;
+    if (!std::isfinite(out)) { s.stage1 = s.stage2 = 0.0f; return 0.0f; }
+    return out;
+  }
+  float process(float in) override { return one(st[0], in); }
+  StereoFrame process_stereo(StereoFrame in) override { StereoFrame o; o.l = one(st[0], in.l); o.r = one(st[1], in.r); return o; }
+};
+
+static const float FRAC_2_PI_F = 0.63661977236758134308f;
+static inline float dc_block(float in, float& x1, float& y1) {  // saturation.rs:135-146, compressor.rs:120-130
+  float out = in - x1 + 0.995f * y1;
+  x1 = in;
+  y1 = fabsf(out) < 1e-15f ? 0.0f : out;
+  return out;
+}
+
+// ---- effects/saturation.rs:202-255 ------------------------------------------------------------------------------------
+struct TubeSaturation : StereoEffect {
+  struct St { SmoothedParam drive, warmth, mix; float dc_x1 = 0, dc_y1 = 0; Oversampler os; };
+  St st[2];
+  float drive_target, warmth_target, mix_target;
+  TubeSaturation(float sr, float drive, float warmth, float mix) {
+    drive = clampf(drive, 0, 1); warmth = clampf(warmth, 0, 1); mix = clampf(mix, 0, 1);
+    for (auto& s : st) { s.drive = SmoothedParam(drive, 0, 1, sr, 30.0f); s.warmth = SmoothedParam(warmth, 0, 1, sr, 30.0f); s.mix = SmoothedParam(mix, 0, 1, sr, 30.0f); }
+    drive_target = drive; warmth_target = warmth; mix_target = mix;
+  }
+  void set_param(uint32_t p, float v) override { v = clampf(v, 0, 1); if (p == 0) drive_target = v; else if (p == 1) warmth_target = v; else if (p == 2) mix_target = v; }
+  void reset() { for (auto& s : st) { s.dc_x1 = s.dc_y1 = 0.0f; s.os.reset(); } }
+  static float saturate(float in, float drive, float bias) {  // :104-123
+    float driven = in * drive;
+    float biased = driven + bias * fabsf(driven);
+    float soft = atanf(biased) * FRAC_2_PI_F;
+    float second = (soft * soft) * copysignf(1.0f, soft) * 0.15f;   // powi(2) * signum()
+    return soft + second * bias;
+  }
+  float one(St& s, float in) {
+    if (!std::isfinite(in)) { s.dc_x1 = s.dc_y1 = 0.0f; s.os.reset(); return 0.0f; }
+    s.os.set_mode(OversamplingMode::X4);
+    s.drive.set_target(drive_target); s.warmth.set_target(warmth_target); s.mix.set_target(mix_target);
+    float drive = 1.0f + s.drive.tick() * 7.0f;
+    float warmth = s.warmth.tick() * 0.4f;
+    float mix = s.mix.tick();
+    if (mix < 0.0001f) return in;
+    float sat = s.os.process(in, [&](float x) { return saturate(x, drive, warmth); });
+    float dcb = dc_block(sat, s.dc_x1, s.dc_y1);
+    float out = in * (1.0f - mix) + dcb * mix;
+    if (!std::isfinite(out)) { s.dc_x1 = s.dc_y1 = 0.0f; s.os.reset(); return 0.0f; }
+    return out;
+  }
+  float process(float in) override { return one(st[0], in); }
+  StereoFrame process_stereo(StereoFrame in) override { StereoFrame o; o.l = one(st[0], in.l); o.r = one(st[1], in.r); return o; }
+};
+
+// ---- effects/compressor.rs:133-250 ------------------------------------------------------------------------------------
+struct TubeCompressor : StereoEffect {
+  struct St { SmoothedParam threshold, ratio, attack, release, mix; float envelope = 0, gain = 1.0f, dc_x1 = 0, dc_y1 = 0; Oversampler os; };
+  float sample_rate;
+  St st[2];
+  float threshold_target, ratio_target, attack_target, release_target, mix_target;
+  TubeCompressor(float sr, float th, float ratio, float att, float rel, float mix) : sample_rate(sr) {
+    th = clampf(th, -60.0f, 0.0f); ratio = clampf(ratio, 1.0f, 20.0f); att = clampf(att, 0.1f, 100.0f); rel = clampf(rel, 5.0f, 1000.0f); mix = clampf(mix, 0, 1);
+    for (auto& s : st) {
+      s.threshold = SmoothedParam(th, -60.0f, 0.0f, sr, 30.0f); s.ratio = SmoothedParam(ratio, 1.0f, 20.0f, sr, 30.0f);
+      s.attack = SmoothedParam(att, 0.1f, 100.0f, sr, 30.0f); s.release = SmoothedParam(rel, 5.0f, 1000.0f, sr, 30.0f); s.mix = SmoothedParam(mix, 0, 1, sr, 30.0f);
+    }
+    threshold_target = th; ratio_target = ratio; attack_target = att; release_target = rel; mix_target = mix;
+  }
+  void set_param(uint32_t p, float v) override {
+    switch (p) { case 0: threshold_target = clampf(v, -60.0f, 0.0f); break; case 1: ratio_target = clampf(v, 1.0f, 20.0f); break;
+      case 2: attack_target = clampf(v, 0.1f, 100.0f); break; case 3: release_target = clampf(v, 5.0f, 1000.0f); break; case 4: mix_target = clampf(v, 0, 1); break; }
+  }
+  void reset() { for (auto& s : st) { s.envelope = 0.0f; s.gain = 1.0f; s.dc_x1 = s.dc_y1 = 0.0f; s.os.reset(); } }
+  static float time_to_coeff(float ms, float sr) { return expf(-1.0f / (ms * 0.001f * sr)); }
+  static float gain_reduction_db(float over_db, float ratio) {  // :103-117
+    float slope = 1.0f - 1.0f / ratio;
+    if (over_db <= -3.0f) return 0.0f;
+    if (over_db >= 3.0f) return over_db * slope;
+    float x = over_db + 3.0f;
+    return x * x / (2.0f * 6.0f) * slope;
+  }
+  float inner(St& s, float in, float sidechain) {
+    if (!std::isfinite(in) || !std::isfinite(sidechain)) return 0.0f;
+    s.threshold.set_target(threshold_target); s.ratio.set_target(ratio_target); s.attack.set_target(attack_target);
+    s.release.set_target(release_target); s.mix.set_target(mix_target);
+    float threshold_db = s.threshold.tick(), ratio = s.ratio.tick(), attack_ms = s.attack.tick(), release_ms = s.release.tick(), mix = s.mix.tick();
+    if (mix < 0.0001f) return in;
+    float sc = fabsf(sidechain);
+    float coeff = sc > s.envelope ? time_to_coeff(attack_ms, sample_rate) : time_to_coeff(release_ms, sample_rate);
+    s.envelope = coeff * s.envelope + (1.0f - coeff) * sc;
+    if (s.envelope < 1e-15f) s.envelope = 0.0f;
+    float env_db = 20.0f * log10f(s.envelope + 1e-20f);
+    float over_db = env_db - threshold_db;
+    float gr = gain_reduction_db(over_db, ratio);
+    float gain_linear = powf(10.0f, -gr * 0.05f);
+    s.gain += 0.05f * (gain_linear - s.gain);
+    float compressed = in * s.gain;
+    s.os.set_mode(OversamplingMode::X4);
+    float colored_os = s.os.process(compressed, [](float x) { return atanf(x) * FRAC_2_PI_F * 1.1f; });
+    float colored = s.gain < 0.99f ? colored_os : compressed;
+    float dcb = dc_block(colored, s.dc_x1, s.dc_y1);
+    float out = in * (1.0f - mix) + dcb * mix;
+    if (!std::isfinite(out)) { s.dc_x1 = s.dc_y1 = 0.0f; s.envelope = 0.0f; s.gain = 1.0f; return 0.0f; }
+    return out;
+  }
+  float process(float in) override { return inner(st[0], in, in); }
+  StereoFrame process_stereo(StereoFrame in) override { StereoFrame o; o.l = inner(st[0], in.l, in.l); o.r = inner(st[1], in.r, in.r); return o; }
+  StereoFrame process_stereo_with_sidechain(StereoFrame in, StereoFrame sc) { StereoFrame o; o.l = inner(st[0], in.l, sc.l); o.r = inner(st[1], in.r, sc.r); return o; }
+};
+
+// Rack variants of the two waveshapers: one instance per channel (effect_chain.rs:49-50, 141-156)
+struct WaveshaperPair : StereoEffect {
+  Waveshaper ws[2];
+  WaveshaperPair() : ws{Waveshaper(1.0f, 0.0f), Waveshaper(1.0f, 0.0f)} {}
+  void set_param(uint32_t p, float v) override { for (auto& w : ws) { if (p == 0) w.set_drive(v); else if (p == 1) w.set_mix(v); } }
+  float process(float in) override { return ws[0].process(in); }
+  StereoFrame process_stereo(StereoFrame in) override { StereoFrame o; o.l = ws[0].process(in.l); o.r = ws[1].process(in.r); return o; }
+};
+struct FeedbackWaveshaperPair : StereoEffect {
+  FeedbackWaveshaper fb[2];
+  explicit FeedbackWaveshaperPair(float sr) : fb{FeedbackWaveshaper(sr, 1.0f, 0.0f, 2000.0f, 0.0f), FeedbackWaveshaper(sr, 1.0f, 0.0f, 2000.0f, 0.0f)} {}
+  void set_param(uint32_t p, float v) override {
+    for (auto& w : fb) { if (p == 0) w.set_drive(v); else if (p == 1) w.set_feedback(v); else if (p == 2) w.set_filter_cutoff(v); else if (p == 3) w.set_mix(v); }
+  }
+  float process(float in) override { return fb[0].process(in); }
+  StereoFrame process_stereo(StereoFrame in) override { StereoFrame o; o.l = fb[0].process(in.l); o.r = fb[1].process(in.r); return o; }
 };
 
 // ---- effects/delay.rs ---------------------------------------------------------------------------------
@@ -72,6 +232,7 @@ struct DelayEffect : StereoEffect {
     timing_target = timing; bpm_target = bpm; feedback_target = fbc; mix_target = mc; cutoff_target = cc;
   }
   void set_bpm(float b) override { bpm_target = b; }
+  void reset() { for (auto& s : st) { std::fill(s.buffer.begin(), s.buffer.end(), 0.0f); s.write_index = 0; s.z1 = s.z2 = 0.0f; } }   // delay.rs:229-238
   void set_param(uint32_t p, float v) override {  // ffi.rs:3006-3017
     switch (p) {
       case 0: { uint32_t t = (uint32_t)f32_as_u64(v) ; if (f32_as_u64(v) > 0xffffffffull) t = 0xffffffffu; if (t <= 8) timing_target = t; } break;
@@ -152,6 +313,7 @@ struct SpringReverbEffect : StereoEffect {
     decay_target = decay; mix_target = mix; damping_target = damping;
   }
   void set_param(uint32_t p, float v) override { v = clampf(v, 0, 1); if (p == 0) decay_target = v; else if (p == 1) mix_target = v; else if (p == 2) damping_target = v; }
+  void reset() { for (auto& s : st) { for (auto& a : s.ap) { std::fill(a.buf.begin(), a.buf.end(), 0.0f); a.idx = 0; } s.fb = s.damp = 0.0f; } }   // reverb.rs:148-159
   float one(St& s, float in) {  // :162-217
     const float G[6] = {0.70f, 0.68f, 0.65f, 0.62f, 0.60f, 0.58f};
     in = std::isfinite(in) ? in : 0.0f;
@@ -224,6 +386,11 @@ struct PlateReverbEffect : StereoEffect {
   void set_param(uint32_t p, float v) override {
     v = clampf(v, 0, 1);
     switch (p) { case 0: decay_t = v; break; case 1: mix_t = v; break; case 2: damping_t = v; break; case 3: predelay_t = v; break; case 4: width_t = v; break; case 5: size_t_ = v; break; }
+  }
+  void reset() {   // plate_reverb.rs:380-402
+    DL* all[13] = {&predelay, &in_ap[0], &in_ap[1], &in_ap[2], &in_ap[3], &mod_ap_a, &delay1_a, &ap2_a, &delay2_a, &mod_ap_b, &delay1_b, &ap2_b, &delay2_b};
+    for (DL* d : all) { std::fill(d->buf.begin(), d->buf.end(), 0.0f); d->idx = 0; }
+    bandwidth_state = damp_a = damp_b = fb_a = fb_b = lfo_pa = lfo_pb = 0.0f;
   }
   static void flush(float& x) { if (fabsf(x) < 1e-15f) x = 0.0f; }
   void tick_tank(float in, float& wl, float& wr, float& mix) {  // :406-534

@@ -1,7 +1,7 @@
 // oracle/engine.hpp — TEST INFRASTRUCTURE ONLY.
 // CPU restatement of the control + mix layer: Sequencer (engine/sequencer.rs), MixerGraph (mixer/graph.rs),
 // the Rust-API Engine + bounce (engine/mod.rs, bounce.rs) and the C-FFI GooeyEngine (ffi.rs:570-1541, 7833-7884).
-// Out of scope here exactly as in SURVEY.md §2: LFO pool, preset blender, performance recorder, loop mixer,
+// Out of scope here exactly as in SURVEY.md §2: performance recorder, loop mixer,
 // samplers, host-time arm (all default-off / contribute +0.0 on the bounce path).
 #pragma once
 #include <memory>
@@ -57,11 +57,16 @@ struct Sequencer {
 // ---- mixer/graph.rs --------------------------------------------------------------------------------------
 static inline std::unique_ptr<StereoEffect> make_channel_effect(uint32_t id, float sr, float bpm) {  // effect_chain.rs:57-109
   switch (id) {
+    case 0: return std::make_unique<LowpassFilterEffect>(sr, 20000.0f, 0.0f);
     case 1: return std::make_unique<DelayEffect>(sr, 2, bpm, 0.3f, 0.3f, 8000.0f);
+    case 2: return std::make_unique<TubeSaturation>(sr, 0.3f, 0.4f, 0.5f);
+    case 3: return std::make_unique<TubeCompressor>(sr, -12.0f, 4.0f, 5.0f, 100.0f, 0.5f);
     case 4: return std::make_unique<TiltFilterEffect>(sr);
     case 6: return std::make_unique<SpringReverbEffect>(sr, 0.5f, 0.3f, 0.5f);
+    case 7: return std::make_unique<WaveshaperPair>();
+    case 8: return std::make_unique<FeedbackWaveshaperPair>(sr);
     case 9: return std::make_unique<PlateReverbEffect>(sr, 0.5f, 0.3f, 0.5f);
-    default: return nullptr;  // effects outside SURVEY.md §8a
+    default: return nullptr;  // the master limiter is not a channel effect
   }
 }
 struct Track {
@@ -141,6 +146,11 @@ struct FfiEngine {
   SpringReverbEffect reverb; bool reverb_enabled = false;
   PlateReverbEffect plate; bool plate_enabled = false;
   SoftLimiter limiter; bool limiter_enabled = false;
+  LowpassFilterEffect lowpass; bool lowpass_enabled = false;
+  TubeSaturation saturation; bool saturation_enabled = false;
+  TubeCompressor compressor; bool compressor_enabled = false; uint32_t compressor_sidechain = 0xFFFFFFFFu;
+  Waveshaper waveshaper; bool waveshaper_enabled = false;                          // ONE instance: L then R through the same state (ffi.rs:1344-1349)
+  FeedbackWaveshaper feedback_waveshaper; bool feedback_waveshaper_enabled = false;
   uint32_t effect_order[9] = {7, 2, 0, 4, 1, 3, 8, 6, 9};  // DEFAULT_EFFECT_ORDER (ffi.rs:1583-1593)
   SmoothedParam master_gain;
   bool seq_triggers_enabled = true;
@@ -149,13 +159,16 @@ struct FfiEngine {
   MixerGraph graph;
   explicit FfiEngine(float sr)
       : sample_rate(sr), delay(sr, 2, 120.0f, 0.0f, 0.0f, 20000.0f), tilt(sr), reverb(sr, 0.5f, 0.0f, 0.5f), plate(sr, 0.5f, 0.0f, 0.5f),
-        limiter(1.0f), master_gain(0.25f, 0.0f, 2.0f, sr, 30.0f), poly(sr), granulator(sr), graph(sr, 120.0f) {
+        limiter(1.0f), lowpass(sr, 20000.0f, 0.0f), saturation(sr, 0.3f, 0.4f, 0.5f), compressor(sr, -12.0f, 4.0f, 5.0f, 100.0f, 0.5f),
+        waveshaper(1.0f, 0.0f), feedback_waveshaper(sr, 1.0f, 0.0f, 2000.0f, 0.0f),
+        master_gain(0.25f, 0.0f, 2.0f, sr, 30.0f), poly(sr), granulator(sr), graph(sr, 120.0f) {
     for (uint32_t t = 0; t < 5; t++) voices.emplace_back(make_instrument(t, sr), t, bpm, sr);
     graph.default_layout();
   }
   VoiceStrip* by_type(uint32_t t) { for (auto& v : voices) if (v.type == t) return &v; return nullptr; }
   void set_bpm(float b) { bpm = b; for (auto& v : voices) v.seq.set_bpm(b); delay.set_bpm(b); graph.set_bpm(b); }
   void set_swing(float s) { swing = clampf(s, 0.0f, 1.0f); for (auto& v : voices) v.seq.set_swing(swing); }
+  void reset_effect_states() { saturation.reset(); lowpass.reset(); tilt.reset(); delay.reset(); compressor.reset(); reverb.reset(); plate.reset(); }  // ffi.rs:1417-1425
   static bool freq_range(uint32_t type, float& mn, float& mx) {  // :1511-1518
     if (type == 4) { mn = 30.0f; mx = 200.0f; return true; }
     if (type == 0) { mn = 30.0f; mx = 120.0f; return true; }
@@ -199,9 +212,11 @@ struct FfiEngine {
       }
       StereoFrame kit, bassf;
       double time = current_time;
+      float channel_outs[5];
       for (int ch = 0; ch < 5; ch++) {
         VoiceStrip& v = voices[ch];
         float out = v.inst->tick(time) * v.channel_gain.tick() * v.mute_gain.tick();
+        channel_outs[ch] = out;
         StereoFrame p = StereoFrame::panned(out, v.pan.tick());
         if (ch < 4) kit += p; else bassf += p;
       }
@@ -216,7 +231,15 @@ struct FfiEngine {
       StereoFrame st = graph.mix_down();
       st = st.scaled(master_gain.tick());
       for (uint32_t id : effect_order) {
-        if (id == 4 && tilt_enabled) st = tilt.process_stereo(st);
+        if (id == 2 && saturation_enabled) st = saturation.process_stereo(st);
+        else if (id == 0 && lowpass_enabled) st = lowpass.process_stereo(st);
+        else if (id == 3 && compressor_enabled) {
+          if (compressor_sidechain < 5) { StereoFrame sc; sc.l = sc.r = channel_outs[compressor_sidechain]; st = compressor.process_stereo_with_sidechain(st, sc); }
+          else st = compressor.process_stereo(st);
+        }
+        else if (id == 7 && waveshaper_enabled) { float l = waveshaper.process(st.l); float r = waveshaper.process(st.r); st.l = l; st.r = r; }
+        else if (id == 8 && feedback_waveshaper_enabled) { float l = feedback_waveshaper.process(st.l); float r = feedback_waveshaper.process(st.r); st.l = l; st.r = r; }
+        else if (id == 4 && tilt_enabled) st = tilt.process_stereo(st);
         else if (id == 1 && delay_enabled) st = delay.process_stereo(st);
         else if (id == 6 && reverb_enabled) st = reverb.process_stereo(st);
         else if (id == 9 && plate_enabled) st = plate.process_stereo(st);

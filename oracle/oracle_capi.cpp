@@ -161,30 +161,86 @@ void orc_engine_sequencer_set_instrument_step(void* e, uint32_t inst, uint32_t s
   VoiceStrip* s = &E->voices[inst];
   if (step < s->seq.pattern.size()) s->seq.pattern[step].enabled = enabled;
 }
+void orc_engine_sequencer_set_step(void* e, uint32_t step, bool enabled) { orc_engine_sequencer_set_instrument_step(e, 0, step, enabled); }   // kick only (ffi.rs:3695-3708)
+void orc_engine_sequencer_set_instrument_step_with_velocity(void* e, uint32_t inst, uint32_t step, bool enabled, float vel) {  // sequencer.rs:705-712: keeps blend and note
+  if (!e || inst >= 5) return;
+  VoiceStrip* s = &E->voices[inst];
+  if (step < s->seq.pattern.size()) { s->seq.pattern[step].enabled = enabled; s->seq.pattern[step].velocity = clampf(vel, 0.0f, 1.0f); }
+}
+void orc_engine_sequencer_set_instrument_step_note(void* e, uint32_t inst, uint32_t step, uint8_t note) {  // ffi.rs:3975-3995
+  if (!e || inst >= 5) return;
+  VoiceStrip* s = &E->voices[inst];
+  if (step < s->seq.pattern.size()) { if (note == 255) s->seq.pattern[step].has_note = false; else { s->seq.pattern[step].has_note = true; s->seq.pattern[step].note = note; } }
+}
+void orc_engine_sequencer_set_instrument_pattern(void* e, uint32_t inst, const bool* pattern) {  // sequencer.rs:822-828
+  if (!e || !pattern || inst >= 5) return;
+  Sequencer& q = E->voices[inst].seq;
+  q.pattern.assign(16, SeqStep());
+  for (int i = 0; i < 16; i++) { q.pattern[i].enabled = pattern[i]; q.pattern[i].velocity = 1.0f; }
+  if (q.current_step >= q.pattern.size()) q.current_step = 0;
+}
 void orc_engine_sequencer_start(void* e) { if (e) for (auto& v : E->voices) v.seq.start(); }
 void orc_engine_sequencer_stop(void* e) { if (e) for (auto& v : E->voices) v.seq.stop(); }
 void orc_engine_sequencer_reset(void* e) { if (e) for (auto& v : E->voices) v.seq.reset(); }
 void orc_engine_set_global_effect_param(void* e, uint32_t fx, uint32_t p, float v) {
   if (!e) return;
   switch (fx) { case 1: E->delay.set_param(p, v); break; case 4: E->tilt.set_param(p, v); break; case 6: E->reverb.set_param(p, v); break;
-    case 9: E->plate.set_param(p, v); break; case 5: if (p == 0) E->limiter.set_threshold(v); break; }
+    case 9: E->plate.set_param(p, v); break; case 5: if (p == 0) E->limiter.set_threshold(v); break;
+    case 0: E->lowpass.set_param(p, v); break; case 2: E->saturation.set_param(p, v); break; case 3: E->compressor.set_param(p, v); break;
+    case 7: if (p == 0) E->waveshaper.set_drive(v); else if (p == 1) E->waveshaper.set_mix(v); break;
+    case 8: {
+      if (p == 0) E->feedback_waveshaper.set_drive(v); else if (p == 1) E->feedback_waveshaper.set_feedback(v);
+      else if (p == 2) E->feedback_waveshaper.set_filter_cutoff(v); else if (p == 3) E->feedback_waveshaper.set_mix(v);
+    } break; }
 }
 void orc_engine_set_global_effect_enabled(void* e, uint32_t fx, bool on) {
   if (!e) return;
   switch (fx) { case 1: E->delay_enabled = on; break; case 4: E->tilt_enabled = on; break; case 6: E->reverb_enabled = on; break;
-    case 9: E->plate_enabled = on; break; case 5: E->limiter_enabled = on; break; }
+    case 9: E->plate_enabled = on; break; case 5: E->limiter_enabled = on; break;
+    case 0: E->lowpass_enabled = on; break; case 2: E->saturation_enabled = on; break; case 3: E->compressor_enabled = on; break;
+    case 7: E->waveshaper_enabled = on; break; case 8: E->feedback_waveshaper_enabled = on; break; }
 }
+void orc_engine_set_compressor_sidechain(void* e, uint32_t inst) { if (e) E->compressor_sidechain = inst; }
 bool orc_engine_set_effect_order(void* e, const uint32_t* ids, uint32_t len) {
   if (!e || !ids || len != 9) return false;
   for (uint32_t i = 0; i < 9; i++) { if (ids[i] > 9 || ids[i] == 5) return false; for (uint32_t j = 0; j < i; j++) if (ids[j] == ids[i]) return false; }
   for (uint32_t i = 0; i < 9; i++) E->effect_order[i] = ids[i];
-  return true;  // reset_effect_states: tests only reorder before any audio has run
+  E->reset_effect_states();
+  return true;
 }
 void orc_engine_set_instrument_gain(void* e, uint32_t i, float g) { if (e && i < 5) E->voices[i].channel_gain.set_target(clampf(g, 0, 1)); }
 void orc_engine_set_instrument_pan(void* e, uint32_t i, float p) { if (e && i < 5) E->voices[i].pan.set_target(clampf(p, 0, 1)); }
 void orc_engine_set_instrument_mute(void* e, uint32_t i, bool m) { if (e && i < 5) E->voices[i].muted = m; }
 void orc_engine_set_instrument_solo(void* e, uint32_t i, bool s) { if (e && i < 5) E->voices[i].soloed = s; }
 void orc_engine_trigger_instrument_with_velocity(void* e, uint32_t i, float v) { if (e && i < 5) { E->voices[i].trigger_velocity = clampf(v, 0, 1); E->voices[i].trigger_pending = true; } }
+void orc_engine_trigger_instrument(void* e, uint32_t i) { orc_engine_trigger_instrument_with_velocity(e, i, 1.0f); }
+bool orc_engine_move_effect(void* e, uint32_t id, uint32_t new_position) {  // ffi.rs:4544-4581
+  if (!e || id > 9 || id == 5 || new_position >= 9) return false;
+  int cur = -1;
+  for (int i = 0; i < 9; i++) if (E->effect_order[i] == id) cur = i;
+  if (cur < 0) return false;
+  int np = (int)new_position;
+  if (cur == np) return true;
+  if (np > cur) for (int i = cur; i < np; i++) E->effect_order[i] = E->effect_order[i + 1];
+  else for (int i = cur - 1; i >= np; i--) E->effect_order[i + 1] = E->effect_order[i];
+  E->effect_order[np] = id;
+  E->reset_effect_states();
+  return true;
+}
+bool orc_engine_track_effect_remove(void* e, uint32_t t, uint32_t slot) {
+  if (!e || t >= E->graph.tracks.size() || slot >= E->graph.tracks[t].rack.size()) return false;
+  E->graph.tracks[t].rack.erase(E->graph.tracks[t].rack.begin() + slot);
+  return true;
+}
+bool orc_engine_track_effect_move(void* e, uint32_t t, uint32_t slot, uint32_t np) {
+  if (!e || t >= E->graph.tracks.size() || slot >= E->graph.tracks[t].rack.size()) return false;
+  auto& r = E->graph.tracks[t].rack;
+  auto fx = std::move(r[slot]);
+  r.erase(r.begin() + slot);
+  size_t dest = np < r.size() ? np : r.size();
+  r.insert(r.begin() + dest, std::move(fx));
+  return true;
+}
 int32_t orc_engine_mixer_add_track(void* e, const char*) { return e ? (int32_t)E->graph.add_track() : -1; }
 bool orc_engine_mixer_route_source(void* e, uint32_t src, uint32_t track) { return e ? E->graph.route(src, track) : false; }
 void orc_engine_mixer_set_track_gain(void* e, uint32_t t, float g) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].gain.set_target(clampf(g, 0.0f, 2.0f)); }

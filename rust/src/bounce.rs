@@ -103,7 +103,7 @@ impl EngineBatch {
         if total > 0 {
             check(unsafe { gooey_rs_batch_bounce(self.raw, total as u32, flat.as_mut_ptr()) })?;
         }
-        Ok(flat.chunks(total.max(1)).take(n).map(|c| c[..total].to_vec()).collect())
+        Ok((0..n).map(|i| flat[i * total..(i + 1) * total].to_vec()).collect())
     }
 }
 

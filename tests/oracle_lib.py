@@ -73,3 +73,18 @@ def trigger_table(engine, channel, frames, cap=4096):
     L.orc_engine_trigger_table.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
     n = L.orc_engine_trigger_table(engine._h, channel, frames, fr.ctypes.data, ve.ctypes.data, cap)
     return fr[:n].copy(), ve[:n].copy()
+
+
+def bounce_many(script, indices, bars):
+    """Oracle bounce of engine i (configured by script(engine, i)) for every i, one engine per host thread (ctypes calls
+    release the GIL, engines share nothing).  Returns {i: mono array}."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        o = oracle_engine()
+        script(o, i)
+        out = o.bounce_to_buffer(bars)
+        o.close()
+        return i, out
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        return dict(ex.map(one, list(indices)))

@@ -1,0 +1,381 @@
+"""GPU parity for every exported engine entry point that the round-1 suite did not reach: track effect racks of every kind,
+effect reordering, delay ping-pong, instrument solo, track mute / solo, bass presets, per-channel parameters and
+instrument swap, every sequencer setter, the batch stereo render, bounce_to_wav, the sticky error + callback, and the
+saturation / compressor (+ side-chain) / low-pass / waveshaper / feedback-waveshaper effect slots.
+One FFI-named call script drives the CPU oracle and the product; tolerance 1e-5 of full scale (BASELINE.json)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from libgooey_b200 import engine as G
+import oracle_lib as O
+import engine_scripts as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+FX_LOWPASS, FX_DELAY, FX_SAT, FX_COMP, FX_TILT, FX_LIMITER, FX_REVERB, FX_WS, FX_FBWS, FX_PLATE = range(10)
+
+
+def busy_pattern(e, snare_overdrive=0.0):
+    """Every voice plays, nothing blows up: default (preset) voices, a dense pattern, pans apart so that L != R."""
+    for s in (0, 3, 6, 8, 11, 14):
+        e.sequencer_set_instrument_step(S.KICK, s, True)
+    for s in (4, 12):
+        e.sequencer_set_instrument_step(S.SNARE, s, True)
+    for s in range(0, 16, 2):
+        e.sequencer_set_instrument_step_with_velocity(S.HIHAT, s, True, 0.5 + 0.03 * s)
+    for s in (2, 10):
+        e.sequencer_set_instrument_step(S.TOM, s, True)
+    for s in (0, 7, 9):
+        e.sequencer_set_instrument_step(S.BASS, s, True)
+    e.set_instrument_pan(S.KICK, 0.35)
+    e.set_instrument_pan(S.HIHAT, 0.8)
+    e.set_instrument_pan(S.BASS, 0.6)
+    e.set_snare_param(15, snare_overdrive)
+    e.set_master_gain(0.6)
+
+
+def both(script, bars=1, stereo_frames=None):
+    o = O.oracle_engine()
+    g = G.Engine()
+    script(o)
+    script(g)
+    if stereo_frames:
+        for e in (o, g):
+            e.sequencer_reset(); e.sequencer_start()
+        want, got = o.render(stereo_frames), g.render(stereo_frames)
+    else:
+        want, got = o.bounce_to_buffer(bars), g.bounce_to_buffer(bars)
+    assert not g.has_error(), g.get_error_message()
+    o.close(); g.close()
+    assert got.shape == want.shape and np.isfinite(want).all()
+    assert np.abs(want).max() > 0.01
+    return got, want
+
+
+RACK_PARAMS = {
+    FX_LOWPASS: [(0, 1800.0), (1, 0.6)], FX_DELAY: [(0, 3.0), (1, 0.5), (2, 0.4), (3, 6000.0)], FX_SAT: [(0, 0.7), (1, 0.6), (2, 0.8)],
+    FX_COMP: [(0, -30.0), (1, 8.0), (2, 2.0), (3, 60.0), (4, 0.9)], FX_TILT: [(0, 0.25), (1, 0.4)], FX_REVERB: [(0, 0.6), (1, 0.5), (2, 0.3)],
+    FX_WS: [(0, 5.0), (1, 0.8)], FX_FBWS: [(0, 6.0), (1, 0.4), (2, 3000.0), (3, 0.7)], FX_PLATE: [(0, 0.6), (1, 0.5), (2, 0.4), (5, 0.35)],
+}
+
+
+@pytest.mark.parametrize("kind", sorted(RACK_PARAMS))
+def test_track_rack_of_every_effect_kind(kind):
+    def script(e):
+        busy_pattern(e)
+        assert e.track_effect_add(0, kind) == 0                 # drum-kit track
+        for p, v in RACK_PARAMS[kind]:
+            e.track_effect_set_param(0, 0, p, v)
+    got, want = both(script, stereo_frames=44100)
+    err = np.abs(got - want).max()
+    print(f"rack kind {kind}: err {err:.3e} peak {np.abs(want).max():.3f}")
+    assert err <= TOL
+
+
+def test_rack_chain_add_move_remove_and_limiter_is_not_a_rack_effect():
+    def script(e):
+        busy_pattern(e)
+        assert e.track_effect_add(1, FX_LIMITER) == -1
+        assert e.track_effect_add(1, FX_SAT) == 0 and e.track_effect_add(1, FX_DELAY) == 1 and e.track_effect_add(1, FX_TILT) == 2
+        e.track_effect_set_param(1, 1, 2, 0.5)
+        e.track_effect_set_param(1, 2, 0, 0.8)
+        assert e.track_effect_move(1, 0, 5)                     # saturation to the end (clamped)
+        assert e.track_effect_remove(1, 0)                      # drops the delay
+        assert not e.track_effect_remove(1, 7)
+        e.track_effect_set_param(1, 1, 0, 0.9)                  # now the saturation
+        assert e.track_effect_add(1, FX_REVERB) == 2
+    got, want = both(script, bars=1)
+    assert np.abs(got - want).max() <= TOL
+
+
+@pytest.mark.parametrize("order", [[9, 6, 3, 1, 4, 0, 2, 8, 7], [1, 6, 4, 9, 0, 2, 3, 7, 8]])
+def test_permuted_effect_order_with_every_global_effect_enabled(order):
+    def script(e):
+        busy_pattern(e)
+        S.fx_chain(e, 21, plate=True)
+        for fx, params in RACK_PARAMS.items():
+            if fx in (FX_LOWPASS, FX_SAT, FX_COMP, FX_WS, FX_FBWS):
+                for p, v in params:
+                    e.set_global_effect_param(fx, p, v)
+                e.set_global_effect_enabled(fx, True)
+        assert not e.set_effect_order([5] + order[1:])           # limiter is not reorderable
+        assert not e.set_effect_order(order[:8])
+        assert e.set_effect_order(order)
+        assert e.move_effect(order[0], 3)
+    got, want = both(script, stereo_frames=30000)
+    err = np.abs(got - want).max()
+    print(f"effect order {order}: err {err:.3e}")
+    assert err <= TOL
+
+
+def test_reorder_after_audio_resets_effect_states():
+    def run(e):
+        busy_pattern(e)
+        S.fx_chain(e, 4, plate=True)
+        e.set_global_effect_param(FX_SAT, 2, 0.7); e.set_global_effect_enabled(FX_SAT, True)
+        e.sequencer_start()
+        a = e.render(12000)
+        assert e.set_effect_order([9, 6, 3, 1, 4, 0, 2, 8, 7])   # reset_effect_states: delay lines / tanks cleared mid-stream
+        b = e.render(12000)
+        return np.concatenate([a, b])
+    o = O.oracle_engine(); g = G.Engine()
+    want, got = run(o), run(g)
+    o.close(); g.close()
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_delay_pingpong_stereo():
+    def script(e):
+        busy_pattern(e)
+        for p, v in [(0, 4.0), (1, 0.6), (2, 0.5), (3, 5000.0), (4, 1.0)]:
+            e.set_global_effect_param(FX_DELAY, p, v)
+        e.set_global_effect_enabled(FX_DELAY, True)
+    got, want = both(script, stereo_frames=44100)
+    assert np.abs(want[:, 0] - want[:, 1]).max() > 1e-3          # the echoes really alternate sides
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_instrument_solo_and_track_mute_solo():
+    def script(e):
+        busy_pattern(e)
+        e.set_instrument_solo(S.SNARE, True)
+        e.set_instrument_solo(S.BASS, True)
+        e.set_instrument_mute(S.BASS, True)                      # solo wins over mute
+        t = e.mixer_add_track("aux")
+        e.mixer_route_source(1, t)                               # bass -> aux
+        e.mixer_set_track_mute(0, True)
+        e.mixer_set_track_solo(t, True)
+    o = O.oracle_engine(); g = G.Engine()
+    script(o); script(g)
+    for e in (o, g):
+        e.sequencer_start()
+    a = [o.render(6000)]; b = [g.render(6000)]
+    for e in (o, g):
+        e.mixer_set_track_solo(4, False)                         # targets change between renders: mute gains glide
+        e.set_instrument_solo(S.SNARE, False)
+    a.append(o.render(9000)); b.append(g.render(9000))
+    for e in (o, g):
+        e.mixer_set_track_mute(0, False)
+        e.set_instrument_solo(S.BASS, False)                     # the bass is now plainly muted
+    a.append(o.render(9000)); b.append(g.render(9000))
+    o.close(); g.close()
+    want, got = np.concatenate(a), np.concatenate(b)
+    assert np.abs(want).max() > 0.01
+    assert np.abs(got - want).max() <= TOL
+
+
+@pytest.mark.parametrize("preset", [0, 1, 2, 3])
+def test_load_bass_preset(preset):
+    def script(e):
+        for s in (0, 4, 6, 10):
+            e.sequencer_set_instrument_step_with_velocity(S.BASS, s, True, 0.9)
+        e.sequencer_set_instrument_step_note(S.BASS, 4, 43)
+        e.load_bass_preset(preset)
+        e.load_bass_preset(9)                                    # unknown id: ignored
+    got, want = both(script, bars=1)
+    err = np.abs(got - want).max()
+    print(f"bass preset {preset}: err {err:.3e} peak {np.abs(want).max():.3f}")
+    assert err <= TOL
+
+
+def test_set_channel_param_and_instrument_type_swap():
+    def script(e):
+        busy_pattern(e)
+        e.set_channel_param(0, 1, 0.9)                           # kick punch through the channel interface
+        e.set_channel_param(2, 1, 0.4)                           # hi-hat decay
+        e.set_channel_param(9, 0, 0.5)                           # bad channel: ignored
+        e.set_channel_instrument_type(3, S.SNARE)                # the tom channel becomes a second snare (SnareDrum::new)
+        e.set_channel_param(3, 0, 0.8)                           # ... and takes snare parameter ids
+        e.set_channel_instrument_type(1, S.TOM)
+        e.set_channel_instrument_type(1, S.TOM)                  # no-op
+        e.set_channel_instrument_type(0, 7)                      # unknown type: ignored
+    got, want = both(script, bars=1)
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_instrument_type_swap_between_renders():
+    def run(e):
+        busy_pattern(e)
+        e.sequencer_start()
+        a = e.render(20000)
+        e.set_channel_instrument_type(2, S.BASS)                 # a fresh bass joins at the engine's current time
+        e.set_channel_param(2, 0, 0.7)
+        b = e.render(30000)
+        return np.concatenate([a, b])
+    o = O.oracle_engine(); g = G.Engine()
+    want, got = run(o), run(g)
+    o.close(); g.close()
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_every_sequencer_setter():
+    def script(e):
+        e.sequencer_set_step(0, True); e.sequencer_set_step(8, True); e.sequencer_set_step(99, True)     # kick only; bad step ignored
+        e.sequencer_set_instrument_pattern(S.HIHAT, [i % 3 == 0 for i in range(16)])
+        e.sequencer_set_instrument_step_with_velocity(S.SNARE, 4, True, 0.7)
+        e.sequencer_set_instrument_step_with_velocity(S.SNARE, 12, True, 1.7)                           # clamped to 1
+        e.sequencer_set_instrument_step(S.TOM, 6, True)
+        e.sequencer_set_instrument_step_note(S.TOM, 6, 50)
+        e.sequencer_set_instrument_step(S.TOM, 14, True)                                                 # no note: restores the tune
+        e.sequencer_set_instrument_step_settings(S.BASS, 2, True, True, 0.8, False, 0.0, 0.0, True, 40)
+        e.sequencer_set_instrument_step_settings(S.BASS, 10, True, False, 0.0, False, 0.0, 0.0, True, 255)
+        e.sequencer_set_instrument_step_note(S.BASS, 2, 255)                                             # cleared again
+        e.sequencer_set_instrument_step_note(S.KICK, 8, 38)
+    got, want = both(script, bars=2)
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_manual_trigger_default_velocity_and_stop_reset():
+    def run(e):
+        busy_pattern(e)
+        e.trigger_instrument(S.TOM)
+        e.sequencer_start()
+        a = e.render(15000)
+        e.sequencer_stop()
+        e.trigger_instrument(S.KICK)
+        b = e.render(8000)
+        e.sequencer_reset(); e.sequencer_start()
+        c = e.render(15000)
+        return np.concatenate([a, b, c])
+    o = O.oracle_engine(); g = G.Engine()
+    want, got = run(o), run(g)
+    o.close(); g.close()
+    assert np.abs(want).max() > 0.01
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_batch_render_stereo_matches_oracle_renders():
+    n, frames = 12, 20000
+
+    def script(e, i):
+        busy_pattern(e, snare_overdrive=0.1 * (i % 4))
+        e.set_swing(0.5 + 0.02 * i)
+        if i % 3 == 0:
+            S.fx_chain(e, 40 + i, plate=(i % 2 == 0))
+        e.sequencer_start()
+    engines = [G.Engine() for _ in range(n)]
+    for i, e in enumerate(engines):
+        script(e, i)
+    got = G.batch_render(engines, frames)
+    got2 = G.batch_render(engines, 5000)                          # state and clock carry over
+    for e in engines:
+        e.close()
+    for i in range(n):
+        o = O.oracle_engine(); script(o, i)
+        want = o.render(frames); want2 = o.render(5000)
+        o.close()
+        assert np.abs(got[i] - want).max() <= TOL, i
+        assert np.abs(got2[i] - want2).max() <= TOL, i
+
+
+def test_bounce_to_wav_bytes(tmp_path):
+    def script(e):
+        busy_pattern(e, snare_overdrive=0.3)
+    o = O.oracle_engine(); g = G.Engine()
+    script(o); script(g)
+    want = o.bounce_to_buffer(1)
+    path = tmp_path / "bounce.wav"
+    assert g.bounce_to_wav(1, path)
+    assert not g.bounce_to_wav(1, tmp_path / "no_such_dir" / "x.wav")
+    o.close(); g.close()
+    raw = path.read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and raw[36:40] == b"data"
+    fmt = struct.unpack("<HHIIHH", raw[20:36])
+    assert fmt == (1, 1, 44100, 88200, 2, 16)                    # PCM, mono, 44.1 kHz, 16 bit (ffi.rs:7957-7964)
+    data = np.frombuffer(raw[44:], dtype="<i2")
+    assert len(data) == len(want) == 88200 and struct.unpack("<I", raw[40:44])[0] == 2 * 88200
+    q = np.clip(np.sign(want) * np.floor(np.abs(want * np.float32(32767.0)) + 0.5), -32768, 32767).astype(np.int16)   # (s * 32767).round() as i16
+    assert np.abs(data.astype(np.int32) - q.astype(np.int32)).max() <= 1       # 1e-5 of full scale is a third of one 16-bit step
+    assert (data != q).mean() < 0.01
+
+
+def test_sticky_error_and_callback_when_an_engine_runs_out_of_effect_slots():
+    g = G.Engine()
+    seen = []
+    g.set_error_callback(seen.append)
+    assert not g.has_error() and g.get_error_message() is None
+    for k in range(4):
+        assert g.track_effect_add(0, FX_TILT) == k
+    assert g.track_effect_add(0, FX_TILT) == -1                  # a rack holds four here: refused loudly, not silently
+    assert g.has_error() and "rack" in g.get_error_message()
+    assert len(seen) == 1 and seen[0] == g.get_error_message()
+    g.track_effect_add(0, FX_TILT)
+    assert len(seen) == 1                                        # fired once (ffi.rs:2236-2284)
+    out = g.render(256)
+    assert not out.any()                                         # an engine in the error state renders silence
+    g.close()
+
+
+@pytest.mark.parametrize("fx", [FX_LOWPASS, FX_SAT, FX_COMP, FX_WS, FX_FBWS])
+def test_each_new_global_effect_alone(fx):
+    def script(e):
+        busy_pattern(e, snare_overdrive=0.2)
+        for p, v in RACK_PARAMS[fx]:
+            e.set_global_effect_param(fx, p, v)
+        e.set_global_effect_param(fx, 17, 0.5)                   # unknown parameter id: ignored
+        e.set_global_effect_enabled(fx, True)
+    got, want = both(script, stereo_frames=44100)
+    err = np.abs(got - want).max()
+    print(f"global effect {fx}: err {err:.3e} peak {np.abs(want).max():.3f}")
+    assert err <= TOL
+
+
+def test_global_effects_glide_from_their_defaults_when_enabled_late():
+    def run(e):
+        busy_pattern(e)
+        e.sequencer_start()
+        a = e.render(9000)
+        e.set_global_effect_param(FX_SAT, 0, 0.9)
+        e.set_global_effect_param(FX_LOWPASS, 0, 900.0)
+        e.set_global_effect_param(FX_LOWPASS, 1, 0.8)
+        e.set_global_effect_enabled(FX_SAT, True)
+        e.set_global_effect_enabled(FX_LOWPASS, True)
+        b = e.render(9000)
+        e.set_global_effect_enabled(FX_SAT, False)               # state is kept while disabled
+        c = e.render(4000)
+        e.set_global_effect_enabled(FX_SAT, True)
+        d = e.render(9000)
+        return np.concatenate([a, b, c, d])
+    o = O.oracle_engine(); g = G.Engine()
+    want, got = run(o), run(g)
+    o.close(); g.close()
+    assert np.abs(got - want).max() <= TOL
+
+
+@pytest.mark.parametrize("sidechain", [0xFFFFFFFF, S.KICK, S.BASS])
+def test_bounce_example_chain_saturation_delay_compressor_limiter(sidechain):
+    """The chain of examples/bounce.rs:104-123 on the FFI engine: TubeSaturation(0.3, 0.4, 0.5) -> DelayEffect(Eighth, 0.35,
+    0.2, 8 kHz) -> TubeCompressor(-12 dB, 4:1, 10 ms, 100 ms, 0.6) -> SoftLimiter(0.95), with and without a side-chain."""
+    def script(e):
+        busy_pattern(e, snare_overdrive=0.15)
+        e.set_bpm(128.0)
+        for p, v in [(0, 0.3), (1, 0.4), (2, 0.5)]:
+            e.set_global_effect_param(FX_SAT, p, v)
+        for p, v in [(0, 3.0), (1, 0.35), (2, 0.2), (3, 8000.0)]:
+            e.set_global_effect_param(FX_DELAY, p, v)
+        for p, v in [(0, -12.0), (1, 4.0), (2, 10.0), (3, 100.0), (4, 0.6)]:
+            e.set_global_effect_param(FX_COMP, p, v)
+        e.set_compressor_sidechain(sidechain)
+        e.set_global_effect_param(FX_LIMITER, 0, 0.95)
+        for fx in (FX_SAT, FX_DELAY, FX_COMP, FX_LIMITER):
+            e.set_global_effect_enabled(fx, True)
+    got, want = both(script, bars=2)
+    err = np.abs(got - want).max()
+    print(f"bounce.rs chain, sidechain {sidechain:#x}: err {err:.3e} peak {np.abs(want).max():.3f}")
+    assert err <= TOL
+
+
+def test_poly_trigger_chord_equals_the_voiced_notes():
+    def script_notes(e, notes):
+        e.poly_trigger_notes(notes, 2, 0.8)
+    # C major, degree ii (Dm7), first inversion, octave 4: D4 F4 A4 C5 -> F4 A4 C5 D5 (music/voicing.rs:96-101 on key.rs:55-84)
+    o = O.oracle_engine(); g = G.Engine()
+    script_notes(o, [65, 69, 72, 74])
+    g.poly_trigger_chord(0, 0, 1, 1, preset=2, octave=4, velocity=0.8)
+    want, got = o.render(30000), g.render(30000)
+    o.close(); g.close()
+    assert np.abs(want).max() > 0.01
+    assert np.abs(got - want).max() <= TOL

@@ -76,3 +76,33 @@ def test_schedule_matches_oracle_sequencer_bit_exact(bpm, swing):
     got_f, got_v = schedule(bpm, swing, en, ve, 8 * 88200)
     assert np.array_equal(got_f, want_f)
     assert np.array_equal(got_v.view(np.uint32), want_v.view(np.uint32))
+
+
+def _chord(root, scale, degree, voicing, octave):
+    import ctypes as c
+    L = lib()
+    L.gooey_b200_chord_notes.restype = c.c_uint32
+    L.gooey_b200_chord_notes.argtypes = [c.c_uint32, c.c_uint32, c.c_uint32, c.c_uint32, c.c_int32, c.POINTER(c.c_uint8), c.c_uint32]
+    out = (c.c_uint8 * 8)()
+    n = L.gooey_b200_chord_notes(root, scale, degree, voicing, octave, out, 8)
+    return list(out[:n])
+
+
+def test_chord_tables_against_the_reference_unit_tests():
+    """gooey_engine_poly_trigger_chord's note table (host-only view).  Known answers: music/voicing.rs:225-241 (Cmaj7 drop-2
+    and shell voicings at octave 4), music/key.rs:270-276 (C major: I = Cmaj7, V = G7, vii = Bm7b5)."""
+    assert _chord(0, 0, 0, 0, 4) == [60, 64, 67, 71]            # Cmaj7 root position
+    assert _chord(0, 0, 0, 5, 4) == [55, 60, 64, 71]            # drop 2: G4 -> G3
+    assert _chord(0, 0, 0, 8, 4) == [60, 64, 71]                # shell: root, 3rd, 7th
+    assert _chord(0, 0, 4, 0, 4) == [67, 71, 74, 77]            # G7
+    assert _chord(0, 0, 6, 0, 4) == [71, 74, 77, 81]            # Bm7b5
+    assert _chord(0, 0, 13, 0, 4) == _chord(0, 0, 6, 0, 4)      # degree % 7
+    assert _chord(9, 1, 0, 0, 3) == [57, 60, 64, 67]            # A natural minor: i7 = Am7 at octave 3
+    assert _chord(0, 0, 0, 1, 4) == [64, 67, 71, 72]            # first inversion
+    assert _chord(0, 0, 0, 3, 4) == [71, 72, 76, 79]            # third inversion
+    assert _chord(0, 0, 0, 4, 4) == [60, 67, 76, 83]            # open: every other note up an octave
+    assert _chord(0, 0, 0, 7, 4) == [60, 64, 79, 83]            # spread
+    assert _chord(0, 0, 0, 9, 4) == [52, 67, 71]                # rootless: drop the root, 3rd down an octave
+    assert _chord(0, 0, 0, 6, 4) == [60, 64, 67, 71]            # drop 3 needs five notes: unchanged
+    assert _chord(0, 0, 0, 0, 40) == _chord(0, 0, 0, 0, 8)      # octave clamped to 0..8
+    assert all(n <= 127 for n in _chord(11, 0, 0, 3, 8))
