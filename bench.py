@@ -1,24 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the batched offline bounce path.
+"""bench.py — benchmark of the batched offline bounce path.
 
-Workload (BASELINE.json configs[1], "C2"): a 4096-patch drum sweep (1024 each of kick / snare / hi-hat / tom,
-every FFI-reachable parameter drawn U[0,1), one trigger at frame 0), 2 s each at 44.1 kHz = 88 200 samples per
-voice, per-voice envelopes + filters, per-voice f32 output kept.  One "step" = one full render of the sweep.
+Headline workload (BASELINE.json configs[1], "C2"): a 4096-patch drum sweep per GPU (1024 each of kick / snare / hi-hat /
+tom, every FFI-reachable parameter drawn U[0,1), one trigger at frame 0), 2 s each at 44.1 kHz = 88 200 samples per voice,
+per-voice envelopes + filters, per-voice f32 output kept.  One "step" = one full render of the sweep.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs all|c2]
 
-* ours: `value` = voice-samples/s with patches and output resident in HBM (device time, CUDA events on the
-  library's launching streams, max over ranks); `e2e` = the same through the C ABI with HOST buffers
-  (event tables H2D + kernels + D2H of every voice's audio into pinned host memory inside the timed region; the
-  library drains finished 8192-frame chunks on a copy stream while later chunks render).
-  `roofline` is the contract's store-bandwidth figure for the dominant back-end kernel (algorithmic bytes per launch /
-  its mean launch duration, CUDA events inside the library; `traffic` from the committed ncu capture); `kernels` lists
-  all four back ends.  The kernels are latency-bound, not byte-bound: DESIGN.md section 4 and profiles/README.md.
-* reference: the reference's CPU implementation of the same path.  The Rust reference cannot be built here
-  (no toolchain in the image), so this arm times the C++ restatement in oracle/ ("port") on all host cores,
-  on a bounded sample of the same patches.
-Multi-GPU (torchrun, one rank per GPU): voices shard with no collective; weak scaling — every rank renders its
-own 4096-patch sweep (rank-dependent seed); value = all ranks' voice-samples / max-over-ranks time.
+* ours: `value` = voice-samples/s with patches and output resident in HBM (device time, CUDA events on the library's
+  launching streams, max over ranks); `e2e` = the same through the C ABI with HOST buffers (event tables H2D + kernels +
+  D2H of every voice's audio into pinned host memory inside the timed region; the library drains finished 8192-frame
+  chunks on a copy stream while later chunks render).  `roofline` is the contract's store-bandwidth figure for the
+  dominant back-end kernel (algorithmic bytes per launch / its mean launch duration, CUDA events inside the library;
+  `traffic` from the committed ncu capture); `kernels` lists every back end.
+  `configs` carries the other BASELINE.json configurations measured in the same run (one timed render each):
+  C1 (single kick through the bounce.rs mirror), C3 (1024 FFI engines x 8 bars, patterns + mixer graph), C4 (1600
+  granulators over one shared 60 s source) at N = 1, and C5 (8192 drum+bass engines per GPU with tilt / delay / spring
+  reverb, 2 bars — 65 536 engines at N = 8) at every N; each with device ms, end-to-end ms, its own unit, a spot-check
+  parity error against the oracle and, for C5, the ring-traffic roofline of the effect mixer.
+* reference: the reference's CPU implementation of the same path.  The Rust reference cannot be built here (no
+  toolchain in the image), so this arm times the C++ restatement in oracle/ ("port") on all host cores over the WHOLE
+  4096-patch sweep per step.  It never imports or loads libgooey_b200.
+Multi-GPU (torchrun, one rank per GPU): voices / engines shard with no collective (libgooey_b200/shard.py is the plan:
+the global batch of N x 4096 patches, N x 8192 engines is interleaved by cost class and cut into contiguous shards);
+weak scaling; value = all ranks' voice-samples / max-over-ranks time.
 """
 import argparse
 import ctypes
@@ -43,8 +48,21 @@ SR = 44100.0
 N_PATCHES = 4096
 FRAMES = 88200
 SEED = 0x600E7
-# Algorithmic bytes per voice-sample for this workload: one f32 stored, nothing loaded.
+# Algorithmic bytes per voice-sample for C2: one f32 stored, nothing loaded.
 BYTES_PER_VOICE_SAMPLE = 4
+C3_ENGINES, C3_BARS = 1024, 8
+C4_ENGINES, C4_SECONDS = 1600, 10.0
+C5_ENGINES_PER_GPU, C5_BARS = 8192, 2
+# Algorithmic bytes per engine-sample of the C5 chain: 4 stored + delay 24 + spring 96 (+ plate 268)
+C5_BYTES_PER_ENGINE_SAMPLE = 4 + 24 + 96
+
+
+def workload_config(world):
+    """The `config` object of the JSON line — identical for both arms."""
+    return {"workload": "C2: 4096-patch drum sweep (kick/snare/hihat/tom), 88200 samples each @44.1kHz", "seed": SEED,
+            "voices_per_gpu": N_PATCHES, "frames": FRAMES, "sample_rate": SR,
+            "l2": "output 1.44 GB per step >> 126 MB L2; nothing is re-read between steps",
+            "parallelism": f"independent voice shards x{world}, no collective"}
 
 
 def measured_peaks():
@@ -100,15 +118,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-KERNELS = ["wave_kernel<KickW>", "wave_kernel<SnareW>", "wave_kernel<HatW>", "wave_kernel<TomW>"]
-
-
 def kernel_stats(L):
-    """Per back-end kernel: launches, mean launch duration (CUDA events on the launching stream, measured inside the
-    library over the timed region) and voice-frames per launch."""
+    """Per kernel the library timed: launches, mean launch duration (CUDA events on the launching stream, measured inside
+    the library over the timed region) and units (voice-frames / engine-frames) per launch."""
     L.gooey_b200_kernel_stat.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.gooey_b200_kernel_stat_names.restype = ctypes.c_char_p
+    names = [s for s in (L.gooey_b200_kernel_stat_names() or b"").decode().split(";") if s]
     out = {}
-    for k in KERNELS:
+    for k in names:
         n, ms, vf = ctypes.c_uint64(0), ctypes.c_double(0.0), ctypes.c_double(0.0)
         L.gooey_b200_kernel_stat(k.encode(), ctypes.byref(n), ctypes.byref(ms), ctypes.byref(vf))
         if n.value:
@@ -127,12 +144,12 @@ def ncu_traffic(kernel):
     return (e["dram_bytes_per_launch"], e.get("source")) if e else (None, None)
 
 
-def cpu_port_throughput(n_sample, threads):
-    """C++ restatement of the reference render (oracle/) on `threads` host threads over the first
-    n_sample patches of the workload; returns voice-samples/s."""
+def cpu_port_throughput(n_sample, threads, seed=SEED):
+    """C++ restatement of the reference render (oracle/) on `threads` host threads over the first n_sample patches of the
+    workload; returns voice-samples/s.  Touches nothing of the product (no libgooey_b200 import, no .so load)."""
     import oracle_lib as O
-    from workloads import drum_sweep_patches
-    patches, vel, _ = drum_sweep_patches(n_sample, seed=SEED)
+    from workloads import drum_sweep_raw
+    patches, vel, _ = drum_sweep_raw(n_sample, seed=seed)
     trig = [(i, 0, float(vel[i])) for i in range(n_sample)]
     O.render_voices(patches[:4], 2048, triggers=trig[:4], threads=1)  # warm the library
     t0 = time.perf_counter()
@@ -144,11 +161,12 @@ def cpu_port_throughput(n_sample, threads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
     cores = os.cpu_count() or 1
-    n_sample = 32 * cores
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt = cpu_port_throughput(n_sample, cores)
+        # warm-up steps render a 1/8 sample (page-touch, thread pool); timed steps the whole sweep
+        v, dt = cpu_port_throughput(N_PATCHES if i >= args.warmup else N_PATCHES // 8, cores)
         if i >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
@@ -157,24 +175,176 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "voice-samples/sec", "value": value, "unit": "voice-samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 4096-patch drum sweep (kick/snare/hihat/tom), 88200 samples each @44.1kHz", "seed": SEED},
+        "config": workload_config(world),
         "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": cores, "kind": "port",
-                         "sample": f"first {n_sample} of the 4096 patches x {FRAMES} frames per step, one voice per worker thread"},
+                         "sample": f"all {N_PATCHES} patches x {FRAMES} frames per timed step, one voice per worker thread, {cores} threads"},
         "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "Rust reference not buildable in this image (no cargo/rustc); C++ restatement of the reference render (oracle/), all host cores",
+        "gpu_launches": 0,
+        "note": "Rust reference not buildable in this image (no cargo/rustc); C++ restatement of the reference render (oracle/), all host cores; libgooey_b200 is neither imported nor loaded in this arm",
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- extra configurations ----
+def _c3_script(S):
+    def script(e, i):
+        S.random_voice_params(e, 1000 + i)
+        S.pattern_engine(e, 2000 + i, swing=None if i % 2 == 0 else 0.4 + 0.3 * ((i * 37) % 100) / 100.0)
+    return script
+
+
+def _c5_script(S):
+    def script(e, i):
+        S.random_voice_params(e, 1000 + i)
+        S.pattern_engine(e, 2000 + i, swing=None if i % 2 == 0 else 0.4 + 0.3 * ((i * 37) % 100) / 100.0)
+        S.fx_chain(e, 3000 + i, plate=False)
+    return script
+
+
+def _rel_err(got, want):
+    """max |got - want| / max(1, |want|) over finite frames; non-finite frames must coincide (the reference itself overflows
+    for a few random snare patches: Chamberlin SVF at high cutoff x low resonance)."""
+    fin = np.isfinite(want)
+    if not np.array_equal(fin, np.isfinite(got)):
+        return float("inf")
+    return float((np.abs(got[fin] - want[fin]) / np.maximum(1.0, np.abs(want[fin]))).max()) if fin.any() else 0.0
+
+
+def engine_config(L, torch, dev, ids, script, bars, check_ids, peak, bytes_per_engine_sample, label):
+    """Bounce the engines `ids` (global indices; script(e, i) configures engine i) for `bars` bars: once device-resident
+    (gooey_batch_bounce_device), once through the host-buffer ABI (gooey_batch_bounce).  Parity of `check_ids` vs the oracle."""
+    from libgooey_b200 import engine as G
+    import oracle_lib as O
+    n = len(ids)
+    t0 = time.perf_counter()
+    engines = [G.Engine() for _ in range(n)]          # on the device selected with gooey_b200_set_device
+    for e, i in zip(engines, ids):
+        script(e, int(i))
+    setup_s = time.perf_counter() - t0
+    frames = int(round(bars * 4 * 0.5 * SR))
+    stride = (frames + 3) & ~3
+    out = torch.empty((n, stride), dtype=torch.float32, device=f"cuda:{dev}")
+    L.gooey_b200_kernel_stats_reset()
+    launches0 = L.gooey_b200_launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got_frames = G.batch_bounce_device(engines, bars, out.data_ptr(), stride)
+    torch.cuda.synchronize()
+    wall_dev = time.perf_counter() - t0
+    dev_ms = float(L.gooey_b200_last_kernel_ms())
+    launches = int(L.gooey_b200_launch_count() - launches0)
+    assert got_frames == frames
+    kst = kernel_stats(L)
+    first = {int(i): out[k, :frames].cpu().numpy() for k, i in enumerate(ids) if int(i) in check_ids}
+    del out
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    host = G.batch_bounce(engines, bars)           # second bounce of the same engines: state carried over, clock reset
+    wall_e2e = time.perf_counter() - t0
+    errs, unstable = {}, []
+    for k, i in enumerate(ids):
+        if int(i) not in check_ids:
+            continue
+        o = O.oracle_engine()
+        script(o, int(i))
+        w1 = o.bounce_to_buffer(bars)
+        w2 = o.bounce_to_buffer(bars)
+        o.close()
+        # Some random snare patches drive the reference's Chamberlin SVF unstable (high cutoff x low resonance): the
+        # reference's own output then grows past 1e3 (up to 1e8 on a second bounce) and is chaotic, so a sample-level
+        # comparison is meaningless there; such engines are listed, not compared.
+        if not (np.isfinite(w1).all() and np.isfinite(w2).all() and max(np.abs(w1).max(), np.abs(w2).max()) < 1e3):
+            unstable.append(int(i))
+            continue
+        errs[int(i)] = max(_rel_err(first[int(i)], w1), _rel_err(host[k], w2))
+    for e in engines:
+        e.close()
+    res = {"workload": label, "engines": n, "frames": frames, "setup_s": round(setup_s, 2), "device_ms": dev_ms,
+           "wall_ms_device_resident": wall_dev * 1e3, "e2e_ms": wall_e2e * 1e3, "gpu_launches": launches,
+           "engine_samples_per_s": n * frames / (dev_ms * 1e-3), "voice_samples_per_s": 5 * n * frames / (dev_ms * 1e-3),
+           "e2e_engine_samples_per_s": n * frames / wall_e2e, "d2h_bytes": n * frames * 4,
+           "parity_max_err_vs_oracle": max(errs.values()) if errs else None, "parity_engines_checked": sorted(errs),
+           "reference_unstable_engines_skipped": unstable}
+    if bytes_per_engine_sample:
+        mk = kst.get("mix_kernel")
+        if mk:
+            achieved = mk["voice_frames_per_launch"] * bytes_per_engine_sample / (mk["avg_ms"] * 1e-3) / 1e9
+            res["roofline"] = {"bound": "hbm", "kernel": "mix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                               "algorithmic_bytes_per_engine_sample": bytes_per_engine_sample, "launches": mk["launches"], "avg_launch_ms": mk["avg_ms"], "traffic": None}
+    res["kernels"] = {k: {"launches": v["launches"], "total_ms": round(v["total_ms"], 3)} for k, v in kst.items()}
+    return res
+
+
+def config_c1(L):
+    """BASELINE.json configs[0]: single kick voice, default params, 1 s at 44.1 kHz through the bounce.rs mirror."""
+    from libgooey_b200 import bounce as B
+    import oracle_lib as O
+    pattern = [i == 0 for i in range(16)]
+
+    def fresh():
+        engine = B.Engine(SR)
+        engine.set_bpm(120.0)
+        kick = B.KickDrum(SR)
+        engine.add_instrument("kick", kick)
+        engine.add_sequencer(B.Sequencer.with_pattern(120.0, SR, pattern, "kick"))
+        return engine, kick
+    B.bounce_to_buffer(fresh()[0], B.BounceLength.Samples(44100))       # warm (allocations, module load)
+    engine, kick = fresh()
+    t0 = time.perf_counter()
+    got = B.bounce_to_buffer(engine, B.BounceLength.Samples(44100))
+    wall = time.perf_counter() - t0
+    dev_ms = float(L.gooey_b200_last_kernel_ms())
+    want = O.rust_bounce([("kick", kick)], [("kick", pattern, [1.0] * 16)], 44100)
+    return {"workload": "C1: single kick voice, default params, 1 s @44.1kHz via bounce_to_buffer(Engine, Samples(44100))", "frames": 44100,
+            "device_ms": dev_ms, "e2e_ms": wall * 1e3, "voice_samples_per_s": 44100 / (dev_ms * 1e-3), "e2e_voice_samples_per_s": 44100 / wall,
+            "parity_max_err_vs_oracle": float(np.abs(got - want).max()), "note": "one voice: latency of one render call, not throughput"}
+
+
+def config_c4(L):
+    """BASELINE.json configs[3]: granulators over one shared synthetic 60 s source."""
+    from libgooey_b200 import engine as G
+    import oracle_lib as O
+    n_eng, frames = C4_ENGINES, int(C4_SECONDS * SR)
+    n = np.arange(2646000, dtype=np.float64)
+    rng = np.random.default_rng(SEED)
+    src = (0.5 * np.sin(2 * np.pi * 220.0 * n / SR) * (0.5 + 0.5 * np.sin(2 * np.pi * 0.1 * n / SR)) + 0.1 * rng.uniform(-1, 1, len(n))).astype(np.float32)
+    pitch = rng.uniform(0.3, 0.7, n_eng); tex = rng.random(n_eng)
+
+    def script(e, i, first=None):
+        assert (e.granulator_set_buffer(src, SR) if first is None else e.granulator_share_buffer(first))
+        for p, v in [(4, 1.0), (1, 0.55), (2, 0.5), (3, float(pitch[i])), (6, 0.3), (5, float(tex[i])), (9, 0.3), (10, 0.3), (7, 1.0)]:
+            e.granulator_set_param(p, v)
+        e.granulator_set_seed(i + 1)
+        e.granulator_snap_params()
+        e.granulator_trigger(1.0)
+    engines = [G.Engine() for _ in range(n_eng)]
+    for i, e in enumerate(engines):
+        script(e, i, None if i == 0 else engines[0])
+    t0 = time.perf_counter()
+    out = G.batch_render(engines, frames)
+    wall = time.perf_counter() - t0
+    dev_ms = float(L.gooey_b200_last_kernel_ms())
+    i = n_eng // 2
+    o = O.oracle_engine(); script(o, i); want = o.render(frames); o.close()
+    err = float(np.abs(out[i] - want).max())
+    for e in engines:
+        e.close()
+    return {"workload": f"C4: {n_eng} granulators x {C4_SECONDS:g} s, 64+16 grain slots each (pool saturated, >= 100k concurrent grains), one shared 60 s source, stereo render",
+            "engines": n_eng, "frames": frames, "device_ms": dev_ms, "e2e_ms": wall * 1e3, "engine_samples_per_s": n_eng * frames / (dev_ms * 1e-3),
+            "grain_slot_samples_per_s": 80 * n_eng * frames / (dev_ms * 1e-3), "e2e_engine_samples_per_s": n_eng * frames / wall,
+            "d2h_bytes": n_eng * frames * 8, "parity_max_err_vs_oracle": err, "parity_engines_checked": [i]}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
-    from libgooey_b200 import lib, voices as V
+    from libgooey_b200 import lib, voices as V, shard
     from workloads import drum_sweep_patches
     L = lib()
     if L.gooey_b200_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device — libgooey_b200 has no CPU fallback")
     dev = local_rank
     torch.cuda.set_device(dev)
+    L.gooey_b200_set_device(dev)
     dist = None
     if world > 1:
         # NCCL prints its version banner (and any NCCL_DEBUG output) to stdout; stdout carries exactly one JSON line
@@ -189,14 +359,24 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    patches, vel, kinds = drum_sweep_patches(N_PATCHES, seed=SEED + rank)
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{dev}")
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    # The global batch is world x 4096 patches; the shard plan interleaves the four cost classes and hands this rank
+    # its contiguous block (libgooey_b200/shard.py, the plan tests/test_shard_cpu.py checks under gloo).
+    g_patches, g_vel, g_kinds = drum_sweep_patches(N_PATCHES * world, seed=SEED)
+    mine = shard.shard_indices(g_kinds, rank, world)
+    assert len(mine) == N_PATCHES
+    patches = [g_patches[i] for i in mine]
+    vel = np.ascontiguousarray(g_vel[mine])
     batch = V.VoiceBatch(patches, SR, device=dev)
     stride = FRAMES  # multiple of 4
     out_dev = torch.empty((N_PATCHES, stride), dtype=torch.float32, device=f"cuda:{dev}")
     out_host = torch.empty((N_PATCHES, FRAMES), dtype=torch.float32).pin_memory()
     out_np = out_host.numpy()
-
-    launches0 = L.gooey_b200_launch_count()
 
     def step_device():
         batch.trigger_all(0, vel)
@@ -215,18 +395,16 @@ def run_ours(args, rank, world, local_rank):
     sampler.mark()                       # only rows sampled from here on (the timed region) are reported
     L.gooey_b200_kernel_stats_reset()
     launches_before = L.gooey_b200_launch_count()
-    t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
         dev_ms += step_device()
     barrier()
-    wall_dev = time.perf_counter() - t0
     launches = L.gooey_b200_launch_count() - launches_before
     clocks = sampler.stop()
     kstats = kernel_stats(L)
 
     # end-to-end through the C ABI with host buffers
-    for _ in range(max(args.warmup, 3 if world == 1 else 6)):   # the host-buffer path has its own first-call costs (staging allocations, page touch; with 8 ranks draining at once the first steps were 160 / 140 / 100 ms)
+    for _ in range(max(args.warmup, 3 if world == 1 else 6)):   # the host-buffer path has its own first-call costs (staging allocations, page touch)
         step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -239,28 +417,46 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     wall_e2e = time.perf_counter() - t0
     checksum = float(np.abs(out_np[:, ::97]).sum())
+    dev_ms, wall_e2e = max_over_ranks([dev_ms, wall_e2e])
+    batch.close()
+    del out_dev, out_host
+    torch.cuda.empty_cache()
 
-    t = torch.tensor([dev_ms, wall_dev, wall_e2e], dtype=torch.float64, device=f"cuda:{dev}")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall_dev, wall_e2e = (float(x) for x in t.tolist())
+    peak, peak_kind = measured_peaks()
+    extra = {}
+    if args.configs == "all":
+        import engine_scripts as S
+        if world == 1:
+            extra["C1"] = config_c1(L)
+            ids = np.arange(C3_ENGINES)
+            extra["C3"] = engine_config(L, torch, dev, ids, _c3_script(S), C3_BARS, {0, 1, C3_ENGINES - 1}, peak, None,
+                                        f"C3: {C3_ENGINES} FFI engines x {C3_BARS} bars @120 BPM, 5 x 16-step patterns (velocities, note overrides, swing on odd engines), mixer graph with a 5th track, mono bounce")
+            extra["C4"] = config_c4(L)
+        # C5: the global batch is world x 8192 engines of one cost class; this rank bounces its contiguous shard
+        g_ids = shard.shard_indices(np.zeros(C5_ENGINES_PER_GPU * world, np.int64), rank, world)
+        barrier()
+        c5 = engine_config(L, torch, dev, g_ids, _c5_script(S), C5_BARS, {int(x) for x in g_ids[:4]}, peak, C5_BYTES_PER_ENGINE_SAMPLE,
+                           f"C5: {C5_ENGINES_PER_GPU * world} drum+bass FFI engines ({C5_ENGINES_PER_GPU} per GPU, contiguous shards, no collective) x {C5_BARS} bars with tilt -> delay -> spring reverb global chain, mono bounce")
+        barrier()
+        c5_dev, c5_e2e, c5_err = max_over_ranks([c5["device_ms"], c5["e2e_ms"], c5["parity_max_err_vs_oracle"] or 0.0])
+        tot = C5_ENGINES_PER_GPU * world * c5["frames"]
+        c5.update({"engines": C5_ENGINES_PER_GPU * world, "n_gpus": world, "device_ms": c5_dev, "e2e_ms": c5_e2e,
+                   "engine_samples_per_s": tot / (c5_dev * 1e-3), "voice_samples_per_s": 5 * tot / (c5_dev * 1e-3),
+                   "e2e_engine_samples_per_s": tot / (c5_e2e * 1e-3), "d2h_bytes": tot * 4, "parity_max_err_vs_oracle": c5_err,
+                   "timing": "max over ranks (device: CUDA events inside the library; e2e: host wall clock around gooey_batch_bounce)"})
+        extra["C5"] = c5
 
     if rank == 0:
         units = world * N_PATCHES * FRAMES * args.steps
         value = units / (dev_ms * 1e-3)
         e2e = units / wall_e2e
-        peak, peak_kind = measured_peaks()
         # dominant kernel = the back-end launch with the largest share of device time.  achieved = algorithmic bytes per
         # launch (4 B stored per voice-frame) / its mean launch duration, both measured over the timed region.
-        # (The four buckets overlap on the device, so live durations include contention; the serialised ncu launch list
-        # in profiles/ ranks wave_kernel<TomW> first, and it is kept as the dominant kernel while it is within 10 % of the
-        # live maximum so that both views name the same kernel.)
-        dom = max(kstats, key=lambda k: kstats[k]["total_ms"]) if kstats else None
-        if dom and "wave_kernel<TomW>" in kstats and kstats["wave_kernel<TomW>"]["total_ms"] >= 0.9 * kstats[dom]["total_ms"]:
-            dom = "wave_kernel<TomW>"
+        back = {k: v for k, v in kstats.items() if not k.startswith("mix")}
+        dom = max(back, key=lambda k: back[k]["total_ms"]) if back else None
         if dom:
-            bytes_per_launch = kstats[dom]["voice_frames_per_launch"] * BYTES_PER_VOICE_SAMPLE
-            achieved = bytes_per_launch / (kstats[dom]["avg_ms"] * 1e-3) / 1e9
+            bytes_per_launch = back[dom]["voice_frames_per_launch"] * BYTES_PER_VOICE_SAMPLE
+            achieved = bytes_per_launch / (back[dom]["avg_ms"] * 1e-3) / 1e9
         else:
             bytes_per_launch, achieved = None, N_PATCHES * FRAMES * BYTES_PER_VOICE_SAMPLE / (dev_ms / args.steps * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic(dom) if dom else (None, None)
@@ -271,29 +467,25 @@ def run_ours(args, rank, world, local_rank):
             "metric": "voice-samples/sec", "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 4096-patch drum sweep (kick/snare/hihat/tom), 88200 samples each @44.1kHz", "seed": SEED,
-                       "voices_per_gpu": N_PATCHES, "frames": FRAMES, "sample_rate": SR,
-                       "l2": "output 1.44 GB per step >> 126 MB L2; nothing is re-read between steps",
-                       "parallelism": f"independent voice shards x{world}, no collective"},
+            "config": workload_config(world),
             "e2e": {"value": e2e, "unit": "voice-samples/s", "h2d_bytes_per_step": int(world * N_PATCHES * (16 + 12)),
                     "d2h_bytes_per_step": int(world * N_PATCHES * FRAMES * 4), "ms_per_step": wall_e2e / args.steps * 1e3,
                     "ms_each_step_rank0": [round(x, 2) for x in e2e_steps],
                     "kernel_ms_each_step_rank0": [round(x, 2) for x in e2e_kernel_ms]},
             "gpu_launches": int(launches),
-            "wall_ms_per_step_device_resident": wall_dev / args.steps * 1e3,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_kind": peak_kind, "kernel": dom, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "avg_launch_ms": kstats[dom]["avg_ms"] if dom else None, "traffic_source": traffic_src,
+                         "avg_launch_ms": back[dom]["avg_ms"] if dom else None, "traffic_source": traffic_src,
                          "whole_step_store_gbs": N_PATCHES * FRAMES * BYTES_PER_VOICE_SAMPLE / (dev_ms / args.steps * 1e-3) / 1e9,
-                         "note": "HBM is the contract's roofline for this store-only path, but the voice kernels are bound by dependent-issue latency (replayed recurrences + shuffle scans), not by bytes: see DESIGN.md section 4"},
+                         "note": "HBM is the contract's roofline for this store-only path, but the voice kernels are bound by instruction issue and dependent-issue latency (exact-order recurrences), not by bytes: see DESIGN.md section 4"},
             "kernels": kstats,
             "cpu_baseline": {"value": cpu_v, "unit": "voice-samples/s", "cores": cores, "kind": "port",
                              "sample": f"first {n_sample} of the 4096 patches x {FRAMES} frames, {cores} threads, {cpu_dt:.1f} s"},
             "checksum": checksum,
+            "configs": extra,
         }
         print(json.dumps(line), flush=True)
-    batch.close()
     if dist:
         dist.destroy_process_group()
 
@@ -304,17 +496,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--configs", default="all", choices=["all", "c2"], help="c2: headline only (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)      # CPU only: builds / loads oracle/ and nothing else
+        return
     import __graft_entry__ as g
     if rank == 0 or not os.path.exists(os.path.join(ROOT, "libgooey_b200", "lib", "libgooey_b200.so")):
         g.build()
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_ours(args, rank, world, local_rank)
+    run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -67,6 +67,8 @@ float gooey_b200_last_kernel_ms(void);
 /* Accumulated device time of one back-end kernel ("wave_kernel<KickW>" / "<SnareW>" / "<HatW>" / "<TomW>") since load or
  * the last reset: launches, summed launch durations (ms, CUDA events on the launching stream) and voice-frames written. */
 int gooey_b200_kernel_stat(const char* kernel, uint64_t* launches, double* total_ms, double* voice_frames);
+/* ';'-separated names of the kernels that have statistics (thread-local storage, valid until the next call) */
+const char* gooey_b200_kernel_stat_names(void);
 void gooey_b200_kernel_stats_reset(void);
 
 /* Voice-level batch: n voices built `with_config`, then driven by per-voice events. */

@@ -115,6 +115,18 @@ struct EngineBank {
   DevBuf<gd::VoiceEvent> d_mix_eventss[2];
   std::recursive_mutex mu;   // every use of the bank's shared buffers / streams, held for a whole render call
   float last_ms = 0.0f;
+  // timing brackets of the effect mixer of piece p of the last render (on mix_stream) and its engine-frames
+  std::vector<cudaEvent_t> mixT0, mixT1; std::vector<double> mix_units; int mix_timed = 0;
+  void collect_mix_stats() {     // after the streams have been synchronised
+    std::lock_guard<std::mutex> lk(kernel_stats_mutex());
+    KernelStat& k = kernel_stats()["mix_kernel"];
+    for (int i = 0; i < mix_timed; i++) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, mixT0[i], mixT1[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+      k.launches++; k.ms += ms; k.voice_frames += mix_units[i];
+    }
+    mix_timed = 0;
+  }
   EngineBank(int dev, float sr_) : device(dev), sr(sr_) {
     rc = gd::make_rate_ctx(sr); geo = make_fx_geom(sr);
     GH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -502,7 +514,11 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       static std::set<int> opted;      // per device: allow the mix kernel its dynamic shared memory (> 48 KB with the static tiles)
       if (opted.insert(B.device).second) GH_CUDA(cudaFuncSetAttribute(gd::mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gd::MIX_DYN_SMEM));
     }
+    if (B.mixT0.size() <= pc) { cudaEvent_t a, b; GH_CUDA(cudaEventCreate(&a)); GH_CUDA(cudaEventCreate(&b)); B.mixT0.push_back(a); B.mixT1.push_back(b); B.mix_units.push_back(0.0); }
+    GH_CUDA(cudaEventRecord(B.mixT0[pc], ms));
     gd::mix_kernel<<<(n + 31) / 32, 32, gd::MIX_DYN_SMEM, ms>>>(M);
+    GH_CUDA(cudaEventRecord(B.mixT1[pc], ms));
+    B.mix_units[pc] = (double)n * nf; B.mix_timed = (int)pc + 1;
     g_launches.fetch_add(3, std::memory_order_relaxed);
     GH_CUDA(cudaGetLastError());
     GH_CUDA(cudaEventRecord(B.ev_mixed[vb], ms));

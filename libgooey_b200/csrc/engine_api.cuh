@@ -440,6 +440,8 @@ static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t f
     if (out_rows) for (uint32_t i = 0; i < n; i++) GH_CUDA(cudaMemcpyAsync(out_rows[i], dst + (size_t)i * stride, row * 4, cudaMemcpyDeviceToHost, B.stream));
     GH_CUDA(cudaStreamSynchronize(B.stream));
     GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, B.ev0, B.ev1));
+    B.collect_mix_stats();
+    B.voices.collect_stats();
     return GOOEY_E_OK;
   } catch (const gh::BadBatch& ex) {
     gh::set_error(ex.what());

@@ -205,6 +205,13 @@ int gooey_b200_kernel_stat(const char* kernel, uint64_t* launches, double* total
   if (voice_frames) *voice_frames = k.voice_frames;
   return GOOEY_E_OK;
 }
+const char* gooey_b200_kernel_stat_names(void) {
+  static thread_local std::string names;
+  std::lock_guard<std::mutex> lk(gh::kernel_stats_mutex());
+  names.clear();
+  for (const auto& kv : gh::kernel_stats()) { if (!names.empty()) names += ';'; names += kv.first; }
+  return names.c_str();
+}
 void gooey_b200_kernel_stats_reset(void) { std::lock_guard<std::mutex> lk(gh::kernel_stats_mutex()); gh::kernel_stats().clear(); }
 
 int gooey_voice_batch_new(float sample_rate, uint32_t n_voices, const GooeyVoicePatch* patches, int device, GooeyVoiceBatch** out_batch) {

@@ -752,6 +752,7 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
     } else {
       // interleave L/R: row r, frame f -> out[row*stride + 2*(f0+f) + ch]; 64 consecutive floats per row
       for (int r = 0; r < n_rows; r++) {
+        if (!((row_mask >> r) & 1u)) continue;     // rows of the time-parallel mixer (or past the end) are not this kernel's
         const long long row = L.out_rows ? (long long)L.out_rows[warp_i0 + r] : (long long)(warp_i0 + r);
         float* dst = L.out + row * L.out_stride + 2LL * f0;
         for (int k = lane; k < 2 * nf; k += 32) dst[k] = (k & 1) ? tout[1][r * 33 + (k >> 1)] : tout[0][r * 33 + (k >> 1)];

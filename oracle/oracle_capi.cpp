@@ -102,6 +102,22 @@ float orc_max_curve(float p, float c) { return max_curve(p, c); }
 void orc_halfband_coefs(float* out8) { const float* c = halfband_coefs(); for (int i = 0; i < 8; i++) out8[i] = c[i]; }
 float orc_smoother_coeff(float sr, float ms) { return SmoothedParam::calculate_coeff(sr, ms); }
 void orc_click_table(float* out64) { for (int i = 0; i < 64; i++) out64[i] = TOM_IMPULSE[i]; }
+// Impulse responses of the half-band pair, in the layout rust/examples/dump_golden.rs writes (tests/golden/ref):
+// up[2n], up[2n+1] = Upsampler8::process(impulse[n]); down[0..n) = Downsampler8 fed ((1,0),(0,0)...), down[n..2n) a fresh one fed ((0,1),(0,0)...)
+void orc_halfband_impulse(float* up, float* down, uint32_t n) {
+  Upsampler8 u;
+  for (uint32_t i = 0; i < n; i++) u.process(i == 0 ? 1.0f : 0.0f, up[2 * i], up[2 * i + 1]);
+  Downsampler8 d0, d1;
+  for (uint32_t i = 0; i < n; i++) down[i] = d0.process(i == 0 ? 1.0f : 0.0f, 0.0f);
+  for (uint32_t i = 0; i < n; i++) down[n + i] = d1.process(0.0f, i == 0 ? 1.0f : 0.0f);
+}
+// Oversampler2x then Oversampler4x around tanh(drive x) over the same n samples: out[0..n) and out[n..2n)
+void orc_oversampler_tanh(const float* in, float* out, uint32_t n, float drive) {
+  Oversampler o2, o4;
+  o2.set_mode(OversamplingMode::X2); o4.set_mode(OversamplingMode::X4);
+  for (uint32_t i = 0; i < n; i++) out[i] = o2.process(in[i], [&](float x) { return tanhf(x * drive); });
+  for (uint32_t i = 0; i < n; i++) out[n + i] = o4.process(in[i], [&](float x) { return tanhf(x * drive); });
+}
 // Oversampler: mode 0/2/4, f(x) = tanh(x*drive) (drive<=0: identity); processes n samples.
 void orc_oversample(int mode, float drive, const float* in, float* out, uint32_t n) {
   Oversampler os;

@@ -33,15 +33,34 @@ def lib():
     return _lib
 
 
+class OrcPatch(ctypes.Structure):
+    """Same layout as GooeyVoicePatch (include/gooey_batch.h); lets CPU-only callers avoid the product package."""
+    _fields_ = [("instrument", ctypes.c_uint32), ("aux", ctypes.c_uint32), ("params", ctypes.c_float * 24)]
+
+
+def patch_array(patches):
+    """ctypes array of patches from either product VoicePatch structs or raw (instrument, aux, params) tuples."""
+    if isinstance(patches, ctypes.Array):
+        return patches
+    if patches and isinstance(patches[0], tuple):
+        arr = (OrcPatch * len(patches))()
+        for i, (inst, aux, params) in enumerate(patches):
+            arr[i].instrument = inst
+            arr[i].aux = aux
+            for j, x in enumerate(params):
+                arr[i].params[j] = x
+        return arr
+    return (type(patches[0]) * len(patches))(*patches)
+
+
 def _p(a, t):
     return a.ctypes.data_as(ctypes.POINTER(t))
 
 
 def render_voices(patches, frames, triggers=(), params=(), sample_rate=44100.0, threads=1):
     """triggers: (voice, frame, velocity); params: (voice, frame, ffi_param, value, snap)."""
-    from libgooey_b200._lib import VoicePatch
     n = len(patches)
-    arr = patches if isinstance(patches, ctypes.Array) else (VoicePatch * n)(*patches)
+    arr = patch_array(patches)
     ev = [(v, f, 0, 0, vel) for (v, f, vel) in triggers] + [(v, f, 2 if s else 1, p, x) for (v, f, p, x, s) in params]
     ev.sort(key=lambda e: (e[0], e[1]))
     m = len(ev)
@@ -88,3 +107,35 @@ def bounce_many(script, indices, bars):
         return i, out
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
         return dict(ex.map(one, list(indices)))
+
+
+def rust_bounce(instruments, sequencers, samples, master=None, limiter=True, bpm=120.0, sample_rate=44100.0):
+    """Oracle RustEngine (src/engine/mod.rs + src/bounce.rs restated): instruments = [(name, obj with .patch)],
+    sequencers = [(name, enabled[16], velocity[16])]; returns the mono bounce of `samples` frames."""
+    L = lib()
+    c = ctypes
+    SR = sample_rate
+    L.orc_rust_engine_new.restype = c.c_void_p
+    L.orc_rust_engine_new.argtypes = [c.c_float]
+    L.orc_rust_engine_free.argtypes = [c.c_void_p]
+    L.orc_rust_engine_add_instrument.argtypes = [c.c_void_p, c.c_char_p, c.c_void_p]
+    L.orc_rust_engine_add_sequencer.argtypes = [c.c_void_p, c.c_char_p, c.c_void_p, c.c_void_p, c.c_uint32]
+    L.orc_rust_engine_set_bpm.argtypes = [c.c_void_p, c.c_float]
+    L.orc_rust_engine_set_master_gain.argtypes = [c.c_void_p, c.c_float]
+    L.orc_rust_engine_clear_global_effects.argtypes = [c.c_void_p]
+    L.orc_rust_engine_bounce_samples.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p]
+    e = L.orc_rust_engine_new(SR)
+    L.orc_rust_engine_set_bpm(e, bpm)
+    for name, inst in instruments:
+        assert L.orc_rust_engine_add_instrument(e, name.encode(), c.byref(inst.patch)) == 0
+    for name, en, ve in sequencers:
+        en = np.asarray(en, np.uint8); ve = np.asarray(ve, np.float32)
+        L.orc_rust_engine_add_sequencer(e, name.encode(), en.ctypes.data, ve.ctypes.data, len(en))
+    if master is not None:
+        L.orc_rust_engine_set_master_gain(e, master)
+    if not limiter:
+        L.orc_rust_engine_clear_global_effects(e)
+    out = np.zeros(samples, np.float32)
+    L.orc_rust_engine_bounce_samples(e, samples, out.ctypes.data)
+    L.orc_rust_engine_free(e)
+    return out

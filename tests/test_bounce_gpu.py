@@ -26,33 +26,7 @@ def setup_engine(pattern_on=(0, 4, 8, 12)):
     return engine
 
 
-def oracle_rust_bounce(instruments, sequencers, samples, master=None, limiter=True, bpm=120.0):
-    L = O.lib()
-    c = ctypes
-    L.orc_rust_engine_new.restype = c.c_void_p
-    L.orc_rust_engine_new.argtypes = [c.c_float]
-    L.orc_rust_engine_free.argtypes = [c.c_void_p]
-    L.orc_rust_engine_add_instrument.argtypes = [c.c_void_p, c.c_char_p, c.c_void_p]
-    L.orc_rust_engine_add_sequencer.argtypes = [c.c_void_p, c.c_char_p, c.c_void_p, c.c_void_p, c.c_uint32]
-    L.orc_rust_engine_set_bpm.argtypes = [c.c_void_p, c.c_float]
-    L.orc_rust_engine_set_master_gain.argtypes = [c.c_void_p, c.c_float]
-    L.orc_rust_engine_clear_global_effects.argtypes = [c.c_void_p]
-    L.orc_rust_engine_bounce_samples.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p]
-    e = L.orc_rust_engine_new(SR)
-    L.orc_rust_engine_set_bpm(e, bpm)
-    for name, inst in instruments:
-        assert L.orc_rust_engine_add_instrument(e, name.encode(), c.byref(inst.patch)) == 0
-    for name, en, ve in sequencers:
-        en = np.asarray(en, np.uint8); ve = np.asarray(ve, np.float32)
-        L.orc_rust_engine_add_sequencer(e, name.encode(), en.ctypes.data, ve.ctypes.data, len(en))
-    if master is not None:
-        L.orc_rust_engine_set_master_gain(e, master)
-    if not limiter:
-        L.orc_rust_engine_clear_global_effects(e)
-    out = np.zeros(samples, np.float32)
-    L.orc_rust_engine_bounce_samples(e, samples, out.ctypes.data)
-    L.orc_rust_engine_free(e)
-    return out
+oracle_rust_bounce = O.rust_bounce
 
 
 def test_bounce_correct_length():

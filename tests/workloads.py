@@ -1,13 +1,33 @@
 """Deterministic synthetic workloads shared by tests and bench.py (seed 0x600E7)."""
 import numpy as np
 
-from libgooey_b200 import voices as V
+KICK, SNARE, HIHAT, TOM = 0, 1, 2, 3
+# KickConfig::punch (src/instruments/kick.rs:257-350); the same table as libgooey_b200.voices.KICK_PRESETS["punch"] — kept here
+# so that the CPU reference arm of bench.py can build the workload without importing the product package.
+_KICK_PUNCH = [0.50, 0.20, 1.00, 0.20, 0.12, 0.60, 0.10, 0.85, 0.24, 1.00, 0.07, 0.11, 0.42, 0.20, 0.00, 0.47, 0.12, 0.02]
+
+
+def drum_sweep_raw(n, seed=0x600E7, exact_tier=False):
+    """C2 as plain data: [(instrument, aux, params), ...], velocities, kinds.  n patches cycling kick/snare/hihat/tom,
+    every FFI-reachable parameter ~U[0,1), tuning fixed at neutral, one trigger at frame 0 with velocity U[0.3,1].
+    exact_tier forces overdrive = 0 so the reconstructed half-band oversampler is never exercised."""
+    class V:
+        KICK, SNARE, HIHAT, TOM = KICK, SNARE, HIHAT, TOM
+        KICK_PRESETS = {"punch": _KICK_PUNCH}
+
+        @staticmethod
+        def patch(instrument, params=(), aux=0):
+            return (int(instrument), int(aux), [float(x) for x in params])
+    return _drum_sweep(V, n, seed, exact_tier)
 
 
 def drum_sweep_patches(n, seed=0x600E7, exact_tier=False):
-    """C2: n patches cycling kick/snare/hihat/tom, every FFI-reachable parameter ~U[0,1), tuning fixed at
-    neutral, one trigger at frame 0 with velocity U[0.3,1].  exact_tier forces overdrive = 0 so the
-    reconstructed half-band oversampler is never exercised."""
+    """drum_sweep_raw as GooeyVoicePatch structs of the product library."""
+    from libgooey_b200 import voices as V
+    return _drum_sweep(V, n, seed, exact_tier)
+
+
+def _drum_sweep(V, n, seed, exact_tier):
     rng = np.random.default_rng(seed)
     patches, kinds = [], []
     vel = rng.uniform(0.3, 1.0, n).astype(np.float32)
