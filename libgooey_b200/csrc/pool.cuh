@@ -16,6 +16,7 @@
 #include <mutex>
 #include "device_rt.h"
 #include "wave.cuh"
+#include "coop.cuh"
 #include "gran_wave.cuh"
 #include "bass_wave.cuh"
 #ifndef GOOEY_WAVE_CTA_WARPS_DEFAULT
@@ -146,27 +147,56 @@ ClockTable& clock_table(float sr);
 
 // Which voice types have a scan back-end (wave.cuh); the others use back_kernel (one voice per lane).  ID indexes the
 // per-type group width table below.
-template <class V> struct WaveOf { static constexpr bool has = false; static constexpr int ID = -1; };
-template <> struct WaveOf<gd::KickV> { static constexpr bool has = true; static constexpr int ID = 0; using w32 = gd::w32::KickW;
+template <class V> struct WaveOf { static constexpr bool has = false; static constexpr int ID = -1; static constexpr const char* name = "back_kernel"; };
+template <> struct WaveOf<gd::KickV> { static constexpr bool has = true; static constexpr int ID = 0; using w32 = gd::w32::KickW; static constexpr const char* name = "wave_kernel<KickW>";
 #ifdef GOOEY_WAVE_ALL_WIDTHS
   using w16 = gd::w16::KickW; using w8 = gd::w8::KickW;
 #endif
 };
-template <> struct WaveOf<gd::SnareV> { static constexpr bool has = true; static constexpr int ID = 1; using w32 = gd::w32::SnareW;
+template <> struct WaveOf<gd::SnareV> { static constexpr bool has = true; static constexpr int ID = 1; using w32 = gd::w32::SnareW; static constexpr const char* name = "wave_kernel<SnareW>";
 #ifdef GOOEY_WAVE_ALL_WIDTHS
   using w16 = gd::w16::SnareW; using w8 = gd::w8::SnareW;
 #endif
 };
-template <> struct WaveOf<gd::HatV> { static constexpr bool has = true; static constexpr int ID = 2; using w32 = gd::w32::HatW;
+template <> struct WaveOf<gd::HatV> { static constexpr bool has = true; static constexpr int ID = 2; using w32 = gd::w32::HatW; static constexpr const char* name = "wave_kernel<HatW>";
 #ifdef GOOEY_WAVE_ALL_WIDTHS
   using w16 = gd::w16::HatW; using w8 = gd::w8::HatW;
 #endif
 };
-template <> struct WaveOf<gd::TomV> { static constexpr bool has = true; static constexpr int ID = 3; using w32 = gd::w32::TomW;
+template <> struct WaveOf<gd::TomV> { static constexpr bool has = true; static constexpr int ID = 3; using w32 = gd::w32::TomW; static constexpr const char* name = "wave_kernel<TomW>";
 #ifdef GOOEY_WAVE_ALL_WIDTHS
   using w16 = gd::w16::TomW; using w8 = gd::w8::TomW;
 #endif
 };
+// Which voice types have a CTA-cooperative back end (coop.cuh).
+template <class V> struct CoopOf { static constexpr bool has = false; };
+template <> struct CoopOf<gd::TomV> { static constexpr bool has = true; using C = gd::coop::TomC; static constexpr const char* name = "coop_kernel<TomC>"; };
+// GOOEY_B200_BACKEND: "serial" = per-sample-order kernel C everywhere (the A/B reference of the parity tests), "wave" = the
+// warp-per-voice scan back end of round 1, anything else / unset = the CTA-cooperative back end where a type has one.
+inline bool wave_backend() { const char* e = getenv("GOOEY_B200_BACKEND"); return e && strcmp(e, "wave") == 0; }
+// Voices per CTA of the cooperative back end (4, 8 or 16; GOOEY_B200_COOP_NV overrides the default).
+inline int coop_nv() { const char* e = getenv("GOOEY_B200_COOP_NV"); if (e) { int v = atoi(e); if (v == 4 || v == 8 || v == 16) return v; } return 16; }
+// The cooperative back end issues ~3x fewer instructions per voice-frame but walks a block through barrier-separated phases,
+// so a voice's timeline is slower than in the warp-per-voice back end while voices are too few to fill the device with CTAs:
+// it takes over above this many voices of one type (measured crossover; GOOEY_B200_COOP_ABOVE overrides).
+inline int coop_above() { if (const char* e = getenv("GOOEY_B200_COOP_ABOVE")) { int v = atoi(e); if (v >= 0) return v; } return 4096; }
+template <class C, int NV> inline void coop_launch(int cnt, cudaStream_t s, const gd::VoiceLaunch& L) {
+  using SM = gd::coop::Smem<C, NV>;
+  auto kernel = gd::coop::coop_kernel<C, NV>;
+  static std::mutex mu;
+  static std::set<int> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.insert(dev).second) {
+      GH_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+      GH_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    }
+  }
+  kernel<<<(cnt + NV - 1) / NV, NV * 32, sizeof(SM), s>>>(L);
+}
+
 // Lanes per voice for kick / snare / hat / tom (see wave.cuh "Group width").  GOOEY_B200_WAVE_G="32,32,8,8" overrides
 // (tuning only; every width renders the same audio up to the scans' re-association noise).
 inline int wave_group_width(int id) {
@@ -251,6 +281,7 @@ template <class V> struct TypeRunner {
   std::vector<cudaEvent_t> evChunk;      // evChunk[i]: frames of chunk i are final in the output (fast-path voices)
   int chunk_frames = default_chunk_frames();
   int launched_chunks = 0;               // chunks of the most recent launch (0 = one undivided launch)
+  const char* backend_name = "back_kernel";   // the back-end kernel of the most recent launch (kernel statistics key)
   static int chunk_of(int frames, int chunk_frames) { return std::min(chunk_frames, (frames + 31) & ~31); }
   // Makes `s` wait until every voice of this bucket has written frames [i * chunk, (i + 1) * chunk) of the last launch.
   void wait_chunk(cudaStream_t s, int i) {
@@ -300,7 +331,8 @@ template <class V> struct TypeRunner {
     if (sS) cudaStreamDestroy(sS);
   }
   // After the launch's streams have been synchronised: add the back-end launches of the last call to the global table.
-  void collect_stats(const char* name) {
+  void collect_stats() {
+    const char* name = backend_name;
     if (launched_chunks <= 0) return;
     std::lock_guard<std::mutex> lk(kernel_stats_mutex());
     KernelStat& k = kernel_stats()[name];
@@ -365,7 +397,20 @@ template <class V> struct TypeRunner {
         if ((int)evT0.size() <= i) { cudaEvent_t e0, e1; GH_CUDA(cudaEventCreate(&e0)); GH_CUDA(cudaEventCreate(&e1)); evT0.push_back(e0); evT1.push_back(e1); timed_units.push_back(0.0); }
         timed_units[i] = (double)cnt * L.chunk_frames;
         GH_CUDA(cudaEventRecord(evT0[i], sC));
-        if constexpr (WaveOf<V>::has) {
+        bool launched = false;
+        backend_name = WaveOf<V>::has ? WaveOf<V>::name : "back_kernel";
+        if constexpr (CoopOf<V>::has) {
+          if (!serial_backend() && !wave_backend() && cnt >= coop_above()) {
+            const int nv = coop_nv();
+            if (nv == 4) coop_launch<typename CoopOf<V>::C, 4>(cnt, sC, L);
+            else if (nv == 8) coop_launch<typename CoopOf<V>::C, 8>(cnt, sC, L);
+            else coop_launch<typename CoopOf<V>::C, 16>(cnt, sC, L);
+            backend_name = CoopOf<V>::name;
+            launched = true;
+          }
+        }
+        if (launched) {}
+        else if constexpr (WaveOf<V>::has) {
           if (!serial_backend() && cnt < serial_above()) {
             const int g = wave_group_width(WaveOf<V>::ID);          // voices per warp = 32 / g, one warp per CTA
             const int warps = (cnt * g + 31) / 32;
