@@ -114,6 +114,14 @@ int gooey_batch_bounce(GooeyEngine* const* engines, uint32_t n, uint32_t bars, f
 /* Same, result left in device memory: out_dev[i * stride + frame]; all engines must share bpm (equal length).
  * *out_frames receives the length. */
 int gooey_batch_bounce_device(GooeyEngine* const* engines, uint32_t n, uint32_t bars, float* out_dev, size_t stride, uint32_t* out_frames);
+/* Mono bounce of n engines of equal length into ONE pitched host block: out_host[i * pitch + frame] (f32) or the 16-bit PCM
+ * of gooey_engine_bounce_to_wav (`(s * 32767).round() as i16`, ffi.rs:7968-7972, quantised on the device).  Finished pieces
+ * are drained while later ones render; engines may live on several devices (gooey_b200_set_device before gooey_engine_new):
+ * each device's share is rendered and drained by its own host thread, no collective. */
+int gooey_batch_bounce_host(GooeyEngine* const* engines, uint32_t n, uint32_t bars, float* out_host, size_t pitch, uint32_t* out_frames);
+int gooey_batch_bounce_pcm16(GooeyEngine* const* engines, uint32_t n, uint32_t bars, int16_t* out_host, size_t pitch, uint32_t* out_frames);
+/* gooey_engine_bounce_to_wav for n engines in one device pass (paths[i] = UTF-8 path of engine i's mono 16-bit WAV). */
+int gooey_batch_bounce_to_wav(GooeyEngine* const* engines, uint32_t n, uint32_t bars, const char* const* utf8_paths);
 /* Batch of gooey_engine_render: interleaved stereo, out_host[i * 2 * frames + 2 * f + ch]. */
 int gooey_batch_render(GooeyEngine* const* engines, uint32_t n, uint32_t frames, float* out_host);
 

@@ -83,6 +83,8 @@ int gooey_voice_batch_trigger_all(GooeyVoiceBatch* b, uint32_t frame, const floa
 int gooey_voice_batch_set_param(GooeyVoiceBatch* b, uint32_t voice, uint32_t frame, uint32_t param, float value, int snap);
 /* Render `frames` samples of every voice: out_host[v * frames + i] (host memory; copies are part of the call). */
 int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_host);
+/* Same as 16-bit PCM, `(s * 32767).round() as i16` (bounce.rs:105-113), quantised on the device: out_host[v * frames + i]. */
+int gooey_voice_batch_render_pcm16(GooeyVoiceBatch* b, uint32_t frames, int16_t* out_host);
 /* Same, leaving the result in device memory: out_dev[v * stride + i], stride >= frames. */
 int gooey_voice_batch_render_device(GooeyVoiceBatch* b, uint32_t frames, float* out_dev, size_t stride);
 
@@ -108,6 +110,11 @@ int gooey_rs_batch_bounce(GooeyRsBatch* b, uint32_t samples, float* out_host);
 int gooey_rs_batch_bounce_device(GooeyRsBatch* b, uint32_t samples, float* out_dev, size_t stride);
 /* Mono PCM WAV writer of bounce_to_wav (bounce.rs:80-133; ffi.rs:7942-7980): bit_depth 16 or 24, sample = round(s * (2^(bits-1) - 1)). */
 int gooey_b200_write_wav(const char* utf8_path, const float* samples, uint32_t n, uint32_t sample_rate, uint32_t bit_depth);
+
+/* Pinned host memory for the drains above, allocated on the NUMA node `device` is attached to (*out_numa_node: the node, or
+ * -1 when the placement could not be applied).  Free with gooey_b200_host_free. */
+void* gooey_b200_host_alloc(size_t bytes, int device, int* out_numa_node);
+void gooey_b200_host_free(void* p);
 
 /* Host-only (no device needed): frames and velocities at which a bounce of an engine with this tempo, swing and step
  * pattern fires its triggers — the schedule the host resolves into kernel event tables (reference:

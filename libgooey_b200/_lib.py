@@ -58,3 +58,35 @@ def lib():
 def check(rc):
     if rc != 0:
         raise GooeyError(f"libgooey_b200 error {rc}: {lib().gooey_b200_last_error().decode(errors='replace')}")
+
+
+class HostBuffer:
+    """Pinned host memory from gooey_b200_host_alloc: placed on the NUMA node the device hangs off, so that several ranks
+    draining at once do not all write into one node.  `.array(shape, dtype)` views it as numpy; free with close()."""
+
+    def __init__(self, nbytes, device=0):
+        L = lib()
+        L.gooey_b200_host_alloc.restype = ctypes.c_void_p
+        L.gooey_b200_host_alloc.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.gooey_b200_host_free.argtypes = [ctypes.c_void_p]
+        L.gooey_b200_host_free.restype = None
+        node = ctypes.c_int(-1)
+        self.nbytes = int(nbytes)
+        self.ptr = L.gooey_b200_host_alloc(self.nbytes, int(device), ctypes.byref(node))
+        if not self.ptr:
+            raise GooeyError("gooey_b200_host_alloc failed: " + L.gooey_b200_last_error().decode(errors="replace"))
+        self.numa_node = node.value
+
+    def array(self, shape, dtype):
+        import numpy as np
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        assert n <= self.nbytes
+        buf = (ctypes.c_char * n).from_address(self.ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib().gooey_b200_host_free(self.ptr)
+            self.ptr = None
+
+    __del__ = close

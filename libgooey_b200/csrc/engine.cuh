@@ -6,6 +6,7 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <functional>
 #include "pool.cuh"
 #include "patch.h"
 #include "mix.cuh"
@@ -108,6 +109,8 @@ struct EngineBank {
   cudaStream_t mix_stream = nullptr;
   cudaEvent_t ev_voices[2] = {nullptr, nullptr}, ev_mixed[2] = {nullptr, nullptr};
   DevBuf<float> d_voice_bufs[2], d_out;
+  DevBuf<int16_t> d_pcm;                  // 16-bit PCM of d_out (bounce_to_wav's quantisation done on the device)
+  cudaStream_t copy_stream = nullptr;     // drains finished pieces to the host while later pieces render
   DevBuf<float> d_silent;                 // the granulator's 1-sample silent placeholder buffer (ffi.rs:929-933)
   DevBuf<uint32_t> d_mix_slots, d_mix_ev_begins[2];
   DevBuf<uint8_t> d_mix_fast;
@@ -132,6 +135,7 @@ struct EngineBank {
     GH_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     GH_CUDA(cudaEventCreate(&ev0)); GH_CUDA(cudaEventCreate(&ev1)); GH_CUDA(cudaEventCreateWithFlags(&ev_piece, cudaEventDisableTiming));
     GH_CUDA(cudaStreamCreateWithFlags(&mix_stream, cudaStreamNonBlocking));
+    GH_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) { GH_CUDA(cudaEventCreateWithFlags(&ev_voices[b], cudaEventDisableTiming)); GH_CUDA(cudaEventCreateWithFlags(&ev_mixed[b], cudaEventDisableTiming)); }
     d_silent.alloc(4); d_silent.zero(stream);
   }
@@ -319,7 +323,10 @@ inline void aux_touch(GooeyEngine* e, bool is_gran) {
 // Renders `frames` frames of every engine of `E` (all on one bank) into out_dev: mono rows [n][stride] (the bounce
 // downmix 0.5 (l + r)) or interleaved stereo rows [n][stride >= 2 frames].  `bounce`: apply the reference's bounce
 // preamble first (ffi.rs:7840-7854): clock to 0, sequencers reset + start, strips / graph / master snapped.
-inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, int out_mode, bool bounce, float* out_dev, size_t stride) {
+// on_piece (optional): called after the mix of frames [f0, f0 + nf) has been enqueued, with the event that marks it done.
+using PieceHook = std::function<void(uint32_t f0, uint32_t nf, cudaEvent_t mixed)>;
+inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, int out_mode, bool bounce, float* out_dev, size_t stride,
+                           const PieceHook* on_piece = nullptr) {
   if (E.empty() || frames == 0) return;
   EngineBank& B = *E[0]->bank;
   std::lock_guard<std::recursive_mutex> lk(B.mu);
@@ -434,8 +441,11 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   piece = std::min<size_t>(std::max<size_t>(piece & ~(size_t)31, 2048), 65536);
   piece = std::min<size_t>(piece, (frames + 31) & ~31u);
   const bool two_bufs = frames > piece || frames > 4096;      // more than one piece: overlap mix(p) with voices(p + 1)
-  B.d_voice_bufs[0].alloc(rows * piece);
-  if (two_bufs) B.d_voice_bufs[1].alloc(rows * piece);
+  // row pitch of the voice buffers: an odd multiple of 32 frames (the mixer reads 32 rows x 7 channels per tile; rows a power of
+  // two apart would all fall into the same cache sets)
+  const size_t vstride = ((piece / 32) & 1) ? piece : piece + 32;
+  B.d_voice_bufs[0].alloc(rows * vstride);
+  if (two_bufs) B.d_voice_bufs[1].alloc(rows * vstride);
   cudaStream_t ms = B.mix_stream;
   GH_CUDA(cudaEventRecord(B.ev_piece, st));
   GH_CUDA(cudaStreamWaitEvent(ms, B.ev_piece, 0));             // the mix stream starts after everything queued so far (uploads, ring set-up)
@@ -480,7 +490,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     GH_CUDA(cudaEventRecord(start, st));
     // the clock index differs per engine only through e->k; voices carry their own k, the launch passes the table
     tev(tv0, st);
-    B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_bufs[vb].p, (long long)piece);
+    B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_bufs[vb].p, (long long)vstride);
     tev(tv1, st);
     GH_CUDA(cudaEventRecord(B.ev_voices[vb], st));
     GH_CUDA(cudaStreamWaitEvent(ms, B.ev_voices[vb], 0));
@@ -498,7 +508,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     memset(&M, 0, sizeof M);
     M.state = B.mix_pool.d.p; M.n = n; M.state_cap = B.mix_pool.cap; M.slots = B.d_mix_slots.p; M.n_lpad = n_lpad;
     M.cfg = B.d_cfg.p; M.events = B.d_mix_eventss[vb].p; M.ev_begin = B.d_mix_ev_begins[vb].p;
-    M.voice_buf = B.d_voice_bufs[vb].p; M.voice_stride = (long long)piece; M.chan_mask = 0x1fu | (any_poly ? 0x20u : 0u) | (any_gran ? 0x40u : 0u);
+    M.voice_buf = B.d_voice_bufs[vb].p; M.voice_stride = (long long)vstride; M.chan_mask = 0x1fu | (any_poly ? 0x20u : 0u) | (any_gran ? 0x40u : 0u);
     for (int s = 0; s < gd::MAX_FX; s++) M.ring[s] = B.ring[s].p;
     M.ring_cap = ring_cap;
     M.frames = (int)nf;
@@ -522,6 +532,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     g_launches.fetch_add(3, std::memory_order_relaxed);
     GH_CUDA(cudaGetLastError());
     GH_CUDA(cudaEventRecord(B.ev_mixed[vb], ms));
+    if (on_piece) (*on_piece)(f0, nf, B.ev_mixed[vb]);
     tev(tm1, ms);
   }
   GH_CUDA(cudaStreamWaitEvent(st, B.ev_mixed[0], 0));

@@ -2,6 +2,7 @@
 // the header).  Conventions follow the reference: null / out-of-range arguments are ignored, nothing throws across the
 // boundary; a device failure latches the engine's sticky error and zero-fills the output (ffi.rs:2079-2121).
 #pragma once
+#include <thread>
 #include "engine.cuh"
 #include "music.h"
 #include "../../include/gooey.h"
@@ -418,9 +419,16 @@ uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing
 }
 
 // ---- render / bounce ----
-// out_rows (optional): one host pointer per engine instead of a pitched block (the per-engine buffers of batch bounce)
-static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t frames, int mode, bool bounce, float* out_dev, size_t stride,
-                             float* out_host, size_t host_pitch, float* const* out_rows = nullptr) {
+// Where the result of one device pass goes.  Exactly one of: dev (stays in HBM), host (pitched block of f32 rows), pcm (pitched
+// block of 16-bit PCM rows, quantised on the device), rows (one host pointer per engine: the per-engine buffers of batch bounce).
+struct RenderDst {
+  float* dev = nullptr; size_t dev_stride = 0;
+  float* host = nullptr; size_t host_pitch = 0;
+  int16_t* pcm = nullptr; size_t pcm_pitch = 0;
+  float* const* rows = nullptr;
+};
+static std::mutex g_ms_mutex;
+static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t frames, int mode, bool bounce, const RenderDst& D, bool accumulate_ms = false) {
   std::vector<GooeyEngine*> E(engines, engines + n);
   try {
     gh::EngineBank& B = *E[0]->bank;
@@ -428,18 +436,50 @@ static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t f
     // The bank's output / voice buffers, streams and events are shared by every engine of (device, sample rate): the lock
     // is held from the allocation to the end of the drain, so concurrent renders of different engines serialise here.
     std::lock_guard<std::recursive_mutex> lk(B.mu);
-    float* dst = out_dev;
+    float* dst = D.dev;
+    size_t stride = D.dev_stride;
     const size_t row = mode == gh::OUT_MONO ? (size_t)frames : (size_t)2 * frames;
+    const size_t per_frame = mode == gh::OUT_MONO ? 1 : 2;
     if (!dst) {
       stride = (row + 3) & ~(size_t)3;
       B.d_out.alloc((size_t)n * stride);
       dst = B.d_out.p;
     }
-    gh::engines_render(E, frames, mode, bounce, dst, stride);
-    if (out_host) GH_CUDA(cudaMemcpy2DAsync(out_host, host_pitch * 4, dst, stride * 4, row * 4, n, cudaMemcpyDeviceToHost, B.stream));
-    if (out_rows) for (uint32_t i = 0; i < n; i++) GH_CUDA(cudaMemcpyAsync(out_rows[i], dst + (size_t)i * stride, row * 4, cudaMemcpyDeviceToHost, B.stream));
+    if (D.pcm) B.d_pcm.alloc((size_t)n * stride);
+    // Pitched host destinations are drained piece by piece on the copy stream while later pieces render; the PCM path
+    // quantises each finished piece on the device first and ships half the bytes.
+    gh::PieceHook hook = [&](uint32_t f0, uint32_t nf, cudaEvent_t mixed) {
+      GH_CUDA(cudaStreamWaitEvent(B.copy_stream, mixed, 0));
+      const size_t c0 = per_frame * f0, nc = per_frame * nf;
+      if (D.pcm) {
+        gd::quantize_pcm16_kernel<<<dim3((unsigned)((nc + 1023) / 1024), n), 256, 0, B.copy_stream>>>(dst, (long long)stride, B.d_pcm.p, (long long)stride, (int)c0, (int)nc);
+        gh::g_launches.fetch_add(1, std::memory_order_relaxed);
+        GH_CUDA(cudaGetLastError());
+        GH_CUDA(cudaMemcpy2DAsync(D.pcm + c0, D.pcm_pitch * 2, B.d_pcm.p + c0, stride * 2, nc * 2, n, cudaMemcpyDeviceToHost, B.copy_stream));
+      } else {
+        GH_CUDA(cudaMemcpy2DAsync(D.host + c0, D.host_pitch * 4, dst + c0, stride * 4, nc * 4, n, cudaMemcpyDeviceToHost, B.copy_stream));
+      }
+    };
+    // ... when the destination is pinned.  An asynchronous copy into pageable memory is staged by the driver and blocks the
+    // calling thread, which would stall the enqueueing of the next pieces: pageable destinations get one copy at the end.
+    bool pinned = false;
+    if (D.host || D.pcm) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, D.host ? (const void*)D.host : (const void*)D.pcm) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost;
+      else cudaGetLastError();
+    }
+    const bool piecewise = pinned;
+    gh::engines_render(E, frames, mode, bounce, dst, stride, piecewise ? &hook : nullptr);
+    if ((D.host || D.pcm) && !piecewise) { GH_CUDA(cudaEventRecord(B.ev_piece, B.stream)); hook(0, frames, B.ev_piece); }
+    if (D.rows) for (uint32_t i = 0; i < n; i++) GH_CUDA(cudaMemcpyAsync(D.rows[i], dst + (size_t)i * stride, row * 4, cudaMemcpyDeviceToHost, B.stream));
+    if (D.host || D.pcm) GH_CUDA(cudaStreamSynchronize(B.copy_stream));
     GH_CUDA(cudaStreamSynchronize(B.stream));
-    GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, B.ev0, B.ev1));
+    float ms = 0.0f;
+    GH_CUDA(cudaEventElapsedTime(&ms, B.ev0, B.ev1));
+    {
+      std::lock_guard<std::mutex> g(g_ms_mutex);
+      gh::g_last_kernel_ms = accumulate_ms ? std::max(gh::g_last_kernel_ms, ms) : ms;
+    }
     B.collect_mix_stats();
     B.voices.collect_stats();
     return GOOEY_E_OK;
@@ -452,18 +492,60 @@ static int batch_render_impl(GooeyEngine* const* engines, uint32_t n, uint32_t f
     return GOOEY_E_CUDA;
   }
 }
+// A batch whose engines live on several devices (or sample rates): one group per bank, every group rendered by its own host
+// thread (its own device, streams and pinned drain), no data-path collective.  Host destinations are
+// sliced per group; a group whose engines are not a contiguous index range of the batch falls back to per-engine row copies.
+static int batch_render_multi(GooeyEngine* const* engines, uint32_t n, uint32_t frames, int mode, bool bounce, const RenderDst& D) {
+  std::map<gh::EngineBank*, std::vector<uint32_t>> groups;
+  for (uint32_t i = 0; i < n; i++) groups[engines[i]->bank].push_back(i);
+  if (groups.size() == 1) return batch_render_impl(engines, n, frames, mode, bounce, D);
+  if (D.dev) { gh::set_error("engines of a device-resident batch must share device and sample rate"); return GOOEY_E_INVALID; }
+  { std::lock_guard<std::mutex> g(g_ms_mutex); gh::g_last_kernel_ms = 0.0f; }
+  const size_t row = mode == gh::OUT_MONO ? (size_t)frames : (size_t)2 * frames;
+  std::vector<int> rcs(groups.size(), GOOEY_E_OK);
+  std::vector<std::string> errs(groups.size());
+  std::vector<std::thread> threads;
+  size_t gi = 0;
+  for (auto& g : groups) {
+    const std::vector<uint32_t>& idx = g.second;
+    threads.emplace_back([&, gi, idx]() {
+      std::vector<GooeyEngine*> E;
+      for (uint32_t i : idx) E.push_back(engines[i]);
+      bool contiguous = true;
+      for (size_t k = 1; k < idx.size(); k++) contiguous = contiguous && idx[k] == idx[k - 1] + 1;
+      RenderDst G;
+      std::vector<float*> rows;
+      std::vector<int16_t> pcm_tmp;
+      if (D.rows) { for (uint32_t i : idx) rows.push_back(D.rows[i]); G.rows = rows.data(); }
+      else if (D.host && contiguous) { G.host = D.host + (size_t)idx[0] * D.host_pitch; G.host_pitch = D.host_pitch; }
+      else if (D.pcm && contiguous) { G.pcm = D.pcm + (size_t)idx[0] * D.pcm_pitch; G.pcm_pitch = D.pcm_pitch; }
+      else if (D.host) { for (uint32_t i : idx) rows.push_back(D.host + (size_t)i * D.host_pitch); G.rows = rows.data(); }
+      else { pcm_tmp.resize(idx.size() * row); G.pcm = pcm_tmp.data(); G.pcm_pitch = row; }
+      rcs[gi] = batch_render_impl(E.data(), (uint32_t)E.size(), frames, mode, bounce, G, true);
+      if (rcs[gi] != GOOEY_E_OK) errs[gi] = gh::last_error();          // the error string is thread-local
+      if (D.pcm && !contiguous && rcs[gi] == GOOEY_E_OK)
+        for (size_t k = 0; k < idx.size(); k++) memcpy(D.pcm + (size_t)idx[k] * D.pcm_pitch, pcm_tmp.data() + k * row, row * 2);
+    });
+    gi++;
+  }
+  for (auto& t : threads) t.join();
+  for (size_t k = 0; k < rcs.size(); k++) if (rcs[k] != GOOEY_E_OK) { gh::set_error(errs[k]); return rcs[k]; }
+  return GOOEY_E_OK;
+}
 
 void gooey_engine_render(GooeyEngine* e, float* buffer, uint32_t frames) {
   if (!e || !buffer) return;
   if (frames == 0) return;
-  if (e->has_error || batch_render_impl(&e, 1, frames, gh::OUT_STEREO, false, nullptr, 0, buffer, (size_t)2 * frames) != GOOEY_E_OK)
+  RenderDst D; D.host = buffer; D.host_pitch = (size_t)2 * frames;
+  if (e->has_error || batch_render_impl(&e, 1, frames, gh::OUT_STEREO, false, D) != GOOEY_E_OK)
     memset(buffer, 0, (size_t)frames * 2 * sizeof(float));
 }
 int gooey_batch_render(GooeyEngine* const* engines, uint32_t n, uint32_t frames, float* out_host) {
   if (!engines || !out_host) { gh::set_error("null argument"); return GOOEY_E_INVALID; }
   if (n == 0 || frames == 0) return GOOEY_E_OK;
   for (uint32_t i = 0; i < n; i++) if (!engines[i]) { gh::set_error("null engine in batch"); return GOOEY_E_INVALID; }
-  return batch_render_impl(engines, n, frames, gh::OUT_STEREO, false, nullptr, 0, out_host, (size_t)2 * frames);
+  RenderDst D; D.host = out_host; D.host_pitch = (size_t)2 * frames;
+  return batch_render_multi(engines, n, frames, gh::OUT_STEREO, false, D);
 }
 float* gooey_engine_bounce_to_buffer(GooeyEngine* e, uint32_t bars, uint32_t* out_length) {
   if (!e || !out_length) return nullptr;
@@ -495,7 +577,8 @@ int gooey_batch_bounce(GooeyEngine* const* engines, uint32_t n, uint32_t bars, f
       }
     }
     if (frames > 0) {
-      int rc = batch_render_impl(E.data(), (uint32_t)cnt, frames, gh::OUT_MONO, true, nullptr, 0, nullptr, 0, bufs.data());
+      RenderDst D; D.rows = bufs.data();
+      int rc = batch_render_multi(E.data(), (uint32_t)cnt, frames, gh::OUT_MONO, true, D);
       if (rc != GOOEY_E_OK) {
         for (float* q : bufs) free(q);
         for (uint32_t i = 0; i < n; i++) { free(out_buffers[i]); out_buffers[i] = nullptr; out_lengths[i] = 0; }   // earlier groups
@@ -514,7 +597,33 @@ int gooey_batch_bounce_device(GooeyEngine* const* engines, uint32_t n, uint32_t 
   if (stride < frames) { gh::set_error("stride < frames"); return GOOEY_E_INVALID; }
   if (out_frames) *out_frames = frames;
   if (frames == 0) return GOOEY_E_OK;
-  return batch_render_impl(engines, n, frames, gh::OUT_MONO, true, out_dev, stride, nullptr, 0);
+  RenderDst D; D.dev = out_dev; D.dev_stride = stride;
+  return batch_render_multi(engines, n, frames, gh::OUT_MONO, true, D);
+}
+// Mono bounce of n engines of equal length into one pitched host block (f32) / 16-bit PCM block: the drain of finished pieces
+// overlaps the rendering of later ones; engines may live on several devices (one host thread per device).
+static int bounce_block_checks(GooeyEngine* const* engines, uint32_t n, uint32_t bars, const void* out, size_t pitch, uint32_t* out_frames, uint32_t& frames) {
+  if (!engines || !out || n == 0) { gh::set_error("bad arguments"); return GOOEY_E_INVALID; }
+  for (uint32_t i = 0; i < n; i++) if (!engines[i]) { gh::set_error("null engine in batch"); return GOOEY_E_INVALID; }
+  frames = gh::bounce_frames(engines[0], bars);
+  for (uint32_t i = 1; i < n; i++) if (gh::bounce_frames(engines[i], bars) != frames) { gh::set_error("engines of a block bounce must have equal length"); return GOOEY_E_INVALID; }
+  if (pitch < frames) { gh::set_error("pitch < frames"); return GOOEY_E_INVALID; }
+  if (out_frames) *out_frames = frames;
+  return GOOEY_E_OK;
+}
+int gooey_batch_bounce_host(GooeyEngine* const* engines, uint32_t n, uint32_t bars, float* out_host, size_t pitch, uint32_t* out_frames) {
+  uint32_t frames = 0;
+  const int rc = bounce_block_checks(engines, n, bars, out_host, pitch, out_frames, frames);
+  if (rc != GOOEY_E_OK || frames == 0) return rc;
+  RenderDst D; D.host = out_host; D.host_pitch = pitch;
+  return batch_render_multi(engines, n, frames, gh::OUT_MONO, true, D);
+}
+int gooey_batch_bounce_pcm16(GooeyEngine* const* engines, uint32_t n, uint32_t bars, int16_t* out_host, size_t pitch, uint32_t* out_frames) {
+  uint32_t frames = 0;
+  const int rc = bounce_block_checks(engines, n, bars, out_host, pitch, out_frames, frames);
+  if (rc != GOOEY_E_OK || frames == 0) return rc;
+  RenderDst D; D.pcm = out_host; D.pcm_pitch = pitch;
+  return batch_render_multi(engines, n, frames, gh::OUT_MONO, true, D);
 }
 
 }  // extern "C"

@@ -150,6 +150,7 @@ struct GooeyVoiceBatch {
   std::vector<std::vector<gd::VoiceEvent>> pending;   // per voice, frames relative to the next render
   VoiceBank bank;
   DevBuf<float> d_out;
+  DevBuf<int16_t> d_pcm;
   ~GooeyVoiceBatch() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -310,6 +311,74 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
 
 #include "engine_api.cuh"
 #include "rs_api.cuh"
+#include <sys/syscall.h>
+#include <unistd.h>
+
+extern "C" {
+
+// 16-bit PCM of every voice (what bounce_to_wav stores, bounce.rs:105-113): rendered as f32 on the device, quantised there
+// chunk by chunk and drained as int16 — half the bytes of gooey_voice_batch_render over PCIe and into host memory.
+int gooey_voice_batch_render_pcm16(GooeyVoiceBatch* b, uint32_t frames, int16_t* out_host) {
+  GOOEY_TRY
+  if (!b || !out_host) { set_error("bad arguments"); return GOOEY_E_INVALID; }
+  use_device(b->device);
+  const size_t stride = (frames + 3) & ~(size_t)3;
+  b->d_out.alloc((size_t)b->n * stride);
+  b->d_pcm.alloc((size_t)b->n * stride);
+  voice_batch_render_impl(b, frames, b->d_out.p, stride);
+  const uint32_t chunk = (uint32_t)b->bank.chunk_frames((int)frames);
+  int ci = 0;
+  for (uint32_t c0 = 0; c0 < frames; c0 += chunk, ci++) {
+    const uint32_t nf = std::min(chunk, frames - c0);
+    b->bank.wait_chunk(b->copy_stream, ci);
+    gd::quantize_pcm16_kernel<<<dim3((nf + 1023) / 1024, b->n), 256, 0, b->copy_stream>>>(b->d_out.p, (long long)stride, b->d_pcm.p, (long long)stride, (int)c0, (int)nf);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GH_CUDA(cudaGetLastError());
+    GH_CUDA(cudaMemcpy2DAsync(out_host + c0, (size_t)frames * 2, b->d_pcm.p + c0, stride * 2, (size_t)nf * 2, b->n, cudaMemcpyDeviceToHost, b->copy_stream));
+  }
+  GH_CUDA(cudaStreamSynchronize(b->copy_stream));
+  GH_CUDA(cudaStreamSynchronize(b->stream));
+  GH_CUDA(cudaEventElapsedTime(&gh::g_last_kernel_ms, b->ev0, b->ev1));
+  b->bank.collect_stats();
+  return GOOEY_E_OK;
+  GOOEY_CATCH
+}
+
+// Pinned host memory for drains, placed on the NUMA node the device hangs off (read from sysfs through the device's PCI bus
+// id; no libnuma: the memory policy is set with the raw syscall for the duration of the allocation and restored afterwards).
+// With eight ranks draining at once, buffers that all sit on one node bound the whole box (profiles/README.md, round 1).
+void* gooey_b200_host_alloc(size_t bytes, int device, int* out_numa_node) {
+  if (out_numa_node) *out_numa_node = -1;
+  if (bytes == 0) return nullptr;
+  try { use_device(device); } catch (const std::exception& ex) { set_error(ex.what()); return nullptr; }
+  int node = -1;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) {
+    for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    if (FILE* f = fopen(path.c_str(), "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+  } else cudaGetLastError();
+  bool bound = false;
+#ifdef SYS_set_mempolicy
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(sizeof mask * 8)) == 0;
+  }
+#endif
+  void* p = nullptr;
+  const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+  if (e == cudaSuccess) memset(p, 0, bytes);           // first touch under the policy
+#ifdef SYS_set_mempolicy
+  if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaHostAlloc failed"); return nullptr; }
+  if (out_numa_node) *out_numa_node = bound ? node : -1;
+  return p;
+}
+void gooey_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"
 
 // =================================================================================================
 // Self-test hooks (tests/test_gmath_gpu.py): evaluate the gm:: routines on the device so the test can

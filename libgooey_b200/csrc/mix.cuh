@@ -871,6 +871,25 @@ __global__ void __launch_bounds__(256) mix_fast_kernel(const MixLaunch L) {
     for (int q = 0; q < nf; q++) { dst[2 * q] = ol[q]; dst[2 * q + 1] = orr[q]; }
   }
 }
+// 16-bit PCM of rows of f32 samples: `(s * 32767.0).round() as i16` (bounce.rs:105-113, ffi.rs:7968-7972: f32::round = half
+// away from zero, saturating cast, NaN -> 0).  grid = (ceil(cols / 1024), rows), 256 threads, 4 samples per thread.
+__device__ __forceinline__ int16_t pcm16_of(float s) {
+  const float r = roundf(s * 32767.0f);
+  return (int16_t)(r != r ? 0 : (r >= 32767.0f ? 32767 : (r <= -32768.0f ? -32768 : (int)r)));
+}
+__global__ void __launch_bounds__(256) quantize_pcm16_kernel(const float* __restrict__ in, long long in_stride, int16_t* __restrict__ out, long long out_stride,
+                                                             int col0, int cols) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const float* src = in + (long long)blockIdx.y * in_stride + col0 + c;
+  int16_t* dst = out + (long long)blockIdx.y * out_stride + col0 + c;
+  const int nq = min(4, cols - c);
+  if (nq == 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+    const float4 v = *reinterpret_cast<const float4*>(src);
+    short4 q; q.x = pcm16_of(v.x); q.y = pcm16_of(v.y); q.z = pcm16_of(v.z); q.w = pcm16_of(v.w);
+    *reinterpret_cast<short4*>(dst) = q;
+  } else for (int k = 0; k < nq; k++) dst[k] = pcm16_of(src[k]);
+}
 #endif  // __CUDACC__
 
 }  // namespace gd

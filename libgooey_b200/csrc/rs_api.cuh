@@ -269,6 +269,45 @@ int gooey_b200_write_wav(const char* utf8_path, const float* samples, uint32_t n
   return GOOEY_E_OK;
   GOOEY_CATCH
 }
+// 16-bit mono WAV from samples that are already PCM (the device-quantised drain)
+static int write_wav_pcm16(const char* utf8_path, const int16_t* pcm, uint32_t n, uint32_t sample_rate) {
+  const uint64_t data_bytes = (uint64_t)n * 2;
+  if (data_bytes + 36 > 0xffffffffull) { set_error("WAV too large"); return GOOEY_E_INVALID; }
+  FILE* f = fopen(utf8_path, "wb");
+  if (!f) { set_error("Failed to create WAV"); return GOOEY_E_INVALID; }
+  uint8_t h[44];
+  auto u32 = [&](int o, uint32_t v) { for (int i = 0; i < 4; i++) h[o + i] = (uint8_t)(v >> (8 * i)); };
+  auto u16 = [&](int o, uint32_t v) { h[o] = (uint8_t)v; h[o + 1] = (uint8_t)(v >> 8); };
+  memcpy(h, "RIFF", 4); u32(4, (uint32_t)(36 + data_bytes)); memcpy(h + 8, "WAVEfmt ", 8);
+  u32(16, 16); u16(20, 1); u16(22, 1); u32(24, sample_rate); u32(28, sample_rate * 2); u16(32, 2); u16(34, 16);
+  memcpy(h + 36, "data", 4); u32(40, (uint32_t)data_bytes);
+  const bool ok = fwrite(h, 1, 44, f) == 44 && fwrite(pcm, 2, n, f) == n;      // little-endian host (x86-64 / aarch64)
+  const bool closed = fclose(f) == 0;
+  if (!ok || !closed) { set_error("Failed to write sample"); return GOOEY_E_INVALID; }
+  return GOOEY_E_OK;
+}
+int gooey_batch_bounce_to_wav(GooeyEngine* const* engines, uint32_t n, uint32_t bars, const char* const* utf8_paths) {
+  if (!engines || !utf8_paths) { set_error("null argument"); return GOOEY_E_INVALID; }
+  for (uint32_t i = 0; i < n; i++) if (!engines[i] || !utf8_paths[i]) { set_error("null engine / path in batch"); return GOOEY_E_INVALID; }
+  // engines whose tempo gives a different length are bounced as separate groups
+  std::map<uint32_t, std::vector<uint32_t>> groups;
+  for (uint32_t i = 0; i < n; i++) groups[gh::bounce_frames(engines[i], bars)].push_back(i);
+  for (auto& g : groups) {
+    const uint32_t frames = g.first;
+    std::vector<GooeyEngine*> E;
+    for (uint32_t i : g.second) E.push_back(engines[i]);
+    std::vector<int16_t> pcm((size_t)E.size() * std::max<uint32_t>(frames, 1));
+    if (frames > 0) {
+      const int rc = gooey_batch_bounce_pcm16(E.data(), (uint32_t)E.size(), bars, pcm.data(), frames, nullptr);
+      if (rc != GOOEY_E_OK) return rc;
+    }
+    for (size_t k = 0; k < E.size(); k++) {
+      const int rc = write_wav_pcm16(utf8_paths[g.second[k]], pcm.data() + k * frames, frames, (uint32_t)gd::f32_to_u64_sat(E[k]->sr));
+      if (rc != GOOEY_E_OK) return rc;
+    }
+  }
+  return GOOEY_E_OK;
+}
 bool gooey_engine_bounce_to_wav(GooeyEngine* e, uint32_t bars, const char* utf8_path) {   // ffi.rs:7942-7980
   if (!e || !utf8_path) return false;
   uint32_t n = 0;

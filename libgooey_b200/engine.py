@@ -205,12 +205,54 @@ def batch_bounce(engines, bars):
     return out
 
 
-def batch_render(engines, frames):
+def _block_bounce(name, ctype, dtype, engines, bars, out):
+    L = lib()
+    n = len(engines)
+    hs = (c.c_void_p * n)(*[e._h for e in engines])
+    f = getattr(L, name)
+    f.argtypes = [c.POINTER(c.c_void_p), c.c_uint32, c.c_uint32, c.c_void_p, c.c_size_t, c.POINTER(c.c_uint32)]
+    frames = c.c_uint32(0)
+    if out is None:
+        # length first (host arithmetic of bounce.rs:20-32 done by the library): probe with the reference formula
+        L.gooey_engine_get_bpm.restype = c.c_float
+        L.gooey_engine_get_bpm.argtypes = [c.c_void_p]
+        sr, bpm = float(engines[0].sample_rate), float(L.gooey_engine_get_bpm(engines[0]._h))
+        guess = int(round(bars * 4.0 * (60.0 / bpm) * sr))
+        out = np.zeros((n, guess), dtype)
+    assert out.dtype == dtype and out.flags.c_contiguous and out.shape[0] == n
+    check(f(hs, n, bars, out.ctypes.data, out.shape[1], c.byref(frames)))
+    return out[:, :frames.value]
+
+
+def batch_bounce_host(engines, bars, out=None):
+    """gooey_batch_bounce_host: mono bounce of every engine into one (n, pitch) float32 block (drain overlapped with the render;
+    engines may live on several devices).  Pass `out` (e.g. a HostBuffer view) to choose the memory; returns out[:, :frames]."""
+    return _block_bounce("gooey_batch_bounce_host", c.c_float, np.float32, engines, bars, out)
+
+
+def batch_bounce_pcm16(engines, bars, out=None):
+    """gooey_batch_bounce_pcm16: the same as 16-bit PCM quantised on the device (what bounce_to_wav stores)."""
+    return _block_bounce("gooey_batch_bounce_pcm16", c.c_int16, np.int16, engines, bars, out)
+
+
+def batch_bounce_to_wav(engines, bars, paths):
+    """gooey_batch_bounce_to_wav: one mono 16-bit WAV per engine, all bounced in one device pass."""
+    L = lib()
+    n = len(engines)
+    hs = (c.c_void_p * n)(*[e._h for e in engines])
+    ps = (c.c_char_p * n)(*[str(p).encode() for p in paths])
+    L.gooey_batch_bounce_to_wav.argtypes = [c.POINTER(c.c_void_p), c.c_uint32, c.c_uint32, c.POINTER(c.c_char_p)]
+    check(L.gooey_batch_bounce_to_wav(hs, n, bars, ps))
+
+
+def batch_render(engines, frames, out=None):
     """gooey_batch_render: every engine rendered `frames` frames in one device pass; (n, frames, 2) interleaved stereo."""
     L = lib()
     n = len(engines)
     hs = (c.c_void_p * n)(*[e._h for e in engines])
-    out = np.zeros((n, frames, 2), np.float32)
+    if out is None:
+        out = np.zeros((n, frames, 2), np.float32)
+    assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (n, frames, 2)
     L.gooey_batch_render.argtypes = [c.POINTER(c.c_void_p), c.c_uint32, c.c_uint32, c.c_void_p]
     check(L.gooey_batch_render(hs, n, frames, out.ctypes.data))
     return out

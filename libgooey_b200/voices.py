@@ -107,5 +107,15 @@ class VoiceBatch:
         check(lib().gooey_voice_batch_render(self._h, frames, out.ctypes.data))
         return out
 
+    def render_pcm16(self, frames, out=None):
+        """gooey_voice_batch_render_pcm16: (N, frames) int16, `(s * 32767).round() as i16` quantised on the device."""
+        if out is None:
+            out = np.empty((self.n, frames), dtype=np.int16)
+        assert out.dtype == np.int16 and out.flags.c_contiguous and out.shape == (self.n, frames)
+        f = lib().gooey_voice_batch_render_pcm16
+        f.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+        check(f(self._h, frames, out.ctypes.data))
+        return out
+
     def render_device(self, frames, dev_ptr, stride):
         check(lib().gooey_voice_batch_render_device(self._h, frames, ctypes.c_void_p(dev_ptr), stride))
