@@ -125,6 +125,16 @@ int gooey_batch_bounce_to_wav(GooeyEngine* const* engines, uint32_t n, uint32_t 
 /* Batch of gooey_engine_render: interleaved stereo, out_host[i * 2 * frames + 2 * f + ch]. */
 int gooey_batch_render(GooeyEngine* const* engines, uint32_t n, uint32_t frames, float* out_host);
 
+/* ---- meters and MIDI export ---- */
+/* :2572-2584 — per-channel peak |x| (pre-pan, post gain x mute) since the last call, reset to 0 by the read; count <= 5. */
+void gooey_engine_get_channel_peaks(GooeyEngine* engine, float* out_peaks, uint32_t count);
+/* :6573-6580 — a mixer track's post-strip peak max(|l|, |r|) since the last call (read and reset); 0 for a bad track. */
+float gooey_engine_mixer_get_track_peak(GooeyEngine* engine, uint32_t track);
+/* :78-83, :2145-2167 — note-on events of the most recent render call (manual triggers at offset 0, sequencer triggers at their
+ * frame), at most 64; drained events are removed.  After a bounce: the events of its last 512-frame chunk (:7855-7870). */
+typedef struct GooeyMidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; } GooeyMidiEvent;
+uint32_t gooey_engine_drain_midi_events(GooeyEngine* engine, GooeyMidiEvent* out_events, uint32_t max_events);
+
 /* ---- errors (:2236-2284) ---- */
 bool gooey_engine_has_error(const GooeyEngine* engine);
 const char* gooey_engine_get_error_message(const GooeyEngine* engine);

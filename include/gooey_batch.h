@@ -111,6 +111,8 @@ int gooey_rs_batch_bounce_device(GooeyRsBatch* b, uint32_t samples, float* out_d
 /* Mono PCM WAV writer of bounce_to_wav (bounce.rs:80-133; ffi.rs:7942-7980): bit_depth 16 or 24, sample = round(s * (2^(bits-1) - 1)). */
 int gooey_b200_write_wav(const char* utf8_path, const float* samples, uint32_t n, uint32_t sample_rate, uint32_t bit_depth);
 
+/* 32-bit float WAV (WAVE_FORMAT_IEEE_FLOAT), 1 or 2 interleaved channels: the container of ffi.rs:8030-8048. */
+int gooey_b200_write_wav_f32(const char* utf8_path, const float* interleaved, uint32_t frames, uint32_t channels, uint32_t sample_rate);
 /* Pinned host memory for the drains above, allocated on the NUMA node `device` is attached to (*out_numa_node: the node, or
  * -1 when the placement could not be applied).  Free with gooey_b200_host_free. */
 void* gooey_b200_host_alloc(size_t bytes, int device, int* out_numa_node);

@@ -239,6 +239,15 @@ def bounce_to_buffer(engine, length):
     raise GooeyError("engine belongs to an EngineBatch: call batch.bounce(length)")
 
 
+def write_wav_f32(path, samples, sample_rate):
+    """32-bit float WAV (mono (n,) or interleaved stereo (n, 2)) — the container of gooey_engine_loop_render_to_wav."""
+    s = np.ascontiguousarray(samples, np.float32)
+    ch = 1 if s.ndim == 1 else s.shape[1]
+    f = _L().gooey_b200_write_wav_f32
+    f.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+    check(f(str(path).encode(), s.ctypes.data, s.shape[0], ch, int(sample_rate)))
+
+
 def write_wav(path, samples, sample_rate, bit_depth=16):
     s = np.ascontiguousarray(samples, np.float32)
     check(_L().gooey_b200_write_wav(str(path).encode(), s.ctypes.data, s.size, int(sample_rate), int(bit_depth)))

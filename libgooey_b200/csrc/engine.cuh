@@ -115,6 +115,9 @@ struct EngineBank {
   DevBuf<uint32_t> d_mix_slots, d_mix_ev_begins[2];
   DevBuf<uint8_t> d_mix_fast;
   DevBuf<gd::MixConst> d_mix_consts;
+  DevBuf<float> d_premix;                 // [2][n_lpad][vstride]: pre-chain stereo mix of the engines whose strips are time-parallel
+  DevBuf<float> d_peaks;                  // [n][N_PEAKS] maxima of the current render call
+  std::vector<float> h_peaks;
   DevBuf<gd::VoiceEvent> d_mix_eventss[2];
   std::recursive_mutex mu;   // every use of the bank's shared buffers / streams, held for a whole render call
   float last_ms = 0.0f;
@@ -186,6 +189,9 @@ struct GooeyEngine {
   std::vector<gd::VoiceEvent> mix_pending;
   bool track_muted[gd::MAX_TRACKS] = {false}, track_soloed[gd::MAX_TRACKS] = {false};
   bool seq_triggers_enabled = true;
+  float peaks[gd::N_PEAKS] = {0};          // read-and-reset meters (ffi.rs:2572-2584, graph.rs:233-237), merged after every render
+  struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
+  std::vector<MidiEvent> midi_events;      // of the most recent render call, at most 64 (ffi.rs:71, 994-1004, 1045)
   bool has_error = false;
   std::string error;
   void (*error_cb)(void*, const char*) = nullptr; void* error_ctx = nullptr;
@@ -394,22 +400,39 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       ev = a.pending; a.pending.clear();
       if (bounce) ev.push_back(make_event(0, gd::EV_SET_TIME, 0, 0.0f, 0));
     }
+    struct MidiKey { uint32_t frame, seq, ch; float vel; };
+    std::vector<MidiKey> midi;
     for (int ch = 0; ch < 5; ch++) {
       auto& s = e->strip[ch];
       auto& ev = vev[(size_t)i * 7 + ch];
       if (bounce) ev.push_back(make_event(0, gd::EV_SET_TIME, 0, 0.0f, 0));
       ev.insert(ev.end(), s.pending.begin(), s.pending.end());
       s.pending.clear();
-      if (s.trig_pending) { s.trig_pending = false; ev.push_back(make_event(0, gd::EV_TRIGGER, 0, s.trig_vel)); }
+      if (s.trig_pending) { s.trig_pending = false; ev.push_back(make_event(0, gd::EV_TRIGGER, 0, s.trig_vel)); midi.push_back({0u, 0u, (uint32_t)ch, s.trig_vel}); }
       fires.clear();
       s.seq.run(frames, fires);
       if (e->seq_triggers_enabled) {
+        for (const SeqFire& f : fires) midi.push_back({f.frame, 1u, (uint32_t)ch, f.velocity});
         for (const SeqFire& f : fires) {   // ffi.rs:1162-1198
           float mn, mxf;
           if (f.has_note) { if (note_freq_range(s.type, mn, mxf)) ev.push_back(make_event(f.frame, gd::EV_NOTE_FREQ, 0, midi_to_norm(f.note, mn, mxf))); }
           else ev.push_back(make_event(f.frame, gd::EV_RESTORE_FREQ, 0, 0.0f));
           ev.push_back(make_event(f.frame, gd::EV_TRIGGER, 0, f.velocity));
         }
+      }
+    }
+    // MIDI note-on export (ffi.rs:994-1004, 1079-1094, 1196): manual triggers first (offset 0, channel order), then the sequencer's
+    // in frame / channel order; the list is cleared by every render() call and capped at 64, and a bounce IS a run of 512-frame
+    // render() calls (ffi.rs:7855-7870), so after a bounce only the last chunk's events are pending, offsets relative to it.
+    {
+      std::stable_sort(midi.begin(), midi.end(), [](const MidiKey& a, const MidiKey& b) {
+        return a.frame != b.frame ? a.frame < b.frame : (a.seq != b.seq ? a.seq < b.seq : a.ch < b.ch); });
+      const uint32_t base = bounce ? ((frames - 1) / 512u) * 512u : 0u;
+      e->midi_events.clear();
+      for (const MidiKey& m : midi) {
+        if (m.frame < base) continue;
+        if (e->midi_events.size() >= 64) break;
+        e->midi_events.push_back({m.ch, m.vel, m.frame - base});
       }
     }
   }
@@ -446,6 +469,13 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   const size_t vstride = ((piece / 32) & 1) ? piece : piece + 32;
   B.d_voice_bufs[0].alloc(rows * vstride);
   if (two_bufs) B.d_voice_bufs[1].alloc(rows * vstride);
+  {
+    bool any_chain = false;
+    for (int i = 0; i < n && !any_chain; i++) for (int q = 0; q < gd::MAX_FX; q++) any_chain = any_chain || (E[i]->cfg.fx_kind[q] != gd::FXK_NONE && E[i]->cfg.fx_enabled[q]);
+    if (any_chain) B.d_premix.alloc((size_t)2 * n_lpad * vstride);
+  }
+  B.d_peaks.alloc((size_t)n * gd::N_PEAKS);
+  GH_CUDA(cudaMemsetAsync(B.d_peaks.p, 0, (size_t)n * gd::N_PEAKS * 4, st));
   cudaStream_t ms = B.mix_stream;
   GH_CUDA(cudaEventRecord(B.ev_piece, st));
   GH_CUDA(cudaStreamWaitEvent(ms, B.ev_piece, 0));             // the mix stream starts after everything queued so far (uploads, ring set-up)
@@ -517,6 +547,8 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     M.center_l = gm::g_cosf(0.5f * 1.57079632679489661923f); M.center_r = gm::g_sinf(0.5f * 1.57079632679489661923f);
     B.d_mix_fast.alloc(n); B.d_mix_consts.alloc(n);
     M.fast = B.d_mix_fast.p; M.consts = B.d_mix_consts.p;
+    M.peaks = B.d_peaks.p;
+    M.premix = B.d_premix.p; M.premix_stride = (long long)vstride;
     tev(tm0, ms);
     gd::mix_prepare_kernel<<<(n + 127) / 128, 128, 0, ms>>>(M);
     gd::mix_fast_kernel<<<dim3((nf + 1023) / 1024, n), 256, 0, ms>>>(M);
@@ -547,7 +579,12 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     }
     for (auto* v : {&tv0, &tv1, &tm0, &tm1}) for (auto e : *v) cudaEventDestroy(e);
   }
+  // meters: the call's maxima join the engines' read-and-reset peaks (one small copy; the caller synchronises the stream anyway)
+  B.h_peaks.resize((size_t)n * gd::N_PEAKS);
+  GH_CUDA(cudaMemcpyAsync(B.h_peaks.data(), B.d_peaks.p, B.h_peaks.size() * 4, cudaMemcpyDeviceToHost, st));
+  GH_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < n; i++) {
+    for (int q = 0; q < gd::N_PEAKS; q++) { const float v = B.h_peaks[(size_t)i * gd::N_PEAKS + q]; if (v > E[i]->peaks[q]) E[i]->peaks[q] = v; }
     E[i]->k += frames;
     if (bounce) for (auto& s : E[i]->strip) s.seq.stop();
   }

@@ -418,6 +418,23 @@ uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing
   return n;
 }
 
+// ---- meters and MIDI export (ffi.rs:2572-2584, 6573-6580, 2145-2167) ----
+void gooey_engine_get_channel_peaks(GooeyEngine* e, float* out_peaks, uint32_t count) {
+  if (!e || !out_peaks) return;
+  for (uint32_t i = 0; i < count && i < 5; i++) { out_peaks[i] = e->peaks[i]; e->peaks[i] = 0.0f; }
+}
+float gooey_engine_mixer_get_track_peak(GooeyEngine* e, uint32_t track) {
+  if (!e || track >= e->cfg.n_tracks) return 0.0f;
+  const float p = e->peaks[5 + track]; e->peaks[5 + track] = 0.0f; return p;
+}
+uint32_t gooey_engine_drain_midi_events(GooeyEngine* e, GooeyMidiEvent* out_events, uint32_t max_events) {
+  if (!e || !out_events || max_events == 0) return 0;
+  const size_t n = std::min<size_t>(e->midi_events.size(), max_events);
+  for (size_t i = 0; i < n; i++) { out_events[i].instrument_index = e->midi_events[i].instrument_index; out_events[i].velocity = e->midi_events[i].velocity; out_events[i].sample_offset = e->midi_events[i].sample_offset; }
+  e->midi_events.erase(e->midi_events.begin(), e->midi_events.begin() + n);
+  return (uint32_t)n;
+}
+
 // ---- render / bounce ----
 // Where the result of one device pass goes.  Exactly one of: dev (stays in HBM), host (pitched block of f32 rows), pcm (pitched
 // block of 16-bit PCM rows, quantised on the device), rows (one host pointer per engine: the per-engine buffers of batch bounce).

@@ -15,6 +15,7 @@ namespace gd {
 constexpr int MAX_TRACKS = 8;
 constexpr int MAX_FX = 12;       // slots 0..3 = global tilt/delay/spring/plate, 4..11 = track-rack effects and the other global effects (on first use)
 constexpr int N_VOICE_CH = 5;
+constexpr int N_PEAKS = 5 + 8;   // voice strips + MAX_TRACKS
 enum { FXK_NONE = 0xff, FXK_LOWPASS = 0, FXK_DELAY = 1, FXK_SATURATION = 2, FXK_COMPRESSOR = 3, FXK_TILT = 4, FXK_LIMITER = 5, FXK_SPRING = 6,
        FXK_WAVESHAPER = 7, FXK_FBWS = 8, FXK_PLATE = 9 };  // = FFI effect ids (ffi.rs:1548-1575)
 enum { FXS_TILT = 0, FXS_DELAY = 1, FXS_SPRING = 2, FXS_PLATE = 3, FXS_RACK0 = 4 };
@@ -97,9 +98,14 @@ struct MixLaunch {
   float* out; long long out_stride; int out_mode;  // 0: mono downmix [engine][frame], 1: interleaved stereo [engine][2*frame]
   const uint32_t* out_rows;
   RateCtx rc; FxGeom geo;
+  long long premix_stride;
   float center_l, center_r;           // cos/sin(0.5 * pi/2) for the center-panned poly / granulator (ffi.rs:1287-1288)
   // time-parallel path for engines whose mixer is memoryless over this launch (see mix_prepare_kernel)
-  uint8_t* fast;                      // [n] 1 = handled by mix_fast_kernel, the general kernel skips it
+  float* peaks;                       // [n][N_PEAKS] running maxima of the call (bit pattern of a non-negative float): 5 voice strips
+                                      // (pre-pan |x|, ffi.rs:1281-1282), then MAX_TRACKS post-strip max(|l|, |r|) (graph.rs:395)
+  uint8_t* fast;                      // [n] 1 = handled by mix_fast_kernel, the general kernel skips it; 2 = mix_fast_kernel writes the
+                                      // engine's pre-chain stereo mix (strips -> graph -> master) and the general kernel runs only its global chain
+  float* premix;                      // [2][n_lpad][premix_stride]: left plane, right plane
   struct MixConst* consts;            // [n]
 };
 // Everything mix_fast_kernel needs for one engine: the settled smoother values and the trig of the constant pans.
@@ -645,13 +651,17 @@ constexpr size_t MIX_DYN_SMEM = 32 * (sizeof(MixState) + sizeof(MixCfg));
 __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
   __shared__ float tin[MIX_CH][TILE * 33];
   __shared__ float tout[2][TILE * 33];
+  __shared__ float tpre[2][TILE * 33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int lane = threadIdx.x;
   const int warp_i0 = i - lane;
   if (warp_i0 >= L.n) return;
-  const bool valid = i < L.n && !(L.fast && L.fast[i]);
+  const uint8_t fmode = (i < L.n && L.fast) ? L.fast[i] : 0;
+  const bool valid = i < L.n && fmode != 1;
+  const bool pre = valid && fmode == 2;          // strips / graph / master already mixed by mix_fast_kernel: only the global chain runs here
   const uint32_t row_mask = __ballot_sync(0xffffffffu, valid);
   if (row_mask == 0) return;
+  const bool any_pre = __any_sync(0xffffffffu, pre), any_full = __any_sync(0xffffffffu, valid && !pre);
   const int n_rows = min(32, L.n - warp_i0);
   // The per-engine mixer state (414 words) and configuration are indexed with run-time slots (effect order, racks,
   // routes), which would put them in local memory — 3.7 MB for 2048 engines, thrashing L1 on every access.  They live in
@@ -666,16 +676,25 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
     load_words(st, L.state, es, L.state_cap, 0);
     cfg = L.cfg[es];
     ev = L.ev_begin[i]; ev_end = L.ev_begin[i + 1];
+    if (pre) ev = ev_end;                          // mix_prepare_kernel consumed them (all at frame 0)
   }
   const RateCtx& rc = L.rc;
   // pan trig cache (pan is constant during a bounce; recomputed when the smoothed value moves)
   float pan_v[N_VOICE_CH], pan_cos[N_VOICE_CH], pan_sin[N_VOICE_CH];
 #pragma unroll
   for (int c = 0; c < N_VOICE_CH; c++) { pan_v[c] = -1.0f; pan_cos[c] = pan_sin[c] = 0.0f; }
+  float pk[N_VOICE_CH], tpk[MAX_TRACKS];   // record_peak: `if level > prev` (NaN never wins)
+#pragma unroll
+  for (int c = 0; c < N_VOICE_CH; c++) pk[c] = 0.0f;
+#pragma unroll
+  for (int t = 0; t < MAX_TRACKS; t++) tpk[t] = 0.0f;
   for (int f0 = 0; f0 < L.frames; f0 += TILE) {
     const int nf = min(TILE, L.frames - f0);
-    for (int c = 0; c < MIX_CH; c++)
-      if ((L.chan_mask >> c) & 1u) load_tile_rows_any(tin[c], L.voice_buf, L.voice_stride, c * L.n_lpad + warp_i0, n_rows, f0, nf, lane);
+    if (any_full)
+      for (int c = 0; c < MIX_CH; c++)
+        if ((L.chan_mask >> c) & 1u) load_tile_rows_any(tin[c], L.voice_buf, L.voice_stride, c * L.n_lpad + warp_i0, n_rows, f0, nf, lane);
+    if (any_pre)
+      for (int c = 0; c < 2; c++) load_tile_rows_any(tpre[c], L.premix + (long long)c * L.n_lpad * L.premix_stride, L.premix_stride, warp_i0, n_rows, f0, nf, lane);
     __syncwarp();
     if (valid) {
       for (int j = 0; j < nf; j++) {
@@ -696,12 +715,19 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
           }
           ev++;
         }
-        float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
+        float ml = 0.0f, mr = 0.0f;
         float channel_outs[N_VOICE_CH];
+        if (pre) {
+          ml = tpre[0][lane * 33 + j]; mr = tpre[1][lane * 33 + j];
+#pragma unroll
+          for (int c = 0; c < N_VOICE_CH; c++) channel_outs[c] = 0.0f;
+        } else {
+        float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
 #pragma unroll
         for (int c = 0; c < N_VOICE_CH; c++) {  // ffi.rs:1268-1283
           float x = tin[c][lane * 33 + j] * sm_tick(st.ch_gain[c], rc.smooth10) * sm_tick(st.ch_mute[c], rc.smooth10);
           channel_outs[c] = x;
+          if (fabsf(x) > pk[c]) pk[c] = fabsf(x);
           float pan = sm_tick(st.ch_pan[c], rc.smooth10);
           if (pan != pan_v[c]) { float ang = clampf(pan, 0.0f, 1.0f) * 1.57079632679489661923f; pan_v[c] = pan; pan_cos[c] = gm::g_cosf(ang); pan_sin[c] = gm::g_sinf(ang); }
           float pl = x * pan_cos[c], pr = x * pan_sin[c];
@@ -710,7 +736,6 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
         float src_l[5] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f}, src_r[5] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f};
         if (cfg.src_poly) { float x = tin[5][lane * 33 + j]; src_l[2] = x * L.center_l; src_r[2] = x * L.center_r; }
         if (cfg.src_gran) { float x = tin[6][lane * 33 + j]; src_l[3] = x * L.center_l; src_r[3] = x * L.center_r; }
-        float ml = 0.0f, mr = 0.0f;
         for (uint32_t t = 0; t < cfg.n_tracks; t++) {  // graph.rs:344-350, 385-399
           float fl = 0.0f, fr = 0.0f;
 #pragma unroll
@@ -724,10 +749,16 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
             const uint32_t slot = cfg.rack_slot[t][k];
             fx_process(st.fx[slot], cfg.fx_kind[slot], RingRef{L.ring[slot], L.ring_cap, es}, L.geo, fl, fr, rc);
           }
+          {
+            const float lv = fmaxf(fabsf(fl), fabsf(fr));
+#pragma unroll
+            for (int q = 0; q < MAX_TRACKS; q++) if ((uint32_t)q == t && lv > tpk[q]) tpk[q] = lv;
+          }
           ml += fl; mr += fr;
         }
         const float mg = sm_tick(st.master, rc.smooth30);
         ml *= mg; mr *= mg;
+        }
 #pragma unroll 1
         for (int o = 0; o < 9; o++) {  // ffi.rs:1317-1364
           const uint32_t id = cfg.order[o];
@@ -760,7 +791,16 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
     }
     __syncwarp();
   }
-  if (valid) store_words(st, L.state, es, L.state_cap, 0);
+  if (valid) {
+    store_words(st, L.state, es, L.state_cap, 0);
+    if (L.peaks) {
+      float* pp = L.peaks + (size_t)i * N_PEAKS;
+#pragma unroll
+      for (int c = 0; c < N_VOICE_CH; c++) if (pk[c] > pp[c]) pp[c] = pk[c];
+#pragma unroll
+      for (int t = 0; t < MAX_TRACKS; t++) if (tpk[t] > pp[N_VOICE_CH + t]) pp[N_VOICE_CH + t] = tpk[t];
+    }
+  }
 }
 
 // ---- time-parallel mixer ------------------------------------------------------------------------------------------
@@ -775,10 +815,14 @@ __global__ void __launch_bounds__(128) mix_prepare_kernel(const MixLaunch L) {
   const int es = (int)L.slots[i];
   const MixCfg cfg = L.cfg[es];
   const uint32_t ev0 = L.ev_begin[i], ev1 = L.ev_begin[i + 1];
-  bool ok = true;
-  for (int s = 0; s < MAX_FX; s++) ok = ok && !(cfg.fx_kind[s] != FXK_NONE && cfg.fx_enabled[s]);
+  bool ok = true, chain = false;
+  for (int s = 0; s < MAX_FX; s++) chain = chain || (cfg.fx_kind[s] != FXK_NONE && cfg.fx_enabled[s] && !((cfg.fx_rack >> s) & 1u));
   for (uint32_t t = 0; t < cfg.n_tracks; t++) ok = ok && cfg.rack_n[t] == 0;
   for (uint32_t e = ev0; e < ev1; e++) ok = ok && L.events[e].frame == 0 && L.events[e].kind != MX_FX_INIT && L.events[e].kind != MX_FX_RESET;
+  // a global chain does not disqualify the engine: its strips / graph / master still run time-parallel (fast = 2) and only
+  // the chain is left to the per-engine kernel — unless the compressor listens to a voice strip (ffi.rs:1331-1343)
+  if (chain && cfg.comp_sidechain < (uint32_t)N_VOICE_CH) ok = false;
+  if (chain && !L.premix) ok = false;
   if (!ok) { L.fast[i] = 0; return; }
   MixState st;
   load_words(st, L.state, es, L.state_cap, 0);
@@ -786,7 +830,7 @@ __global__ void __launch_bounds__(128) mix_prepare_kernel(const MixLaunch L) {
   for (int c = 0; c < N_VOICE_CH; c++) ok = ok && st.ch_gain[c].c == st.ch_gain[c].t && st.ch_mute[c].c == st.ch_mute[c].t && st.ch_pan[c].c == st.ch_pan[c].t;
   for (uint32_t t = 0; t < cfg.n_tracks; t++) ok = ok && st.tr_gain[t].c == st.tr_gain[t].t && st.tr_mute[t].c == st.tr_mute[t].t && st.tr_pan[t].c == st.tr_pan[t].t;
   ok = ok && st.master.c == st.master.t;
-  L.fast[i] = ok ? 1 : 0;
+  L.fast[i] = ok ? (chain ? 2 : 1) : 0;
   if (!ok) return;                                   // state untouched: the general kernel re-applies the events itself
   store_words(st, L.state, es, L.state_cap, 0);      // events consumed
   MixConst k;
@@ -801,16 +845,17 @@ __global__ void __launch_bounds__(128) mix_prepare_kernel(const MixLaunch L) {
     k.tbl[t] = fminf(2.0f * (1.0f - pan), 1.0f); k.tbr[t] = fminf(2.0f * pan, 1.0f);
   }
   k.master = st.master.c; k.lim_th = cfg.lim_th; k.lim_inv = cfg.lim_inv;
-  k.n_tracks = cfg.n_tracks; k.limiter_on = cfg.limiter_on; k.src_poly = cfg.src_poly; k.src_gran = cfg.src_gran;
+  k.n_tracks = cfg.n_tracks; k.limiter_on = chain ? 0u : cfg.limiter_on; k.src_poly = cfg.src_poly; k.src_gran = cfg.src_gran;   // the limiter follows the chain
   for (int s = 0; s < 5; s++) k.route[s] = cfg.route[s];
   L.consts[i] = k;
 }
 
-__device__ __forceinline__ void mix_fast_frame(const MixConst& k, const float* x, float center_l, float center_r, float& ml, float& mr) {
+__device__ __forceinline__ void mix_fast_frame(const MixConst& k, const float* x, float center_l, float center_r, float& ml, float& mr, float* pk) {
   float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
 #pragma unroll
   for (int c = 0; c < N_VOICE_CH; c++) {
     const float v = x[c] * k.g[c] * k.m[c];
+    if (fabsf(v) > pk[c]) pk[c] = fabsf(v);
     const float pl = v * k.pc[c], pr = v * k.ps[c];
     if (c < 4) { kit_l += pl; kit_r += pr; } else { bass_l += pl; bass_r += pr; }
   }
@@ -824,6 +869,11 @@ __device__ __forceinline__ void mix_fast_frame(const MixConst& k, const float* x
     for (int s = 0; s < 5; s++) if (k.route[s] == (int32_t)t) { fl += src_l[s]; fr += src_r[s]; }
     fl *= k.tgain[t]; fr *= k.tgain[t];
     fl *= k.tbl[t]; fr *= k.tbr[t];
+    {
+      const float lv = fmaxf(fabsf(fl), fabsf(fr));
+#pragma unroll
+      for (int q = 0; q < MAX_TRACKS; q++) if ((uint32_t)q == t && lv > pk[N_VOICE_CH + q]) pk[N_VOICE_CH + q] = lv;
+    }
     ml += fl; mr += fr;
   }
   ml *= k.master; mr *= k.master;
@@ -852,13 +902,33 @@ __global__ void __launch_bounds__(256) mix_fast_kernel(const MixLaunch L) {
     if (vec_in) { const float4 v = *reinterpret_cast<const float4*>(row); x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w; }
     else for (int q = 0; q < nf; q++) x[c][q] = row[q];
   }
-  float ol[4], orr[4];
+  float ol[4], orr[4], pk[N_PEAKS];
+#pragma unroll
+  for (int q = 0; q < N_PEAKS; q++) pk[q] = 0.0f;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     float xs[MIX_CH];
 #pragma unroll
     for (int c = 0; c < MIX_CH; c++) xs[c] = x[c][q];
-    mix_fast_frame(ks, xs, L.center_l, L.center_r, ol[q], orr[q]);
+    float junk[N_PEAKS];
+    mix_fast_frame(ks, xs, L.center_l, L.center_r, ol[q], orr[q], q < nf ? pk : junk);
+  }
+  if (L.peaks) {   // maxima of non-negative floats compare like their bit patterns: warp reduce, then one atomic per value
+    unsigned* pp = reinterpret_cast<unsigned*>(L.peaks + (size_t)i * N_PEAKS);
+    const unsigned act = __activemask();
+#pragma unroll
+    for (int q = 0; q < N_PEAKS; q++) {
+      if (q >= N_VOICE_CH + (int)ks.n_tracks) break;
+      const unsigned m = __reduce_max_sync(act, __float_as_uint(pk[q]));
+      if ((threadIdx.x & 31) == (__ffs(act) - 1) && m > pp[q]) atomicMax(pp + q, m);
+    }
+  }
+  if (L.fast[i] == 2) {          // pre-chain mix for the general kernel
+    float* pl = L.premix + (long long)i * L.premix_stride + f;
+    float* pr = pl + (long long)L.n_lpad * L.premix_stride;
+    if (nf == 4 && (L.premix_stride & 3) == 0) { *reinterpret_cast<float4*>(pl) = make_float4(ol[0], ol[1], ol[2], ol[3]); *reinterpret_cast<float4*>(pr) = make_float4(orr[0], orr[1], orr[2], orr[3]); }
+    else for (int q = 0; q < nf; q++) { pl[q] = ol[q]; pr[q] = orr[q]; }
+    return;
   }
   const long long row = L.out_rows ? (long long)L.out_rows[i] : (long long)i;
   if (L.out_mode == 0) {

@@ -269,6 +269,25 @@ int gooey_b200_write_wav(const char* utf8_path, const float* samples, uint32_t n
   return GOOEY_E_OK;
   GOOEY_CATCH
 }
+// 32-bit float WAV (the format of ffi.rs:8030-8048 / tests/loop_render_wav.rs: WAVE_FORMAT_IEEE_FLOAT, `channels` interleaved)
+int gooey_b200_write_wav_f32(const char* utf8_path, const float* interleaved, uint32_t frames, uint32_t channels, uint32_t sample_rate) {
+  if (!utf8_path || (!interleaved && frames) || channels == 0 || channels > 2) { set_error("bad arguments"); return GOOEY_E_INVALID; }
+  const uint64_t data_bytes = (uint64_t)frames * channels * 4;
+  if (data_bytes + 36 > 0xffffffffull) { set_error("WAV too large"); return GOOEY_E_INVALID; }
+  FILE* f = fopen(utf8_path, "wb");
+  if (!f) { set_error("Failed to create WAV"); return GOOEY_E_INVALID; }
+  uint8_t h[44];
+  auto u32 = [&](int o, uint32_t v) { for (int i = 0; i < 4; i++) h[o + i] = (uint8_t)(v >> (8 * i)); };
+  auto u16 = [&](int o, uint32_t v) { h[o] = (uint8_t)v; h[o + 1] = (uint8_t)(v >> 8); };
+  memcpy(h, "RIFF", 4); u32(4, (uint32_t)(36 + data_bytes)); memcpy(h + 8, "WAVEfmt ", 8);
+  u32(16, 16); u16(20, 3); u16(22, channels); u32(24, sample_rate); u32(28, sample_rate * channels * 4); u16(32, channels * 4); u16(34, 32);
+  memcpy(h + 36, "data", 4); u32(40, (uint32_t)data_bytes);
+  const size_t n = (size_t)frames * channels;
+  const bool ok = fwrite(h, 1, 44, f) == 44 && fwrite(interleaved, 4, n, f) == n;      // little-endian host
+  const bool closed = fclose(f) == 0;
+  if (!ok || !closed) { set_error("Failed to write sample"); return GOOEY_E_INVALID; }
+  return GOOEY_E_OK;
+}
 // 16-bit mono WAV from samples that are already PCM (the device-quantised drain)
 static int write_wav_pcm16(const char* utf8_path, const int16_t* pcm, uint32_t n, uint32_t sample_rate) {
   const uint64_t data_bytes = (uint64_t)n * 2;

@@ -139,6 +139,29 @@ class Engine:
         f.argtypes = [c.c_void_p, c.c_void_p]; f.restype = c.c_bool
         return bool(f(self._h, other._h))
 
+    def get_channel_peaks(self, count=5):
+        """gooey_engine_get_channel_peaks: read-and-reset pre-pan peaks of the five voice strips."""
+        out = (c.c_float * count)()
+        f = getattr(self._L, self._prefix + "get_channel_peaks")
+        f.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.c_uint32]; f.restype = None
+        f(self._h, out, count)
+        return np.array(out[:], np.float32)
+
+    def mixer_get_track_peak(self, track):
+        f = getattr(self._L, self._prefix + "mixer_get_track_peak")
+        f.argtypes = [c.c_void_p, c.c_uint32]; f.restype = c.c_float
+        return float(f(self._h, track))
+
+    def drain_midi_events(self, max_events=64):
+        """gooey_engine_drain_midi_events: [(instrument_index, velocity, sample_offset)] of the last render call."""
+        class Ev(c.Structure):
+            _fields_ = [("instrument_index", c.c_uint32), ("velocity", c.c_float), ("sample_offset", c.c_uint32)]
+        buf = (Ev * max_events)()
+        f = getattr(self._L, self._prefix + "drain_midi_events")
+        f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32]; f.restype = c.c_uint32
+        n = f(self._h, buf, max_events)
+        return [(int(buf[i].instrument_index), float(buf[i].velocity), int(buf[i].sample_offset)) for i in range(n)]
+
     # ---- product-only entry points (no oracle counterpart) ----
     def bounce_to_wav(self, bars, path):
         """gooey_engine_bounce_to_wav: mono 16-bit PCM of the bounce."""

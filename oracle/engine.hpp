@@ -72,6 +72,7 @@ static inline std::unique_ptr<StereoEffect> make_channel_effect(uint32_t id, flo
 struct Track {
   SmoothedParam gain, pan, mute_gain;
   bool muted = false, soloed = false;
+  float peak = 0.0f;                                  // post-strip peak, read-and-reset (graph.rs:93-98, 233-237)
   std::vector<std::unique_ptr<StereoEffect>> rack;
   explicit Track(float sr) : gain(1.0f, 0.0f, 2.0f, sr, 10.0f), pan(0.5f, 0.0f, 1.0f, sr, 10.0f), mute_gain(1.0f, 0.0f, 1.0f, sr, 10.0f) {}
 };
@@ -107,6 +108,7 @@ struct MixerGraph {
       StereoFrame f = scratch[i].scaled(g);
       f = balanced(f, t.pan.tick());
       for (auto& e : t.rack) f = e->process_stereo(f);
+      { float lv = rust_max(fabsf(f.l), fabsf(f.r)); if (lv > t.peak) t.peak = lv; }   // record_peak(f.l.abs().max(f.r.abs())) (:395)
       master += f;
     }
     return master;
@@ -123,6 +125,7 @@ struct VoiceStrip {
   float trigger_velocity = 1.0f;
   bool has_saved = false;
   float saved_freq = 0;
+  float peak = 0.0f;                                  // pre-pan mono peak, read-and-reset (ffi.rs:654-659, 2572-2584)
   VoiceStrip(std::unique_ptr<Instrument> i, uint32_t t, float bpm, float sr)
       : inst(std::move(i)), type(t), seq(bpm, sr, 16, false), channel_gain(1.0f, 0, 1, sr, 10.0f), mute_gain(1.0f, 0, 1, sr, 10.0f), pan(0.5f, 0, 1, sr, 10.0f) {}
 };
@@ -157,6 +160,9 @@ struct FfiEngine {
   PolySynth poly;
   Granulator granulator;
   MixerGraph graph;
+  struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
+  std::vector<MidiEvent> pending_midi_events;                                                // capacity 64, cleared by every render (:71, :1045)
+  void push_midi_event(uint32_t ch, float vel, uint32_t off) { if (pending_midi_events.size() < 64) pending_midi_events.push_back({ch, vel, off}); }
   explicit FfiEngine(float sr)
       : sample_rate(sr), delay(sr, 2, 120.0f, 0.0f, 0.0f, 20000.0f), tilt(sr), reverb(sr, 0.5f, 0.0f, 0.5f), plate(sr, 0.5f, 0.0f, 0.5f),
         limiter(1.0f), lowpass(sr, 20000.0f, 0.0f), saturation(sr, 0.3f, 0.4f, 0.5f), compressor(sr, -12.0f, 4.0f, 5.0f, 100.0f, 0.5f),
@@ -178,8 +184,10 @@ struct FfiEngine {
   static float midi_to_norm(uint8_t note, float mn, float mx) { float hz = 440.0f * powf(2.0f, ((float)note - 69.0f) / 12.0f); return clampf((hz - mn) / (mx - mn), 0.0f, 1.0f); }
 
   void render(float* buffer, size_t frames) {  // ffi.rs:1043-1382
-    for (auto& v : voices) {
-      if (v.trigger_pending) { v.trigger_pending = false; v.inst->trigger_with_velocity(current_time, v.trigger_velocity); }
+    pending_midi_events.clear();
+    for (size_t ch = 0; ch < voices.size(); ch++) {
+      VoiceStrip& v = voices[ch];
+      if (v.trigger_pending) { v.trigger_pending = false; push_midi_event((uint32_t)ch, v.trigger_velocity, 0); v.inst->trigger_with_velocity(current_time, v.trigger_velocity); }
     }
     const double period = 1.0 / (double)sample_rate;
     bool any_solo = false;
@@ -208,6 +216,7 @@ struct FfiEngine {
             v.inst->snap_params();
           }
           v.inst->trigger_with_velocity(time, trig[ch].velocity);
+          push_midi_event((uint32_t)ch, trig[ch].velocity, (uint32_t)f);
         }
       }
       StereoFrame kit, bassf;
@@ -217,6 +226,7 @@ struct FfiEngine {
         VoiceStrip& v = voices[ch];
         float out = v.inst->tick(time) * v.channel_gain.tick() * v.mute_gain.tick();
         channel_outs[ch] = out;
+        if (fabsf(out) > v.peak) v.peak = fabsf(out);      // record_peak(ch_out.abs()) (:1281-1282)
         StereoFrame p = StereoFrame::panned(out, v.pan.tick());
         if (ch < 4) kit += p; else bassf += p;
       }

@@ -294,6 +294,22 @@ void orc_engine_poly_release(void* e) { if (e) E->poly.release_all(); }
 void orc_engine_poly_set_preset(void* e, uint32_t p) { if (e) E->poly.set_config(PolyConfig::preset(p)); }
 void orc_engine_poly_set_param(void* e, uint32_t p, float v) { if (e) E->poly.set_param(p, v); }
 void orc_engine_render(void* e, float* buf, uint32_t frames) { if (e && buf) E->render(buf, frames); }
+// ffi.rs:2572-2584, 6573-6580, 2145-2167
+void orc_engine_get_channel_peaks(void* e, float* out, uint32_t count) {
+  if (!e || !out) return;
+  for (uint32_t i = 0; i < count && i < 5; i++) { out[i] = E->voices[i].peak; E->voices[i].peak = 0.0f; }
+}
+float orc_engine_mixer_get_track_peak(void* e, uint32_t t) {
+  if (!e || t >= E->graph.tracks.size()) return 0.0f;
+  float p = E->graph.tracks[t].peak; E->graph.tracks[t].peak = 0.0f; return p;
+}
+uint32_t orc_engine_drain_midi_events(void* e, void* out, uint32_t max_events) {
+  if (!e || !out || max_events == 0) return 0;
+  auto& q = E->pending_midi_events;
+  const size_t n = q.size() < max_events ? q.size() : max_events;
+  if (n) { memcpy(out, q.data(), n * sizeof(FfiEngine::MidiEvent)); q.erase(q.begin(), q.begin() + n); }
+  return (uint32_t)n;
+}
 float* orc_engine_bounce_to_buffer(void* e, uint32_t bars, uint32_t* out_len) {
   if (!e || !out_len) return nullptr;
   std::vector<float> v = E->bounce_to_buffer(bars);

@@ -379,3 +379,61 @@ def test_poly_trigger_chord_equals_the_voiced_notes():
     o.close(); g.close()
     assert np.abs(want).max() > 0.01
     assert np.abs(got - want).max() <= TOL
+
+
+def test_peak_meters_and_midi_export_match_the_oracle():
+    """gooey_engine_get_channel_peaks / mixer_get_track_peak (read-and-reset maxima) and gooey_engine_drain_midi_events
+    (ffi.rs:2572-2584, 6573-6580, 2145-2167) over several render calls, with manual triggers, an effect rack and mute."""
+    def script(e):
+        busy_pattern(e)
+        e.set_swing(0.57)
+        e.set_instrument_gain(S.SNARE, 0.6)
+        e.mixer_set_track_gain(0, 1.3); e.mixer_set_track_pan(1, 0.3)
+        e.track_effect_add(0, 2)                                   # saturation on the drum track
+        e.sequencer_start()
+
+    def run(e):
+        script(e)
+        log = []
+        e.trigger_instrument_with_velocity(S.TOM, 0.7)
+        e.render(9000)
+        log.append((e.drain_midi_events(), e.get_channel_peaks(), [e.mixer_get_track_peak(t) for t in range(5)]))
+        e.set_instrument_mute(S.HIHAT, True)
+        e.trigger_instrument(S.KICK)
+        e.render(12000)
+        log.append((e.drain_midi_events(3), e.drain_midi_events(), e.get_channel_peaks(3), [e.mixer_get_track_peak(t) for t in range(4)]))
+        e.render(700)                                              # peaks not read in between: maxima carry over
+        e.render(300)
+        log.append((e.drain_midi_events(), e.get_channel_peaks(), [e.mixer_get_track_peak(t) for t in range(4)]))
+        e.bounce_to_buffer(1)                                      # a bounce is a run of 512-frame renders: the last chunk's events remain
+        log.append((e.drain_midi_events(), e.get_channel_peaks(), [e.mixer_get_track_peak(t) for t in range(4)]))
+        return log
+    o = O.oracle_engine(); g = G.Engine()
+    want, got = run(o), run(g)
+    o.close(); g.close()
+    assert len(want[0][0]) > 3 and want[0][0][0] == (S.TOM, pytest.approx(0.7), 0)
+
+    def same(a, b):
+        if len(a) == 0 or len(b) == 0:
+            assert len(a) == len(b), (a, b)
+        elif isinstance(a, (list, tuple)) and isinstance(a[0], tuple):               # midi events: exact
+            assert [(x[0], x[2]) for x in a] == [(x[0], x[2]) for x in b]
+            assert np.array_equal(np.array([x[1] for x in a], np.float32), np.array([x[1] for x in b], np.float32))
+        else:
+            a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
+            assert a.shape == b.shape and np.abs(a - b).max() <= TOL, (a, b)
+    for w, g_ in zip(want, got):
+        assert len(w) == len(g_)
+        for a, b in zip(w, g_):
+            same(a, b)
+    assert max(want[0][1]) > 0.01 and max(want[0][2]) > 0.01
+
+
+def test_float_wav_writer(tmp_path):
+    from libgooey_b200 import bounce as B
+    import struct
+    x = np.linspace(-1, 1, 2000, dtype=np.float32).reshape(1000, 2)
+    B.write_wav_f32(tmp_path / "f.wav", x, 44100)
+    raw = (tmp_path / "f.wav").read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and struct.unpack("<HHIIHH", raw[20:36]) == (3, 2, 44100, 44100 * 8, 8, 32)
+    assert np.array_equal(np.frombuffer(raw[44:], np.float32).reshape(1000, 2), x)
