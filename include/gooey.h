@@ -125,6 +125,47 @@ int gooey_batch_bounce_to_wav(GooeyEngine* const* engines, uint32_t n, uint32_t 
 /* Batch of gooey_engine_render: interleaved stereo, out_host[i * 2 * frames + 2 * f + ch]. */
 int gooey_batch_render(GooeyEngine* const* engines, uint32_t n, uint32_t frames, float* out_host);
 
+/* ---- LFO pool (:4616-4993; engine/lfo.rs:170-185): eight sine LFOs synced to the tempo (timing 0..7 = 4 bars, 2 bars, 1 bar, 1/2,
+ * 1/4, 1/8, 1/16, 1/32), value = offset + sin(2 pi phase) * amount.  Every frame, after the sequencer's triggers and before the
+ * voices tick, each enabled LFO writes `value * depth` (bipolar, -1..1 onto the parameter's range) to its routed channel parameters
+ * (:1238-1251, :322-405).  Routed voices are rendered on the per-sample path. */
+uint32_t gooey_engine_lfo_count(void);
+uint32_t gooey_engine_lfo_timing_count(void);
+void gooey_engine_set_lfo_enabled(GooeyEngine* engine, uint32_t lfo_index, bool enabled);
+bool gooey_engine_get_lfo_enabled(const GooeyEngine* engine, uint32_t lfo_index);
+void gooey_engine_set_lfo_timing(GooeyEngine* engine, uint32_t lfo_index, uint32_t timing);
+uint32_t gooey_engine_get_lfo_timing(const GooeyEngine* engine, uint32_t lfo_index);     /* 0xFFFFFFFF for a bad argument */
+void gooey_engine_set_lfo_amount(GooeyEngine* engine, uint32_t lfo_index, float amount);
+float gooey_engine_get_lfo_amount(const GooeyEngine* engine, uint32_t lfo_index);
+void gooey_engine_set_lfo_offset(GooeyEngine* engine, uint32_t lfo_index, float offset);
+float gooey_engine_get_lfo_offset(const GooeyEngine* engine, uint32_t lfo_index);
+uint32_t gooey_engine_add_lfo_route(GooeyEngine* engine, uint32_t lfo_index, uint32_t instrument, uint32_t param, float depth);   /* route id, 0xFFFFFFFF when full (16) */
+bool gooey_engine_remove_lfo_route(GooeyEngine* engine, uint32_t lfo_index, uint32_t route_id);
+void gooey_engine_clear_lfo_routes(GooeyEngine* engine, uint32_t lfo_index);
+uint32_t gooey_engine_get_lfo_route_count(const GooeyEngine* engine, uint32_t lfo_index);
+void gooey_engine_reset_lfo_phase(GooeyEngine* engine, uint32_t lfo_index);
+float gooey_engine_get_lfo_phase(const GooeyEngine* engine, uint32_t lfo_index);          /* -1 for a bad argument */
+
+/* ---- preset blend: X/Y pad over four corner presets (:5245-5490; utils/blendable.rs:73-86) and per-step blends (:4009-4075) ----
+ * A blend is `<Voice>::set_config(bilinear(corners, x, y))`.  set_position applies it at once (only while enabled); at every
+ * sequencer trigger the step's own blend — or, when blending is enabled, the pad position — is applied and followed by
+ * snap_params (:1162-1171, :1384-1402).  Corner presets: GOOEY_*_PRESET ids 0..3 of the channel's instrument type. */
+void gooey_engine_blend_enable(GooeyEngine* engine, uint32_t instrument);
+void gooey_engine_blend_disable(GooeyEngine* engine, uint32_t instrument);
+bool gooey_engine_blend_is_enabled(const GooeyEngine* engine, uint32_t instrument);
+void gooey_engine_blend_set_position(GooeyEngine* engine, uint32_t instrument, float x, float y);
+float gooey_engine_blend_get_position_x(const GooeyEngine* engine, uint32_t instrument);   /* -1 for a bad argument */
+float gooey_engine_blend_get_position_y(const GooeyEngine* engine, uint32_t instrument);
+void gooey_engine_blend_set_corner_preset(GooeyEngine* engine, uint32_t instrument, uint32_t corner, uint32_t preset_id);
+uint32_t gooey_engine_blend_get_corner_preset(const GooeyEngine* engine, uint32_t instrument, uint32_t corner);   /* 0xFFFFFFFF for a bad argument */
+void gooey_engine_blend_reset_corners(GooeyEngine* engine, uint32_t instrument);
+void gooey_engine_sequencer_set_instrument_step_blend(GooeyEngine* engine, uint32_t instrument, uint32_t step, float x, float y);
+void gooey_engine_sequencer_set_instrument_step_blend_override(GooeyEngine* engine, uint32_t instrument, uint32_t step, float x, float y);   /* legacy alias */
+void gooey_engine_sequencer_clear_instrument_step_blend(GooeyEngine* engine, uint32_t instrument, uint32_t step);
+void gooey_engine_sequencer_clear_instrument_step_blend_override(GooeyEngine* engine, uint32_t instrument, uint32_t step);
+float gooey_engine_sequencer_get_instrument_step_blend_x(const GooeyEngine* engine, uint32_t instrument, uint32_t step);   /* -1: no blend on the step */
+float gooey_engine_sequencer_get_instrument_step_blend_y(const GooeyEngine* engine, uint32_t instrument, uint32_t step);
+
 /* ---- meters and MIDI export ---- */
 /* :2572-2584 — per-channel peak |x| (pre-pan, post gain x mute) since the last call, reset to 0 by the read; count <= 5. */
 void gooey_engine_get_channel_peaks(GooeyEngine* engine, float* out_peaks, uint32_t count);

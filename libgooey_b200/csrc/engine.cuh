@@ -18,7 +18,7 @@ namespace gh {
 // SmoothedParam ticking once per sample while running.  Instead of ticking every sample it jumps from firing to firing;
 // the swing smoother is stepped sample by sample only while it is unsettled.
 struct SeqStep { bool enabled = false; float velocity = 1.0f; bool has_note = false; uint8_t note = 0; bool has_blend = false; float bx = 0, by = 0; };
-struct SeqFire { uint32_t frame; float velocity; bool has_note; uint8_t note; };
+struct SeqFire { uint32_t frame; float velocity; bool has_note; uint8_t note; bool has_blend; float bx, by; };
 struct HostSeq {
   float bpm = 120.0f, sr = 44100.0f, sps = 0.0f;
   uint64_t sample_count = 0, next_trigger = 0;
@@ -44,13 +44,104 @@ struct HostSeq {
       sample_count += wait; f += (uint32_t)wait;
       swing_ticks(1);
       const SeqStep& st = pattern[current_step];
-      if (st.enabled) out.push_back({f, st.velocity, st.has_note, st.note});
+      if (st.enabled) out.push_back({f, st.velocity, st.has_note, st.note, st.has_blend, st.bx, st.by});
       current_step = (current_step + 1) % pattern.size();
       const float swing_offset = (sw_cur - 0.5f) * 2.0f * sps;
       const float signed_off = (current_step % 2 == 1) ? swing_offset : -swing_offset;
       const float nx = roundf((float)next_trigger + sps + signed_off);
       next_trigger = gd::f32_to_u64_sat(nx);
       sample_count += 1; f += 1;
+    }
+  }
+};
+
+// ---- utils/blendable.rs PresetBlender over the channel's config (ffi.rs ChannelBlender :405-560) ----------------------
+// Presets as flat values in the order of the config's fields; preset ids ffi.rs:1882-1998.  Returns the field count (0 = unknown).
+inline int preset_flat(uint32_t type, uint32_t id, float* v) {
+  static const float KICK[4][18] = {   // KickConfig::{tight,punch,loose,dirt} (kick.rs:257-350)
+      {0.22f, 0.00f, 1.00f, 0.00f, 0.12f, 0.70f, 0.01f, 0.85f, 0.64f, 1.00f, 0.07f, 0.01f, 0.02f, 0.20f, 0.00f, 0.47f, 0.12f, 0.02f},
+      {0.50f, 0.20f, 1.00f, 0.20f, 0.12f, 0.60f, 0.10f, 0.85f, 0.24f, 1.00f, 0.07f, 0.11f, 0.42f, 0.20f, 0.00f, 0.47f, 0.12f, 0.02f},
+      {0.32f, 0.40f, 1.00f, 0.00f, 0.62f, 0.20f, 0.12f, 0.85f, 0.84f, 1.00f, 0.07f, 0.01f, 0.02f, 0.25f, 0.00f, 0.47f, 0.12f, 0.12f},
+      {0.62f, 0.10f, 1.00f, 0.10f, 0.10f, 0.60f, 0.10f, 0.85f, 0.44f, 1.00f, 0.20f, 0.10f, 0.82f, 0.20f, 0.00f, 0.47f, 0.10f, 0.10f}};
+  const float d = 0.029f;   // SnareConfig::tight() = new(0.2, 0.4, 0.7, 0.5, 0.029, 0.3, 0.8): derived decays in f32 (snare.rs:99-132)
+  const float SNARE[4][19] = {   // SnareConfig::{tight,loose,hiss,smack} (snare.rs:270-351), new_full order
+      {0.2f, 0.4f, 0.7f, 0.5f, d, 0.3f, 0.8f, d * 0.8f, 0.091f, d * 0.6f, d, 0.495f, 0.053f, 1.0f, 0.5f, 0.0f, 0.0f, 0.125f, 0.02f},
+      {0.16f, 0.80f, 0.60f, 0.30f, 0.79f, 0.10f, 0.90f, 0.33f, 0.20f, 0.23f, 0.34f, 0.55f, 0.05f, 1.0f, 0.50f, 0.00f, 0.10f, 0.12f, 0.02f},
+      {0.16f, 0.00f, 0.60f, 0.30f, 0.04f, 0.40f, 0.90f, 0.53f, 0.09f, 0.38f, 0.29f, 0.29f, 0.45f, 1.0f, 0.50f, 1.00f, 0.20f, 0.18f, 0.02f},
+      {0.2f, 0.3f, 0.8f, 0.0f, 0.029f, 0.3f, 0.85f, 0.014f, 0.091f, 0.034f, 0.086f, 0.293f, 0.158f, 1.0f, 0.4f, 0.5f, 0.0f, 0.125f, 0.02f}};
+  static const float HAT[4][7] = {     // HiHat2Config::{short,loose,dark,soft} (hihat2.rs:79-96): pitch, decay, attack, pink, db24, tone, volume
+      {0.76f, 0.05f, 0.00f, 0.0f, 1.0f, 1.00f, 1.0f}, {0.76f, 0.30f, 0.00f, 0.0f, 1.0f, 1.00f, 1.0f},
+      {0.41f, 0.05f, 0.00f, 0.0f, 1.0f, 0.15f, 1.0f}, {0.41f, 0.05f, 0.15f, 0.0f, 1.0f, 0.60f, 1.0f}};
+  static const float TOM[4][8] = {     // Tom2Config::{derp,ring,brush,void_preset} (tom2.rs:119-172)
+      {60.0f, 70.0f, 50.0f, 0.0f, 20.0f, 0.0f, 50.0f, 100.0f}, {80.0f, 20.0f, 10.0f, 0.0f, 100.0f, 60.0f, 70.0f, 100.0f},
+      {40.0f, 20.0f, 10.0f, 90.0f, 30.0f, 0.0f, 50.0f, 100.0f}, {60.0f, 30.0f, 100.0f, 50.0f, 90.0f, 40.0f, 80.0f, 100.0f}};
+  static const float BASS[4][15] = {   // BassConfig::{acid,sub,reese,stab} (bass.rs:188-269)
+      {0.24f, 0.40f, 0.80f, 0.00f, 0.00f, 0.10f, 0.15f, 0.70f, 0.85f, 0.15f, 0.08f, 0.35f, 0.10f, 0.30f, 0.80f},
+      {0.18f, 1.00f, 0.15f, 0.00f, 0.00f, 0.00f, 0.70f, 0.05f, 0.10f, 0.30f, 0.20f, 0.60f, 0.15f, 0.00f, 0.85f},
+      {0.18f, 0.30f, 0.80f, 0.80f, 0.50f, 0.05f, 0.35f, 0.30f, 0.50f, 0.40f, 0.15f, 0.55f, 0.12f, 0.60f, 0.80f},
+      {0.30f, 0.20f, 0.90f, 0.00f, 0.00f, 0.90f, 0.20f, 0.40f, 0.90f, 0.08f, 0.05f, 0.20f, 0.08f, 0.20f, 0.80f}};
+  if (id > 3) return 0;
+  const float* src; int n;
+  switch (type) {
+    case GOOEY_INSTRUMENT_KICK: src = KICK[id]; n = 18; break;
+    case GOOEY_INSTRUMENT_SNARE: src = SNARE[id]; n = 19; break;
+    case GOOEY_INSTRUMENT_HIHAT: src = HAT[id]; n = 7; break;
+    case GOOEY_INSTRUMENT_TOM: src = TOM[id]; n = 8; break;
+    case GOOEY_INSTRUMENT_BASS: src = BASS[id]; n = 15; break;
+    default: return 0;
+  }
+  for (int i = 0; i < n; i++) v[i] = src[i];
+  return n;
+}
+struct ChannelBlender {
+  uint32_t type = 0; int n = 0;
+  float corner[4][24];                       // bottom_left, bottom_right, top_left, top_right
+  uint32_t corner_ids[4] = {0, 1, 2, 3};
+  void default_for_type(uint32_t t) { type = t; for (uint32_t c = 0; c < 4; c++) { n = preset_flat(t, c, corner[c]); corner_ids[c] = c; } }
+  bool discrete(int i) const { return (type == GOOEY_INSTRUMENT_SNARE && i == 13) || (type == GOOEY_INSTRUMENT_HIHAT && (i == 3 || i == 4)); }
+  void lerp(const float* a, const float* b, float t, float* o) const {   // impl Blendable: self * inv_t + other * t, enums switch at t = 0.5
+    t = gd::clampf(t, 0.0f, 1.0f);
+    volatile float inv_t = 1.0f - t;           // (volatile: keep the two roundings of `a * inv_t + b * t`, no host FMA contraction)
+    for (int i = 0; i < n; i++) {
+      if (discrete(i)) { o[i] = t < 0.5f ? a[i] : b[i]; continue; }
+      volatile float p = a[i] * inv_t, q = b[i] * t;
+      o[i] = p + q;
+    }
+  }
+  void blend(float x, float y, float* o) const {   // blendable.rs:73-86
+    x = gd::clampf(x, 0.0f, 1.0f); y = gd::clampf(y, 0.0f, 1.0f);
+    float bottom[24], top[24];
+    lerp(corner[0], corner[1], x, bottom);
+    lerp(corner[2], corner[3], x, top);
+    lerp(bottom, top, y, o);
+  }
+  void set_corner_preset(uint32_t c, uint32_t id) { float v[24]; if (c < 4 && preset_flat(type, id, v) > 0) for (int i = 0; i < n; i++) corner[c][i] = v[i]; }
+  // `<Voice>::set_config(blend(x, y))` as voice events at `frame` (kick.rs:905-941, snare.rs:818-855, hihat2.rs:382-390, tom2.rs:400-411, bass.rs:636-662)
+  template <class Add> void apply(float x, float y, uint32_t frame, Add add) const {
+    float v[24];
+    blend(x, y, v);
+    switch (type) {
+      case GOOEY_INSTRUMENT_KICK: for (int i = 0; i < 18; i++) add(make_event(frame, gd::EV_SET_TARGET, i, v[i])); break;
+      case GOOEY_INSTRUMENT_SNARE: {
+        float cfg[18]; uint32_t ft;
+        snare_cfg_from_patch(v, cfg, ft);
+        volatile float psm = v[5] * 1.5f;
+        add(make_event(frame, gd::EV_SET_AUX, gd::AUX_SNARE_PITCH_START, 1.0f + psm));
+        for (int i = 0; i < 18; i++) add(make_event(frame, gd::EV_SET_TARGET, i, cfg[i]));
+        add(make_event(frame, gd::EV_SET_AUX, gd::AUX_SNARE_FILTER_TYPE, (float)ft));
+      } break;
+      case GOOEY_INSTRUMENT_HIHAT:
+        add(make_event(frame, gd::EV_SET_TARGET, gd::H_PITCH, v[0])); add(make_event(frame, gd::EV_SET_TARGET, gd::H_DECAY, v[1]));
+        add(make_event(frame, gd::EV_SET_TARGET, gd::H_ATTACK, v[2])); add(make_event(frame, gd::EV_SET_TARGET, gd::H_TONE, v[5]));
+        add(make_event(frame, gd::EV_SET_TARGET, gd::H_VOLUME, v[6]));
+        add(make_event(frame, gd::EV_SET_AUX, gd::AUX_HAT_PINK, v[3])); add(make_event(frame, gd::EV_SET_AUX, gd::AUX_HAT_DB24, v[4]));
+        break;
+      case GOOEY_INSTRUMENT_TOM:
+        for (int i = 0; i < 8; i++) add(make_event(frame, gd::EV_SET_AUX, gd::AUX_TOM_RAW_PARAM0 + i, v[i]));
+        add(make_event(frame, gd::EV_SET_AUX, gd::AUX_TOM_CONFIG_DONE, 0.0f));
+        break;
+      case GOOEY_INSTRUMENT_BASS: for (int i = 0; i < 15; i++) add(make_event(frame, gd::EV_SET_TARGET, i, v[i])); break;
+      default: break;
     }
   }
 };
@@ -116,6 +207,9 @@ struct EngineBank {
   DevBuf<uint8_t> d_mix_fast;
   DevBuf<gd::MixConst> d_mix_consts;
   DevBuf<float> d_premix;                 // [2][n_lpad][vstride]: pre-chain stereo mix of the engines whose strips are time-parallel
+  DevBuf<gd::LfoStream> d_lfo_streams;    // LFO pool of the current render call
+  DevBuf<float> d_lfo_planes;             // [routed streams][frames] LFO values
+  std::vector<gd::LfoStream> h_lfo_streams;
   DevBuf<float> d_peaks;                  // [n][N_PEAKS] maxima of the current render call
   std::vector<float> h_peaks;
   DevBuf<gd::VoiceEvent> d_mix_eventss[2];
@@ -174,6 +268,7 @@ struct GooeyEngine {
     bool muted = false, soloed = false, trig_pending = false;
     float trig_vel = 1.0f;
     std::vector<gd::VoiceEvent> pending;
+    gh::ChannelBlender blender; bool blend_enabled = false; float blend_x = 0.5f, blend_y = 0.5f;   // ffi.rs:598-600
   } strip[5];
   // poly synth and granulator: their FFI calls act immediately in the reference (ffi.rs:5571-5648, 7702-7827); here they
   // queue events that are applied before frame 0 of the next render — the same instant, since nothing ticks in between.
@@ -188,6 +283,12 @@ struct GooeyEngine {
   gd::MixCfg cfg;
   std::vector<gd::VoiceEvent> mix_pending;
   bool track_muted[gd::MAX_TRACKS] = {false}, track_soloed[gd::MAX_TRACKS] = {false};
+  // LFO pool (ffi.rs:33-54, 716-719, 876-884): eight tempo-synced sine LFOs, disabled, Quarter division, amount 1, offset 0
+  struct LfoHost { uint32_t division = 4; float phase = 0.0f, amount = 1.0f, offset = 0.0f; } lfos[8];
+  bool lfo_enabled[8] = {false};
+  struct LfoRoute { uint32_t id, instrument, param; float depth; };
+  std::vector<LfoRoute> lfo_routes[8];
+  uint32_t lfo_next_route_id[8] = {0};
   bool seq_triggers_enabled = true;
   float peaks[gd::N_PEAKS] = {0};          // read-and-reset meters (ffi.rs:2572-2584, graph.rs:233-237), merged after every render
   struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
@@ -241,6 +342,7 @@ inline GooeyEngine* engine_create(int device, float sr) {
     e->strip[ch].type = p[ch].instrument;
     e->strip[ch].slot = B.voices.create(p[ch], sr);
     e->strip[ch].seq.init(120.0f, sr);
+    e->strip[ch].blender.default_for_type(p[ch].instrument);
   }
   {
     GooeyVoicePatch q;
@@ -306,6 +408,21 @@ inline float midi_to_norm(uint8_t note, float mn, float mx) {
 }
 
 enum { OUT_MONO = 0, OUT_STEREO = 1 };
+
+// ChannelInstrument::apply_modulation (ffi.rs:322-405): FFI parameter id of the channel's instrument type -> internal
+// parameter index + how the bipolar value lands on it.  false: the id is not modulatable (ignored, like the reference).
+inline bool lfo_route_target(uint32_t type, uint32_t ffi_param, uint32_t& param, uint32_t& mode) {
+  mode = 0;
+  switch (type) {
+    case GOOEY_INSTRUMENT_KICK: if (ffi_param >= 8 || ffi_param == 5) return false; param = (uint32_t)kKickFfi[ffi_param]; return true;   // not the pitch envelope (:330-332)
+    case GOOEY_INSTRUMENT_SNARE: if (ffi_param >= 20 || ffi_param == 12) return false; param = (uint32_t)kSnareFfi[ffi_param]; return true;
+    case GOOEY_INSTRUMENT_HIHAT: if (ffi_param >= 6) return false; param = (uint32_t)kHatFfi[ffi_param]; return true;
+    case GOOEY_INSTRUMENT_TOM: if (ffi_param >= 9) return false; param = ffi_param; mode = ffi_param == 8 ? 2u : 1u; return true;
+    case GOOEY_INSTRUMENT_BASS: if (ffi_param >= 16) return false; param = ffi_param; return true;
+    default: return false;
+  }
+}
+inline float lfo_beats(uint32_t d) { const float B[8] = {16.0f, 8.0f, 4.0f, 2.0f, 1.0f, 0.5f, 0.25f, 0.125f}; return B[d < 8 ? d : 4]; }   // lfo.rs:14-25
 
 // First FFI touch of the poly synth / granulator of an engine: from now on the voice is launched with the engine.  It was
 // not ticked so far (an untouched poly synth / granulator is bit-exactly silent and its state does not move), so its
@@ -405,15 +522,23 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     for (int ch = 0; ch < 5; ch++) {
       auto& s = e->strip[ch];
       auto& ev = vev[(size_t)i * 7 + ch];
-      if (bounce) ev.push_back(make_event(0, gd::EV_SET_TIME, 0, 0.0f, 0));
       ev.insert(ev.end(), s.pending.begin(), s.pending.end());
       s.pending.clear();
+      // the bounce's clock reset comes after the pending edits: a voice swapped in since the last render carries a
+      // "join the engine clock at k" event that must not outlive the reset (the clock window of a bounce is [0, frames])
+      if (bounce) ev.push_back(make_event(0, gd::EV_SET_TIME, 0, 0.0f, 0));
       if (s.trig_pending) { s.trig_pending = false; ev.push_back(make_event(0, gd::EV_TRIGGER, 0, s.trig_vel)); midi.push_back({0u, 0u, (uint32_t)ch, s.trig_vel}); }
       fires.clear();
       s.seq.run(frames, fires);
       if (e->seq_triggers_enabled) {
         for (const SeqFire& f : fires) midi.push_back({f.frame, 1u, (uint32_t)ch, f.velocity});
         for (const SeqFire& f : fires) {   // ffi.rs:1162-1198
+          // apply_sequencer_blend_setting (:1384-1402): the step's own blend, else the channel's pad position when blending is
+          // on; a blend that was applied is followed by snap_params (:1168-1171)
+          auto add = [&](const gd::VoiceEvent& x) { ev.push_back(x); };
+          if (f.has_blend) s.blender.apply(f.bx, f.by, f.frame, add);
+          else if (s.blend_enabled) s.blender.apply(s.blend_x, s.blend_y, f.frame, add);
+          if (f.has_blend || s.blend_enabled) ev.push_back(make_event(f.frame, gd::EV_SNAP, 0, 0.0f));
           float mn, mxf;
           if (f.has_note) { if (note_freq_range(s.type, mn, mxf)) ev.push_back(make_event(f.frame, gd::EV_NOTE_FREQ, 0, midi_to_norm(f.note, mn, mxf))); }
           else ev.push_back(make_event(f.frame, gd::EV_RESTORE_FREQ, 0, 0.0f));
@@ -474,6 +599,41 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     for (int i = 0; i < n && !any_chain; i++) for (int q = 0; q < gd::MAX_FX; q++) any_chain = any_chain || (E[i]->cfg.fx_kind[q] != gd::FXK_NONE && E[i]->cfg.fx_enabled[q]);
     if (any_chain) B.d_premix.alloc((size_t)2 * n_lpad * vstride);
   }
+  // ---- LFO pool: one stream per enabled LFO; routed ones get a plane of per-frame values (computed on the device) ----
+  std::vector<std::vector<gd::ModRoute>> vroutes((size_t)n * 5);
+  struct LfoRef { int engine, lfo; };
+  std::vector<LfoRef> lfo_refs;
+  B.h_lfo_streams.clear();
+  int n_planes = 0;
+  for (int i = 0; i < n; i++) {
+    GooeyEngine* e = E[i];
+    for (int li = 0; li < 8; li++) {
+      if (!e->lfo_enabled[li]) continue;
+      gd::LfoStream sdesc;
+      volatile float bps = e->bpm / 60.0f;                                   // MusicalDivision::to_frequency (lfo.rs:27-33)
+      volatile float freq = bps / lfo_beats(e->lfos[li].division);
+      sdesc.phase = e->lfos[li].phase; sdesc.inc = freq / e->sr; sdesc.amount = e->lfos[li].amount; sdesc.offset = e->lfos[li].offset;
+      sdesc.plane = -1;
+      for (const auto& r : e->lfo_routes[li]) {
+        if (r.instrument >= 5) continue;                                     // voice_mut(channel) is None
+        uint32_t param, mode;
+        if (!lfo_route_target(e->strip[r.instrument].type, r.param, param, mode)) continue;
+        if (sdesc.plane < 0) sdesc.plane = n_planes++;
+        vroutes[(size_t)i * 5 + r.instrument].push_back(gd::ModRoute{param, mode, r.depth, (uint32_t)sdesc.plane});
+      }
+      B.h_lfo_streams.push_back(sdesc);
+      lfo_refs.push_back({i, li});
+    }
+  }
+  const float* lfo_planes = nullptr;
+  if (!B.h_lfo_streams.empty()) {
+    B.d_lfo_streams.upload(B.h_lfo_streams.data(), B.h_lfo_streams.size(), st);
+    if (n_planes) B.d_lfo_planes.alloc((size_t)n_planes * frames);
+    gd::lfo_kernel<<<((int)B.h_lfo_streams.size() + 63) / 64, 64, 0, st>>>(B.d_lfo_streams.p, (int)B.h_lfo_streams.size(), B.d_lfo_planes.p, (long long)frames, (int)frames);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    GH_CUDA(cudaGetLastError());
+    if (n_planes) lfo_planes = B.d_lfo_planes.p;
+  }
   B.d_peaks.alloc((size_t)n * gd::N_PEAKS);
   GH_CUDA(cudaMemsetAsync(B.d_peaks.p, 0, (size_t)n * gd::N_PEAKS * 4, st));
   cudaStream_t ms = B.mix_stream;
@@ -514,12 +674,13 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
         while (p < ev.size() && ev[p].frame < f0 + nf) { gd::VoiceEvent x = ev[p++]; x.frame -= f0; cur.push_back(x); }
         const uint32_t type = ch < 5 ? E[i]->strip[ch].type : (ch == 5 ? GOOEY_B200_VOICE_POLY : GOOEY_B200_VOICE_GRANULATOR);
         const int slot = ch < 5 ? E[i]->strip[ch].slot : (ch == 5 ? E[i]->poly.slot : E[i]->gran.slot);
-        B.voices.add(type, (uint32_t)slot, (uint32_t)(ch * n_lpad + i), cur);
+        B.voices.add(type, (uint32_t)slot, (uint32_t)(ch * n_lpad + i), cur, (ch < 5 && lfo_planes && !vroutes[(size_t)i * 5 + ch].empty()) ? &vroutes[(size_t)i * 5 + ch] : nullptr);
       }
     cudaEvent_t start = B.ev_piece;
     GH_CUDA(cudaEventRecord(start, st));
     // the clock index differs per engine only through e->k; voices carry their own k, the launch passes the table
     tev(tv0, st);
+    B.voices.set_mod(lfo_planes, (long long)frames, (int)f0);
     B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_bufs[vb].p, (long long)vstride);
     tev(tv1, st);
     GH_CUDA(cudaEventRecord(B.ev_voices[vb], st));
@@ -582,7 +743,9 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   // meters: the call's maxima join the engines' read-and-reset peaks (one small copy; the caller synchronises the stream anyway)
   B.h_peaks.resize((size_t)n * gd::N_PEAKS);
   GH_CUDA(cudaMemcpyAsync(B.h_peaks.data(), B.d_peaks.p, B.h_peaks.size() * 4, cudaMemcpyDeviceToHost, st));
+  if (!B.h_lfo_streams.empty()) GH_CUDA(cudaMemcpyAsync(B.h_lfo_streams.data(), B.d_lfo_streams.p, B.h_lfo_streams.size() * sizeof(gd::LfoStream), cudaMemcpyDeviceToHost, st));
   GH_CUDA(cudaStreamSynchronize(st));
+  for (size_t q = 0; q < lfo_refs.size(); q++) E[lfo_refs[q].engine]->lfos[lfo_refs[q].lfo].phase = B.h_lfo_streams[q].phase;
   for (int i = 0; i < n; i++) {
     for (int q = 0; q < gd::N_PEAKS; q++) { const float v = B.h_peaks[(size_t)i * gd::N_PEAKS + q]; if (v > E[i]->peaks[q]) E[i]->peaks[q] = v; }
     E[i]->k += frames;

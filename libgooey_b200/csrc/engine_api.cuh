@@ -98,9 +98,81 @@ void gooey_engine_set_channel_instrument_type(GooeyEngine* e, uint32_t ch, uint3
     s.type = type; s.slot = slot;
     s.pending.clear();
     s.pending.push_back(gh::make_event(0, gd::EV_SET_TIME, 0, 0.0f, e->k));   // the fresh voice joins the engine's clock
+    s.blender.default_for_type(type);                                          // ffi.rs:2334-2342
+    if (s.blend_enabled) s.blender.apply(s.blend_x, s.blend_y, 0, [&](const gd::VoiceEvent& x) { s.pending.push_back(x); });
   } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); }
 }
 uint32_t gooey_engine_get_channel_instrument_type(const GooeyEngine* e, uint32_t ch) { return (e && ch < 5) ? e->strip[ch].type : 0xFFFFFFFFu; }   /* :2354-2371 */
+
+// ---- LFO pool (ffi.rs:4616-4993): eight tempo-synced sine LFOs, each routed to up to 16 (channel, parameter, depth) targets ----
+uint32_t gooey_engine_lfo_count(void) { return 8; }
+uint32_t gooey_engine_lfo_timing_count(void) { return 8; }
+void gooey_engine_set_lfo_enabled(GooeyEngine* e, uint32_t i, bool on) { if (e && i < 8) e->lfo_enabled[i] = on; }
+bool gooey_engine_get_lfo_enabled(const GooeyEngine* e, uint32_t i) { return e && i < 8 && e->lfo_enabled[i]; }
+void gooey_engine_set_lfo_timing(GooeyEngine* e, uint32_t i, uint32_t timing) { if (e && i < 8 && timing < 8) e->lfos[i].division = timing; }
+uint32_t gooey_engine_get_lfo_timing(const GooeyEngine* e, uint32_t i) { return (e && i < 8) ? e->lfos[i].division : 0xFFFFFFFFu; }
+void gooey_engine_set_lfo_amount(GooeyEngine* e, uint32_t i, float a) { if (e && i < 8) e->lfos[i].amount = a; }
+float gooey_engine_get_lfo_amount(const GooeyEngine* e, uint32_t i) { return (e && i < 8) ? e->lfos[i].amount : 0.0f; }
+void gooey_engine_set_lfo_offset(GooeyEngine* e, uint32_t i, float o) { if (e && i < 8) e->lfos[i].offset = o; }
+float gooey_engine_get_lfo_offset(const GooeyEngine* e, uint32_t i) { return (e && i < 8) ? e->lfos[i].offset : 0.0f; }
+uint32_t gooey_engine_add_lfo_route(GooeyEngine* e, uint32_t i, uint32_t instrument, uint32_t param, float depth) {
+  if (!e || i >= 8 || e->lfo_routes[i].size() >= 16) return 0xFFFFFFFFu;
+  const uint32_t id = e->lfo_next_route_id[i]++;
+  e->lfo_routes[i].push_back({id, instrument, param, depth});
+  return id;
+}
+bool gooey_engine_remove_lfo_route(GooeyEngine* e, uint32_t i, uint32_t route_id) {
+  if (!e || i >= 8) return false;
+  auto& r = e->lfo_routes[i];
+  for (size_t k = 0; k < r.size(); k++) if (r[k].id == route_id) { r.erase(r.begin() + k); return true; }
+  return false;
+}
+void gooey_engine_clear_lfo_routes(GooeyEngine* e, uint32_t i) { if (e && i < 8) e->lfo_routes[i].clear(); }
+uint32_t gooey_engine_get_lfo_route_count(const GooeyEngine* e, uint32_t i) { return (e && i < 8) ? (uint32_t)e->lfo_routes[i].size() : 0u; }
+void gooey_engine_reset_lfo_phase(GooeyEngine* e, uint32_t i) { if (e && i < 8) e->lfos[i].phase = 0.0f; }
+float gooey_engine_get_lfo_phase(const GooeyEngine* e, uint32_t i) { return (e && i < 8) ? e->lfos[i].phase : -1.0f; }
+
+// ---- preset blend: 2-D pad over four corner presets (ffi.rs:5245-5490) and per-step blends (:4009-4075, 4314-4380) ----
+void gooey_engine_blend_enable(GooeyEngine* e, uint32_t inst) { if (e && inst < 5) e->strip[inst].blend_enabled = true; }
+void gooey_engine_blend_disable(GooeyEngine* e, uint32_t inst) { if (e && inst < 5) e->strip[inst].blend_enabled = false; }
+bool gooey_engine_blend_is_enabled(const GooeyEngine* e, uint32_t inst) { return e && inst < 5 && e->strip[inst].blend_enabled; }
+void gooey_engine_blend_set_position(GooeyEngine* e, uint32_t inst, float x, float y) {
+  if (!e || inst >= 5) return;
+  GooeyEngine::Strip& s = e->strip[inst];
+  if (!s.blend_enabled) return;
+  s.blend_x = gd::clampf(x, 0.0f, 1.0f); s.blend_y = gd::clampf(y, 0.0f, 1.0f);
+  s.blender.apply(s.blend_x, s.blend_y, 0, [&](const gd::VoiceEvent& ev) { s.pending.push_back(ev); });
+}
+float gooey_engine_blend_get_position_x(const GooeyEngine* e, uint32_t inst) { return (e && inst < 5) ? e->strip[inst].blend_x : -1.0f; }
+float gooey_engine_blend_get_position_y(const GooeyEngine* e, uint32_t inst) { return (e && inst < 5) ? e->strip[inst].blend_y : -1.0f; }
+void gooey_engine_blend_set_corner_preset(GooeyEngine* e, uint32_t inst, uint32_t corner, uint32_t preset_id) {
+  if (!e || inst >= 5 || corner >= 4) return;
+  e->strip[inst].blender.corner_ids[corner] = preset_id;
+  e->strip[inst].blender.set_corner_preset(corner, preset_id);
+}
+uint32_t gooey_engine_blend_get_corner_preset(const GooeyEngine* e, uint32_t inst, uint32_t corner) {
+  return (e && inst < 5 && corner < 4) ? e->strip[inst].blender.corner_ids[corner] : 0xFFFFFFFFu;
+}
+void gooey_engine_blend_reset_corners(GooeyEngine* e, uint32_t inst) { if (e && inst < 5) e->strip[inst].blender.default_for_type(e->strip[inst].type); }
+void gooey_engine_sequencer_set_instrument_step_blend(GooeyEngine* e, uint32_t inst, uint32_t step, float x, float y) {
+  if (!e || inst >= 5 || step >= e->strip[inst].seq.pattern.size()) return;
+  gh::SeqStep& st = e->strip[inst].seq.pattern[step];
+  st.has_blend = true; st.bx = gd::clampf(x, 0.0f, 1.0f); st.by = gd::clampf(y, 0.0f, 1.0f);
+}
+void gooey_engine_sequencer_set_instrument_step_blend_override(GooeyEngine* e, uint32_t inst, uint32_t step, float x, float y) { gooey_engine_sequencer_set_instrument_step_blend(e, inst, step, x, y); }
+void gooey_engine_sequencer_clear_instrument_step_blend(GooeyEngine* e, uint32_t inst, uint32_t step) {
+  if (!e || inst >= 5 || step >= e->strip[inst].seq.pattern.size()) return;
+  e->strip[inst].seq.pattern[step].has_blend = false;
+}
+void gooey_engine_sequencer_clear_instrument_step_blend_override(GooeyEngine* e, uint32_t inst, uint32_t step) { gooey_engine_sequencer_clear_instrument_step_blend(e, inst, step); }
+float gooey_engine_sequencer_get_instrument_step_blend_x(const GooeyEngine* e, uint32_t inst, uint32_t step) {
+  if (!e || inst >= 5 || step >= e->strip[inst].seq.pattern.size() || !e->strip[inst].seq.pattern[step].has_blend) return -1.0f;
+  return e->strip[inst].seq.pattern[step].bx;
+}
+float gooey_engine_sequencer_get_instrument_step_blend_y(const GooeyEngine* e, uint32_t inst, uint32_t step) {
+  if (!e || inst >= 5 || step >= e->strip[inst].seq.pattern.size() || !e->strip[inst].seq.pattern[step].has_blend) return -1.0f;
+  return e->strip[inst].seq.pattern[step].by;
+}
 
 void gooey_engine_load_bass_preset(GooeyEngine* e, uint32_t id) {
   if (!e || id > 3) return;

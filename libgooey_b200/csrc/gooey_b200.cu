@@ -91,13 +91,18 @@ struct VoiceBank {
       default: return -1;
     }
   }
-  void add(uint32_t type, uint32_t slot, uint32_t row, const std::vector<gd::VoiceEvent>& ev) {
+  void set_mod(const float* planes, long long pitch, int frame0) {
+    kicks.mod_planes = snares.mod_planes = hats.mod_planes = toms.mod_planes = basses.mod_planes = planes;
+    kicks.mod_pitch = snares.mod_pitch = hats.mod_pitch = toms.mod_pitch = basses.mod_pitch = pitch;
+    kicks.mod_frame0 = snares.mod_frame0 = hats.mod_frame0 = toms.mod_frame0 = basses.mod_frame0 = frame0;
+  }
+  void add(uint32_t type, uint32_t slot, uint32_t row, const std::vector<gd::VoiceEvent>& ev, const std::vector<gd::ModRoute>* routes = nullptr) {
     switch (type) {
-      case GOOEY_INSTRUMENT_KICK: kicks.add(slot, row, ev); break;
-      case GOOEY_INSTRUMENT_SNARE: snares.add(slot, row, ev); break;
-      case GOOEY_INSTRUMENT_HIHAT: hats.add(slot, row, ev); break;
-      case GOOEY_INSTRUMENT_TOM: toms.add(slot, row, ev); break;
-      case GOOEY_INSTRUMENT_BASS: basses.add(slot, row, ev); break;
+      case GOOEY_INSTRUMENT_KICK: kicks.add(slot, row, ev, routes); break;
+      case GOOEY_INSTRUMENT_SNARE: snares.add(slot, row, ev, routes); break;
+      case GOOEY_INSTRUMENT_HIHAT: hats.add(slot, row, ev, routes); break;
+      case GOOEY_INSTRUMENT_TOM: toms.add(slot, row, ev, routes); break;
+      case GOOEY_INSTRUMENT_BASS: basses.add(slot, row, ev, routes); break;
       case GOOEY_B200_VOICE_POLY: polys.add(slot, row, ev); break;
       case GOOEY_B200_VOICE_GRANULATOR: grans.add(slot, row, ev); break;
     }

@@ -160,6 +160,13 @@ struct GranV { using State = GranState; static constexpr bool FAST = false;
   static __device__ __forceinline__ void slow_event(State& s, const VoiceEvent& e, const double* tt, const RateCtx&) { gran_event(s, e, tt); } };
 
 // ------------------------------------------------------------------------------------------- launch records ----
+// One LFO route of a voice (ffi.rs:1238-1251): every frame, after the frame's events and before the tick, the voice's parameter
+// `param` (internal index) receives `apply_modulation(plane[frame] * depth)` (ffi.rs:322-405).
+//   mode 0: smoothed parameter, set_bipolar (smoother.rs:105-115): target = (clamp(m, -1, 1) + 1) * 0.5
+//   mode 1: Tom2 plain parameter: set_*(m * 100), clamped to 0..100          mode 2: Tom2 tuning: clamp(m, 0, 1)
+struct ModRoute { uint32_t param, mode; float depth; uint32_t plane; };
+struct LfoStream { float phase, inc, amount, offset; int plane; };   // plane: row of the value planes, -1 = enabled but unrouted (the phase still runs)
+
 struct VoiceLaunch {
   uint32_t* state;           // [words][n_pad]
   int n, n_pad;
@@ -182,6 +189,10 @@ struct VoiceLaunch {
   long long plane_stride;    // floats between planes
   int pitch;                 // floats between rows of a plane (chunk capacity, multiple of 32)
   int chunk0, chunk_frames;  // frames [chunk0, chunk0 + chunk_frames) of the call
+  // LFO modulation (nullptr = none): routes of voice v = routes[route_begin[v] .. route_begin[v + 1]); LFO values of the call's
+  // frame j at mod_planes[plane * mod_pitch + mod_frame0 + j]
+  const ModRoute* routes; const uint32_t* route_begin;
+  const float* mod_planes; long long mod_pitch; int mod_frame0;
 };
 
 // Warp-cooperative store of a 32x32 tile (tile[lane][frame]) to voice-major output; row_mask = rows to write.
@@ -250,6 +261,8 @@ __global__ void __launch_bounds__(BLOCK) slow_kernel(const VoiceLaunch L) {
     ev = L.ev_begin[v];
     ev_end = L.ev_begin[v + 1];
   }
+  uint32_t r0 = 0, r1 = 0;
+  if (mine && L.routes) { r0 = L.route_begin[v]; r1 = L.route_begin[v + 1]; }
   float* tile = tiles[warp];
   for (int f0 = 0; f0 < L.frames; f0 += TILE) {
     const int nf = min(TILE, L.frames - f0);
@@ -257,6 +270,13 @@ __global__ void __launch_bounds__(BLOCK) slow_kernel(const VoiceLaunch L) {
       for (int j = 0; j < nf; j++) {
         const uint32_t frame = f0 + j;
         while (ev < ev_end && L.events[ev].frame <= frame) { V::slow_event(st, L.events[ev], L.tt, L.rc); ev++; }
+        for (uint32_t q = r0; q < r1; q++) {       // LFO pool: after the triggers, before the tick
+          const ModRoute r = L.routes[q];
+          const float m = L.mod_planes[(long long)r.plane * L.mod_pitch + L.mod_frame0 + (int)frame] * r.depth;
+          VoiceEvent e; e.frame = frame; e.kind = EV_SET_TARGET; e.param = (uint16_t)r.param; e.aux = 0;
+          e.value = r.mode == 0 ? (clampf(m, -1.0f, 1.0f) + 1.0f) * 0.5f : (r.mode == 1 ? m * 100.0f : clampf(m, 0.0f, 1.0f));
+          V::slow_event(st, e, L.tt, L.rc);
+        }
         tile[lane * 33 + j] = V::tick(st, L.tt, L.rc);
       }
     }
@@ -281,6 +301,7 @@ __global__ void __launch_bounds__(64) plan_kernel(const VoiceLaunch L) {
   const uint32_t ee = L.ev_begin[v + 1];
   uint32_t ns = 0;
   bool fast = V::settled(c);
+  if (L.routes && L.route_begin[v + 1] > L.route_begin[v]) fast = false;     // an LFO writes a new target every frame: per-sample path
   int j = 0;
   while (fast && j < L.frames) {
     uint32_t resets = 0;
@@ -387,6 +408,22 @@ __global__ void __launch_bounds__(BLOCK) back_kernel(const VoiceLaunch L) {
     store_words(a, L.state, sv, L.n_pad, WC);
     L.span_cursor[v] = cur;
   }
+}
+
+// The LFO pool of a batch (engine/lfo.rs:170-185): one thread per (engine, enabled LFO) walks the call's frames —
+// value = sin(phase * 2 * pi); phase += inc, wrapped at 1; out = offset + value * amount — and leaves the final phase.
+__global__ void __launch_bounds__(64) lfo_kernel(LfoStream* __restrict__ streams, int n, float* __restrict__ planes, long long pitch, int frames) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LfoStream s = streams[i];
+  float* out = s.plane >= 0 ? planes + (long long)s.plane * pitch : nullptr;
+  for (int f = 0; f < frames; f++) {
+    const float value = gm::g_sinf(s.phase * 2.0f * PI_F);
+    s.phase += s.inc;
+    if (s.phase >= 1.0f) s.phase -= 1.0f;
+    if (out) out[f] = s.offset + (value * s.amount);
+  }
+  streams[i].phase = s.phase;
 }
 
 }  // namespace gd

@@ -274,6 +274,9 @@ template <class V> struct TypeRunner {
   Pool<State> pool;
   std::vector<uint32_t> slots, rows, ev_begin, span_off;
   std::vector<gd::VoiceEvent> ev_flat;
+  std::vector<gd::ModRoute> routes_flat; std::vector<uint32_t> route_begin;       // LFO routes per voice of this launch
+  DevBuf<gd::ModRoute> d_routes; DevBuf<uint32_t> d_route_begin;
+  const float* mod_planes = nullptr; long long mod_pitch = 0; int mod_frame0 = 0;  // set by the engine path before launch()
   DevBuf<uint32_t> d_slots, d_rows, d_ev_begin, d_span_off, d_n_spans, d_span_cursor;
   DevBuf<gd::VoiceEvent> d_events;
   DevBuf<uint8_t> d_mode, d_spans;
@@ -296,10 +299,13 @@ template <class V> struct TypeRunner {
   }
 
   int n() const { return (int)slots.size(); }
-  void reset() { slots.clear(); rows.clear(); ev_flat.clear(); ev_begin.clear(); ev_begin.push_back(0); span_off.clear(); span_off.push_back(0); }
+  void reset() { slots.clear(); rows.clear(); ev_flat.clear(); ev_begin.clear(); ev_begin.push_back(0); span_off.clear(); span_off.push_back(0);
+                 routes_flat.clear(); route_begin.clear(); route_begin.push_back(0); }
   // events must be ordered by frame and lie inside the call
-  void add(uint32_t slot, uint32_t out_row, const std::vector<gd::VoiceEvent>& events) {
+  void add(uint32_t slot, uint32_t out_row, const std::vector<gd::VoiceEvent>& events, const std::vector<gd::ModRoute>* routes = nullptr) {
     slots.push_back(slot); rows.push_back(out_row);
+    if (routes) routes_flat.insert(routes_flat.end(), routes->begin(), routes->end());
+    route_begin.push_back((uint32_t)routes_flat.size());
     uint32_t distinct = 0, last = 0xffffffffu;
     for (const auto& e : events) { if (e.frame != last) { distinct++; last = e.frame; } }
     ev_flat.insert(ev_flat.end(), events.begin(), events.end());
@@ -365,6 +371,12 @@ template <class V> struct TypeRunner {
     L.state = pool.d.p; L.n = cnt; L.n_pad = pool.cap;
     L.slots = d_slots.p; L.rows = d_rows.p; L.row0 = 0;
     L.events = d_events.p; L.ev_begin = d_ev_begin.p; L.tt = tt; L.frames = frames; L.out = out; L.stride = stride; L.rc = rc;
+    const bool modulated = !routes_flat.empty() && mod_planes;
+    if (modulated) {
+      d_routes.upload(routes_flat.data(), routes_flat.size(), sC);
+      d_route_begin.upload(route_begin.data(), route_begin.size(), sC);
+      L.routes = d_routes.p; L.route_begin = d_route_begin.p; L.mod_planes = mod_planes; L.mod_pitch = mod_pitch; L.mod_frame0 = mod_frame0;
+    }
     if constexpr (V::FAST) {
       using Span = typename V::Span;
       d_span_off.upload(span_off.data(), span_off.size(), sC);
@@ -455,7 +467,7 @@ template <class V> struct TypeRunner {
       }
       if constexpr (std::is_same<V, gd::BassV>::value) {
         const char* be = getenv("GOOEY_B200_BASS");
-        if (!(be && strcmp(be, "serial") == 0)) {       // one warp per bass voice, lane = frame (bass_wave.cuh)
+        if (!(be && strcmp(be, "serial") == 0) && !modulated) {      // LFO-routed basses take the per-sample kernel       // one warp per bass voice, lane = frame (bass_wave.cuh)
           GH_LAUNCH((gd::bass_wave_kernel<2>), (cnt + 1) / 2, 64, sC, L);
           g_launches.fetch_add(1, std::memory_order_relaxed);
           GH_CUDA(cudaGetLastError());

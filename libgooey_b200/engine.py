@@ -34,6 +34,12 @@ _SIGS = {
     "poly_release": [], "poly_set_preset": [c.c_uint32], "poly_set_param": [c.c_uint32, c.c_float],
     "granulator_trigger": [c.c_float], "granulator_set_param": [c.c_uint32, c.c_float], "granulator_set_seed": [c.c_uint32],
     "granulator_snap_params": [],
+    "set_lfo_enabled": [c.c_uint32, c.c_bool], "set_lfo_timing": [c.c_uint32, c.c_uint32], "set_lfo_amount": [c.c_uint32, c.c_float],
+    "set_lfo_offset": [c.c_uint32, c.c_float], "clear_lfo_routes": [c.c_uint32], "reset_lfo_phase": [c.c_uint32],
+    "blend_enable": [c.c_uint32], "blend_disable": [c.c_uint32], "blend_set_position": [c.c_uint32, c.c_float, c.c_float],
+    "blend_set_corner_preset": [c.c_uint32, c.c_uint32, c.c_uint32], "blend_reset_corners": [c.c_uint32],
+    "sequencer_set_instrument_step_blend": [c.c_uint32, c.c_uint32, c.c_float, c.c_float],
+    "sequencer_clear_instrument_step_blend": [c.c_uint32, c.c_uint32],
 }
 _bound = set()
 
@@ -60,6 +66,9 @@ def _bind(L, prefix):
     f = getattr(L, prefix + "sequencer_set_instrument_pattern"); f.argtypes = [c.c_void_p, c.c_uint32, c.POINTER(c.c_bool)]; f.restype = None
     f = getattr(L, prefix + "poly_trigger_notes"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]; f.restype = None
     f = getattr(L, prefix + "granulator_set_buffer"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32, c.c_float]; f.restype = c.c_bool
+    f = getattr(L, prefix + "add_lfo_route"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_uint32, c.c_float]; f.restype = c.c_uint32
+    f = getattr(L, prefix + "remove_lfo_route"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; f.restype = c.c_bool
+    f = getattr(L, prefix + "get_lfo_phase"); f.argtypes = [c.c_void_p, c.c_uint32]; f.restype = c.c_float
     f = getattr(L, prefix + "render"); f.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32]; f.restype = None
     f = getattr(L, prefix + "bounce_to_buffer"); f.argtypes = [c.c_void_p, c.c_uint32, c.POINTER(c.c_uint32)]; f.restype = c.POINTER(c.c_float)
     f = getattr(L, prefix + "free_buffer"); f.argtypes = [c.POINTER(c.c_float), c.c_uint32]; f.restype = None
@@ -138,6 +147,15 @@ class Engine:
         f = self._L.gooey_b200_granulator_share_buffer
         f.argtypes = [c.c_void_p, c.c_void_p]; f.restype = c.c_bool
         return bool(f(self._h, other._h))
+
+    def add_lfo_route(self, lfo, instrument, param, depth):
+        return int(getattr(self._L, self._prefix + "add_lfo_route")(self._h, lfo, instrument, param, c.c_float(depth)))
+
+    def remove_lfo_route(self, lfo, route_id):
+        return bool(getattr(self._L, self._prefix + "remove_lfo_route")(self._h, lfo, route_id))
+
+    def get_lfo_phase(self, lfo):
+        return float(getattr(self._L, self._prefix + "get_lfo_phase")(self._h, lfo))
 
     def get_channel_peaks(self, count=5):
         """gooey_engine_get_channel_peaks: read-and-reset pre-pan peaks of the five voice strips."""

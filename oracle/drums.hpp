@@ -15,6 +15,11 @@ struct Instrument {
   virtual void snap_params() {}
   virtual void set_param(uint32_t, float) {}       // FFI param ids (ffi.rs:168-250)
   virtual bool get_freq_param(float&) const { return false; }
+  // `set_config(cfg)` with the config given as flat values in the order of its fields (kick.rs:905-941, snare.rs:818-855,
+  // hihat2.rs:382-390, tom2.rs:400-411, bass.rs:636-662); enum / integer fields are passed as floats.  Used by the preset blender.
+  virtual void set_config_flat(const float*) {}
+  // ChannelInstrument::apply_modulation (ffi.rs:322-405): bipolar -1..1 onto the FFI parameter's range (LFO routes)
+  virtual void apply_modulation(uint32_t, float) {}
 };
 
 // ============================ KickDrum (instruments/kick.rs) ============================
@@ -84,6 +89,7 @@ struct KickDrum : Instrument {
     click_osc.set_volume(click * 0.15f * cvs);
   }
   void set_config(const KickConfig& c) { for (int i = 0; i < 18; i++) p[i].set_target(c.v[i]); }  // :837-879
+  void set_config_flat(const float* v) override { KickConfig c; for (int i = 0; i < 18; i++) c.v[i] = v[i]; set_config(c); }
   void snap_params() override { for (auto& s : p) s.snap(); }
   void set_param(uint32_t id, float v) override {  // ffi.rs:170-180, ids ffi.rs:1737-1751
     static const int map[8] = {K_FREQ, K_PUNCH, K_SUB, K_CLICK, K_OSC_DECAY, K_PITCH_ENV_AMT, K_VOLUME, K_TUNING};
@@ -91,6 +97,10 @@ struct KickDrum : Instrument {
   }
   bool get_freq_param(float& f) const override { f = p[K_FREQ].get(); return true; }
   bool is_active() const override { return active; }
+  void apply_modulation(uint32_t id, float v) override {  // ffi.rs:324-336: every FFI id except the pitch envelope (5)
+    static const int map[8] = {K_FREQ, K_PUNCH, K_SUB, K_CLICK, K_OSC_DECAY, -1, K_VOLUME, K_TUNING};
+    if (id < 8 && map[id] >= 0) p[map[id]].set_bipolar(v);
+  }
 
   void trigger_with_velocity(double time, float velocity) override {  // :971-1086
     current_velocity = clampf(velocity, 0.0f, 1.0f);
@@ -256,6 +266,13 @@ struct SnareDrum : Instrument {
     noise_osc.waveform = Waveform::Noise;
     crack_osc.waveform = Waveform::Noise;
   }
+  void set_config_flat(const float* v) override {
+    SnareConfig c;
+    c.frequency = v[0]; c.tonal_amount = v[1]; c.noise_amount = v[2]; c.crack_amount = v[3]; c.decay = v[4]; c.pitch_drop = v[5]; c.volume = v[6];
+    c.tonal_decay = v[7]; c.tonal_decay_curve = v[8]; c.noise_decay = v[9]; c.noise_tail_decay = v[10]; c.filter_cutoff = v[11]; c.filter_resonance = v[12];
+    c.filter_type = (uint8_t)v[13]; c.xfade = v[14]; c.phase_mod_amount = v[15]; c.overdrive_amount = v[16]; c.amp_decay = v[17]; c.amp_decay_curve = v[18];
+    set_config(c);
+  }
   void set_config(const SnareConfig& c) {  // :818-855
     pitch_start_multiplier = 1.0f + c.pitch_drop * 1.5f;
     for (int i = 0; i < 18; i++) p[i].set_target(c.get(i));
@@ -276,6 +293,12 @@ struct SnareDrum : Instrument {
       return;
     }
     p[map[id]].set_target(clampf(v, 0.0f, 1.0f));
+  }
+  void apply_modulation(uint32_t id, float v) override {  // ffi.rs:337-358: every FFI id except the filter type (12)
+    static const int map[20] = {S_FREQ, S_DECAY, S_BRIGHTNESS, S_VOLUME, S_TONAL, S_NOISE, S_PITCH_DROP, S_TONAL_DECAY, S_NOISE_DECAY,
+                                S_NOISE_TAIL_DECAY, S_FILTER_CUTOFF, S_FILTER_RES, -1, S_XFADE, S_PHASE_MOD, S_OVERDRIVE, S_AMP_DECAY,
+                                S_AMP_DECAY_CURVE, S_TONAL_DECAY_CURVE, S_TUNING};
+    if (id < 20 && map[id] >= 0) p[map[id]].set_bipolar(v);
   }
   bool is_active() const override { return active; }
   float freq_hz() const { return denorm(p[S_FREQ].get(), 100.0f, 600.0f); }
@@ -457,6 +480,7 @@ struct HiHat2 : Instrument {
     p[H_ATTACK] = SmoothedParam(c.attack, 0, 1, sr, 15.0f); p[H_TONE] = SmoothedParam(c.tone, 0, 1, sr, 15.0f);
     p[H_VOLUME] = SmoothedParam(c.volume, 0, 1, sr, 15.0f); p[H_TUNING] = SmoothedParam(0.5f, 0, 1, sr, 15.0f);
   }
+  void set_config_flat(const float* v) override { HiHat2Config c{v[0], v[1], v[2], v[3] != 0.0f, v[4] != 0.0f, v[5], v[6]}; set_config(c); }
   void set_config(const HiHat2Config& c) {  // :390-398 (tuning untouched)
     p[H_PITCH].set_target(c.pitch); p[H_DECAY].set_target(c.decay); p[H_ATTACK].set_target(c.attack);
     p[H_TONE].set_target(c.tone); p[H_VOLUME].set_target(c.volume); pink = c.pink; db24 = c.db24;
@@ -471,6 +495,10 @@ struct HiHat2 : Instrument {
       case 4: p[H_VOLUME].set_target(clampf(v, 0.0f, 1.0f)); break;
       case 5: p[H_TUNING].set_target(clampf(v, 0.0f, 1.0f)); break;
     }
+  }
+  void apply_modulation(uint32_t id, float v) override {  // ffi.rs:359-367
+    static const int map[6] = {H_PITCH, H_DECAY, H_ATTACK, H_TONE, H_VOLUME, H_TUNING};
+    if (id < 6) p[map[id]].set_bipolar(v);
   }
   bool is_active() const override { return active; }
   float attack_ms() const { return denorm(p[H_ATTACK].get(), 0.5f, 200.0f); }
@@ -541,9 +569,24 @@ struct Tom2 : Instrument {
     membrane_res.set_q_scale(qs);
     membrane_res.set_gain_scale(0.003f);
   }
+  void set_config_flat(const float* v) override { set_config(Tom2Config{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]}); }
   void set_config(const Tom2Config& c) { tune = c.tune; bend = c.bend; tone = c.tone; color = c.color; decay = c.decay; membrane = c.membrane; membrane_q = c.membrane_q; volume = c.volume; update_membrane(); }
   void set_param(uint32_t id, float v) override {  // ffi.rs:213-231; ids :1820-1836
     float s = clampf(v, 0.0f, 1.0f) * 100.0f;
+    switch (id) {
+      case 0: tune = clampf(s, 0, 100); break;
+      case 1: bend = clampf(s, 0, 100); break;
+      case 2: tone = clampf(s, 0, 100); break;
+      case 3: color = clampf(s, 0, 100); break;
+      case 4: decay = clampf(s, 0, 100); break;
+      case 5: membrane = clampf(s, 0, 100); break;
+      case 6: membrane_q = clampf(s, 0, 100); update_membrane(); break;
+      case 7: volume = clampf(s, 0, 100); break;
+      case 8: tuning = clampf(clampf(v, 0.0f, 1.0f), 0.0f, 1.0f); break;
+    }
+  }
+  void apply_modulation(uint32_t id, float v) override {  // ffi.rs:368-385: set_*(value * 100), tuning = clamp01(value)
+    const float s = v * 100.0f;
     switch (id) {
       case 0: tune = clampf(s, 0, 100); break;
       case 1: bend = clampf(s, 0, 100); break;

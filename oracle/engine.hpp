@@ -115,6 +115,74 @@ struct MixerGraph {
   }
 };
 
+// ---- utils/blendable.rs PresetBlender + ffi.rs ChannelBlender (:405-560) --------------------------------------
+// Presets as flat values in config-field order; ids ffi.rs:1882-1998.  Returns the number of fields (0 = unknown id).
+static inline int preset_flat(uint32_t type, uint32_t id, float* v) {
+  if (id > 3) return 0;
+  switch (type) {
+    case 0: { KickConfig c = id == 0 ? KickConfig::tight() : id == 1 ? KickConfig::punch() : id == 2 ? KickConfig::loose() : KickConfig::dirt();
+      for (int i = 0; i < 18; i++) { v[i] = c.v[i]; }
+      return 18; }
+    case 1: { SnareConfig c = id == 0 ? SnareConfig::tight() : id == 1 ? SnareConfig::loose() : id == 2 ? SnareConfig::hiss() : SnareConfig::smack();
+      const float a[19] = {c.frequency, c.tonal_amount, c.noise_amount, c.crack_amount, c.decay, c.pitch_drop, c.volume, c.tonal_decay, c.tonal_decay_curve,
+                           c.noise_decay, c.noise_tail_decay, c.filter_cutoff, c.filter_resonance, (float)c.filter_type, c.xfade, c.phase_mod_amount,
+                           c.overdrive_amount, c.amp_decay, c.amp_decay_curve};
+      for (int i = 0; i < 19; i++) { v[i] = a[i]; }
+      return 19; }
+    case 2: { HiHat2Config c = id == 0 ? HiHat2Config::short_() : id == 1 ? HiHat2Config::loose() : id == 2 ? HiHat2Config::dark() : HiHat2Config::soft();
+      const float a[7] = {c.pitch, c.decay, c.attack, c.pink ? 1.0f : 0.0f, c.db24 ? 1.0f : 0.0f, c.tone, c.volume};
+      for (int i = 0; i < 7; i++) { v[i] = a[i]; }
+      return 7; }
+    case 3: {  // Tom2Config::{derp,ring,brush,void_preset} (tom2.rs:119-172)
+      static const float T[4][8] = {{60.0f, 70.0f, 50.0f, 0.0f, 20.0f, 0.0f, 50.0f, 100.0f}, {80.0f, 20.0f, 10.0f, 0.0f, 100.0f, 60.0f, 70.0f, 100.0f},
+                                    {40.0f, 20.0f, 10.0f, 90.0f, 30.0f, 0.0f, 50.0f, 100.0f}, {60.0f, 30.0f, 100.0f, 50.0f, 90.0f, 40.0f, 80.0f, 100.0f}};
+      for (int i = 0; i < 8; i++) { v[i] = T[id][i]; }
+      return 8; }
+    case 4: { BassConfig c = id == 0 ? BassConfig::acid() : id == 1 ? BassConfig::sub() : id == 2 ? BassConfig::reese() : BassConfig::stab();
+      for (int i = 0; i < 15; i++) { v[i] = c.v[i]; }
+      return 15; }
+    default: return 0;
+  }
+}
+struct ChannelBlender {
+  uint32_t type = 0; int n = 0;
+  float corner[4][24];                       // bottom_left, bottom_right, top_left, top_right
+  uint32_t corner_ids[4] = {0, 1, 2, 3};     // default_corner_preset_ids: presets 0..3 of the type
+  void default_for_type(uint32_t t) { type = t; for (uint32_t c = 0; c < 4; c++) { n = preset_flat(t, c, corner[c]); corner_ids[c] = c; } }
+  bool discrete(int i) const { return (type == 1 && i == 13) || (type == 2 && (i == 3 || i == 4)); }   // filter_type / noise_color / filter_slope: `if t < 0.5 { self } else { other }`
+  void lerp(const float* a, const float* b, float t, float* o) const {
+    t = clampf(t, 0.0f, 1.0f);
+    const float inv_t = 1.0f - t;
+    for (int i = 0; i < n; i++) o[i] = discrete(i) ? (t < 0.5f ? a[i] : b[i]) : a[i] * inv_t + b[i] * t;
+  }
+  void blend(float x, float y, float* o) const {   // blendable.rs:73-86
+    x = clampf(x, 0.0f, 1.0f); y = clampf(y, 0.0f, 1.0f);
+    float bottom[24], top[24];
+    lerp(corner[0], corner[1], x, bottom);
+    lerp(corner[2], corner[3], x, top);
+    lerp(bottom, top, y, o);
+  }
+  void set_corner_preset(uint32_t c, uint32_t id) { float v[24]; if (c < 4 && preset_flat(type, id, v) > 0) for (int i = 0; i < n; i++) corner[c][i] = v[i]; }
+};
+
+// ---- engine/lfo.rs Lfo (sine, free-running or tempo-synced) + the FFI's LFO pool (ffi.rs:33-54, 716-719, 1238-1251) ----
+struct Lfo {
+  bool synced = true; uint32_t division = 4; float hz = 1.0f;   // Lfo::with_sample_rate: BpmSync(Quarter) (lfo.rs:86-97)
+  float bpm = 120.0f, phase = 0.0f, sample_rate;
+  float amount = 1.0f, offset = 0.0f;
+  explicit Lfo(float sr) : sample_rate(sr) {}
+  static float beats(uint32_t d) { const float B[8] = {16.0f, 8.0f, 4.0f, 2.0f, 1.0f, 0.5f, 0.25f, 0.125f}; return B[d < 8 ? d : 4]; }   // lfo.rs:14-25
+  float frequency() const { if (!synced) return hz; float bps = bpm / 60.0f; return bps / beats(division); }                            // :27-33, 155-160
+  float tick() {                                                                                                                          // :170-185
+    float value = sinf(phase * 2.0f * 3.14159265358979323846f);
+    float inc = frequency() / sample_rate;
+    phase += inc;
+    if (phase >= 1.0f) phase -= 1.0f;
+    return offset + (value * amount);
+  }
+};
+struct LfoRoute { uint32_t id, instrument, param; float depth; };
+
 // ---- ffi.rs GooeyEngine -------------------------------------------------------------------------------------
 struct VoiceStrip {
   std::unique_ptr<Instrument> inst;
@@ -126,8 +194,10 @@ struct VoiceStrip {
   bool has_saved = false;
   float saved_freq = 0;
   float peak = 0.0f;                                  // pre-pan mono peak, read-and-reset (ffi.rs:654-659, 2572-2584)
+  ChannelBlender blender; bool blend_enabled = false; float blend_x = 0.5f, blend_y = 0.5f;   // ffi.rs:598-600, 635-637
   VoiceStrip(std::unique_ptr<Instrument> i, uint32_t t, float bpm, float sr)
-      : inst(std::move(i)), type(t), seq(bpm, sr, 16, false), channel_gain(1.0f, 0, 1, sr, 10.0f), mute_gain(1.0f, 0, 1, sr, 10.0f), pan(0.5f, 0, 1, sr, 10.0f) {}
+      : inst(std::move(i)), type(t), seq(bpm, sr, 16, false), channel_gain(1.0f, 0, 1, sr, 10.0f), mute_gain(1.0f, 0, 1, sr, 10.0f), pan(0.5f, 0, 1, sr, 10.0f) { blender.default_for_type(t); }
+  void blend_and_apply(float x, float y) { float v[24]; blender.blend(x, y, v); inst->set_config_flat(v); }   // ffi.rs:419-428
 };
 static inline std::unique_ptr<Instrument> make_instrument(uint32_t type, float sr) {
   switch (type) {
@@ -160,6 +230,7 @@ struct FfiEngine {
   PolySynth poly;
   Granulator granulator;
   MixerGraph graph;
+  std::vector<Lfo> lfos; bool lfo_enabled[8] = {false}; std::vector<LfoRoute> lfo_routes[8]; uint32_t lfo_next_route_id[8] = {0};
   struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
   std::vector<MidiEvent> pending_midi_events;                                                // capacity 64, cleared by every render (:71, :1045)
   void push_midi_event(uint32_t ch, float vel, uint32_t off) { if (pending_midi_events.size() < 64) pending_midi_events.push_back({ch, vel, off}); }
@@ -169,10 +240,11 @@ struct FfiEngine {
         waveshaper(1.0f, 0.0f), feedback_waveshaper(sr, 1.0f, 0.0f, 2000.0f, 0.0f),
         master_gain(0.25f, 0.0f, 2.0f, sr, 30.0f), poly(sr), granulator(sr), graph(sr, 120.0f) {
     for (uint32_t t = 0; t < 5; t++) voices.emplace_back(make_instrument(t, sr), t, bpm, sr);
+    for (int i = 0; i < 8; i++) lfos.emplace_back(sr);
     graph.default_layout();
   }
   VoiceStrip* by_type(uint32_t t) { for (auto& v : voices) if (v.type == t) return &v; return nullptr; }
-  void set_bpm(float b) { bpm = b; for (auto& v : voices) v.seq.set_bpm(b); delay.set_bpm(b); graph.set_bpm(b); }
+  void set_bpm(float b) { bpm = b; for (auto& v : voices) v.seq.set_bpm(b); for (auto& l : lfos) l.bpm = b; delay.set_bpm(b); graph.set_bpm(b); }   // :3337-3364
   void set_swing(float s) { swing = clampf(s, 0.0f, 1.0f); for (auto& v : voices) v.seq.set_swing(swing); }
   void reset_effect_states() { saturation.reset(); lowpass.reset(); tilt.reset(); delay.reset(); compressor.reset(); reverb.reset(); plate.reset(); }  // ffi.rs:1417-1425
   static bool freq_range(uint32_t type, float& mn, float& mx) {  // :1511-1518
@@ -203,6 +275,10 @@ struct FfiEngine {
         for (int ch = 0; ch < 5; ch++) {
           if (!fired[ch]) continue;
           VoiceStrip& v = voices[ch];
+          // apply_sequencer_blend_setting (ffi.rs:1384-1402) and the snap that follows an applied blend (:1168-1171)
+          if (trig[ch].has_blend) v.blend_and_apply(clampf(trig[ch].bx, 0.0f, 1.0f), clampf(trig[ch].by, 0.0f, 1.0f));
+          else if (v.blend_enabled) v.blend_and_apply(v.blend_x, v.blend_y);
+          if (trig[ch].has_blend || v.blend_enabled) v.inst->snap_params();
           if (trig[ch].has_note) {
             float mn, mx;
             if (freq_range(v.type, mn, mx)) {
@@ -218,6 +294,11 @@ struct FfiEngine {
           v.inst->trigger_with_velocity(time, trig[ch].velocity);
           push_midi_event((uint32_t)ch, trig[ch].velocity, (uint32_t)f);
         }
+      }
+      for (int li = 0; li < 8; li++) {   // LFO pool (:1238-1251): after the triggers, before the voices tick
+        if (!lfo_enabled[li]) continue;
+        const float lv = lfos[li].tick();
+        for (const LfoRoute& r : lfo_routes[li]) if (r.instrument < voices.size()) voices[r.instrument].inst->apply_modulation(r.param, lv * r.depth);
       }
       StereoFrame kit, bassf;
       double time = current_time;

@@ -148,8 +148,61 @@ void orc_engine_set_bass_param(void* e, uint32_t p, float v) { set_typed(e, 4, p
 void orc_engine_set_channel_param(void* e, uint32_t ch, uint32_t p, float v) { if (e && ch < 5) E->voices[ch].inst->set_param(p, v); }
 void orc_engine_set_channel_instrument_type(void* e, uint32_t ch, uint32_t type) {
   if (!e || ch >= 5 || type > 4 || E->voices[ch].type == type) return;
-  E->voices[ch].inst = make_instrument(type, E->sample_rate);
-  E->voices[ch].type = type;
+  VoiceStrip& v = E->voices[ch];
+  v.inst = make_instrument(type, E->sample_rate);
+  v.type = type;
+  v.blender.default_for_type(type);                                    // ffi.rs:2334-2342
+  if (v.blend_enabled) v.blend_and_apply(v.blend_x, v.blend_y);
+}
+// ---- LFO pool (ffi.rs:4616-4993) ----
+void orc_engine_set_lfo_enabled(void* e, uint32_t i, bool on) { if (e && i < 8) E->lfo_enabled[i] = on; }
+void orc_engine_set_lfo_timing(void* e, uint32_t i, uint32_t timing) { if (e && i < 8 && timing < 8) { E->lfos[i].synced = true; E->lfos[i].division = timing; } }
+void orc_engine_set_lfo_frequency(void* e, uint32_t i, float hz) { if (e && i < 8) { E->lfos[i].synced = false; E->lfos[i].hz = hz; } }
+void orc_engine_set_lfo_amount(void* e, uint32_t i, float a) { if (e && i < 8) E->lfos[i].amount = a; }
+void orc_engine_set_lfo_offset(void* e, uint32_t i, float o) { if (e && i < 8) E->lfos[i].offset = o; }
+uint32_t orc_engine_add_lfo_route(void* e, uint32_t i, uint32_t inst, uint32_t param, float depth) {
+  if (!e || i >= 8 || E->lfo_routes[i].size() >= 16) return 0xFFFFFFFFu;
+  const uint32_t id = E->lfo_next_route_id[i]++;
+  E->lfo_routes[i].push_back({id, inst, param, depth});
+  return id;
+}
+bool orc_engine_remove_lfo_route(void* e, uint32_t i, uint32_t id) {
+  if (!e || i >= 8) return false;
+  auto& r = E->lfo_routes[i];
+  for (size_t k = 0; k < r.size(); k++) if (r[k].id == id) { r.erase(r.begin() + k); return true; }
+  return false;
+}
+void orc_engine_clear_lfo_routes(void* e, uint32_t i) { if (e && i < 8) E->lfo_routes[i].clear(); }
+void orc_engine_reset_lfo_phase(void* e, uint32_t i) { if (e && i < 8) E->lfos[i].phase = 0.0f; }
+float orc_engine_get_lfo_phase(void* e, uint32_t i) { return (e && i < 8) ? E->lfos[i].phase : -1.0f; }
+// ---- preset blend (ffi.rs:5245-5490) and per-step blend (:4009-4075) ----
+void orc_engine_blend_enable(void* e, uint32_t i) { if (e && i < 5) E->voices[i].blend_enabled = true; }
+void orc_engine_blend_disable(void* e, uint32_t i) { if (e && i < 5) E->voices[i].blend_enabled = false; }
+bool orc_engine_blend_is_enabled(void* e, uint32_t i) { return e && i < 5 && E->voices[i].blend_enabled; }
+void orc_engine_blend_set_position(void* e, uint32_t i, float x, float y) {
+  if (!e || i >= 5) return;
+  VoiceStrip& v = E->voices[i];
+  if (!v.blend_enabled) return;
+  v.blend_x = clampf(x, 0.0f, 1.0f); v.blend_y = clampf(y, 0.0f, 1.0f);
+  v.blend_and_apply(v.blend_x, v.blend_y);
+}
+float orc_engine_blend_get_position_x(void* e, uint32_t i) { return (e && i < 5) ? E->voices[i].blend_x : -1.0f; }
+float orc_engine_blend_get_position_y(void* e, uint32_t i) { return (e && i < 5) ? E->voices[i].blend_y : -1.0f; }
+void orc_engine_blend_set_corner_preset(void* e, uint32_t i, uint32_t corner, uint32_t id) {
+  if (!e || i >= 5 || corner >= 4) return;
+  E->voices[i].blender.corner_ids[corner] = id;
+  E->voices[i].blender.set_corner_preset(corner, id);
+}
+uint32_t orc_engine_blend_get_corner_preset(void* e, uint32_t i, uint32_t corner) { return (e && i < 5 && corner < 4) ? E->voices[i].blender.corner_ids[corner] : 0xFFFFFFFFu; }
+void orc_engine_blend_reset_corners(void* e, uint32_t i) { if (e && i < 5) E->voices[i].blender.default_for_type(E->voices[i].type); }
+void orc_engine_sequencer_set_instrument_step_blend(void* e, uint32_t inst, uint32_t step, float x, float y) {
+  if (!e || inst >= 5 || step >= E->voices[inst].seq.pattern.size()) return;
+  SeqStep& st = E->voices[inst].seq.pattern[step];
+  st.has_blend = true; st.bx = clampf(x, 0.0f, 1.0f); st.by = clampf(y, 0.0f, 1.0f);
+}
+void orc_engine_sequencer_clear_instrument_step_blend(void* e, uint32_t inst, uint32_t step) {
+  if (!e || inst >= 5 || step >= E->voices[inst].seq.pattern.size()) return;
+  E->voices[inst].seq.pattern[step].has_blend = false;
 }
 void orc_engine_load_bass_preset(void* e, uint32_t id) {
   if (!e || id > 3) return;

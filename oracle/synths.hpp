@@ -34,8 +34,10 @@ struct BassSynth : Instrument {
     p[B_TUNING] = SmoothedParam(0.5f, 0.0f, 1.0f, sr, 15.0f);
   }
   void set_config(const BassConfig& c) { for (int i = 0; i < 15; i++) p[i].set_target(c.v[i]); }
+  void set_config_flat(const float* v) override { BassConfig c; for (int i = 0; i < 15; i++) c.v[i] = v[i]; set_config(c); }
   void snap_params() override { for (auto& s : p) s.snap(); }
   void set_param(uint32_t id, float v) override { if (id < 16) p[id].set_target(clampf(v, 0.0f, 1.0f)); }  // ffi.rs:232-249
+  void apply_modulation(uint32_t id, float v) override { if (id < 16) p[id].set_bipolar(v); }  // ffi.rs:386-403
   bool get_freq_param(float& f) const override { f = p[B_FREQ].get(); return true; }
   bool is_active() const override { return active; }
   void trigger_with_velocity(double time, float velocity) override {  // bass.rs:747-791

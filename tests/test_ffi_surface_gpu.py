@@ -3,6 +3,7 @@ effect reordering, delay ping-pong, instrument solo, track mute / solo, bass pre
 instrument swap, every sequencer setter, the batch stereo render, bounce_to_wav, the sticky error + callback, and the
 saturation / compressor (+ side-chain) / low-pass / waveshaper / feedback-waveshaper effect slots.
 One FFI-named call script drives the CPU oracle and the product; tolerance 1e-5 of full scale (BASELINE.json)."""
+import ctypes
 import os
 import struct
 
@@ -437,3 +438,120 @@ def test_float_wav_writer(tmp_path):
     raw = (tmp_path / "f.wav").read_bytes()
     assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt " and struct.unpack("<HHIIHH", raw[20:36]) == (3, 2, 44100, 44100 * 8, 8, 32)
     assert np.array_equal(np.frombuffer(raw[44:], np.float32).reshape(1000, 2), x)
+
+
+def test_preset_blend_pad_and_per_step_blends():
+    """gooey_engine_blend_* (ffi.rs:5245-5490) and per-step blends (:4009-4075): bilinear blend of four corner presets applied by
+    set_position and at every sequencer trigger (followed by snap_params), with corner edits, a cleared step blend, a reset and an
+    instrument swap while blending is on."""
+    def script(e):
+        busy_pattern(e, snare_overdrive=0.2)
+        for inst, (x, y) in zip(range(5), [(0.2, 0.8), (0.7, 0.4), (0.5, 0.5), (0.9, 0.1), (0.35, 0.65)]):
+            e.blend_enable(inst)
+            e.blend_set_position(inst, x, y)
+        e.blend_set_corner_preset(S.KICK, 0, 3)            # bottom-left = dirt
+        e.blend_set_corner_preset(S.BASS, 3, 1)            # top-right = sub
+        e.blend_set_position(S.KICK, 0.25, 0.75)
+        e.blend_disable(S.TOM)
+        e.blend_set_position(S.TOM, 0.0, 0.0)              # ignored while disabled
+        e.sequencer_set_instrument_step_blend(S.TOM, 4, 0.1, 0.9)      # steps with their own blend fire even when the pad is off
+        e.sequencer_set_instrument_step_blend(S.KICK, 8, 1.0, 0.0)
+        e.sequencer_set_instrument_step_blend(S.SNARE, 4, 0.49, 0.51)  # the filter type switches at t = 0.5
+        e.sequencer_set_instrument_step_blend(S.HIHAT, 2, 0.6, 0.6)
+        e.sequencer_clear_instrument_step_blend(S.HIHAT, 2)
+        e.sequencer_set_instrument_step_settings(S.BASS, 0, True, True, 0.9, True, 0.8, 0.2, False, 0)
+    o = O.oracle_engine(); g = G.Engine()
+    script(o); script(g)
+    w1, g1 = o.bounce_to_buffer(1), g.bounce_to_buffer(1)
+    for e in (o, g):
+        e.blend_reset_corners(S.KICK)
+        e.set_channel_instrument_type(3, S.KICK)           # the tom channel becomes a second kick: default corners
+        e.blend_enable(3); e.blend_set_position(3, 0.6, 0.3)
+        e.sequencer_set_instrument_step(3, 6, True)
+    w2, g2 = o.bounce_to_buffer(1), g.bounce_to_buffer(1)
+    o.close(); g.close()
+    assert np.abs(w1).max() > 0.01 and np.abs(w2).max() > 0.01
+    assert np.abs(g1 - w1).max() <= TOL
+    assert np.abs(g2 - w2).max() <= TOL
+
+
+def test_blend_getters_and_sentinels():
+    c = ctypes
+    g = G.Engine()
+    L = g._L
+    L.gooey_engine_blend_is_enabled.restype = c.c_bool; L.gooey_engine_blend_is_enabled.argtypes = [c.c_void_p, c.c_uint32]
+    for name in ("gooey_engine_blend_get_position_x", "gooey_engine_blend_get_position_y"):
+        getattr(L, name).restype = c.c_float; getattr(L, name).argtypes = [c.c_void_p, c.c_uint32]
+    L.gooey_engine_blend_get_corner_preset.restype = c.c_uint32; L.gooey_engine_blend_get_corner_preset.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]
+    L.gooey_engine_sequencer_get_instrument_step_blend_x.restype = c.c_float
+    L.gooey_engine_sequencer_get_instrument_step_blend_x.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]
+    assert not L.gooey_engine_blend_is_enabled(g._h, 0)
+    assert L.gooey_engine_blend_get_position_x(g._h, 0) == 0.5 and L.gooey_engine_blend_get_position_x(g._h, 9) == -1.0
+    g.blend_set_position(0, 0.9, 0.9)                       # ignored: blending is off
+    assert L.gooey_engine_blend_get_position_y(g._h, 0) == 0.5
+    g.blend_enable(0); g.blend_set_position(0, 2.0, -1.0)   # clamped
+    assert L.gooey_engine_blend_is_enabled(g._h, 0)
+    assert L.gooey_engine_blend_get_position_x(g._h, 0) == 1.0 and L.gooey_engine_blend_get_position_y(g._h, 0) == 0.0
+    assert [L.gooey_engine_blend_get_corner_preset(g._h, 1, k) for k in range(4)] == [0, 1, 2, 3]
+    g.blend_set_corner_preset(1, 2, 0)
+    assert L.gooey_engine_blend_get_corner_preset(g._h, 1, 2) == 0 and L.gooey_engine_blend_get_corner_preset(g._h, 1, 4) == 0xFFFFFFFF
+    assert L.gooey_engine_sequencer_get_instrument_step_blend_x(g._h, 0, 3) == -1.0
+    g.sequencer_set_instrument_step_blend(0, 3, 0.25, 0.5)
+    assert L.gooey_engine_sequencer_get_instrument_step_blend_x(g._h, 0, 3) == 0.25
+    g.close()
+
+
+def test_lfo_pool_routes_match_the_oracle():
+    """gooey_engine_*lfo* (ffi.rs:4616-4993): tempo-synced sine LFOs writing bipolar modulation to routed channel parameters every
+    frame, after the triggers and before the voices tick (:1238-1251, :322-405); unrouted LFOs keep running; removed / invalid routes."""
+    def script(e):
+        busy_pattern(e)
+        e.set_bpm(126.0)
+        e.set_lfo_enabled(0, True); e.set_lfo_timing(0, 4)
+        e.add_lfo_route(0, S.KICK, 0, 0.5)                   # kick frequency
+        r = e.add_lfo_route(0, S.SNARE, 10, 0.8)             # snare filter cutoff
+        e.add_lfo_route(0, S.SNARE, 3, 0.3)                  # snare volume ...
+        e.set_lfo_enabled(1, True); e.set_lfo_timing(1, 6); e.set_lfo_amount(1, 0.7); e.set_lfo_offset(1, 0.2)
+        e.add_lfo_route(1, S.HIHAT, 3, 1.0)                  # hat tone
+        e.add_lfo_route(1, S.TOM, 0, 0.9)                    # tom tune (0-100 scale)
+        e.add_lfo_route(1, S.TOM, 8, 0.5)                    # tom tuning (0-1, not bipolar-mapped)
+        e.add_lfo_route(1, S.BASS, 6, 0.6)                   # bass filter cutoff
+        e.add_lfo_route(1, S.KICK, 5, 1.0)                   # kick pitch envelope: not modulatable, ignored
+        e.add_lfo_route(1, 7, 0, 1.0)                        # no such channel, ignored
+        e.set_lfo_enabled(2, True); e.set_lfo_timing(2, 7)   # enabled, unrouted: the phase still runs
+        e.set_lfo_timing(3, 2); e.add_lfo_route(3, S.KICK, 6, 1.0)   # routed but disabled
+        return r
+    o = O.oracle_engine(); g = G.Engine()
+    ro, rg = script(o), script(g)
+    assert ro == rg == 1
+    w1, g1 = o.bounce_to_buffer(1), g.bounce_to_buffer(1)
+    assert [g.get_lfo_phase(i) for i in range(4)] == [o.get_lfo_phase(i) for i in range(4)]
+    assert o.get_lfo_phase(2) > 0.0 and o.get_lfo_phase(3) == 0.0
+    for e in (o, g):
+        assert e.remove_lfo_route(0, 1) and not e.remove_lfo_route(0, 1)
+        e.clear_lfo_routes(1)
+        e.reset_lfo_phase(0)
+        e.sequencer_start()
+    w2, g2 = o.render(9000), g.render(9000)
+    assert [g.get_lfo_phase(i) for i in range(3)] == [o.get_lfo_phase(i) for i in range(3)]
+    o.close(); g.close()
+    assert np.abs(w1).max() > 0.01 and np.abs(w2).max() > 0.001
+    assert np.abs(g1 - w1).max() <= TOL
+    assert np.abs(g2 - w2).max() <= TOL
+
+
+def test_lfo_modulated_and_plain_engines_share_a_batch():
+    def script(e, i):
+        busy_pattern(e, snare_overdrive=0.1 * (i % 3))
+        if i % 2 == 1:
+            e.set_lfo_enabled(i % 8, True); e.set_lfo_timing(i % 8, 3 + i % 4)
+            e.add_lfo_route(i % 8, i % 5, 0, 0.4 + 0.05 * i)
+    n = 7
+    es = [G.Engine() for _ in range(n)]
+    for i, e in enumerate(es):
+        script(e, i)
+    got = G.batch_bounce(es, 1)
+    [e.close() for e in es]
+    wants = O.bounce_many(script, range(n), 1)
+    for i in range(n):
+        assert np.abs(got[i] - wants[i]).max() <= TOL, i
