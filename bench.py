@@ -216,13 +216,26 @@ def engine_config(L, torch, dev, ids, script, bars, check_ids, peak, bytes_per_e
     from libgooey_b200 import engine as G
     import oracle_lib as O
     n = len(ids)
+    # Warm-up pass on a throw-away set of engines of the same size: the first bounce of a batch shape pays one-time host-blocking
+    # work inside the timed window (pool growth + state uploads, plane / voice-buffer / ring cudaMallocs, the clock-table upload)
+    # that a long-running host has behind it.  The timed engines below are created fresh, so their first bounce still renders with
+    # the FFI parameter edits gliding.
+    warm = [G.Engine() for _ in range(n)]
+    for e, i in zip(warm, ids):
+        script(e, int(i))
+    frames = int(round(bars * 4 * 0.5 * SR))
+    stride = (frames + 3) & ~3
+    wout = torch.empty((n, stride), dtype=torch.float32, device=f"cuda:{dev}")
+    G.batch_bounce_device(warm, bars, wout.data_ptr(), stride)
+    torch.cuda.synchronize()
+    del wout
+    for e in warm:
+        e.close()
     t0 = time.perf_counter()
     engines = [G.Engine() for _ in range(n)]          # on the device selected with gooey_b200_set_device
     for e, i in zip(engines, ids):
         script(e, int(i))
     setup_s = time.perf_counter() - t0
-    frames = int(round(bars * 4 * 0.5 * SR))
-    stride = (frames + 3) & ~3
     out = torch.empty((n, stride), dtype=torch.float32, device=f"cuda:{dev}")
     L.gooey_b200_kernel_stats_reset()
     launches0 = L.gooey_b200_launch_count()
@@ -284,7 +297,7 @@ def engine_config(L, torch, dev, ids, script, bars, check_ids, peak, bytes_per_e
     for e in engines:
         e.close()
     res = {"workload": label, "engines": n, "frames": frames, "setup_s": round(setup_s, 2), "device_ms": dev_ms, "device_ms_settled": dev_ms_settled,
-           "bounces": "1: device-resident, FFI edits still gliding (device_ms, parity); 2: device-resident, settled (device_ms_settled); 3: pitched pinned host block, settled (e2e_ms, parity); 4: 16-bit PCM drain (e2e_pcm16_ms)",
+           "bounces": "0: untimed warm-up on a throw-away set of engines of the same size; 1: device-resident, FFI edits still gliding (device_ms, parity); 2: device-resident, settled (device_ms_settled); 3: pitched pinned host block, settled (e2e_ms, parity); 4: 16-bit PCM drain (e2e_pcm16_ms)",
            "wall_ms_device_resident": wall_dev * 1e3, "e2e_ms": wall_e2e * 1e3, "gpu_launches": launches,
            "engine_samples_per_s": n * frames / (dev_ms * 1e-3), "voice_samples_per_s": 5 * n * frames / (dev_ms * 1e-3),
            "e2e_engine_samples_per_s": n * frames / wall_e2e, "d2h_bytes": n * frames * 4, "e2e_pcm16_ms": wall_pcm * 1e3,
@@ -342,12 +355,19 @@ def config_c4(L):
         e.granulator_set_seed(i + 1)
         e.granulator_snap_params()
         e.granulator_trigger(1.0)
-    engines = [G.Engine() for _ in range(n_eng)]
-    for i, e in enumerate(engines):
-        script(e, i, None if i == 0 else engines[0])
     from libgooey_b200 import HostBuffer
     hb = HostBuffer(n_eng * frames * 8, device=0)
     out = hb.array((n_eng, frames, 2), np.float32)
+    # warm-up on a throw-away set of engines of the same size (one-time allocations and uploads, see engine_config)
+    warm = [G.Engine() for _ in range(n_eng)]
+    for i, e in enumerate(warm):
+        script(e, i, None if i == 0 else warm[0])
+    G.batch_render(warm, frames, out=out)
+    for e in warm:
+        e.close()
+    engines = [G.Engine() for _ in range(n_eng)]
+    for i, e in enumerate(engines):
+        script(e, i, None if i == 0 else engines[0])
     t0 = time.perf_counter()
     G.batch_render(engines, frames, out=out)
     wall = time.perf_counter() - t0

@@ -252,8 +252,34 @@ struct EngineBank {
     ring_words[slot] = nw; ring_cap_of[slot] = nc;
   }
   long long ring_cap_of[gd::MAX_FX] = {0};
+  std::vector<uint32_t> ring_dirty;       // engine slots re-used since the last render: their ring columns must read as silence
+  DevBuf<uint32_t> d_ring_dirty;
+  void clear_dirty_rings(cudaStream_t st);
 };
 EngineBank& engine_bank(int device, float sr);
+
+__global__ void ring_clear_kernel(float* __restrict__ ring, long long cap, uint32_t words, const uint32_t* __restrict__ slots, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = slots[i];
+  if ((long long)slot >= cap) return;
+  for (uint32_t w = blockIdx.y; w < words; w += gridDim.y) ring[(long long)w * cap + slot] = 0.0f;
+}
+inline void EngineBank::clear_dirty_rings(cudaStream_t st) {
+  if (ring_dirty.empty()) return;
+  std::sort(ring_dirty.begin(), ring_dirty.end());          // neighbouring slots -> neighbouring threads -> coalesced rows
+  ring_dirty.erase(std::unique(ring_dirty.begin(), ring_dirty.end()), ring_dirty.end());
+  d_ring_dirty.upload(ring_dirty.data(), ring_dirty.size(), st);
+  const int n = (int)ring_dirty.size();
+  for (int s = 0; s < gd::MAX_FX; s++)
+    if (ring[s].p && ring_words[s]) {
+      ring_clear_kernel<<<dim3((n + 127) / 128, std::min<uint32_t>(ring_words[s], 4096u)), 128, 0, st>>>(ring[s].p, ring_cap_of[s], ring_words[s], d_ring_dirty.p, n);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  GH_CUDA(cudaGetLastError());
+  GH_CUDA(cudaStreamSynchronize(st));                       // ring_dirty (host) is reused
+  ring_dirty.clear();
+}
 
 }  // namespace gh
 
@@ -361,11 +387,12 @@ inline GooeyEngine* engine_create(int device, float sr) {
   const uint32_t kinds[4] = {gd::FXK_TILT, gd::FXK_DELAY, gd::FXK_SPRING, gd::FXK_PLATE};
   for (int s = 0; s < 4; s++) gd::fx_construct(ms.fx[s], kinds[s], false, sr, 120.0f);
   e->mix_slot = B.mix_pool.alloc(ms);
-  // a recycled slot inherits its predecessor's delay-line columns: a fresh engine starts from silence
+  // a recycled slot inherits its predecessor's delay-line columns: a fresh engine starts from silence.  The columns are
+  // cleared in bulk at the next render (one coalesced kernel per arena over every dirty slot) instead of one strided
+  // memset per engine and arena (thousands of engines re-created between two batches: ~14 MB of 4-byte writes each).
   GH_CUDA(cudaSetDevice(B.device));
   for (int s = 0; s < gd::MAX_FX; s++)
-    if (B.ring[s].p && e->mix_slot < B.ring_cap_of[s])
-      GH_CUDA(cudaMemset2DAsync(B.ring[s].p + e->mix_slot, (size_t)B.ring_cap_of[s] * 4, 0, 4, B.ring_words[s], B.stream));
+    if (B.ring[s].p && e->mix_slot < B.ring_cap_of[s]) { B.ring_dirty.push_back((uint32_t)e->mix_slot); break; }
   gd::MixCfg& c = e->cfg;
   memset(&c, 0, sizeof c);
   c.n_tracks = 4;
@@ -573,6 +600,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       if (used) need_words[s] = std::max(need_words[s], ring_words_of(B.geo, c.fx_kind[s]));
     }
   }
+  B.clear_dirty_rings(st);
   // every arena shares one row pitch (the mix pool's capacity); arenas that already exist are re-laid when it grows
   const long long ring_cap = B.mix_pool.cap;
   for (int s = 0; s < gd::MAX_FX; s++) {

@@ -13,6 +13,12 @@
 // so results are bit-identical to the host libm the reference links.
 // Table constants are those of the platform libm (verified in tests/).
 //
+// Provenance / licence: the algorithms and table constants restate third-party code, not the reference — glibc 2.39
+// (GNU LGPL-2.1-or-later) `sysdeps/ieee754/flt-32/`: e_powf.c, e_expf.c, s_sinf.c, s_cosf.c, sincosf.h and their data tables
+// (derived from ARM Optimized Routines, MIT / Apache-2.0-with-LLVM-exception, (c) Arm Ltd.), and the fdlibm single-precision
+// routines glibc still carries for tanf / tanhf / expm1f ((c) 1993 Sun Microsystems, "freely granted" permission notice).
+// Nothing here is copied from gooey-audio/libgooey.
+//
 // The same header compiles for the host (g++, tests only) with GM_HD empty.
 #pragma once
 #include <stdint.h>

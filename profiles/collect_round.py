@@ -74,6 +74,27 @@ def main(tag):
         mix.write(f"== wave_kernel<{k}>: {tot} warp instructions; opcode mix (share of instructions / share of stall samples)\n")
         for op, n in m.most_common(12):
             mix.write(f"   {op:10s} {100 * n / tot:5.1f}%  {100 * sm[op] / ts:5.1f}%\n")
+    for k in ["mix_kernel", "bass_wave_kernel", "gran_wave_kernel", "coop_kernel"]:      # engine-level kernels and the cooperative back end
+        path = f"gpurun_out/ncu_{tag}_raw_{k}.csv"
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        if len(rows) < 3:
+            continue
+        head, units = rows[0], rows[1]
+        dd, u = dict(zip(head, rows[2])), dict(zip(head, units))
+        out.write(f"\n== {k} ({dd.get('Kernel Name', '')[:70]})\n")
+        for key in KEYS:
+            if key in dd:
+                out.write(f"  {key:66s} {dd[key]:>18s} {u[key]}\n")
+        st = [(float(v), kk) for kk, v in dd.items() if kk.startswith("smsp__average_warps_issue_stalled") and kk.endswith("per_issue_active.ratio") and v not in ("", "n/a")]
+        for v, kk in sorted(st, reverse=True)[:6]:
+            out.write(f"  stall {kk[34:-23]:40s} {v:.2f}\n")
+        rd, wr = to_bytes(dd["dram__bytes_read.sum"], u["dram__bytes_read.sum"]), to_bytes(dd["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+        traffic[k] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "source": f"profiles/{tag}_ncu_summary.txt"}
+    warm = f"gpurun_out/ncu_{tag}_warm_dram.csv"
+    if os.path.exists(warm):
+        shutil.copy(warm, f"profiles/{tag}_ncu_warm_cache_dram.csv")
     open(f"profiles/{tag}_ncu_summary.txt", "w").write(out.getvalue())
     open(f"profiles/{tag}_sass_mix.txt", "w").write(mix.getvalue())
     json.dump(traffic, open("profiles/ncu_dram_traffic.json", "w"), indent=1)

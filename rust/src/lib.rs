@@ -60,6 +60,38 @@ extern "C" {
     pub fn gooey_voice_batch_render(b: *mut GooeyVoiceBatch, frames: u32, out_host: *mut c_float) -> c_int;
 
     pub fn gooey_b200_write_wav(path: *const c_char, samples: *const c_float, n: u32, sample_rate: u32, bit_depth: u32) -> c_int;
+    pub fn gooey_b200_write_wav_f32(path: *const c_char, interleaved: *const c_float, frames: u32, channels: u32, sample_rate: u32) -> c_int;
+    pub fn gooey_voice_batch_render_pcm16(b: *mut GooeyVoiceBatch, frames: u32, out_host: *mut i16) -> c_int;
+
+    // FFI engines (`include/gooey.h`): the handles are the reference's `*mut GooeyEngine`; these are the batch calls a host adds
+    pub fn gooey_b200_set_device(device: c_int) -> c_int;
+    pub fn gooey_batch_bounce(engines: *const *mut GooeyEngineOpaque, n: u32, bars: u32, out_buffers: *mut *mut c_float, out_lengths: *mut u32) -> c_int;
+    pub fn gooey_batch_bounce_host(engines: *const *mut GooeyEngineOpaque, n: u32, bars: u32, out_host: *mut c_float, pitch: usize, out_frames: *mut u32) -> c_int;
+    pub fn gooey_batch_bounce_pcm16(engines: *const *mut GooeyEngineOpaque, n: u32, bars: u32, out_host: *mut i16, pitch: usize, out_frames: *mut u32) -> c_int;
+    pub fn gooey_batch_bounce_to_wav(engines: *const *mut GooeyEngineOpaque, n: u32, bars: u32, utf8_paths: *const *const c_char) -> c_int;
+    pub fn gooey_batch_render(engines: *const *mut GooeyEngineOpaque, n: u32, frames: u32, out_host: *mut c_float) -> c_int;
+    pub fn gooey_b200_host_alloc(bytes: usize, device: c_int, out_numa_node: *mut c_int) -> *mut std::ffi::c_void;
+    pub fn gooey_b200_host_free(p: *mut std::ffi::c_void);
+}
+
+/// Opaque `GooeyEngine` of `include/gooey.h` (the reference's handle type, `src/ffi.rs:670`).
+#[repr(C)]
+pub struct GooeyEngineOpaque {
+    _private: [u8; 0],
+}
+
+/// `gooey_engine_bounce_to_wav` (ffi.rs:7942-7980) for a whole batch of FFI engines: one device pass, 16-bit PCM quantised on
+/// the device, one mono WAV per engine.
+///
+/// # Safety
+/// every pointer must be a live handle returned by `gooey_engine_new` of libgooey_b200.
+pub unsafe fn batch_bounce_to_wav(engines: &[*mut GooeyEngineOpaque], bars: u32, paths: &[&str]) -> Result<(), String> {
+    if engines.len() != paths.len() {
+        return Err(String::from("one path per engine"));
+    }
+    let c: Vec<CString> = paths.iter().map(|p| cstr(p)).collect::<Result<_, _>>()?;
+    let p: Vec<*const c_char> = c.iter().map(|s| s.as_ptr()).collect();
+    check(gooey_batch_bounce_to_wav(engines.as_ptr(), engines.len() as u32, bars, p.as_ptr()))
 }
 
 /// The library's thread-local error text, as the `Err(String)` the reference's Rust API uses.
