@@ -469,7 +469,7 @@ def run_ours(args, rank, world, local_rank):
     kstats = kernel_stats(L)
 
     # end-to-end through the C ABI with host buffers
-    for _ in range(max(args.warmup, 3 if world == 1 else 6)):   # the host-buffer path has its own first-call costs (staging allocations, page touch)
+    for _ in range(max(args.warmup, 3 if world == 1 else 10)):   # the host-buffer path has its own first-call costs (staging allocations, page touch)
         step_e2e()
     barrier()
     t0 = time.perf_counter()
