@@ -10,6 +10,7 @@
 #include "pool.cuh"
 #include "patch.h"
 #include "mix.cuh"
+#include "chain.cuh"
 
 namespace gh {
 
@@ -211,6 +212,7 @@ struct EngineBank {
   DevBuf<float> d_lfo_planes;             // [routed streams][frames] LFO values
   std::vector<gd::LfoStream> h_lfo_streams;
   DevBuf<float> d_peaks;                  // [n][N_PEAKS] maxima of the current render call
+  DevBuf<unsigned long long> d_chain_units; unsigned long long h_chain_units = 0;   // engine-frames the settled-chain kernel took in the last render
   std::vector<float> h_peaks;
   DevBuf<gd::VoiceEvent> d_mix_eventss[2];
   std::recursive_mutex mu;   // every use of the bank's shared buffers / streams, held for a whole render call
@@ -226,6 +228,7 @@ struct EngineBank {
       k.launches++; k.ms += ms; k.voice_frames += mix_units[i];
     }
     mix_timed = 0;
+    if (h_chain_units) { KernelStat& c = kernel_stats()["chain_fast_kernel"]; c.launches++; c.voice_frames += (double)h_chain_units; h_chain_units = 0; }
   }
   EngineBank(int dev, float sr_) : device(dev), sr(sr_) {
     rc = gd::make_rate_ctx(sr); geo = make_fx_geom(sr);
@@ -664,6 +667,8 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   }
   B.d_peaks.alloc((size_t)n * gd::N_PEAKS);
   GH_CUDA(cudaMemsetAsync(B.d_peaks.p, 0, (size_t)n * gd::N_PEAKS * 4, st));
+  B.d_chain_units.alloc(1);
+  GH_CUDA(cudaMemsetAsync(B.d_chain_units.p, 0, sizeof(unsigned long long), st));
   cudaStream_t ms = B.mix_stream;
   GH_CUDA(cudaEventRecord(B.ev_piece, st));
   GH_CUDA(cudaStreamWaitEvent(ms, B.ev_piece, 0));             // the mix stream starts after everything queued so far (uploads, ring set-up)
@@ -738,15 +743,22 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     M.fast = B.d_mix_fast.p; M.consts = B.d_mix_consts.p;
     M.peaks = B.d_peaks.p;
     M.premix = B.d_premix.p; M.premix_stride = (long long)vstride;
+    M.chain_units = B.d_chain_units.p;
     tev(tm0, ms);
     gd::mix_prepare_kernel<<<(n + 127) / 128, 128, 0, ms>>>(M);
     gd::mix_fast_kernel<<<dim3((nf + 1023) / 1024, n), 256, 0, ms>>>(M);
     {
       static std::set<int> opted;      // per device: allow the mix kernel its dynamic shared memory (> 48 KB with the static tiles)
-      if (opted.insert(B.device).second) GH_CUDA(cudaFuncSetAttribute(gd::mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gd::MIX_DYN_SMEM));
+      if (opted.insert(B.device).second) {
+        GH_CUDA(cudaFuncSetAttribute(gd::mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gd::MIX_DYN_SMEM));
+        GH_CUDA(cudaFuncSetAttribute(gd::chain_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gd::CHAIN_SMEM));
+      }
     }
     if (B.mixT0.size() <= pc) { cudaEvent_t a, b; GH_CUDA(cudaEventCreate(&a)); GH_CUDA(cudaEventCreate(&b)); B.mixT0.push_back(a); B.mixT1.push_back(b); B.mix_units.push_back(0.0); }
     GH_CUDA(cudaEventRecord(B.mixT0[pc], ms));
+    // settled tilt / delay / spring chains: whole warps of engines go to the pipelined chain kernel, mix_kernel takes the rest
+    const bool chain_fast = getenv("GOOEY_B200_NO_CHAIN_FAST") == nullptr;     // (tests compare the two paths bit for bit)
+    if (chain_fast && M.premix) { gd::chain_fast_kernel<<<(n + 31) / 32, 32, gd::CHAIN_SMEM, ms>>>(M); g_launches.fetch_add(1, std::memory_order_relaxed); }
     gd::mix_kernel<<<(n + 31) / 32, 32, gd::MIX_DYN_SMEM, ms>>>(M);
     GH_CUDA(cudaEventRecord(B.mixT1[pc], ms));
     B.mix_units[pc] = (double)n * nf; B.mix_timed = (int)pc + 1;
@@ -771,6 +783,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   // meters: the call's maxima join the engines' read-and-reset peaks (one small copy; the caller synchronises the stream anyway)
   B.h_peaks.resize((size_t)n * gd::N_PEAKS);
   GH_CUDA(cudaMemcpyAsync(B.h_peaks.data(), B.d_peaks.p, B.h_peaks.size() * 4, cudaMemcpyDeviceToHost, st));
+  GH_CUDA(cudaMemcpyAsync(&B.h_chain_units, B.d_chain_units.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (!B.h_lfo_streams.empty()) GH_CUDA(cudaMemcpyAsync(B.h_lfo_streams.data(), B.d_lfo_streams.p, B.h_lfo_streams.size() * sizeof(gd::LfoStream), cudaMemcpyDeviceToHost, st));
   GH_CUDA(cudaStreamSynchronize(st));
   for (size_t q = 0; q < lfo_refs.size(); q++) E[lfo_refs[q].engine]->lfos[lfo_refs[q].lfo].phase = B.h_lfo_streams[q].phase;

@@ -107,6 +107,7 @@ struct MixLaunch {
                                       // engine's pre-chain stereo mix (strips -> graph -> master) and the general kernel runs only its global chain
   float* premix;                      // [2][n_lpad][premix_stride]: left plane, right plane
   struct MixConst* consts;            // [n]
+  unsigned long long* chain_units;    // engine-frames taken by chain_fast_kernel (chain.cuh) in this render call
 };
 // Everything mix_fast_kernel needs for one engine: the settled smoother values and the trig of the constant pans.
 struct MixConst {
@@ -572,21 +573,23 @@ __device__ __forceinline__ float fbwsfx_one(FbwsDyn& d, int c, const RingRef& r,
 // `reset()` of each reorderable effect, as gooey_engine_set_effect_order / move_effect call it (ffi.rs:1417-1425): saturation,
 // low-pass, tilt, delay, compressor, spring, plate.  The two waveshapers are not in that list.
 __device__ __forceinline__ void fx_reset(FxDyn& f, uint32_t kind, const RingRef& r, const FxGeom& g) {
+  // a slot whose effect was never enabled has no ring arena yet (it is allocated zero-filled on first use): only its scalar state is reset
+  const bool ring = r.base != nullptr;
   switch (kind) {
-    case FXK_SATURATION: for (int c = 0; c < 2; c++) { f.sat.dc_x1[c] = f.sat.dc_y1[c] = 0.0f; os_ring_clear(r, c * OS_WORDS); } break;
+    case FXK_SATURATION: for (int c = 0; c < 2; c++) { f.sat.dc_x1[c] = f.sat.dc_y1[c] = 0.0f; if (ring) os_ring_clear(r, c * OS_WORDS); } break;
     case FXK_LOWPASS: for (int c = 0; c < 2; c++) f.lp.stage1[c] = f.lp.stage2[c] = 0.0f; break;
     case FXK_TILT: for (int c = 0; c < 2; c++) f.tilt.svf[c].ic1 = f.tilt.svf[c].ic2 = 0.0f; break;
     case FXK_DELAY:
-      for (uint32_t j = 0; j < 2u * g.delay_len; j++) r.at(j) = 0.0f;
+      if (ring) for (uint32_t j = 0; j < 2u * g.delay_len; j++) r.at(j) = 0.0f;
       for (int c = 0; c < 2; c++) { f.delay.ch[c].write_index = 0; f.delay.ch[c].z1 = f.delay.ch[c].z2 = 0.0f; }
       break;
-    case FXK_COMPRESSOR: for (int c = 0; c < 2; c++) { f.comp.env[c] = 0.0f; f.comp.gain[c] = 1.0f; f.comp.dc_x1[c] = f.comp.dc_y1[c] = 0.0f; os_ring_clear(r, c * OS_WORDS); } break;
+    case FXK_COMPRESSOR: for (int c = 0; c < 2; c++) { f.comp.env[c] = 0.0f; f.comp.gain[c] = 1.0f; f.comp.dc_x1[c] = f.comp.dc_y1[c] = 0.0f; if (ring) os_ring_clear(r, c * OS_WORDS); } break;
     case FXK_SPRING:
-      for (uint32_t j = 0; j < g.ring_words[2]; j++) r.at(j) = 0.0f;
+      if (ring) for (uint32_t j = 0; j < g.ring_words[2]; j++) r.at(j) = 0.0f;
       for (int c = 0; c < 2; c++) { for (int i = 0; i < 6; i++) f.spring.ch[c].idx[i] = 0; f.spring.ch[c].fb = f.spring.ch[c].damp = 0.0f; }
       break;
     case FXK_PLATE:
-      for (uint32_t j = 0; j < g.ring_words[3]; j++) r.at(j) = 0.0f;
+      if (ring) for (uint32_t j = 0; j < g.ring_words[3]; j++) r.at(j) = 0.0f;
       for (int i = 0; i < 13; i++) f.plate.idx[i] = 0;
       f.plate.bandwidth = f.plate.damp_a = f.plate.damp_b = f.plate.fb_a = f.plate.fb_b = f.plate.lfo_pa = f.plate.lfo_pb = 0.0f;
       break;
