@@ -1,6 +1,8 @@
 // device_rt.h — small CUDA runtime helpers shared by the host-side classes:
 // error latch, device buffers, pinned buffers, SoA state upload.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -33,9 +35,15 @@ template <class T> struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { if (p) cudaFree(p); }
+  // Growth frees and re-allocates, and cudaFree waits for the whole device: a per-piece table that outgrows its buffer by a few
+  // entries in the middle of a render drains the pipeline (measured: ~0.5 s at the bar boundary of an 8192-engine bounce).
+  // Small buffers therefore grow with 50 % headroom; large ones (voice / output blocks) are sized exactly.
   void alloc(size_t count) {
     if (count <= n && p) return;
+    static const bool trace = getenv("GOOEY_B200_TRACE") != nullptr;
+    if (trace && p) fprintf(stderr, "[gooey trace] device buffer regrown: %zu -> %zu bytes (cudaFree drains the device)\n", n * sizeof(T), count * sizeof(T));
     if (p) { cudaFree(p); p = nullptr; }
+    if (count * sizeof(T) <= ((size_t)64 << 20)) count += count / 2 + 64;
     n = count;
     if (count) GH_CUDA(cudaMalloc(&p, count * sizeof(T)));
   }

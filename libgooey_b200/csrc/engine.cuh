@@ -3,6 +3,7 @@
 // one pass: host-resolved sequencer schedule -> per-voice event tables -> voice kernels (kernels.cuh / wave.cuh) ->
 // mix kernel (mix.cuh: strips, pan, MixerGraph, master gain, global effect chain, limiter, stereo / mono write-out).
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -695,6 +696,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   for (size_t pc = 0; pc < cuts.size(); f0 = cuts[pc], pc++) {
     const uint32_t nf = cuts[pc] - f0;
     const int vb = two_bufs ? (int)(pc & 1) : 0;
+    const auto h0 = std::chrono::steady_clock::now();
     if (pc >= (two_bufs ? 2u : 1u)) GH_CUDA(cudaStreamWaitEvent(st, B.ev_mixed[vb], 0));   // voice buffer vb is free again
     B.voices.reset();
     for (int i = 0; i < n; i++)
@@ -709,6 +711,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
         const int slot = ch < 5 ? E[i]->strip[ch].slot : (ch == 5 ? E[i]->poly.slot : E[i]->gran.slot);
         B.voices.add(type, (uint32_t)slot, (uint32_t)(ch * n_lpad + i), cur, (ch < 5 && lfo_planes && !vroutes[(size_t)i * 5 + ch].empty()) ? &vroutes[(size_t)i * 5 + ch] : nullptr);
       }
+    const auto h1 = std::chrono::steady_clock::now();
     cudaEvent_t start = B.ev_piece;
     GH_CUDA(cudaEventRecord(start, st));
     // the clock index differs per engine only through e->k; voices carry their own k, the launch passes the table
@@ -716,6 +719,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     B.voices.set_mod(lfo_planes, (long long)frames, (int)f0);
     B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_bufs[vb].p, (long long)vstride);
     tev(tv1, st);
+    const auto h2 = std::chrono::steady_clock::now();
     GH_CUDA(cudaEventRecord(B.ev_voices[vb], st));
     GH_CUDA(cudaStreamWaitEvent(ms, B.ev_voices[vb], 0));
     mflat.clear(); mbegin.assign(1, 0);
@@ -767,6 +771,11 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     GH_CUDA(cudaEventRecord(B.ev_mixed[vb], ms));
     if (on_piece) (*on_piece)(f0, nf, B.ev_mixed[vb]);
     tev(tm1, ms);
+    if (trace) {
+      const auto h3 = std::chrono::steady_clock::now();
+      auto msf = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      fprintf(stderr, "[gooey trace] host, piece %zu: wait + event lists %.1f ms, voice launches %.1f ms, mixer launches %.1f ms\n", pc, msf(h0, h1), msf(h1, h2), msf(h2, h3));
+    }
   }
   GH_CUDA(cudaStreamWaitEvent(st, B.ev_mixed[0], 0));
   if (two_bufs && cuts.size() > 1) GH_CUDA(cudaStreamWaitEvent(st, B.ev_mixed[1], 0));

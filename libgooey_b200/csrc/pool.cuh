@@ -453,6 +453,22 @@ template <class V> struct TypeRunner {
       GH_CUDA(cudaEventRecord(evDoneC, sC));
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneC, 0));
       GH_CUDA(cudaStreamWaitEvent(parent, evDoneS, 0));
+      if (getenv("GOOEY_B200_TRACE_TYPES")) {      // diagnostic (serialises the buckets): time of the time-parallel chain and of the per-sample kernel, voices on the latter
+        cudaEvent_t t0, t1, t2;
+        cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+        cudaEventRecord(t1, sC); cudaEventRecord(t2, sS);
+        GH_CUDA(cudaStreamSynchronize(sC)); GH_CUDA(cudaStreamSynchronize(sS));
+        std::vector<uint8_t> mode(cnt);
+        GH_CUDA(cudaMemcpy(mode.data(), d_mode.p, cnt, cudaMemcpyDeviceToHost));
+        int slow = 0; for (uint8_t m : mode) slow += m != 0;
+        float ms_all = 0.0f;
+        cudaEventElapsedTime(&ms_all, evT0[0], t1);
+        float ms_slow_end = 0.0f;
+        cudaEventElapsedTime(&ms_slow_end, evT0[0], t2);
+        fprintf(stderr, "[gooey trace]   %s: %d voices x %d frames, %d on the per-sample path; back ends done %.1f ms, per-sample kernel done %.1f ms after the first back-end launch\n",
+                backend_name, cnt, frames, slow, ms_all, ms_slow_end);
+        cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+      }
     } else {
       if constexpr (std::is_same<V, gd::GranV>::value) {
         const char* ge = getenv("GOOEY_B200_GRAN");
@@ -468,7 +484,16 @@ template <class V> struct TypeRunner {
       if constexpr (std::is_same<V, gd::BassV>::value) {
         const char* be = getenv("GOOEY_B200_BASS");
         if (!(be && strcmp(be, "serial") == 0) && !modulated) {      // LFO-routed basses take the per-sample kernel       // one warp per bass voice, lane = frame (bass_wave.cuh)
+          const bool ttrace = getenv("GOOEY_B200_TRACE_TYPES") != nullptr;
+          cudaEvent_t t0 = nullptr, t1 = nullptr;
+          if (ttrace) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, sC); }
           GH_LAUNCH((gd::bass_wave_kernel<2>), (cnt + 1) / 2, 64, sC, L);
+          if (ttrace) {
+            cudaEventRecord(t1, sC); GH_CUDA(cudaStreamSynchronize(sC));
+            float ms = 0.0f; cudaEventElapsedTime(&ms, t0, t1);
+            fprintf(stderr, "[gooey trace]   bass_wave_kernel: %d voices x %d frames, %.1f ms\n", cnt, frames, ms);
+            cudaEventDestroy(t0); cudaEventDestroy(t1);
+          }
           g_launches.fetch_add(1, std::memory_order_relaxed);
           GH_CUDA(cudaGetLastError());
           GH_CUDA(cudaEventRecord(evDoneC, sC));
