@@ -242,10 +242,16 @@ template <bool FAST = false> G_HD float osc_sine(float idx, float freq, float sr
   if (FAST) return gm::g_sinf_fast(x);
   return gm::g_sinf(x);
 }
+// the same with the reciprocal of the sample rate hoisted by the caller (additive oscillators: one division per harmonic)
+G_HD float osc_sine_fast(float idx, float freq, float sr, float rcp_sr) {
+  const float two_pi = 2.0f * PI_F;
+  return gm::g_sinf_fast(gm::g_div_by(idx * freq * two_pi, sr, rcp_sr));
+}
 // additive "triangle": odd harmonics, gain 1/i^2 (powf(i,2) is exact so 1/(i*i) matches), Gibbs taper (:106-131)
 template <bool FAST = false> G_HD float osc_triangle(float idx, float freq, float sr) {
   float output = 0.0f;
   float nyquist = sr / 2.0f;
+  const float rcp_sr = 1.0f / sr;
   float q = nyquist / freq;
   int max_h = !(q == q) ? 0 : (q >= 2147483648.0f ? 2147483647 : (q <= -2147483648.0f ? (-2147483647 - 1) : (int)q));
   for (int i = 1; i <= max_h; i += 2) {
@@ -262,7 +268,7 @@ template <bool FAST = false> G_HD float osc_triangle(float idx, float freq, floa
       float ratio = hf / nyquist;
       if (ratio > 0.75f) { float t = (ratio - 0.75f) / 0.25f; taper = 1.0f - t * t; }
     }
-    output += gain * taper * osc_sine<FAST>(idx, hf, sr);
+    output += gain * taper * (FAST ? osc_sine_fast(idx, hf, sr, rcp_sr) : osc_sine<false>(idx, hf, sr));
   }
   return output;
 }

@@ -404,6 +404,8 @@ __global__ void math_selftest_kernel(int kind, const float* x, const float* y, f
     case 6: r = gm::g_tanhf(x[i]); break;
     case 7: r = gm::g_tanf(x[i]); break;
     case 8: r = gm::g_expm1f(x[i]); break;
+    case 9: r = gm::g_sinf_fast(x[i]); break;                                  // the front end's ~1-ulp sine
+    case 10: r = gm::g_div_by(x[i], y[i], 1.0f / y[i]); break;                  // x / y through the hoisted reciprocal: must equal the IEEE quotient
     default: r = 0.0f;
   }
   out[i] = r;

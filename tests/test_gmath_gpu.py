@@ -89,3 +89,22 @@ def test_fdlibm_ports_bit_exact(kind, fn, lo, hi):
     got = dev(kind, x)
     want = np.array([f(float(a)) for a in x], np.float32)
     assert np.array_equal(bits(got), bits(want))
+
+
+def test_fast_sine_of_the_additive_oscillators_stays_within_two_ulp_of_one():
+    """g_sinf_fast (front end only): absolute error against f64 over the argument range a 4-minute bounce reaches."""
+    rng = np.random.default_rng(6)
+    x = np.concatenate([rng.uniform(-7, 7, N), rng.uniform(0, 4e5, N), rng.uniform(0, 3e7, N), [0.0, np.pi, -np.pi / 2]]).astype(np.float32)
+    got = dev(9, x).astype(np.float64)
+    err = np.abs(got - np.sin(x.astype(np.float64))).max()
+    print(f"g_sinf_fast max abs err {err:.3e}")
+    assert err <= 2.4e-7
+
+
+def test_division_by_the_sample_rate_through_the_hoisted_reciprocal_is_the_ieee_quotient():
+    rng = np.random.default_rng(7)
+    for sr in (44100.0, 48000.0, 22050.0, 96000.0, 11025.0):
+        a = np.concatenate([rng.uniform(0, 1e3, N), rng.uniform(0, 3e9, N), np.exp(rng.uniform(-12, 30, N)), [0.0]]).astype(np.float32)
+        b = np.full_like(a, sr)
+        got = dev(10, a, b)
+        assert np.array_equal(bits(got), bits(a / b)), sr
