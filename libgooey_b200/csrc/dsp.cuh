@@ -298,7 +298,13 @@ G_HD PinkCoef pink_coefs(float sr) {  // :24-46
 }
 G_HD float pink_tick(Pink& p, const PinkCoef& c) {  // :56-79
   uint64_t h = xorshift64s_next(p.rng);
+#ifdef __CUDA_ARCH__
+  // a / 16777215 through the rounded reciprocal (gm::g_div_by): bit-identical to the IEEE quotient for EVERY a in [0, 2^24)
+  // (all 16 777 216 cases checked on the host), 3 instructions instead of div.rn's ~9 — the division was 9 % of a kick block
+  float w = gm::g_div_by((float)(uint32_t)(h >> 40), 16777215.0f, 0x1.000002p-24f);
+#else
   float w = (float)(uint32_t)(h >> 40) / 16777215.0f;
+#endif
   w = w * 2.0f - 1.0f;
   p.f0 = c.p0 * p.f0 + c.g0 * w;
   p.f1 = c.p1 * p.f1 + c.g1 * w;

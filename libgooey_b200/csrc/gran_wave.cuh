@@ -112,7 +112,16 @@ __global__ void __launch_bounds__(WARPS * 32) gran_wave_kernel(const VoiceLaunch
           if (!g.active) continue;
           if (g.age >= g.duration) { g.active = 0; continue; }
           const float phase = clampf(g.age / g.duration, 0.0f, 1.0f);
+          // window = max(sin(pi phase), 0) ^ shape (granulator.rs:686-689).  A memoryless gain in [0, 1] applied to one grain of up to 80:
+          // the ~1-ulp sine of the front ends (relative accuracy kept near its zeros: the reduction is exact) and exp2(shape log2 s) with
+          // CUDA's 1-ulp log2f / exp2f — relative error <= 3e-6 of a value <= 1 — replace ~180 instructions of the bit-exact ports per
+          // grain-sample (GOOEY_GRAN_EXACT_WINDOW restores them; the per-sample path, GOOEY_B200_GRAN=serial, always uses them)
+#ifdef GOOEY_GRAN_EXACT_WINDOW
           const float window = gm::g_powf(fmaxf(gm::g_sinf(PI_F * clampf(phase, 0.0f, 1.0f)), 0.0f), g.window_shape);
+#else
+          const float sw = fmaxf(gm::g_sinf_fast(PI_F * clampf(phase, 0.0f, 1.0f)), 0.0f);
+          const float window = sw > 0.0f ? exp2f(g.window_shape * log2f(sw)) : gm::g_powf(sw, g.window_shape);
+#endif
           const float rg = g.release_total > 0.0f ? clampf(g.release_samples / g.release_total, 0.0f, 1.0f) : 1.0f;
           const float smp = gran_sample(buf, blen, g.source_pos);
           part += smp * window * rg * g.velocity * gc;

@@ -103,8 +103,8 @@ def test_fast_sine_of_the_additive_oscillators_stays_within_two_ulp_of_one():
 
 def test_division_by_the_sample_rate_through_the_hoisted_reciprocal_is_the_ieee_quotient():
     rng = np.random.default_rng(7)
-    for sr in (44100.0, 48000.0, 22050.0, 96000.0, 11025.0):
-        a = np.concatenate([rng.uniform(0, 1e3, N), rng.uniform(0, 3e9, N), np.exp(rng.uniform(-12, 30, N)), [0.0]]).astype(np.float32)
+    for sr in (44100.0, 48000.0, 22050.0, 96000.0, 11025.0, 16777215.0):   # the last: the pink-noise generator's 24-bit scale (every numerator below)
+        a = np.arange(1 << 24, dtype=np.float32) if sr == 16777215.0 else np.concatenate([rng.uniform(0, 1e3, N), rng.uniform(0, 3e9, N), np.exp(rng.uniform(-12, 30, N)), [0.0]]).astype(np.float32)
         b = np.full_like(a, sr)
         got = dev(10, a, b)
         assert np.array_equal(bits(got), bits(a / b)), sr
