@@ -13,6 +13,10 @@
 //   * ring words laid out [word][engine] (mix.cuh), so the 32 engines of a warp read and write one 128-byte row per access;
 //   * the pre-chain stereo mix (strips -> graph -> master, mix_fast_kernel) read through the same pipeline and the output
 //     written through a shared-memory tile, 64-byte row segments.
+// (Tried and dropped: requesting a line's cell of frame n + 4 straight into the register frame n has just consumed, no shared-memory
+// staging — half the instructions, but slower, 2.0 vs 1.25 us per frame alone: a warp has six scoreboards, so a wait on the oldest
+// of 56 outstanding loads is a wait on the newest one sharing its scoreboard and the kernel runs at DRAM latency.  cp.async groups
+// do not have that limit.)
 // A warp takes its 32 engines only if ALL of them qualify with the same chain (same effects in the same order); it then marks
 // them done (fast[i] = 1) and mix_kernel, launched next on the same stream, skips them.  Everything else — first pieces of a
 // bounce while FFI edits glide, racks, the other effect kinds, ping-pong, mid-piece events — stays with mix_kernel.
@@ -173,23 +177,25 @@ __global__ void __launch_bounds__(32) chain_fast_kernel(const MixLaunch L) {
   }
   __syncwarp();
 
-  // ---- ring cursors ----
+  // ---- ring cursors, as words of the slot's arena (line offset included); the bases carry the engine column ----
   const long long cap = L.ring_cap;
-  float* const dring = L.ring[FXS_DELAY];
-  float* const sring = L.ring[FXS_SPRING];
-  uint32_t d_pf[2] = {0, 0};           // prefetch cursor of the delay read (word within the channel's half)
+  float* const dring = L.ring[FXS_DELAY] ? L.ring[FXS_DELAY] + es : nullptr;
+  float* const sring = L.ring[FXS_SPRING] ? L.ring[FXS_SPRING] + es : nullptr;
+  uint32_t d_pf[2] = {0, 0};           // prefetch cursor of the delay read
   if (has_delay && valid) {
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-      d_pf[c] = wrap2(d_wi[c] + dlen - d_di[c], dlen);
-      d_s2[c] = dring[(long long)(c * dlen + wrap2(d_wi[c] + dlen - d_di[c] - 1u, dlen)) * cap + es];   // the frame-0 second tap; later frames carry it
+      d_pf[c] = c * dlen + wrap2(d_wi[c] + dlen - d_di[c], dlen);
+      d_s2[c] = dring[(long long)(c * dlen + wrap2(d_wi[c] + dlen - d_di[c] - 1u, dlen)) * cap];   // the frame-0 second tap; later frames carry it
+      d_wi[c] += c * dlen;
     }
   }
-  uint32_t s_pf[2][6];
+  uint32_t s_pf[2][6], s_w[2][6];      // prefetch / write cursors of the spring lines
 #pragma unroll
   for (int c = 0; c < 2; c++)
 #pragma unroll
-    for (int k = 0; k < 6; k++) s_pf[c][k] = s_idx[c][k];
+    for (int k = 0; k < 6; k++) s_pf[c][k] = s_w[c][k] = geo.spring_off[c * 6 + k] + s_idx[c][k];
+#define CF_NEXT(w, lo, len) ((w) + 1u == (lo) + (len) ? (lo) : (w) + 1u)
 
   const int frames = L.frames;
   const int ntiles = (frames + CF_T - 1) / CF_T;
@@ -204,8 +210,8 @@ __global__ void __launch_bounds__(32) chain_fast_kernel(const MixLaunch L) {
         if (has_delay) {
 #pragma unroll
           for (int c = 0; c < 2; c++) {
-            __pipeline_memcpy_async(&S.ring[st][j][c][lane], dring + (long long)(c * dlen + d_pf[c]) * cap + es, 4);
-            d_pf[c] = wrap2(d_pf[c] + 1u, dlen);
+            __pipeline_memcpy_async(&S.ring[st][j][c][lane], dring + (long long)d_pf[c] * cap, 4);
+            d_pf[c] = CF_NEXT(d_pf[c], c * dlen, dlen);
           }
         }
         if (has_spring) {
@@ -213,8 +219,8 @@ __global__ void __launch_bounds__(32) chain_fast_kernel(const MixLaunch L) {
           for (int c = 0; c < 2; c++)
 #pragma unroll
             for (int k = 0; k < 6; k++) {
-              __pipeline_memcpy_async(&S.ring[st][j][2 + c * 6 + k][lane], sring + (long long)(geo.spring_off[c * 6 + k] + s_pf[c][k]) * cap + es, 4);
-              s_pf[c][k] = wrap2(s_pf[c][k] + 1u, geo.spring_len[c * 6 + k]);
+              __pipeline_memcpy_async(&S.ring[st][j][2 + c * 6 + k][lane], sring + (long long)s_pf[c][k] * cap, 4);
+              s_pf[c][k] = CF_NEXT(s_pf[c][k], geo.spring_off[c * 6 + k], geo.spring_len[c * 6 + k]);
             }
         }
       }
@@ -281,8 +287,8 @@ __global__ void __launch_bounds__(32) chain_fast_kernel(const MixLaunch L) {
                 if (fabsf(d_z2[c]) < 1e-15f) d_z2[c] = 0.0f;
                 float w = dry + filtered * d_fb[c];
                 w = (isfinite(w) && fabsf(w) > 1e-15f) ? w : 0.0f;
-                dring[(long long)(c * dlen + d_wi[c]) * cap + es] = w;
-                d_wi[c] = wrap2(d_wi[c] + 1u, dlen);
+                dring[(long long)d_wi[c] * cap] = w;
+                d_wi[c] = CF_NEXT(d_wi[c], c * dlen, dlen);
                 const float out = dry * (1.0f - d_mix[c]) + filtered * d_mix[c];
                 x[c] = isfinite(out) ? out : dry;
               }
@@ -297,8 +303,8 @@ __global__ void __launch_bounds__(32) chain_fast_kernel(const MixLaunch L) {
                   const float delayed = S.ring[st][j][2 + c * 6 + k][lane];
                   const float v = sgl - G[k] * delayed;
                   sgl = G[k] * v + delayed;
-                  sring[(long long)(geo.spring_off[c * 6 + k] + s_idx[c][k]) * cap + es] = v;
-                  s_idx[c][k] = wrap2(s_idx[c][k] + 1u, geo.spring_len[c * 6 + k]);
+                  sring[(long long)s_w[c][k] * cap] = v;
+                  s_w[c][k] = CF_NEXT(s_w[c][k], geo.spring_off[c * 6 + k], geo.spring_len[c * 6 + k]);
                 }
                 s_damp[c] = sgl * s_d2[c] + s_damp[c] * s_d1[c];
                 if (fabsf(s_damp[c]) < 1e-15f) s_damp[c] = 0.0f;
@@ -338,6 +344,14 @@ __global__ void __launch_bounds__(32) chain_fast_kernel(const MixLaunch L) {
     __syncwarp();
   }
   __pipeline_wait_prior(0);
+  // cursors back to the state's own units
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    d_wi[c] -= c * dlen;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s_idx[c][k] = s_w[c][k] - geo.spring_off[c * 6 + k];
+  }
+#undef CF_NEXT
 
   // ---- carried state back to the pool ----
   if (valid) {

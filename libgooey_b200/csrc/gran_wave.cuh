@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(WARPS * 32) gran_wave_kernel(const VoiceLaunch
   const RateCtx& rc = L.rc;
   const float sr = rc.sr;
   bool settled = false;                       // re-derived after every event
+  int tg_n = -1; float tg = 1.0f;             // lane 0: active-grain count of the last gain-compensation target and the target
   for (int f0 = 0; f0 < L.frames; f0 += 32) {
     const int nf = min(32, L.frames - f0);
     float mine = 0.0f;
@@ -90,11 +91,10 @@ __global__ void __launch_bounds__(WARPS * 32) gran_wave_kernel(const VoiceLaunch
       int n_act = 0;
 #pragma unroll
       for (int q = 0; q < 3; q++) { const int i = lane + 32 * q; if (i < 80) n_act += (int)s.grains[i].active; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) n_act += __shfl_xor_sync(0xffffffffu, n_act, o);
+      n_act = __reduce_add_sync(0xffffffffu, n_act);                       // one redux.sync instead of a five-step shuffle tree
       float raw = 0.0f;
       if (lane == 0) {
-        const float tg = n_act == 0 ? 1.0f : clampf(1.0f / sqrtf((float)n_act), 0.0f, 1.0f);
+        if (n_act != tg_n) { tg_n = n_act; tg = n_act == 0 ? 1.0f : clampf(1.0f / sqrtf((float)n_act), 0.0f, 1.0f); }   // pure function of the count: once per change
         if (fabsf(s.gc_tgt - tg) > 1e-8f) s.gc_tgt = tg;
         smooth_tick(s.gc_cur, s.gc_tgt, rc.smooth10);
       }

@@ -74,7 +74,7 @@ def main(tag):
         mix.write(f"== wave_kernel<{k}>: {tot} warp instructions; opcode mix (share of instructions / share of stall samples)\n")
         for op, n in m.most_common(12):
             mix.write(f"   {op:10s} {100 * n / tot:5.1f}%  {100 * sm[op] / ts:5.1f}%\n")
-    for k in ["mix_kernel", "bass_wave_kernel", "gran_wave_kernel", "coop_kernel"]:      # engine-level kernels and the cooperative back end
+    for k in ["chain_fast_kernel", "mix_kernel", "bass_wave_kernel", "gran_wave_kernel", "coop_kernel"]:      # engine-level kernels and the cooperative back end
         path = f"gpurun_out/ncu_{tag}_raw_{k}.csv"
         if not os.path.exists(path):
             continue
@@ -92,6 +92,12 @@ def main(tag):
             out.write(f"  stall {kk[34:-23]:40s} {v:.2f}\n")
         rd, wr = to_bytes(dd["dram__bytes_read.sum"], u["dram__bytes_read.sum"]), to_bytes(dd["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
         traffic[k] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "source": f"profiles/{tag}_ncu_summary.txt"}
+    import subprocess
+    for k, rep in [("chain_fast_kernel", f"gpurun_out/prof_{tag}_chain_fast_kernel.ncu-rep"), ("bass_wave_kernel", f"gpurun_out/prof_{tag}_bass_wave_kernel.ncu-rep"),
+                   ("gran_wave_kernel", f"gpurun_out/prof_{tag}_gran.ncu-rep")]:
+        if os.path.exists(rep):
+            txt = subprocess.run([sys.executable, "profiles/ncu_hot_lines.py", rep], capture_output=True, text=True).stdout
+            open(f"profiles/{tag}_hot_lines_{k}.txt", "w").write("\n".join(txt.splitlines()[:45]) + "\n")
     warm = f"gpurun_out/ncu_{tag}_warm_dram.csv"
     if os.path.exists(warm):
         shutil.copy(warm, f"profiles/{tag}_ncu_warm_cache_dram.csv")
