@@ -510,9 +510,9 @@ def run_ours(args, rank, world, local_rank):
 
     peak, peak_kind = measured_peaks()
     extra = {}
-    if args.configs == "all":
+    if args.configs in ("all", "c5"):
         import engine_scripts as S
-        if world == 1:
+        if world == 1 and args.configs == "all":
             extra["C1"] = config_c1(L)
             ids = np.arange(C3_ENGINES)
             extra["C3"] = engine_config(L, torch, dev, ids, _c3_script(S), C3_BARS, {0, 1, C3_ENGINES - 1}, peak, None,
@@ -586,7 +586,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--configs", default="all", choices=["all", "c2"], help="c2: headline only (profiling runs)")
+    ap.add_argument("--configs", default="all", choices=["all", "c2", "c5"], help="c2: headline only (profiling runs); c5: headline + the C5 block only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -374,6 +374,21 @@ void* gooey_b200_host_alloc(size_t bytes, int device, int* out_numa_node) {
   void* p = nullptr;
   const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
   if (e == cudaSuccess) memset(p, 0, bytes);           // first touch under the policy
+  if (e == cudaSuccess) {
+    // First DMA into freshly pinned pages is several times slower than later passes (measured with eight ranks draining into new
+    // 5.8 GB blocks: 20 GB/s aggregate against 94 GB/s into blocks that had been written before — IOMMU / page-table warm-up on
+    // the host side), so the allocator makes that first pass itself: zeros from a small device block over the whole range.
+    void* d = nullptr;
+    const size_t chunk = (size_t)64 << 20;
+    if (cudaMalloc(&d, std::min(chunk, bytes)) == cudaSuccess) {
+      cudaMemset(d, 0, std::min(chunk, bytes));
+      for (size_t off = 0; off < bytes; off += chunk)
+        cudaMemcpyAsync((char*)p + off, d, std::min(chunk, bytes - off), cudaMemcpyDeviceToHost, 0);
+      cudaDeviceSynchronize();
+      cudaFree(d);
+    }
+    cudaGetLastError();
+  }
 #ifdef SYS_set_mempolicy
   if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
 #endif

@@ -92,12 +92,9 @@ def main(tag):
             out.write(f"  stall {kk[34:-23]:40s} {v:.2f}\n")
         rd, wr = to_bytes(dd["dram__bytes_read.sum"], u["dram__bytes_read.sum"]), to_bytes(dd["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
         traffic[k] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "source": f"profiles/{tag}_ncu_summary.txt"}
-    import subprocess
-    for k, rep in [("chain_fast_kernel", f"gpurun_out/prof_{tag}_chain_fast_kernel.ncu-rep"), ("bass_wave_kernel", f"gpurun_out/prof_{tag}_bass_wave_kernel.ncu-rep"),
-                   ("gran_wave_kernel", f"gpurun_out/prof_{tag}_gran.ncu-rep")]:
-        if os.path.exists(rep):
-            txt = subprocess.run([sys.executable, "profiles/ncu_hot_lines.py", rep], capture_output=True, text=True).stdout
-            open(f"profiles/{tag}_hot_lines_{k}.txt", "w").write("\n".join(txt.splitlines()[:45]) + "\n")
+    for k in ["chain_fast_kernel", "bass_wave_kernel", "gran_wave_kernel"]:
+        if os.path.exists(f"gpurun_out/hot_lines_{tag}_{k}.txt"):
+            shutil.copy(f"gpurun_out/hot_lines_{tag}_{k}.txt", f"profiles/{tag}_hot_lines_{k}.txt")
     warm = f"gpurun_out/ncu_{tag}_warm_dram.csv"
     if os.path.exists(warm):
         shutil.copy(warm, f"profiles/{tag}_ncu_warm_cache_dram.csv")
