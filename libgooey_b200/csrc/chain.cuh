@@ -1,7 +1,7 @@
 // chain.cuh — the global effect chain of SETTLED engines: tilt filter, delay and spring reverb (any order, any subset) + soft limiter.
 //
 // mix_kernel (mix.cuh) is the general per-engine mixer: events, racks, every effect kind, gliding smoothers, state in shared
-// memory behind run-time slot indices — ~1000 instructions per engine-frame on a single warp per CTA (profiles/r2_mix_*).  Once
+// memory behind run-time slot indices — ~1000+ warp-instructions per frame of its 32 engines on a single warp per CTA (profiles/r2_mix_*).  Once
 // the parameter smoothers of an engine's chain have settled (SmoothedParam::tick returns the same value every sample,
 // smoother.rs:120-137) the chain of ffi.rs:1317-1364 is the same few recurrences every frame with constant coefficients.  This
 // kernel runs exactly those, in the reference's operation order (effects/tilt_filter.rs:87-139, delay.rs:321-491,
