@@ -504,7 +504,7 @@ GM_HD float g_sinf_fast(float y) {
 }
 // a / b, correctly rounded, for a fixed divisor whose reciprocal y = RN(1 / b) the caller hoists (Markstein: q = RN(a y),
 // r = a - b q exactly, q' = RN(q + r y)); bit-identical to the IEEE quotient away from overflow / underflow of the quotient
-// (checked on 7.2e8 random numerators x 12 sample rates, tests/test_oracle_pins_cpu.py holds a smaller run).  3 instructions
+// (checked on 7.2e8 random numerators x 12 sample rates; tests/test_emu_cpu.py and tests/test_gmath_gpu.py hold smaller runs on the host and on the device).  3 instructions
 // instead of the ~9 + slow-path branch of div.rn.f32.
 GM_HD float g_div_by(float a, float b, float y) {
   const float q = a * y;

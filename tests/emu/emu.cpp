@@ -175,4 +175,20 @@ int emu_render_voices(const GooeyVoicePatch* patches, uint32_t n, float sr, uint
   return 0;
 }
 
+// The front end's arithmetic shortcuts, evaluated by the host build of the very functions the kernels call (gmath.cuh):
+// kind 0 = g_div_by(a, b, 1 / b) (must equal the IEEE quotient bit for bit), 1 = g_sinf_fast(a), 2 = the additive triangle with
+// FAST = true (osc_triangle<true>(a, b, sr)), 3 = the same with the bit-exact sine.
+int emu_math(int kind, const float* a, const float* b, float sr, float* out, uint32_t n) {
+  for (uint32_t i = 0; i < n; i++) {
+    switch (kind) {
+      case 0: { volatile float y = 1.0f / b[i]; out[i] = gm::g_div_by(a[i], b[i], y); } break;
+      case 1: out[i] = gm::g_sinf_fast(a[i]); break;
+      case 2: out[i] = osc_triangle<true>(a[i], b[i], sr); break;
+      case 3: out[i] = osc_triangle<false>(a[i], b[i], sr); break;
+      default: return -1;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -57,3 +57,14 @@ def render_voices(patches, frames, triggers=(), params=(), sample_rate=44100.0, 
                                  _p(ev_x, f32), _p(out, f32), int(mode), int(n_calls), _p(fast, ctypes.c_int))
     assert rc == 0
     return out, fast
+
+
+def math(kind, a, b=None, sample_rate=44100.0):
+    """emu_math: 0 = division through the hoisted reciprocal, 1 = the front end's sine, 2 / 3 = additive triangle with that sine / the exact one."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = a if b is None else np.ascontiguousarray(b, np.float32)
+    out = np.empty_like(a)
+    f32 = ctypes.c_float
+    rc = lib().emu_math(int(kind), _p(a, f32), _p(b, f32), f32(sample_rate), _p(out, f32), a.size)
+    assert rc == 0
+    return out

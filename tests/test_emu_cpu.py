@@ -54,3 +54,27 @@ def test_gliding_parameters_fall_back_to_general_path_and_recover():
     assert (fast[smoothed] == 3).all()      # the call containing the edit runs the general path, the others split
     assert (fast[~smoothed] == 4).all()     # Tom2 parameters are not smoothed
     assert np.array_equal(got, want)
+
+
+def test_division_through_the_hoisted_reciprocal_equals_the_ieee_quotient():
+    """gm::g_div_by (Markstein correction) as the additive oscillators and the pink-noise scale use it: bit-identical to `/`
+    (host build of the same function; tests/test_gmath_gpu.py runs it on the device, with every 24-bit numerator for the noise scale)."""
+    rng = np.random.default_rng(11)
+    for b in (44100.0, 48000.0, 22050.0, 96000.0, 16777215.0):
+        a = np.concatenate([rng.uniform(0, 1e3, 200000), rng.uniform(0, 3e9, 200000), np.exp(rng.uniform(-12, 30, 200000)),
+                            np.arange(0, 1 << 24, 37), [0.0]]).astype(np.float32)
+        got = E.math(0, a, np.full_like(a, b))
+        assert np.array_equal(got.view(np.uint32), (a / np.float32(b)).astype(np.float32).view(np.uint32)), b
+
+
+def test_front_end_sine_and_additive_triangle_stay_inside_their_error_budget():
+    rng = np.random.default_rng(12)
+    x = np.concatenate([rng.uniform(-7, 7, 200000), rng.uniform(0, 4e5, 200000), rng.uniform(0, 3e7, 200000)]).astype(np.float32)
+    err = np.abs(E.math(1, x).astype(np.float64) - np.sin(x.astype(np.float64))).max()
+    assert err <= 2.4e-7, err
+    # the additive triangle (oscillator.rs:106-131) over two seconds of sample indices at drum pitches: fast against exact sine
+    idx = rng.integers(0, 88200, 20000).astype(np.float32)
+    freq = rng.uniform(30.0, 400.0, 20000).astype(np.float32)
+    d = np.abs(E.math(2, idx, freq).astype(np.float64) - E.math(3, idx, freq).astype(np.float64)).max()
+    print(f"g_sinf_fast err {err:.2e}; additive triangle, fast vs exact sine: {d:.2e}")
+    assert d <= 6e-7, d
