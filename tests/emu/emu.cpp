@@ -168,6 +168,14 @@ int emu_render_voices(const GooeyVoicePatch* patches, uint32_t n, float sr, uint
       case GOOEY_INSTRUMENT_SNARE: { SnareState s; gh::init_from_patch(s, patches[v], sr); run_calls(SnareE{}, s); } break;
       case GOOEY_INSTRUMENT_HIHAT: { HatState s; gh::init_from_patch(s, patches[v], sr); run_calls(HatE{}, s); } break;
       case GOOEY_INSTRUMENT_TOM: { TomState s; gh::init_from_patch(s, patches[v], sr); run_calls(TomE{}, s); } break;
+      case GOOEY_INSTRUMENT_BASS: {      // no split path: the per-sample tick (what bass_wave_kernel falls back to, block by block)
+        BassState s; gh::init_from_patch(s, patches[v], sr);
+        size_t e = 0;
+        for (uint32_t j = 0; j < frames; j++) {
+          while (e < all.size() && all[e].frame <= j) { bass_event(s, all[e], tt); e++; }
+          o[j] = bass_tick(s, tt, rc);
+        }
+      } break;
       default: return -1;
     }
     if (took_fast) took_fast[v] = fast_calls;

@@ -78,3 +78,16 @@ def test_front_end_sine_and_additive_triangle_stay_inside_their_error_budget():
     d = np.abs(E.math(2, idx, freq).astype(np.float64) - E.math(3, idx, freq).astype(np.float64)).max()
     print(f"g_sinf_fast err {err:.2e}; additive triangle, fast vs exact sine: {d:.2e}")
     assert d <= 6e-7, d
+
+
+def test_bass_per_sample_tick_bit_exact():
+    """bass_tick / bass_event (voices2.cuh: the tick bass_wave_kernel falls back to block by block, and the reference order its
+    time-parallel blocks restate) against the oracle's BassSynth, host build: presets, retriggers, gliding and snapped edits."""
+    patches = [V.patch(V.BASS, V.BASS_PRESETS[k]) for k in ("acid", "sub", "reese", "stab")] + [V.patch(V.BASS, V.BASS_PRESETS["reese"], tuning=0.7)]
+    n = len(patches)
+    trig = [(i, 0, 0.6 + 0.1 * i) for i in range(n)] + [(i, f, 0.8) for i in range(n) for f in (5513, 16539, 30000)]
+    params = [(i, 9000, 6, 0.35, False) for i in range(n)] + [(i, 20000, 7, 0.9, True) for i in range(n)] + [(1, 12000, 13, 0.4, False), (3, 100, 2, 0.1, True)]
+    want = O.render_voices(patches, 40000, triggers=trig, params=params)
+    got, _ = E.render_voices(patches, 40000, triggers=trig, params=params, mode=0)
+    assert np.abs(want).max() > 0.05
+    assert np.array_equal(got, want)
