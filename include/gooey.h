@@ -211,6 +211,9 @@ void gooey_engine_sequencer_set_instrument_pattern(GooeyEngine* engine, uint32_t
 void gooey_engine_sequencer_start(GooeyEngine* engine);
 void gooey_engine_sequencer_stop(GooeyEngine* engine);
 void gooey_engine_sequencer_reset(GooeyEngine* engine);
+/* src/ffi.rs:2188-2215: sequencers keep their clock but fire nothing (and export no MIDI event) while disabled; default true */
+void gooey_engine_set_sequencer_triggers_enabled(GooeyEngine* engine, bool enabled);
+bool gooey_engine_get_sequencer_triggers_enabled(const GooeyEngine* engine);
 
 /* ---- voice strips (:5036-5210) and manual triggers (:2518-2552; latched, fire at frame 0 of the next render) ---- */
 void gooey_engine_set_instrument_gain(GooeyEngine* engine, uint32_t instrument, float gain);

@@ -239,6 +239,10 @@ void gooey_engine_sequencer_set_instrument_pattern(GooeyEngine* e, uint32_t inst
 void gooey_engine_sequencer_start(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.start(); }
 void gooey_engine_sequencer_stop(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.stop(); }
 void gooey_engine_sequencer_reset(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.reset(); }
+// ffi.rs:2188-2215: with the triggers disabled the sequencers keep ticking (clock, step position) but fire nothing and export no
+// MIDI event; host triggers (trigger_instrument*) still sound.  The render path reads the flag per call (engine.cuh).
+void gooey_engine_set_sequencer_triggers_enabled(GooeyEngine* e, bool enabled) { if (e) e->seq_triggers_enabled = enabled; }
+bool gooey_engine_get_sequencer_triggers_enabled(const GooeyEngine* e) { return e ? e->seq_triggers_enabled : true; }     // null: the safe default of ffi.rs:2209-2211
 
 void gooey_engine_set_instrument_gain(GooeyEngine* e, uint32_t i, float g) { if (e && i < 5) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_CH_GAIN + i, gd::clampf(g, 0.0f, 1.0f))); }
 void gooey_engine_set_instrument_pan(GooeyEngine* e, uint32_t i, float p) { if (e && i < 5) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_CH_PAN + i, gd::clampf(p, 0.0f, 1.0f))); }

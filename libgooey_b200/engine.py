@@ -22,6 +22,7 @@ _SIGS = {
     "sequencer_set_instrument_step_with_velocity": [c.c_uint32, c.c_uint32, c.c_bool, c.c_float],
     "sequencer_set_instrument_step_note": [c.c_uint32, c.c_uint32, c.c_uint8],
     "sequencer_start": [], "sequencer_stop": [], "sequencer_reset": [],
+    "set_sequencer_triggers_enabled": [c.c_bool],
     "set_channel_instrument_type": [c.c_uint32, c.c_uint32], "set_compressor_sidechain": [c.c_uint32],
     "trigger_instrument": [c.c_uint32],
     "set_instrument_gain": [c.c_uint32, c.c_float], "set_instrument_pan": [c.c_uint32, c.c_float],
@@ -169,6 +170,11 @@ class Engine:
         f = getattr(self._L, self._prefix + "mixer_get_track_peak")
         f.argtypes = [c.c_void_p, c.c_uint32]; f.restype = c.c_float
         return float(f(self._h, track))
+
+    def get_sequencer_triggers_enabled(self):
+        f = getattr(self._L, self._prefix + "get_sequencer_triggers_enabled")
+        f.argtypes = [c.c_void_p]; f.restype = c.c_bool
+        return bool(f(self._h))
 
     def drain_midi_events(self, max_events=64):
         """gooey_engine_drain_midi_events: [(instrument_index, velocity, sample_offset)] of the last render call."""

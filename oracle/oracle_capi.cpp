@@ -251,6 +251,8 @@ void orc_engine_sequencer_set_instrument_pattern(void* e, uint32_t inst, const b
 void orc_engine_sequencer_start(void* e) { if (e) for (auto& v : E->voices) v.seq.start(); }
 void orc_engine_sequencer_stop(void* e) { if (e) for (auto& v : E->voices) v.seq.stop(); }
 void orc_engine_sequencer_reset(void* e) { if (e) for (auto& v : E->voices) v.seq.reset(); }
+void orc_engine_set_sequencer_triggers_enabled(void* e, bool on) { if (e) E->seq_triggers_enabled = on; }   // ffi.rs:2188-2198
+bool orc_engine_get_sequencer_triggers_enabled(void* e) { return e ? E->seq_triggers_enabled : true; }    // ffi.rs:2205-2215
 void orc_engine_set_global_effect_param(void* e, uint32_t fx, uint32_t p, float v) {
   if (!e) return;
   switch (fx) { case 1: E->delay.set_param(p, v); break; case 4: E->tilt.set_param(p, v); break; case 6: E->reverb.set_param(p, v); break;
