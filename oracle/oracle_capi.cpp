@@ -406,4 +406,60 @@ void orc_rust_engine_clear_global_effects(void* e) { R->limiter_on = false; }
 void orc_rust_engine_bounce_samples(void* e, uint32_t n, float* out) { auto v = R->bounce_samples(n); memcpy(out, v.data(), n * sizeof(float)); }
 #undef R
 
+// ---- stand-alone effects (tests/test_reference_units_cpu.py restates the reference's inline unit tests of src/effects/*.rs on these) ----
+// kind = FFI effect id (ffi.rs:1548-1575); ctor[] = the effect's constructor arguments after the sample rate, in the reference's order:
+//   0 low-pass (cutoff, res) · 1 delay (timing, bpm, feedback, mix, cutoff) · 2 saturation (drive, warmth, mix) ·
+//   3 compressor (threshold, ratio, attack, release, mix) · 4 tilt () · 6 spring (decay, mix, damping) · 7 waveshaper (drive, mix) ·
+//   8 feedback waveshaper (drive, feedback, cutoff, mix) · 9 plate (decay, mix, damping)
+struct FxBox { uint32_t kind; std::unique_ptr<StereoEffect> fx; std::unique_ptr<Waveshaper> ws; std::unique_ptr<FeedbackWaveshaper> fb; };
+void* orc_fx_new(uint32_t kind, float sr, const float* c) {
+  auto b = std::make_unique<FxBox>();
+  b->kind = kind;
+  switch (kind) {
+    case 0: b->fx.reset(new LowpassFilterEffect(sr, c[0], c[1])); break;
+    case 1: b->fx.reset(new DelayEffect(sr, (uint32_t)c[0], c[1], c[2], c[3], c[4])); break;
+    case 2: b->fx.reset(new TubeSaturation(sr, c[0], c[1], c[2])); break;
+    case 3: b->fx.reset(new TubeCompressor(sr, c[0], c[1], c[2], c[3], c[4])); break;
+    case 4: b->fx.reset(new TiltFilterEffect(sr)); break;
+    case 6: b->fx.reset(new SpringReverbEffect(sr, c[0], c[1], c[2])); break;
+    case 7: b->ws.reset(new Waveshaper(c[0], c[1])); break;
+    case 8: b->fb.reset(new FeedbackWaveshaper(sr, c[0], c[1], c[2], c[3])); break;
+    case 9: b->fx.reset(new PlateReverbEffect(sr, c[0], c[1], c[2])); break;
+    default: return nullptr;
+  }
+  return b.release();
+}
+void orc_fx_free(void* h) { delete (FxBox*)h; }
+void orc_fx_set_param(void* h, uint32_t p, float v) {
+  FxBox* b = (FxBox*)h;
+  if (b->fx) b->fx->set_param(p, v);
+  else if (b->ws) { if (p == 0) b->ws->set_drive(v); else if (p == 1) b->ws->set_mix(v); }
+  else if (b->fb) { if (p == 0) b->fb->set_drive(v); else if (p == 1) b->fb->set_feedback(v); else if (p == 2) b->fb->set_filter_cutoff(v); else if (p == 3) b->fb->set_mix(v); }
+}
+void orc_fx_set_bpm(void* h, float bpm) { FxBox* b = (FxBox*)h; if (b->fx) b->fx->set_bpm(bpm); }
+void orc_fx_reset(void* h) {
+  FxBox* b = (FxBox*)h;
+  if (b->ws) { b->ws->reset(); return; }
+  if (b->fb) { b->fb->reset(); return; }
+  switch (b->kind) {
+    case 0: static_cast<LowpassFilterEffect*>(b->fx.get())->reset(); break;
+    case 1: static_cast<DelayEffect*>(b->fx.get())->reset(); break;
+    case 2: static_cast<TubeSaturation*>(b->fx.get())->reset(); break;
+    case 3: static_cast<TubeCompressor*>(b->fx.get())->reset(); break;
+    case 4: static_cast<TiltFilterEffect*>(b->fx.get())->reset(); break;
+    case 6: static_cast<SpringReverbEffect*>(b->fx.get())->reset(); break;
+    case 9: static_cast<PlateReverbEffect*>(b->fx.get())->reset(); break;
+  }
+}
+void orc_fx_process(void* h, const float* in, float* out, uint32_t n) {     // the mono `process` of the effect
+  FxBox* b = (FxBox*)h;
+  for (uint32_t i = 0; i < n; i++) out[i] = b->fx ? b->fx->process(in[i]) : (b->ws ? b->ws->process(in[i]) : b->fb->process(in[i]));
+}
+void orc_fx_process_stereo(void* h, const float* l, const float* r, float* ol, float* orr, uint32_t n) {
+  FxBox* b = (FxBox*)h;
+  if (!b->fx) return;
+  for (uint32_t i = 0; i < n; i++) { StereoFrame f; f.l = l[i]; f.r = r[i]; f = b->fx->process_stereo(f); ol[i] = f.l; orr[i] = f.r; }
+}
+float orc_limiter(float threshold, float x) { SoftLimiter lim(1.0f); lim.set_threshold(threshold); return lim.process(x); }
+
 }  // extern "C"

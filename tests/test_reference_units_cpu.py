@@ -1,0 +1,383 @@
+"""The reference's inline unit tests of src/effects/*.rs (`#[cfg(test)] mod tests`), restated against the oracle's effect classes
+(oracle/effects.hpp, oracle/prims.hpp) through `orc_fx_*`: each test cites the Rust test it follows and asserts what it asserts.
+Getter-only tests (parameter clamping read back through `get_*`) and the oversampling-mode setters (no FFI for them on this path)
+are left out.  f32 inputs are formed the way the Rust tests form them (`(i as f32 * 0.1).sin()` -> numpy float32 arithmetic)."""
+import ctypes as c
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+LOWPASS, DELAY, SATURATION, COMPRESSOR, TILT, LIMITER, SPRING, WAVESHAPER, FBWS, PLATE = range(10)
+SR = 44100.0
+f32 = np.float32
+
+
+class Fx:
+    def __init__(self, kind, *ctor, sr=SR):
+        L = O.lib()
+        L.orc_fx_new.restype = c.c_void_p
+        L.orc_fx_new.argtypes = [c.c_uint32, c.c_float, c.c_void_p]
+        for name, args in [("orc_fx_free", [c.c_void_p]), ("orc_fx_set_param", [c.c_void_p, c.c_uint32, c.c_float]), ("orc_fx_set_bpm", [c.c_void_p, c.c_float]),
+                           ("orc_fx_reset", [c.c_void_p]), ("orc_fx_process", [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32]),
+                           ("orc_fx_process_stereo", [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32])]:
+            getattr(L, name).argtypes = args
+            getattr(L, name).restype = None
+        self.L = L
+        arr = np.array(list(ctor) + [0.0], np.float32)
+        self.h = L.orc_fx_new(kind, c.c_float(sr), arr.ctypes.data)
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_fx_free(self.h)
+            self.h = None
+
+    def set(self, p, v):
+        self.L.orc_fx_set_param(self.h, p, c.c_float(v))
+
+    def set_bpm(self, bpm):
+        self.L.orc_fx_set_bpm(self.h, c.c_float(bpm))
+
+    def reset(self):
+        self.L.orc_fx_reset(self.h)
+
+    def run(self, x):
+        x = np.ascontiguousarray(np.atleast_1d(x), np.float32)
+        out = np.empty_like(x)
+        self.L.orc_fx_process(self.h, x.ctypes.data, out.ctypes.data, x.size)
+        return out
+
+    def one(self, x):
+        return float(self.run([x])[0])
+
+    def stereo(self, l, r):
+        l = np.ascontiguousarray(l, np.float32); r = np.ascontiguousarray(r, np.float32)
+        ol, orr = np.empty_like(l), np.empty_like(r)
+        self.L.orc_fx_process_stereo(self.h, l.ctypes.data, r.ctypes.data, ol.ctypes.data, orr.ctypes.data, l.size)
+        return ol, orr
+
+
+def sin_i(n, k, amp=1.0):
+    """(i as f32 * k).sin() * amp, in f32"""
+    return (np.sin((np.arange(n, dtype=np.float32) * f32(k)).astype(np.float32)).astype(np.float32) * f32(amp)).astype(np.float32)
+
+
+def tone(n, freq, sr=SR, amp=1.0):
+    i = np.arange(n, dtype=np.float32)
+    return (np.sin((f32(2.0) * f32(np.pi) * f32(freq) * i / f32(sr)).astype(np.float32)).astype(np.float32) * f32(amp)).astype(np.float32)
+
+
+def impulse(n, width=100, level=1.0):
+    x = np.zeros(n, np.float32)
+    x[:width] = level
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ effects/saturation.rs
+def test_saturation_bypass_when_mix_zero():                      # saturation.rs test_bypass_when_mix_zero
+    sat = Fx(SATURATION, 0.5, 0.5, 0.0)
+    assert sat.one(0.5) == 0.5 and sat.one(-0.3) == f32(-0.3)
+
+
+def test_saturation_soft_limiting():                             # test_soft_limiting
+    out = Fx(SATURATION, 1.0, 0.0, 1.0).run(tone(4000, 1000.0))
+    peak = float(np.abs(out[2000:]).max())
+    assert 0.1 < peak < 1.0
+
+
+def test_saturation_dc_stability_and_nan_protection():           # test_dc_stability, test_nan_protection
+    assert np.isfinite(Fx(SATURATION, 0.5, 1.0, 1.0).run(np.full(44100, 0.5, np.float32))).all()
+    assert Fx(SATURATION, 0.5, 0.5, 0.5).one(float("nan")) == 0.0
+
+
+def test_saturation_reset_matches_fresh_instance():              # test_reset_matches_fresh_instance, test_nan_protection_resets_state
+    reset = Fx(SATURATION, 0.5, 0.5, 1.0)
+    reset.run(sin_i(1000, 0.1))
+    reset.reset()
+    x = sin_i(100, 0.27)
+    assert np.array_equal(reset.run(x), Fx(SATURATION, 0.5, 0.5, 1.0).run(x))
+    nan_reset = Fx(SATURATION, 0.5, 0.5, 1.0)
+    nan_reset.run(sin_i(1000, 0.1))
+    assert nan_reset.one(float("nan")) == 0.0
+    assert nan_reset.one(0.5) == Fx(SATURATION, 0.5, 0.5, 1.0).one(0.5)
+
+
+# ------------------------------------------------------------------------------------------------ effects/lowpass_filter.rs
+def test_lowpass_basic_nan_and_stability():                      # test_filter_basic_processing, _nan_protection, _stability_at_high_resonance
+    assert np.isfinite(Fx(LOWPASS, 1000.0, 0.0).run(np.ones(1000, np.float32))).all()
+    assert np.isfinite(Fx(LOWPASS, 1000.0, 0.5).one(float("nan")))
+    out = Fx(LOWPASS, 500.0, 0.95).run(impulse(44100))
+    assert np.isfinite(out).all() and float(np.abs(out).max()) < 100.0
+
+
+def test_lowpass_high_frequency_stability():                     # test_filter_high_frequency_stability
+    out = Fx(LOWPASS, 20000.0, 0.95).run(sin_i(44100, 0.1, 0.5))
+    assert np.isfinite(out).all() and float(np.abs(out).max()) < 10.0
+
+
+def test_lowpass_parameter_changes_and_full_sweep_stay_stable():  # test_filter_control_thread_safety, test_filter_sweep_full_range
+    f = Fx(LOWPASS, 1000.0, 0.5)
+    for i in range(1000):
+        f.set(0, 200.0 + i * 10.0)
+        f.set(1, i / 2000.0)
+        assert np.isfinite(f.one(1.0))
+    f = Fx(LOWPASS, 20.0, 0.7)
+    x = sin_i(44100, 0.05)
+    for i in range(0, 44100, 49):                                # the sweep in 900 steps (one setter call per 49 samples)
+        f.set(0, 20.0 * 1000.0 ** (i / 44100.0))
+        out = f.run(x[i:i + 49])
+        assert np.isfinite(out).all() and float(np.abs(out).max()) < 10.0
+
+
+# ------------------------------------------------------------------------------------------------ effects/tilt_filter.rs
+def test_tilt_passthrough_at_center():                           # test_passthrough_at_center
+    f = Fx(TILT)
+    f.run(np.zeros(4410, np.float32))
+    assert abs(f.one(0.7) - 0.7) < 0.001
+
+
+def test_tilt_lowpass_attenuates_high_freq():                    # test_lowpass_attenuates_high_freq
+    f = Fx(TILT)
+    f.set(0, 0.0)
+    f.run(np.zeros(4410, np.float32))
+    i = np.arange(4410, dtype=np.float32)
+    x = np.sin((f32(2.0) * f32(np.pi) * f32(10000.0) * (i / f32(44100.0))).astype(np.float32)).astype(np.float32)
+    assert float(np.abs(f.run(x)).max()) < 0.1
+
+
+def test_tilt_highpass_attenuates_low_freq():                    # test_highpass_attenuates_low_freq
+    f = Fx(TILT)
+    f.set(0, 1.0)
+    f.run(np.zeros(4410, np.float32))
+    i = np.arange(4410, dtype=np.float32)
+    x = np.sin((f32(2.0) * f32(np.pi) * f32(100.0) * (i / f32(44100.0))).astype(np.float32)).astype(np.float32)
+    assert float(np.abs(f.run(x)).max()) < 0.1
+
+
+def test_tilt_nan_sweep_and_high_resonance_stability():          # test_nan_protection, test_stability_full_sweep, test_stability_high_resonance
+    f = Fx(TILT)
+    f.set(0, 0.0)
+    f.run(np.full(1000, 0.5, np.float32))
+    assert np.isfinite(f.one(float("nan")))
+    f = Fx(TILT)
+    x = sin_i(44100, 0.05)
+    for i in range(0, 44100, 49):
+        f.set(0, i / 44100.0); f.set(1, 0.8)
+        out = f.run(x[i:i + 49])
+        assert np.isfinite(out).all() and float(np.abs(out).max()) < 10.0
+    f = Fx(TILT)
+    f.set(0, 0.1); f.set(1, 1.0)
+    out = f.run(impulse(44100))
+    assert np.isfinite(out).all() and float(np.abs(out).max()) < 100.0
+
+
+# ------------------------------------------------------------------------------------------------ effects/compressor.rs
+def test_compressor_bypass_when_mix_zero():                      # test_bypass_when_mix_zero
+    comp = Fx(COMPRESSOR, -12.0, 4.0, 5.0, 100.0, 0.0)
+    assert comp.one(0.5) == 0.5 and comp.one(-0.3) == f32(-0.3)
+
+
+def test_compressor_gain_reduction_above_threshold():            # test_gain_reduction_above_threshold
+    comp = Fx(COMPRESSOR, -20.0, 10.0, 0.1, 50.0, 1.0)
+    comp.run(np.tile(np.array([0.8, -0.8], np.float32), 4000))
+    out = abs(comp.one(0.8))
+    assert 0.01 < out < 0.8
+
+
+def test_compressor_no_reduction_below_threshold():              # test_no_reduction_below_threshold
+    comp = Fx(COMPRESSOR, -1.0, 4.0, 5.0, 100.0, 1.0)
+    comp.run(np.zeros(2000, np.float32))
+    assert abs(comp.one(0.01) - 0.01) < 0.05
+
+
+def test_compressor_nan_dc_and_reset():                          # test_nan_protection, test_dc_stability, test_compressor_oversampling_reset_matches_fresh
+    assert Fx(COMPRESSOR, -12.0, 4.0, 5.0, 100.0, 0.5).one(float("nan")) == 0.0
+    assert np.isfinite(Fx(COMPRESSOR, -12.0, 4.0, 5.0, 100.0, 1.0).run(np.full(44100, 0.5, np.float32))).all()
+    reset = Fx(COMPRESSOR, -20.0, 10.0, 0.1, 50.0, 1.0)
+    reset.run(sin_i(2000, 0.3, 0.9))
+    reset.reset()
+    x = sin_i(100, 0.27, 0.9)
+    assert np.array_equal(reset.run(x), Fx(COMPRESSOR, -20.0, 10.0, 0.1, 50.0, 1.0).run(x))
+
+
+# ------------------------------------------------------------------------------------------------ effects/delay.rs
+EIGHTH, QUARTER = 3, 2
+
+
+def test_delay_basic_processing_and_nan():                       # test_delay_basic_processing, test_delay_nan_protection
+    assert np.isfinite(Fx(DELAY, EIGHTH, 120.0, 0.5, 0.5, 10000.0).run(np.ones(1000, np.float32))).all()
+    assert np.isfinite(Fx(DELAY, EIGHTH, 120.0, 0.5, 0.5, 10000.0).one(float("nan")))
+
+
+def test_delay_feedback_stability():                             # test_delay_feedback_stability
+    out = Fx(DELAY, EIGHTH, 120.0, 0.95, 0.5, 5000.0).run(impulse(44100))
+    assert np.isfinite(out).all() and float(np.abs(out).max()) < 100.0
+
+
+def test_delay_filter_darkens_echoes():                          # test_delay_filter_darkens_echoes
+    d = Fx(DELAY, EIGHTH, 120.0, 0.9, 1.0, 2000.0)
+    d.one(1.0)
+    ds = int(f32(0.25) * f32(44100.0))
+    out = np.abs(d.run(np.zeros(ds * 3 - 1, np.float32)))       # out[k] is iteration i = k + 1
+    first = float(out[ds - 3:ds + 2].max())
+    second = float(out[2 * ds - 3:2 * ds + 2].max())
+    assert first > 0.01 and second < first
+
+
+def test_delay_reset_and_bpm_change():                           # test_delay_reset, test_delay_bpm_change_updates_time
+    d = Fx(DELAY, QUARTER, 120.0, 0.5, 0.5, 10000.0)
+    d.run(np.ones(44100, np.float32))
+    d.reset()
+    assert abs(d.one(0.0)) < 0.001
+    d = Fx(DELAY, QUARTER, 120.0, 0.0, 1.0, 20000.0)
+    d.set_bpm(60.0)
+    assert np.isfinite(d.run(np.zeros(100, np.float32))).all()
+
+
+# ------------------------------------------------------------------------------------------------ effects/plate_reverb.rs
+def plate_ir(p, frames):
+    x = np.zeros(frames, np.float32); x[0] = 1.0
+    return p.stereo(x, x)
+
+
+def test_plate_stable_at_max_decay():                            # stable_at_max_decay
+    n = int(SR * 5.0)
+    l, r = plate_ir(Fx(PLATE, 1.0, 1.0, 0.0), n)
+    assert np.isfinite(l).all() and np.isfinite(r).all()
+    assert float(np.abs(l).max()) < 4.0 and float(np.abs(r).max()) < 4.0
+    one = int(SR)
+    first = max(float(np.abs(l[:one]).max()), float(np.abs(r[:one]).max()))
+    last = max(float(np.abs(l[n - one:]).max()), float(np.abs(r[n - one:]).max()))
+    assert last <= first * 1.5
+
+
+def test_plate_decay_time_is_sane():                             # decay_time_is_sane
+    l, r = plate_ir(Fx(PLATE, 0.5, 1.0, 0.0), int(SR * 5.0))
+    w = int(SR * 0.1)
+    rms = [float(np.sqrt(((l[k:k + w].astype(np.float64) ** 2) + (r[k:k + w].astype(np.float64) ** 2)).sum() / (2.0 * len(l[k:k + w])))) for k in range(0, len(l), w)]
+    th = max(rms) * 0.001
+    t60 = next((i * 0.1 for i, v in enumerate(rms) if v < th), None)
+    assert t60 is not None and 0.3 <= t60 <= 4.0
+    for a, b in zip(rms[2:], rms[3:]):
+        assert b <= a * 1.2
+
+
+def test_plate_decorrelates_and_zero_width_collapses_to_mono():  # decorrelates_left_and_right, zero_width_collapses_to_mono
+    l, r = plate_ir(Fx(PLATE, 0.7, 1.0, 0.3), int(SR))
+    assert float(np.abs(l - r).max()) > 1e-3
+    p = Fx(PLATE, 0.7, 1.0, 0.3)
+    p.set(4, 0.0)                                                # PLATE_PARAM_WIDTH
+    x = np.zeros(13230 + 22050, np.float32)
+    x[:13230][np.arange(13230) % 1000 == 0] = 1.0
+    x[13230:][np.arange(22050) % 1000 == 0] = 1.0
+    l, r = p.stereo(x, x)
+    assert float(np.abs(l[13230:] - r[13230:]).max()) < 1e-6
+
+
+def test_plate_nan_reset_and_common_sample_rates():              # nan_input_produces_finite_output, reset_clears_state, constructs_and_runs_at_common_sample_rates
+    p = Fx(PLATE, 0.8, 1.0, 0.2)
+    l, r = p.stereo(np.full(1000, np.nan, np.float32), np.full(1000, np.inf, np.float32))
+    assert np.isfinite(l).all() and np.isfinite(r).all()
+    l, r = p.stereo(np.array([0.5], np.float32), np.array([0.5], np.float32))
+    assert np.isfinite(l).all() and np.isfinite(r).all()
+    p = Fx(PLATE, 0.9, 1.0, 0.0)
+    plate_ir(p, 8192)
+    p.reset()
+    l, r = p.stereo(np.zeros(8192, np.float32), np.zeros(8192, np.float32))
+    assert not l.any() and not r.any()
+    for sr in (22050.0, 44100.0, 48000.0, 96000.0):
+        p = Fx(PLATE, 1.0, 1.0, 0.0, sr=sr)
+        p.set(5, 1.0)                                            # PLATE_PARAM_SIZE: max tank scale exercises buffer headroom
+        l, r = plate_ir(p, 4096)
+        assert np.isfinite(l).all() and np.isfinite(r).all()
+
+
+# ------------------------------------------------------------------------------------------------ effects/waveshaper.rs
+def test_waveshaper_bypasses():                                  # test_bypass_when_mix_zero, test_bypass_when_drive_one, test_zero_input
+    for ws in (Fx(WAVESHAPER, 5.0, 0.0), Fx(WAVESHAPER, 1.0, 1.0)):
+        assert ws.one(0.5) == 0.5 and ws.one(-0.3) == f32(-0.3)
+    ws = Fx(WAVESHAPER, 5.0, 1.0)
+    ws.run(np.zeros(20, np.float32))
+    assert ws.one(0.0) == 0.0
+
+
+def test_waveshaper_soft_clipping_and_gain_compensation():       # test_soft_clipping, test_gain_compensation_consistency
+    ws = Fx(WAVESHAPER, 10.0, 1.0)
+    ws.run(np.ones(20, np.float32))
+    assert 0.3 < ws.one(1.0) < 0.8
+    lo, hi = Fx(WAVESHAPER, 2.0, 1.0), Fx(WAVESHAPER, 10.0, 1.0)
+    lo.run(np.full(100, 0.5, np.float32)); hi.run(np.full(100, 0.5, np.float32))
+    assert lo.one(0.5) > 0.1 and hi.one(0.5) > 0.1
+
+
+def test_waveshaper_reset_matches_fresh_instance():              # test_reset_matches_fresh_instance, test_nan_protection_resets_state
+    reset = Fx(WAVESHAPER, 5.0, 1.0)
+    reset.run(sin_i(1000, 0.1))
+    reset.reset()
+    x = sin_i(100, 0.27)
+    assert np.array_equal(reset.run(x), Fx(WAVESHAPER, 5.0, 1.0).run(x))
+    nan_reset = Fx(WAVESHAPER, 5.0, 1.0)
+    nan_reset.run(sin_i(1000, 0.1))
+    assert nan_reset.one(float("nan")) == 0.0
+    assert nan_reset.one(0.5) == Fx(WAVESHAPER, 5.0, 1.0).one(0.5)
+
+
+# ------------------------------------------------------------------------------------------------ effects/feedback_waveshaper.rs
+def test_fbws_bypasses_and_zero_input():                         # test_bypass_when_mix_zero, test_bypass_when_drive_one, test_zero_input
+    for ws in (Fx(FBWS, 5.0, 0.5, 2000.0, 0.0), Fx(FBWS, 1.0, 0.5, 2000.0, 1.0)):
+        assert ws.one(0.5) == 0.5 and ws.one(-0.3) == f32(-0.3)
+    assert Fx(FBWS, 5.0, 0.5, 2000.0, 1.0).one(0.0) == 0.0
+
+
+def test_fbws_soft_clipping():                                   # test_soft_clipping
+    full = float(np.abs(Fx(FBWS, 10.0, 0.0, 2000.0, 1.0).run(sin_i(2000, 0.3))).max())
+    quiet = float(np.abs(Fx(FBWS, 10.0, 0.0, 2000.0, 1.0).run(sin_i(2000, 0.3, 0.1))).max())
+    assert 0.5 < full < 1.1 and quiet < full
+
+
+def test_fbws_feedback_changes_output_and_stays_bounded():       # test_feedback_changes_output, test_feedback_does_not_blow_up, test_extreme_settings_stability
+    x = sin_i(1000, 0.1, 0.5)
+    assert float(np.abs(Fx(FBWS, 5.0, 0.7, 2000.0, 1.0).run(x) - Fx(FBWS, 5.0, 0.0, 2000.0, 1.0).run(x)).max()) > 0.01
+    sq = np.where(np.arange(44100) % 100 < 50, 0.8, -0.8).astype(np.float32)
+    for ws in (Fx(FBWS, 10.0, 0.9, 2000.0, 1.0), Fx(FBWS, 100.0, 0.98, 2000.0, 1.0)):
+        out = ws.run(sq)
+        assert np.isfinite(out).all() and float(np.abs(out).max()) < 5.0
+
+
+def test_fbws_dc_decays_nan_and_reset():                         # test_dc_stability, test_nan_protection, test_reset_clears_state
+    ws = Fx(FBWS, 5.0, 0.8, 1000.0, 1.0)
+    ws.run(np.full(44100, 0.3, np.float32))
+    assert abs(float(ws.run(np.zeros(4410, np.float32))[-1])) < 0.01
+    ws = Fx(FBWS, 5.0, 0.5, 2000.0, 1.0)
+    ws.one(0.5); ws.one(0.3)
+    assert ws.one(float("nan")) == 0.0 and np.isfinite(ws.one(0.5))
+    ws = Fx(FBWS, 5.0, 0.8, 2000.0, 1.0)
+    ws.run(np.full(1000, 0.5, np.float32))
+    ws.reset()
+    assert ws.one(0.5) == Fx(FBWS, 5.0, 0.8, 2000.0, 1.0).one(0.5)
+
+
+def test_fbws_feedback_gain_compensation_and_transient():        # test_feedback_gain_compensation, test_transient_not_compressed_below_tail
+    x = sin_i(4000, 0.1, 0.5)
+    no_fb = Fx(FBWS, 5.0, 0.0, 2000.0, 1.0).run(x).astype(np.float64)
+    fb = Fx(FBWS, 100.0, 0.98, 2000.0, 1.0).run(x).astype(np.float64)
+    ratio = float(np.sqrt((fb ** 2).mean() / (no_fb ** 2).mean()))
+    assert 1.0 < ratio < 5.0
+    n = int(0.2 * SR); aw = int(0.005 * SR)
+    i = np.arange(n, dtype=np.float32)
+    amp = ((f32(1.0) - i / f32(n)) * f32(0.9) + f32(0.1)).astype(np.float32)
+    out = np.abs(Fx(FBWS, 10.0, 0.0, 2000.0, 1.0).run((np.sin((i * f32(0.2)).astype(np.float32)).astype(np.float32) * amp).astype(np.float32)))
+    assert float(out[:aw].max()) > float(out[n - aw + 1:].max())
+
+
+# ------------------------------------------------------------------------------------------------ effects/limiter.rs
+def test_limiter_is_a_scaled_tanh():                             # limiter.rs:24-41 (process), as tests/ffi_gain_staging.rs uses it
+    L = O.lib()
+    L.orc_limiter.restype = c.c_float
+    L.orc_limiter.argtypes = [c.c_float, c.c_float]
+    for th in (1.0, 0.7, 0.25):
+        for x in (-2.0, -0.3, 0.0, 0.1, 0.9, 5.0):
+            want = f32(np.tanh(f32(f32(x) * f32(f32(1.0) / f32(th))))) * f32(th)
+            assert abs(L.orc_limiter(th, x) - float(want)) < 1e-6
