@@ -460,6 +460,28 @@ void orc_fx_process_stereo(void* h, const float* l, const float* r, float* ol, f
   if (!b->fx) return;
   for (uint32_t i = 0; i < n; i++) { StereoFrame f; f.l = l[i]; f.r = r[i]; f = b->fx->process_stereo(f); ol[i] = f.l; orr[i] = f.r; }
 }
+// ---- stand-alone filters and generators (the reference's inline unit tests of src/filters/*.rs and src/gen/*.rs) ----
+// kind: 0 Chamberlin SVF (mode = type 0 lp / 1 bp / 2 hp), 1 TPT SVF (mode), 2 resonant low-pass, 3 band-pass biquad (a = freq, b = q, c = gain),
+// 4 high-pass biquad (a = freq, b = q), 5 membrane resonator (a = gain scale, <= 0: default)
+void orc_filter_run(uint32_t kind, float sr, float a, float b, float c, uint32_t mode, const float* in, float* out, uint32_t n) {
+  switch (kind) {
+    case 0: { StateVariableFilter f(sr, a, b); for (uint32_t i = 0; i < n; i++) out[i] = f.process_mode(in[i], (uint8_t)mode); } break;
+    case 1: { StateVariableFilterTpt f(sr, a, b); for (uint32_t i = 0; i < n; i++) out[i] = f.process_mode(in[i], (uint8_t)mode); } break;
+    case 2: { ResonantLowpassFilter f(sr, a, b); for (uint32_t i = 0; i < n; i++) out[i] = f.process(in[i]); } break;
+    case 3: { BiquadBandpass f(sr); f.set_params(a, b, c); for (uint32_t i = 0; i < n; i++) out[i] = f.process(in[i]); } break;
+    case 4: { BiquadHighpass f(sr); f.set_params(a, b); for (uint32_t i = 0; i < n; i++) out[i] = f.process(in[i]); } break;
+    case 5: { MembraneResonator f(sr); if (a > 0.0f) f.set_gain_scale(a); for (uint32_t i = 0; i < n; i++) out[i] = f.process(in[i]); } break;
+    default: for (uint32_t i = 0; i < n; i++) out[i] = 0.0f;
+  }
+}
+void orc_polyblep(int square, double inc, float* out, uint32_t n) {   // gen/polyblep.rs tests: phase += inc; phase -= floor(phase)
+  double phase = 0.0;
+  for (uint32_t i = 0; i < n; i++) { out[i] = square ? polyblep_square(phase, inc) : polyblep_saw(phase, inc); phase += inc; phase -= floor(phase); }
+}
+void orc_morph_osc(float sr, float freq, float morph, float color, float tone, float* out, uint32_t n) {
+  MorphOsc o(sr);
+  for (uint32_t i = 0; i < n; i++) out[i] = o.tick(freq, morph, color, tone);
+}
 float orc_limiter(float threshold, float x) { SoftLimiter lim(1.0f); lim.set_threshold(threshold); return lim.process(x); }
 
 }  // extern "C"

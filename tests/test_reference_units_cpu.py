@@ -381,3 +381,84 @@ def test_limiter_is_a_scaled_tanh():                             # limiter.rs:24
         for x in (-2.0, -0.3, 0.0, 0.1, 0.9, 5.0):
             want = f32(np.tanh(f32(f32(x) * f32(f32(1.0) / f32(th))))) * f32(th)
             assert abs(L.orc_limiter(th, x) - float(want)) < 1e-6
+
+
+# ================================================================================================ src/filters/*.rs, src/gen/*.rs
+def filt(kind, x, a, b=0.0, cc=0.0, mode=0, sr=SR):
+    L = O.lib()
+    L.orc_filter_run.argtypes = [c.c_uint32, c.c_float, c.c_float, c.c_float, c.c_float, c.c_uint32, c.c_void_p, c.c_void_p, c.c_uint32]
+    L.orc_filter_run.restype = None
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    L.orc_filter_run(kind, sr, a, b, cc, mode, x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
+def test_svf_bandpass_settles_on_dc_and_all_outputs_respond():   # state_variable.rs test_svf_bandpass_output, test_svf_all_outputs
+    assert abs(float(filt(0, np.ones(1000, np.float32), 1000.0, 2.0, mode=1)[-1])) < 0.1
+    first = [float(filt(0, np.ones(1, np.float32), 1000.0, 1.0, mode=m)[0]) for m in (0, 1, 2)]
+    assert any(v != 0.0 for v in first)
+
+
+def rlp_rms(sr, cutoff, q, freq):                                # resonant_lowpass.rs response_rms
+    n = int(sr)
+    out = filt(2, tone(n, freq, sr), cutoff, q, sr=sr).astype(np.float64)
+    return float(np.sqrt((out[n // 2:] ** 2).sum() / (n // 2)))
+
+
+def test_resonant_lowpass_response():                            # lowpass_attenuates_frequencies_above_cutoff, resonance_boosts_response_near_cutoff
+    assert rlp_rms(48000.0, 1000.0, 0.707, 100.0) > rlp_rms(48000.0, 1000.0, 0.707, 8000.0) * 10.0
+    assert rlp_rms(48000.0, 1000.0, 4.0, 1000.0) > rlp_rms(48000.0, 1000.0, 0.5, 1000.0) * 4.0
+
+
+def test_resonant_lowpass_stable_at_extreme_settings_and_sample_rates():   # remains_stable_at_extreme_settings_and_sample_rates
+    for sr in (44100.0, 48000.0, 96000.0):
+        x = sin_i(int(sr), 0.1)
+        for cutoff in (20.0, 1000.0, 20000.0):
+            for res in (0.5, 5.0, 10.0):
+                out = filt(2, x, cutoff, res, sr=sr)
+                assert np.isfinite(out).all() and float(np.abs(out).max()) < 100.0, (sr, cutoff, res)
+
+
+def test_biquads_attenuate_dc():                                 # biquad_bandpass.rs test_bandpass_attenuates_dc, biquad_highpass.rs test_highpass_attenuates_dc
+    assert abs(float(filt(3, np.ones(1000, np.float32), 1000.0, 1.0, 1.0)[-1])) < 0.1
+    assert abs(float(filt(4, np.ones(2000, np.float32), 1000.0, 1.0)[-1])) < 0.1
+
+
+def test_membrane_keeps_ringing_after_excitation():              # membrane_resonator.rs test_membrane_ringing
+    x = np.zeros(101, np.float32); x[0] = 1.0
+    assert float(np.abs(filt(5, x, 0.01)[1:]).max()) > 0.0001
+
+
+def polyblep(square, n=44100, inc=100.0 / 44100.0):
+    L = O.lib()
+    L.orc_polyblep.argtypes = [c.c_int, c.c_double, c.c_void_p, c.c_uint32]
+    L.orc_polyblep.restype = None
+    out = np.empty(n, np.float32)
+    L.orc_polyblep(int(square), inc, out.ctypes.data, n)
+    return out
+
+
+@pytest.mark.parametrize("square", [False, True])
+def test_polyblep_range_and_energy(square):                      # polyblep.rs test_polyblep_{saw,square}_range, _not_silent
+    out = polyblep(square, inc=float(np.float32(100.0) / np.float32(44100.0)))
+    assert float(out.min()) >= -1.1 and float(out.max()) <= 1.1
+    assert float((out.astype(np.float64) ** 2).sum()) > 1.0
+
+
+def morph(morph_v, color, tone_v, n):
+    L = O.lib()
+    L.orc_morph_osc.argtypes = [c.c_float, c.c_float, c.c_float, c.c_float, c.c_float, c.c_void_p, c.c_uint32]
+    L.orc_morph_osc.restype = None
+    out = np.empty(n, np.float32)
+    L.orc_morph_osc(SR, 440.0, morph_v, color, tone_v, out.ctypes.data, n)
+    return out
+
+
+def test_morph_osc_channels_and_range():                         # morph_osc.rs test_morph_osc_output_range, test_channel{1,2,3}_has_output, gated sine, colour
+    out = morph(0.0, 60.0, 50.0, 1000)
+    assert np.isfinite(out).all() and float(np.abs(out).max()) < 2.0
+    for m in (-1.0, 0.0, 1.0):
+        assert float(np.abs(morph(m, 60.0, 50.0, 100)).sum()) > 0.1
+    assert float(np.abs(morph(1.0, 60.0, 99.0, 100)).sum()) > 0.1        # gate closed: the noise is still there
+    assert float(np.abs(morph(1.0, 20.0, 50.0, 1000)).sum()) > 1.0 and float(np.abs(morph(1.0, 100.0, 50.0, 1000)).sum()) > 1.0
