@@ -462,3 +462,116 @@ def test_morph_osc_channels_and_range():                         # morph_osc.rs 
         assert float(np.abs(morph(m, 60.0, 50.0, 100)).sum()) > 0.1
     assert float(np.abs(morph(1.0, 60.0, 99.0, 100)).sum()) > 0.1        # gate closed: the noise is still there
     assert float(np.abs(morph(1.0, 20.0, 50.0, 1000)).sum()) > 1.0 and float(np.abs(morph(1.0, 100.0, 50.0, 1000)).sum()) > 1.0
+
+
+# ================================================================================================ src/instruments/{bass,poly_synth,granulator}.rs
+BASS_DEFAULT = [0.24, 0.40, 0.80, 0.00, 0.00, 0.10, 0.15, 0.70, 0.85, 0.15, 0.08, 0.35, 0.10, 0.30, 0.80]      # BassConfig::default() == acid (bass.rs:188-208)
+BASS_PRESETS = {"acid": BASS_DEFAULT,
+                "sub": [0.18, 1.00, 0.15, 0.00, 0.00, 0.00, 0.70, 0.05, 0.10, 0.30, 0.20, 0.60, 0.15, 0.00, 0.85],
+                "reese": [0.18, 0.30, 0.80, 0.80, 0.50, 0.05, 0.35, 0.30, 0.50, 0.40, 0.15, 0.55, 0.12, 0.60, 0.80],
+                "stab": [0.30, 0.20, 0.90, 0.00, 0.00, 0.90, 0.20, 0.40, 0.90, 0.08, 0.05, 0.20, 0.08, 0.20, 0.80]}
+
+
+def bass_render(params, frames):
+    return O.render_voices([(4, 0, list(params))], frames, triggers=[(0, 0, 1.0)])[0]
+
+
+def test_bass_synth_produces_audio_and_presets_differ():         # bass.rs test_bass_synth_produces_audio, test_bass_presets_produce_different_sounds
+    assert float((bass_render(BASS_DEFAULT, 44100).astype(np.float64) ** 2).sum()) > 0.1
+    outs = {k: bass_render(v, 22050) for k, v in BASS_PRESETS.items()}
+    for k, o in outs.items():
+        assert float((o.astype(np.float64) ** 2).sum()) > 0.01, k
+    assert not np.array_equal(outs["acid"], outs["sub"])
+
+
+def test_bass_synth_deactivates():                               # bass.rs test_bass_synth_deactivates: amp_decay 0.01, two seconds
+    p = list(BASS_DEFAULT); p[11] = 0.01
+    out = bass_render(p, 88200)
+    assert float(np.abs(out[:2000]).max()) > 0.01 and not out[-22050:].any()      # an inactive voice returns exactly 0 (bass.rs:800-803)
+
+
+@pytest.fixture
+def eng():
+    made = []
+
+    def make():
+        e = O.oracle_engine()
+        e.set_master_gain(1.0)                                   # instrument-level thresholds; the centre pan leaves cos(pi/4) of the level
+        e.render(16384)
+        made.append(e)
+        return e
+    yield make
+    for e in made:
+        e.close()
+
+
+def test_poly_synth_produces_audio_and_releases(eng):            # poly_synth.rs test_poly_synth_produces_audio, test_poly_synth_release
+    e = eng()
+    e.poly_trigger_notes([60])
+    buf = e.render(4410)[:, 0].astype(np.float64)
+    assert float((buf ** 2).sum()) > 0.1 * 0.5                   # the reference's 0.1 at unity, through the centre pan (x 0.5 in energy)
+    e.poly_release()
+    tail = e.render(441000)
+    assert not tail[-44100:].any()
+
+
+def test_poly_synth_voice_stealing_keeps_six_voices_sounding(eng):   # poly_synth.rs test_poly_synth_six_voices, _voice_stealing
+    six, seven = eng(), eng()
+    six.poly_trigger_notes(list(range(60, 66)))
+    seven.poly_trigger_notes(list(range(60, 66)))
+    seven.poly_trigger_notes([66])
+    a, b = six.render(4410), seven.render(4410)
+    assert np.isfinite(b).all() and float(np.abs(b).max()) > 0.01 and not np.array_equal(a, b)
+    assert float(np.abs(b).max()) < 2.0 * float(np.abs(a).max())    # the seventh note replaced a voice, it did not add one
+
+
+def gran_buffer(n=4410):                                         # granulator.rs test_buffer
+    i = np.arange(n, dtype=np.float32)
+    return (np.sin(((i / f32(44100.0)) * f32(440.0) * f32(2 * np.pi)).astype(np.float32)).astype(np.float32) * f32(0.5)).astype(np.float32)
+
+
+def gran(eng, seed, params, velocity=1.0, buffer=None):
+    e = eng()
+    assert e.granulator_set_buffer(gran_buffer() if buffer is None else buffer, 44100.0)
+    e.granulator_set_seed(seed)
+    for p, v in params:
+        e.granulator_set_param(p, v)
+    e.granulator_snap_params()
+    e.granulator_trigger(velocity)
+    return e
+
+
+G_GRAIN_LENGTH, G_DENSITY, G_CLOUD, G_VOLUME, G_RAND_TIMING, G_RAND_AMP, G_DRIVE = 1, 4, 7, 8, 9, 10, 11
+
+
+def test_triggered_granulator_produces_finite_audio_and_same_seed_same_output(eng):   # granulator.rs triggered_granulator_produces_finite_audio, same_seed_produces_same_output
+    out = gran(eng, 7, []).render(44100)
+    assert np.isfinite(out).all() and float(np.abs(out).max()) > 0.001 * 0.7
+    a, b = gran(eng, 99, [], 0.8).render(4096), gran(eng, 99, [], 0.8).render(4096)
+    assert np.array_equal(a, b)
+
+
+def test_dense_cloud_with_random_amp_remains_finite(eng):        # dense_cloud_with_random_amp_remains_finite
+    out = gran(eng, 13, [(G_DENSITY, 1.0), (G_RAND_AMP, 1.0), (G_RAND_TIMING, 1.0), (G_CLOUD, 1.0)]).render(88200)
+    assert np.isfinite(out).all() and float(np.abs(out).max()) > 0.001 * 0.7
+
+
+def test_random_timing_preserves_average_density(eng):           # random_timing_preserves_average_density
+    out = gran(eng, 101, [(G_DENSITY, 0.5), (G_GRAIN_LENGTH, 0.0), (G_RAND_TIMING, 1.0), (G_CLOUD, 1.0)]).render(88200)[:, 0]
+    assert np.isfinite(out).all()
+    audible_blocks = sum(float(np.abs(out[b * 4410:(b + 1) * 4410]).max()) > 1e-4 * 0.7 for b in range(20))
+    assert audible_blocks >= 12
+
+
+def test_soft_grain_stealing_does_not_run_away(eng):             # soft_grain_stealing_does_not_click
+    out = gran(eng, 31, [(G_DENSITY, 1.0), (G_GRAIN_LENGTH, 1.0), (G_CLOUD, 1.0)]).render(88200)
+    assert np.isfinite(out).all() and float(np.abs(out).max()) < 4.0
+
+
+def test_drive_is_roughly_gain_neutral(eng):                     # drive_is_roughly_gain_neutral
+    def peak(drive):
+        out = gran(eng, 17, [(G_DENSITY, 0.4), (G_CLOUD, 0.6), (G_VOLUME, 1.0), (G_DRIVE, drive)]).render(44100)
+        assert np.isfinite(out).all()
+        return float(np.abs(out).max())
+    dry, wet = peak(0.0), peak(1.0)
+    assert wet <= dry * 1.25 and wet < 4.0
