@@ -482,6 +482,43 @@ void orc_morph_osc(float sr, float freq, float morph, float color, float tone, f
   MorphOsc o(sr);
   for (uint32_t i = 0; i < n; i++) out[i] = o.tick(freq, morph, color, tone);
 }
+// ---- SmoothedParam, StereoFrame and MixerGraph micro-operations (inline unit tests of utils/smoother.rs, frame.rs, mixer/graph.rs) ----
+// ops: a script of (code, value): 0 set_target, 1 set_immediate, 2 snap, 3 set_normalized, 4 set_bipolar, 5 tick x (int)value.
+// out = {current, target, settled}
+void orc_smoother_script(float init, float mn, float mx, float sr, float ms, const uint32_t* codes, const float* values, uint32_t n, float* out3) {
+  SmoothedParam p(init, mn, mx, sr, ms);
+  for (uint32_t i = 0; i < n; i++) {
+    switch (codes[i]) {
+      case 0: p.set_target(values[i]); break;
+      case 1: p.set_immediate(values[i]); break;
+      case 2: p.snap(); break;
+      case 3: p.set_normalized(values[i]); break;
+      case 4: p.set_bipolar(values[i]); break;
+      case 5: for (int k = 0; k < (int)values[i]; k++) p.tick(); break;
+    }
+  }
+  out3[0] = p.get(); out3[1] = p.target; out3[2] = p.is_settled() ? 1.0f : 0.0f;
+}
+void orc_frame_panned(float x, float pan, float* lr) { StereoFrame f = StereoFrame::panned(x, pan); lr[0] = f.l; lr[1] = f.r; }
+float orc_frame_downmix(float l, float r) { StereoFrame f; f.l = l; f.r = r; return f.downmix(); }
+// One-track graph fed by the drum-kit source: gain / pan / mute / solo of track 0 (and an optional second track that is soloed),
+// strips snapped, one frame scattered and mixed down; out = {l, r, peak after, peak after second read}
+void orc_graph_one_frame(float gain, float pan, int mute, int second_track_solo, float in_l, float in_r, float* out4) {
+  MixerGraph g(44100.0f, 120.0f);
+  size_t t = g.add_track();
+  g.route(0, t);
+  g.tracks[t].gain.set_target(gain);
+  g.tracks[t].pan.set_target(pan);
+  g.tracks[t].muted = mute != 0;
+  if (second_track_solo) { size_t s2 = g.add_track(); g.tracks[s2].soloed = true; }
+  g.snap_strip_params();
+  g.clear_scratch();
+  StereoFrame f; f.l = in_l; f.r = in_r;
+  g.scatter(0, f);
+  StereoFrame o = g.mix_down();
+  out4[0] = o.l; out4[1] = o.r;
+  out4[2] = g.tracks[t].peak; g.tracks[t].peak = 0.0f; out4[3] = g.tracks[t].peak;
+}
 float orc_limiter(float threshold, float x) { SoftLimiter lim(1.0f); lim.set_threshold(threshold); return lim.process(x); }
 
 }  // extern "C"

@@ -575,3 +575,75 @@ def test_drive_is_roughly_gain_neutral(eng):                     # drive_is_roug
         return float(np.abs(out).max())
     dry, wet = peak(0.0), peak(1.0)
     assert wet <= dry * 1.25 and wet < 4.0
+
+
+# ================================================================================================ utils/smoother.rs, frame.rs, mixer/graph.rs
+def smoother(init, mn, mx, ops, sr=44100.0, ms=10.0):
+    L = O.lib()
+    L.orc_smoother_script.argtypes = [c.c_float] * 5 + [c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p]
+    L.orc_smoother_script.restype = None
+    codes = np.array([o[0] for o in ops], np.uint32)
+    vals = np.array([o[1] for o in ops], np.float32)
+    out = np.zeros(3, np.float32)
+    L.orc_smoother_script(init, mn, mx, sr, ms, codes.ctypes.data, vals.ctypes.data, len(ops), out.ctypes.data)
+    return float(out[0]), float(out[1]), bool(out[2])
+
+
+SET_TARGET, SET_IMMEDIATE, SNAP, SET_NORMALIZED, SET_BIPOLAR, TICK = range(6)
+
+
+def test_smoother_unit_tests():                                  # smoother.rs test_smoother_reaches_target ... test_snap
+    cur, _, settled = smoother(0.0, 0.0, 1.0, [(SET_TARGET, 1.0), (TICK, 4410)])
+    assert abs(cur - 1.0) < 0.001 and settled
+    assert smoother(0.0, 0.0, 1.0, [(SET_IMMEDIATE, 1.0)]) == (1.0, 1.0, True)
+    assert smoother(50.0, 20.0, 200.0, [(SET_TARGET, 300.0)])[1] == 200.0
+    assert smoother(50.0, 20.0, 200.0, [(SET_TARGET, 10.0)])[1] == 20.0
+    for n, want in [(0.5, 50.0), (0.0, 0.0), (1.0, 100.0)]:
+        assert smoother(50.0, 0.0, 100.0, [(SET_NORMALIZED, n)])[1] == want
+    for b, want in [(0.0, 50.0), (-1.0, 0.0), (1.0, 100.0)]:
+        assert smoother(50.0, 0.0, 100.0, [(SET_BIPOLAR, b)])[1] == want
+    assert smoother(0.0, 0.0, 1.0, [(SET_TARGET, 0.75)]) == (0.0, 0.75, False)
+    assert smoother(0.0, 0.0, 1.0, [(SET_TARGET, 0.75), (SNAP, 0.0)]) == (0.75, 0.75, True)
+
+
+def panned(x, pan):
+    L = O.lib()
+    L.orc_frame_panned.argtypes = [c.c_float, c.c_float, c.c_void_p]
+    L.orc_frame_panned.restype = None
+    out = np.zeros(2, np.float32)
+    L.orc_frame_panned(x, pan, out.ctypes.data)
+    return float(out[0]), float(out[1])
+
+
+def test_stereo_frame_unit_tests():                              # frame.rs tests
+    L = O.lib()
+    L.orc_frame_downmix.argtypes = [c.c_float, c.c_float]
+    L.orc_frame_downmix.restype = c.c_float
+    assert L.orc_frame_downmix(-0.3, -0.3) == float(f32(-0.3))   # downmix_of_a_mono_frame_is_the_original_sample
+    assert L.orc_frame_downmix(1.0, 0.0) == 0.5                  # downmix_averages_the_two_channels
+    l, r = panned(0.8, 0.0)
+    assert abs(l - 0.8) < 1e-6 and abs(r) < 1e-6                 # panned_hard_left_silences_right
+    l, r = panned(0.8, 1.0)
+    assert abs(l) < 1e-6 and abs(r - 0.8) < 1e-6                 # panned_hard_right_silences_left
+    l, r = panned(1.0, 0.5)
+    assert abs(l - r) < 1e-6 and abs(l - 2 ** -0.5) < 1e-6       # panned_center_is_equal_and_minus_three_db
+    for pan in (0.0, 0.25, 0.5, 0.75, 1.0):                      # panned_preserves_power_across_sweep
+        l, r = panned(0.6, pan)
+        assert abs(l * l + r * r - 0.36) < 1e-5
+    assert panned(0.5, -1.0) == panned(0.5, 0.0) and panned(0.5, 2.0) == panned(0.5, 1.0)   # panned_clamps_out_of_range
+
+
+def graph_frame(gain=1.0, pan=0.5, mute=False, second_solo=False, l=1.0, r=1.0):
+    L = O.lib()
+    L.orc_graph_one_frame.argtypes = [c.c_float, c.c_float, c.c_int, c.c_int, c.c_float, c.c_float, c.c_void_p]
+    L.orc_graph_one_frame.restype = None
+    out = np.zeros(4, np.float32)
+    L.orc_graph_one_frame(gain, pan, int(mute), int(second_solo), l, r, out.ctypes.data)
+    return [float(v) for v in out]
+
+
+def test_mixer_graph_unit_tests():                               # graph.rs mix_down_records_and_resets_track_peak, snap_strip_params_applies_current_targets_immediately
+    assert graph_frame(l=0.25, r=-0.5) == [0.25, -0.5, 0.5, 0.0]
+    assert graph_frame(gain=0.5, pan=0.0)[:2] == [0.5, 0.0]
+    assert graph_frame(mute=True)[:2] == [0.0, 0.0]
+    assert graph_frame(second_solo=True)[:2] == [0.0, 0.0]
