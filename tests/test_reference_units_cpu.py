@@ -647,3 +647,30 @@ def test_mixer_graph_unit_tests():                               # graph.rs mix_
     assert graph_frame(gain=0.5, pan=0.0)[:2] == [0.5, 0.0]
     assert graph_frame(mute=True)[:2] == [0.0, 0.0]
     assert graph_frame(second_solo=True)[:2] == [0.0, 0.0]
+
+
+# ================================================================================================ engine/sequencer.rs (swing), on the oracle AND on the product's host sequencer
+def trigger_frames(swing, frames=6 * 88200):
+    """Every step enabled at 120 BPM; the oracle's trigger table and the product's host-side schedule (csrc/engine.cuh HostSeq through
+    gooey_b200_sequencer_schedule — no GPU involved) must agree bit for bit (tests/test_host_cpu.py); both are returned."""
+    o = O.oracle_engine()
+    o.set_bpm(120.0)
+    o.set_swing(swing)
+    for s in range(16):
+        o.sequencer_set_instrument_step(0, s, True)
+    fr, _ = O.trigger_table(o, 0, frames)
+    o.close()
+    from test_host_cpu import schedule
+    got, _ = schedule(120.0, swing, [1] * 16, [1.0] * 16, frames)
+    assert np.array_equal(got, fr)
+    return fr.astype(np.int64)
+
+
+def test_swing_delays_the_off_beats_and_preserves_the_tempo():   # sequencer.rs test_swing_timing_affects_triggers, test_swing_preserves_average_tempo
+    straight, swung = trigger_frames(0.5), trigger_frames(0.75)
+    k = 64                                                       # bar 5: the swing smoother (FFI set_swing glides, sequencer.rs:909) has settled
+    straight_gap = straight[k + 1] - straight[k]
+    assert swung[k + 1] - swung[k] > straight_gap                # the swung off-beat is late
+    assert swung[k + 2] - swung[k + 1] < straight_gap            # and the step after it is short
+    assert abs((swung[k + 2] - swung[k]) - (straight[k + 2] - straight[k])) <= 2
+    assert abs((swung[k + 4] - swung[k]) - (straight[k + 4] - straight[k])) <= 4
