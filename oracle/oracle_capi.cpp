@@ -519,6 +519,14 @@ void orc_graph_one_frame(float gain, float pan, int mute, int second_track_solo,
   out4[0] = o.l; out4[1] = o.r;
   out4[2] = g.tracks[t].peak; g.tracks[t].peak = 0.0f; out4[3] = g.tracks[t].peak;
 }
+// tests/aliasing.rs render_oversampled_naive_square: a naive square generated INSIDE the oversampler's callback at the oversampled rate
+void orc_oversample_square(int mode, double sub_dt, float* out, uint32_t n) {
+  Oversampler os;
+  os.set_mode(mode == 0 ? OversamplingMode::Off : (mode == 2 ? OversamplingMode::X2 : OversamplingMode::X4));
+  double phase = 0.0;
+  for (uint32_t i = 0; i < n; i++)
+    out[i] = os.process(0.0f, [&](float) { float v = phase < 0.5 ? 1.0f : -1.0f; phase = phase + sub_dt; phase -= floor(phase); return v; });
+}
 float orc_limiter(float threshold, float x) { SoftLimiter lim(1.0f); lim.set_threshold(threshold); return lim.process(x); }
 
 }  // extern "C"

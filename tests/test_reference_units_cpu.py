@@ -674,3 +674,102 @@ def test_swing_delays_the_off_beats_and_preserves_the_tempo():   # sequencer.rs 
     assert swung[k + 2] - swung[k + 1] < straight_gap            # and the step after it is short
     assert abs((swung[k + 2] - swung[k]) - (straight[k + 2] - straight[k])) <= 2
     assert abs((swung[k + 4] - swung[k]) - (straight[k + 4] - straight[k])) <= 4
+
+
+# ================================================================================================ tests/effect_distortion_balance.rs
+DB_SR, DB_N, DB_WARM, DB_BIN, DB_AMP = 48000.0, 8192, 8192, 37, 0.5
+
+
+def db_input(total):
+    fund = float(f32(DB_BIN) * f32(DB_SR) / f32(DB_N))                                     # fundamental_hz() in f32
+    i = np.arange(total, dtype=np.float64)
+    return (np.sin(2 * np.pi * fund * i / DB_SR).astype(np.float32) * f32(DB_AMP)).astype(np.float32)
+
+
+def db_dry():
+    i = np.arange(DB_WARM, DB_WARM + DB_N, dtype=np.float64)
+    return (np.sin(2 * np.pi * DB_BIN * i / DB_N).astype(np.float32) * f32(DB_AMP)).astype(np.float32)
+
+
+def rms(x):
+    return float(np.sqrt((x.astype(np.float64) ** 2).mean()))
+
+
+def bin_power(x, b):
+    ph = 2 * np.pi * b / len(x) * np.arange(len(x))
+    re, im = float((x.astype(np.float64) * np.cos(ph)).sum()), float(-(x.astype(np.float64) * np.sin(ph)).sum())
+    return re * re + im * im
+
+
+def harmonic_distortion(x):
+    fund = max(bin_power(x, DB_BIN), 1e-30)
+    return float(np.sqrt(sum(bin_power(x, DB_BIN * h) for h in range(2, 11) if DB_BIN * h < DB_N // 2) / fund))
+
+
+def gain_db(p, dry):
+    return 20.0 * np.log10(rms(p) / max(rms(dry), 1e-30))
+
+
+def test_max_feedback_matches_saturation_gain_and_distortion():   # effect_distortion_balance.rs:90-112
+    x, dry = db_input(DB_WARM + DB_N), db_dry()
+    sat = Fx(SATURATION, 1.0, 0.5, 1.0, sr=DB_SR).run(x)[DB_WARM:]
+    fb = Fx(FBWS, 100.0, 0.98, 2000.0, 1.0, sr=DB_SR).run(x)[DB_WARM:]
+    assert abs(gain_db(fb, dry) - gain_db(sat, dry)) <= 1.5
+    assert harmonic_distortion(fb) >= harmonic_distortion(sat) * 0.9
+
+
+def test_mid_feedback_stays_near_mid_saturation_gain():          # effect_distortion_balance.rs:114-128
+    x, dry = db_input(DB_WARM + DB_N), db_dry()
+    sat = Fx(SATURATION, 0.5, 0.4, 1.0, sr=DB_SR).run(x)[DB_WARM:]
+    fb = Fx(FBWS, 50.0, 0.49, 2000.0, 1.0, sr=DB_SR).run(x)[DB_WARM:]
+    assert abs(gain_db(fb, dry) - gain_db(sat, dry)) <= 3.0
+
+
+# ================================================================================================ tests/aliasing.rs
+AL_SR, AL_N, AL_J = 48000.0, 8192, 367
+
+
+def al_dt():
+    return float(f32(AL_J) * f32(AL_SR) / f32(AL_N)) / AL_SR     # fundamental_hz() as f64 / SAMPLE_RATE as f64
+
+
+def alias_to_signal(x, bins):                                    # aliasing.rs:46-57
+    x = x.astype(np.float64)
+    n = len(x)
+    total_positive = (n * float((x ** 2).sum()) - float(x.sum()) ** 2) / 2.0
+    signal = sum(bin_power(x, k) for k in bins)
+    return max(total_positive - signal, 0.0) / max(signal, 1e-30)
+
+
+def signal_bins(square):
+    return [m * AL_J for m in range(1, AL_N) if m * AL_J <= AL_N // 2 and (not square or m % 2 == 1)]
+
+
+def naive_wave(square):
+    dt, phase, out = al_dt(), 0.0, np.empty(AL_N, np.float32)
+    for i in range(AL_N):
+        out[i] = (1.0 if phase < 0.5 else -1.0) if square else f32(2.0 * phase - 1.0)
+        phase = (phase + dt) % 1.0
+    return out
+
+
+@pytest.mark.parametrize("square", [False, True])
+def test_polyblep_suppresses_aliasing(square):                   # polyblep_saw_suppresses_aliasing, polyblep_square_suppresses_aliasing
+    bins = signal_bins(square)
+    naive = alias_to_signal(naive_wave(square), bins)
+    clean = alias_to_signal(polyblep(square, AL_N, al_dt()), bins)
+    assert naive > 0.02 and clean < naive * 0.25 and clean < 0.01
+
+
+def test_oversampling_reduces_naive_square_aliasing():           # oversampling_reduces_naive_square_aliasing (the reconstructed half-band)
+    L = O.lib()
+    L.orc_oversample_square.argtypes = [c.c_int, c.c_double, c.c_void_p, c.c_uint32]
+    L.orc_oversample_square.restype = None
+
+    def render(mode, factor):
+        out = np.empty(4096 + AL_N, np.float32)
+        L.orc_oversample_square(mode, al_dt() / factor, out.ctypes.data, out.size)
+        return out[4096:]
+    bins = signal_bins(True)
+    off, x4 = alias_to_signal(render(0, 1), bins), alias_to_signal(render(4, 4), bins)
+    assert off > 0.02 and x4 < off * 0.5
