@@ -527,6 +527,21 @@ void orc_oversample_square(int mode, double sub_dt, float* out, uint32_t n) {
   for (uint32_t i = 0; i < n; i++)
     out[i] = os.process(0.0f, [&](float) { float v = phase < 0.5 ? 1.0f : -1.0f; phase = phase + sub_dt; phase -= floor(phase); return v; });
 }
+// max_curve.rs test_envelope_basic: two-segment MaxCurveEnvelope sampled at the given times after trigger(0)
+void orc_maxcurve_envelope(const float* seg6, const double* times, float* out, uint32_t n) {
+  MaxCurveEnvelope env({{seg6[0], seg6[1], seg6[2]}, {seg6[3], seg6[4], seg6[5]}});
+  env.trigger(0.0);
+  for (uint32_t i = 0; i < n; i++) out[i] = env.get_value(times[i]);
+}
+// utils/blendable.rs tests: a two-field config blended bilinearly over four corners (ChannelBlender::blend with n = 2, no discrete field)
+void orc_blend2(const float* corners8, float x, float y, float* out2) {
+  ChannelBlender b;
+  b.type = 0; b.n = 2;
+  for (int c = 0; c < 4; c++) { b.corner[c][0] = corners8[2 * c]; b.corner[c][1] = corners8[2 * c + 1]; }
+  float o[24];
+  b.blend(x, y, o);
+  out2[0] = o[0]; out2[1] = o[1];
+}
 float orc_limiter(float threshold, float x) { SoftLimiter lim(1.0f); lim.set_threshold(threshold); return lim.process(x); }
 
 }  // extern "C"

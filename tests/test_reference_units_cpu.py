@@ -773,3 +773,42 @@ def test_oversampling_reduces_naive_square_aliasing():           # oversampling_
     bins = signal_bins(True)
     off, x4 = alias_to_signal(render(0, 1), bins), alias_to_signal(render(4, 4), bins)
     assert off > 0.02 and x4 < off * 0.5
+
+
+# ================================================================================================ max_curve.rs, utils/blendable.rs
+def test_max_curve_unit_tests():                                 # max_curve.rs test_max_curve_linear ... test_envelope_basic
+    L = O.lib()
+    mc = lambda p, cv: L.orc_max_curve(float(p), float(cv))
+    for p in (0.0, 0.5, 1.0):
+        assert abs(mc(p, 0.0) - p) < 0.001
+    for cv in (-0.9, -0.5, 0.0, 0.5, 0.9):
+        assert abs(mc(0.0, cv)) < 0.001 and abs(mc(1.0, cv) - 1.0) < 0.001
+    assert mc(0.5, -0.83) > 0.5 and mc(0.5, 0.83) < 0.5
+    L.orc_maxcurve_envelope.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32]
+    L.orc_maxcurve_envelope.restype = None
+    seg = np.array([1.0, 10.0, 0.0, 0.0, 100.0, 0.0], np.float32)       # (target, ms, curve) x 2
+    times = np.array([0.0, 0.005, 0.01, 0.06], np.float64)
+    out = np.zeros(4, np.float32)
+    L.orc_maxcurve_envelope(seg.ctypes.data, times.ctypes.data, out.ctypes.data, 4)
+    assert abs(out[0]) < 0.01 and abs(out[1] - 0.5) < 0.1 and abs(out[2] - 1.0) < 0.1 and abs(out[3] - 0.5) < 0.1
+
+
+def blend2(corners, x, y):
+    L = O.lib()
+    L.orc_blend2.argtypes = [c.c_void_p, c.c_float, c.c_float, c.c_void_p]
+    L.orc_blend2.restype = None
+    cs = np.array(corners, np.float32).reshape(8)
+    out = np.zeros(2, np.float32)
+    L.orc_blend2(cs.ctypes.data, x, y, out.ctypes.data)
+    return float(out[0]), float(out[1])
+
+
+def test_preset_blender_unit_tests():                            # blendable.rs test_lerp_* (through the x axis), test_blend_at_corners ... test_uniform_blender
+    ab = [(0.0, 10.0), (1.0, 20.0), (0.0, 10.0), (1.0, 20.0)]            # bottom: a -> b, top the same: blend(x, .) == a.lerp(b, x)
+    assert blend2(ab, 0.0, 0.0) == (0.0, 10.0) and blend2(ab, 1.0, 0.0) == (1.0, 20.0) and blend2(ab, 0.5, 0.0) == (0.5, 15.0)
+    sq = [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0), (1.0, 1.0)]                # bottom_left, bottom_right, top_left, top_right
+    assert blend2(sq, 0.0, 0.0) == (0.0, 0.0) and blend2(sq, 1.0, 0.0) == (1.0, 0.0)
+    assert blend2(sq, 0.0, 1.0) == (0.0, 1.0) and blend2(sq, 1.0, 1.0) == (1.0, 1.0)
+    assert blend2(sq, 0.5, 0.5) == (0.5, 0.5)
+    assert blend2(sq, -0.5, 1.5) == (0.0, 1.0)
+    assert blend2([(0.5, 0.75)] * 4, 0.3, 0.7) == (0.5, 0.75)
