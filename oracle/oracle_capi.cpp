@@ -542,6 +542,44 @@ void orc_blend2(const float* corners8, float x, float y, float* out2) {
   b.blend(x, y, o);
   out2[0] = o[0]; out2[1] = o[1];
 }
+// ---- bare PolySynth / Granulator renders (tests/test_emu_cpu.py: the product's poly_tick / gran_tick host builds must match bit for bit) ----
+// events sorted by frame; kind 0 = trigger_note(a = midi note, b = velocity), 1 = release_all, 2 = set_param(a = id, b = value).  The clock is the
+// engine's: t += 1/sr by repeated addition; an event at frame j is applied before tick j (trigger_note reads current_time = the previous tick's time).
+void orc_poly_render(uint32_t preset, float sr, uint32_t n_ev, const uint32_t* ev_frame, const uint32_t* ev_kind, const float* ev_a, const float* ev_b,
+                     uint32_t frames, float* out) {
+  PolySynth syn(sr, PolyConfig::preset(preset));
+  double t = 0.0; const double dt = 1.0 / (double)sr;
+  uint32_t e = 0;
+  for (uint32_t j = 0; j < frames; j++) {
+    while (e < n_ev && ev_frame[e] <= j) {
+      if (ev_kind[e] == 0) syn.trigger_note((uint8_t)ev_a[e], ev_b[e]); else if (ev_kind[e] == 1) syn.release_all(); else syn.set_param((uint32_t)ev_a[e], ev_b[e]);
+      e++;
+    }
+    out[j] = syn.tick(t);
+    t += dt;
+  }
+}
+// kind 0 = trigger(b = velocity), 2 = set_param(a, b), 3 = snap_params, 4 = set_seed(a)
+void orc_gran_render(float sr, const float* buf, uint32_t buf_len, float buf_sr, uint32_t n_ev, const uint32_t* ev_frame, const uint32_t* ev_kind,
+                     const float* ev_a, const float* ev_b, uint32_t frames, float* out) {
+  Granulator g(sr);
+  g.set_buffer(std::make_shared<std::vector<float>>(buf, buf + buf_len), buf_sr);
+  double t = 0.0; const double dt = 1.0 / (double)sr;
+  uint32_t e = 0;
+  for (uint32_t j = 0; j < frames; j++) {
+    while (e < n_ev && ev_frame[e] <= j) {
+      switch (ev_kind[e]) {
+        case 0: g.trigger_with_velocity(t, ev_b[e]); break;
+        case 2: g.set_param((uint32_t)ev_a[e], ev_b[e]); break;
+        case 3: g.snap_params(); break;
+        case 4: g.set_seed((uint32_t)ev_a[e]); break;
+      }
+      e++;
+    }
+    out[j] = g.tick(t);
+    t += dt;
+  }
+}
 float orc_limiter(float threshold, float x) { SoftLimiter lim(1.0f); lim.set_threshold(threshold); return lim.process(x); }
 
 }  // extern "C"

@@ -183,6 +183,64 @@ int emu_render_voices(const GooeyVoicePatch* patches, uint32_t n, float sr, uint
   return 0;
 }
 
+// Bare poly synth / granulator through the device functions of voices2.cuh (what slow_kernel<PolyV> / the granulator's control lane run),
+// same event vocabulary and clock as orc_poly_render / orc_gran_render.
+int emu_poly_render(uint32_t preset, float sr, uint32_t n_ev, const uint32_t* ev_frame, const uint32_t* ev_kind, const float* ev_a, const float* ev_b,
+                    uint32_t frames, float* out) {
+  static const float T[5][14] = {
+      {0.0f, 0.2f, 0.6f, 0.15f, 0.3f, 0.55f, 0.7f, 0.7f, 0.8f, 0.5f, 0.65f, 0.4f, 0.75f, 0.7f},
+      {0.0f, 0.4f, 0.45f, 0.2f, 0.2f, 0.8f, 0.75f, 0.8f, 0.85f, 0.75f, 0.7f, 0.5f, 0.8f, 0.6f},
+      {0.3f, 0.1f, 0.7f, 0.25f, 0.6f, 0.0f, 0.75f, 0.0f, 0.65f, 0.0f, 0.7f, 0.1f, 0.65f, 0.7f},
+      {0.5f, 0.15f, 0.55f, 0.1f, 0.4f, 0.35f, 0.7f, 0.5f, 0.75f, 0.3f, 0.65f, 0.3f, 0.7f, 0.7f},
+      {0.0f, 0.5f, 0.5f, 0.1f, 0.15f, 0.85f, 0.7f, 0.9f, 0.85f, 0.8f, 0.7f, 0.6f, 0.8f, 0.5f}};   // PolySynthConfig presets (poly_synth.rs:49-142), as engine.cuh passes them
+  for (int n = 0; n < 128; n++) g_midi_freq_host[n] = 440.0 * pow(2.0, ((double)n - 69.0) / 12.0);
+  const RateCtx rc = make_rate_ctx(sr);
+  std::vector<double> clock = make_clock(sr, (size_t)frames + 2);
+  const double* tt = clock.data();
+  PolyState s; memset(&s, 0, sizeof s);
+  poly_init(s, T[preset < 5 ? preset : 0], sr);
+  uint32_t e = 0;
+  for (uint32_t j = 0; j < frames; j++) {
+    while (e < n_ev && ev_frame[e] <= j) {
+      VoiceEvent x; memset(&x, 0, sizeof x); x.frame = j;
+      if (ev_kind[e] == 0) { x.kind = EV_POLY_NOTE; x.param = (uint16_t)ev_a[e]; x.value = ev_b[e]; }
+      else if (ev_kind[e] == 1) x.kind = EV_POLY_RELEASE;
+      else { x.kind = EV_SET_TARGET; x.param = (uint16_t)ev_a[e]; x.value = ev_b[e]; }
+      poly_event(s, x, tt);
+      e++;
+    }
+    out[j] = poly_tick(s, tt, rc);
+  }
+  return 0;
+}
+int emu_gran_render(float sr, const float* buf, uint32_t buf_len, float buf_sr, uint32_t n_ev, const uint32_t* ev_frame, const uint32_t* ev_kind,
+                    const float* ev_a, const float* ev_b, uint32_t frames, float* out) {
+  design_halfband8(g_hb_host);
+  const RateCtx rc = make_rate_ctx(sr);
+  std::vector<double> clock = make_clock(sr, (size_t)frames + 2);
+  const double* tt = clock.data();
+  GranState s; memset(&s, 0, sizeof s);
+  gran_init(s, sr);
+  auto ev = [&](uint16_t kind, uint16_t param, float value, uint32_t aux) { VoiceEvent x; memset(&x, 0, sizeof x); x.kind = kind; x.param = param; x.value = value; x.aux = aux; gran_event(s, x, tt); };
+  const uint64_t addr = (uint64_t)(uintptr_t)buf;                       // set_buffer as the engine encodes it: pointer halves + length / rate
+  { float lo; uint32_t lo_bits = (uint32_t)(addr & 0xffffffffu); memcpy(&lo, &lo_bits, 4); ev(EV_GRAN_BUFFER, 0, lo, (uint32_t)(addr >> 32)); }
+  ev(EV_SET_AUX, AUX_GRAN_BUFINFO, buf_sr, buf_len);
+  uint32_t e = 0;
+  for (uint32_t j = 0; j < frames; j++) {
+    while (e < n_ev && ev_frame[e] <= j) {
+      switch (ev_kind[e]) {
+        case 0: ev(EV_TRIGGER, 0, ev_b[e], 0); break;
+        case 2: ev(EV_SET_TARGET, (uint16_t)ev_a[e], ev_b[e], 0); break;
+        case 3: ev(EV_SNAP, 0, 0.0f, 0); break;
+        case 4: ev(EV_GRAN_SEED, 0, 0.0f, (uint32_t)ev_a[e]); break;
+      }
+      e++;
+    }
+    out[j] = gran_tick(s, tt, rc);
+  }
+  return 0;
+}
+
 // The front end's arithmetic shortcuts, evaluated by the host build of the very functions the kernels call (gmath.cuh):
 // kind 0 = g_div_by(a, b, 1 / b) (must equal the IEEE quotient bit for bit), 1 = g_sinf_fast(a), 2 = the additive triangle with
 // FAST = true (osc_triangle<true>(a, b, sr)), 3 = the same with the bit-exact sine.

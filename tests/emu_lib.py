@@ -68,3 +68,35 @@ def math(kind, a, b=None, sample_rate=44100.0):
     rc = lib().emu_math(int(kind), _p(a, f32), _p(b, f32), f32(sample_rate), _p(out, f32), a.size)
     assert rc == 0
     return out
+
+
+def _events(ev):
+    ev = sorted(ev, key=lambda e: e[0])
+    fr = np.array([e[0] for e in ev], np.uint32)
+    kd = np.array([e[1] for e in ev], np.uint32)
+    a = np.array([e[2] for e in ev], np.float32)
+    b = np.array([e[3] for e in ev], np.float32)
+    return fr, kd, a, b
+
+
+def poly_render(fn, preset, events, frames, sample_rate=44100.0):
+    """events: (frame, kind, a, b); kind 0 note-on (a = midi note, b = velocity), 1 release_all, 2 set_param (a = id, b = value).
+    fn = emu lib's emu_poly_render or the oracle's orc_poly_render (same signature)."""
+    fr, kd, a, b = _events(events)
+    out = np.zeros(frames, np.float32)
+    u32, f32 = ctypes.c_uint32, ctypes.c_float
+    fn.restype = None if fn.__name__.startswith("orc_") else ctypes.c_int
+    fn(ctypes.c_uint32(preset), f32(sample_rate), ctypes.c_uint32(len(fr)), _p(fr, u32), _p(kd, u32), _p(a, f32), _p(b, f32), ctypes.c_uint32(frames), _p(out, f32))
+    return out
+
+
+def gran_render(fn, buf, events, frames, sample_rate=44100.0, buf_sr=44100.0):
+    """events: (frame, kind, a, b); kind 0 trigger (b = velocity), 2 set_param, 3 snap_params, 4 set_seed (a)."""
+    fr, kd, a, b = _events(events)
+    buf = np.ascontiguousarray(buf, np.float32)
+    out = np.zeros(frames, np.float32)
+    u32, f32 = ctypes.c_uint32, ctypes.c_float
+    fn.restype = None if fn.__name__.startswith("orc_") else ctypes.c_int
+    fn(f32(sample_rate), _p(buf, f32), ctypes.c_uint32(buf.size), f32(buf_sr), ctypes.c_uint32(len(fr)), _p(fr, u32), _p(kd, u32), _p(a, f32), _p(b, f32),
+       ctypes.c_uint32(frames), _p(out, f32))
+    return out

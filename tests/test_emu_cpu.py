@@ -91,3 +91,29 @@ def test_bass_per_sample_tick_bit_exact():
     got, _ = E.render_voices(patches, 40000, triggers=trig, params=params, mode=0)
     assert np.abs(want).max() > 0.05
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("preset", [0, 1, 2, 3, 4])
+def test_poly_synth_tick_bit_exact(preset):
+    """poly_event / poly_tick (voices2.cuh, what slow_kernel<PolyV> runs) against the oracle's PolySynth, host build: chords, voice stealing
+    (a seventh and eighth note), a parameter glide, release_all and a re-trigger during the release."""
+    ev = [(0, 0, 60, 1.0), (0, 0, 64, 0.8), (0, 0, 67, 0.9), (3000, 0, 72, 0.7), (3000, 0, 76, 0.6), (3000, 0, 79, 0.5), (6000, 0, 84, 1.0), (6001, 0, 48, 0.9),
+          (8000, 2, 2, 0.9), (8000, 2, 0, 0.7), (12000, 1, 0, 0.0), (15000, 0, 55, 1.0), (20000, 2, 13, 0.2)]
+    want = E.poly_render(O.lib().orc_poly_render, preset, ev, 30000)
+    got = E.poly_render(E.lib().emu_poly_render, preset, ev, 30000)
+    assert np.abs(want).max() > 0.01
+    assert np.array_equal(got, want)
+
+
+def test_granulator_tick_bit_exact():
+    """gran_event / gran_tick (voices2.cuh: the per-sample granulator path and the functions gran_wave_kernel's control lane runs) against the
+    oracle's Granulator, host build: dense saturating cloud (slot stealing), random timing / amplitude, spray, reverse direction, glides."""
+    rng = np.random.default_rng(5)
+    n = 3 * 44100
+    buf = (0.5 * np.sin(2 * np.pi * 220.0 * np.arange(n) / 44100.0) * (0.5 + 0.5 * np.sin(2 * np.pi * 0.7 * np.arange(n) / 44100.0)) + 0.1 * rng.uniform(-1, 1, n)).astype(np.float32)
+    ev = [(0, 4, 7, 0.0), (0, 2, 4, 1.0), (0, 2, 1, 0.55), (0, 2, 2, 0.5), (0, 2, 3, 0.62), (0, 2, 6, 0.3), (0, 2, 5, 0.8), (0, 2, 9, 0.3), (0, 2, 10, 0.3), (0, 2, 7, 0.4),
+          (0, 3, 0, 0.0), (0, 0, 0, 0.9), (9000, 2, 3, 0.4), (9000, 2, 11, 0.6), (20000, 2, 6, 0.9), (26000, 0, 0, 0.6)]
+    want = E.gran_render(O.lib().orc_gran_render, buf, ev, 40000)
+    got = E.gran_render(E.lib().emu_gran_render, buf, ev, 40000)
+    assert np.abs(want).max() > 0.01
+    assert np.array_equal(got, want)
