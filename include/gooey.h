@@ -89,6 +89,7 @@ typedef struct GooeyEngine GooeyEngine;
 #define GOOEY_SOURCE_POLYSYNTH 2u
 #define GOOEY_SOURCE_GRANULATOR 3u
 #define GOOEY_SOURCE_LOOPMIXER 4u
+#define GOOEY_SOURCE_SAMPLER_BASE 5u         /* + rack id; routable once the rack is registered (ffi.rs:1872-1873) */
 #define GOOEY_STEP_NOTE_NONE 255u             /* :1980 */
 #define GOOEY_BASS_PRESET_ACID 0u             /* :1882-1998 */
 #define GOOEY_BASS_PRESET_SUB 1u
@@ -280,6 +281,57 @@ void gooey_engine_granulator_set_seed(GooeyEngine* engine, uint32_t seed);
 void gooey_engine_granulator_snap_params(GooeyEngine* engine);
 /* libgooey_b200 addition: dst plays the buffer already loaded into src, without another device copy. */
 bool gooey_b200_granulator_share_buffer(GooeyEngine* dst, const GooeyEngine* src);
+
+/* ---- loop mixer: 4 stereo loop channels summed into graph source GOOEY_SOURCE_LOOPMIXER (ffi.rs:7150-7535; src/mixer/mod.rs,
+ * loop_channel.rs, stereo_buffer.rs).  The host passes decoded PCM (interleaved f32; 1 channel is duplicated, 2+ use channels 0 / 1);
+ * the buffer is copied to the device.  Calls act immediately, like the reference's.  Playback state is not touched by a bounce
+ * (ffi.rs:7840-7854 resets sequencers and snaps strips only).
+ * This build: PitchMode Off and Resample.  gooey_engine_loop_set_pitch_mode(PRESERVE_PITCH), gooey_engine_loop_queue_swap and
+ * gooey_engine_loop_effect_add latch the sticky error (WSOLA, queued swaps, per-channel effect chains and the clip grid are not built). ---- */
+#define GOOEY_LOOP_CHANNEL_COUNT 4u            /* src/mixer/mod.rs:32 */
+#define GOOEY_PITCH_MODE_OFF 0u                /* :7163-7168 */
+#define GOOEY_PITCH_MODE_RESAMPLE 1u
+#define GOOEY_PITCH_MODE_PRESERVE_PITCH 2u
+bool gooey_engine_loop_load(GooeyEngine* engine, uint32_t channel, const float* samples, uint32_t frames, uint32_t channels, float sample_rate);   /* :7184 */
+void gooey_engine_loop_set_playing(GooeyEngine* engine, uint32_t channel, bool playing);            /* :7209 */
+void gooey_engine_loop_set_gain(GooeyEngine* engine, uint32_t channel, float gain);                 /* :7224, 0 .. 2, 15 ms fader */
+void gooey_engine_loop_set_mute(GooeyEngine* engine, uint32_t channel, bool muted);                 /* :7239 */
+void gooey_engine_loop_set_solo(GooeyEngine* engine, uint32_t channel, bool soloed);                /* :7255 */
+void gooey_engine_loop_set_start(GooeyEngine* engine, uint32_t channel, float normalized);          /* :7275; end < start plays the wrap-around region */
+void gooey_engine_loop_set_end(GooeyEngine* engine, uint32_t channel, float normalized);            /* :7295 */
+void gooey_engine_loop_set_speed(GooeyEngine* engine, uint32_t channel, float speed);               /* :7311, -4 .. 4, negative = reverse */
+void gooey_engine_loop_set_source_bpm(GooeyEngine* engine, uint32_t channel, float source_bpm);     /* :7331, <= 0 clears the tag */
+float gooey_engine_loop_get_source_bpm(const GooeyEngine* engine, uint32_t channel);                /* :7352 */
+void gooey_engine_loop_set_pitch_mode(GooeyEngine* engine, uint32_t channel, uint32_t mode);        /* :7368 */
+uint32_t gooey_engine_loop_get_pitch_mode(const GooeyEngine* engine, uint32_t channel);             /* :7389 */
+void gooey_engine_loop_restart(GooeyEngine* engine, uint32_t channel);                              /* :7408 */
+void gooey_engine_loop_set_position(GooeyEngine* engine, uint32_t channel, float normalized);       /* :7422 */
+float gooey_engine_loop_get_position(const GooeyEngine* engine, uint32_t channel);                  /* :7516 */
+bool gooey_engine_loop_queue_swap(GooeyEngine* engine, uint32_t channel, const float* samples, uint32_t frames, uint32_t channels, float sample_rate,
+                                  float source_bpm, uint32_t divisions);                            /* :7449, not built: false + sticky error */
+int32_t gooey_engine_loop_effect_add(GooeyEngine* engine, uint32_t channel, uint32_t effect_id);    /* :7536, not built: -1 + sticky error */
+/* Offline render of one loop channel, ignoring mute / solo, from its loop start (mixer/mod.rs:444-476): a stereo 32-bit float WAV
+ * (:8006-8048), or (libgooey_b200 addition) the same frames interleaved into out_interleaved[2 * frames]. */
+bool gooey_engine_loop_render_to_wav(GooeyEngine* engine, uint32_t channel, uint32_t frame_count, uint32_t preroll_frame_count, const char* utf8_path);
+bool gooey_engine_loop_render(GooeyEngine* engine, uint32_t channel, uint32_t frames, uint32_t preroll, float* out_interleaved);
+
+/* ---- sampler racks: up to 4 racks of 16 PCM pads and 32 voices, graph sources GOOEY_SOURCE_SAMPLER_BASE + rack, unrouted until
+ * gooey_engine_mixer_route_source (ffi.rs:6000-6172; src/instruments/sampler.rs).  Pads are interleaved f32, 1 or 2 channels.
+ * This build: pads are fired with gooey_engine_sampler_trigger; the transport-armed step pattern (gooey_engine_sampler_set_step,
+ * :6173-6290) latches the sticky error. ---- */
+#define GOOEY_SAMPLER_RACK_MAX 4u              /* :585 */
+#define GOOEY_SAMPLER_SLOT_COUNT 16u           /* sampler.rs:14 */
+int32_t gooey_engine_sampler_register(GooeyEngine* engine);                                          /* :6007, rack id or -1 */
+uint32_t gooey_engine_sampler_get_source_id(const GooeyEngine* engine, uint32_t rack);               /* :6031, UINT32_MAX if not registered */
+bool gooey_engine_sampler_set_slot_buffer(GooeyEngine* engine, uint32_t rack, uint32_t slot, const float* samples, uint32_t frames, uint32_t channels,
+                                          float sample_rate);                                        /* :6044 */
+bool gooey_engine_sampler_clear_slot(GooeyEngine* engine, uint32_t rack, uint32_t slot);             /* :6076 */
+bool gooey_engine_sampler_slot_is_loaded(const GooeyEngine* engine, uint32_t rack, uint32_t slot);   /* :6090 */
+uint32_t gooey_engine_sampler_slot_frames(const GooeyEngine* engine, uint32_t rack, uint32_t slot);  /* :6104 */
+uint32_t gooey_engine_sampler_slot_channels(const GooeyEngine* engine, uint32_t rack, uint32_t slot);   /* :6119 */
+float gooey_engine_sampler_slot_sample_rate(const GooeyEngine* engine, uint32_t rack, uint32_t slot);   /* :6134 */
+bool gooey_engine_sampler_trigger(GooeyEngine* engine, uint32_t rack, uint32_t slot, float velocity);   /* :6150 */
+bool gooey_engine_sampler_set_step(GooeyEngine* engine, uint32_t rack, uint32_t step, bool enabled, uint32_t slot, float velocity);   /* :6173, not built: false + sticky error */
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@
 #include "patch.h"
 #include "mix.cuh"
 #include "chain.cuh"
+#include "loops.cuh"
 
 namespace gh {
 
@@ -212,6 +213,10 @@ struct EngineBank {
   DevBuf<gd::LfoStream> d_lfo_streams;    // LFO pool of the current render call
   DevBuf<float> d_lfo_planes;             // [routed streams][frames] LFO values
   std::vector<gd::LfoStream> h_lfo_streams;
+  // sample-playback sources (loops.cuh): per-call descriptors (state read back when the call ends) and the pieces' stereo rows
+  std::vector<gd::LoopMixer> h_loop_descs; DevBuf<gd::LoopMixer> d_loop_descs;
+  std::vector<gd::SamplerRack> h_rack_descs; DevBuf<gd::SamplerRack> d_rack_descs;
+  DevBuf<float> d_ext[2];
   DevBuf<float> d_peaks;                  // [n][N_PEAKS] maxima of the current render call
   DevBuf<unsigned long long> d_chain_units; unsigned long long h_chain_units = 0;   // engine-frames the settled-chain kernel took in the last render
   std::vector<float> h_peaks;
@@ -320,6 +325,31 @@ struct GooeyEngine {
   std::vector<LfoRoute> lfo_routes[8];
   uint32_t lfo_next_route_id[8] = {0};
   bool seq_triggers_enabled = true;
+  // ---- sample-playback sources (loops.cuh) ----
+  // mixer/loop_channel.rs LoopChannel: the buffer lives on the device as two planes (left[len], right[len]); the rest is the
+  // reference's struct, edited directly by the gooey_engine_loop_* setters and advanced by the device during a render.
+  struct LoopHost {
+    std::shared_ptr<gh::DevBuf<float>> buf;
+    uint32_t len = 0; float buf_sr = 0.0f;
+    bool has_source_bpm = false; float source_bpm = 0.0f;
+    double cursor = 0.0;
+    float loop_start = 0.0f, loop_end = 1.0f, speed = 1.0f;
+    bool playing = false, muted = false, soloed = false;
+    uint32_t pitch_mode = 0;
+    gd::LSm gain = {1.0f, 1.0f}, active = {1.0f, 1.0f};
+    gd::LoopWindow window() const { return gd::loop_window(loop_start, loop_end, (double)len); }
+  } loops[gd::LOOP_CHANNELS];
+  float loop_engine_bpm = 120.0f;          // LoopChannel::engine_bpm: written by Mixer::set_bpm only (loop_channel.rs:28, 365-367)
+  // instruments/sampler.rs SamplerRack: 16 slots of interleaved PCM on the device, 32 voices (a voice keeps its buffer alive)
+  struct SamplerHost {
+    bool registered = false;
+    struct Slot { std::shared_ptr<gh::DevBuf<float>> buf; uint32_t frames = 0, channels = 0; float sr = 0.0f; } slots[gd::SAMPLER_SLOTS];
+    gd::SampleVoice voices[gd::SAMPLER_VOICES];
+    std::shared_ptr<gh::DevBuf<float>> voice_buf[gd::SAMPLER_VOICES];
+    void voices_release(int v) { voices[v].samples = nullptr; voice_buf[v].reset(); }
+    unsigned long long next_age = 0;
+    SamplerHost() { memset(voices, 0, sizeof voices); for (auto& v : voices) v.increment = 1.0; }
+  } samplers[gd::SAMPLER_RACKS];
   float peaks[gd::N_PEAKS] = {0};          // read-and-reset meters (ffi.rs:2572-2584, graph.rs:233-237), merged after every render
   struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
   std::vector<MidiEvent> midi_events;      // of the most recent render call, at most 64 (ffi.rs:71, 994-1004, 1045)
@@ -400,8 +430,8 @@ inline GooeyEngine* engine_create(int device, float sr) {
   gd::MixCfg& c = e->cfg;
   memset(&c, 0, sizeof c);
   c.n_tracks = 4;
-  const int32_t routes[7] = {0, 1, 2, 3, 3, -1, -1};
-  for (int i = 0; i < 7; i++) c.route[i] = routes[i];
+  const int32_t routes[9] = {0, 1, 2, 3, 3, -1, -1, -1, -1};   // graph.rs:131-143; sampler racks start unrouted
+  for (int i = 0; i < 9; i++) c.route[i] = routes[i];
   const uint32_t order[9] = {7, 2, 0, 4, 1, 3, 8, 6, 9};   // DEFAULT_EFFECT_ORDER (ffi.rs:1583-1593)
   for (int i = 0; i < 9; i++) c.order[i] = order[i];
   for (int s = 0; s < gd::MAX_FX; s++) { c.fx_kind[s] = s < 4 ? kinds[s] : (uint32_t)gd::FXK_NONE; c.fx_enabled[s] = 0; }
@@ -421,7 +451,10 @@ inline void engine_destroy(GooeyEngine* e) {
   for (int ch = 0; ch < 5; ch++) B.voices.release(e->strip[ch].type, e->strip[ch].slot);
   B.voices.release(GOOEY_B200_VOICE_POLY, e->poly.slot);
   B.voices.release(GOOEY_B200_VOICE_GRANULATOR, e->gran.slot);
-  if (e->gran_buf) { cudaSetDevice(B.device); cudaStreamSynchronize(B.stream); }   // no launch may still read the buffer
+  bool holds_pcm = (bool)e->gran_buf;
+  for (auto& l : e->loops) holds_pcm = holds_pcm || l.buf;
+  for (auto& r : e->samplers) holds_pcm = holds_pcm || r.registered;
+  if (holds_pcm) { cudaSetDevice(B.device); cudaStreamSynchronize(B.stream); }   // no launch may still read the buffers
   B.mix_pool.release(e->mix_slot);
   delete e;
 }
@@ -592,6 +625,55 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       }
     }
   }
+  // ---- sample-playback sources: one descriptor per engine with a loaded loop / per rack with a sounding voice ----
+  B.h_loop_descs.clear(); B.h_rack_descs.clear();
+  struct ExtRef { int engine, rack; };
+  std::vector<int> loop_refs; std::vector<ExtRef> rack_refs;
+  uint32_t ext_pairs = 0;
+  for (int i = 0; i < n; i++) {
+    GooeyEngine* e = E[i];
+    e->cfg.src_ext = 0;
+    for (int s = 0; s < gd::EXT_SOURCES; s++) e->cfg.ext_row[s] = 0;
+    // Mixer::tick writes the gate targets every sample from the mute / solo flags, which only change between calls (mod.rs:63-72)
+    bool any_lsolo = false, any_loaded = false;
+    for (auto& l : e->loops) { any_lsolo = any_lsolo || l.soloed; any_loaded = any_loaded || (l.buf && l.len > 0); }
+    for (auto& l : e->loops) gd::lsm_set(l.active, (any_lsolo ? l.soloed : !l.muted) ? 1.0f : 0.0f, 0.0f, 1.0f);
+    if (any_loaded) {
+      gd::LoopMixer m;
+      memset(&m, 0, sizeof m);
+      for (int c = 0; c < gd::LOOP_CHANNELS; c++) {
+        const auto& l = e->loops[c];
+        gd::LoopChan& d = m.ch[c];
+        const bool loaded = l.buf && l.len > 0;
+        d.left = loaded ? l.buf->p : nullptr; d.right = loaded ? l.buf->p + l.len : nullptr;
+        d.cursor = l.cursor; d.len = loaded ? l.len : 0u; d.buf_sr = l.buf_sr;
+        // warp_ratio (loop_channel.rs:282-291) applies in Resample mode only (:239-243); PreservePitch with speed < 0 is refused upstream
+        d.warp = (l.pitch_mode == 1 && l.has_source_bpm && l.source_bpm > 0.0f && e->loop_engine_bpm > 0.0f) ? (double)e->loop_engine_bpm / (double)l.source_bpm : 1.0;
+        d.loop_start = l.loop_start; d.loop_end = l.loop_end; d.speed = l.speed; d.playing = l.playing ? 1u : 0u;
+        d.gain = l.gain; d.active = l.active;
+      }
+      m.row = ext_pairs;
+      e->cfg.src_ext |= 1u; e->cfg.ext_row[0] = ext_pairs++;
+      B.h_loop_descs.push_back(m); loop_refs.push_back(i);
+    } else {
+      // nothing to read: the channels output exactly 0 and only their smoothers move (they tick every sample, :202-207)
+      for (auto& l : e->loops)
+        for (uint32_t f = 0; f < frames && (l.gain.c != l.gain.t || l.active.c != l.active.t); f++) { gd::lsm_tick(l.gain, B.rc.smooth15); gd::lsm_tick(l.active, B.rc.smooth15); }
+    }
+    for (int r = 0; r < gd::SAMPLER_RACKS; r++) {
+      auto& R = e->samplers[r];
+      if (!R.registered) continue;
+      bool sounding = false;
+      for (const auto& v : R.voices) sounding = sounding || v.samples != nullptr;
+      if (!sounding) continue;                       // a rack with no active voice ticks to exactly 0 and its state does not move
+      gd::SamplerRack d;
+      memcpy(d.v, R.voices, sizeof d.v);
+      d.row = ext_pairs; d.rack = (uint32_t)r;
+      e->cfg.src_ext |= 2u << r; e->cfg.ext_row[1 + r] = ext_pairs++;
+      B.h_rack_descs.push_back(d); rack_refs.push_back({i, r});
+    }
+    B.cfgs[e->mix_slot] = e->cfg;
+  }
   const double* tt = B.clock.view(clock_table(B.sr), kmin, kmax, st);
   // ---- device state: pools, configs, rings ----
   B.mix_pool.flush(st);
@@ -626,6 +708,12 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   const size_t vstride = ((piece / 32) & 1) ? piece : piece + 32;
   B.d_voice_bufs[0].alloc(rows * vstride);
   if (two_bufs) B.d_voice_bufs[1].alloc(rows * vstride);
+  if (ext_pairs) {
+    B.d_ext[0].alloc((size_t)2 * ext_pairs * vstride);
+    if (two_bufs) B.d_ext[1].alloc((size_t)2 * ext_pairs * vstride);
+    if (!B.h_loop_descs.empty()) B.d_loop_descs.upload(B.h_loop_descs.data(), B.h_loop_descs.size(), st);
+    if (!B.h_rack_descs.empty()) B.d_rack_descs.upload(B.h_rack_descs.data(), B.h_rack_descs.size(), st);
+  }
   {
     bool any_chain = false;
     for (int i = 0; i < n && !any_chain; i++) for (int q = 0; q < gd::MAX_FX; q++) any_chain = any_chain || (E[i]->cfg.fx_kind[q] != gd::FXK_NONE && E[i]->cfg.fx_enabled[q]);
@@ -718,6 +806,20 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     tev(tv0, st);
     B.voices.set_mod(lfo_planes, (long long)frames, (int)f0);
     B.voices.launch(st, start, B.rc, tt, (int)nf, B.d_voice_bufs[vb].p, (long long)vstride);
+    if (ext_pairs) {   // loop mixers and sampler racks of this piece, on the voice stream (the mixer waits for ev_voices)
+      const gd::ExtTickCtx xc{B.sr, B.rc.smooth15};
+      if (!B.h_loop_descs.empty()) {
+        const int nd = (int)B.h_loop_descs.size();
+        gd::ext_source_kernel<gd::LoopMixer><<<(nd + 63) / 64, 64, 0, st>>>(B.d_loop_descs.p, nd, B.d_ext[vb].p, (long long)vstride, (int)nf, xc);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+      }
+      if (!B.h_rack_descs.empty()) {
+        const int nd = (int)B.h_rack_descs.size();
+        gd::ext_source_kernel<gd::SamplerRack><<<(nd + 63) / 64, 64, 0, st>>>(B.d_rack_descs.p, nd, B.d_ext[vb].p, (long long)vstride, (int)nf, xc);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+      }
+      GH_CUDA(cudaGetLastError());
+    }
     tev(tv1, st);
     const auto h2 = std::chrono::steady_clock::now();
     GH_CUDA(cudaEventRecord(B.ev_voices[vb], st));
@@ -747,6 +849,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     M.fast = B.d_mix_fast.p; M.consts = B.d_mix_consts.p;
     M.peaks = B.d_peaks.p;
     M.premix = B.d_premix.p; M.premix_stride = (long long)vstride;
+    M.ext = ext_pairs ? B.d_ext[vb].p : nullptr; M.ext_stride = (long long)vstride;
     M.chain_units = B.d_chain_units.p;
     tev(tm0, ms);
     gd::mix_prepare_kernel<<<(n + 127) / 128, 128, 0, ms>>>(M);
@@ -794,7 +897,20 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   GH_CUDA(cudaMemcpyAsync(B.h_peaks.data(), B.d_peaks.p, B.h_peaks.size() * 4, cudaMemcpyDeviceToHost, st));
   GH_CUDA(cudaMemcpyAsync(&B.h_chain_units, B.d_chain_units.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (!B.h_lfo_streams.empty()) GH_CUDA(cudaMemcpyAsync(B.h_lfo_streams.data(), B.d_lfo_streams.p, B.h_lfo_streams.size() * sizeof(gd::LfoStream), cudaMemcpyDeviceToHost, st));
+  if (!B.h_loop_descs.empty()) GH_CUDA(cudaMemcpyAsync(B.h_loop_descs.data(), B.d_loop_descs.p, B.h_loop_descs.size() * sizeof(gd::LoopMixer), cudaMemcpyDeviceToHost, st));
+  if (!B.h_rack_descs.empty()) GH_CUDA(cudaMemcpyAsync(B.h_rack_descs.data(), B.d_rack_descs.p, B.h_rack_descs.size() * sizeof(gd::SamplerRack), cudaMemcpyDeviceToHost, st));
   GH_CUDA(cudaStreamSynchronize(st));
+  for (size_t q = 0; q < loop_refs.size(); q++)      // playback state back into the engines' loop channels / sampler voices
+    for (int c = 0; c < gd::LOOP_CHANNELS; c++) {
+      auto& l = E[loop_refs[q]]->loops[c];
+      const gd::LoopChan& d = B.h_loop_descs[q].ch[c];
+      l.cursor = d.cursor; l.gain = d.gain; l.active = d.active;
+    }
+  for (size_t q = 0; q < rack_refs.size(); q++) {
+    auto& R = E[rack_refs[q].engine]->samplers[rack_refs[q].rack];
+    memcpy(R.voices, B.h_rack_descs[q].v, sizeof R.voices);
+    for (int v = 0; v < gd::SAMPLER_VOICES; v++) if (!R.voices[v].samples) R.voices_release(v);
+  }
   for (size_t q = 0; q < lfo_refs.size(); q++) E[lfo_refs[q].engine]->lfos[lfo_refs[q].lfo].phase = B.h_lfo_streams[q].phase;
   for (int i = 0; i < n; i++) {
     for (int q = 0; q < gd::N_PEAKS; q++) { const float v = B.h_peaks[(size_t)i * gd::N_PEAKS + q]; if (v > E[i]->peaks[q]) E[i]->peaks[q] = v; }

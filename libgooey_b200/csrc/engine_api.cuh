@@ -189,6 +189,7 @@ void gooey_engine_load_bass_preset(GooeyEngine* e, uint32_t id) {
 void gooey_engine_set_bpm(GooeyEngine* e, float bpm) {
   if (!e) return;
   e->bpm = bpm;
+  e->loop_engine_bpm = bpm;                                    // Mixer::set_bpm (ffi.rs:3360, mixer/mod.rs:80-87)
   for (auto& s : e->strip) s.seq.set_bpm(bpm);
   for (int slot = 0; slot < gd::MAX_FX; slot++)
     if (e->cfg.fx_kind[slot] == gd::FXK_DELAY) e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_BPM, slot, bpm));
@@ -318,7 +319,9 @@ int32_t gooey_engine_mixer_add_track(GooeyEngine* e, const char*) {
 }
 uint32_t gooey_engine_mixer_get_track_count(const GooeyEngine* e) { return e ? e->cfg.n_tracks : 0; }
 bool gooey_engine_mixer_route_source(GooeyEngine* e, uint32_t src, uint32_t track) {
-  if (!e || src >= 5 || track >= e->cfg.n_tracks) return false;
+  // MixerGraph::route (graph.rs:243-250): the five fixed sources, and sampler racks once registered (source 5 + rack)
+  if (!e || src >= 9 || track >= e->cfg.n_tracks) return false;
+  if (src >= 5 && !e->samplers[src - 5].registered) return false;
   e->cfg.route[src] = (int32_t)track;
   gh::sync_cfg(e);
   return true;

@@ -316,6 +316,7 @@ int gooey_voice_batch_render(GooeyVoiceBatch* b, uint32_t frames, float* out_hos
 
 #include "engine_api.cuh"
 #include "rs_api.cuh"
+#include "loops_api.cuh"
 #include <sys/syscall.h>
 #include <unistd.h>
 

@@ -1,0 +1,235 @@
+// loops.cuh — sample-playback sources of the engine path: the 4-channel stereo loop mixer
+// (mixer/mod.rs:60-75, mixer/loop_channel.rs:181-208 and :262-300, mixer/stereo_buffer.rs:198-262) and the sampler racks
+// (instruments/sampler.rs:64-225).  Both feed the MixerGraph as stereo sources (ffi.rs:1289-1308): source 4 = loop mixer,
+// sources 5-8 = sampler racks.
+//
+// Shape of the work: every source is a gather from a host-supplied PCM buffer at a cursor that advances by a constant f64
+// increment per output frame — `cursor += delta` accumulated frame by frame in the reference, with a modulo at the loop
+// seam — so the cursor recurrence is replayed exactly as written (one thread per engine walks its own cursors; the adds
+// are one f64 add per frame and channel) and the reads are 4-tap cubic (loops) or 2-tap linear (samplers) gathers from
+// buffers that stay L2-resident (a 10 s stereo loop is 3.5 MB).  A warp's 32 engines stage 32 frames of their stereo rows
+// in shared memory and store them transposed, so the planes the mixer reads are written with full 128-byte lines.
+//
+// The playback state (cursors, fader and gate smoothers, sampler voices) is host-authoritative between render calls: the
+// FFI setters act on it directly, exactly like the reference's setters act on the LoopChannel / SamplerRack structs;
+// engines_render uploads one descriptor per engine with a loaded source, the kernel advances it piece by piece, and the
+// state is read back when the call ends.
+//
+// Not built (a request latches the engine's sticky error instead of rendering different audio): PitchMode::PreservePitch
+// (mixer/wsola.rs), queued buffer swaps, per-channel effect chains, the clip grid and transport-armed sampler patterns.
+#pragma once
+#include "dsp.cuh"
+
+namespace gd {
+
+constexpr int LOOP_CHANNELS = 4;                      // mixer/mod.rs:32
+constexpr int SAMPLER_RACKS = 4;                      // ffi.rs:585
+constexpr int SAMPLER_SLOTS = 16, SAMPLER_VOICES = 32;   // sampler.rs:14-15
+constexpr int EXT_SOURCES = 1 + SAMPLER_RACKS;        // graph sources 4 .. 8 (graph.rs:35-42)
+constexpr float LOOP_MAX_SPEED = 4.0f, LOOP_MAX_GAIN = 2.0f, LOOP_FADER_MS = 15.0f;   // loop_channel.rs:20-24
+
+struct LSm { float c, t; };                           // SmoothedParam: current, target (settled <=> c == t)
+G_HD void lsm_set(LSm& s, float v, float lo, float hi) { float c = clampf(v, lo, hi); if (fabsf(s.t - c) > 1e-8f) s.t = c; }   // smoother.rs:84-95
+G_HD float lsm_tick(LSm& s, float coeff) { smooth_tick(s.c, s.t, coeff); return s.c; }
+
+G_HD double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+G_HD double rem_euclid_d(double a, double b) { double r = fmod(a, b); return r < 0.0 ? r + fabs(b) : r; }   // f64::rem_euclid
+G_HD long long rem_euclid_i(long long a, long long b) { long long r = a % b; return r < 0 ? r + b : r; }    // isize::rem_euclid (b > 0)
+
+// utils/mod.rs:26-32
+G_HD float cubic_interp(float p0, float p1, float p2, float p3, float t) {
+  float a0 = -0.5f * p0 + 1.5f * p1 - 1.5f * p2 + 0.5f * p3;
+  float a1 = p0 - 2.5f * p1 + 2.0f * p2 - 0.5f * p3;
+  float a2 = -0.5f * p0 + 0.5f * p2;
+  float a3 = p1;
+  return ((a0 * t + a1) * t + a2) * t + a3;
+}
+
+// ---- loop_channel.rs LoopWindow (:59-116) and LoopChannel::window (:293-307) -------------------------------------------
+struct LoopWindow { double lo, hi, span, len; bool wraps; };
+G_HD LoopWindow loop_window(float loop_start, float loop_end, double len) {
+  LoopWindow w;
+  w.lo = clampd((double)loop_start * len, 0.0, len);
+  w.hi = clampd((double)loop_end * len, 0.0, len);
+  w.wraps = w.hi < w.lo;
+  w.span = w.wraps ? len - w.lo + w.hi : w.hi - w.lo;
+  w.len = len;
+  return w;
+}
+G_HD double window_to_virtual(const LoopWindow& w, double p) { return rem_euclid_d(p - w.lo, w.len); }
+G_HD double window_to_physical(const LoopWindow& w, double v) { return rem_euclid_d(w.lo + v, w.len); }
+G_HD bool window_contains(const LoopWindow& w, double p) { return w.wraps ? (p >= w.lo || p < w.hi) : (p >= w.lo && p < w.hi); }
+G_HD double window_fold(const LoopWindow& w, double p) {   // :99-115
+  if (window_contains(w, p)) return p;
+  if (w.wraps) return (p - w.hi) <= (w.lo - p) ? w.hi : w.lo;
+  return clampd(p, w.lo, w.hi);
+}
+
+// One loop channel of one engine.  `left` / `right` are device planes of `len` frames (nullptr: nothing loaded).
+struct LoopChan {
+  const float* left; const float* right;
+  double cursor;              // playback position in source frames
+  double warp;                // warp_ratio() when the pitch mode is Resample, else 1.0 (:282-291, :233-237)
+  uint32_t len; float buf_sr;
+  float loop_start, loop_end, speed;
+  uint32_t playing;
+  LSm gain, active;           // user fader; mute / solo gate written by Mixer::tick (mod.rs:63-72)
+};
+struct LoopMixer { LoopChan ch[LOOP_CHANNELS]; uint32_t row; uint32_t pad; };   // row = index of the stereo row pair this mixer writes
+
+// stereo_buffer.rs:198-262
+G_HD void loop_read_interpolated(const float* L, const float* R, uint32_t len, double position, float& ol, float& orr) {
+  if (len == 1) { ol = L[0]; orr = R[0]; return; }
+  const double last = (double)(len - 1);
+  position = clampd(position, 0.0, last);
+  const long long index = (long long)floor(position);
+  const float frac = (float)(position - (double)index);
+  const long long lastI = (long long)len - 1;
+  const long long i0 = index - 1 < 0 ? 0 : (index - 1 > lastI ? lastI : index - 1);
+  const long long i1 = index < 0 ? 0 : (index > lastI ? lastI : index);
+  const long long i2 = index + 1 > lastI ? lastI : index + 1;
+  const long long i3 = index + 2 > lastI ? lastI : index + 2;
+  ol = cubic_interp(L[i0], L[i1], L[i2], L[i3], frac);
+  orr = cubic_interp(R[i0], R[i1], R[i2], R[i3], frac);
+}
+G_HD void loop_read_wrapped(const float* L, const float* R, uint32_t len, double position, float& ol, float& orr) {
+  if (len == 1) { ol = L[0]; orr = R[0]; return; }
+  const double flen = (double)len;
+  position = rem_euclid_d(position, flen);
+  const long long index = (long long)floor(position);
+  const float frac = (float)(position - (double)index);
+  const long long n = (long long)len;
+  const long long i0 = rem_euclid_i(index - 1, n), i1 = rem_euclid_i(index, n), i2 = rem_euclid_i(index + 1, n), i3 = rem_euclid_i(index + 2, n);
+  ol = cubic_interp(L[i0], L[i1], L[i2], L[i3], frac);
+  orr = cubic_interp(R[i0], R[i1], R[i2], R[i3], frac);
+}
+
+// LoopChannel::advance (:233-279), without the queued-swap check (not built)
+G_HD void loop_advance(LoopChan& c, float engine_sr) {
+  const double len = (double)c.len, source_sr = (double)c.buf_sr;
+  const LoopWindow w = loop_window(c.loop_start, c.loop_end, len);
+  const double span = w.span > 1.0 ? w.span : 1.0;                 // window.span.max(1.0)
+  const double ratio = source_sr / (double)fmaxf(engine_sr, 1.0f);
+  const double delta = (double)c.speed * ratio * c.warp;
+  if (w.wraps) {
+    const double prev_v = window_to_virtual(w, c.cursor);
+    const double raw = prev_v + delta;
+    const double cur_v = rem_euclid_d(raw, span);
+    c.cursor = window_to_physical(w, cur_v);
+  } else {
+    c.cursor += delta;
+    if (c.cursor >= w.hi) c.cursor = w.lo + rem_euclid_d(c.cursor - w.lo, span);
+    else if (c.cursor < w.lo) c.cursor = w.hi - rem_euclid_d(w.lo - c.cursor, span);
+  }
+}
+// LoopChannel::tick (:181-208) with an empty effect chain (EffectChain::process of no effects is the identity, effect_chain.rs:294-299)
+G_HD void loop_chan_tick(LoopChan& c, float engine_sr, float coeff15, float& ol, float& orr) {
+  float dl = 0.0f, dr = 0.0f;
+  if (c.playing && c.left) {
+    const LoopWindow w = loop_window(c.loop_start, c.loop_end, (double)c.len);
+    if (w.wraps) loop_read_wrapped(c.left, c.right, c.len, c.cursor, dl, dr);
+    else loop_read_interpolated(c.left, c.right, c.len, c.cursor, dl, dr);
+    loop_advance(c, engine_sr);
+  }
+  const float g = lsm_tick(c.gain, coeff15);
+  const float gl = dl * g, gr = dr * g;
+  const float a = lsm_tick(c.active, coeff15);
+  ol = gl * a; orr = gr * a;
+}
+// Mixer::tick (mod.rs:60-75) after the gate targets were written (they only change between render calls); the clip grid holds nothing
+G_HD void loop_mixer_tick(LoopMixer& m, float engine_sr, float coeff15, float& ol, float& orr) {
+  float l = 0.0f, r = 0.0f;
+#pragma unroll
+  for (int k = 0; k < LOOP_CHANNELS; k++) {
+    float cl, cr;
+    loop_chan_tick(m.ch[k], engine_sr, coeff15, cl, cr);
+    l += cl; r += cr;
+  }
+  ol = l; orr = r;
+}
+
+// ---- instruments/sampler.rs ----------------------------------------------------------------------------------------
+// SamplerBuffer::frame (:64-81): linear read of an interleaved buffer, position clamped to the last frame
+struct SampleVoice {          // :84-150
+  const float* samples;       // device copy of the slot's interleaved PCM the voice was started on (nullptr: inactive)
+  double position, increment;
+  unsigned long long age;
+  uint32_t frames, channels, slot;
+  float velocity;
+};
+struct SamplerRack { SampleVoice v[SAMPLER_VOICES]; uint32_t row; uint32_t rack; };
+
+G_HD void sample_voice_tick(SampleVoice& v, float& ol, float& orr) {
+  if (!v.samples) { ol = 0.0f; orr = 0.0f; return; }
+  const double pos = clampd(v.position, 0.0, (double)(v.frames - 1));
+  const uint32_t i0 = (uint32_t)floor(pos);
+  const uint32_t i1 = i0 + 1 < v.frames - 1 ? i0 + 1 : v.frames - 1;
+  const float frac = (float)(pos - (double)i0);
+  float fl, fr;
+  if (v.channels == 1) {
+    const float a = v.samples[i0], b = v.samples[i1];
+    fl = fr = a + (b - a) * frac;
+  } else {
+    const float a = v.samples[2 * i0], b = v.samples[2 * i1];
+    fl = a + (b - a) * frac;
+    const float c = v.samples[2 * i0 + 1], d = v.samples[2 * i1 + 1];
+    fr = c + (d - c) * frac;
+  }
+  const double fade = 32.0, end = (double)v.frames;               // fixed click guard (:134-141)
+  const double tail = (end - v.position) / fade;
+  const double g = fmin(fmin(v.position / fade, tail > 0.0 ? tail : 0.0), 1.0);
+  const float gain = (float)g * v.velocity;
+  v.position += v.increment;
+  if (v.position >= end) v.samples = nullptr;
+  ol = fl * gain; orr = fr * gain;
+}
+// SamplerRack::tick (:225-229): fold over the 32 voices in index order
+G_HD void sampler_rack_tick(SamplerRack& r, float& ol, float& orr) {
+  float l = 0.0f, rr = 0.0f;
+  for (int k = 0; k < SAMPLER_VOICES; k++) {
+    float vl, vr;
+    sample_voice_tick(r.v[k], vl, vr);
+    l += vl; rr += vr;
+  }
+  ol = l; orr = rr;
+}
+
+#ifdef __CUDACC__
+// Stereo rows of the sample-playback sources of one piece: descriptor with row r writes ext[2 * r][frame] (left) and
+// ext[2 * r + 1][frame] (right); MixCfg::ext_row tells the mixer which pair belongs to which (engine, graph source).
+// One thread per descriptor; a warp stages 32 frames of its 32 descriptors' stereo output in shared memory (pitch 33) and
+// writes each row's 32 frames with one coalesced store.
+struct ExtTickCtx { float engine_sr, coeff15; };
+__device__ __forceinline__ void ext_tick(LoopMixer& m, const ExtTickCtx& c, float& l, float& r) { loop_mixer_tick(m, c.engine_sr, c.coeff15, l, r); }
+__device__ __forceinline__ void ext_tick(SamplerRack& m, const ExtTickCtx&, float& l, float& r) { sampler_rack_tick(m, l, r); }
+
+template <class Desc>
+__global__ void __launch_bounds__(64) ext_source_kernel(Desc* descs, int n, float* ext, long long stride, int frames, ExtTickCtx ctx) {
+  __shared__ float tile_l[2][32][33], tile_r[2][32][33];
+  float (*tl)[33] = tile_l[threadIdx.x >> 5];
+  float (*tr)[33] = tile_r[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  Desc d;
+  unsigned row_mine = 0u;
+  if (valid) { d = descs[i]; row_mine = d.row; }
+  for (int t0 = 0; t0 < frames; t0 += 32) {
+    const int nf = min(32, frames - t0);
+    if (valid)
+      for (int j = 0; j < nf; j++) { float l, r; ext_tick(d, ctx, l, r); tl[lane][j] = l; tr[lane][j] = r; }
+    __syncwarp();
+    for (int q = 0; q < 32; q++) {
+      const unsigned row = __shfl_sync(0xffffffffu, row_mine, q);
+      const int ok = __shfl_sync(0xffffffffu, (int)valid, q);
+      if (!ok || lane >= nf) continue;
+      float* pl = ext + (long long)(2u * row) * stride + t0 + lane;
+      pl[0] = tl[q][lane]; pl[stride] = tr[q][lane];
+    }
+    __syncwarp();
+  }
+  if (valid) descs[i] = d;
+}
+#endif
+
+}  // namespace gd

@@ -1,0 +1,192 @@
+// loops_api.cuh — extern "C" surface of the sample-playback sources (include/gooey.h, "loop mixer" and "sampler racks"
+// sections; reference: src/ffi.rs:6000-6172 and :7150-7535, :8006-8048).  The setters edit the host-side channel / rack
+// structs exactly like the reference's setters edit LoopChannel / SamplerRack; the audio work is loops.cuh, driven by
+// engines_render (engine.cuh).  Requests for the parts that are not built latch the engine's sticky error.
+#pragma once
+#include "engine_api.cuh"
+
+namespace gh {
+static GooeyEngine::LoopHost* loop_ch(GooeyEngine* e, uint32_t ch) { return (e && ch < (uint32_t)gd::LOOP_CHANNELS) ? &e->loops[ch] : nullptr; }
+static const GooeyEngine::LoopHost* loop_ch(const GooeyEngine* e, uint32_t ch) { return (e && ch < (uint32_t)gd::LOOP_CHANNELS) ? &e->loops[ch] : nullptr; }
+static GooeyEngine::SamplerHost* rack_of(GooeyEngine* e, uint32_t rack) { return (e && rack < (uint32_t)gd::SAMPLER_RACKS && e->samplers[rack].registered) ? &e->samplers[rack] : nullptr; }
+static const GooeyEngine::SamplerHost* rack_of(const GooeyEngine* e, uint32_t rack) { return (e && rack < (uint32_t)gd::SAMPLER_RACKS && e->samplers[rack].registered) ? &e->samplers[rack] : nullptr; }
+// host PCM -> a device buffer of the engine's bank; the bank's stream is drained so no in-flight render reads a buffer that is replaced
+static std::shared_ptr<DevBuf<float>> upload_pcm(GooeyEngine* e, const std::vector<float>& host) {
+  use_device(e->bank->device);
+  auto buf = std::make_shared<DevBuf<float>>();
+  buf->alloc(host.size());
+  GH_CUDA(cudaMemcpy(buf->p, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  GH_CUDA(cudaStreamSynchronize(e->bank->stream));
+  return buf;
+}
+static void sampler_stop_slot(GooeyEngine::SamplerHost& R, uint32_t slot) {   // sampler.rs:321-327
+  for (int v = 0; v < gd::SAMPLER_VOICES; v++) if (R.voices[v].samples && R.voices[v].slot == slot) R.voices_release(v);
+}
+}  // namespace gh
+
+extern "C" {
+
+// ---- loop mixer --------------------------------------------------------------------------------------------------------
+bool gooey_engine_loop_load(GooeyEngine* e, uint32_t channel, const float* samples, uint32_t frames, uint32_t channels, float sample_rate) {   /* :7184-7202 */
+  if (!e || !samples || frames == 0 || channels == 0) return false;
+  // StereoSampleBuffer::from_interleaved + from_channels (stereo_buffer.rs:22-87): channels 0 / 1 become left / right (mono is
+  // duplicated), the rate and every kept sample must be finite
+  if (!std::isfinite(sample_rate) || !(sample_rate > 0.0f)) return false;
+  std::vector<float> planes((size_t)2 * frames);
+  for (uint32_t f = 0; f < frames; f++) {
+    const float* fr = samples + (size_t)f * channels;
+    const float l = fr[0], r = channels == 1 ? fr[0] : fr[1];
+    if (!std::isfinite(l) || !std::isfinite(r)) return false;
+    planes[f] = l; planes[(size_t)frames + f] = r;
+  }
+  GooeyEngine::LoopHost* c = gh::loop_ch(e, channel);
+  if (!c) return false;                                                           // Mixer::load: bad channel index
+  try {
+    auto buf = gh::upload_pcm(e, planes);
+    c->buf = buf; c->len = frames; c->buf_sr = sample_rate;
+    c->has_source_bpm = false; c->source_bpm = 0.0f;                              // a new buffer carries no tempo tag
+    c->cursor = c->window().lo;                                                   // set_buffer (loop_channel.rs:311-316)
+  } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
+  return true;
+}
+void gooey_engine_loop_set_playing(GooeyEngine* e, uint32_t ch, bool playing) { if (auto* c = gh::loop_ch(e, ch)) c->playing = playing; }
+void gooey_engine_loop_set_gain(GooeyEngine* e, uint32_t ch, float gain) { if (auto* c = gh::loop_ch(e, ch)) gd::lsm_set(c->gain, gd::clampf(gain, 0.0f, gd::LOOP_MAX_GAIN), 0.0f, gd::LOOP_MAX_GAIN); }
+void gooey_engine_loop_set_mute(GooeyEngine* e, uint32_t ch, bool muted) { if (auto* c = gh::loop_ch(e, ch)) c->muted = muted; }
+void gooey_engine_loop_set_solo(GooeyEngine* e, uint32_t ch, bool soloed) { if (auto* c = gh::loop_ch(e, ch)) c->soloed = soloed; }
+void gooey_engine_loop_set_start(GooeyEngine* e, uint32_t ch, float n) { if (auto* c = gh::loop_ch(e, ch)) c->loop_start = gd::clampf(n, 0.0f, 1.0f); }
+void gooey_engine_loop_set_end(GooeyEngine* e, uint32_t ch, float n) { if (auto* c = gh::loop_ch(e, ch)) c->loop_end = gd::clampf(n, 0.0f, 1.0f); }
+void gooey_engine_loop_set_speed(GooeyEngine* e, uint32_t ch, float s) { if (auto* c = gh::loop_ch(e, ch)) c->speed = gd::clampf(s, -gd::LOOP_MAX_SPEED, gd::LOOP_MAX_SPEED); }
+void gooey_engine_loop_set_source_bpm(GooeyEngine* e, uint32_t ch, float bpm) {   /* :7331-7344; StereoSampleBuffer::set_source_bpm :178-180 */
+  auto* c = gh::loop_ch(e, ch);
+  if (!c || !c->buf) return;
+  c->has_source_bpm = bpm > 0.0f && std::isfinite(bpm);
+  c->source_bpm = c->has_source_bpm ? bpm : 0.0f;
+}
+float gooey_engine_loop_get_source_bpm(const GooeyEngine* e, uint32_t ch) { const auto* c = gh::loop_ch(e, ch); return (c && c->buf && c->has_source_bpm) ? c->source_bpm : 0.0f; }
+void gooey_engine_loop_set_pitch_mode(GooeyEngine* e, uint32_t ch, uint32_t mode) {   /* :7368-7381 */
+  auto* c = gh::loop_ch(e, ch);
+  if (!c) return;
+  c->pitch_mode = mode == GOOEY_PITCH_MODE_RESAMPLE ? 1u : (mode == GOOEY_PITCH_MODE_PRESERVE_PITCH ? 2u : 0u);
+  if (c->pitch_mode == 2u) gh::engine_fail(e, "libgooey_b200: PitchMode::PreservePitch (WSOLA time-stretch, mixer/wsola.rs) is not built; the channel plays unwarped");
+}
+uint32_t gooey_engine_loop_get_pitch_mode(const GooeyEngine* e, uint32_t ch) { const auto* c = gh::loop_ch(e, ch); return c ? c->pitch_mode : 0u; }
+void gooey_engine_loop_restart(GooeyEngine* e, uint32_t ch) { auto* c = gh::loop_ch(e, ch); if (c && c->buf) c->cursor = c->window().lo; }
+void gooey_engine_loop_set_position(GooeyEngine* e, uint32_t ch, float n) {   /* loop_channel.rs:388-397 */
+  auto* c = gh::loop_ch(e, ch);
+  if (!c || !c->buf) return;
+  const double len = (double)c->len;
+  c->cursor = gd::window_fold(c->window(), (double)gd::clampf(n, 0.0f, 1.0f) * len);
+}
+float gooey_engine_loop_get_position(const GooeyEngine* e, uint32_t ch) {     /* position_normalized :497-502 */
+  const auto* c = gh::loop_ch(e, ch);
+  return (c && c->buf && c->len > 1) ? (float)(c->cursor / (double)c->len) : 0.0f;
+}
+/* not built: they latch the sticky error and report failure */
+bool gooey_engine_loop_queue_swap(GooeyEngine* e, uint32_t, const float*, uint32_t, uint32_t, float, float, uint32_t) {
+  if (e) gh::engine_fail(e, "libgooey_b200: queued loop swaps (loop_channel.rs:413-423) are not built");
+  return false;
+}
+int32_t gooey_engine_loop_effect_add(GooeyEngine* e, uint32_t, uint32_t) {
+  if (e) gh::engine_fail(e, "libgooey_b200: per-loop-channel effect chains (ffi.rs:7536-7655) are not built; put the effect on the track the loop mixer is routed to");
+  return -1;
+}
+
+// Mixer::render_channel_to_interleaved (mixer/mod.rs:444-476): `frames` stereo frames of one loop channel from its loop start,
+// ignoring mute / solo, after prepare_offline_render (playing, fader snapped, gate open) — the audio of
+// gooey_engine_loop_render_to_wav.  With no per-channel effects the preroll only moves the cursor, which is restarted after it.
+bool gooey_engine_loop_render(GooeyEngine* e, uint32_t channel, uint32_t frames, uint32_t /*preroll*/, float* out_interleaved) {
+  auto* c = gh::loop_ch(e, channel);
+  if (!c || !out_interleaved || frames == 0 || !c->buf || c->len == 0) return false;
+  gh::EngineBank& B = *e->bank;
+  try {
+    std::lock_guard<std::recursive_mutex> lk(B.mu);
+    gh::use_device(B.device);
+    c->playing = true; c->gain.c = c->gain.t; c->active = {1.0f, 1.0f};
+    c->cursor = c->window().lo;
+    gd::LoopMixer m;
+    memset(&m, 0, sizeof m);
+    gd::LoopChan& d = m.ch[0];
+    d.left = c->buf->p; d.right = c->buf->p + c->len; d.cursor = c->cursor; d.len = c->len; d.buf_sr = c->buf_sr;
+    d.warp = (c->pitch_mode == 1 && c->has_source_bpm && c->source_bpm > 0.0f && e->loop_engine_bpm > 0.0f) ? (double)e->loop_engine_bpm / (double)c->source_bpm : 1.0;
+    d.loop_start = c->loop_start; d.loop_end = c->loop_end; d.speed = c->speed; d.playing = 1u; d.gain = c->gain; d.active = c->active;
+    m.row = 0;
+    const size_t stride = ((size_t)frames + 31) & ~(size_t)31;
+    B.d_ext[0].alloc(2 * stride);
+    B.d_loop_descs.upload(&m, 1, B.stream);
+    gd::ext_source_kernel<gd::LoopMixer><<<1, 64, 0, B.stream>>>(B.d_loop_descs.p, 1, B.d_ext[0].p, (long long)stride, (int)frames, gd::ExtTickCtx{e->sr, B.rc.smooth15});
+    gh::g_launches.fetch_add(1, std::memory_order_relaxed);
+    GH_CUDA(cudaGetLastError());
+    std::vector<float> planes(2 * stride);
+    GH_CUDA(cudaMemcpyAsync(planes.data(), B.d_ext[0].p, planes.size() * 4, cudaMemcpyDeviceToHost, B.stream));
+    GH_CUDA(cudaMemcpyAsync(&m, B.d_loop_descs.p, sizeof m, cudaMemcpyDeviceToHost, B.stream));
+    GH_CUDA(cudaStreamSynchronize(B.stream));
+    for (uint32_t f = 0; f < frames; f++) { out_interleaved[2 * (size_t)f] = planes[f]; out_interleaved[2 * (size_t)f + 1] = planes[stride + f]; }
+    c->cursor = m.ch[0].cursor; c->gain = m.ch[0].gain; c->active = m.ch[0].active;
+  } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
+  return true;
+}
+bool gooey_engine_loop_render_to_wav(GooeyEngine* e, uint32_t channel, uint32_t frame_count, uint32_t preroll_frame_count, const char* utf8_path) {   /* :8006-8048 */
+  if (!e || !utf8_path || !utf8_path[0] || frame_count == 0) return false;
+  std::vector<float> il((size_t)2 * frame_count);
+  if (!gooey_engine_loop_render(e, channel, frame_count, preroll_frame_count, il.data())) return false;
+  return gooey_b200_write_wav_f32(utf8_path, il.data(), frame_count, 2, (uint32_t)gd::f32_to_u64_sat(e->sr)) == GOOEY_E_OK;
+}
+
+// ---- sampler racks -----------------------------------------------------------------------------------------------------
+int32_t gooey_engine_sampler_register(GooeyEngine* e) {   /* :6007-6027 */
+  if (!e) return -1;
+  for (int r = 0; r < gd::SAMPLER_RACKS; r++)
+    if (!e->samplers[r].registered) { e->samplers[r].registered = true; return r; }
+  return -1;
+}
+uint32_t gooey_engine_sampler_get_source_id(const GooeyEngine* e, uint32_t rack) { return gh::rack_of(e, rack) ? GOOEY_SOURCE_SAMPLER_BASE + rack : 0xFFFFFFFFu; }
+bool gooey_engine_sampler_set_slot_buffer(GooeyEngine* e, uint32_t rack, uint32_t slot, const float* samples, uint32_t frames, uint32_t channels, float sample_rate) {   /* :6044-6072 */
+  if (!e || !samples) return false;
+  // SamplerBuffer::from_interleaved (sampler.rs:25-50)
+  if (!(channels == 1 || channels == 2) || frames == 0 || !std::isfinite(sample_rate) || !(sample_rate > 0.0f)) return false;
+  const size_t count = (size_t)frames * channels;
+  for (size_t i = 0; i < count; i++) if (!std::isfinite(samples[i])) return false;
+  auto* R = gh::rack_of(e, rack);
+  if (!R || slot >= (uint32_t)gd::SAMPLER_SLOTS) return false;
+  try {
+    auto buf = gh::upload_pcm(e, std::vector<float>(samples, samples + count));
+    auto& S = R->slots[slot];
+    S.buf = buf; S.frames = frames; S.channels = channels; S.sr = sample_rate;
+  } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
+  gh::sampler_stop_slot(*R, slot);
+  return true;
+}
+bool gooey_engine_sampler_clear_slot(GooeyEngine* e, uint32_t rack, uint32_t slot) {
+  auto* R = gh::rack_of(e, rack);
+  if (!R || slot >= (uint32_t)gd::SAMPLER_SLOTS) return false;
+  try { gh::use_device(e->bank->device); GH_CUDA(cudaStreamSynchronize(e->bank->stream)); } catch (const std::exception& ex) { gh::set_error(ex.what()); return false; }
+  R->slots[slot] = GooeyEngine::SamplerHost::Slot();
+  gh::sampler_stop_slot(*R, slot);
+  return true;
+}
+bool gooey_engine_sampler_slot_is_loaded(const GooeyEngine* e, uint32_t rack, uint32_t slot) { const auto* R = gh::rack_of(e, rack); return R && slot < (uint32_t)gd::SAMPLER_SLOTS && R->slots[slot].buf; }
+uint32_t gooey_engine_sampler_slot_frames(const GooeyEngine* e, uint32_t rack, uint32_t slot) { return gooey_engine_sampler_slot_is_loaded(e, rack, slot) ? e->samplers[rack].slots[slot].frames : 0u; }
+uint32_t gooey_engine_sampler_slot_channels(const GooeyEngine* e, uint32_t rack, uint32_t slot) { return gooey_engine_sampler_slot_is_loaded(e, rack, slot) ? e->samplers[rack].slots[slot].channels : 0u; }
+float gooey_engine_sampler_slot_sample_rate(const GooeyEngine* e, uint32_t rack, uint32_t slot) { return gooey_engine_sampler_slot_is_loaded(e, rack, slot) ? e->samplers[rack].slots[slot].sr : 0.0f; }
+bool gooey_engine_sampler_trigger(GooeyEngine* e, uint32_t rack, uint32_t slot, float velocity) {   /* :6150-6168; SamplerRack::trigger sampler.rs:200-223 */
+  auto* R = gh::rack_of(e, rack);
+  if (!R || slot >= (uint32_t)gd::SAMPLER_SLOTS || !R->slots[slot].buf) return false;
+  int vi = -1;
+  for (int v = 0; v < gd::SAMPLER_VOICES; v++) if (!R->voices[v].samples) { vi = v; break; }
+  if (vi < 0) { vi = 0; for (int v = 1; v < gd::SAMPLER_VOICES; v++) if (R->voices[v].age < R->voices[vi].age) vi = v; }   // oldest voice, first on ties
+  R->next_age += 1;
+  const auto& S = R->slots[slot];
+  gd::SampleVoice& V = R->voices[vi];
+  V.samples = S.buf->p; V.frames = S.frames; V.channels = S.channels; V.slot = slot;
+  V.position = 0.0; V.increment = (double)S.sr / (double)e->sr;
+  V.velocity = gd::clampf(velocity, 0.0f, 1.0f); V.age = R->next_age;
+  R->voice_buf[vi] = S.buf;
+  return true;
+}
+/* not built: transport-armed sampler patterns (ffi.rs:6173-6290) */
+bool gooey_engine_sampler_set_step(GooeyEngine* e, uint32_t, uint32_t, bool, uint32_t, float) {
+  if (e) gh::engine_fail(e, "libgooey_b200: sampler-rack step patterns (transport-armed, ffi.rs:6173-6290) are not built; trigger the pads with gooey_engine_sampler_trigger");
+  return false;
+}
+
+}  // extern "C"

@@ -60,7 +60,7 @@ enum { MP_CH_GAIN = 0, MP_CH_MUTE = 5, MP_CH_PAN = 10, MP_TR_GAIN = 15, MP_TR_PA
 // Host-authoritative structure of one engine's mixer (AoS; re-uploaded when edited).
 struct MixCfg {
   uint32_t n_tracks;
-  int32_t route[7];                 // source -> track (-1 none): drumkit, bass, poly, granulator, loop mixer
+  int32_t route[9];                 // source -> track (-1 none): drumkit, bass, poly, granulator, loop mixer, sampler racks 0-3 (graph.rs:31-42)
   uint32_t order[9];                // effect_order (ffi.rs:1583-1593)
   uint8_t gslot[12];                // global effect id -> slot (0xff = never touched: the effect is still in its constructor state and disabled)
   uint32_t comp_sidechain;          // compressor_sidechain (ffi.rs:3252-3265): instrument 0-4 or 0xFFFFFFFF
@@ -72,6 +72,10 @@ struct MixCfg {
   uint32_t limiter_on;
   float lim_th, lim_inv;
   uint32_t src_poly, src_gran;      // 1 when the poly / granulator voice buffers carry this engine's output
+  // sample-playback sources (loops.cuh), rewritten by every render call: bit 0 = the loop mixer, bit 1 + k = sampler rack k has a
+  // stereo row pair in the launch's ext planes; ext_row[s] = that pair's index (left row 2 * r, right row 2 * r + 1)
+  uint32_t src_ext;
+  uint32_t ext_row[5];
 };
 
 // Geometry of the delay lines at the launch's sample rate (host-computed, reference formulas).
@@ -106,6 +110,7 @@ struct MixLaunch {
   uint8_t* fast;                      // [n] 1 = handled by mix_fast_kernel, the general kernel skips it; 2 = mix_fast_kernel writes the
                                       // engine's pre-chain stereo mix (strips -> graph -> master) and the general kernel runs only its global chain
   float* premix;                      // [2][n_lpad][premix_stride]: left plane, right plane
+  const float* ext; long long ext_stride;   // sample-playback sources of this piece: [2 * pairs][ext_stride] (MixCfg::ext_row), or nullptr
   struct MixConst* consts;            // [n]
   unsigned long long* chain_units;    // engine-frames taken by chain_fast_kernel (chain.cuh) in this render call
 };
@@ -115,7 +120,8 @@ struct MixConst {
   float tgain[MAX_TRACKS], tbl[MAX_TRACKS], tbr[MAX_TRACKS];
   float master, lim_th, lim_inv;
   uint32_t n_tracks, limiter_on, src_poly, src_gran;
-  int32_t route[5];
+  int32_t route[9];
+  uint32_t src_ext, ext_row[5];
 };
 
 // ---------------------------------------------------------------- effect constructors (device + host) ----
@@ -736,13 +742,22 @@ __global__ void __launch_bounds__(32) mix_kernel(const MixLaunch L) {
           float pl = x * pan_cos[c], pr = x * pan_sin[c];
           if (c < 4) { kit_l += pl; kit_r += pr; } else { bass_l += pl; bass_r += pr; }
         }
-        float src_l[5] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f}, src_r[5] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f};
+        float src_l[9] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, src_r[9] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         if (cfg.src_poly) { float x = tin[5][lane * 33 + j]; src_l[2] = x * L.center_l; src_r[2] = x * L.center_r; }
         if (cfg.src_gran) { float x = tin[6][lane * 33 + j]; src_l[3] = x * L.center_l; src_r[3] = x * L.center_r; }
+        if (cfg.src_ext && L.ext) {   // loop mixer and sampler racks: already stereo (ffi.rs:1289-1308)
+#pragma unroll
+          for (int s = 0; s < 5; s++)
+            if ((cfg.src_ext >> s) & 1u) { const float* p = L.ext + (long long)(2u * cfg.ext_row[s]) * L.ext_stride + frame; src_l[4 + s] = p[0]; src_r[4 + s] = p[L.ext_stride]; }
+        }
         for (uint32_t t = 0; t < cfg.n_tracks; t++) {  // graph.rs:344-350, 385-399
           float fl = 0.0f, fr = 0.0f;
 #pragma unroll
           for (int s = 0; s < 5; s++) if (cfg.route[s] == (int32_t)t) { fl += src_l[s]; fr += src_r[s]; }
+          if (cfg.src_ext >> 1) {
+#pragma unroll
+            for (int s = 5; s < 9; s++) if (cfg.route[s] == (int32_t)t) { fl += src_l[s]; fr += src_r[s]; }
+          }
           float gain = sm_tick(st.tr_gain[t], rc.smooth10) * sm_tick(st.tr_mute[t], rc.smooth10);
           fl *= gain; fr *= gain;
           float pan = clampf(sm_tick(st.tr_pan[t], rc.smooth10), 0.0f, 1.0f);
@@ -849,11 +864,14 @@ __global__ void __launch_bounds__(128) mix_prepare_kernel(const MixLaunch L) {
   }
   k.master = st.master.c; k.lim_th = cfg.lim_th; k.lim_inv = cfg.lim_inv;
   k.n_tracks = cfg.n_tracks; k.limiter_on = chain ? 0u : cfg.limiter_on; k.src_poly = cfg.src_poly; k.src_gran = cfg.src_gran;   // the limiter follows the chain
-  for (int s = 0; s < 5; s++) k.route[s] = cfg.route[s];
+  for (int s = 0; s < 9; s++) k.route[s] = cfg.route[s];
+  k.src_ext = L.ext ? cfg.src_ext : 0u;
+  for (int s = 0; s < 5; s++) k.ext_row[s] = cfg.ext_row[s];
   L.consts[i] = k;
 }
 
-__device__ __forceinline__ void mix_fast_frame(const MixConst& k, const float* x, float center_l, float center_r, float& ml, float& mr, float* pk) {
+__device__ __forceinline__ void mix_fast_frame(const MixConst& k, const float* x, const float* ext_l, const float* ext_r, float center_l, float center_r,
+                                               float& ml, float& mr, float* pk) {
   float kit_l = 0.0f, kit_r = 0.0f, bass_l = 0.0f, bass_r = 0.0f;
 #pragma unroll
   for (int c = 0; c < N_VOICE_CH; c++) {
@@ -862,14 +880,22 @@ __device__ __forceinline__ void mix_fast_frame(const MixConst& k, const float* x
     const float pl = v * k.pc[c], pr = v * k.ps[c];
     if (c < 4) { kit_l += pl; kit_r += pr; } else { bass_l += pl; bass_r += pr; }
   }
-  float src_l[5] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f}, src_r[5] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f};
+  float src_l[9] = {kit_l, bass_l, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, src_r[9] = {kit_r, bass_r, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   if (k.src_poly) { src_l[2] = x[5] * center_l; src_r[2] = x[5] * center_r; }
   if (k.src_gran) { src_l[3] = x[6] * center_l; src_r[3] = x[6] * center_r; }
+  if (k.src_ext) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) if ((k.src_ext >> s) & 1u) { src_l[4 + s] = ext_l[s]; src_r[4 + s] = ext_r[s]; }
+  }
   ml = 0.0f; mr = 0.0f;
   for (uint32_t t = 0; t < k.n_tracks; t++) {
     float fl = 0.0f, fr = 0.0f;
 #pragma unroll
     for (int s = 0; s < 5; s++) if (k.route[s] == (int32_t)t) { fl += src_l[s]; fr += src_r[s]; }
+    if (k.src_ext >> 1) {
+#pragma unroll
+      for (int s = 5; s < 9; s++) if (k.route[s] == (int32_t)t) { fl += src_l[s]; fr += src_r[s]; }
+    }
     fl *= k.tgain[t]; fr *= k.tgain[t];
     fl *= k.tbl[t]; fr *= k.tbr[t];
     {
@@ -914,7 +940,13 @@ __global__ void __launch_bounds__(256) mix_fast_kernel(const MixLaunch L) {
 #pragma unroll
     for (int c = 0; c < MIX_CH; c++) xs[c] = x[c][q];
     float junk[N_PEAKS];
-    mix_fast_frame(ks, xs, L.center_l, L.center_r, ol[q], orr[q], q < nf ? pk : junk);
+    float el[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, er[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (ks.src_ext && q < nf) {
+#pragma unroll
+      for (int s = 0; s < 5; s++)
+        if ((ks.src_ext >> s) & 1u) { const float* p = L.ext + (long long)(2u * ks.ext_row[s]) * L.ext_stride + f + q; el[s] = p[0]; er[s] = p[L.ext_stride]; }
+    }
+    mix_fast_frame(ks, xs, el, er, L.center_l, L.center_r, ol[q], orr[q], q < nf ? pk : junk);
   }
   if (L.peaks) {   // maxima of non-negative floats compare like their bit patterns: warp reduce, then one atomic per value
     unsigned* pp = reinterpret_cast<unsigned*>(L.peaks + (size_t)i * N_PEAKS);

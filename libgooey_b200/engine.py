@@ -41,6 +41,19 @@ _SIGS = {
     "blend_set_corner_preset": [c.c_uint32, c.c_uint32, c.c_uint32], "blend_reset_corners": [c.c_uint32],
     "sequencer_set_instrument_step_blend": [c.c_uint32, c.c_uint32, c.c_float, c.c_float],
     "sequencer_clear_instrument_step_blend": [c.c_uint32, c.c_uint32],
+    # loop mixer (ffi.rs:7150-7535)
+    "loop_set_playing": [c.c_uint32, c.c_bool], "loop_set_gain": [c.c_uint32, c.c_float], "loop_set_mute": [c.c_uint32, c.c_bool],
+    "loop_set_solo": [c.c_uint32, c.c_bool], "loop_set_start": [c.c_uint32, c.c_float], "loop_set_end": [c.c_uint32, c.c_float],
+    "loop_set_speed": [c.c_uint32, c.c_float], "loop_set_source_bpm": [c.c_uint32, c.c_float], "loop_set_pitch_mode": [c.c_uint32, c.c_uint32],
+    "loop_restart": [c.c_uint32], "loop_set_position": [c.c_uint32, c.c_float],
+}
+# functions with a return value: name -> (argument types after the handle, result type)
+_RSIGS = {
+    "loop_get_source_bpm": ([c.c_uint32], c.c_float), "loop_get_pitch_mode": ([c.c_uint32], c.c_uint32), "loop_get_position": ([c.c_uint32], c.c_float),
+    "sampler_register": ([], c.c_int32), "sampler_get_source_id": ([c.c_uint32], c.c_uint32),
+    "sampler_clear_slot": ([c.c_uint32, c.c_uint32], c.c_bool), "sampler_slot_is_loaded": ([c.c_uint32, c.c_uint32], c.c_bool),
+    "sampler_slot_frames": ([c.c_uint32, c.c_uint32], c.c_uint32), "sampler_slot_channels": ([c.c_uint32, c.c_uint32], c.c_uint32),
+    "sampler_slot_sample_rate": ([c.c_uint32, c.c_uint32], c.c_float), "sampler_trigger": ([c.c_uint32, c.c_uint32, c.c_float], c.c_bool),
 }
 _bound = set()
 
@@ -53,6 +66,13 @@ def _bind(L, prefix):
         f = getattr(L, prefix + name)
         f.argtypes = [c.c_void_p] + args
         f.restype = None
+    for name, (args, res) in _RSIGS.items():
+        f = getattr(L, prefix + name)
+        f.argtypes = [c.c_void_p] + args
+        f.restype = res
+    f = getattr(L, prefix + "loop_load"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]; f.restype = c.c_bool
+    f = getattr(L, prefix + "loop_render"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_uint32, c.c_void_p]; f.restype = c.c_bool
+    f = getattr(L, prefix + "sampler_set_slot_buffer"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]; f.restype = c.c_bool
     getattr(L, prefix + "new").restype = c.c_void_p
     getattr(L, prefix + "new").argtypes = [c.c_float]
     getattr(L, prefix + "free").argtypes = [c.c_void_p]
@@ -96,10 +116,32 @@ class Engine:
     __del__ = close
 
     def __getattr__(self, name):
-        if name in _SIGS:
+        if name in _SIGS or name in _RSIGS:
             f = getattr(self._L, self._prefix + name)
             return lambda *a: f(self._h, *a)
         raise AttributeError(name)
+
+    # ---- sample-playback sources: the host's decoded PCM as float32 arrays [frames] (mono) or [frames, channels] ----
+    @staticmethod
+    def _pcm(samples):
+        a = np.ascontiguousarray(samples, np.float32)
+        if a.ndim == 1:
+            a = a[:, None]
+        return a, a.shape[0], a.shape[1]
+
+    def loop_load(self, channel, samples, sample_rate):
+        a, frames, channels = self._pcm(samples)
+        return bool(getattr(self._L, self._prefix + "loop_load")(self._h, channel, a.ctypes.data, frames, channels, c.c_float(sample_rate)))
+
+    def loop_render(self, channel, frames, preroll=0):
+        """Mixer::render_channel_to_interleaved: [frames, 2] of one loop channel, offline, from its loop start; None on failure."""
+        out = np.zeros((frames, 2), np.float32)
+        ok = getattr(self._L, self._prefix + "loop_render")(self._h, channel, frames, preroll, out.ctypes.data)
+        return out if ok else None
+
+    def sampler_set_slot_buffer(self, rack, slot, samples, sample_rate):
+        a, frames, channels = self._pcm(samples)
+        return bool(getattr(self._L, self._prefix + "sampler_set_slot_buffer")(self._h, rack, slot, a.ctypes.data, frames, channels, c.c_float(sample_rate)))
 
     def set_effect_order(self, ids):
         arr = (c.c_uint32 * len(ids))(*ids)

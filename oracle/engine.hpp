@@ -9,6 +9,7 @@
 #include "synths.hpp"
 #include "sources.hpp"
 #include "effects.hpp"
+#include "loops.hpp"
 
 namespace orc {
 
@@ -82,13 +83,16 @@ struct MixerGraph {
   int routes[SOURCE_CAPACITY];
   std::vector<StereoFrame> scratch;
   float sample_rate, bpm;
-  MixerGraph(float sr, float b) : sample_rate(sr), bpm(b) { for (int& r : routes) r = -1; }
+  bool active_sources[SOURCE_CAPACITY];               // loop mixer and below always; sampler racks once registered (graph.rs:120, 269-282)
+  MixerGraph(float sr, float b) : sample_rate(sr), bpm(b) { for (int& r : routes) r = -1; for (int i = 0; i < SOURCE_CAPACITY; i++) active_sources[i] = i < 5; }
+  bool register_source(uint32_t src) { if (src >= (uint32_t)SOURCE_CAPACITY) return false; active_sources[src] = true; return true; }
+  bool source_is_active(uint32_t src) const { return src < (uint32_t)SOURCE_CAPACITY && active_sources[src]; }
   size_t add_track() { tracks.emplace_back(sample_rate); scratch.push_back({}); return tracks.size() - 1; }
   void default_layout() { add_track(); add_track(); add_track(); add_track(); route(0, 0); route(1, 1); route(2, 2); route(3, 3); route(4, 3); }
-  bool route(uint32_t src, size_t track) { if (src < 5 && track < tracks.size()) { routes[src] = (int)track; return true; } return false; }
+  bool route(uint32_t src, size_t track) { if (source_is_active(src) && track < tracks.size()) { routes[src] = (int)track; return true; } return false; }
   void set_bpm(float b) { bpm = b; for (auto& t : tracks) for (auto& e : t.rack) e->set_bpm(b); }
   void clear_scratch() { for (auto& s : scratch) s = {}; }
-  void scatter(uint32_t src, StereoFrame f) { if (src < 5 && routes[src] >= 0 && (size_t)routes[src] < scratch.size()) scratch[routes[src]] += f; }
+  void scatter(uint32_t src, StereoFrame f) { if (source_is_active(src) && routes[src] >= 0 && (size_t)routes[src] < scratch.size()) scratch[routes[src]] += f; }
   void update_mute_solo_targets() {
     bool any = false;
     for (auto& t : tracks) any |= t.soloed;
@@ -230,6 +234,8 @@ struct FfiEngine {
   PolySynth poly;
   Granulator granulator;
   MixerGraph graph;
+  LoopMixer mixer;                                   // ffi.rs:768 (`mixer: Mixer`)
+  std::unique_ptr<SamplerRack> samplers[4];          // ffi.rs:770
   std::vector<Lfo> lfos; bool lfo_enabled[8] = {false}; std::vector<LfoRoute> lfo_routes[8]; uint32_t lfo_next_route_id[8] = {0};
   struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
   std::vector<MidiEvent> pending_midi_events;                                                // capacity 64, cleared by every render (:71, :1045)
@@ -238,13 +244,13 @@ struct FfiEngine {
       : sample_rate(sr), delay(sr, 2, 120.0f, 0.0f, 0.0f, 20000.0f), tilt(sr), reverb(sr, 0.5f, 0.0f, 0.5f), plate(sr, 0.5f, 0.0f, 0.5f),
         limiter(1.0f), lowpass(sr, 20000.0f, 0.0f), saturation(sr, 0.3f, 0.4f, 0.5f), compressor(sr, -12.0f, 4.0f, 5.0f, 100.0f, 0.5f),
         waveshaper(1.0f, 0.0f), feedback_waveshaper(sr, 1.0f, 0.0f, 2000.0f, 0.0f),
-        master_gain(0.25f, 0.0f, 2.0f, sr, 30.0f), poly(sr), granulator(sr), graph(sr, 120.0f) {
+        master_gain(0.25f, 0.0f, 2.0f, sr, 30.0f), poly(sr), granulator(sr), graph(sr, 120.0f), mixer(sr) {
     for (uint32_t t = 0; t < 5; t++) voices.emplace_back(make_instrument(t, sr), t, bpm, sr);
     for (int i = 0; i < 8; i++) lfos.emplace_back(sr);
     graph.default_layout();
   }
   VoiceStrip* by_type(uint32_t t) { for (auto& v : voices) if (v.type == t) return &v; return nullptr; }
-  void set_bpm(float b) { bpm = b; for (auto& v : voices) v.seq.set_bpm(b); for (auto& l : lfos) l.bpm = b; delay.set_bpm(b); graph.set_bpm(b); }   // :3337-3364
+  void set_bpm(float b) { bpm = b; for (auto& v : voices) v.seq.set_bpm(b); for (auto& l : lfos) l.bpm = b; delay.set_bpm(b); graph.set_bpm(b); mixer.set_bpm(b); }   // :3337-3364
   void set_swing(float s) { swing = clampf(s, 0.0f, 1.0f); for (auto& v : voices) v.seq.set_swing(swing); }
   void reset_effect_states() { saturation.reset(); lowpass.reset(); tilt.reset(); delay.reset(); compressor.reset(); reverb.reset(); plate.reset(); }  // ffi.rs:1417-1425
   static bool freq_range(uint32_t type, float& mn, float& mx) {  // :1511-1518
@@ -318,7 +324,11 @@ struct FfiEngine {
       graph.scatter(1, bassf);
       graph.scatter(2, polyf);
       graph.scatter(3, granf);
-      graph.scatter(4, StereoFrame{});
+      StereoFrame sampler_frames[4];                 // :1289-1294
+      for (int r = 0; r < 4; r++) if (samplers[r]) sampler_frames[r] = samplers[r]->tick();
+      StereoFrame loop_frame = mixer.tick(sample_rate);   // :1296
+      graph.scatter(4, loop_frame);
+      for (int r = 0; r < 4; r++) graph.scatter(5 + r, sampler_frames[r]);
       StereoFrame st = graph.mix_down();
       st = st.scaled(master_gain.tick());
       for (uint32_t id : effect_order) {

@@ -383,6 +383,75 @@ uint32_t orc_engine_trigger_table(void* e, uint32_t ch, uint32_t frames, uint32_
   for (uint32_t f = 0; f < frames; f++) { SeqTrigger t; if (s.tick(t)) { if (n < cap) { out_frames[n] = f; out_vel[n] = t.velocity; } n++; } }
   return n;
 }
+// ---- loop mixer (ffi.rs:7150-7535, 8006-8048) and sampler racks (ffi.rs:6000-6172) ----------------------------------
+bool orc_engine_loop_load(void* e, uint32_t ch, const float* samples, uint32_t frames, uint32_t channels, float sr) {
+  if (!e || !samples || frames == 0 || channels == 0) return false;
+  auto b = StereoSampleBuffer::from_interleaved(samples, (size_t)frames * channels, channels, sr);
+  if (!b) return false;
+  LoopChannel* c = E->mixer.ch(ch);
+  if (!c) return false;
+  c->set_buffer(b);
+  return true;
+}
+#define LCH(body) do { if (e) { if (LoopChannel* c = E->mixer.ch(ch)) { body; } } } while (0)
+void orc_engine_loop_set_playing(void* e, uint32_t ch, bool v) { LCH(c->playing = v); }
+void orc_engine_loop_set_gain(void* e, uint32_t ch, float v) { LCH(c->set_gain(v)); }
+void orc_engine_loop_set_mute(void* e, uint32_t ch, bool v) { LCH(c->muted = v); }
+void orc_engine_loop_set_solo(void* e, uint32_t ch, bool v) { LCH(c->soloed = v); }
+void orc_engine_loop_set_start(void* e, uint32_t ch, float v) { LCH(c->set_loop_start(v)); }
+void orc_engine_loop_set_end(void* e, uint32_t ch, float v) { LCH(c->set_loop_end(v)); }
+void orc_engine_loop_set_speed(void* e, uint32_t ch, float v) { LCH(c->set_speed(v)); }
+void orc_engine_loop_set_source_bpm(void* e, uint32_t ch, float v) { LCH(if (c->buffer) c->buffer->set_source_bpm(v > 0.0f, v)); }
+void orc_engine_loop_set_pitch_mode(void* e, uint32_t ch, uint32_t m) { LCH(c->pitch_mode = (m == 1 ? PITCH_RESAMPLE : (m == 2 ? PITCH_PRESERVE : PITCH_OFF))); }
+void orc_engine_loop_restart(void* e, uint32_t ch) { LCH(c->restart()); }
+void orc_engine_loop_set_position(void* e, uint32_t ch, float v) { LCH(c->set_position(v)); }
+#undef LCH
+float orc_engine_loop_get_source_bpm(void* e, uint32_t ch) { if (!e) return 0.0f; LoopChannel* c = E->mixer.ch(ch); return (c && c->buffer && c->buffer->has_source_bpm) ? c->buffer->source_bpm : 0.0f; }
+uint32_t orc_engine_loop_get_pitch_mode(void* e, uint32_t ch) { if (!e) return 0; LoopChannel* c = E->mixer.ch(ch); return c ? (uint32_t)c->pitch_mode : 0u; }
+float orc_engine_loop_get_position(void* e, uint32_t ch) { if (!e) return 0.0f; LoopChannel* c = E->mixer.ch(ch); return c ? c->position_normalized() : 0.0f; }
+// render_channel_to_interleaved (mixer/mod.rs:444-476), the audio gooey_engine_loop_render_to_wav writes as 32-bit float stereo
+bool orc_engine_loop_render(void* e, uint32_t ch, uint32_t frames, uint32_t preroll, float* out) {
+  if (!e || !out || frames == 0) return false;
+  std::vector<float> v;
+  if (!E->mixer.render_channel_to_interleaved(ch, frames, preroll, v)) return false;
+  memcpy(out, v.data(), v.size() * sizeof(float));
+  return true;
+}
+int32_t orc_engine_sampler_register(void* e) {
+  if (!e) return -1;
+  for (int i = 0; i < 4; i++)
+    if (!E->samplers[i]) { E->samplers[i] = std::make_unique<SamplerRack>(E->sample_rate); E->graph.register_source(5 + i); return i; }
+  return -1;
+}
+uint32_t orc_engine_sampler_get_source_id(void* e, uint32_t rack) { return (e && rack < 4 && E->samplers[rack]) ? 5u + rack : 0xFFFFFFFFu; }
+bool orc_engine_sampler_set_slot_buffer(void* e, uint32_t rack, uint32_t slot, const float* s, uint32_t frames, uint32_t channels, float sr) {
+  if (!e || !s) return false;
+  auto b = SamplerBuffer::from_interleaved(s, frames, channels, sr);
+  if (!b || rack >= 4 || !E->samplers[rack]) return false;
+  return E->samplers[rack]->set_buffer(slot, b);
+}
+bool orc_engine_sampler_clear_slot(void* e, uint32_t rack, uint32_t slot) { return e && rack < 4 && E->samplers[rack] && E->samplers[rack]->clear_slot(slot); }
+bool orc_engine_sampler_slot_is_loaded(void* e, uint32_t rack, uint32_t slot) { return e && rack < 4 && E->samplers[rack] && slot < 16 && E->samplers[rack]->slots[slot]; }
+uint32_t orc_engine_sampler_slot_frames(void* e, uint32_t rack, uint32_t slot) { return orc_engine_sampler_slot_is_loaded(e, rack, slot) ? (uint32_t)E->samplers[rack]->slots[slot]->frames : 0u; }
+uint32_t orc_engine_sampler_slot_channels(void* e, uint32_t rack, uint32_t slot) { return orc_engine_sampler_slot_is_loaded(e, rack, slot) ? (uint32_t)E->samplers[rack]->slots[slot]->channels : 0u; }
+float orc_engine_sampler_slot_sample_rate(void* e, uint32_t rack, uint32_t slot) { return orc_engine_sampler_slot_is_loaded(e, rack, slot) ? E->samplers[rack]->slots[slot]->sample_rate : 0.0f; }
+bool orc_engine_sampler_trigger(void* e, uint32_t rack, uint32_t slot, float vel) { return e && rack < 4 && E->samplers[rack] && E->samplers[rack]->trigger(slot, vel); }
+// test hooks: the loop mixer / one sampler rack ticked on their own (what the product's ext_source_kernel computes per descriptor)
+void orc_engine_loop_mixer_tick(void* e, uint32_t frames, float* out_interleaved) {
+  if (!e || !out_interleaved) return;
+  for (uint32_t f = 0; f < frames; f++) { StereoFrame s = E->mixer.tick(E->sample_rate); out_interleaved[2 * f] = s.l; out_interleaved[2 * f + 1] = s.r; }
+}
+void orc_engine_sampler_rack_tick(void* e, uint32_t rack, uint32_t frames, float* out_interleaved) {
+  if (!e || !out_interleaved || rack >= 4 || !E->samplers[rack]) return;
+  for (uint32_t f = 0; f < frames; f++) { StereoFrame s = E->samplers[rack]->tick(); out_interleaved[2 * f] = s.l; out_interleaved[2 * f + 1] = s.r; }
+}
+uint32_t orc_engine_sampler_active_voices(void* e, uint32_t rack) {
+  if (!e || rack >= 4 || !E->samplers[rack]) return 0;
+  uint32_t n = 0;
+  for (auto& v : E->samplers[rack]->voices) n += v.active();
+  return n;
+}
+double orc_engine_loop_get_cursor(void* e, uint32_t ch) { if (!e) return 0.0; LoopChannel* c = E->mixer.ch(ch); return c ? c->cursor : 0.0; }
 #undef E
 
 // ---- Rust-API engine (engine/mod.rs + bounce.rs): instruments by type with optional config, one sequencer each ----

@@ -258,3 +258,46 @@ int emu_math(int kind, const float* a, const float* b, float sr, float* out, uin
 }
 
 }  // extern "C"
+
+// ---- sample-playback sources (libgooey_b200/csrc/loops.cuh): the loop mixer and the sampler rack ticks on the host ----------
+#include "../../libgooey_b200/csrc/loops.cuh"
+extern "C" {
+// One LoopMixer descriptor driven for `frames` frames, exactly like ext_source_kernel<LoopMixer> drives it.  Per-channel arrays
+// of 4; left[k] == nullptr: nothing loaded.  cursor / gain_ct / active_ct ([4][2] = current, target) are read and written back.
+int emu_loop_mixer(const float* const* left, const float* const* right, const uint32_t* len, const float* buf_sr, double* cursor, const double* warp,
+                   const float* loop_start, const float* loop_end, const float* speed, const uint32_t* playing, float* gain_ct, float* active_ct,
+                   float engine_sr, int frames, float* out_l, float* out_r) {
+  LoopMixer m;
+  memset(&m, 0, sizeof m);
+  for (int k = 0; k < LOOP_CHANNELS; k++) {
+    LoopChan& c = m.ch[k];
+    c.left = left[k]; c.right = right[k]; c.len = len[k]; c.buf_sr = buf_sr[k]; c.cursor = cursor[k]; c.warp = warp[k];
+    c.loop_start = loop_start[k]; c.loop_end = loop_end[k]; c.speed = speed[k]; c.playing = playing[k];
+    c.gain = {gain_ct[2 * k], gain_ct[2 * k + 1]}; c.active = {active_ct[2 * k], active_ct[2 * k + 1]};
+  }
+  const float coeff15 = smooth_coeff(engine_sr, LOOP_FADER_MS);
+  for (int f = 0; f < frames; f++) loop_mixer_tick(m, engine_sr, coeff15, out_l[f], out_r[f]);
+  for (int k = 0; k < LOOP_CHANNELS; k++) {
+    cursor[k] = m.ch[k].cursor;
+    gain_ct[2 * k] = m.ch[k].gain.c; gain_ct[2 * k + 1] = m.ch[k].gain.t; active_ct[2 * k] = m.ch[k].active.c; active_ct[2 * k + 1] = m.ch[k].active.t;
+  }
+  return 0;
+}
+double emu_window_fold(float loop_start, float loop_end, double len, double p) { return window_fold(loop_window(loop_start, loop_end, len), p); }
+double emu_window_lo(float loop_start, float loop_end, double len) { return loop_window(loop_start, loop_end, len).lo; }
+// One SamplerRack descriptor: n_voices (<= 32) voices started at position 0 (voice v plays pads[v], frames[v] x channels[v], increment inc[v],
+// velocity vel[v]); returns the number of voices still sounding after `n` frames.
+int emu_sampler_rack(int n_voices, const float* const* pads, const uint32_t* frames, const uint32_t* channels, const double* inc, const float* vel,
+                     const double* start_pos, int n, float* out_l, float* out_r) {
+  SamplerRack r;
+  memset(&r, 0, sizeof r);
+  for (int v = 0; v < n_voices && v < SAMPLER_VOICES; v++) {
+    SampleVoice& s = r.v[v];
+    s.samples = pads[v]; s.frames = frames[v]; s.channels = channels[v]; s.increment = inc[v]; s.velocity = vel[v]; s.position = start_pos[v]; s.age = v + 1;
+  }
+  for (int f = 0; f < n; f++) sampler_rack_tick(r, out_l[f], out_r[f]);
+  int alive = 0;
+  for (int v = 0; v < SAMPLER_VOICES; v++) alive += r.v[v].samples != nullptr;
+  return alive;
+}
+}

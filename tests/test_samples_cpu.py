@@ -1,0 +1,377 @@
+"""Sample-playback sources on the CPU.
+
+1. The reference's own unit tests of mixer/loop_channel.rs, mixer/stereo_buffer.rs, mixer/mod.rs and instruments/sampler.rs,
+   restated against the oracle (oracle/loops.hpp) — the pins this path has (the reference holds no golden audio for it).
+2. The product's device functions (libgooey_b200/csrc/loops.cuh, compiled for the host by tests/emu) against the oracle's
+   loop mixer and sampler rack, bit for bit, on random playback states: forward / reverse varispeed, sample-rate conversion,
+   interior and wrap-around loop windows, gliding faders and gates, tempo warp, layered and expiring sampler voices.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import emu_lib as EMU
+import oracle_lib as O
+
+SR = 44100.0
+c = ctypes
+
+
+def ramp(frames):
+    return np.arange(frames, dtype=np.float32)
+
+
+def dc(value, frames):
+    return np.full(frames, value, np.float32)
+
+
+def tick(e, frames):
+    """LoopMixer::tick on its own, `frames` times: [frames, 2]."""
+    out = np.zeros((frames, 2), np.float32)
+    L = O.lib()
+    L.orc_engine_loop_mixer_tick.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p]
+    L.orc_engine_loop_mixer_tick.restype = None
+    L.orc_engine_loop_mixer_tick(e._h, frames, out.ctypes.data)
+    return out
+
+
+def rack_tick(e, rack, frames):
+    out = np.zeros((frames, 2), np.float32)
+    L = O.lib()
+    L.orc_engine_sampler_rack_tick.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_void_p]
+    L.orc_engine_sampler_rack_tick.restype = None
+    L.orc_engine_sampler_rack_tick(e._h, rack, frames, out.ctypes.data)
+    return out
+
+
+def cursor(e, ch):
+    L = O.lib()
+    L.orc_engine_loop_get_cursor.argtypes = [c.c_void_p, c.c_uint32]
+    L.orc_engine_loop_get_cursor.restype = c.c_double
+    return L.orc_engine_loop_get_cursor(e._h, ch)
+
+
+@pytest.fixture
+def e():
+    eng = O.oracle_engine()
+    yield eng
+    eng.close()
+
+
+# ---- mixer/loop_channel.rs mod tests ------------------------------------------------------------------------------------
+def test_silent_until_playing(e):                                   # :634
+    assert e.loop_load(0, ramp(100), SR)
+    assert np.array_equal(tick(e, 1), np.zeros((1, 2), np.float32))
+
+
+def test_cursor_wraps_within_loop_window(e):                        # :642
+    e.loop_load(0, ramp(10), SR)
+    e.loop_set_start(0, 0.0); e.loop_set_end(0, 0.5); e.loop_set_playing(0, True)
+    for _ in range(50):
+        tick(e, 1)
+        assert e.loop_get_position(0) < 0.5 + 1e-3
+
+
+def test_set_buffer_starts_at_loop_start(e):                        # :656
+    e.loop_set_start(0, 0.5); e.loop_set_end(0, 1.0)
+    e.loop_load(0, ramp(100), SR)
+    assert abs(e.loop_get_position(0) - 0.5) < 1e-3
+
+
+def test_set_position_round_trips_and_clamps_into_window(e):        # :666, :674
+    e.loop_load(0, ramp(100), SR)
+    e.loop_set_position(0, 0.42)
+    assert abs(e.loop_get_position(0) - 0.42) < 1e-2
+    e.loop_set_start(0, 0.25); e.loop_set_end(0, 0.75)
+    e.loop_set_position(0, 0.9)
+    assert e.loop_get_position(0) <= 0.75 + 1e-6
+    e.loop_set_position(0, 0.1)
+    assert e.loop_get_position(0) >= 0.25 - 1e-6
+
+
+def test_reverse_playback_stays_in_window(e):                       # :687
+    e.loop_load(0, ramp(20), SR)
+    e.loop_set_start(0, 0.25); e.loop_set_end(0, 0.75); e.loop_set_speed(0, -1.0); e.loop_set_playing(0, True)
+    for _ in range(100):
+        tick(e, 1)
+        assert 0.25 <= e.loop_get_position(0) < 0.75 + 1e-2
+
+
+def settle_then(e, script, frames):
+    """The fader and the gate start settled at 1, so the first ticks are the raw reads."""
+    script()
+    return tick(e, frames)
+
+
+def test_wrapped_window_plays_union(e):                             # :792 — exact values
+    e.loop_set_start(0, 0.75); e.loop_set_end(0, 0.25)
+    e.loop_load(0, ramp(8), SR)
+    e.loop_set_playing(0, True)
+    out = tick(e, 16)
+    assert np.array_equal(out[:, 0], np.tile(np.float32([6, 7, 0, 1]), 4))
+
+
+def test_non_wrapped_interior_window_exact_sequence(e):             # :808 — exact values
+    e.loop_set_start(0, 0.25); e.loop_set_end(0, 0.5)
+    e.loop_load(0, ramp(8), SR)
+    e.loop_set_playing(0, True)
+    out = tick(e, 16)
+    assert np.array_equal(out[:, 0], np.tile(np.float32([2, 3]), 8))
+
+
+def test_wrapped_window_reverse_stays_in_union(e):                  # :824
+    e.loop_set_start(0, 0.7); e.loop_set_end(0, 0.3)
+    e.loop_load(0, ramp(10), SR)
+    e.loop_set_speed(0, -1.0); e.loop_set_playing(0, True)
+    for _ in range(200):
+        tick(e, 1)
+        p = e.loop_get_position(0)
+        assert not (0.3 + 1e-3 <= p <= 0.7 - 1e-3), p
+
+
+def test_set_position_folds_into_wrapped_window(e):                 # :842
+    e.loop_set_start(0, 0.7); e.loop_set_end(0, 0.3)
+    e.loop_load(0, ramp(10), SR)
+    for pos, want in ((0.1, 0.1), (0.9, 0.9), (0.45, 0.3), (0.55, 0.7)):
+        e.loop_set_position(0, pos)
+        assert abs(e.loop_get_position(0) - want) < 1e-6
+
+
+def test_degenerate_wrapped_window_is_clamped(e):                   # :874
+    e.loop_set_start(0, 0.9); e.loop_set_end(0, 0.1)
+    e.loop_load(0, ramp(4), SR)
+    e.loop_set_playing(0, True)
+    out = tick(e, 200)
+    assert np.isfinite(out).all() and np.isfinite(e.loop_get_position(0))
+
+
+# ---- mixer/stereo_buffer.rs mod tests -----------------------------------------------------------------------------------
+def test_from_interleaved_mono_and_stereo(e):                       # :267, :276
+    e.loop_load(0, np.float32([0.1, 0.2, 0.3]), SR)
+    e.loop_set_playing(0, True)
+    out = tick(e, 3)
+    assert np.array_equal(out[:, 0], out[:, 1]) and np.allclose(out[:, 0], [0.1, 0.2, 0.3], atol=1e-7)
+    st = np.float32([[1.0, -1.0], [0.5, -0.5]])
+    e.loop_load(1, st, SR)
+    e.loop_set_playing(0, False); e.loop_set_playing(1, True)
+    out = tick(e, 2)
+    assert np.array_equal(out, st)
+
+
+def test_non_finite_and_bad_rate_rejected(e):                       # :293
+    assert not e.loop_load(0, np.float32([0.0, np.nan]), SR)
+    assert not e.loop_load(0, np.float32([0.0, 1.0]), 0.0)
+    assert not e.loop_load(7, np.float32([0.0, 1.0]), SR)
+
+
+# ---- mixer/mod.rs mod tests ---------------------------------------------------------------------------------------------
+def test_muted_channel_drops_out_after_smoothing(e):                # :497
+    e.loop_load(0, dc(0.5, 64), SR); e.loop_set_playing(0, True)
+    tick(e, 4096)
+    assert abs(tick(e, 1)[0, 0]) > 0.1
+    e.loop_set_mute(0, True)
+    tick(e, 4096)
+    assert abs(tick(e, 1)[0, 0]) < 5e-3
+
+
+def test_solo_silences_other_channels(e):                           # :519
+    for ch in (0, 1):
+        e.loop_load(ch, dc(0.5, 64), SR); e.loop_set_playing(ch, True)
+    e.loop_set_solo(0, True)
+    tick(e, 4096)
+    assert abs(tick(e, 1)[0, 0] - 0.5) < 0.05
+
+
+def test_render_channel_frame_count_rejects_and_region(e):          # :555, :564, :576
+    e.loop_load(0, dc(0.5, 4096), SR)
+    assert e.loop_render(0, 1000, 512).shape == (1000, 2)
+    assert e.loop_render(99, 100) is None and e.loop_render(1, 100) is None
+    e.loop_load(0, ramp(400), SR)
+    e.loop_set_start(0, 0.0); e.loop_set_end(0, 0.25)
+    out = e.loop_render(0, 350)
+    assert np.abs(out[:, 0] - (np.arange(350) % 100)).max() < 1e-3
+
+
+def test_render_channel_applies_gain_and_ignores_mute_solo(e):      # :597, :612
+    e.loop_load(0, dc(0.5, 4096), SR)
+    e.loop_set_gain(0, 0.5)
+    assert abs(e.loop_render(0, 256, 128)[0, 0] - 0.25) < 1e-3
+    e.loop_set_gain(0, 1.0)
+    e.loop_load(1, dc(-0.9, 4096), SR)
+    e.loop_set_mute(0, True); e.loop_set_solo(1, True)
+    assert abs(e.loop_render(0, 256, 128)[0, 0] - 0.5) < 1e-3
+
+
+# ---- instruments/sampler.rs mod tests -----------------------------------------------------------------------------------
+def test_sampler_stereo_buffer_is_interpolated_and_preserved(e):    # :335 (through a voice: position 0.5 needs increment 0.5)
+    r = e.sampler_register()
+    assert r == 0 and e.sampler_get_source_id(0) == 5 and e.sampler_get_source_id(1) == 0xFFFFFFFF
+    long = np.zeros((200, 2), np.float32); long[:, 0] = np.arange(200); long[:, 1] = -np.arange(200)
+    assert e.sampler_set_slot_buffer(0, 3, long, SR / 2)
+    assert e.sampler_slot_is_loaded(0, 3) and e.sampler_slot_frames(0, 3) == 200 and e.sampler_slot_channels(0, 3) == 2
+    assert e.sampler_slot_sample_rate(0, 3) == SR / 2
+    assert e.sampler_trigger(0, 3, 1.0) and not e.sampler_trigger(0, 4, 1.0)
+    out = rack_tick(e, 0, 101)
+    # past the 32-frame fade-in the voice is the linear read at position f / 2
+    assert np.allclose(out[80:101, 0], np.arange(80, 101) / 2, atol=1e-5) and np.allclose(out[80:101, 1], -np.arange(80, 101) / 2, atol=1e-5)
+
+
+def test_rack_layers_and_steals_without_non_finite_audio(e):        # :343
+    e.sampler_register()
+    e.sampler_set_slot_buffer(0, 0, dc(0.5, 256), 22050.0)
+    for _ in range(32 + 4):
+        assert e.sampler_trigger(0, 0, 1.0)
+    assert np.isfinite(rack_tick(e, 0, 32)).all()
+
+
+# ---- device functions (host build) against the oracle, bit for bit --------------------------------------------------------
+def emu_loop_mixer(chans, engine_sr, frames):
+    """chans: 4 dicts (or None) with left, right, buf_sr, cursor, warp, start, end, speed, playing, gain (c, t), active (c, t)."""
+    L = EMU.lib()
+    fp = c.POINTER(c.c_float)
+    left = (fp * 4)(); right = (fp * 4)()
+    ln = np.zeros(4, np.uint32); bsr = np.zeros(4, np.float32); cur = np.zeros(4, np.float64); warp = np.ones(4, np.float64)
+    st = np.zeros(4, np.float32); en = np.ones(4, np.float32); sp = np.ones(4, np.float32); pl = np.zeros(4, np.uint32)
+    g = np.ones((4, 2), np.float32); a = np.ones((4, 2), np.float32)
+    keep = []
+    for k, ch in enumerate(chans):
+        if ch is None:
+            continue
+        if ch.get("left") is not None:
+            l = np.ascontiguousarray(ch["left"], np.float32); r = np.ascontiguousarray(ch["right"], np.float32)
+            keep += [l, r]
+            left[k] = l.ctypes.data_as(fp); right[k] = r.ctypes.data_as(fp); ln[k] = len(l)
+        bsr[k] = ch.get("buf_sr", 0.0); cur[k] = ch.get("cursor", 0.0); warp[k] = ch.get("warp", 1.0)
+        st[k] = ch.get("start", 0.0); en[k] = ch.get("end", 1.0); sp[k] = ch.get("speed", 1.0); pl[k] = 1 if ch.get("playing") else 0
+        g[k] = ch.get("gain", (1.0, 1.0)); a[k] = ch.get("active", (1.0, 1.0))
+    ol = np.zeros(frames, np.float32); orr = np.zeros(frames, np.float32)
+    p = lambda arr, t: arr.ctypes.data_as(c.POINTER(t))
+    L.emu_loop_mixer(left, right, p(ln, c.c_uint32), p(bsr, c.c_float), p(cur, c.c_double), p(warp, c.c_double), p(st, c.c_float), p(en, c.c_float),
+                     p(sp, c.c_float), p(pl, c.c_uint32), p(g, c.c_float), p(a, c.c_float), c.c_float(engine_sr), frames, p(ol, c.c_float), p(orr, c.c_float))
+    return np.stack([ol, orr], 1), cur, g, a
+
+
+def window_lo(start, end, n):
+    L = EMU.lib()
+    L.emu_window_lo.restype = c.c_double
+    L.emu_window_lo.argtypes = [c.c_float, c.c_float, c.c_double]
+    return L.emu_window_lo(start, end, float(n))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_device_loop_mixer_matches_oracle_bit_for_bit(seed):
+    rng = np.random.default_rng(1000 + seed)
+    engine_sr = [44100.0, 48000.0, 22050.0][seed % 3]
+    o = O.oracle_engine(engine_sr)
+    chans = [None] * 4
+    for k in range(4):
+        if rng.random() < 0.2:
+            continue                                   # channel left empty
+        n = int(rng.integers(1, 3000)) if rng.random() < 0.9 else 1
+        pcm = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        buf_sr = float(rng.choice([44100.0, 48000.0, 32000.0, 96000.0]))
+        assert o.loop_load(k, pcm, buf_sr)
+        start, end = (float(np.float32(x)) for x in rng.uniform(0, 1, 2))
+        if rng.random() < 0.3:
+            start, end = 0.0, 1.0
+        speed = float(np.float32(rng.uniform(-4, 4))) if rng.random() < 0.7 else 1.0
+        o.loop_set_start(k, start); o.loop_set_end(k, end); o.loop_set_speed(k, speed)
+        o.loop_restart(k)
+        playing = rng.random() < 0.85
+        o.loop_set_playing(k, bool(playing))
+        gain_t = float(np.float32(rng.uniform(0, 2))) if rng.random() < 0.6 else 1.0
+        o.loop_set_gain(k, gain_t)
+        muted = rng.random() < 0.25
+        o.loop_set_mute(k, bool(muted))
+        warp = 1.0
+        if rng.random() < 0.4:
+            src_bpm = float(np.float32(rng.uniform(70, 170)))
+            o.loop_set_source_bpm(k, src_bpm); o.loop_set_pitch_mode(k, 1)
+            warp = float(np.float32(133.0)) / src_bpm
+        chans[k] = dict(left=pcm[:, 0], right=pcm[:, 1], buf_sr=buf_sr, cursor=window_lo(start, end, n), warp=warp, start=start, end=end, speed=speed,
+                        playing=playing, gain=(1.0, gain_t), active=(1.0, 0.0 if muted else 1.0))
+    o.set_bpm(133.0)
+    frames = 6000
+    want = tick(o, frames)
+    got, cur, g, a = emu_loop_mixer([ch if ch is not None else None for ch in chans], engine_sr, frames)
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    for k in range(4):
+        if chans[k] is not None:
+            assert cur[k] == cursor(o, k)
+    o.close()
+
+
+def test_device_loop_mixer_second_call_continues_state():
+    """Two calls with the state carried over equal one long call (what engines_render does piece by piece and call by call)."""
+    rng = np.random.default_rng(7)
+    pcm = rng.uniform(-1, 1, (777, 2)).astype(np.float32)
+    ch = dict(left=pcm[:, 0], right=pcm[:, 1], buf_sr=48000.0, cursor=window_lo(0.8, 0.3, 777), start=0.8, end=0.3, speed=-1.37, playing=True,
+              gain=(1.0, 0.4), active=(1.0, 0.0))
+    whole, _, _, _ = emu_loop_mixer([ch, None, None, None], 44100.0, 5000)
+    a, cur, g, act = emu_loop_mixer([ch, None, None, None], 44100.0, 1234)
+    ch2 = dict(ch, cursor=cur[0], gain=tuple(g[0]), active=tuple(act[0]))
+    b, _, _, _ = emu_loop_mixer([ch2, None, None, None], 44100.0, 5000 - 1234)
+    assert np.array_equal(np.concatenate([a, b]), whole)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_device_sampler_rack_matches_oracle_bit_for_bit(seed):
+    rng = np.random.default_rng(2000 + seed)
+    engine_sr = [44100.0, 48000.0][seed % 2]
+    o = O.oracle_engine(engine_sr)
+    assert o.sampler_register() == 0
+    pads = []
+    for slot in range(5):
+        n = int(rng.integers(1, 1500))
+        chn = int(rng.integers(1, 3))
+        pcm = rng.uniform(-1, 1, (n, chn)).astype(np.float32)
+        sr = float(rng.choice([44100.0, 22050.0, 48000.0, 11025.0]))
+        assert o.sampler_set_slot_buffer(0, slot, pcm, sr)
+        pads.append((pcm, sr))
+    n_hits = int(rng.integers(1, 33))                      # all at the start of the call: voices 0 .. n_hits - 1 in order
+    hits = [(int(rng.integers(0, 5)), float(np.float32(rng.uniform(-0.2, 1.3)))) for _ in range(n_hits)]
+    for slot, vel in hits:
+        assert o.sampler_trigger(0, slot, vel)
+    frames = 4000
+    want = rack_tick(o, 0, frames)
+    L = EMU.lib()
+    fp = c.POINTER(c.c_float)
+    ptrs = (fp * n_hits)()
+    fr = np.zeros(n_hits, np.uint32); chs = np.zeros(n_hits, np.uint32); inc = np.zeros(n_hits, np.float64); vel = np.zeros(n_hits, np.float32)
+    pos = np.zeros(n_hits, np.float64)
+    for v, (slot, ve) in enumerate(hits):
+        pcm, sr = pads[slot]
+        ptrs[v] = pcm.ctypes.data_as(fp); fr[v] = pcm.shape[0]; chs[v] = pcm.shape[1]
+        inc[v] = float(np.float32(sr)) / float(np.float32(engine_sr)); vel[v] = min(max(ve, 0.0), 1.0)
+    ol = np.zeros(frames, np.float32); orr = np.zeros(frames, np.float32)
+    p = lambda arr, t: arr.ctypes.data_as(c.POINTER(t))
+    alive = L.emu_sampler_rack(n_hits, ptrs, p(fr, c.c_uint32), p(chs, c.c_uint32), p(inc, c.c_double), p(vel, c.c_float), p(pos, c.c_double), frames,
+                               p(ol, c.c_float), p(orr, c.c_float))
+    got = np.stack([ol, orr], 1)
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    O.lib().orc_engine_sampler_active_voices.argtypes = [c.c_void_p, c.c_uint32]
+    assert alive == O.lib().orc_engine_sampler_active_voices(o._h, 0)
+    assert np.abs(want).max() > 0.05
+    o.close()
+
+
+def test_loop_source_reaches_the_engine_mix_on_the_loops_track():
+    """ffi.rs:1296-1308: the loop mixer is graph source 4 (default track 3); a sampler rack sounds once it is routed."""
+    o = O.oracle_engine()
+    silent = o.render(256)
+    assert np.abs(silent).max() == 0.0
+    o.loop_load(0, dc(0.5, 64), SR); o.loop_set_playing(0, True)
+    out = o.render(2048)
+    assert abs(out[-1, 0] - 0.5 * 0.25) < 1e-3                 # unity strip, centre balance, master gain 0.25
+    o.mixer_set_track_mute(3, True)
+    assert abs(o.render(4096)[-1, 0]) < 1e-3
+    assert o.sampler_register() == 0
+    o.sampler_set_slot_buffer(0, 0, dc(0.8, 4000), SR)
+    assert not o.mixer_route_source(6, 0)                      # rack 1 is not registered
+    o.sampler_trigger(0, 0, 1.0)
+    assert np.abs(o.render(512)).max() < 1e-3                  # registered racks start unrouted
+    assert o.mixer_route_source(5, 0)
+    out = o.render(512)
+    assert abs(out[-1, 0] - 0.8 * 0.25) < 1e-3
+    o.close()
