@@ -1,0 +1,243 @@
+"""Sample-playback sources on the GPU: the loop mixer and the sampler racks of the product, through the C ABI
+(gooey_engine_loop_* / gooey_engine_sampler_*), against the oracle running the same call script.  Comparisons with drum voices in
+the mix are held to the repo's audio bar (1e-5, the voices set it); where only the sample-playback path sounds the bar is EXACT_TOL:
+its arithmetic is IEEE f32 / f64 adds, multiplies, divisions and fmod in the reference's order (tests/test_samples_cpu.py holds the
+same device functions, compiled for the host, to bit-identity with the oracle), so anything above rounding noise is a logic error."""
+import ctypes
+import struct
+
+import numpy as np
+import pytest
+
+from libgooey_b200 import engine as G
+import oracle_lib as O
+import engine_scripts as S
+from test_ffi_surface_gpu import busy_pattern
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+EXACT_TOL = 1e-6
+c = ctypes
+
+
+def pcm(seed, frames, channels=2):
+    rng = np.random.default_rng(seed)
+    t = np.arange(frames)[:, None] / 44100.0
+    tone = 0.4 * np.sin(2 * np.pi * (110.0 * (1 + np.arange(channels))[None, :]) * t)
+    return (tone + rng.uniform(-0.3, 0.3, (frames, channels))).astype(np.float32)
+
+
+def both(script, run):
+    o = O.oracle_engine()
+    g = G.Engine()
+    script(o); script(g)
+    want, got = run(o), run(g)
+    assert not g.has_error(), g.get_error_message()
+    o.close(); g.close()
+    return got, want
+
+
+def test_loop_on_the_loops_track_with_the_kit_playing():
+    def script(e):
+        busy_pattern(e)
+        e.loop_load(0, pcm(1, 3000), 48000.0)
+        e.loop_set_start(0, 0.2); e.loop_set_end(0, 0.9); e.loop_set_speed(0, 0.8); e.loop_set_gain(0, 0.7)
+        e.loop_set_playing(0, True)
+        e.loop_load(2, pcm(2, 1777, channels=1), 32000.0)
+        e.loop_set_playing(2, True)
+        e.mixer_set_track_pan(3, 0.3)
+        e.sequencer_start()
+    got, want = both(script, lambda e: e.render(20000))
+    assert np.abs(want).max() > 0.05
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_loops_alone_through_the_whole_mix():
+    """No voice sounds: the output is loop mixer -> Loops track strip -> master gain (settled), all exact f32 products."""
+    def script(e):
+        e.loop_load(1, pcm(3, 2500), 44100.0)
+        e.loop_set_start(1, 0.8); e.loop_set_end(1, 0.3); e.loop_set_speed(1, -1.37)      # wrap-around window, reverse
+        e.loop_set_playing(1, True)
+        e.loop_load(3, pcm(4, 900), 96000.0)
+        e.loop_set_gain(3, 1.6); e.loop_set_playing(3, True)
+    got, want = both(script, lambda e: np.concatenate([e.render(5000), e.render(3000)]))
+    assert np.abs(want).max() > 0.05
+    assert np.abs(got - want).max() <= EXACT_TOL
+
+
+def test_mute_solo_gates_and_edits_between_render_calls():
+    def run(e):
+        a = e.render(4000)
+        e.loop_set_mute(0, True); e.loop_set_gain(1, 0.25); e.loop_set_speed(1, 2.5)
+        b = e.render(4000)
+        e.loop_set_solo(0, True)                        # solo wins over mute (mod.rs:63-72)
+        e.loop_set_position(1, 0.5); e.loop_restart(0)
+        cc = e.render(4000)
+        e.loop_set_playing(1, False)
+        d = e.render(1000)
+        return np.concatenate([a, b, cc, d]), [e.loop_get_position(k) for k in range(4)]
+
+    def script(e):
+        e.loop_load(0, pcm(5, 2000), 44100.0); e.loop_set_playing(0, True)
+        e.loop_load(1, pcm(6, 4000), 22050.0); e.loop_set_start(1, 0.25); e.loop_set_end(1, 0.75); e.loop_set_playing(1, True)
+    (got, gpos), (want, wpos) = both(script, run)
+    assert np.abs(want).max() > 0.05
+    assert np.abs(got - want).max() <= EXACT_TOL
+    assert np.allclose(gpos, wpos, atol=1e-6)
+
+
+def test_resample_warp_follows_the_engine_tempo():
+    def script(e):
+        e.loop_load(0, pcm(7, 5000), 44100.0)
+        e.loop_set_source_bpm(0, 100.0); e.loop_set_pitch_mode(0, 1)
+        e.set_bpm(133.0)
+        e.loop_set_playing(0, True)
+    got, want = both(script, lambda e: (e.render(6000), e.loop_get_source_bpm(0), e.loop_get_pitch_mode(0)))
+    assert got[1:] == want[1:] == (100.0, 1)
+    assert np.abs(got[0] - want[0]).max() <= EXACT_TOL
+
+
+def test_bounce_with_loops_many_pieces_and_a_global_chain():
+    """One bar = 88 200 frames: the lead pieces, double-buffered rows, the time-parallel strips feeding the chain kernel."""
+    def script(e):
+        busy_pattern(e)
+        S.fx_chain(e, 11)
+        e.loop_load(0, pcm(8, 30000), 44100.0); e.loop_set_playing(0, True)
+        e.loop_load(1, pcm(9, 7000, channels=1), 48000.0); e.loop_set_speed(1, -0.5); e.loop_set_playing(1, True)
+    got, want = both(script, lambda e: e.bounce_to_buffer(1))
+    assert got.shape == want.shape == (88200,)
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_loop_through_a_track_rack_effect():
+    def script(e):
+        e.loop_load(0, pcm(10, 6000), 44100.0); e.loop_set_playing(0, True)
+        slot = e.track_effect_add(3, 1)                  # delay on the Loops track
+        e.track_effect_set_param(3, slot, 1, 0.5); e.track_effect_set_param(3, slot, 2, 0.5)
+    got, want = both(script, lambda e: e.render(30000))
+    assert np.abs(got - want).max() <= TOL
+
+
+def test_offline_channel_render_and_the_float_wav(tmp_path):
+    def script(e):
+        e.loop_load(2, pcm(12, 4096), 48000.0)
+        e.loop_set_start(2, 0.1); e.loop_set_end(2, 0.6); e.loop_set_gain(2, 0.5)
+        e.loop_set_mute(2, True)                        # ignored by the offline render
+    got, want = both(script, lambda e: (e.loop_render(2, 10000, 512), e.loop_render(0, 16)))
+    assert got[1] is None and want[1] is None
+    assert np.abs(got[0] - want[0]).max() <= EXACT_TOL
+    g = G.Engine(); script(g)
+    L = G.lib()
+    L.gooey_engine_loop_render_to_wav.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_uint32, c.c_char_p]
+    L.gooey_engine_loop_render_to_wav.restype = c.c_bool
+    path = tmp_path / "loop.wav"
+    assert L.gooey_engine_loop_render_to_wav(g._h, 2, 10000, 512, str(path).encode())
+    assert not L.gooey_engine_loop_render_to_wav(g._h, 1, 100, 0, str(path).encode())
+    g.close()
+    raw = path.read_bytes()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"WAVE"
+    fmt = raw.index(b"fmt ")
+    tag, ch, rate, _, _, bits = struct.unpack("<HHIIHH", raw[fmt + 8:fmt + 24])
+    assert (tag, ch, rate, bits) == (3, 2, 44100, 32)            # IEEE float stereo (ffi.rs:8032-8037)
+    data = raw.index(b"data")
+    n = struct.unpack("<I", raw[data + 4:data + 8])[0]
+    assert n == 10000 * 2 * 4
+    assert np.abs(np.frombuffer(raw[data + 8:data + 8 + n], np.float32).reshape(-1, 2) - want[0]).max() <= EXACT_TOL
+
+
+def test_sampler_rack_layers_retriggers_and_carries_voices_across_calls():
+    def run(e):
+        r = e.sampler_register()
+        assert r == 0 and e.mixer_route_source(5, 0) and not e.mixer_route_source(6, 0)
+        e.sampler_set_slot_buffer(0, 0, pcm(20, 9000), 44100.0)
+        e.sampler_set_slot_buffer(0, 1, pcm(21, 2500, channels=1), 22050.0)
+        e.sampler_set_slot_buffer(0, 7, pcm(22, 700), 48000.0)
+        info = (e.sampler_slot_is_loaded(0, 1), e.sampler_slot_frames(0, 1), e.sampler_slot_channels(0, 1), e.sampler_slot_sample_rate(0, 1),
+                e.sampler_slot_is_loaded(0, 2), e.sampler_get_source_id(0), e.sampler_get_source_id(3))
+        e.sampler_trigger(0, 0, 1.0); e.sampler_trigger(0, 1, 0.6)
+        a = e.render(3000)
+        e.sampler_trigger(0, 7, 0.9); e.sampler_trigger(0, 0, 0.5)         # layered on the voices still sounding
+        b = e.render(3000)
+        e.sampler_clear_slot(0, 0)                                           # stops its voices (sampler.rs:187-194)
+        cc = e.render(6000)
+        d = e.render(500)                                                    # everything has run out: silence
+        return np.concatenate([a, b, cc, d]), info
+    (got, ginfo), (want, winfo) = both(lambda e: None, run)
+    assert ginfo == winfo == (True, 2500, 1, 22050.0, False, 5, 0xFFFFFFFF)
+    assert np.abs(want[:3000]).max() > 0.05 and np.abs(want[-500:]).max() == 0.0
+    assert np.abs(got - want).max() <= EXACT_TOL
+
+
+def test_sampler_voice_stealing_takes_the_oldest_voice():
+    def run(e):
+        e.sampler_register(); e.sampler_register()
+        e.mixer_route_source(6, 2)
+        e.sampler_set_slot_buffer(1, 4, pcm(23, 20000, channels=1), 44100.0)
+        e.sampler_set_slot_buffer(1, 5, pcm(24, 300), 44100.0)
+        out = []
+        for k in range(36):                                                  # 32 voices, then four steals
+            e.sampler_trigger(1, 4 if k % 3 else 5, 0.2 + 0.02 * k)
+            out.append(e.render(64))
+        out.append(e.render(2000))
+        return np.concatenate(out)
+    got, want = both(lambda e: None, run)
+    assert np.abs(want).max() > 0.05
+    assert np.abs(got - want).max() <= EXACT_TOL
+
+
+def test_batch_of_engines_with_and_without_sources():
+    """Row pairs are handed out per engine and source: engines without loops, with loops, with racks, in one launch."""
+    n = 40
+
+    def script(e, i):
+        if i % 2 == 0:
+            busy_pattern(e)
+        if i % 3 != 1:
+            e.loop_load(i % 4, pcm(100 + i, 1000 + 37 * i), [44100.0, 48000.0][i % 2])
+            e.loop_set_speed(i % 4, 0.5 + 0.1 * (i % 7)); e.loop_set_gain(i % 4, 0.3 + 0.04 * (i % 10))
+            e.loop_set_playing(i % 4, True)
+        if i % 5 == 0:
+            r = e.sampler_register()
+            e.mixer_route_source(5 + r, 1)
+            e.sampler_set_slot_buffer(r, 2, pcm(200 + i, 5000, channels=1 + i % 2), 44100.0)
+            e.sampler_trigger(r, 2, 0.8)
+    engines = [G.Engine() for _ in range(n)]
+    for i, e in enumerate(engines):
+        script(e, i)
+    got = G.batch_bounce(engines, 1)
+    assert not any(e.has_error() for e in engines)
+    for e in engines:
+        e.close()
+    for i in range(n):
+        o = O.oracle_engine(); script(o, i)
+        want = o.bounce_to_buffer(1)
+        o.close()
+        assert np.abs(got[i] - want).max() <= TOL, i
+        if i % 3 != 1:
+            assert np.abs(want).max() > 0.01
+
+
+def test_requests_for_parts_that_are_not_built_latch_the_sticky_error():
+    L = G.lib()
+    L.gooey_engine_loop_effect_add.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; L.gooey_engine_loop_effect_add.restype = c.c_int32
+    L.gooey_engine_sampler_set_step.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_bool, c.c_uint32, c.c_float]; L.gooey_engine_sampler_set_step.restype = c.c_bool
+    L.gooey_engine_loop_queue_swap.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float, c.c_float, c.c_uint32]
+    L.gooey_engine_loop_queue_swap.restype = c.c_bool
+    for call in (lambda e: e.loop_set_pitch_mode(0, 2),
+                 lambda e: L.gooey_engine_loop_effect_add(e._h, 0, 1),
+                 lambda e: L.gooey_engine_sampler_set_step(e._h, 0, 0, True, 0, 1.0),
+                 lambda e: L.gooey_engine_loop_queue_swap(e._h, 0, pcm(1, 8).ctypes.data, 8, 2, c.c_float(44100.0), c.c_float(0.0), 1)):
+        g = G.Engine()
+        assert not g.has_error()
+        call(g)
+        assert g.has_error() and "not built" in g.get_error_message()
+        g.close()
+    g = G.Engine()
+    assert not g.loop_load(0, np.float32([0.0, np.inf]), 44100.0) and not g.loop_load(4, pcm(1, 8), 44100.0) and not g.loop_load(0, pcm(1, 8), -1.0)
+    assert not g.sampler_set_slot_buffer(0, 0, pcm(1, 8), 44100.0)               # rack not registered
+    assert g.sampler_register() == 0
+    assert not g.sampler_set_slot_buffer(0, 16, pcm(1, 8), 44100.0) and not g.sampler_set_slot_buffer(0, 0, pcm(1, 8, channels=3), 44100.0)
+    assert not g.sampler_trigger(0, 0, 1.0)
+    assert [g.sampler_register() for _ in range(4)] == [1, 2, 3, -1]
+    assert not g.has_error()
+    g.close()
