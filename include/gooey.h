@@ -286,8 +286,9 @@ bool gooey_b200_granulator_share_buffer(GooeyEngine* dst, const GooeyEngine* src
  * loop_channel.rs, stereo_buffer.rs).  The host passes decoded PCM (interleaved f32; 1 channel is duplicated, 2+ use channels 0 / 1);
  * the buffer is copied to the device.  Calls act immediately, like the reference's.  Playback state is not touched by a bounce
  * (ffi.rs:7840-7854 resets sequencers and snaps strips only).
- * This build: PitchMode Off and Resample.  gooey_engine_loop_set_pitch_mode(PRESERVE_PITCH), gooey_engine_loop_queue_swap and
- * gooey_engine_loop_effect_add latch the sticky error (WSOLA, queued swaps, per-channel effect chains and the clip grid are not built). ---- */
+ * Pitch modes: Off, Resample (tempo warp shifts pitch) and PreservePitch (WSOLA time-stretch, src/mixer/wsola.rs; reverse speeds
+ * fall back to the direct read, loop_channel.rs:184).  This build: gooey_engine_loop_queue_swap and gooey_engine_loop_effect_add latch
+ * the sticky error (queued swaps, per-channel effect chains and the clip grid are not built). ---- */
 #define GOOEY_LOOP_CHANNEL_COUNT 4u            /* src/mixer/mod.rs:32 */
 #define GOOEY_PITCH_MODE_OFF 0u                /* :7163-7168 */
 #define GOOEY_PITCH_MODE_RESAMPLE 1u

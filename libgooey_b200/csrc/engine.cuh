@@ -217,6 +217,22 @@ struct EngineBank {
   std::vector<gd::LoopMixer> h_loop_descs; DevBuf<gd::LoopMixer> d_loop_descs;
   std::vector<gd::SamplerRack> h_rack_descs; DevBuf<gd::SamplerRack> d_rack_descs;
   DevBuf<float> d_ext[2];
+  DevBuf<float> d_hann; uint32_t wsola_hop = 0;    // WSOLA window table of this sample rate (wsola.rs:80-82), built at first use
+  // PreservePitch channel: the window table and the channel's own stretcher buffers (9 hops of floats, content irrelevant until the
+  // device builds the stretcher) behind the descriptor
+  template <class LoopHostT> void attach_stretcher(LoopHostT& l, gd::LoopChan& d) {
+    d.hop = 0; d.hann = nullptr; d.st_buf = nullptr;
+    if (!d.preserve) return;
+    if (!d_hann.p) {
+      wsola_hop = gd::wsola_hop_len(sr);
+      std::vector<float> h((size_t)2 * wsola_hop);
+      for (uint32_t i = 0; i < 2 * wsola_hop; i++) h[i] = gd::wsola_window_coeff(i, 2 * wsola_hop);
+      d_hann.alloc(h.size());
+      GH_CUDA(cudaMemcpy(d_hann.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (!l.stretch) { l.stretch = std::make_shared<DevBuf<float>>(); l.stretch->alloc((size_t)9 * wsola_hop); l.st_valid = false; d.st_valid = 0; }
+    d.hop = wsola_hop; d.hann = d_hann.p; d.st_buf = l.stretch->p;
+  }
   DevBuf<float> d_peaks;                  // [n][N_PEAKS] maxima of the current render call
   DevBuf<unsigned long long> d_chain_units; unsigned long long h_chain_units = 0;   // engine-frames the settled-chain kernel took in the last render
   std::vector<float> h_peaks;
@@ -337,6 +353,28 @@ struct GooeyEngine {
     bool playing = false, muted = false, soloed = false;
     uint32_t pitch_mode = 0;
     gd::LSm gain = {1.0f, 1.0f}, active = {1.0f, 1.0f};
+    // WsolaStretcher of PitchMode::PreservePitch (loop_channel.rs:141-146): its buffers on the device, its scalars here; dropped
+    // (st_valid = false) whenever the cursor is moved from outside so that it re-seeds at the new position
+    std::shared_ptr<gh::DevBuf<float>> stretch;
+    bool st_valid = false; uint32_t st_have_prev = 0, st_drain = 0; double st_cursor = 0.0;
+    // fills the playback half of a device descriptor (shared by engines_render and the offline channel render)
+    void describe(gd::LoopChan& d, float engine_bpm) const {
+      const bool loaded = buf && len > 0;
+      d.left = loaded ? buf->p : nullptr; d.right = loaded ? buf->p + len : nullptr;
+      d.cursor = cursor; d.len = loaded ? len : 0u; d.buf_sr = buf_sr;
+      const bool tagged = has_source_bpm && source_bpm > 0.0f && engine_bpm > 0.0f;               // warp_ratio (loop_channel.rs:282-291)
+      const double ratio = tagged ? (double)engine_bpm / (double)source_bpm : 1.0;
+      d.warp = pitch_mode == 1 ? ratio : 1.0;                                                      // advance(): Resample mode only (:239-243)
+      d.warp_pp = pitch_mode != 0 ? ratio : 1.0;
+      d.loop_start = loop_start; d.loop_end = loop_end; d.speed = speed; d.playing = playing ? 1u : 0u;
+      d.gain = gain; d.active = active;
+      d.preserve = pitch_mode == 2 ? 1u : 0u;
+      d.st_valid = st_valid ? 1u : 0u; d.st_have_prev = st_have_prev; d.st_drain = st_drain; d.st_cursor = st_cursor;
+    }
+    void absorb(const gd::LoopChan& d) {   // the state a render moved
+      cursor = d.cursor; gain = d.gain; active = d.active;
+      st_valid = d.st_valid != 0; st_have_prev = d.st_have_prev; st_drain = d.st_drain; st_cursor = d.st_cursor;
+    }
     gd::LoopWindow window() const { return gd::loop_window(loop_start, loop_end, (double)len); }
   } loops[gd::LOOP_CHANNELS];
   float loop_engine_bpm = 120.0f;          // LoopChannel::engine_bpm: written by Mixer::set_bpm only (loop_channel.rs:28, 365-367)
@@ -642,15 +680,9 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       gd::LoopMixer m;
       memset(&m, 0, sizeof m);
       for (int c = 0; c < gd::LOOP_CHANNELS; c++) {
-        const auto& l = e->loops[c];
-        gd::LoopChan& d = m.ch[c];
-        const bool loaded = l.buf && l.len > 0;
-        d.left = loaded ? l.buf->p : nullptr; d.right = loaded ? l.buf->p + l.len : nullptr;
-        d.cursor = l.cursor; d.len = loaded ? l.len : 0u; d.buf_sr = l.buf_sr;
-        // warp_ratio (loop_channel.rs:282-291) applies in Resample mode only (:239-243); PreservePitch with speed < 0 is refused upstream
-        d.warp = (l.pitch_mode == 1 && l.has_source_bpm && l.source_bpm > 0.0f && e->loop_engine_bpm > 0.0f) ? (double)e->loop_engine_bpm / (double)l.source_bpm : 1.0;
-        d.loop_start = l.loop_start; d.loop_end = l.loop_end; d.speed = l.speed; d.playing = l.playing ? 1u : 0u;
-        d.gain = l.gain; d.active = l.active;
+        auto& l = e->loops[c];
+        l.describe(m.ch[c], e->loop_engine_bpm);
+        B.attach_stretcher(l, m.ch[c]);
       }
       m.row = ext_pairs;
       e->cfg.src_ext |= 1u; e->cfg.ext_row[0] = ext_pairs++;
@@ -902,9 +934,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   GH_CUDA(cudaStreamSynchronize(st));
   for (size_t q = 0; q < loop_refs.size(); q++)      // playback state back into the engines' loop channels / sampler voices
     for (int c = 0; c < gd::LOOP_CHANNELS; c++) {
-      auto& l = E[loop_refs[q]]->loops[c];
-      const gd::LoopChan& d = B.h_loop_descs[q].ch[c];
-      l.cursor = d.cursor; l.gain = d.gain; l.active = d.active;
+      E[loop_refs[q]]->loops[c].absorb(B.h_loop_descs[q].ch[c]);
     }
   for (size_t q = 0; q < rack_refs.size(); q++) {
     auto& R = E[rack_refs[q].engine]->samplers[rack_refs[q].rack];

@@ -15,8 +15,12 @@
 // engines_render uploads one descriptor per engine with a loaded source, the kernel advances it piece by piece, and the
 // state is read back when the call ends.
 //
-// Not built (a request latches the engine's sticky error instead of rendering different audio): PitchMode::PreservePitch
-// (mixer/wsola.rs), queued buffer swaps, per-channel effect chains, the clip grid and transport-armed sampler patterns.
+// PitchMode::PreservePitch (mixer/wsola.rs) runs inside the same tick: every hop (20 ms) the channel's thread searches the best
+// aligned grain start (<= ~130 candidates x hop taps of normalised cross-correlation), windows a 2-hop grain and overlap-adds it;
+// the stretcher's buffers (9 hops of floats per channel) live in a device buffer owned by the channel.
+//
+// Not built (a request latches the engine's sticky error instead of rendering different audio): queued buffer swaps,
+// per-channel effect chains, the clip grid and transport-armed sampler patterns.
 #pragma once
 #include "dsp.cuh"
 
@@ -74,6 +78,15 @@ struct LoopChan {
   float loop_start, loop_end, speed;
   uint32_t playing;
   LSm gain, active;           // user fader; mute / solo gate written by Mixer::tick (mod.rs:63-72)
+  // PitchMode::PreservePitch (mixer/wsola.rs): the channel's WsolaStretcher.  st_buf holds its buffers as planes of `hop` floats:
+  // out l, out r | grain l (2 hop), grain r (2 hop) | tail l, tail r | tail mono = 9 * hop floats; hann = the window table [2 * hop]
+  float* st_buf; const float* hann;
+  double st_cursor;           // analysis_cursor
+  double warp_pp;             // warp_ratio() of this mode (tempo enters through the hop-to-hop jump only)
+  uint32_t hop;               // hop_len = round(20 ms * engine rate)
+  uint32_t preserve;          // the pitch mode is PreservePitch (the stretcher plays while speed >= 0, loop_channel.rs:184)
+  uint32_t st_valid;          // a stretcher exists (0: built from the cursor at the next tick, :222-224)
+  uint32_t st_have_prev, st_drain, pad;
 };
 struct LoopMixer { LoopChan ch[LOOP_CHANNELS]; uint32_t row; uint32_t pad; };   // row = index of the stereo row pair this mixer writes
 
@@ -122,14 +135,127 @@ G_HD void loop_advance(LoopChan& c, float engine_sr) {
     else if (c.cursor < w.lo) c.cursor = w.hi - rem_euclid_d(w.lo - c.cursor, span);
   }
 }
+// ---- mixer/wsola.rs: WSOLA time-stretch (tempo follows engine_bpm / source_bpm, pitch does not) ----------------------------
+G_HD uint32_t wsola_hop_len(float engine_sr) {   // :73-74
+  const double sr = (double)fmaxf(engine_sr, 1.0f);
+  const double h = round(((double)20.0f / 1000.0) * sr);
+  return (uint32_t)(h > 1.0 ? h : 1.0);
+}
+G_HD float raised_sine_window(float phase, float shape) {   // utils/mod.rs:39-44
+  return gm::g_powf(fmaxf(gm::g_sinf(PI_F * clampf(phase, 0.0f, 1.0f)), 0.0f), shape);
+}
+// Periodic Hann (:80-82): raised_sine_window(i / window_len, 2.0).  The exponent is a literal at the (inlined) call site, and both
+// LLVM and GCC lower pow(x, 2.0) to x * x whatever the math flags, so the table is sin^2 by one multiplication (correctly rounded;
+// glibc's powf(x, 2) differs from it by 1 ulp on about one entry in a thousand).  A debug build of the reference would call powf.
+G_HD float wsola_window_coeff(uint32_t i, uint32_t window_len) {
+  const float s = fmaxf(gm::g_sinf(PI_F * clampf((float)i / (float)window_len, 0.0f, 1.0f)), 0.0f);
+  return s * s;
+}
+struct WsolaView { float *out_l, *out_r, *grain_l, *grain_r, *tail_l, *tail_r, *mono; };
+G_HD WsolaView wsola_view(float* b, uint32_t hop) {
+  WsolaView v;
+  v.out_l = b; v.out_r = b + hop; v.grain_l = b + 2 * hop; v.grain_r = b + 4 * hop; v.tail_l = b + 6 * hop; v.tail_r = b + 7 * hop; v.mono = b + 8 * hop;
+  return v;
+}
+G_HD double maxd(double a, double b) { return a > b ? a : b; }
+G_HD double mind(double a, double b) { return a < b ? a : b; }
+// A source read of either synthesis path: physical frames (linear window) or the window's virtual coordinates (wrap-around window)
+G_HD void wsola_read(const LoopChan& c, const LoopWindow& w, double pos, float& l, float& r) {
+  if (w.wraps) loop_read_wrapped(c.left, c.right, c.len, window_to_physical(w, pos), l, r);
+  else loop_read_interpolated(c.left, c.right, c.len, pos, l, r);
+}
+// score_at (:330-347, :398-415): normalised cross-correlation of the candidate's next hop with the previous grain's tail
+G_HD float wsola_score(const LoopChan& c, const LoopWindow& w, const float* mono, double start, double step, double lo_floor, double hi_clamp) {
+  float num = 0.0f, ref_energy = 0.0f, cand_energy = 0.0f;
+  for (uint32_t i = 0; i < c.hop; i++) {
+    const float reference = mono[i];
+    float l, r;
+    wsola_read(c, w, clampd(start + (double)i * step, lo_floor, hi_clamp), l, r);
+    const float cand = l + r;
+    num += cand * reference;
+    ref_energy += reference * reference;
+    cand_energy += cand * cand;
+  }
+  if (ref_energy <= 1.1920929e-7f || cand_energy <= 1.1920929e-7f) return 0.0f;
+  return num / (sqrtf(ref_energy) * sqrtf(cand_energy));
+}
+// search_best_start / search_best_start_wrapped (:314-380, :386-448): coarse pass of <= 65 candidates, then a +-stride refinement
+G_HD double wsola_search(const LoopChan& c, const LoopWindow& w, const float* mono, double center, double step, double lo_floor, double max_start) {
+  const double radius = maxd(round(((double)10.0f / 1000.0) * (double)c.buf_sr), 1.0);
+  const double lo_bound = maxd(center - radius, lo_floor), hi_bound = mind(center + radius, max_start);
+  if (hi_bound <= lo_bound) return clampd(center, lo_floor, max_start);
+  const double span = hi_bound - lo_bound;
+  const double coarse_stride = maxd(span / 64.0, 1.0);
+  double best = lo_bound;
+  float best_score = -3.40282347e+38f;
+  for (double k = lo_bound; k <= hi_bound; k += coarse_stride) {
+    const float sc = wsola_score(c, w, mono, k, step, lo_floor, max_start + step);
+    if (sc > best_score) { best_score = sc; best = k; }
+  }
+  const double refine_lo = maxd(best - coarse_stride, lo_bound), refine_hi = mind(best + coarse_stride, hi_bound);
+  for (double k = refine_lo; k <= refine_hi; k += 1.0) {
+    const float sc = wsola_score(c, w, mono, k, step, lo_floor, max_start + step);
+    if (sc > best_score) { best_score = sc; best = k; }
+  }
+  return best;
+}
+// synthesize_next_hop (:121-311): both paths in one body — the linear window works in physical frames [lo, hi], the wrap-around
+// window in virtual frames [0, span] read back through to_physical; returns the new (physical) analysis cursor
+G_HD double wsola_synthesize(LoopChan& c, const LoopWindow& w, double sr_ratio, double speed, double warp) {
+  const WsolaView v = wsola_view(c.st_buf, c.hop);
+  const uint32_t hop = c.hop, window_len = 2 * c.hop;
+  const double step = maxd(sr_ratio * maxd(speed, 0.0), 1e-6);
+  const double hop_source_span = (double)hop * step;
+  const double grain_source_span = ((double)window_len - 1.0) * step + 1.0;
+  const double lo_floor = w.wraps ? 0.0 : w.lo, hi_ceil = w.wraps ? w.span : w.hi;
+  const double max_start = maxd(hi_ceil - grain_source_span, lo_floor);
+  const double from = w.wraps ? window_to_virtual(w, c.st_cursor) : c.st_cursor;
+  const double raw_target = from + hop_source_span * maxd(warp, 0.0);
+  double search_center;
+  if (raw_target > max_start || max_start <= lo_floor) { search_center = lo_floor; c.st_have_prev = 0; }   // restart at the loop start with a fresh grain
+  else search_center = maxd(raw_target, lo_floor);
+  const double best_start = c.st_have_prev ? wsola_search(c, w, v.mono, search_center, step, lo_floor, max_start) : search_center;
+  for (uint32_t i = 0; i < window_len; i++) {
+    float l, r;
+    wsola_read(c, w, clampd(best_start + (double)i * step, lo_floor, hi_ceil), l, r);
+    const float wi = c.hann[i];
+    v.grain_l[i] = l * wi; v.grain_r[i] = r * wi;
+  }
+  for (uint32_t i = 0; i < hop; i++) {
+    const float pl = c.st_have_prev ? v.tail_l[i] : 0.0f, pr = c.st_have_prev ? v.tail_r[i] : 0.0f;
+    v.out_l[i] = pl + v.grain_l[i]; v.out_r[i] = pr + v.grain_r[i];
+  }
+  for (uint32_t i = 0; i < hop; i++) {
+    v.tail_l[i] = v.grain_l[hop + i]; v.tail_r[i] = v.grain_r[hop + i];
+    v.mono[i] = v.tail_l[i] + v.tail_r[i];
+  }
+  c.st_have_prev = 1; c.st_drain = 0;
+  const double phys = w.wraps ? window_to_physical(w, best_start) : best_start;
+  c.st_cursor = phys;
+  return phys;
+}
+// LoopChannel::tick_preserve_pitch (:215-262, no queued swap): one frame out of the stretcher, a new hop first if it ran dry
+G_HD void wsola_tick(LoopChan& c, float engine_sr, float& ol, float& orr) {
+  const LoopWindow w = loop_window(c.loop_start, c.loop_end, (double)c.len);
+  const double sr_ratio = (double)c.buf_sr / (double)fmaxf(engine_sr, 1.0f);
+  if (!c.st_valid) { c.st_valid = 1; c.st_have_prev = 0; c.st_drain = c.hop; c.st_cursor = c.cursor; }   // WsolaStretcher::new(engine rate, cursor)
+  if (c.st_drain >= c.hop) c.cursor = wsola_synthesize(c, w, sr_ratio, (double)c.speed, c.warp_pp);
+  if (c.st_drain < c.hop) { ol = c.st_buf[c.st_drain]; orr = c.st_buf[c.hop + c.st_drain]; }
+  else { ol = 0.0f; orr = 0.0f; }
+  c.st_drain += 1;
+}
+
 // LoopChannel::tick (:181-208) with an empty effect chain (EffectChain::process of no effects is the identity, effect_chain.rs:294-299)
 G_HD void loop_chan_tick(LoopChan& c, float engine_sr, float coeff15, float& ol, float& orr) {
   float dl = 0.0f, dr = 0.0f;
   if (c.playing && c.left) {
-    const LoopWindow w = loop_window(c.loop_start, c.loop_end, (double)c.len);
-    if (w.wraps) loop_read_wrapped(c.left, c.right, c.len, c.cursor, dl, dr);
-    else loop_read_interpolated(c.left, c.right, c.len, c.cursor, dl, dr);
-    loop_advance(c, engine_sr);
+    if (c.preserve && c.speed >= 0.0f) wsola_tick(c, engine_sr, dl, dr);
+    else {
+      const LoopWindow w = loop_window(c.loop_start, c.loop_end, (double)c.len);
+      if (w.wraps) loop_read_wrapped(c.left, c.right, c.len, c.cursor, dl, dr);
+      else loop_read_interpolated(c.left, c.right, c.len, c.cursor, dl, dr);
+      loop_advance(c, engine_sr);
+    }
   }
   const float g = lsm_tick(c.gain, coeff15);
   const float gl = dl * g, gr = dr * g;

@@ -45,7 +45,7 @@ bool gooey_engine_loop_load(GooeyEngine* e, uint32_t channel, const float* sampl
     auto buf = gh::upload_pcm(e, planes);
     c->buf = buf; c->len = frames; c->buf_sr = sample_rate;
     c->has_source_bpm = false; c->source_bpm = 0.0f;                              // a new buffer carries no tempo tag
-    c->cursor = c->window().lo;                                                   // set_buffer (loop_channel.rs:311-316)
+    c->cursor = c->window().lo; c->st_valid = false;                              // set_buffer (loop_channel.rs:311-316)
   } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
   return true;
 }
@@ -66,16 +66,18 @@ float gooey_engine_loop_get_source_bpm(const GooeyEngine* e, uint32_t ch) { cons
 void gooey_engine_loop_set_pitch_mode(GooeyEngine* e, uint32_t ch, uint32_t mode) {   /* :7368-7381 */
   auto* c = gh::loop_ch(e, ch);
   if (!c) return;
-  c->pitch_mode = mode == GOOEY_PITCH_MODE_RESAMPLE ? 1u : (mode == GOOEY_PITCH_MODE_PRESERVE_PITCH ? 2u : 0u);
-  if (c->pitch_mode == 2u) gh::engine_fail(e, "libgooey_b200: PitchMode::PreservePitch (WSOLA time-stretch, mixer/wsola.rs) is not built; the channel plays unwarped");
+  const uint32_t m = mode == GOOEY_PITCH_MODE_RESAMPLE ? 1u : (mode == GOOEY_PITCH_MODE_PRESERVE_PITCH ? 2u : 0u);
+  if (c->pitch_mode == 2u && m != 2u) c->st_valid = false;                        // leaving PreservePitch drops the stretcher (loop_channel.rs:341-346)
+  c->pitch_mode = m;
 }
 uint32_t gooey_engine_loop_get_pitch_mode(const GooeyEngine* e, uint32_t ch) { const auto* c = gh::loop_ch(e, ch); return c ? c->pitch_mode : 0u; }
-void gooey_engine_loop_restart(GooeyEngine* e, uint32_t ch) { auto* c = gh::loop_ch(e, ch); if (c && c->buf) c->cursor = c->window().lo; }
+void gooey_engine_loop_restart(GooeyEngine* e, uint32_t ch) { auto* c = gh::loop_ch(e, ch); if (c && c->buf) { c->cursor = c->window().lo; c->st_valid = false; } }
 void gooey_engine_loop_set_position(GooeyEngine* e, uint32_t ch, float n) {   /* loop_channel.rs:388-397 */
   auto* c = gh::loop_ch(e, ch);
   if (!c || !c->buf) return;
   const double len = (double)c->len;
   c->cursor = gd::window_fold(c->window(), (double)gd::clampf(n, 0.0f, 1.0f) * len);
+  c->st_valid = false;
 }
 float gooey_engine_loop_get_position(const GooeyEngine* e, uint32_t ch) {     /* position_normalized :497-502 */
   const auto* c = gh::loop_ch(e, ch);
@@ -93,7 +95,8 @@ int32_t gooey_engine_loop_effect_add(GooeyEngine* e, uint32_t, uint32_t) {
 
 // Mixer::render_channel_to_interleaved (mixer/mod.rs:444-476): `frames` stereo frames of one loop channel from its loop start,
 // ignoring mute / solo, after prepare_offline_render (playing, fader snapped, gate open) — the audio of
-// gooey_engine_loop_render_to_wav.  With no per-channel effects the preroll only moves the cursor, which is restarted after it.
+// gooey_engine_loop_render_to_wav.  With no per-channel effects the preroll only moves the cursor and the stretcher, and both
+// are reset by the restart that follows it.
 bool gooey_engine_loop_render(GooeyEngine* e, uint32_t channel, uint32_t frames, uint32_t /*preroll*/, float* out_interleaved) {
   auto* c = gh::loop_ch(e, channel);
   if (!c || !out_interleaved || frames == 0 || !c->buf || c->len == 0) return false;
@@ -102,13 +105,11 @@ bool gooey_engine_loop_render(GooeyEngine* e, uint32_t channel, uint32_t frames,
     std::lock_guard<std::recursive_mutex> lk(B.mu);
     gh::use_device(B.device);
     c->playing = true; c->gain.c = c->gain.t; c->active = {1.0f, 1.0f};
-    c->cursor = c->window().lo;
+    c->cursor = c->window().lo; c->st_valid = false;                              // prepare_offline_render + restart (loop_channel.rs:444-451)
     gd::LoopMixer m;
     memset(&m, 0, sizeof m);
-    gd::LoopChan& d = m.ch[0];
-    d.left = c->buf->p; d.right = c->buf->p + c->len; d.cursor = c->cursor; d.len = c->len; d.buf_sr = c->buf_sr;
-    d.warp = (c->pitch_mode == 1 && c->has_source_bpm && c->source_bpm > 0.0f && e->loop_engine_bpm > 0.0f) ? (double)e->loop_engine_bpm / (double)c->source_bpm : 1.0;
-    d.loop_start = c->loop_start; d.loop_end = c->loop_end; d.speed = c->speed; d.playing = 1u; d.gain = c->gain; d.active = c->active;
+    c->describe(m.ch[0], e->loop_engine_bpm);
+    B.attach_stretcher(*c, m.ch[0]);
     m.row = 0;
     const size_t stride = ((size_t)frames + 31) & ~(size_t)31;
     B.d_ext[0].alloc(2 * stride);
@@ -121,7 +122,7 @@ bool gooey_engine_loop_render(GooeyEngine* e, uint32_t channel, uint32_t frames,
     GH_CUDA(cudaMemcpyAsync(&m, B.d_loop_descs.p, sizeof m, cudaMemcpyDeviceToHost, B.stream));
     GH_CUDA(cudaStreamSynchronize(B.stream));
     for (uint32_t f = 0; f < frames; f++) { out_interleaved[2 * (size_t)f] = planes[f]; out_interleaved[2 * (size_t)f + 1] = planes[stride + f]; }
-    c->cursor = m.ch[0].cursor; c->gain = m.ch[0].gain; c->active = m.ch[0].active;
+    c->absorb(m.ch[0]);
   } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
   return true;
 }

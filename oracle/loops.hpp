@@ -2,9 +2,9 @@
 // CPU restatement of the reference's sample-playback sources:
 //   mixer/stereo_buffer.rs (StereoSampleBuffer), mixer/loop_channel.rs (LoopWindow, LoopChannel), mixer/mod.rs (Mixer),
 //   instruments/sampler.rs (SamplerBuffer, SampleVoice, SamplerRack).
-// Restated: everything a bounce touches with PitchMode Off / Resample and empty per-channel effect chains.  Not restated
-// (the product refuses the same requests): PitchMode::PreservePitch (mixer/wsola.rs), queued swaps, per-channel effect
-// chains, the clip grid, transport-armed sampler patterns.  Parity unpinned like the rest of the oracle (no reference
+//   mixer/wsola.rs (WsolaStretcher, PitchMode::PreservePitch).
+// Restated: everything a bounce touches with empty per-channel effect chains.  Not restated (the product refuses the same
+// requests): queued swaps, per-channel effect chains, the clip grid, transport-armed sampler patterns.  Parity unpinned like the rest of the oracle (no reference
 // build here); the reference's own unit tests of these files are restated in tests/test_samples_cpu.py.
 #pragma once
 #include <memory>
@@ -75,6 +75,122 @@ struct LoopWindow {  // :59-116
   }
 };
 enum PitchMode { PITCH_OFF = 0, PITCH_RESAMPLE = 1, PITCH_PRESERVE = 2 };
+
+// ---- mixer/wsola.rs ---------------------------------------------------------------------------------------------------
+struct WsolaStretcher {
+  size_t hop_len, window_len;
+  std::vector<float> window;
+  std::vector<StereoFrame> out_scratch, grain_scratch, prev_tail;
+  std::vector<float> prev_tail_mono;
+  bool have_prev_tail = false;
+  size_t drain_idx;
+  double analysis_cursor;
+  WsolaStretcher(float engine_sr, double initial_cursor) {  // :70-98
+    double sr = (double)rust_max(engine_sr, 1.0f);
+    double h = std::round(((double)20.0f / 1000.0) * sr);
+    hop_len = (size_t)(h > 1.0 ? h : 1.0);
+    window_len = hop_len * 2;
+    window.resize(window_len);
+    // raised_sine_window(i / window_len, 2.0): `.powf(2.0)` with the literal exponent of the inlined call is lowered to x * x by
+    // LLVM (pow(x, 2.0) -> x * x needs no fast-math), as GCC does for the same C expression; written out so no optimiser decides it.
+    for (size_t i = 0; i < window_len; i++) {
+      float sn = rust_max(sinf(3.14159265358979323846f * clampf((float)i / (float)window_len, 0.0f, 1.0f)), 0.0f);
+      window[i] = sn * sn;
+    }
+    out_scratch.assign(hop_len, {}); grain_scratch.assign(window_len, {}); prev_tail.assign(hop_len, {}); prev_tail_mono.assign(hop_len, 0.0f);
+    drain_idx = hop_len;
+    analysis_cursor = initial_cursor;
+  }
+  bool needs_refill() const { return drain_idx >= hop_len; }
+  StereoFrame drain() { StereoFrame f; if (drain_idx < out_scratch.size()) f = out_scratch[drain_idx]; drain_idx += 1; return f; }
+  static double maxd(double a, double b) { return a > b ? a : b; }
+  static double mind(double a, double b) { return a < b ? a : b; }
+  // score_at of both searches (:330-347, :398-415): `pos_of(i)` yields the stereo read of tap i
+  template <class Read> float score(Read read_at) const {
+    float num = 0.0f, ref_energy = 0.0f, cand_energy = 0.0f;
+    for (size_t i = 0; i < prev_tail_mono.size(); i++) {
+      float reference = prev_tail_mono[i];
+      StereoFrame raw = read_at(i);
+      float cand = raw.l + raw.r;
+      num += cand * reference;
+      ref_energy += reference * reference;
+      cand_energy += cand * cand;
+    }
+    const float EPS = 1.1920929e-7f;
+    if (ref_energy <= EPS || cand_energy <= EPS) return 0.0f;
+    return num / (sqrtf(ref_energy) * sqrtf(cand_energy));
+  }
+  template <class Score> static double coarse_to_fine(double lo_bound, double hi_bound, Score score_at) {  // :349-378, :417-446
+    double span = hi_bound - lo_bound;
+    double coarse_stride = maxd(span / 64.0, 1.0);
+    double best = lo_bound; float best_score = -3.40282347e+38f;
+    for (double c = lo_bound; c <= hi_bound; c += coarse_stride) { float sc = score_at(c); if (sc > best_score) { best_score = sc; best = c; } }
+    double refine_lo = maxd(best - coarse_stride, lo_bound), refine_hi = mind(best + coarse_stride, hi_bound);
+    for (double c = refine_lo; c <= refine_hi; c += 1.0) { float sc = score_at(c); if (sc > best_score) { best_score = sc; best = c; } }
+    return best;
+  }
+  double search_best_start(const StereoSampleBuffer& b, double center, double step, double loop_lo, double max_start) const {  // :386-448
+    double radius = maxd(std::round(((double)10.0f / 1000.0) * (double)b.sample_rate), 1.0);
+    double lo_bound = maxd(center - radius, loop_lo), hi_bound = mind(center + radius, max_start);
+    if (hi_bound <= lo_bound) return clampd(center, loop_lo, max_start);
+    return coarse_to_fine(lo_bound, hi_bound, [&](double start) {
+      return score([&](size_t i) { return b.read_interpolated(clampd(start + (double)i * step, loop_lo, max_start + step)); }); });
+  }
+  double search_best_start_wrapped(const StereoSampleBuffer& b, const LoopWindow& w, double center, double step, double max_start) const {  // :314-380
+    double radius = maxd(std::round(((double)10.0f / 1000.0) * (double)b.sample_rate), 1.0);
+    double lo_bound = maxd(center - radius, 0.0), hi_bound = mind(center + radius, max_start);
+    if (hi_bound <= lo_bound) return clampd(center, 0.0, max_start);
+    return coarse_to_fine(lo_bound, hi_bound, [&](double start) {
+      return score([&](size_t i) { return b.read_wrapped(w.to_physical(clampd(start + (double)i * step, 0.0, max_start + step))); }); });
+  }
+  void overlap_add_and_carry() {  // :206-231, :284-307
+    for (size_t i = 0; i < hop_len; i++) {
+      StereoFrame prev = have_prev_tail ? prev_tail[i] : StereoFrame{};
+      out_scratch[i] = {prev.l + grain_scratch[i].l, prev.r + grain_scratch[i].r};
+    }
+    for (size_t i = 0; i < hop_len; i++) { prev_tail[i] = grain_scratch[hop_len + i]; prev_tail_mono[i] = prev_tail[i].l + prev_tail[i].r; }
+    have_prev_tail = true;
+    drain_idx = 0;
+  }
+  double synthesize_next_hop(const StereoSampleBuffer& b, const LoopWindow& w, double sr_ratio, double speed, double warp) {  // :121-135
+    double step = maxd(sr_ratio * maxd(speed, 0.0), 1e-6);
+    double hop_source_span = (double)hop_len * step;
+    double grain_source_span = ((double)window_len - 1.0) * step + 1.0;
+    if (!w.wraps) {  // :140-236
+      double loop_lo = w.lo, loop_hi = w.hi;
+      double max_start = maxd(loop_hi - grain_source_span, loop_lo);
+      double raw_target = analysis_cursor + hop_source_span * maxd(warp, 0.0);
+      double search_center; bool wrapped;
+      if (raw_target > max_start || max_start <= loop_lo) { search_center = loop_lo; wrapped = true; } else { search_center = maxd(raw_target, loop_lo); wrapped = false; }
+      if (wrapped) have_prev_tail = false;
+      double best_start = have_prev_tail ? search_best_start(b, search_center, step, loop_lo, max_start) : search_center;
+      for (size_t i = 0; i < window_len; i++) {
+        StereoFrame raw = b.read_interpolated(clampd(best_start + (double)i * step, loop_lo, loop_hi));
+        grain_scratch[i] = {raw.l * window[i], raw.r * window[i]};
+      }
+      overlap_add_and_carry();
+      analysis_cursor = best_start;
+      return best_start;
+    }
+    // :246-311
+    double span = w.span;
+    double max_start = maxd(span - grain_source_span, 0.0);
+    double cursor_v = w.to_virtual(analysis_cursor);
+    double raw_target = cursor_v + hop_source_span * maxd(warp, 0.0);
+    double search_center; bool wrapped;
+    if (raw_target > max_start || max_start <= 0.0) { search_center = 0.0; wrapped = true; } else { search_center = maxd(raw_target, 0.0); wrapped = false; }
+    if (wrapped) have_prev_tail = false;
+    double best_start = have_prev_tail ? search_best_start_wrapped(b, w, search_center, step, max_start) : search_center;
+    for (size_t i = 0; i < window_len; i++) {
+      StereoFrame raw = b.read_wrapped(w.to_physical(clampd(best_start + (double)i * step, 0.0, span)));
+      grain_scratch[i] = {raw.l * window[i], raw.r * window[i]};
+    }
+    overlap_add_and_carry();
+    double phys = w.to_physical(best_start);
+    analysis_cursor = phys;
+    return phys;
+  }
+};
 struct LoopChannel {
   std::shared_ptr<StereoSampleBuffer> buffer;
   double cursor = 0.0;
@@ -85,6 +201,7 @@ struct LoopChannel {
   bool muted = false, soloed = false;
   int pitch_mode = PITCH_OFF;
   float engine_bpm = 120.0f;
+  std::shared_ptr<WsolaStretcher> stretcher;            // lazily built in PreservePitch mode, dropped whenever the cursor is moved from outside
   explicit LoopChannel(float sr) : gain(1.0f, 0.0f, 2.0f, sr, 15.0f), active_gain(1.0f, 0.0f, 1.0f, sr, 15.0f) {}   // :157-178
   bool has_buffer() const { return buffer && buffer->len() > 0; }
   LoopWindow window(double len) const {  // :293-307
@@ -121,24 +238,38 @@ struct LoopChannel {
   StereoFrame tick(float engine_sr) {  // :181-208
     StereoFrame dry;
     if (playing && has_buffer()) {
-      LoopWindow w = window((double)buffer->len());
-      dry = w.wraps ? buffer->read_wrapped(cursor) : buffer->read_interpolated(cursor);
-      advance(engine_sr);
+      if (pitch_mode == PITCH_PRESERVE && speed >= 0.0f) dry = tick_preserve_pitch(engine_sr);
+      else {
+        LoopWindow w = window((double)buffer->len());
+        dry = w.wraps ? buffer->read_wrapped(cursor) : buffer->read_interpolated(cursor);
+        advance(engine_sr);
+      }
     }
     StereoFrame gained = dry.scaled(gain.tick());
     return gained.scaled(active_gain.tick());          // empty EffectChain in between
   }
-  void set_buffer(std::shared_ptr<StereoSampleBuffer> b) { double len = (double)b->len(); buffer = std::move(b); cursor = window(len).lo; }   // :311-316
+  StereoFrame tick_preserve_pitch(float engine_sr) {  // :215-262 (no queued swap)
+    double len = (double)buffer->len();
+    LoopWindow w = window(len);
+    double sr_ratio = (double)buffer->sample_rate / (double)rust_max(engine_sr, 1.0f);
+    double warp = warp_ratio(), sp = (double)speed;
+    if (!stretcher) stretcher = std::make_shared<WsolaStretcher>(engine_sr, cursor);
+    if (stretcher->needs_refill()) cursor = stretcher->synthesize_next_hop(*buffer, w, sr_ratio, sp, warp);
+    return stretcher->drain();
+  }
+  void set_pitch_mode(int m) { if (pitch_mode == PITCH_PRESERVE && m != PITCH_PRESERVE) stretcher.reset(); pitch_mode = m; }   // :341-346
+  void set_buffer(std::shared_ptr<StereoSampleBuffer> b) { double len = (double)b->len(); buffer = std::move(b); cursor = window(len).lo; stretcher.reset(); }   // :311-316
   void set_gain(float g) { gain.set_target(clampf(g, 0.0f, 2.0f)); }
   void set_loop_start(float n) { loop_start = clampf(n, 0.0f, 1.0f); }
   void set_loop_end(float n) { loop_end = clampf(n, 0.0f, 1.0f); }
   void set_speed(float s) { speed = clampf(s, -4.0f, 4.0f); }
-  void restart() { if (!buffer) return; cursor = window((double)buffer->len()).lo; }
+  void restart() { if (!buffer) return; cursor = window((double)buffer->len()).lo; stretcher.reset(); }
   void set_position(float n) {  // :388-397
     if (!buffer) return;
     double len = (double)buffer->len();
     LoopWindow w = window(len);
     cursor = w.fold((double)clampf(n, 0.0f, 1.0f) * len);
+    stretcher.reset();
   }
   float position_normalized() const { return (buffer && buffer->len() > 1) ? (float)(cursor / (double)buffer->len()) : 0.0f; }   // :497-502
   void prepare_offline_render() { playing = true; gain.snap(); active_gain.set_target(1.0f); active_gain.snap(); restart(); }      // :444-451

@@ -402,7 +402,7 @@ void orc_engine_loop_set_start(void* e, uint32_t ch, float v) { LCH(c->set_loop_
 void orc_engine_loop_set_end(void* e, uint32_t ch, float v) { LCH(c->set_loop_end(v)); }
 void orc_engine_loop_set_speed(void* e, uint32_t ch, float v) { LCH(c->set_speed(v)); }
 void orc_engine_loop_set_source_bpm(void* e, uint32_t ch, float v) { LCH(if (c->buffer) c->buffer->set_source_bpm(v > 0.0f, v)); }
-void orc_engine_loop_set_pitch_mode(void* e, uint32_t ch, uint32_t m) { LCH(c->pitch_mode = (m == 1 ? PITCH_RESAMPLE : (m == 2 ? PITCH_PRESERVE : PITCH_OFF))); }
+void orc_engine_loop_set_pitch_mode(void* e, uint32_t ch, uint32_t m) { LCH(c->set_pitch_mode(m == 1 ? PITCH_RESAMPLE : (m == 2 ? PITCH_PRESERVE : PITCH_OFF))); }
 void orc_engine_loop_restart(void* e, uint32_t ch) { LCH(c->restart()); }
 void orc_engine_loop_set_position(void* e, uint32_t ch, float v) { LCH(c->set_position(v)); }
 #undef LCH

@@ -266,9 +266,18 @@ extern "C" {
 // of 4; left[k] == nullptr: nothing loaded.  cursor / gain_ct / active_ct ([4][2] = current, target) are read and written back.
 int emu_loop_mixer(const float* const* left, const float* const* right, const uint32_t* len, const float* buf_sr, double* cursor, const double* warp,
                    const float* loop_start, const float* loop_end, const float* speed, const uint32_t* playing, float* gain_ct, float* active_ct,
-                   float engine_sr, int frames, float* out_l, float* out_r) {
+                   float engine_sr, int frames, float* out_l, float* out_r, const uint32_t* preserve, const double* warp_pp) {
   LoopMixer m;
   memset(&m, 0, sizeof m);
+  // PreservePitch channels start with no stretcher (built at their first tick); the window table as the host side of the product builds it
+  const uint32_t hop = wsola_hop_len(engine_sr);
+  std::vector<float> hann(2 * hop);
+  for (uint32_t i = 0; i < 2 * hop; i++) hann[i] = wsola_window_coeff(i, 2 * hop);
+  std::vector<std::vector<float>> stretch(LOOP_CHANNELS, std::vector<float>(9 * (size_t)hop, 123.0f));   // junk: a fresh stretcher must not read it
+  for (int k = 0; k < LOOP_CHANNELS; k++) {
+    m.ch[k].preserve = preserve ? preserve[k] : 0u; m.ch[k].warp_pp = warp_pp ? warp_pp[k] : 1.0;
+    m.ch[k].hop = hop; m.ch[k].hann = hann.data(); m.ch[k].st_buf = stretch[k].data();
+  }
   for (int k = 0; k < LOOP_CHANNELS; k++) {
     LoopChan& c = m.ch[k];
     c.left = left[k]; c.right = right[k]; c.len = len[k]; c.buf_sr = buf_sr[k]; c.cursor = cursor[k]; c.warp = warp[k];
@@ -282,6 +291,12 @@ int emu_loop_mixer(const float* const* left, const float* const* right, const ui
     gain_ct[2 * k] = m.ch[k].gain.c; gain_ct[2 * k + 1] = m.ch[k].gain.t; active_ct[2 * k] = m.ch[k].active.c; active_ct[2 * k + 1] = m.ch[k].active.t;
   }
   return 0;
+}
+// the WSOLA window table as the product's host side builds it (EngineBank::attach_stretcher); returns hop_len
+int emu_wsola_window(float engine_sr, float* out, int cap) {
+  const uint32_t hop = wsola_hop_len(engine_sr);
+  for (uint32_t i = 0; i < 2 * hop && (int)i < cap; i++) out[i] = wsola_window_coeff(i, 2 * hop);
+  return (int)hop;
 }
 double emu_window_fold(float loop_start, float loop_end, double len, double p) { return window_fold(loop_window(loop_start, loop_end, len), p); }
 double emu_window_lo(float loop_start, float loop_end, double len) { return loop_window(loop_start, loop_end, len).lo; }

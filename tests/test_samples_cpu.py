@@ -234,6 +234,7 @@ def emu_loop_mixer(chans, engine_sr, frames):
     ln = np.zeros(4, np.uint32); bsr = np.zeros(4, np.float32); cur = np.zeros(4, np.float64); warp = np.ones(4, np.float64)
     st = np.zeros(4, np.float32); en = np.ones(4, np.float32); sp = np.ones(4, np.float32); pl = np.zeros(4, np.uint32)
     g = np.ones((4, 2), np.float32); a = np.ones((4, 2), np.float32)
+    pres = np.zeros(4, np.uint32); wpp = np.ones(4, np.float64)
     keep = []
     for k, ch in enumerate(chans):
         if ch is None:
@@ -245,10 +246,12 @@ def emu_loop_mixer(chans, engine_sr, frames):
         bsr[k] = ch.get("buf_sr", 0.0); cur[k] = ch.get("cursor", 0.0); warp[k] = ch.get("warp", 1.0)
         st[k] = ch.get("start", 0.0); en[k] = ch.get("end", 1.0); sp[k] = ch.get("speed", 1.0); pl[k] = 1 if ch.get("playing") else 0
         g[k] = ch.get("gain", (1.0, 1.0)); a[k] = ch.get("active", (1.0, 1.0))
+        pres[k] = 1 if ch.get("preserve") else 0; wpp[k] = ch.get("warp_pp", 1.0)
     ol = np.zeros(frames, np.float32); orr = np.zeros(frames, np.float32)
     p = lambda arr, t: arr.ctypes.data_as(c.POINTER(t))
     L.emu_loop_mixer(left, right, p(ln, c.c_uint32), p(bsr, c.c_float), p(cur, c.c_double), p(warp, c.c_double), p(st, c.c_float), p(en, c.c_float),
-                     p(sp, c.c_float), p(pl, c.c_uint32), p(g, c.c_float), p(a, c.c_float), c.c_float(engine_sr), frames, p(ol, c.c_float), p(orr, c.c_float))
+                     p(sp, c.c_float), p(pl, c.c_uint32), p(g, c.c_float), p(a, c.c_float), c.c_float(engine_sr), frames, p(ol, c.c_float), p(orr, c.c_float),
+                     p(pres, c.c_uint32), p(wpp, c.c_double))
     return np.stack([ol, orr], 1), cur, g, a
 
 
@@ -374,4 +377,70 @@ def test_loop_source_reaches_the_engine_mix_on_the_loops_track():
     assert o.mixer_route_source(5, 0)
     out = o.render(512)
     assert abs(out[-1, 0] - 0.8 * 0.25) < 1e-3
+    o.close()
+
+
+# ---- mixer/wsola.rs: PitchMode::PreservePitch ------------------------------------------------------------------------------
+def sine_pcm(seconds, hz, sr):
+    n = int(np.float32(sr) * np.float32(seconds))
+    x = np.sin((np.arange(n, dtype=np.float32) / np.float32(sr) * np.float32(hz) * np.float32(2 * np.pi)).astype(np.float32)).astype(np.float32)
+    return x
+
+
+def test_wsola_hop_window_and_constant_overlap_add():               # wsola.rs:480, :488 (through the product's table builder)
+    L = EMU.lib()
+    L.emu_wsola_window.restype = c.c_int
+    L.emu_wsola_window.argtypes = [c.c_float, c.c_void_p, c.c_int]
+    w = np.zeros(4096, np.float32)
+    hop = L.emu_wsola_window(48000.0, w.ctypes.data, 4096)
+    assert hop == 960
+    assert np.abs(w[:hop] + w[hop:2 * hop] - 1.0).max() < 1e-4
+
+
+def test_wsola_produces_finite_output_and_warp_consumes_source_faster(e):   # wsola.rs:497, :510 through the channel
+    slow, fast = O.oracle_engine(48000.0), O.oracle_engine(48000.0)
+    for eng, bpm in ((slow, 100.0), (fast, 200.0)):
+        eng.loop_load(0, sine_pcm(4.0, 220.0, 48000.0), 48000.0)
+        eng.loop_set_source_bpm(0, 100.0); eng.loop_set_pitch_mode(0, 2); eng.set_bpm(bpm); eng.loop_set_playing(0, True)
+        out = tick(eng, 20 * 960)
+        assert np.isfinite(out).all() and np.abs(out).max() > 0.5
+    assert cursor(fast, 0) > cursor(slow, 0)
+    slow.close(); fast.close()
+
+
+def test_preserve_pitch_wrapped_window_is_finite_and_bounded(e):    # loop_channel.rs:911
+    e.loop_set_start(0, 0.75); e.loop_set_end(0, 0.25)
+    e.loop_load(0, sine_pcm(1.0, 220.0, SR), SR)
+    e.loop_set_source_bpm(0, 120.0); e.loop_set_pitch_mode(0, 2); e.set_bpm(150.0); e.loop_set_playing(0, True)
+    out = tick(e, 20000)
+    assert np.isfinite(out).all() and np.abs(out).max() < 2.0
+    p = e.loop_get_position(0)
+    assert p >= 0.75 - 1e-6 or p < 0.25 + 1e-6
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_device_wsola_matches_oracle_bit_for_bit(seed):
+    rng = np.random.default_rng(3000 + seed)
+    engine_sr = [44100.0, 48000.0, 22050.0][seed % 3]
+    o = O.oracle_engine(engine_sr)
+    n = int(rng.integers(3000, 20000))
+    t = np.arange(n) / 44100.0
+    pcm = np.stack([0.5 * np.sin(2 * np.pi * 180 * t) + 0.2 * rng.uniform(-1, 1, n), 0.5 * np.sin(2 * np.pi * 271 * t + 1) + 0.2 * rng.uniform(-1, 1, n)], 1).astype(np.float32)
+    buf_sr = float(rng.choice([44100.0, 48000.0, 32000.0]))
+    start, end = (0.0, 1.0) if seed % 4 == 0 else (float(np.float32(x)) for x in rng.uniform(0, 1, 2))
+    if seed == 5:
+        start, end = 0.5, 0.52                             # too small for a grain: every hop restarts at the loop start
+    speed = float(np.float32(rng.uniform(0.3, 2.0))) if seed % 2 else 1.0
+    src_bpm = float(np.float32(rng.uniform(80, 160)))
+    assert o.loop_load(0, pcm, buf_sr)
+    o.loop_set_start(0, start); o.loop_set_end(0, end); o.loop_set_speed(0, speed); o.loop_restart(0)
+    o.loop_set_source_bpm(0, src_bpm); o.loop_set_pitch_mode(0, 2); o.set_bpm(128.0); o.loop_set_playing(0, True)
+    frames = 6000
+    want = tick(o, frames)
+    ch = dict(left=pcm[:, 0], right=pcm[:, 1], buf_sr=buf_sr, cursor=window_lo(start, end, n), start=start, end=end, speed=speed, playing=True,
+              preserve=True, warp_pp=float(np.float32(128.0)) / src_bpm)
+    got, cur, _, _ = emu_loop_mixer([ch, None, None, None], engine_sr, frames)
+    assert np.abs(want).max() > 0.05
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    assert cur[0] == cursor(o, 0)
     o.close()

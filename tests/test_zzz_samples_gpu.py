@@ -97,6 +97,32 @@ def test_resample_warp_follows_the_engine_tempo():
     assert np.abs(got[0] - want[0]).max() <= EXACT_TOL
 
 
+def test_preserve_pitch_time_stretch_linear_and_wrapped_windows():
+    """PitchMode::PreservePitch (mixer/wsola.rs): grain search, overlap-add, stretcher state across calls, and the events that drop it."""
+    def script(e):
+        e.loop_load(0, pcm(30, 20000), 48000.0)
+        e.loop_set_source_bpm(0, 100.0); e.loop_set_pitch_mode(0, 2); e.set_bpm(140.0)
+        e.loop_set_playing(0, True)
+        e.loop_load(1, pcm(31, 9000), 44100.0)
+        e.loop_set_start(1, 0.7); e.loop_set_end(1, 0.4); e.loop_restart(1)                  # wrap-around window
+        e.loop_set_source_bpm(1, 120.0); e.loop_set_pitch_mode(1, 2); e.loop_set_speed(1, 1.2); e.loop_set_playing(1, True)
+
+    def run(e):
+        a = e.render(5000)
+        b = e.render(3000)                              # the stretchers carry over (mid-hop)
+        e.loop_set_position(0, 0.3)                     # drops channel 0's stretcher: re-seeded at the new cursor
+        e.loop_set_speed(1, -1.0)                       # reverse: channel 1 falls back to the direct read (loop_channel.rs:184)
+        cc = e.render(3000)
+        e.loop_set_pitch_mode(0, 1); e.loop_set_speed(1, 0.9)
+        d = e.render(2000)
+        return np.concatenate([a, b, cc, d]), [e.loop_get_position(k) for k in (0, 1)], e.loop_get_pitch_mode(1)
+    (got, gpos, gm), (want, wpos, wm) = both(script, run)
+    assert gm == wm == 2
+    assert np.abs(want).max() > 0.05
+    assert np.abs(got - want).max() <= EXACT_TOL
+    assert np.allclose(gpos, wpos, atol=1e-6)
+
+
 def test_bounce_with_loops_many_pieces_and_a_global_chain():
     """One bar = 88 200 frames: the lead pieces, double-buffered rows, the time-parallel strips feeding the chain kernel."""
     def script(e):
@@ -223,8 +249,7 @@ def test_requests_for_parts_that_are_not_built_latch_the_sticky_error():
     L.gooey_engine_sampler_set_step.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_bool, c.c_uint32, c.c_float]; L.gooey_engine_sampler_set_step.restype = c.c_bool
     L.gooey_engine_loop_queue_swap.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float, c.c_float, c.c_uint32]
     L.gooey_engine_loop_queue_swap.restype = c.c_bool
-    for call in (lambda e: e.loop_set_pitch_mode(0, 2),
-                 lambda e: L.gooey_engine_loop_effect_add(e._h, 0, 1),
+    for call in (lambda e: L.gooey_engine_loop_effect_add(e._h, 0, 1),
                  lambda e: L.gooey_engine_sampler_set_step(e._h, 0, 0, True, 0, 1.0),
                  lambda e: L.gooey_engine_loop_queue_swap(e._h, 0, pcm(1, 8).ctypes.data, 8, 2, c.c_float(44100.0), c.c_float(0.0), 1)):
         g = G.Engine()
