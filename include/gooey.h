@@ -315,6 +315,8 @@ int32_t gooey_engine_loop_effect_add(GooeyEngine* engine, uint32_t channel, uint
  * (:8006-8048), or (libgooey_b200 addition) the same frames interleaved into out_interleaved[2 * frames]. */
 bool gooey_engine_loop_render_to_wav(GooeyEngine* engine, uint32_t channel, uint32_t frame_count, uint32_t preroll_frame_count, const char* utf8_path);
 bool gooey_engine_loop_render(GooeyEngine* engine, uint32_t channel, uint32_t frames, uint32_t preroll, float* out_interleaved);
+/* libgooey_b200 addition: dst's channel plays the buffer already loaded into src's channel (same device), without another device copy. */
+bool gooey_b200_loop_share_buffer(GooeyEngine* dst, uint32_t dst_channel, const GooeyEngine* src, uint32_t src_channel);
 
 /* ---- sampler racks: up to 4 racks of 16 PCM pads and 32 voices, graph sources GOOEY_SOURCE_SAMPLER_BASE + rack, unrouted until
  * gooey_engine_mixer_route_source (ffi.rs:6000-6172; src/instruments/sampler.rs).  Pads are interleaved f32, 1 or 2 channels.

@@ -49,6 +49,19 @@ bool gooey_engine_loop_load(GooeyEngine* e, uint32_t channel, const float* sampl
   } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
   return true;
 }
+// libgooey_b200 addition: channel `dst_channel` of `dst` plays the buffer already loaded into `src` (same device) without another
+// copy — a batch of engines over one loop keeps one resident buffer instead of one each (as gooey_b200_granulator_share_buffer does
+// for the granulator source).  Otherwise identical to gooey_engine_loop_load: the playhead goes to the loop start, no tempo tag.
+bool gooey_b200_loop_share_buffer(GooeyEngine* dst, uint32_t dst_channel, const GooeyEngine* src, uint32_t src_channel) {
+  GooeyEngine::LoopHost* d = gh::loop_ch(dst, dst_channel);
+  const GooeyEngine::LoopHost* s = gh::loop_ch(src, src_channel);
+  if (!d || !s || !s->buf || s->len == 0 || dst->bank->device != src->bank->device) return false;
+  try { gh::use_device(dst->bank->device); GH_CUDA(cudaStreamSynchronize(dst->bank->stream)); } catch (const std::exception& ex) { gh::set_error(ex.what()); return false; }
+  d->buf = s->buf; d->len = s->len; d->buf_sr = s->buf_sr;
+  d->has_source_bpm = false; d->source_bpm = 0.0f;
+  d->cursor = d->window().lo; d->st_valid = false;
+  return true;
+}
 void gooey_engine_loop_set_playing(GooeyEngine* e, uint32_t ch, bool playing) { if (auto* c = gh::loop_ch(e, ch)) c->playing = playing; }
 void gooey_engine_loop_set_gain(GooeyEngine* e, uint32_t ch, float gain) { if (auto* c = gh::loop_ch(e, ch)) gd::lsm_set(c->gain, gd::clampf(gain, 0.0f, gd::LOOP_MAX_GAIN), 0.0f, gd::LOOP_MAX_GAIN); }
 void gooey_engine_loop_set_mute(GooeyEngine* e, uint32_t ch, bool muted) { if (auto* c = gh::loop_ch(e, ch)) c->muted = muted; }

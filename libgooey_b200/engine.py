@@ -133,6 +133,12 @@ class Engine:
         a, frames, channels = self._pcm(samples)
         return bool(getattr(self._L, self._prefix + "loop_load")(self._h, channel, a.ctypes.data, frames, channels, c.c_float(sample_rate)))
 
+    def loop_share_buffer(self, channel, src, src_channel):
+        """gooey_b200_loop_share_buffer (product only): play the buffer `src` already holds on the device."""
+        f = self._L.gooey_b200_loop_share_buffer
+        f.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint32]; f.restype = c.c_bool
+        return bool(f(self._h, channel, src._h, src_channel))
+
     def loop_render(self, channel, frames, preroll=0):
         """Mixer::render_channel_to_interleaved: [frames, 2] of one loop channel, offline, from its loop start; None on failure."""
         out = np.zeros((frames, 2), np.float32)

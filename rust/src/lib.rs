@@ -72,6 +72,24 @@ extern "C" {
     pub fn gooey_batch_render(engines: *const *mut GooeyEngineOpaque, n: u32, frames: u32, out_host: *mut c_float) -> c_int;
     pub fn gooey_b200_host_alloc(bytes: usize, device: c_int, out_numa_node: *mut c_int) -> *mut std::ffi::c_void;
     pub fn gooey_b200_host_free(p: *mut std::ffi::c_void);
+
+    // sample-playback sources: the reference's own names (`src/ffi.rs:6007-6168`, `:7184-7535`, `:8006-8048`); a host that already
+    // binds libgooey's FFI needs no new declarations for them — listed here for the Rust-side batch host
+    pub fn gooey_engine_loop_load(e: *mut GooeyEngineOpaque, channel: u32, samples: *const c_float, frames: u32, channels: u32, sample_rate: c_float) -> bool;
+    pub fn gooey_engine_loop_set_playing(e: *mut GooeyEngineOpaque, channel: u32, playing: bool);
+    pub fn gooey_engine_loop_set_gain(e: *mut GooeyEngineOpaque, channel: u32, gain: c_float);
+    pub fn gooey_engine_loop_set_start(e: *mut GooeyEngineOpaque, channel: u32, normalized: c_float);
+    pub fn gooey_engine_loop_set_end(e: *mut GooeyEngineOpaque, channel: u32, normalized: c_float);
+    pub fn gooey_engine_loop_set_speed(e: *mut GooeyEngineOpaque, channel: u32, speed: c_float);
+    pub fn gooey_engine_loop_set_source_bpm(e: *mut GooeyEngineOpaque, channel: u32, source_bpm: c_float);
+    pub fn gooey_engine_loop_set_pitch_mode(e: *mut GooeyEngineOpaque, channel: u32, mode: u32);
+    pub fn gooey_engine_loop_render_to_wav(e: *mut GooeyEngineOpaque, channel: u32, frame_count: u32, preroll_frame_count: u32, path: *const c_char) -> bool;
+    pub fn gooey_b200_loop_share_buffer(dst: *mut GooeyEngineOpaque, dst_channel: u32, src: *const GooeyEngineOpaque, src_channel: u32) -> bool;
+    pub fn gooey_engine_sampler_register(e: *mut GooeyEngineOpaque) -> i32;
+    pub fn gooey_engine_sampler_set_slot_buffer(
+        e: *mut GooeyEngineOpaque, rack: u32, slot: u32, samples: *const c_float, frames: u32, channels: u32, sample_rate: c_float,
+    ) -> bool;
+    pub fn gooey_engine_sampler_trigger(e: *mut GooeyEngineOpaque, rack: u32, slot: u32, velocity: c_float) -> bool;
 }
 
 /// Opaque `GooeyEngine` of `include/gooey.h` (the reference's handle type, `src/ffi.rs:670`).

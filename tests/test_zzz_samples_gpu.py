@@ -243,6 +243,28 @@ def test_batch_of_engines_with_and_without_sources():
             assert np.abs(want).max() > 0.01
 
 
+def test_engines_sharing_one_resident_loop_buffer():
+    src = pcm(40, 12000)
+    engines = [G.Engine() for _ in range(6)]
+    assert engines[0].loop_load(1, src, 44100.0)
+    for i, e in enumerate(engines):
+        if i:
+            assert e.loop_share_buffer(i % 4, engines[0], 1)
+            assert not e.loop_share_buffer(4, engines[0], 1) and not e.loop_share_buffer(0, engines[0], 0)      # bad channel / empty source
+        e.loop_set_speed(1 if i == 0 else i % 4, 0.6 + 0.15 * i); e.loop_set_playing(1 if i == 0 else i % 4, True)
+    got = G.batch_render(engines, 9000)
+    for e in engines:
+        e.close()
+    for i in range(6):
+        o = O.oracle_engine()
+        ch = 1 if i == 0 else i % 4
+        o.loop_load(ch, src, 44100.0); o.loop_set_speed(ch, 0.6 + 0.15 * i); o.loop_set_playing(ch, True)
+        want = o.render(9000)
+        o.close()
+        assert np.abs(want).max() > 0.05
+        assert np.abs(got[i] - want).max() <= EXACT_TOL, i
+
+
 def test_requests_for_parts_that_are_not_built_latch_the_sticky_error():
     L = G.lib()
     L.gooey_engine_loop_effect_add.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; L.gooey_engine_loop_effect_add.restype = c.c_int32
