@@ -287,8 +287,8 @@ bool gooey_b200_granulator_share_buffer(GooeyEngine* dst, const GooeyEngine* src
  * the buffer is copied to the device.  Calls act immediately, like the reference's.  Playback state is not touched by a bounce
  * (ffi.rs:7840-7854 resets sequencers and snaps strips only).
  * Pitch modes: Off, Resample (tempo warp shifts pitch) and PreservePitch (WSOLA time-stretch, src/mixer/wsola.rs; reverse speeds
- * fall back to the direct read, loop_channel.rs:184).  This build: gooey_engine_loop_queue_swap and gooey_engine_loop_effect_add latch
- * the sticky error (queued swaps, per-channel effect chains and the clip grid are not built). ---- */
+ * fall back to the direct read, loop_channel.rs:184).  This build: gooey_engine_loop_effect_add latches the sticky error (per-channel
+ * effect chains and the clip grid are not built). ---- */
 #define GOOEY_LOOP_CHANNEL_COUNT 4u            /* src/mixer/mod.rs:32 */
 #define GOOEY_PITCH_MODE_OFF 0u                /* :7163-7168 */
 #define GOOEY_PITCH_MODE_RESAMPLE 1u
@@ -308,8 +308,11 @@ uint32_t gooey_engine_loop_get_pitch_mode(const GooeyEngine* engine, uint32_t ch
 void gooey_engine_loop_restart(GooeyEngine* engine, uint32_t channel);                              /* :7408 */
 void gooey_engine_loop_set_position(GooeyEngine* engine, uint32_t channel, float normalized);       /* :7422 */
 float gooey_engine_loop_get_position(const GooeyEngine* engine, uint32_t channel);                  /* :7516 */
+/* a take staged to replace the channel's buffer at the next boundary of the loop split into `divisions` equal parts (1 = at the wrap) */
 bool gooey_engine_loop_queue_swap(GooeyEngine* engine, uint32_t channel, const float* samples, uint32_t frames, uint32_t channels, float sample_rate,
-                                  float source_bpm, uint32_t divisions);                            /* :7449, not built: false + sticky error */
+                                  float source_bpm, uint32_t divisions);                            /* :7449 */
+void gooey_engine_loop_cancel_queued_swap(GooeyEngine* engine, uint32_t channel);                   /* :7483 */
+uint32_t gooey_engine_loop_swaps_completed(const GooeyEngine* engine, uint32_t channel);            /* :7500 */
 int32_t gooey_engine_loop_effect_add(GooeyEngine* engine, uint32_t channel, uint32_t effect_id);    /* :7536, not built: -1 + sticky error */
 /* Offline render of one loop channel, ignoring mute / solo, from its loop start (mixer/mod.rs:444-476): a stereo 32-bit float WAV
  * (:8006-8048), or (libgooey_b200 addition) the same frames interleaved into out_interleaved[2 * frames]. */

@@ -357,6 +357,10 @@ struct GooeyEngine {
     // (st_valid = false) whenever the cursor is moved from outside so that it re-seeds at the new position
     std::shared_ptr<gh::DevBuf<float>> stretch;
     bool st_valid = false; uint32_t st_have_prev = 0, st_drain = 0; double st_cursor = 0.0;
+    // queue_swap (loop_channel.rs:147-156, 413-423): a take staged to replace the buffer at the next grid boundary of the loop
+    std::shared_ptr<gh::DevBuf<float>> pend_buf;
+    uint32_t pend_len = 0; float pend_sr = 0.0f; bool pend_has_bpm = false; float pend_bpm = 0.0f;
+    uint32_t pend_div = 1; bool has_pending = false; uint32_t swaps_completed = 0;
     // fills the playback half of a device descriptor (shared by engines_render and the offline channel render)
     void describe(gd::LoopChan& d, float engine_bpm) const {
       const bool loaded = buf && len > 0;
@@ -370,10 +374,21 @@ struct GooeyEngine {
       d.gain = gain; d.active = active;
       d.preserve = pitch_mode == 2 ? 1u : 0u;
       d.st_valid = st_valid ? 1u : 0u; d.st_have_prev = st_have_prev; d.st_drain = st_drain; d.st_cursor = st_cursor;
+      const bool queued = has_pending && pend_buf && pend_len > 0;
+      d.has_pending = queued ? 1u : 0u; d.swaps = 0; d.pend_div = pend_div;
+      d.pend_left = queued ? pend_buf->p : nullptr; d.pend_right = queued ? pend_buf->p + pend_len : nullptr;
+      d.pend_len = queued ? pend_len : 0u; d.pend_buf_sr = pend_sr;
+      const double pratio = (pend_has_bpm && pend_bpm > 0.0f && engine_bpm > 0.0f) ? (double)engine_bpm / (double)pend_bpm : 1.0;
+      d.pend_warp = pitch_mode == 1 ? pratio : 1.0; d.pend_warp_pp = pitch_mode != 0 ? pratio : 1.0;
     }
     void absorb(const gd::LoopChan& d) {   // the state a render moved
       cursor = d.cursor; gain = d.gain; active = d.active;
       st_valid = d.st_valid != 0; st_have_prev = d.st_have_prev; st_drain = d.st_drain; st_cursor = d.st_cursor;
+      if (has_pending && d.swaps) {          // the queued take landed: it is the channel's buffer now
+        buf = pend_buf; len = pend_len; buf_sr = pend_sr; has_source_bpm = pend_has_bpm; source_bpm = pend_bpm;
+        pend_buf.reset(); pend_len = 0; has_pending = false;
+        swaps_completed += d.swaps;
+      }
     }
     gd::LoopWindow window() const { return gd::loop_window(loop_start, loop_end, (double)len); }
   } loops[gd::LOOP_CHANNELS];

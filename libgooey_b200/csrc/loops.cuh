@@ -19,8 +19,8 @@
 // aligned grain start (<= ~130 candidates x hop taps of normalised cross-correlation), windows a 2-hop grain and overlap-adds it;
 // the stretcher's buffers (9 hops of floats per channel) live in a device buffer owned by the channel.
 //
-// Not built (a request latches the engine's sticky error instead of rendering different audio): queued buffer swaps,
-// per-channel effect chains, the clip grid and transport-armed sampler patterns.
+// Not built (a request latches the engine's sticky error instead of rendering different audio): per-channel effect chains,
+// the clip grid and transport-armed sampler patterns.
 #pragma once
 #include "dsp.cuh"
 
@@ -87,6 +87,12 @@ struct LoopChan {
   uint32_t preserve;          // the pitch mode is PreservePitch (the stretcher plays while speed >= 0, loop_channel.rs:184)
   uint32_t st_valid;          // a stretcher exists (0: built from the cursor at the next tick, :222-224)
   uint32_t st_have_prev, st_drain, pad;
+  // a buffer queued to replace this one at the next grid boundary of the loop (queue_swap, loop_channel.rs:413-423): the take's
+  // planes, length, rate and the warp ratios its tempo tag gives; `swaps` counts the swaps that landed during this call
+  const float* pend_left; const float* pend_right;
+  double pend_warp, pend_warp_pp;
+  uint32_t pend_len; float pend_buf_sr;
+  uint32_t pend_div, has_pending, swaps, pad2;
 };
 struct LoopMixer { LoopChan ch[LOOP_CHANNELS]; uint32_t row; uint32_t pad; };   // row = index of the stereo row pair this mixer writes
 
@@ -117,23 +123,40 @@ G_HD void loop_read_wrapped(const float* L, const float* R, uint32_t len, double
   orr = cubic_interp(R[i0], R[i1], R[i2], R[i3], frac);
 }
 
-// LoopChannel::advance (:233-279), without the queued-swap check (not built)
+// maybe_swap_pending (:249-276): the queued take lands when this sample crossed a boundary of the loop split into `divisions`
+// equal parts (or wrapped); the phrase restarts from the new buffer's loop start and any stretcher is dropped
+G_HD void loop_maybe_swap(LoopChan& c, double prev_v, double cur_v, double span, bool wrapped) {
+  if (!c.has_pending) return;
+  const double grid = (double)(c.pend_div > 1u ? c.pend_div : 1u);
+  const double prev_idx = floor((prev_v / span) * grid), new_idx = floor((cur_v / span) * grid);
+  if (!(wrapped || new_idx != prev_idx)) return;
+  c.left = c.pend_left; c.right = c.pend_right; c.len = c.pend_len; c.buf_sr = c.pend_buf_sr; c.warp = c.pend_warp; c.warp_pp = c.pend_warp_pp;
+  c.cursor = loop_window(c.loop_start, c.loop_end, (double)c.len).lo;
+  c.st_valid = 0; c.swaps += 1; c.has_pending = 0;
+}
+// LoopChannel::advance (:233-279)
 G_HD void loop_advance(LoopChan& c, float engine_sr) {
   const double len = (double)c.len, source_sr = (double)c.buf_sr;
   const LoopWindow w = loop_window(c.loop_start, c.loop_end, len);
   const double span = w.span > 1.0 ? w.span : 1.0;                 // window.span.max(1.0)
   const double ratio = source_sr / (double)fmaxf(engine_sr, 1.0f);
   const double delta = (double)c.speed * ratio * c.warp;
+  const double prev = c.cursor;
+  double prev_v, cur_v; bool wrapped;
   if (w.wraps) {
-    const double prev_v = window_to_virtual(w, c.cursor);
+    prev_v = window_to_virtual(w, prev);
     const double raw = prev_v + delta;
-    const double cur_v = rem_euclid_d(raw, span);
+    wrapped = !(raw >= 0.0 && raw < span);
+    cur_v = rem_euclid_d(raw, span);
     c.cursor = window_to_physical(w, cur_v);
   } else {
     c.cursor += delta;
-    if (c.cursor >= w.hi) c.cursor = w.lo + rem_euclid_d(c.cursor - w.lo, span);
-    else if (c.cursor < w.lo) c.cursor = w.hi - rem_euclid_d(w.lo - c.cursor, span);
+    wrapped = false;
+    if (c.cursor >= w.hi) { c.cursor = w.lo + rem_euclid_d(c.cursor - w.lo, span); wrapped = true; }
+    else if (c.cursor < w.lo) { c.cursor = w.hi - rem_euclid_d(w.lo - c.cursor, span); wrapped = true; }
+    prev_v = prev - w.lo; cur_v = c.cursor - w.lo;
   }
+  loop_maybe_swap(c, prev_v, cur_v, span, wrapped);
 }
 // ---- mixer/wsola.rs: WSOLA time-stretch (tempo follows engine_bpm / source_bpm, pitch does not) ----------------------------
 G_HD uint32_t wsola_hop_len(float engine_sr) {   // :73-74
@@ -239,10 +262,20 @@ G_HD void wsola_tick(LoopChan& c, float engine_sr, float& ol, float& orr) {
   const LoopWindow w = loop_window(c.loop_start, c.loop_end, (double)c.len);
   const double sr_ratio = (double)c.buf_sr / (double)fmaxf(engine_sr, 1.0f);
   if (!c.st_valid) { c.st_valid = 1; c.st_have_prev = 0; c.st_drain = c.hop; c.st_cursor = c.cursor; }   // WsolaStretcher::new(engine rate, cursor)
-  if (c.st_drain >= c.hop) c.cursor = wsola_synthesize(c, w, sr_ratio, (double)c.speed, c.warp_pp);
+  const double prev = c.cursor;
+  bool wrapped = false;
+  if (c.st_drain >= c.hop) {
+    c.cursor = wsola_synthesize(c, w, sr_ratio, (double)c.speed, c.warp_pp);
+    wrapped = w.wraps ? window_to_virtual(w, c.cursor) < window_to_virtual(w, prev) : c.cursor < prev;     // forward only: moving back = the hop wrapped the loop
+  }
   if (c.st_drain < c.hop) { ol = c.st_buf[c.st_drain]; orr = c.st_buf[c.hop + c.st_drain]; }
   else { ol = 0.0f; orr = 0.0f; }
   c.st_drain += 1;
+  if (c.has_pending) {   // a queued take lands at hop granularity in this mode (:236-261)
+    const double span = w.span > 1.0 ? w.span : 1.0;
+    const double prev_v = w.wraps ? window_to_virtual(w, prev) : prev - w.lo, cur_v = w.wraps ? window_to_virtual(w, c.cursor) : c.cursor - w.lo;
+    loop_maybe_swap(c, prev_v, cur_v, span, wrapped);
+  }
 }
 
 // LoopChannel::tick (:181-208) with an empty effect chain (EffectChain::process of no effects is the identity, effect_chain.rs:294-299)

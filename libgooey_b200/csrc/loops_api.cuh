@@ -96,11 +96,36 @@ float gooey_engine_loop_get_position(const GooeyEngine* e, uint32_t ch) {     /*
   const auto* c = gh::loop_ch(e, ch);
   return (c && c->buf && c->len > 1) ? (float)(c->cursor / (double)c->len) : 0.0f;
 }
-/* not built: they latch the sticky error and report failure */
-bool gooey_engine_loop_queue_swap(GooeyEngine* e, uint32_t, const float*, uint32_t, uint32_t, float, float, uint32_t) {
-  if (e) gh::engine_fail(e, "libgooey_b200: queued loop swaps (loop_channel.rs:413-423) are not built");
-  return false;
+bool gooey_engine_loop_queue_swap(GooeyEngine* e, uint32_t channel, const float* samples, uint32_t frames, uint32_t channels, float sample_rate,
+                                  float source_bpm, uint32_t divisions) {   /* :7449-7476; LoopChannel::queue_swap loop_channel.rs:413-418 */
+  if (!e || !samples || frames == 0 || channels == 0) return false;
+  if (!std::isfinite(sample_rate) || !(sample_rate > 0.0f)) return false;
+  std::vector<float> planes((size_t)2 * frames);
+  for (uint32_t f = 0; f < frames; f++) {
+    const float* fr = samples + (size_t)f * channels;
+    const float l = fr[0], r = channels == 1 ? fr[0] : fr[1];
+    if (!std::isfinite(l) || !std::isfinite(r)) return false;
+    planes[f] = l; planes[(size_t)frames + f] = r;
+  }
+  GooeyEngine::LoopHost* c = gh::loop_ch(e, channel);
+  if (!c) return false;
+  try {
+    auto buf = gh::upload_pcm(e, planes);
+    c->pend_buf = buf; c->pend_len = frames; c->pend_sr = sample_rate;
+    c->pend_has_bpm = source_bpm > 0.0f && std::isfinite(source_bpm); c->pend_bpm = c->pend_has_bpm ? source_bpm : 0.0f;   // tagged before it lands
+    c->pend_div = divisions > 1u ? divisions : 1u;
+    c->has_pending = true;
+  } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
+  return true;
 }
+void gooey_engine_loop_cancel_queued_swap(GooeyEngine* e, uint32_t ch) {      /* :7483-7490 */
+  auto* c = gh::loop_ch(e, ch);
+  if (!c) return;
+  try { gh::use_device(e->bank->device); GH_CUDA(cudaStreamSynchronize(e->bank->stream)); } catch (const std::exception& ex) { gh::set_error(ex.what()); }
+  c->has_pending = false; c->pend_buf.reset(); c->pend_len = 0;
+}
+uint32_t gooey_engine_loop_swaps_completed(const GooeyEngine* e, uint32_t ch) { const auto* c = gh::loop_ch(e, ch); return c ? c->swaps_completed : 0u; }   /* :7500-7508 */
+/* not built: it latches the sticky error and reports failure */
 int32_t gooey_engine_loop_effect_add(GooeyEngine* e, uint32_t, uint32_t) {
   if (e) gh::engine_fail(e, "libgooey_b200: per-loop-channel effect chains (ffi.rs:7536-7655) are not built; put the effect on the track the loop mixer is routed to");
   return -1;

@@ -45,10 +45,11 @@ _SIGS = {
     "loop_set_playing": [c.c_uint32, c.c_bool], "loop_set_gain": [c.c_uint32, c.c_float], "loop_set_mute": [c.c_uint32, c.c_bool],
     "loop_set_solo": [c.c_uint32, c.c_bool], "loop_set_start": [c.c_uint32, c.c_float], "loop_set_end": [c.c_uint32, c.c_float],
     "loop_set_speed": [c.c_uint32, c.c_float], "loop_set_source_bpm": [c.c_uint32, c.c_float], "loop_set_pitch_mode": [c.c_uint32, c.c_uint32],
-    "loop_restart": [c.c_uint32], "loop_set_position": [c.c_uint32, c.c_float],
+    "loop_restart": [c.c_uint32], "loop_set_position": [c.c_uint32, c.c_float], "loop_cancel_queued_swap": [c.c_uint32],
 }
 # functions with a return value: name -> (argument types after the handle, result type)
 _RSIGS = {
+    "loop_swaps_completed": ([c.c_uint32], c.c_uint32),
     "loop_get_source_bpm": ([c.c_uint32], c.c_float), "loop_get_pitch_mode": ([c.c_uint32], c.c_uint32), "loop_get_position": ([c.c_uint32], c.c_float),
     "sampler_register": ([], c.c_int32), "sampler_get_source_id": ([c.c_uint32], c.c_uint32),
     "sampler_clear_slot": ([c.c_uint32, c.c_uint32], c.c_bool), "sampler_slot_is_loaded": ([c.c_uint32, c.c_uint32], c.c_bool),
@@ -71,6 +72,7 @@ def _bind(L, prefix):
         f.argtypes = [c.c_void_p] + args
         f.restype = res
     f = getattr(L, prefix + "loop_load"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]; f.restype = c.c_bool
+    f = getattr(L, prefix + "loop_queue_swap"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float, c.c_float, c.c_uint32]; f.restype = c.c_bool
     f = getattr(L, prefix + "loop_render"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_uint32, c.c_void_p]; f.restype = c.c_bool
     f = getattr(L, prefix + "sampler_set_slot_buffer"); f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float]; f.restype = c.c_bool
     getattr(L, prefix + "new").restype = c.c_void_p
@@ -132,6 +134,11 @@ class Engine:
     def loop_load(self, channel, samples, sample_rate):
         a, frames, channels = self._pcm(samples)
         return bool(getattr(self._L, self._prefix + "loop_load")(self._h, channel, a.ctypes.data, frames, channels, c.c_float(sample_rate)))
+
+    def loop_queue_swap(self, channel, samples, sample_rate, source_bpm=0.0, divisions=1):
+        a, frames, channels = self._pcm(samples)
+        return bool(getattr(self._L, self._prefix + "loop_queue_swap")(self._h, channel, a.ctypes.data, frames, channels, c.c_float(sample_rate),
+                                                                        c.c_float(source_bpm), divisions))
 
     def loop_share_buffer(self, channel, src, src_channel):
         """gooey_b200_loop_share_buffer (product only): play the buffer `src` already holds on the device."""

@@ -4,7 +4,7 @@
 //   instruments/sampler.rs (SamplerBuffer, SampleVoice, SamplerRack).
 //   mixer/wsola.rs (WsolaStretcher, PitchMode::PreservePitch).
 // Restated: everything a bounce touches with empty per-channel effect chains.  Not restated (the product refuses the same
-// requests): queued swaps, per-channel effect chains, the clip grid, transport-armed sampler patterns.  Parity unpinned like the rest of the oracle (no reference
+// requests): per-channel effect chains, the clip grid, transport-armed sampler patterns.  Parity unpinned like the rest of the oracle (no reference
 // build here); the reference's own unit tests of these files are restated in tests/test_samples_cpu.py.
 #pragma once
 #include <memory>
@@ -202,6 +202,24 @@ struct LoopChannel {
   int pitch_mode = PITCH_OFF;
   float engine_bpm = 120.0f;
   std::shared_ptr<WsolaStretcher> stretcher;            // lazily built in PreservePitch mode, dropped whenever the cursor is moved from outside
+  std::shared_ptr<StereoSampleBuffer> pending;          // queue_swap (:413-423): replaces `buffer` at the next grid boundary
+  uint32_t pending_divisions = 1; bool has_pending = false; uint32_t swaps_completed = 0;
+  void queue_swap(std::shared_ptr<StereoSampleBuffer> b, uint32_t divisions) { pending_divisions = divisions > 1 ? divisions : 1; pending = std::move(b); has_pending = true; }
+  void cancel_queued_swap() { has_pending = false; pending.reset(); }
+  void maybe_swap_pending(double prev_v, double cur_v, double span, bool wrapped) {  // :249-276
+    if (!has_pending) return;
+    double grid = (double)(pending_divisions > 1 ? pending_divisions : 1);
+    double prev_idx = std::floor((prev_v / span) * grid), new_idx = std::floor((cur_v / span) * grid);
+    if (!(wrapped || new_idx != prev_idx)) return;
+    if (pending) {
+      double new_lo = window((double)pending->len()).lo;
+      buffer = std::move(pending); pending.reset();
+      cursor = new_lo;
+      stretcher.reset();
+      swaps_completed += 1;
+      has_pending = false;
+    }
+  }
   explicit LoopChannel(float sr) : gain(1.0f, 0.0f, 2.0f, sr, 15.0f), active_gain(1.0f, 0.0f, 1.0f, sr, 15.0f) {}   // :157-178
   bool has_buffer() const { return buffer && buffer->len() > 0; }
   LoopWindow window(double len) const {  // :293-307
@@ -216,7 +234,7 @@ struct LoopChannel {
     if (buffer && buffer->has_source_bpm && buffer->source_bpm > 0.0f && engine_bpm > 0.0f) return (double)engine_bpm / (double)buffer->source_bpm;
     return 1.0;
   }
-  void advance(float engine_sr) {  // :233-279 (no queued swap)
+  void advance(float engine_sr) {  // :233-279
     if (!buffer) return;
     double len = (double)buffer->len(), source_sr = (double)buffer->sample_rate;
     LoopWindow w = window(len);
@@ -224,16 +242,21 @@ struct LoopChannel {
     double ratio = source_sr / (double)rust_max(engine_sr, 1.0f);
     double warp = pitch_mode == PITCH_RESAMPLE ? warp_ratio() : 1.0;
     double delta = (double)speed * ratio * warp;
+    double prev = cursor, prev_v, cur_v; bool wrapped;
     if (w.wraps) {
-      double prev_v = w.to_virtual(cursor);
+      prev_v = w.to_virtual(prev);
       double raw = prev_v + delta;
-      double cur_v = rem_euclid(raw, span);
+      wrapped = !(0.0 <= raw && raw < span);
+      cur_v = rem_euclid(raw, span);
       cursor = w.to_physical(cur_v);
     } else {
       cursor += delta;
-      if (cursor >= w.hi) cursor = w.lo + rem_euclid(cursor - w.lo, span);
-      else if (cursor < w.lo) cursor = w.hi - rem_euclid(w.lo - cursor, span);
+      wrapped = false;
+      if (cursor >= w.hi) { cursor = w.lo + rem_euclid(cursor - w.lo, span); wrapped = true; }
+      else if (cursor < w.lo) { cursor = w.hi - rem_euclid(w.lo - cursor, span); wrapped = true; }
+      prev_v = prev - w.lo; cur_v = cursor - w.lo;
     }
+    maybe_swap_pending(prev_v, cur_v, span, wrapped);
   }
   StereoFrame tick(float engine_sr) {  // :181-208
     StereoFrame dry;
@@ -248,14 +271,22 @@ struct LoopChannel {
     StereoFrame gained = dry.scaled(gain.tick());
     return gained.scaled(active_gain.tick());          // empty EffectChain in between
   }
-  StereoFrame tick_preserve_pitch(float engine_sr) {  // :215-262 (no queued swap)
+  StereoFrame tick_preserve_pitch(float engine_sr) {  // :215-262
     double len = (double)buffer->len();
     LoopWindow w = window(len);
     double sr_ratio = (double)buffer->sample_rate / (double)rust_max(engine_sr, 1.0f);
     double warp = warp_ratio(), sp = (double)speed;
     if (!stretcher) stretcher = std::make_shared<WsolaStretcher>(engine_sr, cursor);
-    if (stretcher->needs_refill()) cursor = stretcher->synthesize_next_hop(*buffer, w, sr_ratio, sp, warp);
-    return stretcher->drain();
+    double prev = cursor; bool wrapped = false;
+    if (stretcher->needs_refill()) {
+      cursor = stretcher->synthesize_next_hop(*buffer, w, sr_ratio, sp, warp);
+      wrapped = w.wraps ? w.to_virtual(cursor) < w.to_virtual(prev) : cursor < prev;
+    }
+    StereoFrame out = stretcher->drain();
+    double span = w.span > 1.0 ? w.span : 1.0;
+    double prev_v = w.wraps ? w.to_virtual(prev) : prev - w.lo, cur_v = w.wraps ? w.to_virtual(cursor) : cursor - w.lo;
+    maybe_swap_pending(prev_v, cur_v, span, wrapped);        // hop granularity in this mode (:236-261)
+    return out;
   }
   void set_pitch_mode(int m) { if (pitch_mode == PITCH_PRESERVE && m != PITCH_PRESERVE) stretcher.reset(); pitch_mode = m; }   // :341-346
   void set_buffer(std::shared_ptr<StereoSampleBuffer> b) { double len = (double)b->len(); buffer = std::move(b); cursor = window(len).lo; stretcher.reset(); }   // :311-316

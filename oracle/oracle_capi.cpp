@@ -405,7 +405,19 @@ void orc_engine_loop_set_source_bpm(void* e, uint32_t ch, float v) { LCH(if (c->
 void orc_engine_loop_set_pitch_mode(void* e, uint32_t ch, uint32_t m) { LCH(c->set_pitch_mode(m == 1 ? PITCH_RESAMPLE : (m == 2 ? PITCH_PRESERVE : PITCH_OFF))); }
 void orc_engine_loop_restart(void* e, uint32_t ch) { LCH(c->restart()); }
 void orc_engine_loop_set_position(void* e, uint32_t ch, float v) { LCH(c->set_position(v)); }
+void orc_engine_loop_cancel_queued_swap(void* e, uint32_t ch) { LCH(c->cancel_queued_swap()); }
 #undef LCH
+bool orc_engine_loop_queue_swap(void* e, uint32_t ch, const float* samples, uint32_t frames, uint32_t channels, float sr, float source_bpm, uint32_t divisions) {  // ffi.rs:7449-7476
+  if (!e || !samples || frames == 0 || channels == 0) return false;
+  auto b = StereoSampleBuffer::from_interleaved(samples, (size_t)frames * channels, channels, sr);
+  if (!b) return false;
+  b->set_source_bpm(source_bpm > 0.0f, source_bpm);
+  LoopChannel* c = E->mixer.ch(ch);
+  if (!c) return false;
+  c->queue_swap(b, divisions);
+  return true;
+}
+uint32_t orc_engine_loop_swaps_completed(void* e, uint32_t ch) { if (!e) return 0; LoopChannel* c = E->mixer.ch(ch); return c ? c->swaps_completed : 0u; }
 float orc_engine_loop_get_source_bpm(void* e, uint32_t ch) { if (!e) return 0.0f; LoopChannel* c = E->mixer.ch(ch); return (c && c->buffer && c->buffer->has_source_bpm) ? c->buffer->source_bpm : 0.0f; }
 uint32_t orc_engine_loop_get_pitch_mode(void* e, uint32_t ch) { if (!e) return 0; LoopChannel* c = E->mixer.ch(ch); return c ? (uint32_t)c->pitch_mode : 0u; }
 float orc_engine_loop_get_position(void* e, uint32_t ch) { if (!e) return 0.0f; LoopChannel* c = E->mixer.ch(ch); return c ? c->position_normalized() : 0.0f; }

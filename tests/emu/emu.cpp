@@ -261,7 +261,14 @@ int emu_math(int kind, const float* a, const float* b, float sr, float* out, uin
 
 // ---- sample-playback sources (libgooey_b200/csrc/loops.cuh): the loop mixer and the sampler rack ticks on the host ----------
 #include "../../libgooey_b200/csrc/loops.cuh"
+static LoopChan g_pending[LOOP_CHANNELS];     // queued takes for the next emu_loop_mixer call (has_pending = 0: none)
+static uint32_t g_swaps[LOOP_CHANNELS];
 extern "C" {
+void emu_loop_queue(int k, const float* left, const float* right, uint32_t len, float buf_sr, double warp, double warp_pp, uint32_t divisions) {
+  LoopChan& p = g_pending[k];
+  p.pend_left = left; p.pend_right = right; p.pend_len = len; p.pend_buf_sr = buf_sr; p.pend_warp = warp; p.pend_warp_pp = warp_pp; p.pend_div = divisions; p.has_pending = left ? 1u : 0u;
+}
+uint32_t emu_loop_swaps(int k) { return g_swaps[k]; }
 // One LoopMixer descriptor driven for `frames` frames, exactly like ext_source_kernel<LoopMixer> drives it.  Per-channel arrays
 // of 4; left[k] == nullptr: nothing loaded.  cursor / gain_ct / active_ct ([4][2] = current, target) are read and written back.
 int emu_loop_mixer(const float* const* left, const float* const* right, const uint32_t* len, const float* buf_sr, double* cursor, const double* warp,
@@ -277,6 +284,10 @@ int emu_loop_mixer(const float* const* left, const float* const* right, const ui
   for (int k = 0; k < LOOP_CHANNELS; k++) {
     m.ch[k].preserve = preserve ? preserve[k] : 0u; m.ch[k].warp_pp = warp_pp ? warp_pp[k] : 1.0;
     m.ch[k].hop = hop; m.ch[k].hann = hann.data(); m.ch[k].st_buf = stretch[k].data();
+    const LoopChan& q = g_pending[k];
+    m.ch[k].pend_left = q.pend_left; m.ch[k].pend_right = q.pend_right; m.ch[k].pend_len = q.pend_len; m.ch[k].pend_buf_sr = q.pend_buf_sr;
+    m.ch[k].pend_warp = q.pend_warp; m.ch[k].pend_warp_pp = q.pend_warp_pp; m.ch[k].pend_div = q.pend_div; m.ch[k].has_pending = q.has_pending;
+    g_pending[k].has_pending = 0;
   }
   for (int k = 0; k < LOOP_CHANNELS; k++) {
     LoopChan& c = m.ch[k];
@@ -287,6 +298,7 @@ int emu_loop_mixer(const float* const* left, const float* const* right, const ui
   const float coeff15 = smooth_coeff(engine_sr, LOOP_FADER_MS);
   for (int f = 0; f < frames; f++) loop_mixer_tick(m, engine_sr, coeff15, out_l[f], out_r[f]);
   for (int k = 0; k < LOOP_CHANNELS; k++) {
+    g_swaps[k] = m.ch[k].swaps;
     cursor[k] = m.ch[k].cursor;
     gain_ct[2 * k] = m.ch[k].gain.c; gain_ct[2 * k + 1] = m.ch[k].gain.t; active_ct[2 * k] = m.ch[k].active.c; active_ct[2 * k + 1] = m.ch[k].active.t;
   }

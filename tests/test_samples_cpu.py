@@ -444,3 +444,85 @@ def test_device_wsola_matches_oracle_bit_for_bit(seed):
     assert np.array_equal(got, want), np.abs(got - want).max()
     assert cur[0] == cursor(o, 0)
     o.close()
+
+
+# ---- queued swaps (loop_channel.rs:413-423, 249-276) ------------------------------------------------------------------------
+def test_queued_swap_lands_at_first_division_boundary(e):          # :708
+    e.loop_load(0, ramp(100), SR); e.loop_set_playing(0, True)
+    assert e.loop_queue_swap(0, dc(1000.0, 100), SR, divisions=4)
+    out = tick(e, 48)[:, 0]
+    idx = int(np.argmax(out > 500.0))
+    assert out[idx] > 500.0 and 24 <= idx <= 27
+    assert e.loop_swaps_completed(0) == 1
+
+
+def test_queued_swap_divisions_one_only_swaps_at_wrap(e):          # :734
+    e.loop_load(0, ramp(100), SR); e.loop_set_playing(0, True)
+    e.loop_queue_swap(0, dc(1000.0, 100), SR, divisions=1)
+    assert (tick(e, 90)[:, 0] < 500.0).all() and e.loop_swaps_completed(0) == 0
+    tick(e, 20)
+    assert e.loop_swaps_completed(0) == 1
+
+
+def test_cancel_drops_and_requeue_replaces_the_queued_swap(e):     # :754, :768
+    e.loop_load(0, ramp(100), SR); e.loop_set_playing(0, True)
+    e.loop_queue_swap(0, dc(1000.0, 100), SR, divisions=4)
+    e.loop_cancel_queued_swap(0)
+    assert (tick(e, 150)[:, 0] < 500.0).all() and e.loop_swaps_completed(0) == 0
+    e.loop_restart(0)
+    e.loop_queue_swap(0, dc(-1000.0, 100), SR, divisions=4)
+    e.loop_queue_swap(0, dc(2000.0, 100), SR, divisions=4)
+    tick(e, 40)
+    assert e.loop_swaps_completed(0) == 1 and tick(e, 1)[0, 0] > 1500.0
+
+
+def test_queued_swap_lands_in_wrapped_window(e):                   # :889
+    e.loop_set_start(0, 0.7); e.loop_set_end(0, 0.3)
+    e.loop_load(0, ramp(10), SR); e.loop_set_playing(0, True)
+    e.loop_queue_swap(0, dc(1000.0, 10), SR, divisions=1)
+    tick(e, 5)
+    assert e.loop_swaps_completed(0) == 0
+    tick(e, 4)
+    assert e.loop_swaps_completed(0) == 1 and tick(e, 1)[0, 0] > 500.0
+
+
+@pytest.mark.parametrize("seed", range(9))
+def test_device_queued_swap_matches_oracle_bit_for_bit(seed):
+    """The take lands on the same sample, the phrase restarts on the new buffer with ITS rate and tempo tag: direct, wrapped, Resample and
+    PreservePitch channels."""
+    rng = np.random.default_rng(4000 + seed)
+    engine_sr = 44100.0
+    mode = seed % 3                                             # pitch mode
+    o = O.oracle_engine(engine_sr)
+    # (a PreservePitch loop too short for a second grain restarts at its loop start every hop: the cursor never moves and the take never
+    # lands — the reference's behaviour, so the stretched cases get a longer phrase and a grid of at least two divisions)
+    n = int(rng.integers(9000, 14000)) if mode == 2 else int(rng.integers(2500, 6000))
+    a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    nb = int(rng.integers(2500, 6000))
+    b = (2.0 + rng.uniform(-1, 1, (nb, 2))).astype(np.float32)
+    sr_a, sr_b = float(rng.choice([44100.0, 48000.0])), float(rng.choice([44100.0, 32000.0]))
+    start, end = ((0.0, 1.0), (0.1, 0.8), (0.75, 0.3))[seed // 3]
+    speed = 1.0 if mode == 2 else float(np.float32(rng.uniform(0.5, 1.5))) * (-1.0 if seed == 4 else 1.0)
+    bpm_a, bpm_b = float(np.float32(rng.uniform(90, 150))), float(np.float32(rng.uniform(90, 150)))
+    div = int(rng.integers(2 if mode == 2 else 1, 6))
+    assert o.loop_load(0, a, sr_a)
+    o.loop_set_start(0, start); o.loop_set_end(0, end); o.loop_set_speed(0, speed); o.loop_restart(0)
+    o.loop_set_source_bpm(0, bpm_a); o.loop_set_pitch_mode(0, mode); o.set_bpm(120.0); o.loop_set_playing(0, True)
+    assert o.loop_queue_swap(0, b, sr_b, bpm_b, div)
+    frames = 9000
+    want = tick(o, frames)
+    assert o.loop_swaps_completed(0) == 1 and want[:, 0].max() > 1.5
+    L = EMU.lib()
+    fp = c.POINTER(c.c_float)
+    bl, br = np.ascontiguousarray(b[:, 0]), np.ascontiguousarray(b[:, 1])
+    ratio_a, ratio_b = float(np.float32(120.0)) / bpm_a, float(np.float32(120.0)) / bpm_b
+    L.emu_loop_queue.argtypes = [c.c_int, fp, fp, c.c_uint32, c.c_float, c.c_double, c.c_double, c.c_uint32]
+    L.emu_loop_queue(0, bl.ctypes.data_as(fp), br.ctypes.data_as(fp), nb, sr_b, ratio_b if mode == 1 else 1.0, ratio_b if mode else 1.0, div)
+    ch = dict(left=a[:, 0], right=a[:, 1], buf_sr=sr_a, cursor=window_lo(start, end, n), start=start, end=end, speed=speed, playing=True,
+              warp=ratio_a if mode == 1 else 1.0, preserve=mode == 2, warp_pp=ratio_a if mode else 1.0)
+    got, cur, _, _ = emu_loop_mixer([ch, None, None, None], engine_sr, frames)
+    L.emu_loop_swaps.restype = c.c_uint32
+    assert L.emu_loop_swaps(0) == 1
+    assert np.array_equal(got, want), (np.abs(got - want).max(), int(np.argmax((got != want).any(1))))
+    assert cur[0] == cursor(o, 0)
+    o.close()

@@ -123,6 +123,33 @@ def test_preserve_pitch_time_stretch_linear_and_wrapped_windows():
     assert np.allclose(gpos, wpos, atol=1e-6)
 
 
+def test_queued_swaps_land_on_the_grid_and_carry_their_own_rate_and_tempo():
+    """gooey_engine_loop_queue_swap (loop_channel.rs:413-423, 249-276): the take replaces the buffer at the first grid boundary, the count
+    and the new tempo tag are visible afterwards, a cancelled take never lands, a second queue replaces the first."""
+    def run(e):
+        e.set_bpm(126.0)
+        e.loop_load(0, pcm(50, 6000), 44100.0); e.loop_set_source_bpm(0, 110.0); e.loop_set_pitch_mode(0, 1); e.loop_set_playing(0, True)
+        e.loop_load(1, pcm(51, 5000), 48000.0); e.loop_set_start(1, 0.7); e.loop_set_end(1, 0.2); e.loop_restart(1); e.loop_set_playing(1, True)
+        e.loop_load(2, pcm(52, 20000), 44100.0); e.loop_set_source_bpm(2, 100.0); e.loop_set_pitch_mode(2, 2); e.loop_set_playing(2, True)
+        a = e.render(1000)
+        assert e.loop_queue_swap(0, pcm(53, 4000) * 0.5, 32000.0, 140.0, 4)
+        assert e.loop_queue_swap(1, pcm(54, 3000, channels=1), 44100.0, 0.0, 1)
+        assert e.loop_queue_swap(2, pcm(55, 15000), 44100.0, 90.0, 3)
+        assert e.loop_queue_swap(3, pcm(56, 100), 44100.0, 0.0, 1)          # nothing plays on channel 3: it can never land
+        b = e.render(9000)
+        info1 = [e.loop_swaps_completed(k) for k in range(4)], e.loop_get_source_bpm(0), e.loop_get_source_bpm(2)
+        e.loop_queue_swap(0, pcm(57, 2000), 44100.0, 0.0, 2); e.loop_cancel_queued_swap(0)
+        e.loop_queue_swap(1, pcm(58, 2000), 44100.0, 0.0, 2); e.loop_queue_swap(1, pcm(59, 2500) * 0.25, 44100.0, 0.0, 2)
+        cc = e.render(5000)
+        info2 = [e.loop_swaps_completed(k) for k in range(4)]
+        return np.concatenate([a, b, cc]), info1, info2
+    (got, g1, g2), (want, w1, w2) = both(lambda e: None, run)
+    assert g1 == w1 == ([1, 1, 1, 0], 140.0, 90.0)
+    assert g2 == w2 == [1, 2, 1, 0]
+    assert np.abs(want).max() > 0.05
+    assert np.abs(got - want).max() <= EXACT_TOL
+
+
 def test_bounce_with_loops_many_pieces_and_a_global_chain():
     """One bar = 88 200 frames: the lead pieces, double-buffered rows, the time-parallel strips feeding the chain kernel."""
     def script(e):
@@ -269,11 +296,8 @@ def test_requests_for_parts_that_are_not_built_latch_the_sticky_error():
     L = G.lib()
     L.gooey_engine_loop_effect_add.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; L.gooey_engine_loop_effect_add.restype = c.c_int32
     L.gooey_engine_sampler_set_step.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_bool, c.c_uint32, c.c_float]; L.gooey_engine_sampler_set_step.restype = c.c_bool
-    L.gooey_engine_loop_queue_swap.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint32, c.c_uint32, c.c_float, c.c_float, c.c_uint32]
-    L.gooey_engine_loop_queue_swap.restype = c.c_bool
     for call in (lambda e: L.gooey_engine_loop_effect_add(e._h, 0, 1),
-                 lambda e: L.gooey_engine_sampler_set_step(e._h, 0, 0, True, 0, 1.0),
-                 lambda e: L.gooey_engine_loop_queue_swap(e._h, 0, pcm(1, 8).ctypes.data, 8, 2, c.c_float(44100.0), c.c_float(0.0), 1)):
+                 lambda e: L.gooey_engine_sampler_set_step(e._h, 0, 0, True, 0, 1.0)):
         g = G.Engine()
         assert not g.has_error()
         call(g)
