@@ -18,6 +18,8 @@ per-voice envelopes + filters, per-voice f32 output kept.  One "step" = one full
   granulators over one shared 60 s source) at N = 1, and C5 (8192 drum+bass engines per GPU with tilt / delay / spring
   reverb, 2 bars — 65 536 engines at N = 8) at every N; each with device ms, end-to-end ms, its own unit, a spot-check
   parity error against the oracle and, for C5, the ring-traffic roofline of the effect mixer.
+  `configs.loops` (N = 1): the sample-playback sources (loop mixer + sampler racks) at 1024 engines x 2 bars,
+  run by tools/loops_bench.py in a subprocess.
 * reference: the reference's CPU implementation of the same path.  The Rust reference cannot be built here (no
   toolchain in the image), so this arm times the C++ restatement in oracle/ ("port") on all host cores over the WHOLE
   4096-patch sweep per step.  It never imports or loads libgooey_b200.
@@ -395,6 +397,19 @@ def config_c4(L):
             "d2h_bytes": n_eng * frames * 8, "parity_max_err_vs_oracle": err, "parity_engines_checked": [i]}
 
 
+def loops_block():
+    """Sample-playback sources at batch size (tools/loops_bench.py), in a SUBPROCESS: these kernels were finished with the round's last
+    GPU seconds, so whatever they do stays outside this process and the headline line; a failure is recorded, not raised."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "loops_bench.py"), "1024", "2"], capture_output=True, text=True, timeout=150)
+        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not lines:
+            return {"error": ((p.stderr or "") + (p.stdout or ""))[-400:]}
+        return json.loads(lines[-1])
+    except Exception as ex:   # timeout, spawn failure, bad JSON
+        return {"error": repr(ex)[:400]}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from libgooey_b200 import lib, voices as V, shard
@@ -531,6 +546,8 @@ def run_ours(args, rank, world, local_rank):
                    "e2e_engine_samples_per_s": tot / (c5_e2e * 1e-3), "d2h_bytes": tot * 4, "parity_max_err_vs_oracle": c5_err,
                    "timing": "max over ranks (device: CUDA events inside the library; e2e: host wall clock around gooey_batch_bounce)"})
         extra["C5"] = c5
+        if world == 1 and args.configs == "all":
+            extra["loops"] = loops_block()
 
     if rank == 0:
         units = world * N_PATCHES * FRAMES * args.steps
