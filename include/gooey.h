@@ -323,8 +323,7 @@ bool gooey_b200_loop_share_buffer(GooeyEngine* dst, uint32_t dst_channel, const 
 
 /* ---- sampler racks: up to 4 racks of 16 PCM pads and 32 voices, graph sources GOOEY_SOURCE_SAMPLER_BASE + rack, unrouted until
  * gooey_engine_mixer_route_source (ffi.rs:6000-6172; src/instruments/sampler.rs).  Pads are interleaved f32, 1 or 2 channels.
- * This build: pads are fired with gooey_engine_sampler_trigger; the transport-armed step pattern (gooey_engine_sampler_set_step,
- * :6173-6290) latches the sticky error. ---- */
+ * Pads are fired by gooey_engine_sampler_trigger (at once) or by the rack's step pattern below. ---- */
 #define GOOEY_SAMPLER_RACK_MAX 4u              /* :585 */
 #define GOOEY_SAMPLER_SLOT_COUNT 16u           /* sampler.rs:14 */
 int32_t gooey_engine_sampler_register(GooeyEngine* engine);                                          /* :6007, rack id or -1 */
@@ -337,7 +336,18 @@ uint32_t gooey_engine_sampler_slot_frames(const GooeyEngine* engine, uint32_t ra
 uint32_t gooey_engine_sampler_slot_channels(const GooeyEngine* engine, uint32_t rack, uint32_t slot);   /* :6119 */
 float gooey_engine_sampler_slot_sample_rate(const GooeyEngine* engine, uint32_t rack, uint32_t slot);   /* :6134 */
 bool gooey_engine_sampler_trigger(GooeyEngine* engine, uint32_t rack, uint32_t slot, float velocity);   /* :6150 */
-bool gooey_engine_sampler_set_step(GooeyEngine* engine, uint32_t rack, uint32_t step, bool enabled, uint32_t slot, float velocity);   /* :6173, not built: false + sticky error */
+/* the rack's 16-step pattern: a start is armed on the transport beat (gooey_engine_sequencer_start runs the transport) and quantised to
+ * the next sixteenth / quarter / bar; with the transport stopped it is armed at beat 0 and fires when the transport starts */
+#define GOOEY_CLIP_QUANTIZE_SIXTEENTH 0u       /* src/mixer/clip_grid.rs:8-10 */
+#define GOOEY_CLIP_QUANTIZE_QUARTER 1u
+#define GOOEY_CLIP_QUANTIZE_BAR 2u
+bool gooey_engine_sampler_set_step(GooeyEngine* engine, uint32_t rack, uint32_t step, bool enabled, uint32_t slot, float velocity);   /* :6173 */
+bool gooey_engine_sampler_get_step(const GooeyEngine* engine, uint32_t rack, uint32_t step, bool* out_enabled, uint32_t* out_slot, float* out_velocity);   /* :6265 */
+bool gooey_engine_sampler_start_pattern(GooeyEngine* engine, uint32_t rack, uint32_t quantization);  /* :6192 */
+bool gooey_engine_sampler_stop_pattern(GooeyEngine* engine, uint32_t rack);                          /* :6211 */
+bool gooey_engine_sampler_cancel_pattern_start(GooeyEngine* engine, uint32_t rack);                  /* :6225 */
+double gooey_engine_sampler_get_pending_start_beat(const GooeyEngine* engine, uint32_t rack);        /* :6239, -1 when none */
+bool gooey_engine_sampler_is_pattern_running(const GooeyEngine* engine, uint32_t rack);              /* :6253 */
 
 #ifdef __cplusplus
 }

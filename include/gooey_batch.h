@@ -124,6 +124,13 @@ void gooey_b200_host_free(void* p);
 uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing, const uint8_t* enabled, const float* velocity, uint32_t steps,
                                        uint32_t frames, uint32_t* out_frames, float* out_velocity, uint32_t capacity);
 
+/* Host-only (no device): the pad hits a sampler rack's 16-step pattern resolves to over a sequence of render calls — the schedule the host
+ * hands to the device (reference: SamplerRack::activate_start_if_due / tick_sequencer, src/instruments/sampler.rs:232-275; the transport,
+ * src/mixer/clip_grid.rs:174-191, 656-660).  pending_beat < 0: the pattern already runs.  Returns the number of hits (may exceed capacity). */
+uint32_t gooey_b200_sampler_schedule(float sample_rate, float bpm, float swing, const uint8_t* enabled, const uint8_t* pads, const float* velocity,
+                                     int transport_running, double transport_beat, double pending_beat, int bounce, const uint32_t* calls, uint32_t n_calls,
+                                     uint32_t* out_frames, uint32_t* out_pads, float* out_velocity, uint32_t capacity, double* out_transport_beat);
+
 #ifdef __cplusplus
 }
 #endif

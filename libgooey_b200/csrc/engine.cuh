@@ -36,6 +36,16 @@ struct HostSeq {
   void start() { running = true; next_trigger = sample_count; }
   void stop() { running = false; }
   void reset() { sample_count = 0; next_trigger = 0; current_step = 0; }
+  void set_beat_position(double beat) {   // :658-682 (a step is a 16th note = 1/4 beat); `start()` afterwards fires the landing step
+    const size_t n = pattern.size();
+    if (n == 0) return;
+    const double step_f = beat * 4.0, fl = floor(step_f), frac = step_f - fl;
+    current_step = (size_t)fl % n;
+    const double off = frac * (double)sps;
+    sample_count = off <= 0.0 ? 0 : (uint64_t)off;
+    const double nt = round((double)sps - frac * (double)sps);
+    next_trigger = nt <= 0.0 ? 0 : (uint64_t)nt;
+  }
   void swing_ticks(uint64_t n) { while (n > 0 && sw_cur != sw_tgt) { gd::smooth_tick(sw_cur, sw_tgt, sw_coeff); n--; } }
   void run(uint32_t frames, std::vector<SeqFire>& out) {
     uint32_t f = 0;
@@ -57,6 +67,68 @@ struct HostSeq {
     }
   }
 };
+
+// ---- sampler-rack patterns on the mixer's transport (host side; needs no device) -----------------------------------------------------
+// The clip-grid transport as far as the racks need it (clip_grid.rs:144-195, 526-579, 656-660): a beat clock that advances by
+// bpm / (60 sr) per rendered frame while running — accumulated add by add like the reference, but only when somebody looks (`lazy` =
+// frames rendered since the last look), so batches that never query it pay nothing.
+struct Transport {
+  bool running = false; double beat = 0.0; float bpm = 120.0f, sr = 44100.0f; uint64_t lazy = 0;
+  double beats_per_sample() const { return (double)fmaxf(bpm, 0.0f) / (60.0 * (double)fmaxf(sr, 1.0f)); }
+  double now() { const double bps = beats_per_sample(); for (; lazy; lazy--) beat += bps; return beat; }
+  void set_bpm(float b) { if (std::isfinite(b) && b > 0.0f) { now(); bpm = b; } }    // ClipGrid::set_bpm (:520-524): beats so far at the old tempo
+  double quantized_target(double interval) {                                         // :174-191: strictly the NEXT boundary once running
+    if (!running) return 0.0;
+    const double scaled = now() / interval, nearest = round(scaled);
+    const double base = fabs(scaled - nearest) <= 1.0e-9 ? nearest : floor(scaled);
+    return (base + 1.0) * interval;
+  }
+};
+// A rack's 16-step pattern (step note = pad) and its transport-armed start (sampler.rs:160-175, 232-310)
+struct RackPattern {
+  HostSeq seq;
+  bool pattern_running = false, has_pending = false; double pending_beat = 0.0;
+};
+struct RackHit { uint32_t frame, slot; float velocity; };
+// One render call of `frames` frames for the (registered) racks of an engine: `bounce` resets and starts their sequencers first
+// (sequencers_iter_mut covers the racks, ffi.rs:3777-3788, 7840-7843); a pending start fires at the first frame whose transport beat has
+// reached it (:1139-1147, SamplerRack::activate_start_if_due); from there the rack's sequencer ticks with the others and its fires are
+// pad hits (:1199-1210).  The transport advances by the call's frames.
+inline void resolve_rack_patterns(Transport& T, RackPattern* const* racks, int n_racks, uint32_t frames, bool bounce, bool triggers_enabled,
+                                  std::vector<RackHit>* hits) {
+  bool any_pending = false;
+  for (int r = 0; r < n_racks; r++) if (racks[r]) { if (bounce) { racks[r]->seq.reset(); racks[r]->seq.start(); } any_pending = any_pending || racks[r]->has_pending; }
+  std::vector<uint32_t> act(n_racks, 0xffffffffu);
+  if (T.running && any_pending) {
+    double beat = T.now();
+    const double bps = T.beats_per_sample();
+    int left = 0;
+    for (int r = 0; r < n_racks; r++) left += (racks[r] && racks[r]->has_pending) ? 1 : 0;
+    uint32_t f = 0;
+    for (; f < frames && left; f++) {
+      for (int r = 0; r < n_racks; r++)
+        if (racks[r] && racks[r]->has_pending && act[r] == 0xffffffffu && beat + 1.0e-8 >= racks[r]->pending_beat) { act[r] = f; left--; }
+      beat += bps;
+    }
+    T.beat = beat; T.lazy = frames - f;
+  } else if (T.running) T.lazy += frames;
+  std::vector<SeqFire> fires;
+  for (int r = 0; r < n_racks; r++) {
+    if (!racks[r]) continue;
+    RackPattern& R = *racks[r];
+    uint32_t from = 0;
+    if (act[r] != 0xffffffffu) {                       // activate_start_if_due (sampler.rs:266-275)
+      R.has_pending = false;
+      R.seq.set_beat_position(R.pending_beat); R.seq.start(); R.pattern_running = true;
+      from = act[r];
+    }
+    if (!R.pattern_running) continue;                  // tick_sequencer: the rack's sequencer only ticks while its pattern runs
+    fires.clear();
+    R.seq.run(frames - from, fires);
+    if (triggers_enabled)
+      for (const SeqFire& f : fires) hits[r].push_back(RackHit{f.frame + from, f.has_note ? (uint32_t)f.note : 0u, f.velocity});
+  }
+}
 
 // ---- utils/blendable.rs PresetBlender over the channel's config (ffi.rs ChannelBlender :405-560) ----------------------
 // Presets as flat values in the order of the config's fields; preset ids ffi.rs:1882-1998.  Returns the field count (0 = unknown).
@@ -216,6 +288,7 @@ struct EngineBank {
   // sample-playback sources (loops.cuh): per-call descriptors (state read back when the call ends) and the pieces' stereo rows
   std::vector<gd::LoopMixer> h_loop_descs; DevBuf<gd::LoopMixer> d_loop_descs;
   std::vector<gd::SamplerRack> h_rack_descs; DevBuf<gd::SamplerRack> d_rack_descs;
+  DevBuf<gd::SamplerHit> d_rack_hits;
   DevBuf<float> d_ext[2];
   DevBuf<float> d_hann; uint32_t wsola_hop = 0;    // WSOLA window table of this sample rate (wsola.rs:80-82), built at first use
   // PreservePitch channel: the window table and the channel's own stretcher buffers (9 hops of floats, content irrelevant until the
@@ -400,9 +473,14 @@ struct GooeyEngine {
     gd::SampleVoice voices[gd::SAMPLER_VOICES];
     std::shared_ptr<gh::DevBuf<float>> voice_buf[gd::SAMPLER_VOICES];
     void voices_release(int v) { voices[v].samples = nullptr; voice_buf[v].reset(); }
+    void stop_all() { for (int v = 0; v < gd::SAMPLER_VOICES; v++) voices_release(v); }
+    // the rack's 16-step pattern (step note = pad) and its transport-armed start (sampler.rs:160-175, 232-310)
+    gh::RackPattern pat;
     unsigned long long next_age = 0;
     SamplerHost() { memset(voices, 0, sizeof voices); for (auto& v : voices) v.increment = 1.0; }
   } samplers[gd::SAMPLER_RACKS];
+  // the mixer's transport (the beat clock sampler-rack pattern starts are armed on)
+  gh::Transport transport;
   float peaks[gd::N_PEAKS] = {0};          // read-and-reset meters (ffi.rs:2572-2584, graph.rs:233-237), merged after every render
   struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
   std::vector<MidiEvent> midi_events;      // of the most recent render call, at most 64 (ffi.rs:71, 994-1004, 1045)
@@ -448,7 +526,7 @@ inline GooeyEngine* engine_create(int device, float sr) {
   EngineBank& B = engine_bank(device, sr);
   std::lock_guard<std::recursive_mutex> lk(B.mu);
   std::unique_ptr<GooeyEngine> e(new GooeyEngine);
-  e->bank = &B; e->sr = sr;
+  e->bank = &B; e->sr = sr; e->transport.sr = sr;
   GooeyVoicePatch p[5];
   for (uint32_t t = 0; t < 5; t++) p[t] = default_patch(t);
   for (int ch = 0; ch < 5; ch++) {
@@ -682,6 +760,7 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   B.h_loop_descs.clear(); B.h_rack_descs.clear();
   struct ExtRef { int engine, rack; };
   std::vector<int> loop_refs; std::vector<ExtRef> rack_refs;
+  std::vector<gd::SamplerHit> rack_hits; std::vector<size_t> rack_hit_off;
   uint32_t ext_pairs = 0;
   for (int i = 0; i < n; i++) {
     GooeyEngine* e = E[i];
@@ -707,19 +786,39 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
       for (auto& l : e->loops)
         for (uint32_t f = 0; f < frames && (l.gain.c != l.gain.t || l.active.c != l.active.t); f++) { gd::lsm_tick(l.gain, B.rc.smooth15); gd::lsm_tick(l.active, B.rc.smooth15); }
     }
+    // rack patterns: resolved on the host into pad hits (resolve_rack_patterns above)
+    gh::RackPattern* pats[gd::SAMPLER_RACKS];
+    std::vector<gh::RackHit> rhits[gd::SAMPLER_RACKS];
+    for (int r = 0; r < gd::SAMPLER_RACKS; r++) pats[r] = e->samplers[r].registered ? &e->samplers[r].pat : nullptr;
+    gh::resolve_rack_patterns(e->transport, pats, gd::SAMPLER_RACKS, frames, bounce, e->seq_triggers_enabled, rhits);
     for (int r = 0; r < gd::SAMPLER_RACKS; r++) {
       auto& R = e->samplers[r];
       if (!R.registered) continue;
+      std::vector<gd::SamplerHit> hits;
+      for (const gh::RackHit& h : rhits[r]) hits.push_back(gd::SamplerHit{h.frame, h.slot, h.velocity, 0u});
       bool sounding = false;
       for (const auto& v : R.voices) sounding = sounding || v.samples != nullptr;
-      if (!sounding) continue;                       // a rack with no active voice ticks to exactly 0 and its state does not move
+      if (!sounding && hits.empty()) continue;         // no active voice and no hit: the rack ticks to exactly 0 and its state does not move
       gd::SamplerRack d;
+      memset(&d, 0, sizeof d);
       memcpy(d.v, R.voices, sizeof d.v);
       d.row = ext_pairs; d.rack = (uint32_t)r;
+      for (int k = 0; k < gd::SAMPLER_SLOTS; k++) {
+        const auto& S = R.slots[k];
+        if (S.buf) d.slots[k] = gd::SamplerSlotRef{S.buf->p, S.frames, S.channels, (double)S.sr / (double)e->sr};
+      }
+      d.next_age = R.next_age;
+      d.n_hits = (uint32_t)hits.size(); d.next_hit = 0; d.cur_frame = 0;
+      rack_hit_off.push_back(rack_hits.size());
+      rack_hits.insert(rack_hits.end(), hits.begin(), hits.end());
       e->cfg.src_ext |= 2u << r; e->cfg.ext_row[1 + r] = ext_pairs++;
       B.h_rack_descs.push_back(d); rack_refs.push_back({i, r});
     }
     B.cfgs[e->mix_slot] = e->cfg;
+  }
+  if (!rack_hits.empty()) {                             // one flat hit table for the call; the descriptors point into it
+    B.d_rack_hits.upload(rack_hits.data(), rack_hits.size(), st);
+    for (size_t q = 0; q < B.h_rack_descs.size(); q++) if (B.h_rack_descs[q].n_hits) B.h_rack_descs[q].hits = B.d_rack_hits.p + rack_hit_off[q];
   }
   const double* tt = B.clock.view(clock_table(B.sr), kmin, kmax, st);
   // ---- device state: pools, configs, rings ----
@@ -954,13 +1053,17 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
   for (size_t q = 0; q < rack_refs.size(); q++) {
     auto& R = E[rack_refs[q].engine]->samplers[rack_refs[q].rack];
     memcpy(R.voices, B.h_rack_descs[q].v, sizeof R.voices);
-    for (int v = 0; v < gd::SAMPLER_VOICES; v++) if (!R.voices[v].samples) R.voices_release(v);
+    R.next_age = B.h_rack_descs[q].next_age;
+    for (int v = 0; v < gd::SAMPLER_VOICES; v++) {    // a voice the device started plays its pad's buffer (a pad cannot change during a call)
+      if (!R.voices[v].samples) R.voices_release(v);
+      else R.voice_buf[v] = R.slots[R.voices[v].slot].buf;
+    }
   }
   for (size_t q = 0; q < lfo_refs.size(); q++) E[lfo_refs[q].engine]->lfos[lfo_refs[q].lfo].phase = B.h_lfo_streams[q].phase;
   for (int i = 0; i < n; i++) {
     for (int q = 0; q < gd::N_PEAKS; q++) { const float v = B.h_peaks[(size_t)i * gd::N_PEAKS + q]; if (v > E[i]->peaks[q]) E[i]->peaks[q] = v; }
     E[i]->k += frames;
-    if (bounce) for (auto& s : E[i]->strip) s.seq.stop();
+    if (bounce) { for (auto& s : E[i]->strip) s.seq.stop(); for (auto& R : E[i]->samplers) if (R.registered) R.pat.seq.stop(); }
   }
 }
 

@@ -190,7 +190,9 @@ void gooey_engine_set_bpm(GooeyEngine* e, float bpm) {
   if (!e) return;
   e->bpm = bpm;
   e->loop_engine_bpm = bpm;                                    // Mixer::set_bpm (ffi.rs:3360, mixer/mod.rs:80-87)
+  e->transport.set_bpm(bpm);
   for (auto& s : e->strip) s.seq.set_bpm(bpm);
+  for (auto& R : e->samplers) if (R.registered) R.pat.seq.set_bpm(bpm);
   for (int slot = 0; slot < gd::MAX_FX; slot++)
     if (e->cfg.fx_kind[slot] == gd::FXK_DELAY) e->mix_pending.push_back(gh::make_event(0, gd::MX_FX_BPM, slot, bpm));
 }
@@ -200,6 +202,7 @@ void gooey_engine_set_swing(GooeyEngine* e, float swing) {
   float c = gd::clampf(swing, 0.0f, 1.0f);
   e->swing = c;
   for (auto& s : e->strip) s.seq.set_swing(c);
+  for (auto& R : e->samplers) if (R.registered) R.pat.seq.set_swing(c);
 }
 void gooey_engine_set_master_gain(GooeyEngine* e, float g) { if (e && std::isfinite(g)) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_MASTER, g)); }
 
@@ -237,9 +240,27 @@ void gooey_engine_sequencer_set_instrument_pattern(GooeyEngine* e, uint32_t inst
   for (int i = 0; i < 16; i++) q.pattern[i].enabled = pattern[i];
   if (q.current_step >= q.pattern.size()) q.current_step = 0;
 }
-void gooey_engine_sequencer_start(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.start(); }
-void gooey_engine_sequencer_stop(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.stop(); }
-void gooey_engine_sequencer_reset(GooeyEngine* e) { if (e) for (auto& s : e->strip) s.seq.reset(); }
+// ffi.rs:3501-3561: every sequencer — the strips' and the registered sampler racks' — plus the mixer's transport (the beat clock the
+// racks' pattern starts are armed on); stop / reset also drop the racks' pending starts, patterns and sounding voices
+void gooey_engine_sequencer_start(GooeyEngine* e) {
+  if (!e) return;
+  for (auto& s : e->strip) s.seq.start();
+  for (auto& R : e->samplers) if (R.registered) R.pat.seq.start();
+  e->transport.running = true;
+}
+void gooey_engine_sequencer_stop(GooeyEngine* e) {
+  if (!e) return;
+  for (auto& s : e->strip) s.seq.stop();
+  for (auto& R : e->samplers) if (R.registered) { R.pat.has_pending = false; R.pat.pattern_running = false; R.pat.seq.stop(); R.stop_all(); }
+  e->transport.now();
+  e->transport.running = false;
+}
+void gooey_engine_sequencer_reset(GooeyEngine* e) {
+  if (!e) return;
+  for (auto& s : e->strip) s.seq.reset();
+  for (auto& R : e->samplers) if (R.registered) { R.pat.has_pending = false; R.pat.pattern_running = false; R.pat.seq.reset(); R.stop_all(); }
+  e->transport.beat = 0.0; e->transport.lazy = 0;
+}
 // ffi.rs:2188-2215: with the triggers disabled the sequencers keep ticking (clock, step position) but fire nothing and export no
 // MIDI event; host triggers (trigger_instrument*) still sound.  The render path reads the flag per call (engine.cuh).
 void gooey_engine_set_sequencer_triggers_enabled(GooeyEngine* e, bool enabled) { if (e) e->seq_triggers_enabled = enabled; }
@@ -494,6 +515,36 @@ uint32_t gooey_b200_sequencer_schedule(float sample_rate, float bpm, float swing
   q.run(frames, fires);
   uint32_t n = 0;
   for (const auto& f : fires) { if (n < capacity) { if (out_frames) out_frames[n] = f.frame; if (out_velocity) out_velocity[n] = f.velocity; } n++; }
+  return n;
+}
+
+// Host-only: the pad hits one sampler rack's pattern resolves to over a sequence of render calls (gh::resolve_rack_patterns, the code
+// engines_render runs).  steps: 16 x (enabled, pad, velocity).  The transport starts at `transport_beat` (running or not); the pattern start
+// is armed at `pending_beat` (< 0: the pattern already runs from step 0 — a bounce); calls[i] frames are rendered one call after the other
+// (`bounce`: every call is a bounce).  Hits come back with frames counted from the first call.  Returns their number (may exceed capacity);
+// *out_transport_beat = the beat after the last call.  Needs no device; used by the CPU tests.
+uint32_t gooey_b200_sampler_schedule(float sample_rate, float bpm, float swing, const uint8_t* enabled, const uint8_t* pads, const float* velocity,
+                                     int transport_running, double transport_beat, double pending_beat, int bounce, const uint32_t* calls, uint32_t n_calls,
+                                     uint32_t* out_frames, uint32_t* out_pads, float* out_velocity, uint32_t capacity, double* out_transport_beat) {
+  if (!enabled || !pads || !calls) return 0;
+  gh::Transport T;
+  T.sr = sample_rate; T.bpm = 120.0f; T.set_bpm(bpm); T.running = transport_running != 0; T.beat = transport_beat;
+  gh::RackPattern R;
+  R.seq.init(bpm, sample_rate);
+  for (int i = 0; i < 16; i++) { gh::SeqStep& s = R.seq.pattern[i]; s.enabled = enabled[i] != 0; s.velocity = velocity ? gd::clampf(velocity[i], 0.0f, 1.0f) : 1.0f; s.has_note = true; s.note = pads[i]; }
+  R.seq.set_swing(swing);
+  if (pending_beat >= 0.0) { R.has_pending = true; R.pending_beat = pending_beat; }
+  else { R.pattern_running = true; if (!bounce) R.seq.start(); }
+  gh::RackPattern* pats[1] = {&R};
+  uint32_t n = 0, base = 0;
+  for (uint32_t k = 0; k < n_calls; k++) {
+    std::vector<gh::RackHit> hits[1];
+    gh::resolve_rack_patterns(T, pats, 1, calls[k], bounce != 0, true, hits);
+    if (bounce) R.seq.stop();
+    for (const auto& h : hits[0]) { if (n < capacity) { if (out_frames) out_frames[n] = base + h.frame; if (out_pads) out_pads[n] = h.slot; if (out_velocity) out_velocity[n] = h.velocity; } n++; }
+    base += calls[k];
+  }
+  if (out_transport_beat) *out_transport_beat = T.now();
   return n;
 }
 

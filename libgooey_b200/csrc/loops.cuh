@@ -19,8 +19,8 @@
 // aligned grain start (<= ~130 candidates x hop taps of normalised cross-correlation), windows a 2-hop grain and overlap-adds it;
 // the stretcher's buffers (9 hops of floats per channel) live in a device buffer owned by the channel.
 //
-// Not built (a request latches the engine's sticky error instead of rendering different audio): per-channel effect chains,
-// the clip grid and transport-armed sampler patterns.
+// Not built (a request latches the engine's sticky error instead of rendering different audio): per-channel effect chains and
+// the clip grid.
 #pragma once
 #include "dsp.cuh"
 
@@ -316,7 +316,19 @@ struct SampleVoice {          // :84-150
   uint32_t frames, channels, slot;
   float velocity;
 };
-struct SamplerRack { SampleVoice v[SAMPLER_VOICES]; uint32_t row; uint32_t rack; };
+// The rack's step pattern is resolved on the host (its sequencer is the engine's 16th-note sequencer, engine.cuh HostSeq) into hits:
+// (frame of the call, pad, velocity); the device starts the voices itself at those frames — it is the side that knows which voices
+// still sound (SamplerRack::trigger, :200-223).
+struct SamplerHit { uint32_t frame, slot; float velocity; uint32_t pad; };
+struct SamplerSlotRef { const float* samples; uint32_t frames, channels; double increment; };   // a loaded pad: increment = pad rate / engine rate
+struct SamplerRack {
+  SampleVoice v[SAMPLER_VOICES];
+  uint32_t row; uint32_t rack;
+  SamplerSlotRef slots[SAMPLER_SLOTS];
+  const SamplerHit* hits; uint32_t n_hits, next_hit;
+  unsigned long long next_age;
+  uint32_t cur_frame, pad;      // frames of this call already rendered (the kernel runs once per piece)
+};
 
 G_HD void sample_voice_tick(SampleVoice& v, float& ol, float& orr) {
   if (!v.samples) { ol = 0.0f; orr = 0.0f; return; }
@@ -342,8 +354,23 @@ G_HD void sample_voice_tick(SampleVoice& v, float& ol, float& orr) {
   if (v.position >= end) v.samples = nullptr;
   ol = fl * gain; orr = fr * gain;
 }
-// SamplerRack::tick (:225-229): fold over the 32 voices in index order
+// SamplerRack::trigger (:200-223): first free voice, else the oldest (first of equals); false when the pad is empty
+G_HD bool sampler_rack_trigger(SamplerRack& r, uint32_t slot, float velocity) {
+  if (slot >= (uint32_t)SAMPLER_SLOTS || !r.slots[slot].samples) return false;
+  int vi = -1;
+  for (int k = 0; k < SAMPLER_VOICES; k++) if (!r.v[k].samples) { vi = k; break; }
+  if (vi < 0) { vi = 0; for (int k = 1; k < SAMPLER_VOICES; k++) if (r.v[k].age < r.v[vi].age) vi = k; }
+  r.next_age += 1;
+  SampleVoice& v = r.v[vi];
+  const SamplerSlotRef& s = r.slots[slot];
+  v.samples = s.samples; v.frames = s.frames; v.channels = s.channels; v.slot = slot;
+  v.position = 0.0; v.increment = s.increment; v.velocity = clampf(velocity, 0.0f, 1.0f); v.age = r.next_age;
+  return true;
+}
+// SamplerRack::tick (:225-229): fold over the 32 voices in index order — after the pattern hits due at this frame (ffi.rs:1199-1204)
 G_HD void sampler_rack_tick(SamplerRack& r, float& ol, float& orr) {
+  while (r.next_hit < r.n_hits && r.hits[r.next_hit].frame <= r.cur_frame) { sampler_rack_trigger(r, r.hits[r.next_hit].slot, r.hits[r.next_hit].velocity); r.next_hit++; }
+  r.cur_frame++;
   float l = 0.0f, rr = 0.0f;
   for (int k = 0; k < SAMPLER_VOICES; k++) {
     float vl, vr;

@@ -175,7 +175,11 @@ bool gooey_engine_loop_render_to_wav(GooeyEngine* e, uint32_t channel, uint32_t 
 int32_t gooey_engine_sampler_register(GooeyEngine* e) {   /* :6007-6027 */
   if (!e) return -1;
   for (int r = 0; r < gd::SAMPLER_RACKS; r++)
-    if (!e->samplers[r].registered) { e->samplers[r].registered = true; return r; }
+    if (!e->samplers[r].registered) {               // SamplerRack::new(engine.sample_rate, engine.bpm): a stopped 16-step sequencer, every step off
+      e->samplers[r].registered = true;
+      e->samplers[r].pat.seq.init(e->bpm, e->sr);
+      return r;
+    }
   return -1;
 }
 uint32_t gooey_engine_sampler_get_source_id(const GooeyEngine* e, uint32_t rack) { return gh::rack_of(e, rack) ? GOOEY_SOURCE_SAMPLER_BASE + rack : 0xFFFFFFFFu; }
@@ -222,10 +226,41 @@ bool gooey_engine_sampler_trigger(GooeyEngine* e, uint32_t rack, uint32_t slot, 
   R->voice_buf[vi] = S.buf;
   return true;
 }
-/* not built: transport-armed sampler patterns (ffi.rs:6173-6290) */
-bool gooey_engine_sampler_set_step(GooeyEngine* e, uint32_t, uint32_t, bool, uint32_t, float) {
-  if (e) gh::engine_fail(e, "libgooey_b200: sampler-rack step patterns (transport-armed, ffi.rs:6173-6290) are not built; trigger the pads with gooey_engine_sampler_trigger");
-  return false;
+// ---- the rack's step pattern (:6173-6290; sampler.rs:232-310): 16 steps of (enabled, pad, velocity) on the engine's 16th-note grid; a start
+// is armed on the transport beat (quantised to the next sixteenth / quarter / bar while the transport runs, beat 0 while it is stopped)
+// and fires inside the render at the first frame whose beat has reached it ----
+bool gooey_engine_sampler_set_step(GooeyEngine* e, uint32_t rack, uint32_t step, bool enabled, uint32_t slot, float velocity) {
+  auto* R = gh::rack_of(e, rack);
+  if (!R || step >= (uint32_t)gd::SAMPLER_SLOTS || slot >= (uint32_t)gd::SAMPLER_SLOTS) return false;
+  gh::SeqStep& s = R->pat.seq.pattern[step];
+  s.enabled = enabled; s.velocity = gd::clampf(velocity, 0.0f, 1.0f); s.has_note = true; s.note = (uint8_t)slot;
+  return true;
 }
+bool gooey_engine_sampler_get_step(const GooeyEngine* e, uint32_t rack, uint32_t step, bool* out_enabled, uint32_t* out_slot, float* out_velocity) {
+  if (!out_enabled || !out_slot || !out_velocity) return false;
+  const auto* R = gh::rack_of(e, rack);
+  if (!R || step >= (uint32_t)gd::SAMPLER_SLOTS) return false;
+  const gh::SeqStep& s = R->pat.seq.pattern[step];
+  *out_enabled = s.enabled; *out_slot = s.has_note ? s.note : 0u; *out_velocity = s.velocity;
+  return true;
+}
+bool gooey_engine_sampler_start_pattern(GooeyEngine* e, uint32_t rack, uint32_t quantization) {   /* :6192-6207 */
+  if (!e || quantization > GOOEY_CLIP_QUANTIZE_BAR) return false;
+  const double interval = quantization == GOOEY_CLIP_QUANTIZE_SIXTEENTH ? 0.25 : (quantization == GOOEY_CLIP_QUANTIZE_QUARTER ? 1.0 : 4.0);
+  const double target = e->transport.quantized_target(interval);
+  auto* R = gh::rack_of(e, rack);
+  if (!R || !std::isfinite(target) || target < 0.0) return false;
+  R->pat.pattern_running = false; R->pat.seq.stop(); R->pat.has_pending = true; R->pat.pending_beat = target;   // SamplerRack::schedule_start (sampler.rs:254-262)
+  return true;
+}
+bool gooey_engine_sampler_stop_pattern(GooeyEngine* e, uint32_t rack) {      /* :6211-6221; stops the rack's voices too */
+  auto* R = gh::rack_of(e, rack);
+  if (!R) return false;
+  R->pat.has_pending = false; R->pat.pattern_running = false; R->pat.seq.stop(); R->stop_all();
+  return true;
+}
+bool gooey_engine_sampler_cancel_pattern_start(GooeyEngine* e, uint32_t rack) { auto* R = gh::rack_of(e, rack); if (!R) return false; R->pat.has_pending = false; return true; }
+double gooey_engine_sampler_get_pending_start_beat(const GooeyEngine* e, uint32_t rack) { const auto* R = gh::rack_of(e, rack); return (R && R->pat.has_pending) ? R->pat.pending_beat : -1.0; }
+bool gooey_engine_sampler_is_pattern_running(const GooeyEngine* e, uint32_t rack) { const auto* R = gh::rack_of(e, rack); return R && R->pat.pattern_running; }
 
 }  // extern "C"

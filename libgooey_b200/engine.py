@@ -55,6 +55,10 @@ _RSIGS = {
     "sampler_clear_slot": ([c.c_uint32, c.c_uint32], c.c_bool), "sampler_slot_is_loaded": ([c.c_uint32, c.c_uint32], c.c_bool),
     "sampler_slot_frames": ([c.c_uint32, c.c_uint32], c.c_uint32), "sampler_slot_channels": ([c.c_uint32, c.c_uint32], c.c_uint32),
     "sampler_slot_sample_rate": ([c.c_uint32, c.c_uint32], c.c_float), "sampler_trigger": ([c.c_uint32, c.c_uint32, c.c_float], c.c_bool),
+    "sampler_set_step": ([c.c_uint32, c.c_uint32, c.c_bool, c.c_uint32, c.c_float], c.c_bool),
+    "sampler_start_pattern": ([c.c_uint32, c.c_uint32], c.c_bool), "sampler_stop_pattern": ([c.c_uint32], c.c_bool),
+    "sampler_cancel_pattern_start": ([c.c_uint32], c.c_bool), "sampler_get_pending_start_beat": ([c.c_uint32], c.c_double),
+    "sampler_is_pattern_running": ([c.c_uint32], c.c_bool),
 }
 _bound = set()
 
@@ -151,6 +155,13 @@ class Engine:
         out = np.zeros((frames, 2), np.float32)
         ok = getattr(self._L, self._prefix + "loop_render")(self._h, channel, frames, preroll, out.ctypes.data)
         return out if ok else None
+
+    def sampler_get_step(self, rack, step):
+        """(enabled, pad, velocity) of one step of the rack's pattern, or None."""
+        en, slot, vel = c.c_bool(False), c.c_uint32(0), c.c_float(0.0)
+        f = getattr(self._L, self._prefix + "sampler_get_step")
+        f.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.POINTER(c.c_bool), c.POINTER(c.c_uint32), c.POINTER(c.c_float)]; f.restype = c.c_bool
+        return (en.value, slot.value, vel.value) if f(self._h, rack, step, c.byref(en), c.byref(slot), c.byref(vel)) else None
 
     def sampler_set_slot_buffer(self, rack, slot, samples, sample_rate):
         a, frames, channels = self._pcm(samples)

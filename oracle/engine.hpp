@@ -35,6 +35,19 @@ struct Sequencer {
   void reset() { sample_count = 0; next_trigger_sample = 0; step_start_sample = 0; current_step = 0; playhead_step = 0; }
   void set_bpm(float b) { bpm = b; samples_per_step = calc_sps(b, sample_rate); }
   void set_swing(float s) { swing.set_target(clampf(s, 0.0f, 1.0f)); }
+  void set_beat_position(double beat) {  // :658-682 (a step is a 16th = 1/4 beat)
+    size_t n = pattern.size();
+    if (n == 0) return;
+    double step_f = beat * 4.0, fl = std::floor(step_f);
+    size_t idx = (size_t)fl % n;
+    double frac = step_f - fl;
+    current_step = idx; playhead_step = idx;
+    double off = frac * (double)samples_per_step;
+    sample_count = off <= 0.0 ? 0 : (uint64_t)off;
+    step_start_sample = 0;
+    double nt = std::round((double)samples_per_step - frac * (double)samples_per_step);
+    next_trigger_sample = nt <= 0.0 ? 0 : (uint64_t)nt;
+  }
   bool tick(SeqTrigger& out) {  // tick_with_settings :883-952 (armed start not modelled)
     if (!is_running || pattern.empty()) { sample_count += 1; return false; }
     swing.tick();
@@ -236,6 +249,36 @@ struct FfiEngine {
   MixerGraph graph;
   LoopMixer mixer;                                   // ffi.rs:768 (`mixer: Mixer`)
   std::unique_ptr<SamplerRack> samplers[4];          // ffi.rs:770
+  // the rack's own 16-step sequencer (step note = pad) and its transport-armed start (sampler.rs:160-175, 232-310)
+  struct RackPattern {
+    Sequencer seq; bool pattern_running = false, has_pending = false; double pending_start_beat = 0.0;
+    RackPattern(float bpm, float sr) : seq(bpm, sr, 16, false) {}
+  };
+  std::vector<RackPattern> rack_pat;
+  struct RackHitLog { uint64_t frame; uint32_t slot; float velocity; };   // test hook: the pattern hits of rack 0..3 and the frames rendered so far
+  std::vector<RackHitLog> rack_hits[4]; uint64_t frames_rendered = 0;
+  bool capture_rack0 = false; std::vector<float> rack0_capture;          // test hook: rack 0's own stereo frames while the engine renders
+  // the mixer's clip-grid transport, as far as the racks need it (clip_grid.rs:144-195, 526-579, 656-660): a monotonic beat clock
+  bool transport_running = false; double transport_beat = 0.0; float transport_bpm = 120.0f;
+  double beats_per_sample() const { return (double)rust_max(transport_bpm, 0.0f) / (60.0 * (double)rust_max(sample_rate, 1.0f)); }
+  double quantized_target(double interval) const {  // clip_grid.rs:174-191
+    if (!transport_running) return 0.0;
+    double scaled = transport_beat / interval, nearest = std::round(scaled);
+    double base = std::fabs(scaled - nearest) <= 1.0e-9 ? nearest : std::floor(scaled);
+    return (base + 1.0) * interval;
+  }
+  void rack_stop_all(int r) { if (samplers[r]) for (auto& v : samplers[r]->voices) v.buffer.reset(); }
+  void sequencer_start() { for (auto& v : voices) v.seq.start(); for (int r = 0; r < 4; r++) if (samplers[r]) rack_pat[r].seq.start(); transport_running = true; }   // ffi.rs:3501-3512
+  void sequencer_stop() {   // :3515-3530
+    for (auto& v : voices) v.seq.stop();
+    for (int r = 0; r < 4; r++) if (samplers[r]) { auto& p = rack_pat[r]; p.seq.stop(); p.has_pending = false; p.pattern_running = false; p.seq.stop(); rack_stop_all(r); }
+    transport_running = false;
+  }
+  void sequencer_reset() {  // :3547-3561
+    for (auto& v : voices) v.seq.reset();
+    for (int r = 0; r < 4; r++) if (samplers[r]) { auto& p = rack_pat[r]; p.seq.reset(); p.has_pending = false; p.pattern_running = false; p.seq.reset(); rack_stop_all(r); }
+    transport_beat = 0.0;
+  }
   std::vector<Lfo> lfos; bool lfo_enabled[8] = {false}; std::vector<LfoRoute> lfo_routes[8]; uint32_t lfo_next_route_id[8] = {0};
   struct MidiEvent { uint32_t instrument_index; float velocity; uint32_t sample_offset; };   // GooeyMidiEvent (ffi.rs:78-83)
   std::vector<MidiEvent> pending_midi_events;                                                // capacity 64, cleared by every render (:71, :1045)
@@ -247,11 +290,14 @@ struct FfiEngine {
         master_gain(0.25f, 0.0f, 2.0f, sr, 30.0f), poly(sr), granulator(sr), graph(sr, 120.0f), mixer(sr) {
     for (uint32_t t = 0; t < 5; t++) voices.emplace_back(make_instrument(t, sr), t, bpm, sr);
     for (int i = 0; i < 8; i++) lfos.emplace_back(sr);
+    for (int r = 0; r < 4; r++) rack_pat.emplace_back(bpm, sr);
     graph.default_layout();
   }
   VoiceStrip* by_type(uint32_t t) { for (auto& v : voices) if (v.type == t) return &v; return nullptr; }
-  void set_bpm(float b) { bpm = b; for (auto& v : voices) v.seq.set_bpm(b); for (auto& l : lfos) l.bpm = b; delay.set_bpm(b); graph.set_bpm(b); mixer.set_bpm(b); }   // :3337-3364
-  void set_swing(float s) { swing = clampf(s, 0.0f, 1.0f); for (auto& v : voices) v.seq.set_swing(swing); }
+  void set_bpm(float b) { bpm = b; for (auto& v : voices) v.seq.set_bpm(b); for (auto& l : lfos) l.bpm = b; delay.set_bpm(b); graph.set_bpm(b); mixer.set_bpm(b);
+    for (int r = 0; r < 4; r++) if (samplers[r]) rack_pat[r].seq.set_bpm(b);
+    if (std::isfinite(b) && b > 0.0f) transport_bpm = b; }   // :3337-3364, clip_grid.rs:520-524
+  void set_swing(float s) { swing = clampf(s, 0.0f, 1.0f); for (auto& v : voices) v.seq.set_swing(swing); for (int r = 0; r < 4; r++) if (samplers[r]) rack_pat[r].seq.set_swing(swing); }
   void reset_effect_states() { saturation.reset(); lowpass.reset(); tilt.reset(); delay.reset(); compressor.reset(); reverb.reset(); plate.reset(); }  // ffi.rs:1417-1425
   static bool freq_range(uint32_t type, float& mn, float& mx) {  // :1511-1518
     if (type == 4) { mn = 30.0f; mx = 200.0f; return true; }
@@ -273,9 +319,27 @@ struct FfiEngine {
     for (auto& v : voices) v.mute_gain.set_target(v.soloed ? 1.0f : (any_solo ? 0.0f : (v.muted ? 0.0f : 1.0f)));
     graph.update_mute_solo_targets();
     for (size_t f = 0; f < frames; f++) {
+      if (transport_running)   // a rack start is owned by the render clock (:1139-1147; SamplerRack::activate_start_if_due)
+        for (int r = 0; r < 4; r++) {
+          if (!samplers[r]) continue;
+          RackPattern& p = rack_pat[r];
+          if (!p.has_pending || transport_beat + 1.0e-8 < p.pending_start_beat) continue;
+          p.has_pending = false;
+          p.seq.set_beat_position(p.pending_start_beat);
+          p.seq.start();
+          p.pattern_running = true;
+        }
       SeqTrigger trig[5];
       bool fired[5];
       for (int ch = 0; ch < 5; ch++) fired[ch] = voices[ch].seq.tick(trig[ch]);
+      for (int r = 0; r < 4; r++) {   // SamplerRack::tick_sequencer (:1199-1210): ticks only while its pattern runs; hits count only with the triggers enabled
+        if (!samplers[r] || !rack_pat[r].pattern_running) continue;
+        SeqTrigger t{};
+        if (rack_pat[r].seq.tick(t) && seq_triggers_enabled) {
+          samplers[r]->trigger(t.has_note ? (size_t)t.note : 0, t.velocity);
+          rack_hits[r].push_back({frames_rendered, t.has_note ? (uint32_t)t.note : 0u, t.velocity});
+        }
+      }
       if (seq_triggers_enabled) {
         double time = current_time;
         for (int ch = 0; ch < 5; ch++) {
@@ -326,7 +390,10 @@ struct FfiEngine {
       graph.scatter(3, granf);
       StereoFrame sampler_frames[4];                 // :1289-1294
       for (int r = 0; r < 4; r++) if (samplers[r]) sampler_frames[r] = samplers[r]->tick();
+      if (capture_rack0) { rack0_capture.push_back(sampler_frames[0].l); rack0_capture.push_back(sampler_frames[0].r); }
       StereoFrame loop_frame = mixer.tick(sample_rate);   // :1296
+      if (transport_running) transport_beat += beats_per_sample();   // ClipGrid::after_tick, inside Mixer::tick (mod.rs:73)
+      frames_rendered += 1;
       graph.scatter(4, loop_frame);
       for (int r = 0; r < 4; r++) graph.scatter(5 + r, sampler_frames[r]);
       StereoFrame st = graph.mix_down();
@@ -358,6 +425,7 @@ struct FfiEngine {
     size_t total = tot <= 0 ? 0 : (size_t)tot;
     current_time = 0.0;
     for (auto& v : voices) { v.seq.reset(); v.seq.start(); }
+    for (int r = 0; r < 4; r++) if (samplers[r]) { rack_pat[r].seq.reset(); rack_pat[r].seq.start(); }   // sequencers_iter_mut covers the racks (:3777-3788)
     for (auto& v : voices) { v.mute_gain.snap(); v.channel_gain.snap(); v.pan.snap(); }
     graph.snap_strip_params();
     master_gain.snap();
@@ -373,6 +441,7 @@ struct FfiEngine {
       remaining -= n;
     }
     for (auto& v : voices) v.seq.stop();
+    for (int r = 0; r < 4; r++) if (samplers[r]) rack_pat[r].seq.stop();
     return out;
   }
 };

@@ -248,9 +248,9 @@ void orc_engine_sequencer_set_instrument_pattern(void* e, uint32_t inst, const b
   for (int i = 0; i < 16; i++) { q.pattern[i].enabled = pattern[i]; q.pattern[i].velocity = 1.0f; }
   if (q.current_step >= q.pattern.size()) q.current_step = 0;
 }
-void orc_engine_sequencer_start(void* e) { if (e) for (auto& v : E->voices) v.seq.start(); }
-void orc_engine_sequencer_stop(void* e) { if (e) for (auto& v : E->voices) v.seq.stop(); }
-void orc_engine_sequencer_reset(void* e) { if (e) for (auto& v : E->voices) v.seq.reset(); }
+void orc_engine_sequencer_start(void* e) { if (e) E->sequencer_start(); }
+void orc_engine_sequencer_stop(void* e) { if (e) E->sequencer_stop(); }
+void orc_engine_sequencer_reset(void* e) { if (e) E->sequencer_reset(); }
 void orc_engine_set_sequencer_triggers_enabled(void* e, bool on) { if (e) E->seq_triggers_enabled = on; }   // ffi.rs:2188-2198
 bool orc_engine_get_sequencer_triggers_enabled(void* e) { return e ? E->seq_triggers_enabled : true; }    // ffi.rs:2205-2215
 void orc_engine_set_global_effect_param(void* e, uint32_t fx, uint32_t p, float v) {
@@ -432,7 +432,12 @@ bool orc_engine_loop_render(void* e, uint32_t ch, uint32_t frames, uint32_t prer
 int32_t orc_engine_sampler_register(void* e) {
   if (!e) return -1;
   for (int i = 0; i < 4; i++)
-    if (!E->samplers[i]) { E->samplers[i] = std::make_unique<SamplerRack>(E->sample_rate); E->graph.register_source(5 + i); return i; }
+    if (!E->samplers[i]) {   // SamplerRack::new(engine.sample_rate, engine.bpm, ..): its sequencer starts at the engine's CURRENT tempo, swing 0.5
+      E->samplers[i] = std::make_unique<SamplerRack>(E->sample_rate);
+      E->rack_pat[i] = FfiEngine::RackPattern(E->bpm, E->sample_rate);
+      E->graph.register_source(5 + i);
+      return i;
+    }
   return -1;
 }
 uint32_t orc_engine_sampler_get_source_id(void* e, uint32_t rack) { return (e && rack < 4 && E->samplers[rack]) ? 5u + rack : 0xFFFFFFFFu; }
@@ -447,6 +452,53 @@ bool orc_engine_sampler_slot_is_loaded(void* e, uint32_t rack, uint32_t slot) { 
 uint32_t orc_engine_sampler_slot_frames(void* e, uint32_t rack, uint32_t slot) { return orc_engine_sampler_slot_is_loaded(e, rack, slot) ? (uint32_t)E->samplers[rack]->slots[slot]->frames : 0u; }
 uint32_t orc_engine_sampler_slot_channels(void* e, uint32_t rack, uint32_t slot) { return orc_engine_sampler_slot_is_loaded(e, rack, slot) ? (uint32_t)E->samplers[rack]->slots[slot]->channels : 0u; }
 float orc_engine_sampler_slot_sample_rate(void* e, uint32_t rack, uint32_t slot) { return orc_engine_sampler_slot_is_loaded(e, rack, slot) ? E->samplers[rack]->slots[slot]->sample_rate : 0.0f; }
+// the rack's step pattern (ffi.rs:6173-6290; sampler.rs:232-310)
+bool orc_engine_sampler_set_step(void* e, uint32_t rack, uint32_t step, bool enabled, uint32_t slot, float vel) {
+  if (!e || rack >= 4 || !E->samplers[rack] || step >= 16 || slot >= 16) return false;
+  SeqStep& s = E->rack_pat[rack].seq.pattern[step];
+  s.enabled = enabled; s.velocity = clampf(vel, 0.0f, 1.0f); s.has_note = true; s.note = (uint8_t)slot;
+  return true;
+}
+bool orc_engine_sampler_get_step(void* e, uint32_t rack, uint32_t step, bool* en, uint32_t* slot, float* vel) {
+  if (!e || !en || !slot || !vel || rack >= 4 || !E->samplers[rack] || step >= 16) return false;
+  const SeqStep& s = E->rack_pat[rack].seq.pattern[step];
+  *en = s.enabled; *slot = s.has_note ? s.note : 0u; *vel = s.velocity;
+  return true;
+}
+bool orc_engine_sampler_start_pattern(void* e, uint32_t rack, uint32_t quantization) {
+  if (!e || quantization > 2) return false;
+  const double interval = quantization == 0 ? 0.25 : (quantization == 1 ? 1.0 : 4.0);
+  const double target = E->quantized_target(interval);
+  if (rack >= 4 || !E->samplers[rack]) return false;
+  auto& p = E->rack_pat[rack];                      // SamplerRack::schedule_start (:254-262)
+  if (!std::isfinite(target) || target < 0.0) return false;
+  p.pattern_running = false; p.seq.stop(); p.has_pending = true; p.pending_start_beat = target;
+  return true;
+}
+bool orc_engine_sampler_stop_pattern(void* e, uint32_t rack) {
+  if (!e || rack >= 4 || !E->samplers[rack]) return false;
+  auto& p = E->rack_pat[rack];
+  p.has_pending = false; p.pattern_running = false; p.seq.stop(); E->rack_stop_all((int)rack);
+  return true;
+}
+bool orc_engine_sampler_cancel_pattern_start(void* e, uint32_t rack) { if (!e || rack >= 4 || !E->samplers[rack]) return false; E->rack_pat[rack].has_pending = false; return true; }
+double orc_engine_sampler_get_pending_start_beat(void* e, uint32_t rack) { return (e && rack < 4 && E->samplers[rack] && E->rack_pat[rack].has_pending) ? E->rack_pat[rack].pending_start_beat : -1.0; }
+bool orc_engine_sampler_is_pattern_running(void* e, uint32_t rack) { return e && rack < 4 && E->samplers[rack] && E->rack_pat[rack].pattern_running; }
+// test hooks: the pattern hits logged so far (frames counted from the engine's first rendered frame) and the transport beat
+uint32_t orc_engine_sampler_hit_log(void* e, uint32_t rack, uint32_t* frames, uint32_t* slots, float* vel, uint32_t cap) {
+  if (!e || rack >= 4) return 0;
+  uint32_t n = 0;
+  for (const auto& h : E->rack_hits[rack]) { if (n < cap) { frames[n] = (uint32_t)h.frame; slots[n] = h.slot; vel[n] = h.velocity; } n++; }
+  return n;
+}
+double orc_engine_transport_beat(void* e) { return e ? E->transport_beat : 0.0; }
+void orc_engine_capture_rack0(void* e, bool on) { if (e) { E->capture_rack0 = on; E->rack0_capture.clear(); } }
+uint32_t orc_engine_rack0_capture(void* e, float* out_interleaved, uint32_t cap_frames) {
+  if (!e) return 0;
+  uint32_t n = (uint32_t)(E->rack0_capture.size() / 2);
+  if (out_interleaved) memcpy(out_interleaved, E->rack0_capture.data(), sizeof(float) * 2 * (n < cap_frames ? n : cap_frames));
+  return n;
+}
 bool orc_engine_sampler_trigger(void* e, uint32_t rack, uint32_t slot, float vel) { return e && rack < 4 && E->samplers[rack] && E->samplers[rack]->trigger(slot, vel); }
 // test hooks: the loop mixer / one sampler rack ticked on their own (what the product's ext_source_kernel computes per descriptor)
 void orc_engine_loop_mixer_tick(void* e, uint32_t frames, float* out_interleaved) {

@@ -310,6 +310,25 @@ int emu_wsola_window(float engine_sr, float* out, int cap) {
   for (uint32_t i = 0; i < 2 * hop && (int)i < cap; i++) out[i] = wsola_window_coeff(i, 2 * hop);
   return (int)hop;
 }
+// One SamplerRack descriptor with a pad table and a hit list (what the host resolves a rack pattern into), rendered in `n_pieces` kernel-like
+// passes of `piece` frames with the descriptor carried over: the device starts the voices itself at the hit frames.
+int emu_sampler_rack_hits(int n_pads, const float* const* pads, const uint32_t* frames, const uint32_t* channels, const double* inc,
+                          int n_hits, const uint32_t* hit_frame, const uint32_t* hit_slot, const float* hit_vel, int piece, int n_pieces, float* out_l, float* out_r) {
+  SamplerRack r;
+  memset(&r, 0, sizeof r);
+  for (int k = 0; k < n_pads && k < SAMPLER_SLOTS; k++) r.slots[k] = SamplerSlotRef{pads[k], frames[k], channels[k], inc[k]};
+  std::vector<SamplerHit> hits(n_hits);
+  for (int k = 0; k < n_hits; k++) hits[k] = SamplerHit{hit_frame[k], hit_slot[k], hit_vel[k], 0u};
+  r.hits = hits.data(); r.n_hits = (uint32_t)n_hits;
+  for (int p = 0; p < n_pieces; p++) {
+    SamplerRack d = r;                                  // the kernel's local copy, written back at the end of the launch
+    for (int f = 0; f < piece; f++) sampler_rack_tick(d, out_l[p * piece + f], out_r[p * piece + f]);
+    r = d;
+  }
+  int alive = 0;
+  for (int v = 0; v < SAMPLER_VOICES; v++) alive += r.v[v].samples != nullptr;
+  return alive;
+}
 double emu_window_fold(float loop_start, float loop_end, double len, double p) { return window_fold(loop_window(loop_start, loop_end, len), p); }
 double emu_window_lo(float loop_start, float loop_end, double len) { return loop_window(loop_start, loop_end, len).lo; }
 // One SamplerRack descriptor: n_voices (<= 32) voices started at position 0 (voice v plays pads[v], frames[v] x channels[v], increment inc[v],

@@ -526,3 +526,160 @@ def test_device_queued_swap_matches_oracle_bit_for_bit(seed):
     assert np.array_equal(got, want), (np.abs(got - want).max(), int(np.argmax((got != want).any(1))))
     assert cur[0] == cursor(o, 0)
     o.close()
+
+
+# ---- sampler-rack step patterns on the transport (sampler.rs:232-310, ffi.rs:1139-1147, 1199-1210, clip_grid.rs:174-191) -------------
+def oracle_hits(o, rack=0, cap=4096):
+    L = O.lib()
+    u32, f32 = c.c_uint32, c.c_float
+    fr, sl, ve = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.float32)
+    L.orc_engine_sampler_hit_log.argtypes = [c.c_void_p, u32, c.POINTER(u32), c.POINTER(u32), c.POINTER(f32), u32]
+    L.orc_engine_sampler_hit_log.restype = u32
+    n = L.orc_engine_sampler_hit_log(o._h, rack, fr.ctypes.data_as(c.POINTER(u32)), sl.ctypes.data_as(c.POINTER(u32)), ve.ctypes.data_as(c.POINTER(f32)), cap)
+    return [(int(fr[i]), int(sl[i]), float(ve[i])) for i in range(n)]
+
+
+def product_schedule(sr, bpm, swing, steps, transport_running, transport_beat, pending_beat, bounce, calls, cap=4096):
+    """gooey_b200_sampler_schedule: the host code engines_render runs for a rack pattern (no device needed)."""
+    from libgooey_b200._lib import lib
+    L = lib()
+    u8, u32, f32 = c.c_uint8, c.c_uint32, c.c_float
+    en = (u8 * 16)(*[1 if s[0] else 0 for s in steps]); pd = (u8 * 16)(*[s[1] for s in steps]); ve = (f32 * 16)(*[s[2] for s in steps])
+    cl = (u32 * len(calls))(*calls)
+    of, op, ov = (u32 * cap)(), (u32 * cap)(), (f32 * cap)()
+    beat = c.c_double(0.0)
+    L.gooey_b200_sampler_schedule.restype = u32
+    L.gooey_b200_sampler_schedule.argtypes = [f32, f32, f32, c.POINTER(u8), c.POINTER(u8), c.POINTER(f32), c.c_int, c.c_double, c.c_double, c.c_int,
+                                              c.POINTER(u32), u32, c.POINTER(u32), c.POINTER(u32), c.POINTER(f32), u32, c.POINTER(c.c_double)]
+    n = L.gooey_b200_sampler_schedule(sr, bpm, swing, en, pd, ve, int(transport_running), transport_beat, pending_beat, int(bounce), cl, len(calls),
+                                      of, op, ov, cap, c.byref(beat))
+    return [(int(of[i]), int(op[i]), float(ov[i])) for i in range(n)], beat.value
+
+
+def random_steps(rng):
+    return [(bool(rng.random() < 0.5), int(rng.integers(0, 16)), float(np.float32(rng.uniform(0.1, 1.0)))) for _ in range(16)]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_rack_pattern_schedule_matches_the_oracle_exactly(seed):
+    """Armed start on the running transport, quantised to the next sixteenth / quarter / bar after some rendering; hits over several calls."""
+    rng = np.random.default_rng(5000 + seed)
+    sr = [44100.0, 48000.0][seed % 2]
+    bpm = float(np.float32(rng.uniform(70, 180)))
+    swing = 0.5 if seed % 3 else float(np.float32(rng.uniform(0.4, 0.7)))
+    steps = random_steps(rng)
+    steps[0] = (True, steps[0][1], steps[0][2])
+    o = O.oracle_engine(sr)
+    if seed % 2:
+        o.set_bpm(bpm)                                           # a rack registered later starts at the engine's current tempo (ffi.rs:6014-6018)
+    assert o.sampler_register() == 0
+    o.set_bpm(bpm); o.set_swing(swing)
+    for i, (en, pad, vel) in enumerate(steps):
+        assert o.sampler_set_step(0, i, en, pad, vel)
+    assert o.sampler_get_step(0, 3) == (steps[3][0], steps[3][1], pytest.approx(steps[3][2]))
+    pre = int(rng.integers(0, 30000))                        # frames rendered with the transport running before the pattern is armed
+    o.sequencer_start()
+    if pre:
+        o.render(pre)
+    q = seed % 3
+    assert o.sampler_start_pattern(0, q) and not o.sampler_start_pattern(0, 3) and not o.sampler_start_pattern(1, q)
+    pending = o.sampler_get_pending_start_beat(0)
+    assert pending > 0.0 and not o.sampler_is_pattern_running(0)
+    calls = [int(x) for x in rng.integers(1, 40000, 4)] + [int(4 * 60.0 / bpm * sr) + 20000]      # the last call reaches past a whole bar
+    for n in calls:
+        o.render(n)
+    want = [(f - pre, s, v) for (f, s, v) in oracle_hits(o)]
+    L = O.lib(); L.orc_engine_transport_beat.restype = c.c_double; L.orc_engine_transport_beat.argtypes = [c.c_void_p]
+    beat_after_pre, _ = product_schedule(sr, bpm, swing, steps, True, 0.0, -1.0, False, [pre] if pre else [1])[1], None
+    if not pre:
+        beat_after_pre = 0.0
+    got, beat = product_schedule(sr, bpm, swing, steps, True, beat_after_pre, pending, False, calls)
+    assert len(want) > 2 and o.sampler_is_pattern_running(0) and o.sampler_get_pending_start_beat(0) == -1.0
+    assert got == want
+    assert beat == L.orc_engine_transport_beat(o._h)
+    o.close()
+
+
+def test_rack_pattern_waits_for_the_transport_and_restarts_with_every_bounce():
+    """Armed with the transport stopped -> beat 0 -> fires on the first frame after sequencer_start; a bounce resets the rack's sequencer to step 0
+    without touching the transport; stop_pattern / sequencer_stop silence it."""
+    rng = np.random.default_rng(77)
+    steps = random_steps(rng); steps[0] = (True, 2, 0.9)
+    o = O.oracle_engine()
+    o.sampler_register()
+    for i, (en, pad, vel) in enumerate(steps):
+        o.sampler_set_step(0, i, en, pad, vel)
+    assert o.sampler_start_pattern(0, 2) and o.sampler_get_pending_start_beat(0) == 0.0
+    o.render(3000)                                              # transport stopped: nothing happens
+    assert oracle_hits(o) == [] and not o.sampler_is_pattern_running(0)
+    o.sequencer_start()
+    o.render(20000)
+    first = oracle_hits(o)
+    assert first[0] == (3000, 2, pytest.approx(0.9)) and o.sampler_is_pattern_running(0)
+    got, _ = product_schedule(44100.0, 120.0, 0.5, steps, True, 0.0, 0.0, False, [20000])
+    assert got == [(f - 3000, s, v) for (f, s, v) in first]
+    n0 = len(first)
+    o.bounce_to_buffer(1)                                       # 88 200 frames from step 0
+    bounced = [(f - 23000, s, v) for (f, s, v) in oracle_hits(o)[n0:]]
+    got, _ = product_schedule(44100.0, 120.0, 0.5, steps, True, 0.0, -1.0, True, [88200])
+    assert got == bounced and bounced[0][0] == 0
+    assert o.sampler_stop_pattern(0) and not o.sampler_is_pattern_running(0)
+    n1 = len(oracle_hits(o))
+    o.render(10000)
+    assert len(oracle_hits(o)) == n1
+    o.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_device_rack_starts_pattern_hits_like_the_oracle(seed):
+    """The device function that starts voices at the hit frames (free voice first, then the oldest), across kernel-like pieces, against the oracle
+    playing the same pattern — bit for bit."""
+    rng = np.random.default_rng(6000 + seed)
+    sr = 44100.0
+    o = O.oracle_engine(sr)
+    o.set_bpm(170.0)
+    o.sampler_register()
+    pads = []
+    for slot in range(6):
+        n = int(rng.integers(200, 6000)) if seed != 3 else int(rng.integers(150000, 190000))      # seed 3: pads outlive 32 later hits -> stealing
+        chn = int(rng.integers(1, 3))
+        pcm = rng.uniform(-1, 1, (n, chn)).astype(np.float32)
+        psr = float(rng.choice([44100.0, 22050.0, 48000.0]))
+        o.sampler_set_slot_buffer(0, slot, pcm, psr)
+        pads.append((pcm, psr))
+    steps = [(bool(rng.random() < 0.8), int(rng.integers(0, 7)), float(np.float32(rng.uniform(0.2, 1.0)))) for _ in range(16)]   # pad 6 is empty: a hit on it is dropped
+    for i, (en, pad, vel) in enumerate(steps):
+        o.sampler_set_step(0, i, en, pad, vel)
+    o.sampler_start_pattern(0, 0)
+    o.sequencer_start()
+    piece, n_pieces = 4096, 48
+    want = rack_tick_with_engine(o, piece * n_pieces)
+    hits = oracle_hits(o)
+    L = EMU.lib()
+    fp = c.POINTER(c.c_float)
+    ptrs = (fp * 6)()
+    fr = np.zeros(6, np.uint32); chs = np.zeros(6, np.uint32); inc = np.zeros(6, np.float64)
+    for k, (pcm, psr) in enumerate(pads):
+        ptrs[k] = pcm.ctypes.data_as(fp); fr[k] = pcm.shape[0]; chs[k] = pcm.shape[1]; inc[k] = float(np.float32(psr)) / float(np.float32(sr))
+    hf = np.array([h[0] for h in hits], np.uint32); hs = np.array([h[1] for h in hits], np.uint32); hv = np.array([h[2] for h in hits], np.float32)
+    ol = np.zeros(piece * n_pieces, np.float32); orr = np.zeros(piece * n_pieces, np.float32)
+    p = lambda arr, t: arr.ctypes.data_as(c.POINTER(t))
+    L.emu_sampler_rack_hits(6, ptrs, p(fr, c.c_uint32), p(chs, c.c_uint32), p(inc, c.c_double), len(hits), p(hf, c.c_uint32), p(hs, c.c_uint32), p(hv, c.c_float),
+                            piece, n_pieces, p(ol, c.c_float), p(orr, c.c_float))
+    got = np.stack([ol, orr], 1)
+    assert len(hits) > 30 and np.abs(want).max() > 0.1
+    assert np.array_equal(got, want), np.abs(got - want).max()
+    o.close()
+
+
+def rack_tick_with_engine(o, frames):
+    """Rack 0's own stereo frames while the ENGINE renders `frames` frames (so that the pattern and the transport run)."""
+    L = O.lib()
+    L.orc_engine_capture_rack0.argtypes = [c.c_void_p, c.c_bool]; L.orc_engine_capture_rack0.restype = None
+    L.orc_engine_rack0_capture.argtypes = [c.c_void_p, c.c_void_p, c.c_uint32]; L.orc_engine_rack0_capture.restype = c.c_uint32
+    L.orc_engine_capture_rack0(o._h, True)
+    o.render(frames)
+    out = np.zeros((frames, 2), np.float32)
+    assert L.orc_engine_rack0_capture(o._h, out.ctypes.data, frames) == frames
+    L.orc_engine_capture_rack0(o._h, False)
+    return out

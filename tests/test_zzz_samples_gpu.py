@@ -238,6 +238,38 @@ def test_sampler_voice_stealing_takes_the_oldest_voice():
     assert np.abs(got - want).max() <= EXACT_TOL
 
 
+def test_sampler_rack_pattern_armed_on_the_transport_bounced_and_stopped():
+    """The rack's 16-step pattern (ffi.rs:6173-6290): armed on the next quarter of the running transport, fires inside a render call, keeps
+    running across calls, restarts from step 0 in a bounce, is silenced by stop_pattern; with the kit playing next to it."""
+    def run(e):
+        busy_pattern(e)
+        assert e.sampler_register() == 0 and e.mixer_route_source(5, 2)
+        e.set_bpm(140.0); e.set_swing(0.58)
+        for slot, (n, ch, sr) in enumerate([(9000, 2, 44100.0), (2500, 1, 22050.0), (700, 2, 48000.0), (40000, 1, 44100.0)]):
+            e.sampler_set_slot_buffer(0, slot, pcm(60 + slot, n, channels=ch), sr)
+        for step in range(16):
+            e.sampler_set_step(0, step, step % 3 != 1, (step * 5) % 6, 0.3 + 0.04 * step)          # pads 4 and 5 are empty: their hits are dropped
+        info = [e.sampler_get_step(0, 7), e.sampler_start_pattern(0, 3), e.sampler_is_pattern_running(0)]
+        e.sequencer_start()
+        a = e.render(5000)
+        assert e.sampler_start_pattern(0, 1)                                                      # the next quarter note
+        info.append(e.sampler_get_pending_start_beat(0))
+        b = e.render(30000)
+        info += [e.sampler_is_pattern_running(0), e.sampler_get_pending_start_beat(0)]
+        cc = e.render(12345)
+        bounced = e.bounce_to_buffer(1)
+        e.sequencer_start()                                                                       # the bounce stopped the sequencers
+        d = e.render(4000)
+        assert e.sampler_stop_pattern(0)
+        f = e.render(3000)
+        return np.concatenate([a, b, cc, d, f]), bounced, info
+    (got, gb, ginfo), (want, wb, winfo) = both(lambda e: None, run)
+    assert ginfo == winfo and winfo[1] is False and winfo[4] is True and winfo[5] == -1.0
+    assert np.abs(want).max() > 0.05 and np.abs(wb).max() > 0.05
+    assert np.abs(got - want).max() <= TOL
+    assert np.abs(gb - wb).max() <= TOL
+
+
 def test_batch_of_engines_with_and_without_sources():
     """Row pairs are handed out per engine and source: engines without loops, with loops, with racks, in one launch."""
     n = 40
@@ -295,9 +327,7 @@ def test_engines_sharing_one_resident_loop_buffer():
 def test_requests_for_parts_that_are_not_built_latch_the_sticky_error():
     L = G.lib()
     L.gooey_engine_loop_effect_add.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32]; L.gooey_engine_loop_effect_add.restype = c.c_int32
-    L.gooey_engine_sampler_set_step.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, c.c_bool, c.c_uint32, c.c_float]; L.gooey_engine_sampler_set_step.restype = c.c_bool
-    for call in (lambda e: L.gooey_engine_loop_effect_add(e._h, 0, 1),
-                 lambda e: L.gooey_engine_sampler_set_step(e._h, 0, 0, True, 0, 1.0)):
+    for call in (lambda e: L.gooey_engine_loop_effect_add(e._h, 0, 1),):
         g = G.Engine()
         assert not g.has_error()
         call(g)
