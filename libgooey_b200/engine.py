@@ -144,6 +144,24 @@ class Engine:
         return bool(getattr(self._L, self._prefix + "loop_queue_swap")(self._h, channel, a.ctypes.data, frames, channels, c.c_float(sample_rate),
                                                                         c.c_float(source_bpm), divisions))
 
+    # Synthetic PCM by formula, so that a call script (tests/golden/ref/scripts/*.calls) can load buffers without carrying them:
+    # rust/examples/dump_golden.rs evaluates the same integer formula inside libgooey.
+    @staticmethod
+    def synth_pcm(frames, channels, seed):
+        k = np.arange(frames, dtype=np.uint64)[:, None]
+        ch = np.arange(channels, dtype=np.uint64)[None, :]
+        v = ((k * np.uint64(37) + ch * np.uint64(101) + np.uint64(seed) * np.uint64(977)) * (k % np.uint64(89) + np.uint64(3))) % np.uint64(2001)
+        return ((v.astype(np.int64) - 1000).astype(np.float32) / np.float32(1024.0)).astype(np.float32)
+
+    def loop_load_synth(self, channel, frames, channels, sample_rate, seed):
+        return self.loop_load(channel, self.synth_pcm(frames, channels, seed), sample_rate)
+
+    def loop_queue_swap_synth(self, channel, frames, channels, sample_rate, seed, source_bpm, divisions):
+        return self.loop_queue_swap(channel, self.synth_pcm(frames, channels, seed), sample_rate, source_bpm, divisions)
+
+    def sampler_set_slot_synth(self, rack, slot, frames, channels, sample_rate, seed):
+        return self.sampler_set_slot_buffer(rack, slot, self.synth_pcm(frames, channels, seed), sample_rate)
+
     def loop_share_buffer(self, channel, src, src_channel):
         """gooey_b200_loop_share_buffer (product only): play the buffer `src` already holds on the device."""
         f = self._L.gooey_b200_loop_share_buffer

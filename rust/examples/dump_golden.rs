@@ -19,7 +19,8 @@
 //!   preset_kit.f32le        every preset voice of tests/golden_cases.py::kit_patches, 4096 frames each, trigger at t = 0
 //!   c1_kick.f32le           BASELINE config C1: Engine + KickDrum::new + pattern [1,0,...], bounce_to_buffer(Samples(44100))
 //!   engine_<name>.f32le     for every <name>.calls in the scripts directory: the FFI calls replayed on gooey_engine_new(44100),
-//!                           then gooey_engine_bounce_to_buffer(bars) (bars = the script's `bounce` line)
+//!                           then gooey_engine_bounce_to_buffer(bars) (bars = the script's `bounce` line); sample_playback.calls
+//!                           covers the loop mixer (direct / Resample / WSOLA, a queued take) and a sampler rack with its pattern
 //!   sweep64.f32le           for sweep64.voices: 64 voices built with `<Voice>Config::new_full` / Tom2::set_config, 8192 frames
 use std::collections::hash_map::DefaultHasher;
 use std::fs;
@@ -130,6 +131,18 @@ fn sweep(path: &Path, frames: usize) -> Vec<f32> {
 }
 
 /// Replays one `<name>.calls` script (written by tests/golden/make_ref_scripts.py) through the C FFI.
+/// Interleaved synthetic PCM by formula — `Engine.synth_pcm` of libgooey_b200/engine.py: exact in f32 (an integer in -1000..=1000 over 1024).
+fn synth_pcm(frames: usize, channels: usize, seed: u64) -> Vec<f32> {
+    let mut out = Vec::with_capacity(frames * channels);
+    for k in 0..frames as u64 {
+        for ch in 0..channels as u64 {
+            let v = ((k * 37 + ch * 101 + seed * 977) * (k % 89 + 3)) % 2001;
+            out.push((v as i64 - 1000) as f32 / 1024.0);
+        }
+    }
+    out
+}
+
 fn replay(path: &Path) -> Vec<f32> {
     let text = fs::read_to_string(path).expect("script");
     let e = ffi::gooey_engine_new(SR);
@@ -168,6 +181,43 @@ fn replay(path: &Path) -> Vec<f32> {
                 "mixer_set_track_pan" => ffi::gooey_engine_mixer_set_track_pan(e, u(1), f(2)),
                 "set_global_effect_param" => ffi::gooey_engine_set_global_effect_param(e, u(1), u(2), f(3)),
                 "set_global_effect_enabled" => ffi::gooey_engine_set_global_effect_enabled(e, u(1), b(2)),
+                "sequencer_start" => ffi::gooey_engine_sequencer_start(e),
+                // sample-playback sources; the `_synth` forms load synth_pcm buffers (below) so the scripts carry no audio
+                "loop_load_synth" => {
+                    let pcm = synth_pcm(u(2) as usize, u(3) as usize, u(5) as u64);
+                    assert!(ffi::gooey_engine_loop_load(e, u(1), pcm.as_ptr(), u(2), u(3), f(4)));
+                }
+                "loop_queue_swap_synth" => {
+                    let pcm = synth_pcm(u(2) as usize, u(3) as usize, u(5) as u64);
+                    assert!(ffi::gooey_engine_loop_queue_swap(e, u(1), pcm.as_ptr(), u(2), u(3), f(4), f(6), u(7)));
+                }
+                "loop_set_playing" => ffi::gooey_engine_loop_set_playing(e, u(1), b(2)),
+                "loop_set_gain" => ffi::gooey_engine_loop_set_gain(e, u(1), f(2)),
+                "loop_set_mute" => ffi::gooey_engine_loop_set_mute(e, u(1), b(2)),
+                "loop_set_solo" => ffi::gooey_engine_loop_set_solo(e, u(1), b(2)),
+                "loop_set_start" => ffi::gooey_engine_loop_set_start(e, u(1), f(2)),
+                "loop_set_end" => ffi::gooey_engine_loop_set_end(e, u(1), f(2)),
+                "loop_set_speed" => ffi::gooey_engine_loop_set_speed(e, u(1), f(2)),
+                "loop_set_source_bpm" => ffi::gooey_engine_loop_set_source_bpm(e, u(1), f(2)),
+                "loop_set_pitch_mode" => ffi::gooey_engine_loop_set_pitch_mode(e, u(1), u(2)),
+                "loop_restart" => ffi::gooey_engine_loop_restart(e, u(1)),
+                "loop_set_position" => ffi::gooey_engine_loop_set_position(e, u(1), f(2)),
+                "sampler_register" => {
+                    assert!(ffi::gooey_engine_sampler_register(e) >= 0);
+                }
+                "sampler_set_slot_synth" => {
+                    let pcm = synth_pcm(u(3) as usize, u(4) as usize, u(6) as u64);
+                    assert!(ffi::gooey_engine_sampler_set_slot_buffer(e, u(1), u(2), pcm.as_ptr(), u(3), u(4), f(5)));
+                }
+                "sampler_set_step" => {
+                    ffi::gooey_engine_sampler_set_step(e, u(1), u(2), b(3), u(4), f(5));
+                }
+                "sampler_trigger" => {
+                    ffi::gooey_engine_sampler_trigger(e, u(1), u(2), f(3));
+                }
+                "sampler_start_pattern" => {
+                    ffi::gooey_engine_sampler_start_pattern(e, u(1), u(2));
+                }
                 other => panic!("dump_golden: unknown call `{other}` in {}", path.display()),
             }
         }

@@ -31,6 +31,10 @@ class Recorder:
         self._tracks += 1
         return self._tracks - 1
 
+    def sampler_register(self):
+        self.lines.append("sampler_register")
+        return 0
+
     def mixer_route_source(self, source, track):
         self.lines.append(f"mixer_route_source {int(source)} {int(track)}")
         return True
@@ -55,6 +59,7 @@ def main():
     from workloads import drum_sweep_raw
     os.makedirs(OUT, exist_ok=True)
     cases = dict(GC.ENGINE_CASES)
+    cases.update(GC.REF_CASES)
     cases["c3_style_7"] = lambda e: (S.random_voice_params(e, 1007), S.pattern_engine(e, 2007, swing=0.61))
     for name, script in cases.items():
         r = Recorder()

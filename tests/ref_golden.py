@@ -36,7 +36,8 @@ def replay(engine, name):
     return bars
 
 
-_BOOL_ARGS = {"sequencer_set_instrument_step": (2,), "sequencer_set_instrument_step_settings": (2, 3, 5, 8), "set_global_effect_enabled": (1,)}
+_BOOL_ARGS = {"sequencer_set_instrument_step": (2,), "sequencer_set_instrument_step_settings": (2, 3, 5, 8), "set_global_effect_enabled": (1,),
+              "loop_set_playing": (1,), "loop_set_mute": (1,), "loop_set_solo": (1,), "sampler_set_step": (2,)}
 
 
 def _typed(name, args):

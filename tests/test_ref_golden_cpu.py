@@ -19,7 +19,7 @@ def test_scripts_are_current_and_replayable():
     for f, text in keep.items():
         assert open(os.path.join(R.SCRIPTS, f)).read() == text, f"{f} is stale: rerun tests/golden/make_ref_scripts.py"
     import golden_cases as GC
-    for name, script in GC.ENGINE_CASES.items():
+    for name, script in list(GC.ENGINE_CASES.items()) + list(GC.REF_CASES.items()):
         a = O.oracle_engine(); b = O.oracle_engine()
         script(a); bars = R.replay(b, name)
         wa, wb = a.bounce_to_buffer(1), b.bounce_to_buffer(bars)
