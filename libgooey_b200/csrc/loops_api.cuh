@@ -134,8 +134,8 @@ int32_t gooey_engine_loop_effect_add(GooeyEngine* e, uint32_t, uint32_t) {
 // Mixer::render_channel_to_interleaved (mixer/mod.rs:444-476): `frames` stereo frames of one loop channel from its loop start,
 // ignoring mute / solo, after prepare_offline_render (playing, fader snapped, gate open) — the audio of
 // gooey_engine_loop_render_to_wav.  With no per-channel effects the preroll only moves the cursor and the stretcher, and both
-// are reset by the restart that follows it.
-bool gooey_engine_loop_render(GooeyEngine* e, uint32_t channel, uint32_t frames, uint32_t /*preroll*/, float* out_interleaved) {
+// are reset by the restart that follows it — unless a queued take lands during it, so then it is rendered (and discarded) too.
+bool gooey_engine_loop_render(GooeyEngine* e, uint32_t channel, uint32_t frames, uint32_t preroll, float* out_interleaved) {
   auto* c = gh::loop_ch(e, channel);
   if (!c || !out_interleaved || frames == 0 || !c->buf || c->len == 0) return false;
   gh::EngineBank& B = *e->bank;
@@ -143,24 +143,31 @@ bool gooey_engine_loop_render(GooeyEngine* e, uint32_t channel, uint32_t frames,
     std::lock_guard<std::recursive_mutex> lk(B.mu);
     gh::use_device(B.device);
     c->playing = true; c->gain.c = c->gain.t; c->active = {1.0f, 1.0f};
-    c->cursor = c->window().lo; c->st_valid = false;                              // prepare_offline_render + restart (loop_channel.rs:444-451)
-    gd::LoopMixer m;
-    memset(&m, 0, sizeof m);
-    c->describe(m.ch[0], e->loop_engine_bpm);
-    B.attach_stretcher(*c, m.ch[0]);
-    m.row = 0;
-    const size_t stride = ((size_t)frames + 31) & ~(size_t)31;
+    c->cursor = c->window().lo; c->st_valid = false;                              // prepare_offline_render (loop_channel.rs:444-451)
+    const uint32_t longest = std::max(frames, c->has_pending ? preroll : 0u);
+    const size_t stride = ((size_t)longest + 31) & ~(size_t)31;
     B.d_ext[0].alloc(2 * stride);
-    B.d_loop_descs.upload(&m, 1, B.stream);
-    gd::ext_source_kernel<gd::LoopMixer><<<1, 64, 0, B.stream>>>(B.d_loop_descs.p, 1, B.d_ext[0].p, (long long)stride, (int)frames, gd::ExtTickCtx{e->sr, B.rc.smooth15});
-    gh::g_launches.fetch_add(1, std::memory_order_relaxed);
-    GH_CUDA(cudaGetLastError());
+    gd::LoopMixer m;
+    auto pass = [&](uint32_t nf) {                                                 // nf ticks of the channel on its own into the row pair 0
+      memset(&m, 0, sizeof m);
+      c->describe(m.ch[0], e->loop_engine_bpm);
+      B.attach_stretcher(*c, m.ch[0]);
+      m.row = 0;
+      B.d_loop_descs.upload(&m, 1, B.stream);
+      gd::ext_source_kernel<gd::LoopMixer><<<1, 64, 0, B.stream>>>(B.d_loop_descs.p, 1, B.d_ext[0].p, (long long)stride, (int)nf, gd::ExtTickCtx{e->sr, B.rc.smooth15});
+      gh::g_launches.fetch_add(1, std::memory_order_relaxed);
+      GH_CUDA(cudaGetLastError());
+      GH_CUDA(cudaMemcpyAsync(&m, B.d_loop_descs.p, sizeof m, cudaMemcpyDeviceToHost, B.stream));
+      GH_CUDA(cudaStreamSynchronize(B.stream));
+      c->absorb(m.ch[0]);
+    };
+    // the discarded preroll can only matter through a queued take that lands during it (there are no per-channel effects to warm)
+    if (c->has_pending && preroll) pass(preroll);
+    c->cursor = c->window().lo; c->st_valid = false;                              // restart() after the preroll (mod.rs:465-466)
+    pass(frames);
     std::vector<float> planes(2 * stride);
-    GH_CUDA(cudaMemcpyAsync(planes.data(), B.d_ext[0].p, planes.size() * 4, cudaMemcpyDeviceToHost, B.stream));
-    GH_CUDA(cudaMemcpyAsync(&m, B.d_loop_descs.p, sizeof m, cudaMemcpyDeviceToHost, B.stream));
-    GH_CUDA(cudaStreamSynchronize(B.stream));
+    GH_CUDA(cudaMemcpy(planes.data(), B.d_ext[0].p, planes.size() * 4, cudaMemcpyDeviceToHost));
     for (uint32_t f = 0; f < frames; f++) { out_interleaved[2 * (size_t)f] = planes[f]; out_interleaved[2 * (size_t)f + 1] = planes[stride + f]; }
-    c->absorb(m.ch[0]);
   } catch (const std::exception& ex) { gh::set_error(ex.what()); gh::engine_fail(e, ex.what()); return false; }
   return true;
 }
