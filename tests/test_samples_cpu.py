@@ -683,3 +683,43 @@ def rack_tick_with_engine(o, frames):
     assert L.orc_engine_rack0_capture(o._h, out.ctypes.data, frames) == frames
     L.orc_engine_capture_rack0(o._h, False)
     return out
+
+
+# ---- edge cases of the device functions, bit for bit against the oracle --------------------------------------------------------------
+EDGES = [
+    dict(n=1, start=0.0, end=1.0, speed=1.0, mode=0),            # one-frame buffer: every read is that frame
+    dict(n=1, start=0.0, end=1.0, speed=1.0, mode=2),
+    dict(n=2, start=0.0, end=1.0, speed=-4.0, mode=0),
+    dict(n=500, start=0.5, end=0.5, speed=1.0, mode=0),          # empty window: span clamps to one frame
+    dict(n=500, start=0.5, end=0.5, speed=-0.7, mode=1),
+    dict(n=500, start=0.5, end=0.5, speed=1.0, mode=2),
+    dict(n=3000, start=0.0, end=1.0, speed=0.0, mode=0),         # frozen cursor
+    dict(n=3000, start=0.2, end=0.9, speed=0.0, mode=2),         # WSOLA with a zero native step (floored at 1e-6)
+    dict(n=3000, start=1.0, end=0.0, speed=1.3, mode=0),         # start past end at the extremes: the whole buffer as a wrap-around window
+    dict(n=3000, start=1.0, end=0.0, speed=1.3, mode=2),
+    dict(n=40000, start=0.0, end=1.0, speed=4.0, mode=2),        # fastest varispeed through the stretcher
+    dict(n=7, start=0.9, end=0.1, speed=4.0, mode=1),            # window shorter than one step
+]
+
+
+@pytest.mark.parametrize("k", range(len(EDGES)))
+def test_device_loop_channel_edge_cases_match_the_oracle(k):
+    ed = EDGES[k]
+    rng = np.random.default_rng(7000 + k)
+    n, start, end, speed, mode = ed["n"], ed["start"], ed["end"], ed["speed"], ed["mode"]
+    pcm = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    buf_sr, engine_sr, bpm, src_bpm = 48000.0, 44100.0, 133.0, 97.0
+    o = O.oracle_engine(engine_sr)
+    assert o.loop_load(0, pcm, buf_sr)
+    o.loop_set_start(0, start); o.loop_set_end(0, end); o.loop_set_speed(0, speed); o.loop_restart(0)
+    o.loop_set_source_bpm(0, src_bpm); o.loop_set_pitch_mode(0, mode); o.set_bpm(bpm); o.loop_set_gain(0, 0.6); o.loop_set_playing(0, True)
+    frames = 5000
+    want = tick(o, frames)
+    ratio = float(np.float32(bpm)) / float(np.float32(src_bpm))
+    ch = dict(left=pcm[:, 0], right=pcm[:, 1], buf_sr=buf_sr, cursor=window_lo(start, end, n), start=start, end=end, speed=speed, playing=True,
+              warp=ratio if mode == 1 else 1.0, preserve=mode == 2, warp_pp=ratio if mode else 1.0, gain=(1.0, float(np.float32(0.6))))
+    got, cur, _, _ = emu_loop_mixer([ch, None, None, None], engine_sr, frames)
+    assert np.isfinite(want).all()
+    assert np.array_equal(got, want), (np.abs(got - want).max(), int(np.argmax((got != want).any(1))))
+    assert cur[0] == cursor(o, 0)
+    o.close()
