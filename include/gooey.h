@@ -239,6 +239,14 @@ uint32_t gooey_engine_get_effect_order(const GooeyEngine* engine, uint32_t* out_
 int32_t gooey_engine_mixer_add_track(GooeyEngine* engine, const char* name);
 uint32_t gooey_engine_mixer_get_track_count(const GooeyEngine* engine);
 bool gooey_engine_mixer_route_source(GooeyEngine* engine, uint32_t source, uint32_t track);
+bool gooey_engine_mixer_unroute_source(GooeyEngine* engine, uint32_t source);                        /* :6427 */
+int32_t gooey_engine_mixer_get_source_route(const GooeyEngine* engine, uint32_t source);             /* :6442, -1 = unrouted / inactive source */
+void gooey_engine_mixer_reset_default_layout(GooeyEngine* engine);                                   /* :6295: Drums / Bass / Synth / Loops, fresh strips and routes */
+void gooey_engine_mixer_clear_layout(GooeyEngine* engine);                                           /* :6313: no tracks, no routes */
+float gooey_engine_mixer_get_track_gain(const GooeyEngine* engine, uint32_t track);                  /* :6472 */
+float gooey_engine_mixer_get_track_pan(const GooeyEngine* engine, uint32_t track);                   /* :6501 */
+bool gooey_engine_mixer_get_track_mute(const GooeyEngine* engine, uint32_t track);                   /* :6530 */
+bool gooey_engine_mixer_get_track_solo(const GooeyEngine* engine, uint32_t track);                   /* :6559 */
 void gooey_engine_mixer_set_track_gain(GooeyEngine* engine, uint32_t track, float gain);
 void gooey_engine_mixer_set_track_pan(GooeyEngine* engine, uint32_t track, float pan);
 void gooey_engine_mixer_set_track_mute(GooeyEngine* engine, uint32_t track, bool muted);

@@ -407,6 +407,8 @@ struct GooeyEngine {
   gd::MixCfg cfg;
   std::vector<gd::VoiceEvent> mix_pending;
   bool track_muted[gd::MAX_TRACKS] = {false}, track_soloed[gd::MAX_TRACKS] = {false};
+  float track_gain_t[gd::MAX_TRACKS], track_pan_t[gd::MAX_TRACKS];     // the strips' targets, for the getters (graph.rs:196-215)
+  GooeyEngine() { for (int t = 0; t < gd::MAX_TRACKS; t++) { track_gain_t[t] = 1.0f; track_pan_t[t] = 0.5f; } }
   // LFO pool (ffi.rs:33-54, 716-719, 876-884): eight tempo-synced sine LFOs, disabled, Quarter division, amount 1, offset 0
   struct LfoHost { uint32_t division = 4; float phase = 0.0f, amount = 1.0f, offset = 0.0f; } lfos[8];
   bool lfo_enabled[8] = {false};

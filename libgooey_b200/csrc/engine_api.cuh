@@ -334,6 +334,7 @@ int32_t gooey_engine_mixer_add_track(GooeyEngine* e, const char*) {
   const uint32_t t = e->cfg.n_tracks++;
   e->cfg.rack_n[t] = 0;
   e->track_muted[t] = e->track_soloed[t] = false;
+  e->track_gain_t[t] = 1.0f; e->track_pan_t[t] = 0.5f;
   e->mix_pending.push_back(gh::make_event(0, gd::MX_TRACK_INIT, t, 0.0f));
   gh::sync_cfg(e);
   return (int32_t)t;
@@ -347,8 +348,51 @@ bool gooey_engine_mixer_route_source(GooeyEngine* e, uint32_t src, uint32_t trac
   gh::sync_cfg(e);
   return true;
 }
-void gooey_engine_mixer_set_track_gain(GooeyEngine* e, uint32_t t, float g) { if (e && t < e->cfg.n_tracks) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_TR_GAIN + t, gd::clampf(g, 0.0f, 2.0f))); }
-void gooey_engine_mixer_set_track_pan(GooeyEngine* e, uint32_t t, float p) { if (e && t < e->cfg.n_tracks) e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_TR_PAN + t, gd::clampf(p, 0.0f, 1.0f))); }
+void gooey_engine_mixer_set_track_gain(GooeyEngine* e, uint32_t t, float g) {
+  if (!e || t >= e->cfg.n_tracks) return;
+  const float c = gd::clampf(g, 0.0f, 2.0f);
+  if (fabsf(e->track_gain_t[t] - c) > 1e-8f) e->track_gain_t[t] = c;            // SmoothedParam::set_target keeps the old target within 1e-8
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_TR_GAIN + t, c));
+}
+void gooey_engine_mixer_set_track_pan(GooeyEngine* e, uint32_t t, float p) {
+  if (!e || t >= e->cfg.n_tracks) return;
+  const float c = gd::clampf(p, 0.0f, 1.0f);
+  if (fabsf(e->track_pan_t[t] - c) > 1e-8f) e->track_pan_t[t] = c;
+  e->mix_pending.push_back(gh::make_event(0, gd::MX_SET, gd::MP_TR_PAN + t, c));
+}
+// strip getters (ffi.rs:6472-6566): the targets, with the reference's defaults for a bad index
+float gooey_engine_mixer_get_track_gain(const GooeyEngine* e, uint32_t t) { return (e && t < e->cfg.n_tracks) ? e->track_gain_t[t] : 1.0f; }
+float gooey_engine_mixer_get_track_pan(const GooeyEngine* e, uint32_t t) { return (e && t < e->cfg.n_tracks) ? e->track_pan_t[t] : 0.5f; }
+bool gooey_engine_mixer_get_track_mute(const GooeyEngine* e, uint32_t t) { return e && t < e->cfg.n_tracks && e->track_muted[t]; }
+bool gooey_engine_mixer_get_track_solo(const GooeyEngine* e, uint32_t t) { return e && t < e->cfg.n_tracks && e->track_soloed[t]; }
+// graph routes and layout (ffi.rs:6291-6320, 6427-6455; graph.rs:131-149, 253-266)
+static bool source_is_active(const GooeyEngine* e, uint32_t src) { return src < 5 || (src < 9 && e->samplers[src - 5].registered); }
+bool gooey_engine_mixer_unroute_source(GooeyEngine* e, uint32_t src) {
+  if (!e || !source_is_active(e, src)) return false;
+  const bool had = e->cfg.route[src] >= 0;
+  e->cfg.route[src] = -1;
+  gh::sync_cfg(e);
+  return had;
+}
+int32_t gooey_engine_mixer_get_source_route(const GooeyEngine* e, uint32_t src) { return (e && source_is_active(e, src)) ? e->cfg.route[src] : -1; }
+bool gooey_engine_track_effect_remove(GooeyEngine* e, uint32_t t, uint32_t pos);
+void gooey_engine_mixer_clear_layout(GooeyEngine* e) {   // MixerGraph::reset: no tracks (their racks go with them), no routes; registered sources stay registered
+  if (!e) return;
+  for (uint32_t t = 0; t < e->cfg.n_tracks; t++) while (e->cfg.rack_n[t]) gooey_engine_track_effect_remove(e, t, 0);
+  e->cfg.n_tracks = 0;
+  for (int s = 0; s < 9; s++) e->cfg.route[s] = -1;
+  for (int t = 0; t < gd::MAX_TRACKS; t++) e->track_muted[t] = e->track_soloed[t] = false;
+  gh::sync_cfg(e);
+}
+int32_t gooey_engine_mixer_add_track(GooeyEngine* e, const char*);
+void gooey_engine_mixer_reset_default_layout(GooeyEngine* e) {   // MixerGraph::with_default_layout: Drums / Bass / Synth / Loops, fresh strips, the five fixed routes
+  if (!e) return;
+  gooey_engine_mixer_clear_layout(e);
+  for (int t = 0; t < 4; t++) gooey_engine_mixer_add_track(e, "");
+  const int32_t routes[5] = {0, 1, 2, 3, 3};
+  for (int s = 0; s < 5; s++) e->cfg.route[s] = routes[s];
+  gh::sync_cfg(e);
+}
 void gooey_engine_mixer_set_track_mute(GooeyEngine* e, uint32_t t, bool m) { if (e && t < e->cfg.n_tracks) e->track_muted[t] = m; }
 void gooey_engine_mixer_set_track_solo(GooeyEngine* e, uint32_t t, bool s) { if (e && t < e->cfg.n_tracks) e->track_soloed[t] = s; }
 int32_t gooey_engine_track_effect_add(GooeyEngine* e, uint32_t t, uint32_t fx) {   // ChannelEffect::from_id (effect_chain.rs:57-109): every effect but the limiter

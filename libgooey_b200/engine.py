@@ -46,10 +46,14 @@ _SIGS = {
     "loop_set_solo": [c.c_uint32, c.c_bool], "loop_set_start": [c.c_uint32, c.c_float], "loop_set_end": [c.c_uint32, c.c_float],
     "loop_set_speed": [c.c_uint32, c.c_float], "loop_set_source_bpm": [c.c_uint32, c.c_float], "loop_set_pitch_mode": [c.c_uint32, c.c_uint32],
     "loop_restart": [c.c_uint32], "loop_set_position": [c.c_uint32, c.c_float], "loop_cancel_queued_swap": [c.c_uint32],
+    "mixer_reset_default_layout": [], "mixer_clear_layout": [],
 }
 # functions with a return value: name -> (argument types after the handle, result type)
 _RSIGS = {
     "loop_swaps_completed": ([c.c_uint32], c.c_uint32),
+    "mixer_unroute_source": ([c.c_uint32], c.c_bool), "mixer_get_source_route": ([c.c_uint32], c.c_int32),
+    "mixer_get_track_gain": ([c.c_uint32], c.c_float), "mixer_get_track_pan": ([c.c_uint32], c.c_float),
+    "mixer_get_track_mute": ([c.c_uint32], c.c_bool), "mixer_get_track_solo": ([c.c_uint32], c.c_bool),
     "loop_get_source_bpm": ([c.c_uint32], c.c_float), "loop_get_pitch_mode": ([c.c_uint32], c.c_uint32), "loop_get_position": ([c.c_uint32], c.c_float),
     "sampler_register": ([], c.c_int32), "sampler_get_source_id": ([c.c_uint32], c.c_uint32),
     "sampler_clear_slot": ([c.c_uint32, c.c_uint32], c.c_bool), "sampler_slot_is_loaded": ([c.c_uint32, c.c_uint32], c.c_bool),

@@ -103,6 +103,9 @@ struct MixerGraph {
   size_t add_track() { tracks.emplace_back(sample_rate); scratch.push_back({}); return tracks.size() - 1; }
   void default_layout() { add_track(); add_track(); add_track(); add_track(); route(0, 0); route(1, 1); route(2, 2); route(3, 3); route(4, 3); }
   bool route(uint32_t src, size_t track) { if (source_is_active(src) && track < tracks.size()) { routes[src] = (int)track; return true; } return false; }
+  bool unroute(uint32_t src) { if (!source_is_active(src)) return false; bool had = routes[src] >= 0; routes[src] = -1; return had; }   // :253-259
+  int route_of(uint32_t src) const { return source_is_active(src) ? routes[src] : -1; }                                             // :262-266
+  void reset() { tracks.clear(); scratch.clear(); for (int& r : routes) r = -1; }                                                     // :145-149
   void set_bpm(float b) { bpm = b; for (auto& t : tracks) for (auto& e : t.rack) e->set_bpm(b); }
   void clear_scratch() { for (auto& s : scratch) s = {}; }
   void scatter(uint32_t src, StereoFrame f) { if (source_is_active(src) && routes[src] >= 0 && (size_t)routes[src] < scratch.size()) scratch[routes[src]] += f; }

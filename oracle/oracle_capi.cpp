@@ -314,6 +314,20 @@ bool orc_engine_track_effect_move(void* e, uint32_t t, uint32_t slot, uint32_t n
 }
 int32_t orc_engine_mixer_add_track(void* e, const char*) { return e ? (int32_t)E->graph.add_track() : -1; }
 bool orc_engine_mixer_route_source(void* e, uint32_t src, uint32_t track) { return e ? E->graph.route(src, track) : false; }
+// graph layout and strip getters (ffi.rs:6291-6320, 6427-6455, 6472-6566)
+bool orc_engine_mixer_unroute_source(void* e, uint32_t src) { return e ? E->graph.unroute(src) : false; }
+int32_t orc_engine_mixer_get_source_route(void* e, uint32_t src) { return e ? (int32_t)E->graph.route_of(src) : -1; }
+void orc_engine_mixer_clear_layout(void* e) { if (e) E->graph.reset(); }
+void orc_engine_mixer_reset_default_layout(void* e) {
+  if (!e) return;
+  E->graph = MixerGraph(E->sample_rate, E->bpm);
+  E->graph.default_layout();
+  for (uint32_t r = 0; r < 4; r++) if (E->samplers[r]) E->graph.register_source(5 + r);
+}
+float orc_engine_mixer_get_track_gain(void* e, uint32_t t) { return (e && t < E->graph.tracks.size()) ? E->graph.tracks[t].gain.target : 1.0f; }
+float orc_engine_mixer_get_track_pan(void* e, uint32_t t) { return (e && t < E->graph.tracks.size()) ? E->graph.tracks[t].pan.target : 0.5f; }
+bool orc_engine_mixer_get_track_mute(void* e, uint32_t t) { return e && t < E->graph.tracks.size() && E->graph.tracks[t].muted; }
+bool orc_engine_mixer_get_track_solo(void* e, uint32_t t) { return e && t < E->graph.tracks.size() && E->graph.tracks[t].soloed; }
 void orc_engine_mixer_set_track_gain(void* e, uint32_t t, float g) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].gain.set_target(clampf(g, 0.0f, 2.0f)); }
 void orc_engine_mixer_set_track_pan(void* e, uint32_t t, float p) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].pan.set_target(clampf(p, 0.0f, 1.0f)); }
 void orc_engine_mixer_set_track_mute(void* e, uint32_t t, bool m) { if (e && t < E->graph.tracks.size()) E->graph.tracks[t].muted = m; }

@@ -196,6 +196,32 @@ def test_registration_has_a_fixed_limit(e):                      # :21
     assert e.sampler_register() == -1
 
 
+def test_registration_keeps_legacy_sources_and_rack_routes_after_a_default_graph_reset(e):   # :21 (last assert), :43
+    rack = e.sampler_register()
+    assert e.mixer_get_source_route(0) == 0                      # SOURCE_DRUMKIT still on track 0
+    source = e.sampler_get_source_id(rack)
+    assert e.mixer_get_source_route(source) == -1
+    e.mixer_reset_default_layout()
+    assert e.mixer_route_source(source, 3)
+    assert e.mixer_get_source_route(source) == 3
+
+
+def test_graph_layout_calls(e):                                  # ffi.rs:6291-6320, 6427-6455, 6472-6566
+    assert [e.mixer_get_source_route(s) for s in range(6)] == [0, 1, 2, 3, 3, -1]
+    e.mixer_set_track_gain(1, 1.7); e.mixer_set_track_pan(2, 0.2); e.mixer_set_track_mute(0, True); e.mixer_set_track_solo(3, True)
+    assert e.mixer_get_track_gain(1) == pytest.approx(1.7) and e.mixer_get_track_pan(2) == pytest.approx(0.2)
+    assert e.mixer_get_track_mute(0) and e.mixer_get_track_solo(3) and not e.mixer_get_track_mute(1)
+    assert e.mixer_get_track_gain(9) == 1.0 and e.mixer_get_track_pan(9) == 0.5 and not e.mixer_get_track_solo(9)
+    assert e.mixer_unroute_source(1) and not e.mixer_unroute_source(1) and not e.mixer_unroute_source(7)
+    assert e.mixer_get_source_route(1) == -1
+    e.mixer_clear_layout()
+    assert [e.mixer_get_source_route(s) for s in range(5)] == [-1] * 5 and not e.mixer_route_source(0, 0)
+    assert e.mixer_add_track("only") == 0 and e.mixer_route_source(0, 0)
+    e.mixer_reset_default_layout()
+    assert [e.mixer_get_source_route(s) for s in range(5)] == [0, 1, 2, 3, 3]
+    assert e.mixer_get_track_gain(1) == 1.0 and not e.mixer_get_track_mute(0) and not e.mixer_get_track_solo(3)
+
+
 def test_loaded_slot_can_be_routed_and_triggered(e):             # :56 (up to the step pattern)
     rack = e.sampler_register()
     assert e.mixer_route_source(e.sampler_get_source_id(rack), 3)

@@ -270,6 +270,36 @@ def test_sampler_rack_pattern_armed_on_the_transport_bounced_and_stopped():
     assert np.abs(gb - wb).max() <= TOL
 
 
+def test_graph_layout_unroute_clear_and_reset_to_the_default():
+    """gooey_engine_mixer_{unroute_source,get_source_route,clear_layout,reset_default_layout} and the strip getters (ffi.rs:6291-6320,
+    6427-6455, 6472-6566): the audio after each layout edit and the values the getters report."""
+    def run(e):
+        busy_pattern(e)
+        e.loop_load(0, pcm(70, 4000), 44100.0); e.loop_set_playing(0, True)
+        e.mixer_set_track_gain(1, 1.6); e.mixer_set_track_pan(0, 0.3); e.mixer_set_track_mute(2, True)
+        slot = e.track_effect_add(1, 1)
+        e.track_effect_set_param(1, slot, 2, 0.5)
+        e.sequencer_start()
+        info = [[e.mixer_get_source_route(s) for s in range(6)], e.mixer_get_track_gain(1), e.mixer_get_track_pan(0), e.mixer_get_track_mute(2), e.mixer_get_track_solo(2)]
+        a = e.render(6000)
+        info.append((e.mixer_unroute_source(1), e.mixer_unroute_source(1), e.mixer_unroute_source(6), e.mixer_get_source_route(1)))
+        b = e.render(6000)                                   # the bass is out of the mix
+        e.mixer_clear_layout()
+        info.append(([e.mixer_get_source_route(s) for s in range(5)], e.mixer_route_source(0, 0)))
+        cc = e.render(3000)                                  # no tracks: silence
+        info.append((e.mixer_add_track("only"), e.mixer_route_source(0, 0), e.mixer_route_source(4, 0)))
+        d = e.render(6000)                                   # kit and loops on one fresh strip
+        e.mixer_reset_default_layout()
+        info.append(([e.mixer_get_source_route(s) for s in range(5)], e.mixer_get_track_gain(1), e.mixer_get_track_mute(2)))
+        f = e.render(6000)                                   # default strips again, the delay rack is gone
+        return np.concatenate([a, b, cc, d, f]), info
+    (got, ginfo), (want, winfo) = both(lambda e: None, run)
+    assert ginfo == winfo
+    assert winfo[0] == [0, 1, 2, 3, 3, -1] and winfo[5] == (True, False, False, -1) and winfo[6] == ([-1] * 5, False) and winfo[8][0] == [0, 1, 2, 3, 3]
+    assert np.abs(want[:6000]).max() > 0.05 and np.abs(want[12000:15000]).max() == 0.0 and np.abs(want[15000:]).max() > 0.05
+    assert np.abs(got - want).max() <= TOL
+
+
 def test_batch_of_engines_with_and_without_sources():
     """Row pairs are handed out per engine and source: engines without loops, with loops, with racks, in one launch."""
     n = 40
