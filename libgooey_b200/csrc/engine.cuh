@@ -791,9 +791,11 @@ inline void engines_render(const std::vector<GooeyEngine*>& E, uint32_t frames, 
     // rack patterns: resolved on the host into pad hits (resolve_rack_patterns above)
     gh::RackPattern* pats[gd::SAMPLER_RACKS];
     std::vector<gh::RackHit> rhits[gd::SAMPLER_RACKS];
-    for (int r = 0; r < gd::SAMPLER_RACKS; r++) pats[r] = e->samplers[r].registered ? &e->samplers[r].pat : nullptr;
-    gh::resolve_rack_patterns(e->transport, pats, gd::SAMPLER_RACKS, frames, bounce, e->seq_triggers_enabled, rhits);
-    for (int r = 0; r < gd::SAMPLER_RACKS; r++) {
+    bool any_rack = false;
+    for (int r = 0; r < gd::SAMPLER_RACKS; r++) { pats[r] = e->samplers[r].registered ? &e->samplers[r].pat : nullptr; any_rack = any_rack || pats[r]; }
+    if (any_rack) gh::resolve_rack_patterns(e->transport, pats, gd::SAMPLER_RACKS, frames, bounce, e->seq_triggers_enabled, rhits);
+    else if (e->transport.running) e->transport.lazy += frames;       // nothing listens to the transport: it just advances
+    for (int r = 0; any_rack && r < gd::SAMPLER_RACKS; r++) {
       auto& R = e->samplers[r];
       if (!R.registered) continue;
       std::vector<gd::SamplerHit> hits;
