@@ -356,6 +356,7 @@ bool gooey_engine_sampler_stop_pattern(GooeyEngine* engine, uint32_t rack);     
 bool gooey_engine_sampler_cancel_pattern_start(GooeyEngine* engine, uint32_t rack);                  /* :6225 */
 double gooey_engine_sampler_get_pending_start_beat(const GooeyEngine* engine, uint32_t rack);        /* :6239, -1 when none */
 bool gooey_engine_sampler_is_pattern_running(const GooeyEngine* engine, uint32_t rack);              /* :6253 */
+double gooey_engine_transport_get_beat_position(const GooeyEngine* engine);                          /* :7143: the mixer transport's beat clock */
 
 #ifdef __cplusplus
 }

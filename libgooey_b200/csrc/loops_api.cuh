@@ -268,6 +268,7 @@ bool gooey_engine_sampler_stop_pattern(GooeyEngine* e, uint32_t rack) {      /* 
 }
 bool gooey_engine_sampler_cancel_pattern_start(GooeyEngine* e, uint32_t rack) { auto* R = gh::rack_of(e, rack); if (!R) return false; R->pat.has_pending = false; return true; }
 double gooey_engine_sampler_get_pending_start_beat(const GooeyEngine* e, uint32_t rack) { const auto* R = gh::rack_of(e, rack); return (R && R->pat.has_pending) ? R->pat.pending_beat : -1.0; }
+double gooey_engine_transport_get_beat_position(const GooeyEngine* e) { return e ? const_cast<GooeyEngine*>(e)->transport.now() : 0.0; }   /* :7143-7150 */
 bool gooey_engine_sampler_is_pattern_running(const GooeyEngine* e, uint32_t rack) { const auto* R = gh::rack_of(e, rack); return R && R->pat.pattern_running; }
 
 }  // extern "C"

@@ -63,6 +63,7 @@ _RSIGS = {
     "sampler_start_pattern": ([c.c_uint32, c.c_uint32], c.c_bool), "sampler_stop_pattern": ([c.c_uint32], c.c_bool),
     "sampler_cancel_pattern_start": ([c.c_uint32], c.c_bool), "sampler_get_pending_start_beat": ([c.c_uint32], c.c_double),
     "sampler_is_pattern_running": ([c.c_uint32], c.c_bool),
+    "transport_get_beat_position": ([], c.c_double),
 }
 _bound = set()
 

@@ -506,6 +506,7 @@ uint32_t orc_engine_sampler_hit_log(void* e, uint32_t rack, uint32_t* frames, ui
   return n;
 }
 double orc_engine_transport_beat(void* e) { return e ? E->transport_beat : 0.0; }
+double orc_engine_transport_get_beat_position(void* e) { return e ? E->transport_beat : 0.0; }   // ffi.rs:7143-7150
 void orc_engine_capture_rack0(void* e, bool on) { if (e) { E->capture_rack0 = on; E->rack0_capture.clear(); } }
 uint32_t orc_engine_rack0_capture(void* e, float* out_interleaved, uint32_t cap_frames) {
   if (!e) return 0;

@@ -232,3 +232,38 @@ def test_loaded_slot_can_be_routed_and_triggered(e):             # :56 (up to th
     assert np.abs(e.render(256)).max() > 0.01
     assert e.sampler_clear_slot(rack, 0)
     assert not e.sampler_slot_is_loaded(rack, 0) and not e.sampler_trigger(rack, 0, 1.0)
+
+
+def test_pattern_start_is_bar_quantized_and_never_seeks_the_clip_transport(e):   # sampler_rack.rs:227-268
+    e.set_bpm(60.0)
+    rack = e.sampler_register()
+    assert e.mixer_route_source(e.sampler_get_source_id(rack), 3)
+    assert e.sampler_set_slot_buffer(rack, 0, np.full(4096, 0.5, np.float32), SR)
+    assert e.sampler_set_step(rack, 0, True, 0, 1.0)
+    assert e.sampler_get_step(rack, 0) == (True, 0, 1.0)
+    e.sequencer_start()
+    e.render(int(SR / 10.0))                                     # beat 0.1
+    assert e.sampler_start_pattern(rack, 2)                      # CLIP_QUANTIZE_BAR
+    assert e.sampler_get_pending_start_beat(rack) == 4.0 and not e.sampler_is_pattern_running(rack)
+    e.render(int((4.0 - 0.1) * SR))
+    assert not e.sampler_is_pattern_running(rack)
+    before = e.transport_get_beat_position()
+    e.render(1)
+    assert e.sampler_is_pattern_running(rack)
+    assert np.abs(e.render(64)).max() > 0.001                    # step zero fires on the boundary
+    assert e.transport_get_beat_position() > before
+    assert e.sampler_stop_pattern(rack) and not e.sampler_is_pattern_running(rack)
+    assert e.sampler_start_pattern(rack, 2) and e.sampler_get_pending_start_beat(rack) == 8.0
+    assert e.sampler_cancel_pattern_start(rack) and e.sampler_get_pending_start_beat(rack) == -1.0
+
+
+def test_the_products_host_schedule_fires_that_pattern_on_the_same_frame():
+    """The same scenario through gooey_b200_sampler_schedule (the host code engines_render runs): armed at beat 0.1 for beat 4, the first hit
+    lands on the first frame after (4 - 0.1) s of further rendering."""
+    import ctypes as c
+    from test_samples_cpu import product_schedule
+    steps = [(i == 0, 0, 1.0) for i in range(16)]
+    pre, wait = int(SR / 10.0), int((4.0 - 0.1) * SR)
+    _, beat = product_schedule(SR, 60.0, 0.5, steps, True, 0.0, -1.0, False, [pre])
+    hits, _ = product_schedule(SR, 60.0, 0.5, steps, True, beat, 4.0, False, [wait, 1, 64])
+    assert hits == [(wait, 0, 1.0)]

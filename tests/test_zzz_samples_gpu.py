@@ -337,6 +337,7 @@ def test_sampler_rack_pattern_armed_on_the_transport_bounced_and_stopped():
         d = e.render(4000)
         assert e.sampler_stop_pattern(0)
         f = e.render(3000)
+        info.append(e.transport_get_beat_position())                                              # every rendered frame since sequencer_start, add by add
         return np.concatenate([a, b, cc, d, f]), bounced, info
     (got, gb, ginfo), (want, wb, winfo) = both(lambda e: None, run)
     assert ginfo == winfo and winfo[1] is False and winfo[4] is True and winfo[5] == -1.0
